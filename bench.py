@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py -- PPO bin-packing env-steps/s on N B200s (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (libdfrl_b200.so)
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU trainer
+
+A "step" is one PPO iteration of the reference trainer main (ppo_training.cc:53-66): a rollout
+of T = 4 steps of every environment, then learner.step() (1 critic update + k = 4 policy updates
+on all N*T transitions), then forget().  Environments are sharded across ranks; parameters are
+replicated and each optimizer step all-reduces (SUM) the flat gradient.
+
+Prints ONE JSON line on rank 0 (see DESIGN.md "Measurement" for every field).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+T_STEPS = 4            # ppo_training.cc:31 steps_per_worker
+EPOCHS = 4             # policy_gradient.h:300
+POLICY_DIMS = [32, 64, 64, 8]   # C2/C4: "2-layer 64-hidden MLP", B = 8 bins
+VALUE_DIMS = [32, 64, 64, 1]
+REF_LR_P, REF_LR_V, REF_ROWS = 1e-4, 1e-5, 32  # ppo_training.cc:17,26; 8 workers x 4 steps
+
+
+def flops_per_env_step(pd=POLICY_DIMS, vd=VALUE_DIMS, T=T_STEPS, k=EPOCHS):
+    """Algorithmic FLOPs of the reference schedule per transition:
+    F_pi (1 + 3k (T+1)/T) + F_V 5 (T+1)/T with F = sum 2 in out."""
+    fp = sum(2 * a * b for a, b in zip(pd[:-1], pd[1:]))
+    fv = sum(2 * a * b for a, b in zip(vd[:-1], vd[1:]))
+    return fp * (1 + 3 * k * (T + 1) / T) + fv * 5 * (T + 1) / T
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.rows, self.stop, self.th = device, [], threading.Event(), None
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.device)], capture_output=True, text=True, timeout=5).stdout
+                for line in out.strip().splitlines():
+                    self.rows.append([c.strip() for c in line.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.th.join(timeout=6)
+
+    def summary(self):
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# ------------------------------------------------------------------ reference / CPU arm ------
+
+def cpu_reference_rate(n_envs, iters, threads, seed=1234):
+    """Times the reference's own PPO trainer (oracle/_ref, unmodified reference sources) with the
+    bench config's nets on the host cores: rollouts on `threads` worker threads exactly as
+    ppo_training.cc does, learner single-threaded (the reference has no parallel learner).
+    Falls back to the plain-C oracle port when the compiled reference is not present."""
+    from oracle import ref as R
+    if R.available():
+        pol = R.fc_net(POLICY_DIMS, R.SOFTMAX)
+        val = R.fc_net(VALUE_DIMS)
+        pp, vp = R.init_params(pol, seed), R.init_params(val, seed + 1)
+        rows = n_envs * T_STEPS
+        res = R.train(R.PPO, seed, n_envs, T_STEPS, iters, pol, pp, REF_LR_P * REF_ROWS / rows, val, vp,
+                      REF_LR_V * REF_ROWS / rows, record=False, threads=threads)
+        return res["env_steps"] / res["seconds"], res["seconds"], "reference", threads
+    from oracle import orc
+    ecfg = orc.env_cfg(8)
+    pnet, vnet = orc.fc_net(POLICY_DIMS, orc.SOFTMAX), orc.fc_net(VALUE_DIMS)
+    rng = np.random.default_rng(seed)
+    pp = (rng.standard_normal(pnet.param_count()) * 0.01).astype(np.float32)
+    vp = (rng.standard_normal(vnet.param_count()) * 0.01).astype(np.float32)
+    rows = n_envs * T_STEPS
+    lr = orc.Learner(orc.train_cfg(orc.PPO, T_STEPS, policy_lr=REF_LR_P * REF_ROWS / rows,
+                                   value_lr=REF_LR_V * REF_ROWS / rows), ecfg, pnet, pp, vnet, vp)
+    st = orc.env_reset_all(ecfg, n_envs, rng.integers(0, 2, n_envs).astype(np.uint8))
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        items = rng.integers(0, 2, (T_STEPS, n_envs)).astype(np.uint8)
+        ro = orc.rollout(ecfg, st, pnet, lr.pparams, T_STEPS, 0, items, u=rng.random((T_STEPS, n_envs)))
+        lr.learn(ro["state"], st, ro["action"], ro["done"], ro["probs"])
+    dt = time.perf_counter() - t0
+    return n_envs * T_STEPS * iters / dt, dt, "port", 1
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_envs = args.ref_envs
+    # warm-up then K steps; one step = one PPO iteration on the bounded sample of n_envs envs
+    cpu_reference_rate(n_envs, max(1, args.warmup), cores)
+    rate, secs, kind, used = cpu_reference_rate(n_envs, args.steps, cores)
+    line = {
+        "impl": "reference", "metric": "ppo_binpacking_env_steps_per_sec", "value": rate,
+        "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, n_envs_note=f"bounded CPU sample: {n_envs} envs x T={T_STEPS} per step"),
+        "cpu_baseline": {"value": rate, "unit": "env-steps/s", "cores": used, "kind": kind,
+                         "sample": f"{args.steps} PPO iterations of {n_envs} envs x {T_STEPS} steps, reference "
+                                   f"nets of the bench config, rollouts on {used} threads, learner 1 thread"},
+        "e2e": {"value": rate, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, n_envs_note=None):
+    return {
+        "workload": (f"PPO-clip bin packing (8 bins), {args.envs_per_gpu} envs/GPU x {args.gpus} GPU, "
+                     f"T={T_STEPS} steps/iter, k={EPOCHS} epochs, policy 32-64-64-8 softmax, value 32-64-64-1 "
+                     f"(BASELINE configs[3] 'PPO, 1M envs sharded over 8 B200' at 131072 envs/GPU; "
+                     f"same nets/schedule as configs[1])"),
+        "envs_per_gpu": args.envs_per_gpu, "global_envs": args.envs_per_gpu * args.gpus,
+        "steps_per_iter": T_STEPS, "epochs": EPOCHS, "optimizer": "sgd",
+        "lr": "reference 1e-4 / 1e-5 scaled by 32 / (global rows) because gradients are SUMS over rows",
+        "items": "synthetic Bernoulli(0.4) stream, Philox4x32-10 keyed (seed, global env, draw)",
+        "parallelism": f"dp{args.gpus} (envs sharded, flat-gradient all-reduce SUM)",
+        "l2": "activation working set exceeds the 126 MB L2 at 131072 envs/GPU; no flush needed",
+        **({"note": n_envs_note} if n_envs_note else {}),
+    }
+
+
+# ------------------------------------------------------------------ our arm ------------------
+
+def make_trainer(D, ctx, n_envs, env_offset, global_rows, seed=1234, fused=1):
+    policy = D.Model(ctx, D.fc_layers(POLICY_DIMS, D.SOFTMAX), 32)
+    value = D.Model(ctx, D.fc_layers(VALUE_DIMS), 32)
+    policy.init_parameters(seed)       # identical on every rank (replicated parameters)
+    value.init_parameters(seed + 1)
+    env = D.Environment(ctx, n_envs, seed=seed, env_offset=env_offset)
+    tr = D.Trainer(ctx, env, policy, value, algo=D.PPO, work=T_STEPS,
+                   policy_lr=REF_LR_P * REF_ROWS / global_rows, value_lr=REF_LR_V * REF_ROWS / global_rows,
+                   fused=fused)
+    return tr, env, policy, value
+
+
+def measure(D, ctx, dist, args, n_envs, world, rank, steps, warmup, sample_clocks):
+    """Returns dict(value, ms_per_step, e2e, launches, clocks) for n_envs envs per rank."""
+    global_rows = n_envs * world * T_STEPS
+    tr, env, policy, value = make_trainer(D, ctx, n_envs, rank * n_envs, global_rows, fused=args.fused)
+    lib = D._lib.lib
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        ctx.sync()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    # ---- device-resident throughput: `steps` iterations, no host round trips inside
+    tr.iterate(warmup)
+    barrier()
+    sampler = ClockSampler(ctx_device(ctx)) if sample_clocks else None
+    l0 = ctx.launches()
+    if sampler:
+        sampler.__enter__()
+    ctx.timer_start()
+    tr.iterate(steps)
+    ms = ctx.timer_stop()
+    barrier()
+    if sampler:
+        sampler.__exit__()
+    launches = ctx.launches() - l0
+    ms = max_over_ranks(ms)
+    value_rate = n_envs * world * T_STEPS * steps / (ms * 1e-3)
+
+    # ---- e2e through the public call with HOST buffers: per step the item stream of the step
+    # (uint8 [T][n], pinned) goes host->device inside rollout(), learn() runs, and the step's
+    # result (env-steps / episodes / reward counters) comes back device->host.
+    nbytes = T_STEPS * n_envs
+    hp = C.c_void_p()
+    D._lib.check(lib.dfrl_malloc_host(ctx.h, nbytes, C.byref(hp)))
+    host_items = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_uint8)), shape=(nbytes,))
+    rng = np.random.default_rng(rank)
+    streams = [(rng.random(nbytes) < 0.4).astype(np.uint8) for _ in range(4)]
+
+    def e2e_step(i):
+        host_items[:] = streams[i % 4]           # the producer filling the pinned tape
+        tr.rollout_raw(hp, None, None)           # H2D of the tape + rollout
+        tr.learn()
+        return tr.stats()                        # D2H of the step's result (synchronises)
+
+    for i in range(max(1, warmup)):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        s = e2e_step(i)
+    ctx.sync()
+    dt = time.perf_counter() - t0
+    dt = max_over_ranks(dt)
+    e2e_rate = n_envs * world * T_STEPS * steps / dt
+    D._lib.check(lib.dfrl_free_host(ctx.h, hp))
+    res = {"value": value_rate, "ms_per_step": ms / steps, "launches_per_step": launches / steps,
+           "e2e": {"value": e2e_rate, "unit": "env-steps/s", "h2d_bytes_per_step": nbytes * world,
+                   "d2h_bytes_per_step": 32 * world, "ms_per_step": 1e3 * dt / steps},
+           "clocks": sampler.summary() if sampler else None, "stats": s,
+           "objects": (tr, env, policy, value)}
+    return res
+
+
+def ctx_device(ctx):
+    return int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def kernel_profile(D, ctx, tr, iters):
+    """Per-kernel device time with CUDA events on the launching stream (separate pass: the event
+    pairs add launch overhead, so this never overlaps the throughput measurement)."""
+    lib = D._lib.lib
+    tr.iterate(1)
+    ctx.sync()
+    D._lib.check(lib.dfrl_profile_enable(ctx.h, 1))
+    tr.iterate(iters)
+    buf = C.create_string_buffer(1 << 16)
+    D._lib.check(lib.dfrl_profile_report(ctx.h, buf, len(buf)))
+    D._lib.check(lib.dfrl_profile_enable(ctx.h, 0))
+    prof = {}
+    for line in buf.value.decode().strip().splitlines():
+        name, n, ms = line.rsplit(" ", 2)
+        prof[name] = {"launches": int(n) / iters, "ms": float(ms) / iters}
+    return prof
+
+
+def roofline_from_profile(prof, n_envs, peaks):
+    """Roofline of the dominant kernel family.  The MLP GEMM kernels dominate; their algorithmic
+    FLOPs per iteration are flops_per_env_step() * n_envs * T (DESIGN.md section 'Kernels')."""
+    total = sum(v["ms"] for v in prof.values())
+    mlp = {k: v for k, v in prof.items() if "gemm" in k or "fused" in k or "mlp" in k}
+    mlp_ms = sum(v["ms"] for v in mlp.values())
+    top = max(prof.items(), key=lambda kv: kv[1]["ms"])
+    flops = flops_per_env_step() * n_envs * T_STEPS
+    achieved = flops / (mlp_ms * 1e-3) / 1e12 if mlp_ms > 0 else 0.0
+    peak = peaks["bf16_tflops_sustained"]
+    return {
+        "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+        "traffic": None,
+        "kernel": "MLP GEMM family (" + ", ".join(sorted(k.split("<")[0].strip("() ") for k in mlp)) + ")",
+        "kernel_ms_per_step": mlp_ms, "all_kernels_ms_per_step": total, "share_of_step": mlp_ms / total if total else None,
+        "top_kernel": top[0], "top_kernel_ms_per_step": top[1]["ms"],
+        "algorithmic_flops_per_step": flops,
+        "peak_source": f"MEASURED_PEAKS.json bf16 sustained ({peaks['source']}); the kernels are FP32 FFMA "
+                       f"(1e-4 parity), so frac is against the tensor pipe they do not yet use",
+        "per_kernel_ms": {k: round(v["ms"], 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
+    }
+
+
+def run_ours(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+    import dependence_free_rl_b200 as D
+    dist = None
+    nccl_id = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist_mod.init_process_group("gloo", rank=rank, world_size=world)
+        dist = dist_mod
+        obj = [D.Context.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0)
+        nccl_id = obj[0]
+    ctx = D.Context(local_rank, world, rank, nccl_id)
+    peaks = load_peaks()
+
+    main = measure(D, ctx, dist, args, args.envs_per_gpu, world, rank, args.steps, args.warmup, True)
+    tr = main["objects"][0]
+    prof = kernel_profile(D, ctx, tr, 3)
+    roof = roofline_from_profile(prof, args.envs_per_gpu, peaks)
+    for o in main["objects"]:
+        o.close()
+
+    extra = {}
+    if world == 1 and not args.no_c2:
+        # BASELINE configs[1] verbatim: PPO, 4096 parallel envs, 1 GPU (latency-bound size)
+        c2 = measure(D, ctx, None, args, 4096, 1, 0, max(args.steps, 50), max(args.warmup, 5), False)
+        for o in c2["objects"]:
+            o.close()
+        extra["c2_4096_envs"] = {"value": c2["value"], "unit": "env-steps/s", "ms_per_step": c2["ms_per_step"],
+                                 "e2e": c2["e2e"], "launches_per_step": c2["launches_per_step"]}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        rate, secs, kind, used = cpu_reference_rate(args.ref_envs, args.ref_iters, cores)
+        cpu = {"value": rate, "unit": "env-steps/s", "cores": used, "kind": kind,
+               "sample": f"{args.ref_iters} PPO iterations of {args.ref_envs} envs x {T_STEPS} steps ({secs:.1f} s), "
+                         f"same nets; rollouts on {used} threads, learner single-threaded as in the reference"}
+
+    if rank == 0:
+        clocks = main["clocks"] or {}
+        line = {
+            "metric": "ppo_binpacking_env_steps_per_sec", "value": main["value"], "unit": "env-steps/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": main["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(args),
+            "e2e": main["e2e"], "gpu_launches": int(round(main["launches_per_step"] * args.steps)),
+            "clocks": {"sm_mhz": clocks.get("sm_mhz"), "sm_max_mhz": clocks.get("sm_max_mhz"),
+                       "reasons": clocks.get("reasons", []), "samples": clocks.get("samples", 0)},
+            "roofline": roof, "cpu_baseline": cpu,
+            "fraction_of_roofline_note": "env/GAE/optimizer kernels: see profiles/ and DESIGN.md",
+            "train_stats": main["stats"], **extra,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs-per-gpu", type=int, default=131072)
+    ap.add_argument("--fused", type=int, default=1)
+    ap.add_argument("--ref-envs", type=int, default=256, help="bounded CPU sample: envs per PPO iteration")
+    ap.add_argument("--ref-iters", type=int, default=10)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-c2", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,467 @@
+// env.cu -- K1: the batched bin-packing environment (reference apps/bin_packing/bin_packing.h).
+//
+// N independent episodes live in struct-of-arrays planes  state int8 [2B+2][stride]:
+// plane 2b / 2b+1 = remaining (w, h) of bin b, planes 2B / 2B+1 = current item (w, h).
+// One launch steps every environment: environment::apply (bin_packing.h:53-64),
+// agent::game_over / get_reward (94-106), and the reset-on-done of agent::step
+// (xylo/rl.h:341-346) happen on the device; the next item comes from a per-env tape (parity
+// runs) or from Philox4x32-10 keyed by (seed, global env id, draw index).
+//
+// Roofline: HBM.  Algorithmic bytes per env-step = read + write of the 2B+2 state bytes, the
+// action byte and the done byte = 2(2B+2) + 2 (= 38 B at B = 8).
+// The vector kernel moves 4 environments per thread with 32-bit plane accesses so a warp
+// touches 128 contiguous bytes per plane.
+#include "common.cuh"
+#include "env_dev.cuh"
+
+namespace {
+
+// reset(id) for every env (bin_packing.h:67-70) + constructor draw (50-52).
+__global__ void env_reset_kernel(env_params p, int8_t *__restrict__ state,
+                                 uint32_t *__restrict__ draws, uint32_t *__restrict__ steps) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n)
+    return;
+  for (int b = 0; b < p.B; ++b) {
+    state[(size_t)(2 * b) * p.stride + i] = (int8_t)p.cap_w;
+    state[(size_t)(2 * b + 1) * p.stride + i] = (int8_t)p.cap_h;
+  }
+  int s1 = draw_shape1(p, i, 0);
+  state[(size_t)(2 * p.B) * p.stride + i] = (int8_t)(s1 ? p.iw0 : p.iw1);
+  state[(size_t)(2 * p.B + 1) * p.stride + i] = (int8_t)(s1 ? p.ih0 : p.ih1);
+  draws[i] = 1;
+  steps[i] = 0;
+}
+
+// Scalar step: any B. One env per thread, touches only the planes it needs.
+__global__ void env_step_scalar_kernel(env_params p, int8_t *__restrict__ state,
+                                       uint32_t *__restrict__ draws, uint32_t *__restrict__ steps,
+                                       const uint8_t *__restrict__ actions,
+                                       uint8_t *__restrict__ done_out,
+                                       int8_t *__restrict__ terminal) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n)
+    return;
+  const size_t S = p.stride;
+  int a = actions[i];
+  a = a < p.B ? a : p.B - 1;
+  int iw = state[(size_t)(2 * p.B) * S + i], ih = state[(size_t)(2 * p.B + 1) * S + i];
+  int bw = state[(size_t)(2 * a) * S + i] - iw;
+  int bh = state[(size_t)(2 * a + 1) * S + i] - ih;
+  bool over = bw < 0 || bh < 0;
+  if (terminal) {
+    for (int q = 0; q < 2 * p.B + 2; ++q)
+      terminal[(size_t)q * S + i] = state[(size_t)q * S + i];
+    terminal[(size_t)(2 * a) * S + i] = (int8_t)bw;
+    terminal[(size_t)(2 * a + 1) * S + i] = (int8_t)bh;
+  }
+  if (done_out)
+    done_out[i] = over;
+  uint32_t k = draws[i];
+  int s1 = draw_shape1(p, i, k);
+  draws[i] = k + 1;
+  steps[i] += 1;
+  if (over) {
+    for (int b = 0; b < p.B; ++b) {
+      state[(size_t)(2 * b) * S + i] = (int8_t)p.cap_w;
+      state[(size_t)(2 * b + 1) * S + i] = (int8_t)p.cap_h;
+    }
+  } else {
+    state[(size_t)(2 * a) * S + i] = (int8_t)bw;
+    state[(size_t)(2 * a + 1) * S + i] = (int8_t)bh;
+  }
+  state[(size_t)(2 * p.B) * S + i] = (int8_t)(s1 ? p.iw0 : p.iw1);
+  state[(size_t)(2 * p.B + 1) * S + i] = (int8_t)(s1 ? p.ih0 : p.ih1);
+}
+
+// Vector step: B compile-time, 4 envs per thread, every plane read and written as one 32-bit
+// word per thread (128 B per warp per plane, fully coalesced).
+template <int B>
+__global__ void __launch_bounds__(256)
+env_step_vec4_kernel(env_params p, int8_t *__restrict__ state, uint32_t *__restrict__ draws,
+                     uint32_t *__restrict__ steps, const uint8_t *__restrict__ actions,
+                     uint8_t *__restrict__ done_out, int8_t *__restrict__ terminal) {
+  constexpr int P = 2 * B + 2;
+  int g = blockIdx.x * blockDim.x + threadIdx.x;  // group of 4 envs
+  int i0 = g * 4;
+  if (i0 >= p.n)
+    return;
+  const size_t S = p.stride;
+  uint32_t w[P];
+#pragma unroll
+  for (int q = 0; q < P; ++q)
+    w[q] = *reinterpret_cast<const uint32_t *>(state + (size_t)q * S + i0);
+  uint32_t act4 = *reinterpret_cast<const uint32_t *>(actions + i0);  // actions padded to stride
+  uint32_t done4 = 0;
+  uint32_t t[P];
+#pragma unroll
+  for (int q = 0; q < P; ++q)
+    t[q] = w[q];
+  uint4 dr = make_uint4(0, 0, 0, 0), st = make_uint4(0, 0, 0, 0);
+  bool full = i0 + 3 < p.n;
+  if (full) {
+    dr = *reinterpret_cast<const uint4 *>(draws + i0);
+    st = *reinterpret_cast<const uint4 *>(steps + i0);
+  } else {
+    uint32_t *d = &dr.x, *s = &st.x;
+    for (int e = 0; e < 4 && i0 + e < p.n; ++e) {
+      d[e] = draws[i0 + e];
+      s[e] = steps[i0 + e];
+    }
+  }
+  uint32_t *drp = &dr.x, *stp = &st.x;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    if (i0 + e >= p.n)
+      break;
+    const int sh = 8 * e;
+    int a = (act4 >> sh) & 0xff;
+    a = a < B ? a : B - 1;
+    int iw = (int8_t)(w[2 * B] >> sh), ih = (int8_t)(w[2 * B + 1] >> sh);
+    int bw = 0, bh = 0;
+#pragma unroll
+    for (int b = 0; b < B; ++b) {
+      if (b == a) {
+        bw = (int8_t)(w[2 * b] >> sh);
+        bh = (int8_t)(w[2 * b + 1] >> sh);
+      }
+    }
+    bw -= iw;
+    bh -= ih;
+    bool over = bw < 0 || bh < 0;
+    done4 |= (over ? 1u : 0u) << sh;
+    int s1 = draw_shape1(p, i0 + e, drp[e]);
+    drp[e] += 1;
+    stp[e] += 1;
+    const uint32_t m = 0xffu << sh;
+#pragma unroll
+    for (int b = 0; b < B; ++b) {
+      if (b == a) {
+        t[2 * b] = (t[2 * b] & ~m) | (((uint32_t)bw & 0xff) << sh);
+        t[2 * b + 1] = (t[2 * b + 1] & ~m) | (((uint32_t)bh & 0xff) << sh);
+      }
+      uint32_t nw = over ? (uint32_t)p.cap_w : (b == a ? (uint32_t)bw & 0xff : (w[2 * b] >> sh) & 0xff);
+      uint32_t nh = over ? (uint32_t)p.cap_h : (b == a ? (uint32_t)bh & 0xff : (w[2 * b + 1] >> sh) & 0xff);
+      w[2 * b] = (w[2 * b] & ~m) | (nw << sh);
+      w[2 * b + 1] = (w[2 * b + 1] & ~m) | (nh << sh);
+    }
+    uint32_t niw = (uint32_t)(s1 ? p.iw0 : p.iw1) & 0xff, nih = (uint32_t)(s1 ? p.ih0 : p.ih1) & 0xff;
+    w[2 * B] = (w[2 * B] & ~m) | (niw << sh);
+    w[2 * B + 1] = (w[2 * B + 1] & ~m) | (nih << sh);
+  }
+#pragma unroll
+  for (int q = 0; q < P; ++q)
+    *reinterpret_cast<uint32_t *>(state + (size_t)q * S + i0) = w[q];
+  if (terminal) {
+#pragma unroll
+    for (int q = 0; q < P; ++q)
+      *reinterpret_cast<uint32_t *>(terminal + (size_t)q * S + i0) = t[q];
+  }
+  if (done_out)
+    *reinterpret_cast<uint32_t *>(done_out + i0) = done4;
+  if (full) {
+    *reinterpret_cast<uint4 *>(draws + i0) = dr;
+    *reinterpret_cast<uint4 *>(steps + i0) = st;
+  } else {
+    for (int e = 0; e < 4 && i0 + e < p.n; ++e) {
+      draws[i0 + e] = drp[e];
+      steps[i0 + e] = stp[e];
+    }
+  }
+}
+
+// observation::to_vector (bin_packing.h:31-40): one thread per (row, bin) writes one float4.
+__global__ void obs_encode_kernel(const int8_t *__restrict__ state, int rows, int stride, int B,
+                                  float cap_w, float cap_h, float4 *__restrict__ obs) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)rows * B)
+    return;
+  int r = (int)(t / B), b = (int)(t % B);
+  float4 o;
+  // true division, as the reference does (exact for any capacity, not only powers of two)
+  o.x = (float)state[(size_t)(2 * b) * stride + r] / cap_w;
+  o.y = (float)state[(size_t)(2 * b + 1) * stride + r] / cap_h;
+  o.z = (float)state[(size_t)(2 * B) * stride + r] / cap_w;
+  o.w = (float)state[(size_t)(2 * B + 1) * stride + r] / cap_h;
+  obs[t] = o;
+}
+
+// Heuristic policies. Scores follow firstfit_agent.cc:10-28, bestfit_agent.cc:10-30,
+// minwaste_agent.cc:10-39, then argmax (first max). Random: rl.h:305-315 (uniform weights
+// through discrete_distribution).
+__device__ __forceinline__ int heuristic_action(const env_params &p, const int8_t *state, int i,
+                                                int kind, uint32_t step) {
+  const size_t S = p.stride;
+  const int B = p.B;
+  int iw = state[(size_t)(2 * B) * S + i], ih = state[(size_t)(2 * B + 1) * S + i];
+  if (kind == DFRL_HEUR_RANDOM) {
+    philox4 r = philox4x32_10(p.seed, (uint64_t)(p.env_offset + i), step, DFRL_STREAM_HEUR);
+    double u = philox_u53(r.x, r.y);
+    // discrete_distribution over B equal float weights: normalise in double, lower_bound
+    float wf = (float)(1.0 / B);
+    double sum = 0.0;
+    for (int b = 0; b < B; ++b)
+      sum += (double)wf;
+    double c = 0.0;
+    for (int b = 0; b < B; ++b) {
+      c += (double)wf / sum;
+      double cb = (b == B - 1) ? 1.0 : c;
+      if (!(cb < u))
+        return b;
+    }
+    return B - 1;
+  }
+  int best = 0;
+  float best_score = 0.f;
+  bool found_first = false;
+  for (int b = 0; b < B; ++b) {
+    int bw = state[(size_t)(2 * b) * S + i], bh = state[(size_t)(2 * b + 1) * S + i];
+    bool fits = iw <= bw && ih <= bh;
+    float score;
+    if (kind == DFRL_HEUR_FIRSTFIT) {
+      score = (fits && !found_first) ? 1.f : 0.f;
+      found_first = found_first || fits;
+    } else if (kind == DFRL_HEUR_BESTFIT) {
+      score = fits ? (float)iw / (float)bw + (float)ih / (float)bh : -1.f;
+    } else {
+      if (!fits)
+        score = -1.f;
+      else {
+        float r1 = (float)(bw - iw), r2 = (float)(bh - ih);
+        score = ((r1 == (float)(p.cap_w / 2) && r2 == 0.f) || (r1 == 0.f && r2 == (float)(p.cap_h / 2))) ? 0.f : 1.f;
+      }
+    }
+    if (b == 0 || best_score < score) {
+      best = b;
+      best_score = score;
+    }
+  }
+  return best;
+}
+
+__global__ void heuristic_react_kernel(env_params p, const int8_t *__restrict__ state,
+                                       const uint32_t *__restrict__ steps, int kind,
+                                       uint8_t *__restrict__ actions) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n)
+    return;
+  actions[i] = (uint8_t)heuristic_action(p, state, i, kind, steps[i]);
+}
+
+// agent::play_one_episode x episodes for every env, entirely on the device (one thread owns one
+// env for the whole game; no host round trips).  Rewards are summed per block then atomically.
+__global__ void heuristic_play_kernel(env_params p, int8_t *__restrict__ state,
+                                      uint32_t *__restrict__ draws, uint32_t *__restrict__ steps,
+                                      int kind, int episodes, unsigned long long *__restrict__ acc) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long reward = 0, nsteps = 0;
+  if (i < p.n) {
+    const size_t S = p.stride;
+    const int B = p.B;
+    uint32_t k = draws[i], s = steps[i];
+    int ep = 0;
+    while (ep < episodes) {
+      int a = heuristic_action(p, state, i, kind, s);
+      int iw = state[(size_t)(2 * B) * S + i], ih = state[(size_t)(2 * B + 1) * S + i];
+      int bw = state[(size_t)(2 * a) * S + i] - iw, bh = state[(size_t)(2 * a + 1) * S + i] - ih;
+      bool over = bw < 0 || bh < 0;
+      ++nsteps;
+      ++s;
+      if (over) {
+        ++ep;
+        for (int b = 0; b < B; ++b) {
+          state[(size_t)(2 * b) * S + i] = (int8_t)p.cap_w;
+          state[(size_t)(2 * b + 1) * S + i] = (int8_t)p.cap_h;
+        }
+      } else {
+        ++reward;
+        state[(size_t)(2 * a) * S + i] = (int8_t)bw;
+        state[(size_t)(2 * a + 1) * S + i] = (int8_t)bh;
+      }
+      int s1 = draw_shape1(p, i, k++);
+      state[(size_t)(2 * B) * S + i] = (int8_t)(s1 ? p.iw0 : p.iw1);
+      state[(size_t)(2 * B + 1) * S + i] = (int8_t)(s1 ? p.ih0 : p.ih1);
+    }
+    draws[i] = k;
+    steps[i] = s;
+  }
+  // block reduction
+  for (int o = 16; o > 0; o >>= 1) {
+    reward += __shfl_down_sync(0xffffffffu, reward, o);
+    nsteps += __shfl_down_sync(0xffffffffu, nsteps, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&acc[0], reward);
+    atomicAdd(&acc[1], nsteps);
+  }
+}
+
+}  // namespace
+
+extern "C" void dfrl_env_config_default(dfrl_env_config *cfg) {
+  if (!cfg)
+    return;
+  cfg->n_envs = 0;
+  cfg->n_bins = 8;   // bin_packing.h:12
+  cfg->cap_w = 8;    // bin_packing.h:19
+  cfg->cap_h = 8;
+  cfg->item_w[0] = 4;  // shape1, bin_packing.h:73
+  cfg->item_h[0] = 2;
+  cfg->item_w[1] = 1;  // shape2, bin_packing.h:74
+  cfg->item_h[1] = 2;
+  cfg->p_shape1 = 0.4f;  // bin_packing.h:50
+  cfg->seed = 1234;
+  cfg->env_offset = 0;
+}
+
+extern "C" int dfrl_env_create(dfrl_ctx *ctx, const dfrl_env_config *cfg, dfrl_env **out) {
+  DFRL_CHECK(ctx && cfg && out, "null argument");
+  DFRL_CHECK(cfg->n_envs > 0, "n_envs must be positive");
+  DFRL_CHECK(cfg->n_bins >= 1 && cfg->n_bins <= 64, "n_bins %d out of range 1..64", cfg->n_bins);
+  DFRL_CHECK(cfg->cap_w > 0 && cfg->cap_w <= 127 && cfg->cap_h > 0 && cfg->cap_h <= 127,
+             "capacity must fit int8");
+  for (int k = 0; k < 2; ++k)
+    DFRL_CHECK(cfg->item_w[k] >= 0 && cfg->item_w[k] <= 127 && cfg->item_h[k] >= 0 &&
+                   cfg->item_h[k] <= 127, "item shape must fit int8");
+  dfrl_env *e = new dfrl_env();
+  e->ctx = ctx;
+  e->cfg = *cfg;
+  e->n = cfg->n_envs;
+  e->B = cfg->n_bins;
+  e->P = 2 * e->B + 2;
+  e->stride = (int)round_up((size_t)e->n, 16);
+  e->tape = nullptr;
+  e->tape_len = 0;
+  DFRL_CUDA(cudaMalloc(&e->state, (size_t)e->P * e->stride));
+  DFRL_CUDA(cudaMemsetAsync(e->state, 0, (size_t)e->P * e->stride, ctx->stream));
+  DFRL_CUDA(cudaMalloc(&e->draws, sizeof(uint32_t) * e->stride));
+  DFRL_CUDA(cudaMalloc(&e->steps, sizeof(uint32_t) * e->stride));
+  *out = e;
+  return dfrl_env_reset(e);
+}
+
+extern "C" int dfrl_env_destroy(dfrl_env *e) {
+  if (!e)
+    return DFRL_OK;
+  cudaStreamSynchronize(e->ctx->stream);
+  cudaFree(e->state);
+  cudaFree(e->draws);
+  cudaFree(e->steps);
+  if (e->tape)
+    cudaFree(e->tape);
+  delete e;
+  return DFRL_OK;
+}
+
+extern "C" int dfrl_env_reset(dfrl_env *e) {
+  DFRL_CHECK(e, "null env");
+  env_params p = make_params(e);
+  DFRL_LAUNCH(e->ctx, env_reset_kernel, ceil_div(e->n, 256), 256, 0, p, e->state, e->draws, e->steps);
+  return DFRL_OK;
+}
+
+extern "C" int dfrl_env_load_item_tape(dfrl_env *e, const uint8_t *tape_host, int len) {
+  DFRL_CHECK(e, "null env");
+  DFRL_CUDA(cudaStreamSynchronize(e->ctx->stream));
+  if (e->tape) {
+    DFRL_CUDA(cudaFree(e->tape));
+    e->tape = nullptr;
+    e->tape_len = 0;
+  }
+  if (tape_host && len > 0) {
+    DFRL_CUDA(cudaMalloc(&e->tape, (size_t)e->n * len));
+    DFRL_CUDA(cudaMemcpy(e->tape, tape_host, (size_t)e->n * len, cudaMemcpyHostToDevice));
+    e->tape_len = len;
+  }
+  return DFRL_OK;
+}
+
+int dfrl_env_step_internal(dfrl_env *e, const uint8_t *actions_dev, uint8_t *done_dev,
+                           int8_t *terminal_dev, bool actions_padded) {
+  env_params p = make_params(e);
+  bool vec = actions_padded && (((uintptr_t)actions_dev) % 4 == 0) &&
+             (!done_dev || ((uintptr_t)done_dev) % 4 == 0);
+  int groups = ceil_div(e->n, 4);
+  if (vec && e->B == 8) {
+    DFRL_LAUNCH(e->ctx, env_step_vec4_kernel<8>, ceil_div(groups, 256), 256, 0, p, e->state,
+                e->draws, e->steps, actions_dev, done_dev, terminal_dev);
+  } else if (vec && e->B == 16) {
+    DFRL_LAUNCH(e->ctx, env_step_vec4_kernel<16>, ceil_div(groups, 256), 256, 0, p, e->state,
+                e->draws, e->steps, actions_dev, done_dev, terminal_dev);
+  } else if (vec && e->B == 32) {
+    DFRL_LAUNCH(e->ctx, env_step_vec4_kernel<32>, ceil_div(groups, 256), 256, 0, p, e->state,
+                e->draws, e->steps, actions_dev, done_dev, terminal_dev);
+  } else {
+    DFRL_LAUNCH(e->ctx, env_step_scalar_kernel, ceil_div(e->n, 256), 256, 0, p, e->state, e->draws,
+                e->steps, actions_dev, done_dev, terminal_dev);
+  }
+  return DFRL_OK;
+}
+
+extern "C" int dfrl_env_step(dfrl_env *e, const uint8_t *actions_dev, uint8_t *done_dev,
+                             int8_t *terminal_state_dev) {
+  DFRL_CHECK(e && actions_dev, "null argument");
+  // Public buffers are [N] (done) / [2B+2][stride] (terminal). The vector kernel reads and
+  // writes whole 4-env words, which is safe when N is a multiple of 4.
+  return dfrl_env_step_internal(e, actions_dev, done_dev, terminal_state_dev, e->n % 4 == 0);
+}
+
+extern "C" int8_t *dfrl_env_state_dev(dfrl_env *e) { return e ? e->state : nullptr; }
+extern "C" int dfrl_env_state_stride(dfrl_env *e) { return e ? e->stride : 0; }
+
+extern "C" int dfrl_env_get_state(dfrl_env *e, int8_t *state_host) {
+  DFRL_CHECK(e && state_host, "null argument");
+  DFRL_CUDA(cudaMemcpy2DAsync(state_host, e->n, e->state, e->stride, e->n, e->P,
+                              cudaMemcpyDeviceToHost, e->ctx->stream));
+  DFRL_CUDA(cudaStreamSynchronize(e->ctx->stream));
+  return DFRL_OK;
+}
+extern "C" int dfrl_env_set_state(dfrl_env *e, const int8_t *state_host) {
+  DFRL_CHECK(e && state_host, "null argument");
+  DFRL_CUDA(cudaMemcpy2DAsync(e->state, e->stride, state_host, e->n, e->n, e->P,
+                              cudaMemcpyHostToDevice, e->ctx->stream));
+  DFRL_CUDA(cudaStreamSynchronize(e->ctx->stream));
+  return DFRL_OK;
+}
+
+extern "C" int dfrl_obs_encode(dfrl_ctx *ctx, const int8_t *state_dev, int rows, int stride,
+                               int n_bins, int cap_w, int cap_h, float *obs_dev) {
+  DFRL_CHECK(ctx && state_dev && obs_dev, "null argument");
+  DFRL_CHECK(rows >= 0 && stride >= rows && n_bins >= 1 && cap_w > 0 && cap_h > 0, "bad shape");
+  if (rows == 0)
+    return DFRL_OK;
+  long long total = (long long)rows * n_bins;
+  DFRL_LAUNCH(ctx, obs_encode_kernel, ceil_div(total, 256), 256, 0, state_dev, rows, stride, n_bins,
+              (float)cap_w, (float)cap_h, reinterpret_cast<float4 *>(obs_dev));
+  return DFRL_OK;
+}
+
+extern "C" int dfrl_heuristic_react(dfrl_env *e, int kind, uint8_t *actions_dev) {
+  DFRL_CHECK(e && actions_dev, "null argument");
+  DFRL_CHECK(kind >= 0 && kind <= 3, "unknown heuristic %d", kind);
+  env_params p = make_params(e);
+  DFRL_LAUNCH(e->ctx, heuristic_react_kernel, ceil_div(e->n, 256), 256, 0, p, e->state, e->steps,
+              kind, actions_dev);
+  return DFRL_OK;
+}
+
+extern "C" int dfrl_heuristic_play(dfrl_env *e, int kind, int episodes, double *total_reward,
+                                   long long *env_steps) {
+  DFRL_CHECK(e, "null env");
+  DFRL_CHECK(kind >= 0 && kind <= 3, "unknown heuristic %d", kind);
+  DFRL_CHECK(episodes > 0, "episodes must be positive");
+  env_params p = make_params(e);
+  void *acc;
+  DFRL_TRY(dfrl_scratch(e->ctx, 16, &acc));
+  DFRL_CUDA(cudaMemsetAsync(acc, 0, 16, e->ctx->stream));
+  DFRL_LAUNCH(e->ctx, heuristic_play_kernel, ceil_div(e->n, 128), 128, 0, p, e->state, e->draws,
+              e->steps, kind, episodes, (unsigned long long *)acc);
+  unsigned long long h[2];
+  DFRL_CUDA(cudaMemcpyAsync(h, acc, 16, cudaMemcpyDeviceToHost, e->ctx->stream));
+  DFRL_CUDA(cudaStreamSynchronize(e->ctx->stream));
+  if (total_reward)
+    *total_reward = (double)h[0];
+  if (env_steps)
+    *env_steps = (long long)h[1];
+  return DFRL_OK;
+}

@@ -1,0 +1,663 @@
+// trainer.cu -- the on-policy training loop of the reference trainer mains
+// (apps/bin_packing/{pg,ac,ppo,ppo2}_training.cc) on the device: rollout -> learn -> forget.
+//
+// replay_buffer / trajectory / transition (xylo/rl.h:111-296) become struct-of-arrays rollout
+// records, step-major:
+//   rec_state  int8  [L][2B+2][stride]   start state of every recorded step
+//   rec_action uint8 [L][N]              rec_done uint8 [L][N]  (reward = 1 - done)
+//   rec_probs  fp32  [L][N][B]           policy output at the start state (action.distrib)
+// A trajectory is a maximal run of steps of one env without a done flag; "forget()" is
+// implicit: the next rollout overwrites the records and an open trajectory continues from the
+// live env state (rl.h:274-291).
+//
+// End-state rows (policy_gradient.h:168-180): the reference appends one extra row per
+// trajectory holding its end state.  Here step (t, i) owns an end row iff done[t][i] or
+// t == L-1; its state is the overflowed terminal state (start state with bin[a] -= item) or
+// the live env state.  End rows only matter through V(end) in the critic target / advantage
+// (their own loss gradient is exactly zero: value target = own value, advantage = 0), except
+// for KL-PPO where beta (p - p_old) is non-zero on them and they join the policy pass.
+#include <math.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "device_fns.cuh"
+#include "env_dev.cuh"
+#include "trainer.h"
+
+namespace {
+
+// One agent::step for every active env: choose the action from the policy output, record it,
+// apply it, record done, reset / draw the next item (rl.h:325-349).
+//   mode: DFRL_ACT_SAMPLE (u from tape or Philox), DFRL_ACT_ARGMAX, DFRL_ACT_FORCED.
+//   episodic != 0 (REINFORCE / eval): env i is active while ep_done[i] < ep_target.
+__global__ void act_step_kernel(env_params p, int8_t *__restrict__ state,
+                                uint32_t *__restrict__ draws, uint32_t *__restrict__ steps,
+                                const float *__restrict__ probs, int mode,
+                                const uint8_t *__restrict__ forced, const double *__restrict__ u_tape,
+                                const uint8_t *__restrict__ item_tape_step,
+                                uint8_t *__restrict__ rec_action, uint8_t *__restrict__ rec_done,
+                                int episodic, int ep_target, int *__restrict__ ep_done,
+                                int *__restrict__ rec_len, unsigned long long *__restrict__ counters) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long c_steps = 0, c_eps = 0, c_reward = 0, c_active = 0;
+  if (i < p.n && (!episodic || ep_done[i] < ep_target)) {
+    const float *pr = probs + (size_t)i * p.B;
+    int a;
+    if (mode == DFRL_ACT_FORCED) {
+      a = forced[i];
+    } else if (mode == DFRL_ACT_ARGMAX) {
+      a = argmax_first(pr, p.B);
+    } else {
+      double u;
+      if (u_tape)
+        u = u_tape[i];
+      else {
+        philox4 r = philox4x32_10(p.seed, (uint64_t)(p.env_offset + i), steps[i], DFRL_STREAM_ACTION);
+        u = philox_u53(r.x, r.y);
+      }
+      a = discrete_sample(pr, p.B, u);
+    }
+    a = a < p.B ? a : p.B - 1;
+    if (rec_action)
+      rec_action[i] = (uint8_t)a;
+    uint32_t k = draws[i];
+    env_params q = p;
+    if (item_tape_step) {
+      // per-step host tape [n]: the item drawn after this step (draw_shape1 reads tape[i*1 + 0])
+      q.tape = item_tape_step;
+      q.tape_len = 1;
+      k = 0;
+    }
+    bool over = env_apply_global(q, state, i, a, k);
+    draws[i] += 1;
+    steps[i] += 1;
+    if (rec_done)
+      rec_done[i] = over;
+    c_steps = 1;
+    c_reward = over ? 0 : 1;
+    if (over)
+      c_eps = 1;
+    if (episodic) {
+      if (over)
+        ep_done[i] += 1;
+      if (rec_len)
+        rec_len[i] += 1;
+      c_active = (ep_done[i] < ep_target) ? 1 : 0;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    c_steps += __shfl_down_sync(0xffffffffu, c_steps, o);
+    c_eps += __shfl_down_sync(0xffffffffu, c_eps, o);
+    c_reward += __shfl_down_sync(0xffffffffu, c_reward, o);
+    c_active += __shfl_down_sync(0xffffffffu, c_active, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (c_steps) atomicAdd(&counters[0], c_steps);
+    if (c_eps) atomicAdd(&counters[1], c_eps);
+    if (c_reward) atomicAdd(&counters[2], c_reward);
+    if (c_active) atomicAdd(&counters[3], c_active);
+  }
+}
+
+// Observations of the end rows: terminal state (done) / live state (last step) / next start
+// state (otherwise; unused by the learner but finite).
+__global__ void end_obs_kernel(const int8_t *__restrict__ rec_state, const int8_t *__restrict__ live,
+                               const uint8_t *__restrict__ rec_action,
+                               const uint8_t *__restrict__ rec_done, int n, int stride, int B, int L,
+                               float cap_w, float cap_h, float4 *__restrict__ obs_end) {
+  long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= (long long)L * n * B)
+    return;
+  int b = (int)(tid % B);
+  long long row = tid / B;
+  int i = (int)(row % n), t = (int)(row / n);
+  const int P = 2 * B + 2;
+  int d = rec_done[row];
+  const int8_t *src;
+  if (d)
+    src = rec_state + (size_t)t * P * stride;
+  else if (t == L - 1)
+    src = live;
+  else
+    src = rec_state + (size_t)(t + 1) * P * stride;
+  int bw = src[(size_t)(2 * b) * stride + i], bh = src[(size_t)(2 * b + 1) * stride + i];
+  int iw = src[(size_t)(2 * B) * stride + i], ih = src[(size_t)(2 * B + 1) * stride + i];
+  if (d && b == rec_action[row]) {  // overflowed bin, item kept (bin_packing.h:54-61)
+    bw -= iw;
+    bh -= ih;
+  }
+  obs_end[tid] = make_float4((float)bw / cap_w, (float)bh / cap_h, (float)iw / cap_w, (float)ih / cap_h);
+}
+
+// Loss gradient at the policy output for the start rows (and, for KL, the end rows).
+// rows = L*n start rows followed (KL only) by L*n end-row slots.
+__global__ void policy_loss_kernel(int kind, const float *__restrict__ probs,
+                                   const uint8_t *__restrict__ rec_action,
+                                   const uint8_t *__restrict__ rec_done,
+                                   const int *__restrict__ rec_len, const float *__restrict__ adv,
+                                   const float *__restrict__ p_old, float beta, int n, int L, int B,
+                                   int with_end_rows, float *__restrict__ out,
+                                   double *__restrict__ kl_acc) {
+  long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long LN = (long long)L * n;
+  long long total = with_end_rows ? 2 * LN : LN;
+  double kl = 0.0, cnt = 0.0;
+  if (r < total) {
+    bool is_end = r >= LN;
+    long long k = is_end ? r - LN : r;
+    int t = (int)(k / n), i = (int)(k % n);
+    const float *p = probs + (size_t)r * B;
+    float *o = out + (size_t)r * B;
+    int a = rec_action[k];
+    bool valid = !rec_len || t < rec_len[i];
+    if (is_end)
+      valid = rec_done[k] || t == L - 1;
+    float A = (is_end || !valid) ? 0.f : adv[k];
+    if (!valid) {
+      for (int c = 0; c < B; ++c)
+        o[c] = 0.f;
+    } else if (kind == DFRL_LOSS_CLIPPED) {
+      float g = clipped_grad(p[a], p_old[(size_t)k * B + a], A);
+      for (int c = 0; c < B; ++c)
+        o[c] = (c == a) ? g : 0.f;
+    } else {
+      const float *po = p_old + (size_t)k * B;
+      for (int c = 0; c < B; ++c) {
+        float v = p[c] * A - (c == a ? A : 0.f);
+        if (kind == DFRL_LOSS_KL) {
+          v += (p[c] - po[c]) * beta;
+          kl += (double)(po[c] * logf(po[c] / p[c]));  // D_KL(p_old || p), policy_gradient.h:41-45
+        }
+        o[c] = v;
+      }
+      cnt = 1.0;
+    }
+  }
+  if (kl_acc) {
+    for (int o2 = 16; o2 > 0; o2 >>= 1) {
+      kl += __shfl_down_sync(0xffffffffu, kl, o2);
+      cnt += __shfl_down_sync(0xffffffffu, cnt, o2);
+    }
+    if ((threadIdx.x & 31) == 0 && cnt > 0.0) {
+      atomicAdd(&kl_acc[0], kl);
+      atomicAdd(&kl_acc[1], cnt);
+    }
+  }
+}
+
+// square_loss_grad (nn.h:548-550) for the critic on start rows; rows past rec_len get 0.
+__global__ void value_loss_kernel(const float *__restrict__ v, const float *__restrict__ tgt,
+                                  long long rows, float *__restrict__ out) {
+  long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < rows)
+    out[r] = v[r] - tgt[r];
+}
+
+__global__ void reinforce_adv_kernel(const float *__restrict__ g, const int *__restrict__ len, int n,
+                                     int L, float baseline, float *__restrict__ adv) {
+  long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= (long long)n * L)
+    return;
+  int t = (int)(k / n), i = (int)(k % n);
+  adv[k] = (t < len[i]) ? g[k] - baseline : 0.f;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+extern "C" void dfrl_trainer_config_default(dfrl_trainer_config *c) {
+  if (!c)
+    return;
+  memset(c, 0, sizeof(*c));
+  c->algo = DFRL_ALGO_PPO;
+  c->work = 4;            // ppo_training.cc:31
+  c->gamma = 0.99f;       // ppo_training.cc:46
+  c->lambda = 0.95f;      // policy_gradient.h:286
+  c->epochs = 4;          // policy_gradient.h:300
+  c->kl_target = 1e-9f;   // policy_gradient.h:334
+  c->kl_beta0 = 1.0f;     // policy_gradient.h:333
+  c->policy_opt = DFRL_OPT_SGD;
+  c->value_opt = DFRL_OPT_SGD;
+  c->policy_lr = 1e-4f;   // ppo_training.cc:17
+  c->value_lr = 1e-5f;    // ppo_training.cc:26
+  c->adam_beta1 = 0.9f;   // nn.h:661
+  c->adam_beta2 = 0.999f;
+  c->action_mode = DFRL_ACT_SAMPLE;
+  c->fused = 1;
+}
+
+static size_t opt_state_floats(int kind, int n) {
+  return kind == DFRL_OPT_SGD ? 0 : kind == DFRL_OPT_MOMENTUM ? (size_t)n : (size_t)2 * n;
+}
+
+extern "C" int dfrl_trainer_create(dfrl_ctx *ctx, const dfrl_trainer_config *cfg, dfrl_env *env,
+                                   dfrl_mlp *policy, dfrl_mlp *value, dfrl_trainer **out) {
+  DFRL_CHECK(ctx && cfg && env && policy && out, "null argument");
+  DFRL_CHECK(cfg->algo >= 0 && cfg->algo <= 3, "unknown algo %d", cfg->algo);
+  DFRL_CHECK(cfg->work > 0, "work must be positive");
+  DFRL_CHECK(cfg->algo == DFRL_ALGO_REINFORCE || value, "value model required");
+  DFRL_CHECK(policy->input_cols == 4 * env->B, "policy input width %d != 4 * bins", policy->input_cols);
+  DFRL_CHECK(policy->output_cols == env->B, "policy output width %d != bins %d (action.cardinality)",
+             policy->output_cols, env->B);
+  if (value) {
+    DFRL_CHECK(value->input_cols == 4 * env->B, "value input width mismatch");
+    DFRL_CHECK(value->output_cols == 1, "value model must output one column");
+  }
+  dfrl_trainer *t = new dfrl_trainer();
+  t->ctx = ctx;
+  t->cfg = *cfg;
+  t->env = env;
+  t->policy = policy;
+  t->value = cfg->algo == DFRL_ALGO_REINFORCE ? nullptr : value;
+  t->n = env->n;
+  t->B = env->B;
+  t->P = env->P;
+  t->stride = env->stride;
+  t->O = 4 * env->B;
+  if (cfg->algo == DFRL_ALGO_REINFORCE) {
+    int me = env_max_episode_len(env->cfg);
+    DFRL_CHECK(me > 0, "episodes never end with zero-sized items");
+    t->L = cfg->work * me;
+  } else {
+    t->L = cfg->work;
+  }
+  const size_t LN = (size_t)t->L * t->n;
+  const int Pp = policy->n_params, Pv = t->value ? t->value->n_params : 0;
+  DFRL_CUDA(cudaMalloc(&t->rec_state, (size_t)t->L * t->P * t->stride));
+  DFRL_CUDA(cudaMemsetAsync(t->rec_state, 0, (size_t)t->L * t->P * t->stride, ctx->stream));
+  DFRL_CUDA(cudaMalloc(&t->rec_action, LN));
+  DFRL_CUDA(cudaMemsetAsync(t->rec_action, 0, LN, ctx->stream));
+  DFRL_CUDA(cudaMalloc(&t->rec_done, LN));
+  DFRL_CUDA(cudaMemsetAsync(t->rec_done, 0, LN, ctx->stream));
+  DFRL_CUDA(cudaMalloc(&t->rec_probs, sizeof(float) * LN * t->B));
+  DFRL_CUDA(cudaMemsetAsync(t->rec_probs, 0, sizeof(float) * LN * t->B, ctx->stream));
+  DFRL_CUDA(cudaMalloc(&t->rec_len, sizeof(int) * t->n));
+  DFRL_CUDA(cudaMalloc(&t->ep_done, sizeof(int) * t->n));
+  DFRL_CUDA(cudaMalloc(&t->obs, sizeof(float) * 2 * LN * t->O));
+  DFRL_CUDA(cudaMalloc(&t->v_start, sizeof(float) * LN));
+  DFRL_CUDA(cudaMalloc(&t->v_end, sizeof(float) * LN));
+  DFRL_CUDA(cudaMalloc(&t->targets, sizeof(float) * LN));
+  DFRL_CUDA(cudaMalloc(&t->adv, sizeof(float) * LN));
+  DFRL_CUDA(cudaMemsetAsync(t->adv, 0, sizeof(float) * LN, ctx->stream));
+  DFRL_CUDA(cudaMemsetAsync(t->targets, 0, sizeof(float) * LN, ctx->stream));
+  DFRL_CUDA(cudaMalloc(&t->dyv, sizeof(float) * LN));
+  DFRL_CUDA(cudaMalloc(&t->dprobs, sizeof(float) * 2 * LN * t->B));
+  int epochs = (cfg->algo == DFRL_ALGO_PPO || cfg->algo == DFRL_ALGO_KL_PPO) ? cfg->epochs : 1;
+  t->epochs = epochs;
+  DFRL_CUDA(cudaMalloc(&t->pgrad_log, sizeof(float) * (size_t)epochs * Pp));
+  DFRL_CUDA(cudaMemsetAsync(t->pgrad_log, 0, sizeof(float) * (size_t)epochs * Pp, ctx->stream));
+  DFRL_CUDA(cudaMalloc(&t->vgrad, sizeof(float) * (Pv ? Pv : 1)));
+  DFRL_CUDA(cudaMemsetAsync(t->vgrad, 0, sizeof(float) * (Pv ? Pv : 1), ctx->stream));
+  size_t ps = opt_state_floats(cfg->policy_opt, Pp), vs = opt_state_floats(cfg->value_opt, Pv);
+  DFRL_CUDA(cudaMalloc(&t->pstate, sizeof(float) * (ps ? ps : 1)));
+  DFRL_CUDA(cudaMemsetAsync(t->pstate, 0, sizeof(float) * (ps ? ps : 1), ctx->stream));
+  DFRL_CUDA(cudaMalloc(&t->vstate, sizeof(float) * (vs ? vs : 1)));
+  DFRL_CUDA(cudaMemsetAsync(t->vstate, 0, sizeof(float) * (vs ? vs : 1), ctx->stream));
+  DFRL_CUDA(cudaMalloc(&t->counters, sizeof(unsigned long long) * 8));
+  DFRL_CUDA(cudaMemsetAsync(t->counters, 0, sizeof(unsigned long long) * 8, ctx->stream));
+  DFRL_CUDA(cudaMalloc(&t->acc, sizeof(double) * 4));
+  DFRL_CUDA(cudaMalloc(&t->tape_items, LN));
+  DFRL_CUDA(cudaMalloc(&t->tape_actions, LN));
+  DFRL_CUDA(cudaMalloc(&t->tape_u, sizeof(double) * LN));
+  DFRL_CUDA(cudaMallocHost(&t->pin, 64));
+  t->p_adam_t = 1.f;  // nn.h:693
+  t->v_adam_t = 1.f;
+  t->kl_beta = cfg->kl_beta0;
+  t->last_rollout_steps = 0;
+  t->last_rollout_reward = 0;
+  t->fused_impl = nullptr;
+  *out = t;
+  if (cfg->fused)
+    dfrl_fused_try_attach(t);  // silently stays layered when the nets do not qualify
+  return DFRL_OK;
+}
+
+extern "C" int dfrl_trainer_destroy(dfrl_trainer *t) {
+  if (!t)
+    return DFRL_OK;
+  cudaStreamSynchronize(t->ctx->stream);
+  dfrl_fused_detach(t);
+  void *ptrs[] = {t->rec_state, t->rec_action, t->rec_done, t->rec_probs, t->rec_len, t->ep_done,
+                  t->obs, t->v_start, t->v_end, t->targets, t->adv, t->dyv, t->dprobs, t->pgrad_log,
+                  t->vgrad, t->pstate, t->vstate, t->counters, t->acc, t->tape_items,
+                  t->tape_actions, t->tape_u};
+  for (void *p : ptrs)
+    if (p)
+      cudaFree(p);
+  if (t->pin)
+    cudaFreeHost(t->pin);
+  delete t;
+  return DFRL_OK;
+}
+
+// ------------------------------------------------------------------ rollout -----------------
+static int rollout_step(dfrl_trainer *t, int slot, int mode, const uint8_t *forced_step,
+                        const double *u_step, const uint8_t *item_step, int episodic, int ep_target,
+                        bool record) {
+  dfrl_ctx *ctx = t->ctx;
+  dfrl_env *e = t->env;
+  const size_t n = t->n;
+  float *obs_t = t->obs + (size_t)slot * n * t->O;
+  float *probs_t = t->rec_probs + (size_t)slot * n * t->B;
+  if (record)
+    DFRL_CUDA(cudaMemcpyAsync(t->rec_state + (size_t)slot * t->P * t->stride, e->state,
+                              (size_t)t->P * t->stride, cudaMemcpyDeviceToDevice, ctx->stream));
+  DFRL_TRY(dfrl_obs_encode(ctx, e->state, t->n, t->stride, t->B, e->cfg.cap_w, e->cfg.cap_h, obs_t));
+  DFRL_TRY(dfrl_mlp_eval(t->policy, obs_t, t->n, probs_t));
+  env_params p = make_params(e);
+  DFRL_LAUNCH(ctx, act_step_kernel, ceil_div(t->n, 128), 128, 0, p, e->state, e->draws, e->steps,
+              probs_t, mode, forced_step, u_step, item_step,
+              record ? t->rec_action + (size_t)slot * n : nullptr,
+              record ? t->rec_done + (size_t)slot * n : nullptr, episodic, ep_target, t->ep_done,
+              record ? t->rec_len : nullptr, t->counters);
+  return DFRL_OK;
+}
+
+static int read_counters(dfrl_trainer *t, unsigned long long *h4) {
+  DFRL_CUDA(cudaMemcpyAsync(t->pin, t->counters, 32, cudaMemcpyDeviceToHost, t->ctx->stream));
+  DFRL_CUDA(cudaStreamSynchronize(t->ctx->stream));
+  memcpy(h4, t->pin, 32);
+  return DFRL_OK;
+}
+
+static int rollout_layered(dfrl_trainer *t, const uint8_t *items_dev, const uint8_t *actions_dev,
+                           const double *u_dev) {
+  dfrl_ctx *ctx = t->ctx;
+  const size_t n = t->n;
+  int mode = t->cfg.action_mode;
+  if (t->cfg.algo == DFRL_ALGO_REINFORCE) {
+    // agent::play_one_episode x work for every env (pg_training.cc:51-55)
+    DFRL_CUDA(cudaMemsetAsync(t->ep_done, 0, sizeof(int) * n, ctx->stream));
+    DFRL_CUDA(cudaMemsetAsync(t->rec_len, 0, sizeof(int) * n, ctx->stream));
+    for (int s = 0; s < t->L; ++s) {
+      DFRL_CUDA(cudaMemsetAsync(t->counters + 3, 0, sizeof(unsigned long long), ctx->stream));
+      DFRL_TRY(rollout_step(t, s, mode, actions_dev ? actions_dev + s * n : nullptr,
+                            u_dev ? u_dev + s * n : nullptr, items_dev ? items_dev + s * n : nullptr,
+                            1, t->cfg.work, true));
+      if ((s & 3) == 3 || s == t->L - 1) {
+        unsigned long long h[4];
+        DFRL_TRY(read_counters(t, h));
+        if (h[3] == 0)
+          break;
+      }
+    }
+  } else {
+    for (int s = 0; s < t->L; ++s)
+      DFRL_TRY(rollout_step(t, s, mode, actions_dev ? actions_dev + s * n : nullptr,
+                            u_dev ? u_dev + s * n : nullptr, items_dev ? items_dev + s * n : nullptr,
+                            0, 0, true));
+  }
+  return DFRL_OK;
+}
+
+extern "C" int dfrl_trainer_rollout(dfrl_trainer *t, const uint8_t *items_host,
+                                    const uint8_t *actions_host, const double *u_host) {
+  DFRL_CHECK(t, "null trainer");
+  dfrl_ctx *ctx = t->ctx;
+  const size_t LN = (size_t)t->L * t->n;
+  DFRL_CHECK(t->cfg.action_mode != DFRL_ACT_FORCED || actions_host, "forced mode needs an action tape");
+  const uint8_t *items_dev = nullptr, *actions_dev = nullptr;
+  const double *u_dev = nullptr;
+  if (items_host) {
+    DFRL_CUDA(cudaMemcpyAsync(t->tape_items, items_host, LN, cudaMemcpyHostToDevice, ctx->stream));
+    items_dev = t->tape_items;
+  }
+  if (actions_host) {
+    DFRL_CUDA(cudaMemcpyAsync(t->tape_actions, actions_host, LN, cudaMemcpyHostToDevice, ctx->stream));
+    actions_dev = t->tape_actions;
+  }
+  if (u_host) {
+    DFRL_CUDA(cudaMemcpyAsync(t->tape_u, u_host, sizeof(double) * LN, cudaMemcpyHostToDevice, ctx->stream));
+    u_dev = t->tape_u;
+  }
+  if (t->fused_impl)
+    DFRL_TRY(dfrl_fused_rollout(t, items_dev, actions_dev, u_dev));
+  else
+    DFRL_TRY(rollout_layered(t, items_dev, actions_dev, u_dev));
+  return DFRL_OK;
+}
+
+// ------------------------------------------------------------------ learn -------------------
+static int apply_opt(dfrl_trainer *t, dfrl_mlp *m, int kind, float *grad, float *state, float lr,
+                     float wd, float *adam_t) {
+  DFRL_TRY(dfrl_allreduce_sum(t->ctx, grad, (size_t)m->n_params));  // K8: SUM over ranks
+  DFRL_TRY(dfrl_opt_step(t->ctx, kind, m->params, grad, state, m->n_params, lr, wd,
+                         t->cfg.adam_beta1, t->cfg.adam_beta2, *adam_t));
+  if (kind == DFRL_OPT_ADAM)
+    *adam_t += 1.f;  // nn.h:686
+  m->wt_dirty = true;
+  return DFRL_OK;
+}
+
+static int learn_layered(dfrl_trainer *t) {
+  dfrl_ctx *ctx = t->ctx;
+  dfrl_env *e = t->env;
+  const int n = t->n, L = t->L, B = t->B;
+  const long long LN = (long long)L * n;
+  float *obs_start = t->obs, *obs_end = t->obs + (size_t)LN * t->O;
+  const dfrl_trainer_config &c = t->cfg;
+
+  if (c.algo == DFRL_ALGO_REINFORCE) {
+    // policy_gradient_learner::learn (policy_gradient.h:95-123)
+    float *g = t->targets;
+    DFRL_CUDA(cudaMemsetAsync(t->acc, 0, sizeof(double) * 2, ctx->stream));
+    DFRL_TRY(dfrl_returns(ctx, t->rec_done, t->rec_len, n, L, c.gamma, g, t->acc));
+    DFRL_TRY(dfrl_allreduce_sum_f64(ctx, t->acc, 2));
+    double h[2];
+    DFRL_CUDA(cudaMemcpyAsync(t->pin, t->acc, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    DFRL_CUDA(cudaStreamSynchronize(ctx->stream));
+    memcpy(h, t->pin, 16);
+    float baseline = (float)h[0] / (float)h[1];  // total_reward / experience.size() (145)
+    DFRL_LAUNCH(ctx, reinforce_adv_kernel, ceil_div(LN, 256), 256, 0, g, t->rec_len, n, L, baseline, t->adv);
+    float *probs = nullptr;
+    DFRL_TRY(dfrl_mlp_forward_keep(t->policy, obs_start, (int)LN, &probs));
+    DFRL_LAUNCH(ctx, policy_loss_kernel, ceil_div(LN, 128), 128, 0, DFRL_LOSS_SOFTMAX_LOG, probs,
+                t->rec_action, t->rec_done, t->rec_len, t->adv, t->rec_probs, 0.f, n, L, B, 0,
+                t->dprobs, (double *)nullptr);
+    DFRL_TRY(dfrl_mlp_backward(t->policy, t->dprobs, t->pgrad_log));
+    DFRL_TRY(apply_opt(t, t->policy, c.policy_opt, t->pgrad_log, t->pstate, c.policy_lr, c.policy_wd, &t->p_adam_t));
+    return DFRL_OK;
+  }
+
+  // actor_critic_learner::learn (policy_gradient.h:159-185)
+  DFRL_LAUNCH(ctx, end_obs_kernel, ceil_div(LN * B, 256), 256, 0, t->rec_state, e->state,
+              t->rec_action, t->rec_done, n, t->stride, B, L, (float)e->cfg.cap_w, (float)e->cfg.cap_h,
+              reinterpret_cast<float4 *>(obs_end));
+  // update_value_model (196-218): V on every row with the current critic, targets, one step
+  DFRL_TRY(dfrl_mlp_eval(t->value, obs_end, (int)LN, t->v_end));
+  float *v_now = nullptr;
+  DFRL_TRY(dfrl_mlp_forward_keep(t->value, obs_start, (int)LN, &v_now));
+  DFRL_TRY(dfrl_gae(ctx, t->rec_done, v_now, t->v_end, n, L, c.gamma, c.lambda, t->targets, nullptr));
+  DFRL_LAUNCH(ctx, value_loss_kernel, ceil_div(LN, 256), 256, 0, v_now, t->targets, LN, t->dyv);
+  DFRL_TRY(dfrl_mlp_backward(t->value, t->dyv, t->vgrad));
+  DFRL_TRY(apply_opt(t, t->value, c.value_opt, t->vgrad, t->vstate, c.value_lr, c.value_wd, &t->v_adam_t));
+  // calculate_advantage (220-281) with the UPDATED critic
+  DFRL_TRY(dfrl_mlp_eval(t->value, obs_end, (int)LN, t->v_end));
+  DFRL_TRY(dfrl_mlp_eval(t->value, obs_start, (int)LN, t->v_start));
+  DFRL_TRY(dfrl_gae(ctx, t->rec_done, t->v_start, t->v_end, n, L, c.gamma, c.lambda, nullptr, t->adv));
+  // optimize_action (187-194 / 297-307 / 318-330)
+  int kind = c.algo == DFRL_ALGO_ACTOR_CRITIC ? DFRL_LOSS_SOFTMAX_LOG
+             : c.algo == DFRL_ALGO_PPO        ? DFRL_LOSS_CLIPPED
+                                              : DFRL_LOSS_KL;
+  const int with_end = kind == DFRL_LOSS_KL ? 1 : 0;
+  const long long rows = with_end ? 2 * LN : LN;
+  for (int ep = 0; ep < t->epochs; ++ep) {
+    float *probs = nullptr;
+    DFRL_TRY(dfrl_mlp_forward_keep(t->policy, t->obs, (int)rows, &probs));
+    if (with_end)
+      DFRL_CUDA(cudaMemsetAsync(t->acc, 0, sizeof(double) * 2, ctx->stream));
+    DFRL_LAUNCH(ctx, policy_loss_kernel, ceil_div(rows, 128), 128, 0, kind, probs, t->rec_action,
+                t->rec_done, (const int *)nullptr, t->adv, t->rec_probs, t->kl_beta, n, L, B, with_end,
+                t->dprobs, with_end ? t->acc : (double *)nullptr);
+    float *grad = t->pgrad_log + (size_t)ep * t->policy->n_params;
+    DFRL_TRY(dfrl_mlp_backward(t->policy, t->dprobs, grad));
+    if (with_end) {
+      // adaptive beta (policy_gradient.h:68-83): mean KL over ALL rows of all ranks
+      DFRL_TRY(dfrl_allreduce_sum_f64(ctx, t->acc, 2));
+      double h[2];
+      DFRL_CUDA(cudaMemcpyAsync(t->pin, t->acc, 16, cudaMemcpyDeviceToHost, ctx->stream));
+      DFRL_CUDA(cudaStreamSynchronize(ctx->stream));
+      memcpy(h, t->pin, 16);
+      float d_average = (float)(h[0] / h[1]);
+      if (fabsf(d_average) < c.kl_target / 1.5f)
+        t->kl_beta /= 2;
+      else if (fabsf(d_average) > c.kl_target * 1.5f)
+        t->kl_beta *= 2;
+      t->kl_beta = fmaxf(t->kl_beta, 1e-25f);
+      t->kl_beta = fminf(t->kl_beta, 0.1f);
+    }
+    DFRL_TRY(apply_opt(t, t->policy, c.policy_opt, grad, t->pstate, c.policy_lr, c.policy_wd, &t->p_adam_t));
+  }
+  return DFRL_OK;
+}
+
+extern "C" int dfrl_trainer_learn(dfrl_trainer *t) {
+  DFRL_CHECK(t, "null trainer");
+  if (t->fused_impl)
+    return dfrl_fused_learn(t);
+  return learn_layered(t);
+}
+
+extern "C" int dfrl_trainer_iterate(dfrl_trainer *t, int iters) {
+  DFRL_CHECK(t, "null trainer");
+  DFRL_CHECK(t->cfg.action_mode != DFRL_ACT_FORCED, "iterate() cannot teacher-force");
+  for (int it = 0; it < iters; ++it) {
+    if (t->fused_impl) {
+      DFRL_TRY(dfrl_fused_rollout(t, nullptr, nullptr, nullptr));
+      DFRL_TRY(dfrl_fused_learn(t));
+    } else {
+      DFRL_TRY(rollout_layered(t, nullptr, nullptr, nullptr));
+      DFRL_TRY(learn_layered(t));
+    }
+  }
+  return DFRL_OK;
+}
+
+// ------------------------------------------------------------------ introspection -----------
+extern "C" int dfrl_trainer_field_size(dfrl_trainer *t, int field, size_t *bytes) {
+  DFRL_CHECK(t && bytes, "null argument");
+  const size_t LN = (size_t)t->L * t->n;
+  switch (field) {
+  case DFRL_F_REC_STATE: *bytes = (size_t)t->L * t->P * t->n; break;
+  case DFRL_F_REC_ACTION:
+  case DFRL_F_REC_DONE: *bytes = LN; break;
+  case DFRL_F_REC_PROBS: *bytes = sizeof(float) * LN * t->B; break;
+  case DFRL_F_REC_LEN: *bytes = sizeof(int) * t->n; break;
+  case DFRL_F_ADVANTAGE:
+  case DFRL_F_VALUE_TARGET: *bytes = sizeof(float) * LN; break;
+  case DFRL_F_POLICY_GRAD: *bytes = sizeof(float) * t->policy->n_params; break;
+  case DFRL_F_VALUE_GRAD: *bytes = sizeof(float) * (t->value ? t->value->n_params : 0); break;
+  case DFRL_F_POLICY_GRAD_LOG: *bytes = sizeof(float) * (size_t)t->epochs * t->policy->n_params; break;
+  default:
+    dfrl_set_error("unknown field %d", field);
+    return DFRL_ERR_INVALID;
+  }
+  return DFRL_OK;
+}
+
+extern "C" int dfrl_trainer_read(dfrl_trainer *t, int field, void *dst_host, size_t bytes) {
+  DFRL_CHECK(t && dst_host, "null argument");
+  size_t want = 0;
+  DFRL_TRY(dfrl_trainer_field_size(t, field, &want));
+  DFRL_CHECK(bytes == want, "field %d is %zu bytes, caller passed %zu", field, want, bytes);
+  cudaStream_t s = t->ctx->stream;
+  const void *src = nullptr;
+  switch (field) {
+  case DFRL_F_REC_STATE:
+    DFRL_CUDA(cudaMemcpy2DAsync(dst_host, t->n, t->rec_state, t->stride, t->n, (size_t)t->L * t->P,
+                                cudaMemcpyDeviceToHost, s));
+    DFRL_CUDA(cudaStreamSynchronize(s));
+    return DFRL_OK;
+  case DFRL_F_REC_ACTION: src = t->rec_action; break;
+  case DFRL_F_REC_DONE: src = t->rec_done; break;
+  case DFRL_F_REC_PROBS: src = t->rec_probs; break;
+  case DFRL_F_REC_LEN: src = t->rec_len; break;
+  case DFRL_F_ADVANTAGE: src = t->adv; break;
+  case DFRL_F_VALUE_TARGET: src = t->targets; break;
+  case DFRL_F_POLICY_GRAD: src = t->pgrad_log + (size_t)(t->epochs - 1) * t->policy->n_params; break;
+  case DFRL_F_VALUE_GRAD: src = t->vgrad; break;
+  case DFRL_F_POLICY_GRAD_LOG: src = t->pgrad_log; break;
+  }
+  if (bytes) {
+    DFRL_CUDA(cudaMemcpyAsync(dst_host, src, bytes, cudaMemcpyDeviceToHost, s));
+    DFRL_CUDA(cudaStreamSynchronize(s));
+  }
+  return DFRL_OK;
+}
+
+extern "C" int dfrl_trainer_get_stats(dfrl_trainer *t, dfrl_trainer_stats *out) {
+  DFRL_CHECK(t && out, "null argument");
+  unsigned long long h[4];
+  DFRL_TRY(read_counters(t, h));
+  out->env_steps = (long long)h[0];
+  out->episodes = (long long)h[1];
+  out->reward_sum = (double)h[2];
+  // mean reward per step since the previous get_stats() call
+  long long ds = (long long)h[0] - t->last_rollout_steps, dr = (long long)h[2] - t->last_rollout_reward;
+  out->last_mean_reward = ds > 0 ? (double)dr / (double)ds : 0.0;
+  t->last_rollout_steps = (long long)h[0];
+  t->last_rollout_reward = (long long)h[2];
+  out->kl_beta = t->kl_beta;
+  return DFRL_OK;
+}
+
+// deep_agent.cc:28-41: argmax policy, `episodes` episodes per env, mean reward per episode.
+extern "C" int dfrl_eval_argmax(dfrl_ctx *ctx, dfrl_env *env, dfrl_mlp *policy, int episodes,
+                                double *mean_reward, long long *env_steps) {
+  DFRL_CHECK(ctx && env && policy && mean_reward, "null argument");
+  DFRL_CHECK(episodes > 0, "episodes must be positive");
+  DFRL_CHECK(policy->input_cols == 4 * env->B && policy->output_cols == env->B,
+             "policy shape does not match the env");
+  int fused_rc = dfrl_fused_eval_argmax(ctx, env, policy, episodes, mean_reward, env_steps);
+  if (fused_rc != DFRL_ERR_UNSUPPORTED)
+    return fused_rc;
+  const int n = env->n, B = env->B;
+  int max_ep = env_max_episode_len(env->cfg);
+  DFRL_CHECK(max_ep > 0, "episodes never end with zero-sized items");
+  float *obs, *probs;
+  int *ep_done;
+  unsigned long long *counters;
+  DFRL_CUDA(cudaMalloc(&obs, sizeof(float) * (size_t)n * 4 * B));
+  DFRL_CUDA(cudaMalloc(&probs, sizeof(float) * (size_t)n * B));
+  DFRL_CUDA(cudaMalloc(&ep_done, sizeof(int) * n));
+  DFRL_CUDA(cudaMalloc(&counters, 32));
+  DFRL_CUDA(cudaMemsetAsync(ep_done, 0, sizeof(int) * n, ctx->stream));
+  DFRL_CUDA(cudaMemsetAsync(counters, 0, 32, ctx->stream));
+  env_params p = make_params(env);
+  unsigned long long h[4] = {0, 0, 0, 0};
+  int rc = DFRL_OK;
+  for (int s = 0; s < episodes * max_ep && rc == DFRL_OK; ++s) {
+    cudaMemsetAsync(counters + 3, 0, 8, ctx->stream);
+    rc = dfrl_obs_encode(ctx, env->state, n, env->stride, B, env->cfg.cap_w, env->cfg.cap_h, obs);
+    if (rc == DFRL_OK)
+      rc = dfrl_mlp_eval(policy, obs, n, probs);
+    if (rc != DFRL_OK)
+      break;
+    act_step_kernel<<<ceil_div(n, 128), 128, 0, ctx->stream>>>(
+        p, env->state, env->draws, env->steps, probs, DFRL_ACT_ARGMAX, nullptr, nullptr, nullptr,
+        nullptr, nullptr, 1, episodes, ep_done, nullptr, counters);
+    ctx->launches++;
+    if ((s & 7) == 7) {
+      cudaMemcpyAsync(h, counters, 32, cudaMemcpyDeviceToHost, ctx->stream);
+      cudaStreamSynchronize(ctx->stream);
+      if (h[3] == 0)
+        break;
+    }
+  }
+  cudaMemcpyAsync(h, counters, 32, cudaMemcpyDeviceToHost, ctx->stream);
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(obs);
+  cudaFree(probs);
+  cudaFree(ep_done);
+  cudaFree(counters);
+  if (rc != DFRL_OK)
+    return rc;
+  if (e != cudaSuccess) {
+    dfrl_set_error("eval_argmax: %s", cudaGetErrorString(e));
+    return DFRL_ERR_CUDA;
+  }
+  *mean_reward = (double)h[2] / ((double)n * episodes);
+  if (env_steps)
+    *env_steps = (long long)h[0];
+  return DFRL_OK;
+}

@@ -1,0 +1,44 @@
+// trainer.h -- internal layout of dfrl_trainer, shared by trainer.cu (layered path) and
+// fused.cu (fused small-MLP path).
+#pragma once
+
+#include "common.cuh"
+
+struct dfrl_trainer {
+  dfrl_ctx *ctx;
+  dfrl_trainer_config cfg;
+  dfrl_env *env;
+  dfrl_mlp *policy, *value;
+  int n, B, P, stride, O;
+  int L;       // recorded steps per env per iteration (work, or work * max episode length)
+  int epochs;  // policy optimizer steps per learn()
+  // rollout records (see trainer.cu header)
+  int8_t *rec_state;
+  uint8_t *rec_action, *rec_done;
+  float *rec_probs;
+  int *rec_len, *ep_done;
+  // learn workspace
+  float *obs;  // [2][L*n][O]: start rows, then end rows
+  float *v_start, *v_end, *targets, *adv, *dyv, *dprobs;
+  float *pgrad_log, *vgrad;
+  float *pstate, *vstate;
+  float p_adam_t, v_adam_t, kl_beta;
+  // counters: [0] env steps, [1] episodes, [2] reward sum, [3] active envs (episodic rollouts)
+  unsigned long long *counters;
+  double *acc;  // [4] device accumulators (baseline, KL)
+  // device copies of the host tapes
+  uint8_t *tape_items, *tape_actions;
+  double *tape_u;
+  void *pin;  // 64 B pinned host staging
+  long long last_rollout_steps, last_rollout_reward;
+  void *fused_impl;  // non-null when the fused kernels drive this trainer
+};
+
+// fused.cu
+int dfrl_fused_try_attach(dfrl_trainer *t);
+void dfrl_fused_detach(dfrl_trainer *t);
+int dfrl_fused_rollout(dfrl_trainer *t, const uint8_t *items_dev, const uint8_t *actions_dev,
+                       const double *u_dev);
+int dfrl_fused_learn(dfrl_trainer *t);
+int dfrl_fused_eval_argmax(dfrl_ctx *ctx, dfrl_env *env, dfrl_mlp *policy, int episodes,
+                           double *mean_reward, long long *env_steps);

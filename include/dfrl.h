@@ -111,11 +111,20 @@ int dfrl_memcpy_h2d(dfrl_ctx *ctx, void *dst_dev, const void *src_host, size_t b
 int dfrl_memcpy_d2h(dfrl_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
 int dfrl_memcpy_d2d(dfrl_ctx *ctx, void *dst_dev, const void *src_dev, size_t bytes);
 int dfrl_memset(dfrl_ctx *ctx, void *dst_dev, int byte, size_t bytes);
+/* Pinned (page-locked) host memory for the e2e path's tapes and results. */
+int dfrl_malloc_host(dfrl_ctx *ctx, size_t bytes, void **out_host);
+int dfrl_free_host(dfrl_ctx *ctx, void *ptr_host);
 /* Timing helper: device milliseconds of everything enqueued on the stream between the calls. */
 int dfrl_timer_start(dfrl_ctx *ctx);
 int dfrl_timer_stop(dfrl_ctx *ctx, float *ms_out);
 /* Number of kernels this library has launched on this context so far. */
 long long dfrl_launch_count(dfrl_ctx *ctx);
+/* Per-kernel device timing with CUDA events on the context's stream (bench.py's roofline leg).
+ * While enabled every launch is bracketed by an event pair (adds launch overhead: never enable
+ * it inside a throughput measurement).  dfrl_profile_report synchronises and writes one line
+ * per kernel name, "name launches total_ms\n", into buf (truncated to cap); returns DFRL_OK. */
+int dfrl_profile_enable(dfrl_ctx *ctx, int on);
+int dfrl_profile_report(dfrl_ctx *ctx, char *buf, size_t cap);
 
 /* ------------------------------------------------------------- K1: batched environment ---- */
 
@@ -147,8 +156,11 @@ int dfrl_env_load_item_tape(dfrl_env *env, const uint8_t *tape_host, int len);
  * next item is drawn. actions_dev: uint8 [N]. done_dev (optional): uint8 [N]. */
 int dfrl_env_step(dfrl_env *env, const uint8_t *actions_dev, uint8_t *done_dev,
                   int8_t *terminal_state_dev);
-/* view(id) for all ids (bin_packing.h:65): device pointer to the int8 [2B+2][N] planes. */
+/* view(id) for all ids (bin_packing.h:65): device pointer to the int8 [2B+2][stride] planes;
+ * stride = N rounded up to 16 so that every plane starts 16-byte aligned. Device-side buffers
+ * shaped like the state (terminal_state_dev) use the same stride. */
 int8_t *dfrl_env_state_dev(dfrl_env *env);
+int dfrl_env_state_stride(dfrl_env *env);
 int dfrl_env_get_state(dfrl_env *env, int8_t *state_host /* [2B+2][N] */);
 int dfrl_env_set_state(dfrl_env *env, const int8_t *state_host);
 /* observation::to_vector for `rows` states (bin_packing.h:31-40). state planes have row
@@ -329,7 +341,7 @@ typedef struct {
   long long env_steps;     /* transitions made since creation (this rank) */
   long long episodes;      /* episodes finished since creation (this rank) */
   double reward_sum;       /* sum of rewards since creation (this rank) */
-  double last_mean_reward; /* mean reward per step of the last rollout */
+  double last_mean_reward; /* mean reward per step since the previous get_stats() call */
   float kl_beta;           /* current beta (KL-PPO) */
 } dfrl_trainer_stats;
 int dfrl_trainer_get_stats(dfrl_trainer *tr, dfrl_trainer_stats *out);

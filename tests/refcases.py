@@ -39,6 +39,21 @@ def close(a, b, rtol=RTOL, what=""):
         assert rel <= rtol, f"{what}: norm-wise relative error {rel:.3e} > {rtol}"
 
 
+def close_bulk(a, b, rtol=RTOL, max_outlier_frac=1e-4, what=""):
+    """For large random problems: a relu pre-activation within one ulp of zero can take a
+    different sign under a different (equally valid) summation order, which moves the few
+    gradient entries fed by that one row by more than 1e-4.  Require the norm-wise error and
+    all but a 1e-4 fraction of the entries to meet the tolerance."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape and np.all(np.isfinite(a)), what
+    scale = np.max(np.abs(b))
+    bad = np.abs(a - b) > rtol * (np.abs(b) + scale)
+    assert bad.mean() <= max_outlier_frac, f"{what}: {bad.mean():.2e} of entries out of tolerance"
+    rel = np.linalg.norm(a - b) / np.linalg.norm(b)
+    assert rel <= rtol, f"{what}: norm-wise relative error {rel:.3e}"
+
+
 def item_code(item_wh):
     """(4,2) -> 1 (shape1), (1,2) -> 0 (shape2) (bin_packing.h:73-79)."""
     return (np.asarray(item_wh)[..., 0] == 4).astype(np.uint8)
