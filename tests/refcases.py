@@ -39,11 +39,11 @@ def close(a, b, rtol=RTOL, what=""):
         assert rel <= rtol, f"{what}: norm-wise relative error {rel:.3e} > {rtol}"
 
 
-def close_bulk(a, b, rtol=RTOL, max_outlier_frac=1e-4, what=""):
+def close_bulk(a, b, rtol=RTOL, max_outlier_frac=2e-3, what=""):
     """For large random problems: a relu pre-activation within one ulp of zero can take a
     different sign under a different (equally valid) summation order, which moves the few
     gradient entries fed by that one row by more than 1e-4.  Require the norm-wise error and
-    all but a 1e-4 fraction of the entries to meet the tolerance."""
+    all but a 2e-3 fraction of the entries (one flipped unit touches one row of dW, ~1e-3 of a layer) to meet the tolerance."""
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     assert a.shape == b.shape and np.all(np.isfinite(a)), what
