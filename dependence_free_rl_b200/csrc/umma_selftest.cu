@@ -1,0 +1,175 @@
+// umma_selftest.cu -- validates the tcgen05 building blocks of umma.cuh against a host fp64
+// reference: one 128-row tile, bf16 hi/lo split operands in SWIZZLE_128B panels, three operand
+// major-ness combinations (the three GEMMs of an MLP layer):
+//   variant 0  D[128 x N]  = X[128 x K] . W[N x K]^T      A K-major,  B K-major   (forward)
+//   variant 1  D[128 x Ko] = dY[128 x N] . W[N x Ko]      A K-major,  B MN-major  (input gradient)
+//   variant 2  D[128 x N2] = G[128 x 128]^T . H[128 x N2] A MN-major, B MN-major  (weight gradient)
+#include <math.h>
+#include <stdlib.h>
+
+#include <vector>
+
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace {
+
+constexpr int ROWS = 128;
+
+// fp32 row-major [rows][cols] (global) -> hi/lo panels (64 columns each) in shared memory
+__device__ void stage_panels(const float *__restrict__ src, int rows, int cols, uint8_t *hi, uint8_t *lo,
+                             int panel_rows) {
+  int npanels = (cols + 63) / 64;
+  int chunks = rows * npanels * 8;
+  for (int c = threadIdx.x; c < chunks; c += blockDim.x) {
+    int row = c / (npanels * 8), rem = c % (npanels * 8);
+    int panel = rem / 8, chunk = rem % 8;
+    float x[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int col = panel * 64 + chunk * 8 + j;
+      x[j] = col < cols ? src[(size_t)row * cols + col] : 0.f;
+    }
+    uint4 h, l;
+    umma::split8(x, h, l);
+    uint32_t off = panel * panel_rows * 128 + umma::panel_chunk_off(row, chunk);
+    *reinterpret_cast<uint4 *>(hi + off) = h;
+    *reinterpret_cast<uint4 *>(lo + off) = l;
+  }
+}
+
+__global__ void __launch_bounds__(128)
+umma_selftest_kernel(int variant, const float *__restrict__ A, int a_rows, int a_cols,
+                     const float *__restrict__ Bm, int b_rows, int b_cols, float *__restrict__ D,
+                     int n_out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // layout: A_hi [2 panels x 128 rows], A_lo, B_hi [2 panels x 128 rows], B_lo
+  const uint32_t PANEL = 128 * 128;  // bytes of a 128-row panel
+  uint8_t *a_hi = smem, *a_lo = smem + 2 * PANEL, *b_hi = smem + 4 * PANEL, *b_lo = smem + 6 * PANEL;
+  __shared__ uint64_t mbar;
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x / 32;
+  if (warp == 0)
+    umma::tmem_alloc(&tmem_base_slot, 128);
+  if (threadIdx.x == 0) {
+    umma::mbar_init(&mbar, 1);
+    umma::fence_mbar_init();
+  }
+  stage_panels(A, a_rows, a_cols, a_hi, a_lo, 128);
+  stage_panels(Bm, b_rows, b_cols, b_hi, b_lo, 128);
+  umma::fence_proxy_async();
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem = tmem_base_slot;
+
+  if (threadIdx.x == 0) {
+    uint32_t idesc;
+    int ksteps;
+    if (variant == 0) {
+      idesc = umma::make_idesc_bf16(128, n_out, 0, 0);
+      ksteps = a_cols / 16;
+    } else if (variant == 1) {
+      idesc = umma::make_idesc_bf16(128, n_out, 0, 1);
+      ksteps = a_cols / 16;
+    } else {
+      idesc = umma::make_idesc_bf16(128, n_out, 1, 1);
+      ksteps = a_rows / 16;
+    }
+    uint32_t acc = 0;
+    for (int k = 0; k < ksteps; ++k) {
+      uint32_t a_off, b_off;
+      if (variant == 0) {  // both K-major: K runs along the panel row
+        a_off = (k / 4) * PANEL + (k % 4) * umma::KSTEP_BYTES_KMAJOR;
+        b_off = (k / 4) * PANEL + (k % 4) * umma::KSTEP_BYTES_KMAJOR;
+      } else if (variant == 1) {  // A K-major, B MN-major: B's K runs along panel rows
+        a_off = (k / 4) * PANEL + (k % 4) * umma::KSTEP_BYTES_KMAJOR;
+        b_off = k * umma::KSTEP_BYTES_MNMAJOR;
+      } else {  // both MN-major
+        a_off = k * umma::KSTEP_BYTES_MNMAJOR;
+        b_off = k * umma::KSTEP_BYTES_MNMAJOR;
+      }
+      // LBO: K-major swizzled -> 16 B (unused); MN-major -> stride between 64-element MN blocks
+      uint32_t a_lbo = variant == 2 ? PANEL : 16, b_lbo = variant == 0 ? 16 : PANEL;
+      uint64_t ah = umma::make_desc_sw128(umma::smem_u32(a_hi) + a_off, a_lbo, 1024);
+      uint64_t al = umma::make_desc_sw128(umma::smem_u32(a_lo) + a_off, a_lbo, 1024);
+      uint64_t bh = umma::make_desc_sw128(umma::smem_u32(b_hi) + b_off, b_lbo, 1024);
+      uint64_t bl = umma::make_desc_sw128(umma::smem_u32(b_lo) + b_off, b_lbo, 1024);
+      umma::mma_bf16(tmem, ah, bh, idesc, acc);
+      acc = 1;
+      umma::mma_bf16(tmem, ah, bl, idesc, 1);
+      umma::mma_bf16(tmem, al, bh, idesc, 1);
+    }
+    umma::commit(&mbar);
+  }
+  umma::mbar_wait(&mbar, 0);
+  umma::fence_after_sync();
+  const int row = warp * 32 + (threadIdx.x & 31);
+  for (int c0 = 0; c0 < n_out; c0 += 16) {
+    float v[16];
+    umma::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+    umma::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      D[(size_t)row * n_out + c0 + j] = v[j];
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0)
+    umma::tmem_dealloc(tmem, 128);
+}
+
+float lcg(uint32_t &s) {
+  s = s * 1664525u + 1013904223u;
+  return ((s >> 8) & 0xffff) / 32768.0f - 1.0f;
+}
+
+}  // namespace
+
+// variant 0..2, see file header. k = contraction length (multiple of 16, <= 128), n = output
+// columns (multiple of 16, <= 64). Returns max |D - ref| / max |ref| through *rel_err.
+extern "C" int dfrl_umma_selftest(dfrl_ctx *ctx, int variant, int k, int n, float *rel_err) {
+  DFRL_CHECK(ctx && rel_err, "null argument");
+  DFRL_CHECK(variant >= 0 && variant <= 2, "variant 0..2");
+  DFRL_CHECK(k % 16 == 0 && k >= 16 && k <= 128 && n % 16 == 0 && n >= 16 && n <= 64, "bad k / n");
+  DFRL_CHECK(variant != 2 || k == 128, "variant 2 contracts over the 128 tile rows");
+  int a_rows, a_cols, b_rows, b_cols;
+  if (variant == 0) { a_rows = ROWS; a_cols = k; b_rows = n; b_cols = k; }
+  else if (variant == 1) { a_rows = ROWS; a_cols = k; b_rows = k; b_cols = n; }
+  else { a_rows = ROWS; a_cols = 128; b_rows = ROWS; b_cols = n; }
+  std::vector<float> A((size_t)a_rows * a_cols), B((size_t)b_rows * b_cols), D((size_t)ROWS * n);
+  uint32_t s = 12345u + variant * 77 + k * 3 + n;
+  for (float &x : A) x = lcg(s) * 1.7f;
+  for (float &x : B) x = lcg(s) * 0.9f;
+  float *dA, *dB, *dD;
+  DFRL_CUDA(cudaMalloc(&dA, A.size() * 4));
+  DFRL_CUDA(cudaMalloc(&dB, B.size() * 4));
+  DFRL_CUDA(cudaMalloc(&dD, D.size() * 4));
+  DFRL_CUDA(cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice));
+  DFRL_CUDA(cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice));
+  DFRL_CUDA(cudaMemset(dD, 0, D.size() * 4));
+  const int smem = 8 * 128 * 128 + 1024;
+  DFRL_CUDA(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  DFRL_LAUNCH(ctx, umma_selftest_kernel, 1, 128, smem, variant, dA, a_rows, a_cols, dB, b_rows, b_cols, dD, n);
+  DFRL_CUDA(cudaStreamSynchronize(ctx->stream));
+  DFRL_CUDA(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
+  cudaFree(dA); cudaFree(dB); cudaFree(dD);
+  double max_ref = 0, max_err = 0;
+  for (int i = 0; i < ROWS; ++i)
+    for (int j = 0; j < n; ++j) {
+      double ref = 0;
+      if (variant == 0)
+        for (int q = 0; q < k; ++q) ref += (double)A[(size_t)i * k + q] * B[(size_t)j * k + q];
+      else if (variant == 1)
+        for (int q = 0; q < k; ++q) ref += (double)A[(size_t)i * k + q] * B[(size_t)q * n + j];
+      else
+        for (int r = 0; r < ROWS; ++r) ref += (double)A[(size_t)r * 128 + i] * B[(size_t)r * n + j];
+      double err = fabs(ref - (double)D[(size_t)i * n + j]);
+      if (fabs(ref) > max_ref) max_ref = fabs(ref);
+      if (err > max_err) max_err = err;
+    }
+  *rel_err = (float)(max_err / (max_ref + 1e-30));
+  return DFRL_OK;
+}
