@@ -306,6 +306,7 @@ extern "C" int dfrl_trainer_create(dfrl_ctx *ctx, const dfrl_trainer_config *cfg
   t->last_rollout_steps = 0;
   t->last_rollout_reward = 0;
   t->fused_impl = nullptr;
+  t->obs_valid = false;
   *out = t;
   if (cfg->fused)
     dfrl_fused_try_attach(t);  // silently stays layered when the nets do not qualify
@@ -387,6 +388,20 @@ static int rollout_layered(dfrl_trainer *t, const uint8_t *items_dev, const uint
                             u_dev ? u_dev + s * n : nullptr, items_dev ? items_dev + s * n : nullptr,
                             0, 0, true));
   }
+  t->obs_valid = true;
+  return DFRL_OK;
+}
+
+// Start-row observations for the layered kernels when the rollout was fused (it keeps no fp32
+// observations): observation::to_vector of every recorded start state.
+static int ensure_obs(dfrl_trainer *t) {
+  if (t->obs_valid)
+    return DFRL_OK;
+  dfrl_env *e = t->env;
+  for (int s = 0; s < t->L; ++s)
+    DFRL_TRY(dfrl_obs_encode(t->ctx, t->rec_state + (size_t)s * t->P * t->stride, t->n, t->stride, t->B,
+                             e->cfg.cap_w, e->cfg.cap_h, t->obs + (size_t)s * t->n * t->O));
+  t->obs_valid = true;
   return DFRL_OK;
 }
 
@@ -410,10 +425,10 @@ extern "C" int dfrl_trainer_rollout(dfrl_trainer *t, const uint8_t *items_host,
     DFRL_CUDA(cudaMemcpyAsync(t->tape_u, u_host, sizeof(double) * LN, cudaMemcpyHostToDevice, ctx->stream));
     u_dev = t->tape_u;
   }
-  if (t->fused_impl)
-    DFRL_TRY(dfrl_fused_rollout(t, items_dev, actions_dev, u_dev));
-  else
-    DFRL_TRY(rollout_layered(t, items_dev, actions_dev, u_dev));
+  int rc = t->fused_impl ? dfrl_fused_rollout(t, items_dev, actions_dev, u_dev) : DFRL_ERR_UNSUPPORTED;
+  if (rc == DFRL_ERR_UNSUPPORTED)
+    rc = rollout_layered(t, items_dev, actions_dev, u_dev);
+  DFRL_TRY(rc);
   return DFRL_OK;
 }
 
@@ -450,6 +465,7 @@ static int learn_layered(dfrl_trainer *t) {
     float baseline = (float)h[0] / (float)h[1];  // total_reward / experience.size() (145)
     DFRL_LAUNCH(ctx, reinforce_adv_kernel, ceil_div(LN, 256), 256, 0, g, t->rec_len, n, L, baseline, t->adv);
     float *probs = nullptr;
+    DFRL_TRY(ensure_obs(t));
     DFRL_TRY(dfrl_mlp_forward_keep(t->policy, obs_start, (int)LN, &probs));
     DFRL_LAUNCH(ctx, policy_loss_kernel, ceil_div(LN, 128), 128, 0, DFRL_LOSS_SOFTMAX_LOG, probs,
                 t->rec_action, t->rec_done, t->rec_len, t->adv, t->rec_probs, 0.f, n, L, B, 0,
@@ -460,21 +476,30 @@ static int learn_layered(dfrl_trainer *t) {
   }
 
   // actor_critic_learner::learn (policy_gradient.h:159-185)
-  DFRL_LAUNCH(ctx, end_obs_kernel, ceil_div(LN * B, 256), 256, 0, t->rec_state, e->state,
-              t->rec_action, t->rec_done, n, t->stride, B, L, (float)e->cfg.cap_w, (float)e->cfg.cap_h,
-              reinterpret_cast<float4 *>(obs_end));
-  // update_value_model (196-218): V on every row with the current critic, targets, one step
-  DFRL_TRY(dfrl_mlp_eval(t->value, obs_end, (int)LN, t->v_end));
-  float *v_now = nullptr;
-  DFRL_TRY(dfrl_mlp_forward_keep(t->value, obs_start, (int)LN, &v_now));
-  DFRL_TRY(dfrl_gae(ctx, t->rec_done, v_now, t->v_end, n, L, c.gamma, c.lambda, t->targets, nullptr));
-  DFRL_LAUNCH(ctx, value_loss_kernel, ceil_div(LN, 256), 256, 0, v_now, t->targets, LN, t->dyv);
-  DFRL_TRY(dfrl_mlp_backward(t->value, t->dyv, t->vgrad));
-  DFRL_TRY(apply_opt(t, t->value, c.value_opt, t->vgrad, t->vstate, c.value_lr, c.value_wd, &t->v_adam_t));
-  // calculate_advantage (220-281) with the UPDATED critic
-  DFRL_TRY(dfrl_mlp_eval(t->value, obs_end, (int)LN, t->v_end));
-  DFRL_TRY(dfrl_mlp_eval(t->value, obs_start, (int)LN, t->v_start));
-  DFRL_TRY(dfrl_gae(ctx, t->rec_done, t->v_start, t->v_end, n, L, c.gamma, c.lambda, nullptr, t->adv));
+  int frc = dfrl_fused_critic_gradient(t, t->vgrad);  // tcgen05 fused critic step (fused.cu)
+  if (frc == DFRL_OK) {
+    DFRL_TRY(apply_opt(t, t->value, c.value_opt, t->vgrad, t->vstate, c.value_lr, c.value_wd, &t->v_adam_t));
+    DFRL_TRY(dfrl_fused_gae(t));
+  } else if (frc != DFRL_ERR_UNSUPPORTED) {
+    return frc;
+  } else {
+    DFRL_TRY(ensure_obs(t));
+    DFRL_LAUNCH(ctx, end_obs_kernel, ceil_div(LN * B, 256), 256, 0, t->rec_state, e->state,
+                t->rec_action, t->rec_done, n, t->stride, B, L, (float)e->cfg.cap_w, (float)e->cfg.cap_h,
+                reinterpret_cast<float4 *>(obs_end));
+    // update_value_model (196-218): V on every row with the current critic, targets, one step
+    DFRL_TRY(dfrl_mlp_eval(t->value, obs_end, (int)LN, t->v_end));
+    float *v_now = nullptr;
+    DFRL_TRY(dfrl_mlp_forward_keep(t->value, obs_start, (int)LN, &v_now));
+    DFRL_TRY(dfrl_gae(ctx, t->rec_done, v_now, t->v_end, n, L, c.gamma, c.lambda, t->targets, nullptr));
+    DFRL_LAUNCH(ctx, value_loss_kernel, ceil_div(LN, 256), 256, 0, v_now, t->targets, LN, t->dyv);
+    DFRL_TRY(dfrl_mlp_backward(t->value, t->dyv, t->vgrad));
+    DFRL_TRY(apply_opt(t, t->value, c.value_opt, t->vgrad, t->vstate, c.value_lr, c.value_wd, &t->v_adam_t));
+    // calculate_advantage (220-281) with the UPDATED critic
+    DFRL_TRY(dfrl_mlp_eval(t->value, obs_end, (int)LN, t->v_end));
+    DFRL_TRY(dfrl_mlp_eval(t->value, obs_start, (int)LN, t->v_start));
+    DFRL_TRY(dfrl_gae(ctx, t->rec_done, t->v_start, t->v_end, n, L, c.gamma, c.lambda, nullptr, t->adv));
+  }
   // optimize_action (187-194 / 297-307 / 318-330)
   int kind = c.algo == DFRL_ALGO_ACTOR_CRITIC ? DFRL_LOSS_SOFTMAX_LOG
              : c.algo == DFRL_ALGO_PPO        ? DFRL_LOSS_CLIPPED
@@ -482,6 +507,22 @@ static int learn_layered(dfrl_trainer *t) {
   const int with_end = kind == DFRL_LOSS_KL ? 1 : 0;
   const long long rows = with_end ? 2 * LN : LN;
   for (int ep = 0; ep < t->epochs; ++ep) {
+    {
+      // tcgen05 fused forward + loss + backward (fused.cu); layered kernels otherwise
+      float *g = t->pgrad_log + (size_t)ep * t->policy->n_params;
+      int rc = dfrl_fused_policy_gradient(t, kind, g);
+      if (rc == DFRL_OK) {
+        DFRL_TRY(apply_opt(t, t->policy, c.policy_opt, g, t->pstate, c.policy_lr, c.policy_wd, &t->p_adam_t));
+        continue;
+      }
+      if (rc != DFRL_ERR_UNSUPPORTED)
+        return rc;
+    }
+    DFRL_TRY(ensure_obs(t));
+    if (with_end && ep == 0 && frc == DFRL_OK)  // KL rows include the end rows: encode them once
+      DFRL_LAUNCH(ctx, end_obs_kernel, ceil_div(LN * B, 256), 256, 0, t->rec_state, e->state,
+                  t->rec_action, t->rec_done, n, t->stride, B, L, (float)e->cfg.cap_w, (float)e->cfg.cap_h,
+                  reinterpret_cast<float4 *>(obs_end));
     float *probs = nullptr;
     DFRL_TRY(dfrl_mlp_forward_keep(t->policy, t->obs, (int)rows, &probs));
     if (with_end)
@@ -513,8 +554,6 @@ static int learn_layered(dfrl_trainer *t) {
 
 extern "C" int dfrl_trainer_learn(dfrl_trainer *t) {
   DFRL_CHECK(t, "null trainer");
-  if (t->fused_impl)
-    return dfrl_fused_learn(t);
   return learn_layered(t);
 }
 
@@ -522,13 +561,11 @@ extern "C" int dfrl_trainer_iterate(dfrl_trainer *t, int iters) {
   DFRL_CHECK(t, "null trainer");
   DFRL_CHECK(t->cfg.action_mode != DFRL_ACT_FORCED, "iterate() cannot teacher-force");
   for (int it = 0; it < iters; ++it) {
-    if (t->fused_impl) {
-      DFRL_TRY(dfrl_fused_rollout(t, nullptr, nullptr, nullptr));
-      DFRL_TRY(dfrl_fused_learn(t));
-    } else {
-      DFRL_TRY(rollout_layered(t, nullptr, nullptr, nullptr));
-      DFRL_TRY(learn_layered(t));
-    }
+    int rc = t->fused_impl ? dfrl_fused_rollout(t, nullptr, nullptr, nullptr) : DFRL_ERR_UNSUPPORTED;
+    if (rc == DFRL_ERR_UNSUPPORTED)
+      rc = rollout_layered(t, nullptr, nullptr, nullptr);
+    DFRL_TRY(rc);
+    DFRL_TRY(learn_layered(t));
   }
   return DFRL_OK;
 }

@@ -18,7 +18,8 @@ struct dfrl_trainer {
   float *rec_probs;
   int *rec_len, *ep_done;
   // learn workspace
-  float *obs;  // [2][L*n][O]: start rows, then end rows
+  float *obs;  // [2][L*n][O]: start rows, then end rows (layered kernels only)
+  bool obs_valid;  // start rows of `obs` hold the observations of the current records
   float *v_start, *v_end, *targets, *adv, *dyv, *dprobs;
   float *pgrad_log, *vgrad;
   float *pstate, *vstate;
@@ -39,6 +40,11 @@ int dfrl_fused_try_attach(dfrl_trainer *t);
 void dfrl_fused_detach(dfrl_trainer *t);
 int dfrl_fused_rollout(dfrl_trainer *t, const uint8_t *items_dev, const uint8_t *actions_dev,
                        const double *u_dev);
-int dfrl_fused_learn(dfrl_trainer *t);
+// update_value_model up to the flat gradient (writes t->targets) / calculate_advantage (t->adv).
+int dfrl_fused_critic_gradient(dfrl_trainer *t, float *grad_dev);
+int dfrl_fused_gae(dfrl_trainer *t);
+// One policy gradient over all recorded rows (forward + loss gradient + backward), SUM over rows.
+// Returns DFRL_ERR_UNSUPPORTED when the fused policy kernel does not cover this trainer.
+int dfrl_fused_policy_gradient(dfrl_trainer *t, int loss_kind, float *grad_dev);
 int dfrl_fused_eval_argmax(dfrl_ctx *ctx, dfrl_env *env, dfrl_mlp *policy, int episodes,
                            double *mean_reward, long long *env_steps);

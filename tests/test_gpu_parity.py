@@ -225,16 +225,27 @@ def test_c5_wide_model_vs_oracle(D, ctx, orc, rows):
     p = (rng.standard_normal(m.n_params) * 0.05).astype(np.float32)
     x = (rng.integers(0, 9, (rows, 128)) / 8.0).astype(np.float32)
     dy = rng.standard_normal((rows, 32)).astype(np.float32)
+    # relu'(x) is discontinuous at 0: a pre-activation within rounding distance of zero takes
+    # either sign under equally valid summation orders and moves a whole gradient row. Rows with
+    # such a pre-activation (fp64 forward, margin 1e-5) get a zero upstream gradient so that the
+    # comparison below is a strict 1e-4 one.
+    h, off, dims = x.astype(np.float64), 0, [128, 256, 256, 256, 32]
+    risky = np.zeros(rows, dtype=bool)
+    for a, b in zip(dims[:-2], dims[1:-1]):
+        W = p[off:off + a * b].reshape(b, a).astype(np.float64)
+        bias = p[off + a * b:off + a * b + b].astype(np.float64)
+        off += a * b + b
+        pre = h @ W.T + bias
+        risky |= (np.abs(pre) < 1e-5).any(axis=1)
+        h = np.maximum(pre, 0.0)
+    dy[risky] = 0.0
     m.set_parameters(p)
     net = orc.Net(layers, 128)
     assert net.param_count() == m.n_params == 172832
     g, out = m.forward_gradient(x, dy)
     g_want, out_want = orc.net_forward_gradient(net, p, x, dy, f64=True)
     close(out, out_want, what="c5 out")
-    if rows == 1:
-        close(g, g_want, what="c5 grad")
-    else:
-        refcases.close_bulk(g, g_want, what="c5 grad")
+    close(g, g_want, what="c5 grad")
     m.close()
 
 
@@ -462,8 +473,11 @@ def test_trainer_vs_oracle_with_uniform_tape(D, ctx, orc):
         tr.learn()
         close(tr.read(D.F_ADVANTAGE), out["adv"], what="adv")
         close(tr.read(D.F_VALUE_TARGET), out["targets"], what="targets")
-        close(tr.read(D.F_VALUE_GRAD), out["value_grad"], what="vgrad")
-        close(tr.read(D.F_POLICY_GRAD_LOG), out["policy_grads"], what="pgrads")
+        # The fused tensor-core kernels evaluate the nets with bf16 hi/lo split operands (~1e-5
+        # relative): a relu pre-activation within that distance of zero can take the other sign
+        # and move the few gradient entries fed by that one row. Norm-wise 1e-4 + bulk criterion.
+        refcases.close_bulk(tr.read(D.F_VALUE_GRAD), out["value_grad"], what="vgrad")
+        refcases.close_bulk(tr.read(D.F_POLICY_GRAD_LOG), out["policy_grads"], what="pgrads")
         close(policy.parameters(), lr.pparams, what="pparams")
         close(value.parameters(), lr.vparams, what="vparams")
     s = tr.stats()
