@@ -64,6 +64,7 @@ PROTOTYPES = {
     "dfrl_timer_stop": (i32, [vp, C.POINTER(f32)]),
     "dfrl_launch_count": (C.c_longlong, [vp]),
     "dfrl_umma_selftest": (i32, [vp, i32, i32, i32, C.POINTER(f32)]),
+    "dfrl_debug_policy_clocks": (i32, [vp, vp, i32]),
     "dfrl_env_config_default": (None, [C.POINTER(EnvConfig)]),
     "dfrl_env_create": (i32, [vp, C.POINTER(EnvConfig), C.POINTER(vp)]),
     "dfrl_env_destroy": (i32, [vp]),

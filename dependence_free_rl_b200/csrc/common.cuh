@@ -146,6 +146,7 @@ struct dfrl_mlp {
   float *params;   // flat, reference order
   float *wt;       // W^T per parametric layer, refreshed after every parameter change
   bool wt_dirty;
+  uint64_t version = 0;  // bumped on every parameter change (fused.cu panel-image cache)
   // kept activations of the last forward_keep()
   std::vector<float *> acts;  // acts[l] = output of layer l (device), acts.size() == layers.size()
   float *act_arena;

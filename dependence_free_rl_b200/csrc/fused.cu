@@ -8,15 +8,25 @@
 //   Jacobian                                                                         (registers)
 //   input gradients dH2 = (dY W3) . relu', dH1 = (dH2 W2) . relu'                     (2 UMMA GEMMs)
 //   weight gradients dW_l += dY_l^T X_l, accumulated over all tiles of the CTA in TMEM (3 UMMA GEMMs)
-// Activations live in shared memory as SWIZZLE_128B bf16 panels (umma.cuh): the same panel is
+// Activations live in shared memory as SWIZZLE_128B 16-bit panels (umma.cuh): the same panel is
 // the K-major A operand of the forward GEMM and the MN-major operand of the weight-gradient GEMM.
-// FP32-level accuracy: bf16 hi/lo split operands, three products per GEMM, FP32 accumulation.
+//
+// FP32-level accuracy on the 16-bit tensor pipe: every operand is split into hi + lo halves and a
+// product is accumulated as hi*hi + hi*lo + lo*hi in FP32 (TMEM); the dropped lo*lo term is ~2^-17.
+// All operands are BF16 pairs (fp32 exponent range: loss and input gradients span many orders of
+// magnitude). FWD_F16 switches the forward operands (weights, activations) to FP16 pairs pre-scaled
+// by powers of two (22 significant bits); it is off because tcgen05.mma kind::f16 raised an
+// illegal-instruction fault on B200 when the A and B formats differ, which the weight-gradient
+// GEMMs (gradient^T x activation) would need.
+// The split weight panels are built once per parameter update by fused_prep_kernel into a "panel
+// image" in global memory that every CTA copies into its shared memory.
 //
 // Row tiles are env-blocked: a tile holds E = 128 / T environments x all T steps (row = t * E + e)
 // so that the critic target r + gamma V(s_{t+1}) and GAE only need values of the same tile.
 //
 // Reference semantics reproduced: rl.h:54-74 (clipped_gradient), rl.h:45-52, nn.h:393-417 (softmax
 // Jacobian), nn.h:85-100 (dW = SUM over rows), policy_gradient.h:196-281 (targets, GAE).
+#include <cuda_fp16.h>
 #include <math.h>
 #include <string.h>
 
@@ -28,6 +38,7 @@
 namespace {
 
 constexpr int TILE = 128;
+constexpr bool FWD_F16 = false;  // see the header comment
 constexpr uint32_t PANEL = 128 * 128;  // bytes of one 128-row panel
 
 struct net3 {
@@ -38,10 +49,12 @@ struct net3 {
 
 struct tid_t {
   int wg, w, lane, row;
+  int warp;            // warp index in the CTA, provably warp-uniform (MMA issue branch)
   uint32_t lane_base;  // TMEM lane field of this thread's warp
 };
 __device__ __forceinline__ tid_t thread_id() {
   tid_t t;
+  t.warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   t.wg = threadIdx.x >> 7;
   t.w = (threadIdx.x >> 5) & 3;
   t.lane = threadIdx.x & 31;
@@ -49,6 +62,9 @@ __device__ __forceinline__ tid_t thread_id() {
   t.lane_base = (uint32_t)(t.w * 32) << 16;
   return t;
 }
+
+// The single MMA-issuing lane: warp 0 (warp-uniform test), one elected lane.
+__device__ __forceinline__ bool mma_thread(const tid_t &t) { return t.warp == 0 && umma::elect_one(); }
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float *v) {
   uint32_t r[8];
@@ -68,151 +84,76 @@ __device__ __forceinline__ void tmem_load(uint32_t taddr, float (&v)[DC]) {
   umma::tmem_ld_wait();
 }
 
-// fp32 [N][K] row-major (global) -> hi / lo panels [rows_alloc][64], zero padded.
-__device__ void stage_weight(const float *__restrict__ W, int N, int K, int rows_alloc, uint8_t *hi,
-                             uint8_t *lo) {
-  for (int c = threadIdx.x; c < rows_alloc * 8; c += blockDim.x) {
-    int row = c >> 3, chunk = c & 7;
-    float x[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      int col = chunk * 8 + j;
-      x[j] = (row < N && col < K) ? W[(size_t)row * K + col] : 0.f;
-    }
-    uint4 h, l;
-    umma::split8(x, h, l);
-    uint32_t off = umma::panel_chunk_off(row, chunk);
-    *reinterpret_cast<uint4 *>(hi + off) = h;
-    *reinterpret_cast<uint4 *>(lo + off) = l;
-  }
+// ---- fp32 -> 16-bit hi/lo pairs -------------------------------------------------------------
+// FP16 pair (forward operands; the caller pre-scales so that hi and lo are normal numbers).
+__device__ __forceinline__ void split2_f16(float a, float b, uint32_t &hi, uint32_t &lo) {
+  __half2 h = __floats2half2_rn(a, b);
+  float2 hf = __half22float2(h);
+  __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<uint32_t *>(&h);
+  lo = *reinterpret_cast<uint32_t *>(&l);
 }
+template <bool F16>
+__device__ __forceinline__ void split8(const float *x, uint4 &hi, uint4 &lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (F16)
+      split2_f16(x[2 * i], x[2 * i + 1], h[i], l[i]);
+    else
+      umma::split2(x[2 * i], x[2 * i + 1], h[i], l[i]);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// Two fp32 values that are exact in 16 bits -> one packed word in the forward operand format.
+__device__ __forceinline__ uint32_t pack2_fwd(float a, float b) {
+  if (FWD_F16) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&h);
+  }
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t *>(&h);
+}
+constexpr uint16_t ONE_FWD = FWD_F16 ? 0x3C00 : 0x3F80;
 
 __device__ void zero_bytes(uint8_t *p, uint32_t bytes) {
   for (uint32_t o = threadIdx.x * 16; o < bytes; o += blockDim.x * 16)
     *reinterpret_cast<uint4 *>(p + o) = make_uint4(0, 0, 0, 0);
 }
 
-// One GEMM = ksteps x {hi.hi, hi.lo, lo.hi} tcgen05.mma instructions, issued by one thread.
-// a_lo / b_lo == 0: that operand is exact in bf16 (no lo pass).
+// ---- tcgen05.mma issue ----------------------------------------------------------------------
+// Instruction descriptor, kind::f16: c_format F32, a/b format 0 = F16, 1 = BF16.
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_bf16, int b_bf16, int a_mn, int b_mn) {
+  return (1u << 4) | ((uint32_t)a_bf16 << 7) | ((uint32_t)b_bf16 << 10) | ((uint32_t)a_mn << 15) |
+         ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// Descriptor high word: SBO = 1024 B (8-row swizzle atom), version 1, SWIZZLE_128B.
+constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint64_t desc_lo_hi(uint32_t lo) { return ((uint64_t)DESC_HI << 32) | lo; }
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo) {
+  return ((saddr >> 4) & 0x3FFFu) | ((lbo >> 4) << 16);
+}
+// One GEMM = KSTEPS x {hi.hi, hi.lo, lo.hi} tcgen05.mma instructions, issued by one elected lane
+// of warp 0 (warp-uniform branch: descriptors stay in uniform registers).
+// A_LO / B_LO false: that operand is exact in 16 bits (no lo pass).
+template <int KSTEPS, bool A_MN, bool B_MN, bool A_LO, bool B_LO>
 __device__ __forceinline__ void issue_gemm(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi,
-                                           uint32_t b_lo, int ksteps, bool a_mn, bool b_mn,
-                                           uint32_t idesc, bool accumulate) {
-  uint32_t acc = accumulate ? 1u : 0u;
-  const uint32_t a_step = a_mn ? umma::KSTEP_BYTES_MNMAJOR : umma::KSTEP_BYTES_KMAJOR;
-  const uint32_t b_step = b_mn ? umma::KSTEP_BYTES_MNMAJOR : umma::KSTEP_BYTES_KMAJOR;
-  const uint32_t a_lbo = a_mn ? PANEL : 16, b_lbo = b_mn ? PANEL : 16;
-  for (int k = 0; k < ksteps; ++k) {
-    uint64_t ah = umma::make_desc_sw128(a_hi + k * a_step, a_lbo, 1024);
-    uint64_t bh = umma::make_desc_sw128(b_hi + k * b_step, b_lbo, 1024);
-    umma::mma_bf16(tmem_d, ah, bh, idesc, acc);
-    acc = 1;
-    if (b_lo) {
-      uint64_t bl = umma::make_desc_sw128(b_lo + k * b_step, b_lbo, 1024);
-      umma::mma_bf16(tmem_d, ah, bl, idesc, 1);
-    }
-    if (a_lo) {
-      uint64_t al = umma::make_desc_sw128(a_lo + k * a_step, a_lbo, 1024);
-      umma::mma_bf16(tmem_d, al, bh, idesc, 1);
-    }
-  }
-}
-
-// Shared-memory map of the learner kernels (all panel buffers 1024-byte aligned).
-template <int D1, int D2>
-struct smem_map {
-  static constexpr uint32_t W1_HI = 0, W1_LO = W1_HI + D1 * 128;
-  static constexpr uint32_t W2_HI = W1_LO + D1 * 128, W2_LO = W2_HI + D2 * 128;
-  static constexpr uint32_t W3_HI = W2_LO + D2 * 128, W3_LO = W3_HI + 16 * 128;
-  static constexpr uint32_t X0 = W3_LO + 16 * 128;          // hi only (k/8 is exact in bf16)
-  static constexpr uint32_t H_HI = X0 + PANEL;              // [H1 | H2]
-  static constexpr uint32_t H_LO = H_HI + 2 * PANEL;
-  static constexpr uint32_t DH_HI = H_LO + 2 * PANEL;       // [dH1 | dH2]
-  static constexpr uint32_t DH_LO = DH_HI + 2 * PANEL;
-  static constexpr uint32_t DY_HI = DH_LO + 2 * PANEL;
-  static constexpr uint32_t DY_LO = DY_HI + PANEL;
-  static constexpr uint32_t FLOATS = DY_LO + PANEL;         // biases, w3 (fp32), scratch
-  static constexpr uint32_t N_FLOATS = D1 + D2 + 16 + 64 + 128 * 10;
-  static constexpr uint32_t BARS = FLOATS + N_FLOATS * 4;
-  static constexpr uint32_t TOTAL = BARS + 64;
-  static_assert((D1 * 128) % 1024 == 0 && (D2 * 128) % 1024 == 0, "panel alignment");
-};
-
-// TMEM column map
-constexpr uint32_t TC_L1 = 0, TC_L2 = 64, TC_L3 = 128, TC_DH2 = 160, TC_DH1 = 224, TC_DA = 288,
-                   TC_DB = 352, TC_DC = 416, TC_COLS = 512;
-
-// observation::to_vector of learner row r of a tile into the X0 panel (bin_packing.h:31-40).
-// One task = one 16-byte chunk = the 8 floats of two bins.
-__device__ __forceinline__ uint4 obs_chunk(const int8_t *__restrict__ st, int stride, int i, int B,
-                                           int chunk, float inv_w, float inv_h, int over_bin, bool valid) {
-  if (!valid)
-    return make_uint4(0, 0, 0, 0);
-  int iw = st[(size_t)(2 * B) * stride + i], ih = st[(size_t)(2 * B + 1) * stride + i];
-  uint32_t out[4];
+                                           uint32_t b_lo, uint32_t idesc, bool accumulate) {
+  constexpr uint32_t a_step = (A_MN ? umma::KSTEP_BYTES_MNMAJOR : umma::KSTEP_BYTES_KMAJOR) >> 4;
+  constexpr uint32_t b_step = (B_MN ? umma::KSTEP_BYTES_MNMAJOR : umma::KSTEP_BYTES_KMAJOR) >> 4;
+  constexpr uint32_t a_lbo = A_MN ? PANEL : 16, b_lbo = B_MN ? PANEL : 16;
+  const uint32_t ah0 = desc_lo(a_hi, a_lbo), al0 = desc_lo(a_lo, a_lbo);
+  const uint32_t bh0 = desc_lo(b_hi, b_lbo), bl0 = desc_lo(b_lo, b_lbo);
 #pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    int b = 2 * chunk + q;
-    int bw = st[(size_t)(2 * b) * stride + i], bh = st[(size_t)(2 * b + 1) * stride + i];
-    if (b == over_bin) {  // terminal state of a done step: bin[a] -= item (bin_packing.h:54-61)
-      bw -= iw;
-      bh -= ih;
-    }
-    __nv_bfloat16 x0 = __float2bfloat16_rn((float)bw * inv_w), x1 = __float2bfloat16_rn((float)bh * inv_h);
-    __nv_bfloat16 x2 = __float2bfloat16_rn((float)iw * inv_w), x3 = __float2bfloat16_rn((float)ih * inv_h);
-    out[2 * q] = (uint32_t)__bfloat16_as_ushort(x0) | ((uint32_t)__bfloat16_as_ushort(x1) << 16);
-    out[2 * q + 1] = (uint32_t)__bfloat16_as_ushort(x2) | ((uint32_t)__bfloat16_as_ushort(x3) << 16);
-  }
-  return make_uint4(out[0], out[1], out[2], out[3]);
-}
-
-// TMEM accumulator -> (+bias, relu) -> bf16 hi/lo panel. Returns the relu mask of this thread's
-// columns (bit j = column col0 + j was > 0).
-template <int D>
-__device__ __forceinline__ uint32_t epi_hidden_fwd(uint32_t tmem_acc, const tid_t &t,
-                                                   const float *__restrict__ bias, uint8_t *hi,
-                                                   uint8_t *lo) {
-  constexpr int DC = D / 2;
-  const int col0 = t.wg * DC;
-  float v[DC];
-  tmem_load<DC>(tmem_acc + t.lane_base + col0, v);
-  uint32_t mask = 0;
-#pragma unroll
-  for (int j = 0; j < DC; ++j) {
-    float x = v[j] + bias[col0 + j];
-    if (x > 0.f)
-      mask |= 1u << j;
-    else
-      x = 0.f;
-    v[j] = x;
-  }
-#pragma unroll
-  for (int c = 0; c < DC / 8; ++c) {
-    uint4 h, l;
-    umma::split8(&v[8 * c], h, l);
-    uint32_t off = umma::panel_chunk_off(t.row, col0 / 8 + c);
-    *reinterpret_cast<uint4 *>(hi + off) = h;
-    *reinterpret_cast<uint4 *>(lo + off) = l;
-  }
-  return mask;
-}
-// TMEM accumulator -> (. relu mask) -> bf16 hi/lo panel (input-gradient epilogue).
-template <int D>
-__device__ __forceinline__ void epi_hidden_bwd(uint32_t tmem_acc, const tid_t &t, uint32_t mask,
-                                               uint8_t *hi, uint8_t *lo) {
-  constexpr int DC = D / 2;
-  const int col0 = t.wg * DC;
-  float v[DC];
-  tmem_load<DC>(tmem_acc + t.lane_base + col0, v);
-#pragma unroll
-  for (int j = 0; j < DC; ++j)
-    v[j] = (mask >> j) & 1u ? v[j] : 0.f;
-#pragma unroll
-  for (int c = 0; c < DC / 8; ++c) {
-    uint4 h, l;
-    umma::split8(&v[8 * c], h, l);
-    uint32_t off = umma::panel_chunk_off(t.row, col0 / 8 + c);
-    *reinterpret_cast<uint4 *>(hi + off) = h;
-    *reinterpret_cast<uint4 *>(lo + off) = l;
+  for (int k = 0; k < KSTEPS; ++k) {
+    uint64_t ah = desc_lo_hi(ah0 + k * a_step), bh = desc_lo_hi(bh0 + k * b_step);
+    umma::mma_bf16(tmem_d, ah, bh, idesc, (k > 0 || accumulate) ? 1u : 0u);
+    if (B_LO)
+      umma::mma_bf16(tmem_d, ah, desc_lo_hi(bl0 + k * b_step), idesc, 1);
+    if (A_LO)
+      umma::mma_bf16(tmem_d, desc_lo_hi(al0 + k * a_step), bh, idesc, 1);
   }
 }
 
@@ -223,6 +164,239 @@ __device__ __forceinline__ void sync_after_smem_writes() {
   umma::fence_after_sync();
 }
 
+// ---------------------------------------------------------------------------------------------
+// Panel image: what fused_prep_kernel leaves in global memory for one net and every CTA copies
+// into shared memory (same offsets). Weight panels are forward-format hi/lo of (scale * W), swizzled.
+template <int D1, int D2>
+struct image_map {
+  static constexpr uint32_t W1_HI = 0, W1_LO = W1_HI + D1 * 128;
+  static constexpr uint32_t W2_HI = W1_LO + D1 * 128, W2_LO = W2_HI + D2 * 128;
+  static constexpr uint32_t W3_HI = W2_LO + D2 * 128, W3_LO = W3_HI + 16 * 128;
+  static constexpr uint32_t FLOATS = W3_LO + 16 * 128;
+  // floats: b1s[D1] (= sh1 b1), b2s[D2] (= sh2 b2), b3[16], w3[64] (fp32 value head), w3s[64]
+  // (= w3 / sh2), k[16] scale constants (see K_*)
+  static constexpr int F_B1 = 0, F_B2 = D1, F_B3 = D1 + D2, F_W3 = D1 + D2 + 16, F_W3S = F_W3 + 64,
+                       F_K = F_W3S + 64, N_FLOATS = F_K + 16;
+  static constexpr uint32_t BYTES = FLOATS + N_FLOATS * 4;
+  static_assert((D1 * 128) % 1024 == 0 && (D2 * 128) % 1024 == 0, "panel alignment");
+  static_assert(BYTES % 16 == 0, "image is copied in 16-byte words");
+};
+enum {
+  K_C1 = 0,     // sh1 / sw1          : y1 = acc1 * C1 + b1s   (= sh1 * pre-activation 1)
+  K_C2 = 1,     // sh2 / (sh1 sw2)    : y2 = acc2 * C2 + b2s
+  K_C3 = 2,     // 1 / (sh2 sw3)      : logits = acc3 * C3 + b3
+  K_ISW3 = 3,   // 1 / sw3            : dH2 = acc * ISW3
+  K_ISW2 = 4,   // 1 / sw2            : dH1 = acc * ISW2
+  K_ISH1 = 5,   // 1 / sh1            : dW2 = DA * ISH1
+  K_ISH2 = 6,   // 1 / sh2            : dW3 = DC * ISH2
+  K_B3V = 7     // b3[0] (value head bias)
+};
+
+__device__ __forceinline__ float block_max(float v, float *red) {
+  for (int o = 16; o > 0; o >>= 1)
+    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0)
+    red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float m = red[0];
+  for (int i = 1; i < (int)(blockDim.x >> 5); ++i)
+    m = fmaxf(m, red[i]);
+  return m;
+}
+// Largest power of two s with s * bound < 2^target_exp (bound > 0), exponent clamped.
+__device__ __forceinline__ float pow2_scale(float bound, int target_exp) {
+  if (!(bound > 0.f) || !isfinite(bound))
+    return 1.f;
+  int e = ilogbf(bound);  // 2^e <= bound < 2^(e+1)
+  int k = target_exp - 1 - e;
+  k = k > 60 ? 60 : (k < -60 ? -60 : k);
+  return ldexpf(1.f, k);
+}
+
+// fp32 [N][K] row-major -> forward-format hi / lo panels [rows_alloc][64] of (scale * W), zero padded.
+__device__ void stage_weight_f16(const float *__restrict__ W, int N, int K, int rows_alloc, float scale,
+                                 uint8_t *hi, uint8_t *lo) {
+  for (int c = threadIdx.x; c < rows_alloc * 8; c += blockDim.x) {
+    int row = c >> 3, chunk = c & 7;
+    float x[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int col = chunk * 8 + j;
+      x[j] = (row < N && col < K) ? W[(size_t)row * K + col] * scale : 0.f;
+    }
+    uint4 h, l;
+    split8<FWD_F16>(x, h, l);
+    uint32_t off = umma::panel_chunk_off(row, chunk);
+    *reinterpret_cast<uint4 *>(hi + off) = h;
+    *reinterpret_cast<uint4 *>(lo + off) = l;
+  }
+}
+
+// One CTA per net. Bounds (FWD_F16 scaling only): |obs| <= 1 (bins and items never exceed the capacity), so
+// |H1_j| <= |b1_j| + sum_k |W1_jk| =: h1max and |H2_j| <= |b2_j| + h1max sum_k |W2_jk|.
+template <int D0, int D1, int D2>
+__device__ void prep_body(const float *gparams, const net3 &net, uint8_t *__restrict__ image, float *params) {
+  using IM = image_map<D1, D2>;
+  __shared__ float red[8];
+  for (int i = threadIdx.x; i < net.n_params; i += blockDim.x)
+    params[i] = gparams[i];
+  __syncthreads();
+  const float *W1 = params + net.o_w1, *W2 = params + net.o_w2, *W3 = params + net.o_w3;
+  float sw1 = 1.f, sw2 = 1.f, sw3 = 1.f, sh1 = 1.f, sh2 = 1.f;
+  if (FWD_F16) {
+    float m1 = 0.f, m2 = 0.f, m3 = 0.f;
+    for (int i = threadIdx.x; i < D1 * D0; i += blockDim.x) m1 = fmaxf(m1, fabsf(W1[i]));
+    for (int i = threadIdx.x; i < D2 * D1; i += blockDim.x) m2 = fmaxf(m2, fabsf(W2[i]));
+    for (int i = threadIdx.x; i < net.d3 * D2; i += blockDim.x) m3 = fmaxf(m3, fabsf(W3[i]));
+    m1 = block_max(m1, red);
+    m2 = block_max(m2, red);
+    m3 = block_max(m3, red);
+    float h = 0.f;
+    if (threadIdx.x < D1) {
+      float s = fabsf(params[net.o_b1 + threadIdx.x]);
+      for (int k = 0; k < D0; ++k) s += fabsf(W1[threadIdx.x * D0 + k]);
+      h = s;
+    }
+    const float h1max = block_max(h, red);
+    h = 0.f;
+    if (threadIdx.x < D2) {
+      float s = 0.f;
+      for (int k = 0; k < D1; ++k) s += fabsf(W2[threadIdx.x * D1 + k]);
+      h = fabsf(params[net.o_b2 + threadIdx.x]) + h1max * s;
+    }
+    const float h2max = block_max(h, red);
+    // weights -> [512, 1024), activations -> < 2^14: hi and lo halves of everything that matters
+    // are normal FP16 numbers and nothing can overflow (max FP16 = 65504).
+    sw1 = pow2_scale(m1, 10), sw2 = pow2_scale(m2, 10), sw3 = pow2_scale(m3, 10);
+    sh1 = pow2_scale(h1max, 14), sh2 = pow2_scale(h2max, 14);
+  }
+  stage_weight_f16(W1, D1, D0, D1, sw1, image + IM::W1_HI, image + IM::W1_LO);
+  stage_weight_f16(W2, D2, D1, D2, sw2, image + IM::W2_HI, image + IM::W2_LO);
+  stage_weight_f16(W3, net.d3, D2, 16, sw3, image + IM::W3_HI, image + IM::W3_LO);
+  float *fl = reinterpret_cast<float *>(image + IM::FLOATS);
+  for (int i = threadIdx.x; i < D1; i += blockDim.x) fl[IM::F_B1 + i] = params[net.o_b1 + i] * sh1;
+  for (int i = threadIdx.x; i < D2; i += blockDim.x) fl[IM::F_B2 + i] = params[net.o_b2 + i] * sh2;
+  for (int i = threadIdx.x; i < 16; i += blockDim.x) fl[IM::F_B3 + i] = i < net.d3 ? params[net.o_b3 + i] : 0.f;
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) {
+    float w = i < D2 ? W3[i] : 0.f;  // row 0 of W3 (value head)
+    fl[IM::F_W3 + i] = w;
+    fl[IM::F_W3S + i] = w / sh2;
+  }
+  if (threadIdx.x == 0) {
+    float *k = fl + IM::F_K;
+    k[K_C1] = sh1 / sw1;
+    k[K_C2] = sh2 / (sh1 * sw2);
+    k[K_C3] = 1.f / (sh2 * sw3);
+    k[K_ISW3] = 1.f / sw3;
+    k[K_ISW2] = 1.f / sw2;
+    k[K_ISH1] = 1.f / sh1;
+    k[K_ISH2] = 1.f / sh2;
+    k[K_B3V] = params[net.o_b3];
+    for (int i = 8; i < 16; ++i) k[i] = 0.f;
+  }
+}
+template <int D0, int D1, int D2>
+__global__ void __launch_bounds__(256) fused_prep_kernel(const float *__restrict__ gparams, net3 net,
+                                                        uint8_t *__restrict__ image) {
+  extern __shared__ float prep_params[];  // the whole flat parameter vector (<= 27 KB)
+  prep_body<D0, D1, D2>(gparams, net, image, prep_params);
+}
+
+// Copies the panel image into shared memory (same offsets) -- 16-byte words, all threads.
+__device__ __forceinline__ void load_image(uint8_t *smem, const uint8_t *__restrict__ image, uint32_t bytes) {
+  const uint4 *src = reinterpret_cast<const uint4 *>(image);
+  uint4 *dst = reinterpret_cast<uint4 *>(smem);
+  for (uint32_t i = threadIdx.x; i < bytes / 16; i += blockDim.x)
+    dst[i] = __ldg(src + i);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Shared-memory map of the learner kernels: the image first, then the activation panels.
+template <int D1, int D2>
+struct smem_map {
+  using IM = image_map<D1, D2>;
+  static constexpr uint32_t X0 = (IM::BYTES + 1023) / 1024 * 1024;  // hi only (k/cap is exact in 16 bits)
+  static constexpr uint32_t H_HI = X0 + PANEL;                      // [H1 | H2]   (forward format)
+  static constexpr uint32_t H_LO = H_HI + 2 * PANEL;
+  static constexpr uint32_t DH_HI = H_LO + 2 * PANEL;               // [dH1 | dH2] (bf16)
+  static constexpr uint32_t DH_LO = DH_HI + 2 * PANEL;
+  static constexpr uint32_t DY_HI = DH_LO + 2 * PANEL;              // bf16
+  static constexpr uint32_t DY_LO = DY_HI + PANEL;
+  static constexpr uint32_t SCRATCH = DY_LO + PANEL;                // 8 * TILE floats
+  static constexpr uint32_t RAW_S = SCRATCH + 8 * TILE * 4;         // int8 [18][128] start states
+  static constexpr uint32_t RAW_E = RAW_S + 18 * TILE;              // int8 [18][128] end states
+  static constexpr uint32_t BARS = RAW_E + 18 * TILE;
+  static constexpr uint32_t TOTAL = BARS + 64;
+  static_assert(TOTAL + 1024 <= 232448, "exceeds the 227 KB shared memory of an SM");
+};
+
+// TMEM column map (learner kernels)
+constexpr uint32_t TC_L1 = 0, TC_L2 = 64, TC_L3 = 128, TC_DH2 = 160, TC_DH1 = 224, TC_DA = 288,
+                   TC_DB = 352, TC_DC = 416, TC_COLS = 512;
+
+// TMEM accumulator -> y = acc * c + bias_scaled, relu -> forward-format hi/lo panel. Returns the relu mask
+// of this thread's columns (bit j = column col0 + j was > 0); optionally hands y back.
+template <int D, bool WRITE_PANEL, bool KEEP>
+__device__ __forceinline__ uint32_t epi_hidden_fwd(uint32_t tmem_acc, const tid_t &t, float c,
+                                                   const float *__restrict__ bias, uint8_t *hi, uint8_t *lo,
+                                                   float *keep) {
+  constexpr int DC = D / 2;
+  const int col0 = t.wg * DC;
+  float v[DC];
+  tmem_load<DC>(tmem_acc + t.lane_base + col0, v);
+  uint32_t mask = 0;
+#pragma unroll
+  for (int j4 = 0; j4 < DC; j4 += 4) {
+    float4 b = *reinterpret_cast<const float4 *>(bias + col0 + j4);
+    float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float x = fmaf(v[j4 + q], c, bb[q]);
+      if (x > 0.f)
+        mask |= 1u << (j4 + q);
+      else
+        x = 0.f;
+      v[j4 + q] = x;
+    }
+  }
+  if (KEEP) {
+#pragma unroll
+    for (int j = 0; j < DC; ++j)
+      keep[j] = v[j];
+  }
+  if (WRITE_PANEL) {
+#pragma unroll
+    for (int cc = 0; cc < DC / 8; ++cc) {
+      uint4 h, l;
+      split8<FWD_F16>(&v[8 * cc], h, l);
+      uint32_t off = umma::panel_chunk_off(t.row, col0 / 8 + cc);
+      *reinterpret_cast<uint4 *>(hi + off) = h;
+      *reinterpret_cast<uint4 *>(lo + off) = l;
+    }
+  }
+  return mask;
+}
+// TMEM accumulator -> (* c, . relu mask) -> BF16 hi/lo panel (input-gradient epilogue).
+template <int D>
+__device__ __forceinline__ void epi_hidden_bwd(uint32_t tmem_acc, const tid_t &t, float c, uint32_t mask,
+                                               uint8_t *hi, uint8_t *lo) {
+  constexpr int DC = D / 2;
+  const int col0 = t.wg * DC;
+  float v[DC];
+  tmem_load<DC>(tmem_acc + t.lane_base + col0, v);
+#pragma unroll
+  for (int j = 0; j < DC; ++j)
+    v[j] = (mask >> j) & 1u ? v[j] * c : 0.f;
+#pragma unroll
+  for (int cc = 0; cc < DC / 8; ++cc) {
+    uint4 h, l;
+    split8<false>(&v[8 * cc], h, l);
+    uint32_t off = umma::panel_chunk_off(t.row, col0 / 8 + cc);
+    *reinterpret_cast<uint4 *>(hi + off) = h;
+    *reinterpret_cast<uint4 *>(lo + off) = l;
+  }
+}
 
 // Per-CTA context of the fused kernels.
 struct tile_ctx {
@@ -238,154 +412,197 @@ struct tile_ctx {
   }
 };
 
-// As epi_hidden_fwd, but also hands the fp32 activations of this thread's columns back.
-template <int D, bool WRITE_PANEL>
-__device__ __forceinline__ uint32_t epi_hidden_fwd_keep(uint32_t tmem_acc, const tid_t &t,
-                                                        const float *__restrict__ bias, uint8_t *hi,
-                                                        uint8_t *lo, float (&v)[D / 2]) {
-  constexpr int DC = D / 2;
-  const int col0 = t.wg * DC;
-  tmem_load<DC>(tmem_acc + t.lane_base + col0, v);
-  uint32_t mask = 0;
-#pragma unroll
-  for (int j = 0; j < DC; ++j) {
-    float x = v[j] + bias[col0 + j];
-    if (x > 0.f)
-      mask |= 1u << j;
-    else
-      x = 0.f;
-    v[j] = x;
-  }
-  if (WRITE_PANEL) {
-#pragma unroll
-    for (int c = 0; c < DC / 8; ++c) {
-      uint4 h, l;
-      umma::split8(&v[8 * c], h, l);
-      uint32_t off = umma::panel_chunk_off(t.row, col0 / 8 + c);
-      *reinterpret_cast<uint4 *>(hi + off) = h;
-      *reinterpret_cast<uint4 *>(lo + off) = l;
-    }
-  }
-  return mask;
-}
+// idesc shorthands: F = forward-format operand, B = bf16 operand; K = K-major, M = MN-major
+template <int N> struct ID {
+  static constexpr int FB = FWD_F16 ? 0 : 1;  // format code of the forward operands
+  static constexpr uint32_t FK_FK = make_idesc(128, N, FB, FB, 0, 0);  // forward: A fwd K, B fwd K
+  static constexpr uint32_t BK_FM = make_idesc(128, N, 1, FB, 0, 1);   // dX: A bf16 K-major, B fwd MN-major
+  static constexpr uint32_t BM_FM = make_idesc(128, N, 1, FB, 1, 1);   // dW: A = dH^T (bf16), B = H / X0 (fwd)
+  static constexpr uint32_t FM_BM = make_idesc(128, N, FB, 1, 1, 1);   // dW3^T: A = H^T (fwd), B = dY (bf16)
+};
 
 // Layers 1 and 2 of a tile whose X0 panel is staged and synchronised. Leaves H1 (and, if
-// WRITE_H2, H2) panels written but NOT yet synchronised.
-template <int D0, int D1, int D2, bool WRITE_H2>
-__device__ __forceinline__ void fwd_hidden(tile_ctx &c, const float *b1, const float *b2,
-                                           uint32_t &mask1, uint32_t &mask2, float (&h2)[D2 / 2]) {
-  using SM = smem_map<D1, D2>;
-  constexpr uint32_t ID_L1 = umma::make_idesc_bf16(128, D1, 0, 0);
-  constexpr uint32_t ID_L2 = umma::make_idesc_bf16(128, D2, 0, 0);
-  if (threadIdx.x == 0) {
-    issue_gemm(c.tmem + TC_L1, c.sbase + SM::X0, 0, c.sbase + SM::W1_HI, c.sbase + SM::W1_LO, D0 / 16,
-               false, false, ID_L1, false);
+// WRITE_H2, H2) panels written but NOT yet synchronised. y2 = sh2 * H2 of this thread's columns.
+template <int D0, int D1, int D2, typename SM, uint32_t TL1, uint32_t TL2, bool H2_IN_PLACE, bool WRITE_H2>
+__device__ __forceinline__ void fwd_hidden(tile_ctx &c, const float *fl, uint32_t &mask1, uint32_t &mask2,
+                                           float (&y2)[D2 / 2]) {
+  using IM = image_map<D1, D2>;
+  const float *b1s = fl + IM::F_B1, *b2s = fl + IM::F_B2, *k = fl + IM::F_K;
+  constexpr uint32_t H2_OFF = H2_IN_PLACE ? 0 : PANEL;
+  if (mma_thread(c.t)) {
+    issue_gemm<D0 / 16, false, false, false, true>(c.tmem + TL1, c.sbase + SM::X0, 0, c.sbase + IM::W1_HI,
+                                                   c.sbase + IM::W1_LO, ID<D1>::FK_FK, false);
     umma::commit(c.bar);
   }
   c.wait();
-  mask1 = epi_hidden_fwd<D1>(c.tmem + TC_L1, c.t, b1, c.smem + SM::H_HI, c.smem + SM::H_LO);
+  mask1 = epi_hidden_fwd<D1, true, false>(c.tmem + TL1, c.t, k[K_C1], b1s, c.smem + SM::H_HI, c.smem + SM::H_LO,
+                                          nullptr);
   sync_after_smem_writes();
-  if (threadIdx.x == 0) {
-    issue_gemm(c.tmem + TC_L2, c.sbase + SM::H_HI, c.sbase + SM::H_LO, c.sbase + SM::W2_HI,
-               c.sbase + SM::W2_LO, D1 / 16, false, false, ID_L2, false);
+  if (mma_thread(c.t)) {
+    issue_gemm<D1 / 16, false, false, true, true>(c.tmem + TL2, c.sbase + SM::H_HI, c.sbase + SM::H_LO,
+                                                  c.sbase + IM::W2_HI, c.sbase + IM::W2_LO, ID<D2>::FK_FK, false);
     umma::commit(c.bar);
   }
   c.wait();
-  mask2 = epi_hidden_fwd_keep<D2, WRITE_H2>(c.tmem + TC_L2, c.t, b2, c.smem + SM::H_HI + PANEL,
-                                            c.smem + SM::H_LO + PANEL, h2);
+  mask2 = epi_hidden_fwd<D2, WRITE_H2, true>(c.tmem + TL2, c.t, k[K_C2], b2s, c.smem + SM::H_HI + H2_OFF,
+                                             c.smem + SM::H_LO + H2_OFF, y2);
 }
 
-// Value head (D2 -> 1) in registers: each row is held by two threads (one per warpgroup, D2/2
-// columns each); partial dot products meet in shared memory. Contains one __syncthreads.
+// Value head (D2 -> 1) in fp32 registers: each row is held by two threads (one per warpgroup,
+// D2/2 columns each); partial dot products meet in shared memory. Contains one __syncthreads.
 template <int D2>
-__device__ __forceinline__ float value_head(const tid_t &t, const float (&h2)[D2 / 2],
-                                            const float *__restrict__ w3, float b3, float *vpart) {
+__device__ __forceinline__ float value_head(const tid_t &t, const float (&y2)[D2 / 2],
+                                            const float *__restrict__ w3s, float b3, float *vpart) {
   constexpr int DC = D2 / 2;
   float s = 0.f;
 #pragma unroll
   for (int j = 0; j < DC; ++j)
-    s = fmaf(h2[j], w3[t.wg * DC + j], s);
+    s = fmaf(y2[j], w3s[t.wg * DC + j], s);
   vpart[t.wg * TILE + t.row] = s;
   __syncthreads();
   return vpart[t.row] + vpart[TILE + t.row] + b3;
 }
 
-// Common one-time setup of the learner / rollout kernels.
-template <int D0, int D1, int D2>
-__device__ __forceinline__ void setup_common(tile_ctx &c, uint8_t *smem, const float *params, const net3 &net,
-                                             float *b1, float *b2, uint32_t *tmem_slot, uint64_t *bar) {
-  using SM = smem_map<D1, D2>;
+// Common one-time setup: TMEM, barrier, image -> smem, zeroed panels, ones column of X0.
+template <int D0, int D1, int D2, typename SM>
+__device__ __forceinline__ void setup_common(tile_ctx &c, uint8_t *smem, const uint8_t *image, uint32_t zero_from,
+                                             uint32_t zero_bytes_n, uint32_t tmem_cols, uint32_t *tmem_slot,
+                                             uint64_t *bar) {
+  using IM = image_map<D1, D2>;
   c.smem = smem;
   c.sbase = umma::smem_u32(smem);
   c.bar = bar;
   c.phase = 0;
   c.t = thread_id();
-  if (threadIdx.x < 32)
-    umma::tmem_alloc(tmem_slot, TC_COLS);
+  if (c.t.warp == 0)
+    umma::tmem_alloc(tmem_slot, tmem_cols);
   if (threadIdx.x == 0) {
     umma::mbar_init(bar, 1);
     umma::fence_mbar_init();
   }
-  stage_weight(params + net.o_w1, D1, D0, D1, smem + SM::W1_HI, smem + SM::W1_LO);
-  stage_weight(params + net.o_w2, D2, D1, D2, smem + SM::W2_HI, smem + SM::W2_LO);
-  for (int i = threadIdx.x; i < D1; i += blockDim.x) b1[i] = params[net.o_b1 + i];
-  for (int i = threadIdx.x; i < D2; i += blockDim.x) b2[i] = params[net.o_b2 + i];
-  zero_bytes(smem + SM::X0, PANEL);
-  zero_bytes(smem + SM::H_HI, 4 * PANEL);
-  zero_bytes(smem + SM::DH_HI, 4 * PANEL);
-  zero_bytes(smem + SM::DY_HI, 2 * PANEL);
+  load_image(smem, image, IM::BYTES);
+  zero_bytes(smem + zero_from, zero_bytes_n);
   __syncthreads();
+  // ones column (col D0) of the X0 panel: [dH1|dH2]^T . 1 = bias gradients for free
   if (threadIdx.x < TILE)
-    *reinterpret_cast<uint16_t *>(smem + SM::X0 + umma::panel_off(threadIdx.x, D0)) = 0x3F80;  // bf16 1.0
+    *reinterpret_cast<uint16_t *>(smem + SM::X0 + umma::panel_off(threadIdx.x, D0)) = ONE_FWD;  // 1.0
+  sync_after_smem_writes();
+  c.tmem = *tmem_slot;
 }
 
-// Stage the X0 panel of a learner tile (rows = t * E + e). end_rows: observation of the END state
-// of step (t, e): overflowed terminal state when done, live env state at the rollout's last step,
-// zeros (unused) otherwise. Global loads happen before `pre_store` (a wait) runs.
+// Learner rows of a tile (row = t * E + e). end_rows: observation of the END state of step (t, e):
+// overflowed terminal state when done, live env state at the rollout's last step, zeros (unused)
+// otherwise.
 struct learner_rows {
   const int8_t *rec_state, *live_state;
   const uint8_t *rec_action, *rec_done;
   int n, stride, T, E, B;
   float inv_w, inv_h;
 };
-template <typename F>
-__device__ __forceinline__ void stage_x0(uint8_t *x0, const learner_rows &L, int tile, bool end_rows,
-                                         F pre_store) {
-  const int P = 2 * L.B + 2, cpr = L.B / 2;
-  uint4 xc[2];
-  int xrow[2], xchunk[2];
+// Staging of a tile's observations. The int8 state planes of the tile's rows are moved
+// global -> registers (prefetch, one tile ahead) -> shared memory RAW [18][128] (plane, row) ->
+// observation::to_vector (bin_packing.h:31-40) into the X0 panel. With E % 16 == 0 each thread
+// moves ONE 16-byte unit (plane, step, 16 environments); nothing consumes a loaded value before
+// the next tile starts, so the loads stay in flight behind the current tile's math.
+struct x0_pref {
+  uint4 rs, rl;   // start-state unit, live-state unit (end rows of the rollout's last step)
+  int done, act;  // of this thread's row (threads < 128, end rows only)
+};
+template <bool END_ROWS>
+__device__ __forceinline__ void load_x0(const learner_rows &L, int tile, x0_pref &x) {
+  const int P = 2 * L.B + 2;
+  x.rs = x.rl = make_uint4(0, 0, 0, 0);
+  x.done = x.act = 0;
+  if (L.E % 16 == 0) {
+    const int upr = L.E / 16;  // units per (step, plane)
+    const int u = threadIdx.x;
+    if (u < L.T * P * upr) {
+      int h = u % upr, plane = (u / upr) % P, tt = u / (upr * P);
+      int i = tile * L.E + 16 * h;
+      if (i < L.stride) {
+        x.rs = *reinterpret_cast<const uint4 *>(L.rec_state + ((size_t)tt * P + plane) * L.stride + i);
+        if (END_ROWS && tt == L.T - 1)
+          x.rl = *reinterpret_cast<const uint4 *>(L.live_state + (size_t)plane * L.stride + i);
+      }
+    }
+  }
+  if (END_ROWS && threadIdx.x < TILE) {
+    int tt = threadIdx.x / L.E, e = threadIdx.x % L.E, i = tile * L.E + e;
+    if (tt < L.T && i < L.n) {
+      size_t k = (size_t)tt * L.n + i;
+      x.done = L.rec_done[k];
+      x.act = L.rec_action[k];
+    }
+  }
+}
+// Registers -> RAW planes in shared memory (followed by a __syncthreads of the caller).
+template <bool END_ROWS>
+__device__ __forceinline__ void stash_x0(int8_t *raw_s, int8_t *raw_e, const learner_rows &L, int tile,
+                                         const x0_pref &x) {
+  const int P = 2 * L.B + 2;
+  if (L.E % 16 == 0) {
+    const int upr = L.E / 16;
+    const int u = threadIdx.x;
+    if (u < L.T * P * upr) {
+      int h = u % upr, plane = (u / upr) % P, tt = u / (upr * P);
+      int off = plane * TILE + tt * L.E + 16 * h;
+      *reinterpret_cast<uint4 *>(raw_s + off) = x.rs;
+      if (END_ROWS)
+        *reinterpret_cast<uint4 *>(raw_e + off) = tt == L.T - 1 ? x.rl : x.rs;
+    }
+  } else {  // generic step counts: byte loads, no prefetch
+    for (int u = threadIdx.x; u < P * TILE; u += blockDim.x) {
+      int plane = u / TILE, r = u % TILE;
+      int tt = r / L.E, e = r % L.E, i = tile * L.E + e;
+      int8_t vs = 0, ve = 0;
+      if (tt < L.T && i < L.n) {
+        vs = L.rec_state[((size_t)tt * P + plane) * L.stride + i];
+        ve = (END_ROWS && tt == L.T - 1) ? L.live_state[(size_t)plane * L.stride + i] : vs;
+      }
+      raw_s[u] = vs;
+      if (END_ROWS)
+        raw_e[u] = ve;
+    }
+  }
+}
+// END state of step (t, e) in RAW_E (after stash_x0 + __syncthreads): overflowed terminal state
+// when done (bin[a] -= item, item kept: bin_packing.h:54-61), live env state at the rollout's last
+// step (already there), zeros (row unused) otherwise. One thread per row.
+__device__ __forceinline__ void fix_end_rows(int8_t *raw_e, const learner_rows &L, const x0_pref &x) {
+  if (threadIdx.x < TILE) {
+    const int r = threadIdx.x, tt = r / L.E, P = 2 * L.B + 2;
+    if (x.done) {
+      int a = x.act;
+      raw_e[(2 * a) * TILE + r] -= raw_e[(2 * L.B) * TILE + r];
+      raw_e[(2 * a + 1) * TILE + r] -= raw_e[(2 * L.B + 1) * TILE + r];
+    } else if (tt != L.T - 1) {
+      for (int q = 0; q < P; ++q)
+        raw_e[q * TILE + r] = 0;
+    }
+  }
+}
+// RAW planes -> X0 panel: two 16-byte chunks (two bins each) per thread.
+__device__ __forceinline__ void encode_x0(uint8_t *x0, const int8_t *raw, int B, float inv_w, float inv_h) {
+  const int cpr = B / 2;
 #pragma unroll
   for (int q = 0; q < 2; ++q) {
     int task = threadIdx.x + q * 256;
-    int r = task / cpr, c = task % cpr;
-    bool in = task < TILE * cpr;
-    int tt = r / L.E, e = r % L.E;
-    int i = tile * L.E + e;
-    bool valid = in && tt < L.T && i < L.n;
-    const int8_t *src = L.rec_state + (size_t)tt * P * L.stride;
-    int over_bin = -1;
-    if (end_rows && valid) {
-      size_t k = (size_t)tt * L.n + i;
-      if (L.rec_done[k])
-        over_bin = L.rec_action[k];
-      else if (tt == L.T - 1)
-        src = L.live_state;
-      else
-        valid = false;
-    }
-    xc[q] = obs_chunk(src, L.stride, i, L.B, c, L.inv_w, L.inv_h, over_bin, valid);
-    xrow[q] = in ? r : -1;
-    xchunk[q] = c;
-  }
-  pre_store();
+    if (task >= TILE * cpr)
+      continue;
+    int row = task % TILE, ch = task / TILE;  // a warp = 32 consecutive rows: conflict-free LDS / STS
+    const uint32_t it = pack2_fwd((float)raw[(2 * B) * TILE + row] * inv_w, (float)raw[(2 * B + 1) * TILE + row] * inv_h);
+    uint32_t out[2];
 #pragma unroll
-  for (int q = 0; q < 2; ++q)
-    if (xrow[q] >= 0)
-      *reinterpret_cast<uint4 *>(x0 + umma::panel_chunk_off(xrow[q], xchunk[q])) = xc[q];
+    for (int h = 0; h < 2; ++h) {
+      int b = 2 * ch + h;
+      out[h] = pack2_fwd((float)raw[(2 * b) * TILE + row] * inv_w, (float)raw[(2 * b + 1) * TILE + row] * inv_h);
+    }
+    *reinterpret_cast<uint4 *>(x0 + umma::panel_chunk_off(row, ch)) = make_uint4(out[0], it, out[1], it);
+  }
 }
 
 struct critic_args {
-  const float *params;
+  const uint8_t *image;
   net3 net;
   learner_rows rows;
   int n_tiles;
@@ -402,27 +619,22 @@ struct critic_args {
 template <int D0, int D1, int D2>
 __global__ void __launch_bounds__(256, 1) fused_critic_step_kernel(critic_args a) {
   using SM = smem_map<D1, D2>;
+  using IM = image_map<D1, D2>;
   constexpr int DC2 = D2 / 2;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  float *fl = reinterpret_cast<float *>(smem + SM::FLOATS);
-  float *b1 = fl, *b2 = fl + D1, *w3 = fl + D1 + D2 + 16, *vpart = w3 + 64, *ve = vpart + 2 * TILE,
-        *vs = ve + TILE, *dys = vs + TILE;
+  const float *fl = reinterpret_cast<const float *>(smem + IM::FLOATS);
+  const float *w3 = fl + IM::F_W3, *w3s = fl + IM::F_W3S, *kk = fl + IM::F_K;
+  float *scr = reinterpret_cast<float *>(smem + SM::SCRATCH);
+  float *vpart = scr, *ve = scr + 2 * TILE, *vs = scr + 3 * TILE;
   uint64_t *bar = reinterpret_cast<uint64_t *>(smem + SM::BARS);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + SM::BARS + 16);
   const net3 net = a.net;
   tile_ctx c;
-  setup_common<D0, D1, D2>(c, smem, a.params, net, b1, b2, tmem_slot, bar);
-  for (int i = threadIdx.x; i < D2; i += blockDim.x) w3[i] = a.params[net.o_w3 + i];
-  const float b3 = a.params[net.o_b3];
-  sync_after_smem_writes();
-  c.tmem = *tmem_slot;
+  setup_common<D0, D1, D2, SM>(c, smem, a.image, SM::X0, SM::SCRATCH - SM::X0, TC_COLS, tmem_slot, bar);
+  const float b3 = kk[K_B3V];
   const tid_t t = c.t;
   const learner_rows &L = a.rows;
-
-  constexpr uint32_t ID_DH1 = umma::make_idesc_bf16(128, D1, 0, 1);
-  constexpr uint32_t ID_DA = umma::make_idesc_bf16(128, 64, 1, 1);
-  constexpr uint32_t ID_DB = umma::make_idesc_bf16(128, D0 + 16, 1, 1);
 
   bool dw_pending = false, first_tile = true;
   float dw3[DC2];
@@ -431,39 +643,49 @@ __global__ void __launch_bounds__(256, 1) fused_critic_step_kernel(critic_args a
     dw3[j] = 0.f;
   float db3 = 0.f;
 
+  int8_t *raw_s = reinterpret_cast<int8_t *>(smem + SM::RAW_S), *raw_e = reinterpret_cast<int8_t *>(smem + SM::RAW_E);
+  x0_pref xp;
+  if ((int)blockIdx.x < a.n_tiles)
+    load_x0<true>(L, blockIdx.x, xp);
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     uint32_t m1, m2;
-    float h2[DC2];
+    float y2[DC2];
     // ---- pass 1: V of the end rows
-    stage_x0(smem + SM::X0, L, tile, true, [&]() {
-      if (dw_pending) {
-        c.wait();
-        dw_pending = false;
-      }
-    });
+    if (dw_pending) {  // the previous tile's dW GEMMs still read the panels
+      c.wait();
+      dw_pending = false;
+    }
+    stash_x0<true>(raw_s, raw_e, L, tile, xp);
+    __syncthreads();
+    fix_end_rows(raw_e, L, xp);
+    __syncthreads();
+    encode_x0(smem + SM::X0, raw_e, L.B, L.inv_w, L.inv_h);
     sync_after_smem_writes();
-    fwd_hidden<D0, D1, D2, false>(c, b1, b2, m1, m2, h2);
-    float v_end = value_head<D2>(t, h2, w3, b3, vpart);
+    // row data of this tile (used after the forward passes): issue the loads now
+    const int tt = t.row / L.E, e = t.row % L.E;
+    const int i = tile * L.E + e;
+    const bool valid = tt < L.T && i < L.n;
+    const size_t k = (size_t)tt * L.n + i;
+    const int d = valid ? L.rec_done[k] : 0;
+    fwd_hidden<D0, D1, D2, SM, TC_L1, TC_L2, false, false>(c, fl, m1, m2, y2);
+    float v_end = value_head<D2>(t, y2, w3s, b3, vpart);
     if (t.wg == 0)
       ve[t.row] = v_end;
-    __syncthreads();
     // ---- pass 2: start rows, activations kept
-    stage_x0(smem + SM::X0, L, tile, false, []() {});
+    encode_x0(smem + SM::X0, raw_s, L.B, L.inv_w, L.inv_h);
     sync_after_smem_writes();
-    fwd_hidden<D0, D1, D2, true>(c, b1, b2, m1, m2, h2);
-    float v = value_head<D2>(t, h2, w3, b3, vpart);
+    const int next = tile + gridDim.x;
+    if (next < a.n_tiles)  // prefetch the next tile's state bytes behind this tile's math
+      load_x0<true>(L, next, xp);
+    fwd_hidden<D0, D1, D2, SM, TC_L1, TC_L2, false, false>(c, fl, m1, m2, y2);
+    float v = value_head<D2>(t, y2, w3s, b3, vpart);
     if (t.wg == 0)
       vs[t.row] = v;
     __syncthreads();
     // ---- targets and dY = V - target (square_loss_grad, nn.h:548-550)
     {
-      int tt = t.row / L.E, e = t.row % L.E;
-      int i = tile * L.E + e;
-      bool valid = tt < L.T && i < L.n;
       float dy = 0.f;
       if (valid) {
-        size_t k = (size_t)tt * L.n + i;
-        int d = L.rec_done[k];
         bool ends = d || tt == L.T - 1;
         float vn = ends ? ve[t.row] : vs[t.row + L.E];
         float tgt = (d ? 0.f : 1.f) + a.gamma * vn;  // not masked at terminals (quirk 6)
@@ -476,34 +698,35 @@ __global__ void __launch_bounds__(256, 1) fused_critic_step_kernel(critic_args a
 #pragma unroll
       for (int j = 0; j < DC2; ++j) {
         g[j] = (m2 >> j) & 1u ? dy * w3[t.wg * DC2 + j] : 0.f;
-        dw3[j] = fmaf(dy, h2[j], dw3[j]);
+        dw3[j] = fmaf(dy, y2[j], dw3[j]);
       }
       if (t.wg == 0)
         db3 += dy;
 #pragma unroll
       for (int cc = 0; cc < DC2 / 8; ++cc) {
         uint4 h, l;
-        umma::split8(&g[8 * cc], h, l);
+        split8<false>(&g[8 * cc], h, l);
         uint32_t off = umma::panel_chunk_off(t.row, (t.wg * DC2) / 8 + cc);
         *reinterpret_cast<uint4 *>(smem + SM::DH_HI + PANEL + off) = h;
         *reinterpret_cast<uint4 *>(smem + SM::DH_LO + PANEL + off) = l;
       }
     }
     sync_after_smem_writes();
-    // ---- dH1 = dH2 . W2, relu mask
-    if (threadIdx.x == 0) {
-      issue_gemm(c.tmem + TC_DH1, c.sbase + SM::DH_HI + PANEL, c.sbase + SM::DH_LO + PANEL,
-                 c.sbase + SM::W2_HI, c.sbase + SM::W2_LO, D2 / 16, false, true, ID_DH1, false);
+    // ---- dH1 = dH2 . W2, relu mask; dW2 += dH2^T . H1 runs behind the dH1 epilogue
+    if (mma_thread(t)) {
+      issue_gemm<D2 / 16, false, true, true, true>(c.tmem + TC_DH1, c.sbase + SM::DH_HI + PANEL,
+                                                   c.sbase + SM::DH_LO + PANEL, c.sbase + IM::W2_HI,
+                                                   c.sbase + IM::W2_LO, ID<D1>::BK_FM, false);
       umma::commit(c.bar);
+      issue_gemm<8, true, true, true, true>(c.tmem + TC_DA, c.sbase + SM::DH_HI, c.sbase + SM::DH_LO,
+                                            c.sbase + SM::H_HI, c.sbase + SM::H_LO, ID<64>::BM_FM, !first_tile);
     }
     c.wait();
-    epi_hidden_bwd<D1>(c.tmem + TC_DH1, t, m1, smem + SM::DH_HI, smem + SM::DH_LO);
+    epi_hidden_bwd<D1>(c.tmem + TC_DH1, t, kk[K_ISW2], m1, smem + SM::DH_HI, smem + SM::DH_LO);
     sync_after_smem_writes();
-    if (threadIdx.x == 0) {
-      issue_gemm(c.tmem + TC_DA, c.sbase + SM::DH_HI, c.sbase + SM::DH_LO, c.sbase + SM::H_HI,
-                 c.sbase + SM::H_LO, 8, true, true, ID_DA, !first_tile);
-      issue_gemm(c.tmem + TC_DB, c.sbase + SM::DH_HI, c.sbase + SM::DH_LO, c.sbase + SM::X0, 0, 8, true,
-                 true, ID_DB, !first_tile);
+    if (mma_thread(t)) {
+      issue_gemm<8, true, true, true, false>(c.tmem + TC_DB, c.sbase + SM::DH_HI, c.sbase + SM::DH_LO,
+                                             c.sbase + SM::X0, 0, ID<D0 + 16>::BM_FM, !first_tile);
       umma::commit(c.bar);
     }
     dw_pending = true;
@@ -513,106 +736,145 @@ __global__ void __launch_bounds__(256, 1) fused_critic_step_kernel(critic_args a
   float *part = a.partials + (size_t)blockIdx.x * net.n_params;
   if (dw_pending)
     c.wait();
-  {
-    constexpr int DC = D1 / 2;
-    float v[DC];
-    tmem_load<DC>(c.tmem + TC_DA + t.lane_base + t.wg * DC, v);
-    int nrow = t.row - 64;
-    if (nrow >= 0 && nrow < D2)
+  if (first_tile) {  // CTA had no tile
+    for (int i = threadIdx.x; i < net.n_params; i += blockDim.x)
+      part[i] = 0.f;
+  } else {
+    {
+      constexpr int DC = D1 / 2;
+      float v[DC];
+      tmem_load<DC>(c.tmem + TC_DA + t.lane_base + t.wg * DC, v);
+      int nrow = t.row - 64;
+      const float s = kk[K_ISH1];
+      if (nrow >= 0 && nrow < D2)
 #pragma unroll
-      for (int j = 0; j < DC; ++j)
-        part[net.o_w2 + nrow * D1 + t.wg * DC + j] = v[j];
-  }
-  {
-    constexpr int DC = (D0 + 16) / 2;
-    float v[DC];
-    tmem_load<DC>(c.tmem + TC_DB + t.lane_base + t.wg * DC, v);
+        for (int j = 0; j < DC; ++j)
+          part[net.o_w2 + nrow * D1 + t.wg * DC + j] = v[j] * s;
+    }
+    {
+      constexpr int DC = (D0 + 16) / 2;
+      float v[DC];
+      tmem_load<DC>(c.tmem + TC_DB + t.lane_base + t.wg * DC, v);
 #pragma unroll
-    for (int j = 0; j < DC; ++j) {
-      int col = t.wg * DC + j;
-      if (t.row < D1) {
-        if (col < D0)
-          part[net.o_w1 + t.row * D0 + col] = v[j];
-        else if (col == D0)
-          part[net.o_b1 + t.row] = v[j];
-      } else if (t.row >= 64 && t.row - 64 < D2 && col == D0) {
-        part[net.o_b2 + t.row - 64] = v[j];
+      for (int j = 0; j < DC; ++j) {
+        int col = t.wg * DC + j;
+        if (t.row < D1) {
+          if (col < D0)
+            part[net.o_w1 + t.row * D0 + col] = v[j];
+          else if (col == D0)
+            part[net.o_b1 + t.row] = v[j];
+        } else if (t.row >= 64 && t.row - 64 < D2 && col == D0) {
+          part[net.o_b2 + t.row - 64] = v[j];
+        }
       }
     }
-  }
-  // dW3 / db3: thread-local sums -> fixed-order column sums through shared memory (reuse the H
-  // panels as fp32 scratch: [128 rows][D2 + 1])
-  __syncthreads();
-  float *scr = reinterpret_cast<float *>(smem + SM::H_HI);
+    // dW3 / db3: thread-local sums -> fixed-order column sums through shared memory (reuse the H
+    // panels as fp32 scratch: [128 rows][D2 + 1])
+    __syncthreads();
+    float *red = reinterpret_cast<float *>(smem + SM::H_HI);
+    const float s2 = kk[K_ISH2];
 #pragma unroll
-  for (int j = 0; j < DC2; ++j)
-    scr[t.row * (D2 + 1) + t.wg * DC2 + j] = dw3[j];
-  if (t.wg == 0)
-    scr[t.row * (D2 + 1) + D2] = db3;
-  __syncthreads();
-  if (threadIdx.x <= D2) {
-    float s = 0.f;
-    for (int r = 0; r < TILE; ++r)
-      s += scr[r * (D2 + 1) + threadIdx.x];
-    if (threadIdx.x < D2)
-      part[net.o_w3 + threadIdx.x] = s;
-    else
-      part[net.o_b3] = s;
+    for (int j = 0; j < DC2; ++j)
+      red[t.row * (D2 + 1) + t.wg * DC2 + j] = dw3[j] * s2;
+    if (t.wg == 0)
+      red[t.row * (D2 + 1) + D2] = db3;
+    __syncthreads();
+    if (threadIdx.x <= D2) {
+      float s = 0.f;
+      for (int r = 0; r < TILE; ++r)
+        s += red[r * (D2 + 1) + threadIdx.x];
+      if (threadIdx.x < D2)
+        part[net.o_w3 + threadIdx.x] = s;
+      else
+        part[net.o_b3] = s;
+    }
   }
   umma::fence_before_sync();
   __syncthreads();
-  if (threadIdx.x < 32)
+  if (t.warp == 0)
     umma::tmem_dealloc(c.tmem, TC_COLS);
 }
+
+// ---------------------------------------------------------------------------------------------
+// Forward-only kernels (rollout, GAE): image + X0 + one H panel pair (H2 overwrites H1).
+// 2 CTAs per SM (<= 100 KB shared memory, 256 TMEM columns each) so that one CTA's epilogue
+// overlaps the other's MMAs.
+template <int D1, int D2>
+struct smem_fwd {
+  using IM = image_map<D1, D2>;
+  static constexpr uint32_t X0 = (IM::BYTES + 1023) / 1024 * 1024;
+  static constexpr uint32_t H_HI = X0 + PANEL, H_LO = H_HI + PANEL;  // H1, then H2 in place
+  static constexpr uint32_t SCRATCH = H_LO + PANEL;                  // 4 * TILE floats
+  static constexpr uint32_t STATE = SCRATCH + 4 * TILE * 4;          // int8 [18][128] (rollout: live tile state)
+  static constexpr uint32_t RAW_S = STATE;                           // GAE: start states
+  static constexpr uint32_t RAW_E = STATE + 18 * TILE;               // GAE: end states
+  static constexpr uint32_t BARS = RAW_E + 18 * TILE;
+  static constexpr uint32_t TOTAL = BARS + 64;
+  static_assert(2 * (TOTAL + 1024 + 1024) <= 232448, "two CTAs per SM");
+};
+constexpr uint32_t TF_L1 = 0, TF_L2 = 64, TF_L3 = 128, TF_COLS = 256;
 
 // calculate_advantage (policy_gradient.h:220-281) with the updated critic: V of start / end
 // rows, then GAE per environment (all T steps of an env live in the tile).
 template <int D0, int D1, int D2>
-__global__ void __launch_bounds__(256, 1) fused_gae_kernel(critic_args a) {
-  using SM = smem_map<D1, D2>;
+__global__ void __launch_bounds__(256, 2) fused_gae_kernel(critic_args a) {
+  using SM = smem_fwd<D1, D2>;
+  using IM = image_map<D1, D2>;
   constexpr int DC2 = D2 / 2;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  float *fl = reinterpret_cast<float *>(smem + SM::FLOATS);
-  float *b1 = fl, *b2 = fl + D1, *w3 = fl + D1 + D2 + 16, *vpart = w3 + 64, *ve = vpart + 2 * TILE,
-        *vs = ve + TILE;
+  const float *fl = reinterpret_cast<const float *>(smem + IM::FLOATS);
+  const float *w3s = fl + IM::F_W3S, *kk = fl + IM::F_K;
+  float *scr = reinterpret_cast<float *>(smem + SM::SCRATCH);
+  float *vpart = scr, *ve = scr + 2 * TILE, *vs = scr + 3 * TILE;
   uint64_t *bar = reinterpret_cast<uint64_t *>(smem + SM::BARS);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + SM::BARS + 16);
-  const net3 net = a.net;
   tile_ctx c;
-  setup_common<D0, D1, D2>(c, smem, a.params, net, b1, b2, tmem_slot, bar);
-  for (int i = threadIdx.x; i < D2; i += blockDim.x) w3[i] = a.params[net.o_w3 + i];
-  const float b3 = a.params[net.o_b3];
-  sync_after_smem_writes();
-  c.tmem = *tmem_slot;
+  setup_common<D0, D1, D2, SM>(c, smem, a.image, SM::X0, SM::SCRATCH - SM::X0, TF_COLS, tmem_slot, bar);
+  const float b3 = kk[K_B3V];
   const tid_t t = c.t;
   const learner_rows &L = a.rows;
+  int8_t *raw_s = reinterpret_cast<int8_t *>(smem + SM::RAW_S), *raw_e = reinterpret_cast<int8_t *>(smem + SM::RAW_E);
+  x0_pref xp;
+  if ((int)blockIdx.x < a.n_tiles)
+    load_x0<true>(L, blockIdx.x, xp);
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     uint32_t m1, m2;
-    float h2[DC2];
-    stage_x0(smem + SM::X0, L, tile, true, []() {});
+    float y2[DC2];
+    stash_x0<true>(raw_s, raw_e, L, tile, xp);
+    __syncthreads();
+    fix_end_rows(raw_e, L, xp);
+    __syncthreads();
+    encode_x0(smem + SM::X0, raw_e, L.B, L.inv_w, L.inv_h);
     sync_after_smem_writes();
-    fwd_hidden<D0, D1, D2, false>(c, b1, b2, m1, m2, h2);
-    float v_end = value_head<D2>(t, h2, w3, b3, vpart);
+    // done flags of the env this thread walks in the GAE step (threads < E), loaded early
+    uint32_t dmask = 0;
+    if ((int)threadIdx.x < L.E && tile * L.E + (int)threadIdx.x < L.n)
+      for (int tt = 0; tt < L.T && tt < 32; ++tt)
+        dmask |= (uint32_t)(L.rec_done[(size_t)tt * L.n + tile * L.E + threadIdx.x] != 0) << tt;
+    fwd_hidden<D0, D1, D2, SM, TF_L1, TF_L2, true, false>(c, fl, m1, m2, y2);
+    float v_end = value_head<D2>(t, y2, w3s, b3, vpart);
     if (t.wg == 0)
       ve[t.row] = v_end;
-    __syncthreads();
-    stage_x0(smem + SM::X0, L, tile, false, []() {});
+    encode_x0(smem + SM::X0, raw_s, L.B, L.inv_w, L.inv_h);
     sync_after_smem_writes();
-    fwd_hidden<D0, D1, D2, false>(c, b1, b2, m1, m2, h2);
-    float v = value_head<D2>(t, h2, w3, b3, vpart);
+    const int next = tile + gridDim.x;
+    if (next < a.n_tiles)
+      load_x0<true>(L, next, xp);
+    fwd_hidden<D0, D1, D2, SM, TF_L1, TF_L2, true, false>(c, fl, m1, m2, y2);
+    float v = value_head<D2>(t, y2, w3s, b3, vpart);
     if (t.wg == 0)
       vs[t.row] = v;
     __syncthreads();
-    // GAE: thread e < E walks its env backwards (device_fns.cuh gae_env on shared-memory values)
-    if (threadIdx.x < L.E) {
+    // GAE: thread e < E walks its env backwards (same recurrence as device_fns.cuh gae_env)
+    if ((int)threadIdx.x < L.E) {
       int e = threadIdx.x, i = tile * L.E + e;
       if (i < L.n) {
         float a_next = 0.f;
         for (int tt = L.T - 1; tt >= 0; --tt) {
           size_t k = (size_t)tt * L.n + i;
           int r = tt * L.E + e;
-          int d = L.rec_done[k];
+          int d = L.T <= 32 ? (int)((dmask >> tt) & 1u) : (int)L.rec_done[k];
           bool ends = d || tt == L.T - 1;
           float vn = ends ? ve[r] : vs[r + L.E];
           float vn_adv = d ? 0.f : vn;
@@ -627,23 +889,22 @@ __global__ void __launch_bounds__(256, 1) fused_gae_kernel(critic_args a) {
   }
   umma::fence_before_sync();
   __syncthreads();
-  if (threadIdx.x < 32)
-    umma::tmem_dealloc(c.tmem, TC_COLS);
+  if (t.warp == 0)
+    umma::tmem_dealloc(c.tmem, TF_COLS);
 }
 
 enum { HEAD_JACOBIAN = 0, HEAD_IDENTITY = 1 };
 
 struct policy_step_args {
-  const float *params;        // flat fp32 policy parameters
+  const uint8_t *image;
   net3 net;
-  const int8_t *rec_state;    // [T][P][stride]
-  const uint8_t *rec_action;  // [T][n]
-  const float *adv;           // [T][n]
-  const float *p_old;         // [T][n][B]
-  int n, stride, T, E, n_tiles, B;
-  float inv_w, inv_h;
+  learner_rows rows;
+  const float *adv;    // [T][n]
+  const float *p_old;  // [T][n][B]
+  int n_tiles;
   int loss_kind, head_bwd;
-  float *partials;            // [gridDim.x][n_params]
+  float *partials;     // [gridDim.x][n_params]
+  long long *clk;      // optional: phase clocks of CTA 0 (debug)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -651,152 +912,130 @@ struct policy_step_args {
 template <int D0, int D1, int D2, int NOUT>
 __global__ void __launch_bounds__(256, 1) fused_policy_step_kernel(policy_step_args a) {
   using SM = smem_map<D1, D2>;
+  using IM = image_map<D1, D2>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  const uint32_t sbase = umma::smem_u32(smem);
-  float *fl = reinterpret_cast<float *>(smem + SM::FLOATS);
-  float *b1 = fl, *b2 = fl + D1, *b3 = fl + D1 + D2, *red = fl + D1 + D2 + 16 + 64;
+  const float *fl = reinterpret_cast<const float *>(smem + IM::FLOATS);
+  const float *b3 = fl + IM::F_B3, *kk = fl + IM::F_K;
+  float *red = reinterpret_cast<float *>(smem + SM::SCRATCH);
   uint64_t *bar = reinterpret_cast<uint64_t *>(smem + SM::BARS);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + SM::BARS + 16);
-  const tid_t t = thread_id();
   const net3 net = a.net;
+  tile_ctx c;
+  setup_common<D0, D1, D2, SM>(c, smem, a.image, SM::X0, SM::SCRATCH - SM::X0, TC_COLS, tmem_slot, bar);
+  const tid_t t = c.t;
+  const learner_rows &L = a.rows;
+  const uint32_t tmem = c.tmem, sbase = c.sbase;
 
-  // ---- one-time setup: TMEM, barrier, weights -> bf16 hi/lo panels, constant panel parts
-  if (threadIdx.x < 32)
-    umma::tmem_alloc(tmem_slot, TC_COLS);
-  if (threadIdx.x == 0) {
-    umma::mbar_init(bar, 1);
-    umma::fence_mbar_init();
-  }
-  stage_weight(a.params + net.o_w1, D1, D0, D1, smem + SM::W1_HI, smem + SM::W1_LO);
-  stage_weight(a.params + net.o_w2, D2, D1, D2, smem + SM::W2_HI, smem + SM::W2_LO);
-  stage_weight(a.params + net.o_w3, NOUT, D2, 16, smem + SM::W3_HI, smem + SM::W3_LO);
-  for (int i = threadIdx.x; i < D1; i += blockDim.x) b1[i] = a.params[net.o_b1 + i];
-  for (int i = threadIdx.x; i < D2; i += blockDim.x) b2[i] = a.params[net.o_b2 + i];
-  for (int i = threadIdx.x; i < 16; i += blockDim.x) b3[i] = i < NOUT ? a.params[net.o_b3 + i] : 0.f;
-  zero_bytes(smem + SM::X0, PANEL);
-  zero_bytes(smem + SM::H_HI, 4 * PANEL);
-  zero_bytes(smem + SM::DH_HI, 4 * PANEL);
-  zero_bytes(smem + SM::DY_HI, 2 * PANEL);
-  __syncthreads();
-  // ones column (col D0) of the X0 panel: [dH1|dH2]^T . 1 = bias gradients for free
-  if (threadIdx.x < TILE)
-    *reinterpret_cast<uint16_t *>(smem + SM::X0 + umma::panel_off(threadIdx.x, D0)) = 0x3F80;  // bf16 1.0
-  sync_after_smem_writes();
-  const uint32_t tmem = *tmem_slot;
-
-  constexpr uint32_t ID_L1 = umma::make_idesc_bf16(128, D1, 0, 0);
-  constexpr uint32_t ID_L2 = umma::make_idesc_bf16(128, D2, 0, 0);
-  constexpr uint32_t ID_L3 = umma::make_idesc_bf16(128, 16, 0, 0);
-  constexpr uint32_t ID_DH2 = umma::make_idesc_bf16(128, D2, 0, 1);
-  constexpr uint32_t ID_DH1 = umma::make_idesc_bf16(128, D1, 0, 1);
-  constexpr uint32_t ID_DA = umma::make_idesc_bf16(128, 64, 1, 1);
-  constexpr uint32_t ID_DB = umma::make_idesc_bf16(128, D0 + 16, 1, 1);
-  constexpr uint32_t ID_DC = umma::make_idesc_bf16(128, 16, 1, 1);
-
-  uint32_t phase = 0;
   bool dw_pending = false, first_tile = true;
   float db3[NOUT];
 #pragma unroll
   for (int j = 0; j < NOUT; ++j)
     db3[j] = 0.f;
-  const int P = 2 * a.B + 2;
-  const int chunks_per_row = a.B / 2;
 
+  // optional phase clocks of CTA 0 (dfrl_debug_policy_clocks): 12 stamps per tile, first 8 tiles
+  long long *clk = (a.clk && blockIdx.x == 0 && threadIdx.x == 64) ? a.clk : nullptr;
+  int clk_n = 0;
+#define STAMP() do { if (clk && clk_n < 96) clk[clk_n++] = clock64(); } while (0)
+
+  int8_t *raw_s = reinterpret_cast<int8_t *>(smem + SM::RAW_S);
+  x0_pref xp;
+  if ((int)blockIdx.x < a.n_tiles)
+    load_x0<false>(L, blockIdx.x, xp);
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-    // ---- stage X0 (global loads first, then wait for the previous tile's dW GEMMs which still
-    // read the panels, then store)
-    uint4 xc[2];
-    int xrow[2], xchunk[2];
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      int task = threadIdx.x + q * 256;
-      int r = task / chunks_per_row, c = task % chunks_per_row;
-      xrow[q] = r;
-      xchunk[q] = c;
-      bool in = task < TILE * chunks_per_row;
-      int tt = r / a.E, e = r % a.E;
-      int i = tile * a.E + e;
-      bool valid = in && tt < a.T && i < a.n;
-      xc[q] = obs_chunk(a.rec_state + (size_t)tt * P * a.stride, a.stride, i, a.B, c, a.inv_w, a.inv_h,
-                        -1, valid);
-      if (!in)
-        xrow[q] = -1;
-    }
-    if (dw_pending) {
-      umma::mbar_wait(bar, phase);
-      phase ^= 1;
-      umma::fence_after_sync();
+    if (dw_pending) {  // the previous tile's dW GEMMs still read the panels
+      c.wait();
       dw_pending = false;
     }
+    STAMP();
+    stash_x0<false>(raw_s, nullptr, L, tile, xp);
+    __syncthreads();
+    encode_x0(smem + SM::X0, raw_s, L.B, L.inv_w, L.inv_h);
+    sync_after_smem_writes();
+    STAMP();
+    // ---- layer 1 issue first, then the global loads that are consumed later: row data for the
+    // head epilogue and the next tile's observation chunks
+    if (mma_thread(t)) {
+      issue_gemm<D0 / 16, false, false, false, true>(tmem + TC_L1, sbase + SM::X0, 0, sbase + IM::W1_HI,
+                                                     sbase + IM::W1_LO, ID<D1>::FK_FK, false);
+      umma::commit(c.bar);
+    }
+    const int tt = t.row / L.E, e = t.row % L.E;
+    const int i = tile * L.E + e;
+    const bool valid = t.wg == 0 && tt < L.T && i < L.n;
+    const size_t k = (size_t)tt * L.n + i;
+    int act = 0;
+    float A = 0.f;
+    float4 po[NOUT / 4];  // the whole p_old row: no load depends on another load's result
 #pragma unroll
-    for (int q = 0; q < 2; ++q)
-      if (xrow[q] >= 0)
-        *reinterpret_cast<uint4 *>(smem + SM::X0 + umma::panel_chunk_off(xrow[q], xchunk[q])) = xc[q];
-    sync_after_smem_writes();
-
-    // ---- layer 1
-    if (threadIdx.x == 0) {
-      issue_gemm(tmem + TC_L1, sbase + SM::X0, 0, sbase + SM::W1_HI, sbase + SM::W1_LO, D0 / 16, false,
-                 false, ID_L1, false);
-      umma::commit(bar);
+    for (int j = 0; j < NOUT / 4; ++j)
+      po[j] = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (valid) {
+      act = L.rec_action[k];
+      A = a.adv[k];
+      const float4 *pr = reinterpret_cast<const float4 *>(a.p_old + k * NOUT);
+#pragma unroll
+      for (int j = 0; j < NOUT / 4; ++j)
+        po[j] = pr[j];
     }
-    umma::mbar_wait(bar, phase);
-    phase ^= 1;
-    umma::fence_after_sync();
-    uint32_t mask1 = epi_hidden_fwd<D1>(tmem + TC_L1, t, b1, smem + SM::H_HI, smem + SM::H_LO);
+    const int next = tile + gridDim.x;
+    if (next < a.n_tiles)
+      load_x0<false>(L, next, xp);
+    c.wait();
+    STAMP();
+    const uint32_t mask1 = epi_hidden_fwd<D1, true, false>(tmem + TC_L1, t, kk[K_C1], fl + IM::F_B1,
+                                                           smem + SM::H_HI, smem + SM::H_LO, nullptr);
     sync_after_smem_writes();
-    // ---- layer 2
-    if (threadIdx.x == 0) {
-      issue_gemm(tmem + TC_L2, sbase + SM::H_HI, sbase + SM::H_LO, sbase + SM::W2_HI, sbase + SM::W2_LO,
-                 D1 / 16, false, false, ID_L2, false);
-      umma::commit(bar);
+    STAMP();
+    if (mma_thread(t)) {
+      issue_gemm<D1 / 16, false, false, true, true>(tmem + TC_L2, sbase + SM::H_HI, sbase + SM::H_LO,
+                                                    sbase + IM::W2_HI, sbase + IM::W2_LO, ID<D2>::FK_FK, false);
+      umma::commit(c.bar);
     }
-    umma::mbar_wait(bar, phase);
-    phase ^= 1;
-    umma::fence_after_sync();
-    uint32_t mask2 = epi_hidden_fwd<D2>(tmem + TC_L2, t, b2, smem + SM::H_HI + PANEL, smem + SM::H_LO + PANEL);
+    c.wait();
+    STAMP();
+    const uint32_t mask2 = epi_hidden_fwd<D2, true, false>(tmem + TC_L2, t, kk[K_C2], fl + IM::F_B2,
+                                                           smem + SM::H_HI + PANEL, smem + SM::H_LO + PANEL, nullptr);
     sync_after_smem_writes();
+    STAMP();
     // ---- layer 3 (head, N padded to 16)
-    if (threadIdx.x == 0) {
-      issue_gemm(tmem + TC_L3, sbase + SM::H_HI + PANEL, sbase + SM::H_LO + PANEL, sbase + SM::W3_HI,
-                 sbase + SM::W3_LO, D2 / 16, false, false, ID_L3, false);
-      umma::commit(bar);
+    if (mma_thread(t)) {
+      issue_gemm<D2 / 16, false, false, true, true>(tmem + TC_L3, sbase + SM::H_HI + PANEL, sbase + SM::H_LO + PANEL,
+                                                    sbase + IM::W3_HI, sbase + IM::W3_LO, ID<16>::FK_FK, false);
+      umma::commit(c.bar);
     }
-    umma::mbar_wait(bar, phase);
-    phase ^= 1;
-    umma::fence_after_sync();
+    c.wait();
+    STAMP();
     // ---- head epilogue: softmax, loss gradient, softmax backward -> dY panel (cols 0..NOUT-1)
     if (t.wg == 0) {
       float v[8];
       tmem_load<8>(tmem + TC_L3 + t.lane_base, v);
-      int tt = t.row / a.E, e = t.row % a.E;
-      int i = tile * a.E + e;
-      bool valid = tt < a.T && i < a.n;
       float dl[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         dl[j] = 0.f;
       if (valid) {
-        size_t k = (size_t)tt * a.n + i;
+        const float c3 = kk[K_C3];
         float p[NOUT], s = 0.f;
 #pragma unroll
         for (int j = 0; j < NOUT; ++j) {
-          p[j] = expf(v[j] + b3[j]);  // no max subtraction (nn.h:382-392)
+          p[j] = expf(fmaf(v[j], c3, b3[j]));  // no max subtraction (nn.h:382-392)
           s += p[j];
         }
+        const float inv_s = 1.f / s;
 #pragma unroll
         for (int j = 0; j < NOUT; ++j)
-          p[j] = p[j] / s;
-        int act = a.rec_action[k];
-        float A = a.adv[k];
+          p[j] = p[j] * inv_s;
         float g[NOUT];
         if (a.loss_kind == DFRL_LOSS_CLIPPED) {
-          float pa = 0.f;
+          float pa = 0.f, pold = 1.f;
+          const float *pof = reinterpret_cast<const float *>(po);
 #pragma unroll
-          for (int j = 0; j < NOUT; ++j)
+          for (int j = 0; j < NOUT; ++j) {
             pa = (j == act) ? p[j] : pa;
-          float gc = clipped_grad(pa, a.p_old[k * a.B + act], A);
+            pold = (j == act) ? pof[j] : pold;
+          }
+          float gc = clipped_grad(pa, pold, A);
 #pragma unroll
           for (int j = 0; j < NOUT; ++j)
             g[j] = (j == act) ? gc : 0.f;
@@ -823,46 +1062,46 @@ __global__ void __launch_bounds__(256, 1) fused_policy_step_kernel(policy_step_a
           db3[j] += dl[j];
       }
       uint4 h, l;
-      umma::split8(dl, h, l);
+      split8<false>(dl, h, l);
       uint32_t off = umma::panel_chunk_off(t.row, 0);
       *reinterpret_cast<uint4 *>(smem + SM::DY_HI + off) = h;
       *reinterpret_cast<uint4 *>(smem + SM::DY_LO + off) = l;
     }
     sync_after_smem_writes();
-    // ---- dH2 = dY . W3 (contraction over the 16 padded outputs), then relu mask
-    if (threadIdx.x == 0) {
-      issue_gemm(tmem + TC_DH2, sbase + SM::DY_HI, sbase + SM::DY_LO, sbase + SM::W3_HI, sbase + SM::W3_LO,
-                 1, false, true, ID_DH2, false);
-      umma::commit(bar);
+    STAMP();
+    // ---- dH2 = dY . W3 (contraction over the 16 padded outputs); dW3^T += [H1|H2]^T . dY runs
+    // behind the dH2 epilogue
+    if (mma_thread(t)) {
+      issue_gemm<1, false, true, true, true>(tmem + TC_DH2, sbase + SM::DY_HI, sbase + SM::DY_LO, sbase + IM::W3_HI,
+                                             sbase + IM::W3_LO, ID<D2>::BK_FM, false);
+      umma::commit(c.bar);
+      issue_gemm<8, true, true, true, true>(tmem + TC_DC, sbase + SM::H_HI, sbase + SM::H_LO, sbase + SM::DY_HI,
+                                            sbase + SM::DY_LO, ID<16>::FM_BM, !first_tile);
     }
-    umma::mbar_wait(bar, phase);
-    phase ^= 1;
-    umma::fence_after_sync();
-    epi_hidden_bwd<D2>(tmem + TC_DH2, t, mask2, smem + SM::DH_HI + PANEL, smem + SM::DH_LO + PANEL);
+    c.wait();
+    STAMP();
+    epi_hidden_bwd<D2>(tmem + TC_DH2, t, kk[K_ISW3], mask2, smem + SM::DH_HI + PANEL, smem + SM::DH_LO + PANEL);
     sync_after_smem_writes();
-    // ---- dH1 = dH2 . W2, relu mask
-    if (threadIdx.x == 0) {
-      issue_gemm(tmem + TC_DH1, sbase + SM::DH_HI + PANEL, sbase + SM::DH_LO + PANEL, sbase + SM::W2_HI,
-                 sbase + SM::W2_LO, D2 / 16, false, true, ID_DH1, false);
-      umma::commit(bar);
+    STAMP();
+    // ---- dH1 = dH2 . W2; dW2 += [dH1|dH2]^T . H1 (rows 64.. only are used, so the stale dH1
+    // half is harmless) runs behind the dH1 epilogue
+    if (mma_thread(t)) {
+      issue_gemm<D2 / 16, false, true, true, true>(tmem + TC_DH1, sbase + SM::DH_HI + PANEL, sbase + SM::DH_LO + PANEL,
+                                                   sbase + IM::W2_HI, sbase + IM::W2_LO, ID<D1>::BK_FM, false);
+      umma::commit(c.bar);
+      issue_gemm<8, true, true, true, true>(tmem + TC_DA, sbase + SM::DH_HI, sbase + SM::DH_LO, sbase + SM::H_HI,
+                                            sbase + SM::H_LO, ID<64>::BM_FM, !first_tile);
     }
-    umma::mbar_wait(bar, phase);
-    phase ^= 1;
-    umma::fence_after_sync();
-    epi_hidden_bwd<D1>(tmem + TC_DH1, t, mask1, smem + SM::DH_HI, smem + SM::DH_LO);
+    c.wait();
+    STAMP();
+    epi_hidden_bwd<D1>(tmem + TC_DH1, t, kk[K_ISW2], mask1, smem + SM::DH_HI, smem + SM::DH_LO);
     sync_after_smem_writes();
-    // ---- weight gradients, accumulated in TMEM across the CTA's tiles (contraction = 128 rows):
-    //   DA[128 x 64]      += [dH1|dH2]^T . H1        rows 64.. = dW2
-    //   DB[128 x D0+16]   += [dH1|dH2]^T . [X0|1]    rows 0..  = [dW1 | db1], rows 64.. col D0 = db2
-    //   DC[128 x 16]      += [H1|H2]^T . dY          rows 64.. = dW3^T
-    if (threadIdx.x == 0) {
-      issue_gemm(tmem + TC_DA, sbase + SM::DH_HI, sbase + SM::DH_LO, sbase + SM::H_HI, sbase + SM::H_LO, 8,
-                 true, true, ID_DA, !first_tile);
-      issue_gemm(tmem + TC_DB, sbase + SM::DH_HI, sbase + SM::DH_LO, sbase + SM::X0, 0, 8, true, true, ID_DB,
-                 !first_tile);
-      issue_gemm(tmem + TC_DC, sbase + SM::H_HI, sbase + SM::H_LO, sbase + SM::DY_HI, sbase + SM::DY_LO, 8,
-                 true, true, ID_DC, !first_tile);
-      umma::commit(bar);
+    STAMP();
+    //   DB[128 x D0+16] += [dH1|dH2]^T . [X0|1]   rows 0.. = [dW1 | db1], rows 64.. col D0 = db2
+    if (mma_thread(t)) {
+      issue_gemm<8, true, true, true, false>(tmem + TC_DB, sbase + SM::DH_HI, sbase + SM::DH_LO, sbase + SM::X0, 0,
+                                             ID<D0 + 16>::BM_FM, !first_tile);
+      umma::commit(c.bar);
     }
     dw_pending = true;
     first_tile = false;
@@ -870,11 +1109,8 @@ __global__ void __launch_bounds__(256, 1) fused_policy_step_kernel(policy_step_a
 
   // ---- drain: partial gradient of this CTA -> global, in the flat parameter layout
   float *part = a.partials + (size_t)blockIdx.x * net.n_params;
-  if (dw_pending) {
-    umma::mbar_wait(bar, phase);
-    phase ^= 1;
-    umma::fence_after_sync();
-  }
+  if (dw_pending)
+    c.wait();
   if (first_tile) {  // CTA had no tile: contribute zeros
     for (int i = threadIdx.x; i < net.n_params; i += blockDim.x)
       part[i] = 0.f;
@@ -885,10 +1121,11 @@ __global__ void __launch_bounds__(256, 1) fused_policy_step_kernel(policy_step_a
       float v[DC];
       tmem_load<DC>(tmem + TC_DA + t.lane_base + t.wg * DC, v);
       int nrow = t.row - 64;
+      const float s = kk[K_ISH1];
       if (nrow >= 0 && nrow < D2)
 #pragma unroll
         for (int j = 0; j < DC; ++j)
-          part[net.o_w2 + nrow * D1 + t.wg * DC + j] = v[j];
+          part[net.o_w2 + nrow * D1 + t.wg * DC + j] = v[j] * s;
     }
     // dW1[n][k] + db1[n]: DB row n, cols 0..D0-1 and D0; db2[n]: DB row 64 + n, col D0
     {
@@ -913,10 +1150,11 @@ __global__ void __launch_bounds__(256, 1) fused_policy_step_kernel(policy_step_a
       float v[8];
       tmem_load<8>(tmem + TC_DC + t.lane_base, v);
       int krow = t.row - 64;
+      const float s = kk[K_ISH2];
       if (krow >= 0 && krow < D2)
 #pragma unroll
         for (int j = 0; j < NOUT; ++j)
-          part[net.o_w3 + j * D2 + krow] = v[j];
+          part[net.o_w3 + j * D2 + krow] = v[j] * s;
     }
     // db3: per-thread partial sums -> fixed-order block sum
     if (t.wg == 0)
@@ -931,49 +1169,73 @@ __global__ void __launch_bounds__(256, 1) fused_policy_step_kernel(policy_step_a
       part[net.o_b3 + threadIdx.x] = s;
     }
   }
+#undef STAMP
   umma::fence_before_sync();
   __syncthreads();
-  if (threadIdx.x < 32)
+  if (t.warp == 0)
     umma::tmem_dealloc(tmem, TC_COLS);
 }
 
-// Second stage of the gradient: fixed-order sum of the per-CTA partials.
-__global__ void fused_reduce_partials_kernel(const float *__restrict__ part, int ctas, int n,
-                                             float *__restrict__ grad) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n)
-    return;
+// Second stage of the gradient: fixed-order sum of the per-CTA partials. Block = 32 parameters x 8
+// slices of the CTA range; the 8 slice sums are combined in a fixed order. With a single rank the
+// optimizer update (nn.h:616-698) of the same 32 parameters follows in the same kernel, and the
+// block that finishes last rebuilds the net's panel image from the updated parameters.
+struct reduce_tail {
+  dfrl_opt_spec opt;   // params == null: no update
+  uint8_t *image;      // null: no rebuild
+  net3 net;
+  unsigned *ticket;    // zero before the launch, zero again after it
+};
+template <int D0, int D1, int D2>
+__global__ void __launch_bounds__(256) fused_reduce_partials_kernel(const float *__restrict__ part, int ctas,
+                                                                    int n, float *__restrict__ grad,
+                                                                    reduce_tail tail) {
+  __shared__ float sm[8][33];
+  __shared__ int is_last;
+  extern __shared__ float prep_params[];
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
   float s = 0.f;
-  for (int c = 0; c < ctas; ++c)
-    s += part[(size_t)c * n + i];
-  grad[i] = s;
+  if (i < n)
+    for (int c = slice; c < ctas; c += 8)
+      s += part[(size_t)c * n + i];
+  sm[slice][lane] = s;
+  __syncthreads();
+  if (slice == 0 && i < n) {
+    float r = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      r += sm[q][lane];
+    grad[i] = r;
+    const dfrl_opt_spec &opt = tail.opt;
+    if (opt.params)
+      opt_update(opt.kind, opt.params, grad, opt.state, n, i, opt.lr, opt.wd, opt.beta1, opt.beta2, opt.c1, opt.c2);
+  }
+  if (!tail.image)
+    return;
+  __threadfence();  // this block's parameter writes before its ticket
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned tk = atomicAdd(tail.ticket, 1u);
+    is_last = tk == gridDim.x - 1;
+    if (is_last)
+      *tail.ticket = 0;
+  }
+  __syncthreads();
+  if (!is_last)
+    return;
+  __threadfence();
+  prep_body<D0, D1, D2>(tail.opt.params, tail.net, tail.image, prep_params);
 }
 
 // ---------------------------------------------------------------------------------------------
 // Rollout: agent::play_steps(T) (rl.h:325-360) for a tile of 128 environments per CTA iteration.
 // The tile's int8 state planes stay in shared memory for all T steps; per step the CTA records the
-// start state, encodes the observation panel (exact in bf16: multiples of 1/cap), runs the three
+// start state, encodes the observation panel (exact in 16 bits: multiples of 1/cap), runs the three
 // forward GEMMs on the tensor cores, and one thread per environment does softmax -> action
 // (sample / argmax / forced) -> environment::apply -> reward / done / reset / next item.
-// Two CTAs per SM (84 KB shared memory, 256 TMEM columns each) so that one CTA's epilogue
-// overlaps the other's MMAs.
-template <int D1, int D2>
-struct smem_fwd {
-  static constexpr uint32_t W1_HI = 0, W1_LO = W1_HI + D1 * 128;
-  static constexpr uint32_t W2_HI = W1_LO + D1 * 128, W2_LO = W2_HI + D2 * 128;
-  static constexpr uint32_t W3_HI = W2_LO + D2 * 128, W3_LO = W3_HI + 16 * 128;
-  static constexpr uint32_t X0 = W3_LO + 16 * 128;
-  static constexpr uint32_t H_HI = X0 + PANEL, H_LO = H_HI + PANEL;  // H1, then H2 in place
-  static constexpr uint32_t FLOATS = H_LO + PANEL;                   // b1, b2, b3 / w3
-  static constexpr uint32_t N_FLOATS = D1 + D2 + 16 + 64 + 4 * TILE;
-  static constexpr uint32_t STATE = FLOATS + N_FLOATS * 4;           // int8 [18][128]
-  static constexpr uint32_t BARS = STATE + 18 * TILE;
-  static constexpr uint32_t TOTAL = BARS + 64;
-};
-constexpr uint32_t TF_L1 = 0, TF_L2 = 64, TF_L3 = 128, TF_COLS = 256;
-
 struct rollout_args {
-  const float *params;
+  const uint8_t *image;
   net3 net;
   env_params ep;
   int8_t *state;             // live planes [P][stride]
@@ -992,42 +1254,24 @@ struct rollout_args {
 template <int D0, int D1, int D2, int NOUT>
 __global__ void __launch_bounds__(256, 2) fused_rollout_kernel(rollout_args a) {
   using SM = smem_fwd<D1, D2>;
+  using IM = image_map<D1, D2>;
   constexpr int B = NOUT, P = 2 * B + 2;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  const uint32_t sbase = umma::smem_u32(smem);
-  float *fl = reinterpret_cast<float *>(smem + SM::FLOATS);
-  float *b1 = fl, *b2 = fl + D1, *b3 = fl + D1 + D2;
+  const float *fl = reinterpret_cast<const float *>(smem + IM::FLOATS);
+  const float *b3 = fl + IM::F_B3, *kk = fl + IM::F_K;
   int8_t *sst = reinterpret_cast<int8_t *>(smem + SM::STATE);
   uint64_t *bar = reinterpret_cast<uint64_t *>(smem + SM::BARS);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + SM::BARS + 16);
-  const tid_t t = thread_id();
-  const net3 net = a.net;
   const env_params &ep = a.ep;
+  tile_ctx c;
+  setup_common<D0, D1, D2, SM>(c, smem, a.image, SM::X0, SM::SCRATCH - SM::X0, TF_COLS, tmem_slot, bar);
+  const tid_t t = c.t;
+  const uint32_t tmem = c.tmem, sbase = c.sbase;
 
-  if (threadIdx.x < 32)
-    umma::tmem_alloc(tmem_slot, TF_COLS);
-  if (threadIdx.x == 0) {
-    umma::mbar_init(bar, 1);
-    umma::fence_mbar_init();
-  }
-  stage_weight(a.params + net.o_w1, D1, D0, D1, smem + SM::W1_HI, smem + SM::W1_LO);
-  stage_weight(a.params + net.o_w2, D2, D1, D2, smem + SM::W2_HI, smem + SM::W2_LO);
-  stage_weight(a.params + net.o_w3, NOUT, D2, 16, smem + SM::W3_HI, smem + SM::W3_LO);
-  for (int i = threadIdx.x; i < D1; i += blockDim.x) b1[i] = a.params[net.o_b1 + i];
-  for (int i = threadIdx.x; i < D2; i += blockDim.x) b2[i] = a.params[net.o_b2 + i];
-  for (int i = threadIdx.x; i < 16; i += blockDim.x) b3[i] = i < NOUT ? a.params[net.o_b3 + i] : 0.f;
-  zero_bytes(smem + SM::X0, 3 * PANEL);
-  sync_after_smem_writes();
-  const uint32_t tmem = *tmem_slot;
-
-  constexpr uint32_t ID_L1 = umma::make_idesc_bf16(128, D1, 0, 0);
-  constexpr uint32_t ID_L2 = umma::make_idesc_bf16(128, D2, 0, 0);
-  constexpr uint32_t ID_L3 = umma::make_idesc_bf16(128, 16, 0, 0);
-  uint32_t phase = 0;
   unsigned long long c_eps = 0, c_reward = 0, c_steps = 0;
   const size_t S = ep.stride;
-  // plane copies: thread (q, c) moves the 16 environments [16c, 16c+16) of plane q
+  // plane copies: thread (q, cc) moves the 16 environments [16cc, 16cc+16) of plane q
   const int cq = threadIdx.x >> 3, cc = threadIdx.x & 7;
 
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
@@ -1052,64 +1296,41 @@ __global__ void __launch_bounds__(256, 2) fused_rollout_kernel(rollout_args a) {
       if (copier)
         *reinterpret_cast<uint4 *>(a.rec_state + ((size_t)tt * P + cq) * S + i0 + 16 * cc) =
             *reinterpret_cast<const uint4 *>(sst + cq * TILE + 16 * cc);
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        int task = threadIdx.x + q * 256;
-        int row = task >> 2, c = task & 3;
-        float iw = (float)sst[(2 * B) * TILE + row] * a.inv_w, ih = (float)sst[(2 * B + 1) * TILE + row] * a.inv_h;
-        uint32_t out[4];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          int b = 2 * c + h;
-          float bw = (float)sst[(2 * b) * TILE + row] * a.inv_w, bh = (float)sst[(2 * b + 1) * TILE + row] * a.inv_h;
-          out[2 * h] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(bw)) |
-                       ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(bh)) << 16);
-          out[2 * h + 1] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(iw)) |
-                           ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(ih)) << 16);
-        }
-        *reinterpret_cast<uint4 *>(smem + SM::X0 + umma::panel_chunk_off(row, c)) =
-            make_uint4(out[0], out[1], out[2], out[3]);
-      }
+      encode_x0(smem + SM::X0, sst, B, a.inv_w, a.inv_h);
       sync_after_smem_writes();
+      // tape entries of this step (loads issued before the GEMMs, used in the head)
+      const size_t k = (size_t)tt * ep.n + i;
+      int forced_a = 0, tape_item = 0;
+      double tape_u = 0.0;
+      if (owner) {
+        if (a.mode == DFRL_ACT_FORCED)
+          forced_a = a.forced[k];
+        else if (a.mode == DFRL_ACT_SAMPLE && a.u_tape)
+          tape_u = a.u_tape[k];
+        if (a.item_tape)
+          tape_item = a.item_tape[k];
+      }
       // ---- forward
-      if (threadIdx.x == 0) {
-        issue_gemm(tmem + TF_L1, sbase + SM::X0, 0, sbase + SM::W1_HI, sbase + SM::W1_LO, D0 / 16, false,
-                   false, ID_L1, false);
-        umma::commit(bar);
-      }
-      umma::mbar_wait(bar, phase);
-      phase ^= 1;
-      umma::fence_after_sync();
-      epi_hidden_fwd<D1>(tmem + TF_L1, t, b1, smem + SM::H_HI, smem + SM::H_LO);
+      uint32_t m1, m2;
+      float y2[D2 / 2];
+      fwd_hidden<D0, D1, D2, SM, TF_L1, TF_L2, true, true>(c, fl, m1, m2, y2);
       sync_after_smem_writes();
-      if (threadIdx.x == 0) {
-        issue_gemm(tmem + TF_L2, sbase + SM::H_HI, sbase + SM::H_LO, sbase + SM::W2_HI, sbase + SM::W2_LO,
-                   D1 / 16, false, false, ID_L2, false);
-        umma::commit(bar);
+      if (mma_thread(t)) {
+        issue_gemm<D2 / 16, false, false, true, true>(tmem + TF_L3, sbase + SM::H_HI, sbase + SM::H_LO,
+                                                      sbase + IM::W3_HI, sbase + IM::W3_LO, ID<16>::FK_FK, false);
+        umma::commit(c.bar);
       }
-      umma::mbar_wait(bar, phase);
-      phase ^= 1;
-      umma::fence_after_sync();
-      epi_hidden_fwd<D2>(tmem + TF_L2, t, b2, smem + SM::H_HI, smem + SM::H_LO);  // H2 over H1
-      sync_after_smem_writes();
-      if (threadIdx.x == 0) {
-        issue_gemm(tmem + TF_L3, sbase + SM::H_HI, sbase + SM::H_LO, sbase + SM::W3_HI, sbase + SM::W3_LO,
-                   D2 / 16, false, false, ID_L3, false);
-        umma::commit(bar);
-      }
-      umma::mbar_wait(bar, phase);
-      phase ^= 1;
-      umma::fence_after_sync();
+      c.wait();
       // ---- head: softmax (no max subtraction, nn.h:382-392), action, environment::apply
       if (t.wg == 0) {
         float v[8];
         tmem_load<8>(tmem + TF_L3 + t.lane_base, v);
         if (owner) {
-          const size_t k = (size_t)tt * ep.n + i;
+          const float c3 = kk[K_C3];
           float p[NOUT], s = 0.f;
 #pragma unroll
           for (int j = 0; j < NOUT; ++j) {
-            p[j] = expf(v[j] + b3[j]);
+            p[j] = expf(fmaf(v[j], c3, b3[j]));
             s += p[j];
           }
 #pragma unroll
@@ -1121,14 +1342,12 @@ __global__ void __launch_bounds__(256, 2) fused_rollout_kernel(rollout_args a) {
             pr[j] = make_float4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
           int act;
           if (a.mode == DFRL_ACT_FORCED) {
-            act = a.forced[k];
+            act = forced_a;
           } else if (a.mode == DFRL_ACT_ARGMAX) {
             act = argmax_first(p, B);
           } else {
-            double u;
-            if (a.u_tape) {
-              u = a.u_tape[k];
-            } else {
+            double u = tape_u;
+            if (!a.u_tape) {
               philox4 rr = philox4x32_10(ep.seed, (uint64_t)(ep.env_offset + i), my_steps, DFRL_STREAM_ACTION);
               u = philox_u53(rr.x, rr.y);
             }
@@ -1140,7 +1359,7 @@ __global__ void __launch_bounds__(256, 2) fused_rollout_kernel(rollout_args a) {
           int iw = sst[(2 * B) * TILE + r], ih = sst[(2 * B + 1) * TILE + r];
           int bw = sst[(2 * act) * TILE + r] - iw, bh = sst[(2 * act + 1) * TILE + r] - ih;
           bool over = bw < 0 || bh < 0;
-          int s1 = a.item_tape ? (a.item_tape[k] != 0) : draw_shape1(ep, i, my_draws);
+          int s1 = a.item_tape ? (tape_item != 0) : draw_shape1(ep, i, my_draws);
           if (over) {
 #pragma unroll
             for (int b = 0; b < B; ++b) {
@@ -1187,17 +1406,21 @@ __global__ void __launch_bounds__(256, 2) fused_rollout_kernel(rollout_args a) {
   }
   umma::fence_before_sync();
   __syncthreads();
-  if (threadIdx.x < 32)
+  if (t.warp == 0)
     umma::tmem_dealloc(tmem, TF_COLS);
 }
 
+// ---------------------------------------------------------------------------------------------
 struct fused_state {
   net3 pnet, vnet;
-  bool policy_ok, value_ok;
+  bool policy_ok, value_ok, rollout_ok;
   int head_bwd;
   float *partials;  // [ctas][max params]
+  uint8_t *pimage, *vimage;
+  uint64_t pimage_version, vimage_version;  // dfrl_mlp::version the image was built from
+  unsigned *ticket;  // last-block election of the reduction kernel
   int ctas;
-  bool rollout_ok;
+  long long *clk;  // [96] phase clocks of the last policy step (allocated on first request)
 };
 
 // D - R - D - R - D (- softmax / softmax_ce)
@@ -1260,7 +1483,7 @@ int launch_critic_step(dfrl_ctx *ctx, const critic_args &a, int ctas) {
 
 template <int D0, int D1, int D2>
 int launch_gae(dfrl_ctx *ctx, const critic_args &a, int ctas) {
-  constexpr int smem = smem_map<D1, D2>::TOTAL + 1024;
+  constexpr int smem = smem_fwd<D1, D2>::TOTAL + 1024;
   static bool attr = false;
   DFRL_TRY(set_smem_once(fused_gae_kernel<D0, D1, D2>, smem, &attr));
   DFRL_LAUNCH(ctx, (fused_gae_kernel<D0, D1, D2>), ctas, 256, smem, a);
@@ -1280,21 +1503,47 @@ bool widths_ok(const net3 &n) {
   return n.d0 == 32 && ((n.d1 == 64 && n.d2 == 64) || (n.d1 == 16 && n.d2 == 16));
 }
 
+size_t image_bytes(const net3 &n) { return n.d1 == 64 ? image_map<64, 64>::BYTES : image_map<16, 16>::BYTES; }
+
+// (Re)build the panel image of `m` when its parameters changed since the last build.
+int refresh_image(dfrl_ctx *ctx, dfrl_mlp *m, const net3 &net, uint8_t *image, uint64_t *built_version) {
+  if (*built_version == m->version)
+    return DFRL_OK;
+  if (net.d1 == 64)
+    DFRL_LAUNCH(ctx, (fused_prep_kernel<32, 64, 64>), 1, 256, sizeof(float) * net.n_params,
+                (const float *)m->params, net, image);
+  else
+    DFRL_LAUNCH(ctx, (fused_prep_kernel<32, 16, 16>), 1, 256, sizeof(float) * net.n_params,
+                (const float *)m->params, net, image);
+  *built_version = m->version;
+  return DFRL_OK;
+}
+
+struct fused_state;
+int launch_reduce(dfrl_trainer *t, fused_state *f, dfrl_mlp *m, const net3 &net, int ctas, float *grad_dev,
+                  const dfrl_opt_spec *opt, uint8_t *image, uint64_t *image_version);
+
+learner_rows make_rows(dfrl_trainer *t) {
+  learner_rows r;
+  r.rec_state = t->rec_state;
+  r.live_state = t->env->state;
+  r.rec_action = t->rec_action;
+  r.rec_done = t->rec_done;
+  r.n = t->n;
+  r.stride = t->stride;
+  r.T = t->L;
+  r.E = TILE / t->L;
+  r.B = t->B;
+  r.inv_w = 1.0f / (float)t->env->cfg.cap_w;
+  r.inv_h = 1.0f / (float)t->env->cfg.cap_h;
+  return r;
+}
+
 critic_args make_critic_args(dfrl_trainer *t, fused_state *f) {
   critic_args a;
-  a.params = t->value->params;
+  a.image = f->vimage;
   a.net = f->vnet;
-  a.rows.rec_state = t->rec_state;
-  a.rows.live_state = t->env->state;
-  a.rows.rec_action = t->rec_action;
-  a.rows.rec_done = t->rec_done;
-  a.rows.n = t->n;
-  a.rows.stride = t->stride;
-  a.rows.T = t->L;
-  a.rows.E = TILE / t->L;
-  a.rows.B = t->B;
-  a.rows.inv_w = 1.0f / (float)t->env->cfg.cap_w;
-  a.rows.inv_h = 1.0f / (float)t->env->cfg.cap_h;
+  a.rows = make_rows(t);
   a.n_tiles = ceil_div(t->n, a.rows.E);
   a.gamma = t->cfg.gamma;
   a.lambda = t->cfg.lambda;
@@ -1302,6 +1551,33 @@ critic_args make_critic_args(dfrl_trainer *t, fused_state *f) {
   a.adv_out = t->adv;
   a.partials = f->partials;
   return a;
+}
+
+// Partials -> gradient (-> optimizer update -> rebuilt panel image when `opt` is given).
+int launch_reduce(dfrl_trainer *t, fused_state *f, dfrl_mlp *m, const net3 &net, int ctas, float *grad_dev,
+                  const dfrl_opt_spec *opt, uint8_t *image, uint64_t *image_version) {
+  reduce_tail tail;
+  memset(&tail, 0, sizeof(tail));
+  size_t smem = 0;
+  if (opt) {
+    tail.opt = *opt;
+    tail.image = image;
+    tail.net = net;
+    tail.ticket = f->ticket;
+    smem = sizeof(float) * net.n_params;
+  }
+  const int grid = ceil_div(net.n_params, 32);
+  if (net.d1 == 64)
+    DFRL_LAUNCH(t->ctx, (fused_reduce_partials_kernel<32, 64, 64>), grid, 256, smem, (const float *)f->partials,
+                ctas, net.n_params, grad_dev, tail);
+  else
+    DFRL_LAUNCH(t->ctx, (fused_reduce_partials_kernel<32, 16, 16>), grid, 256, smem, (const float *)f->partials,
+                ctas, net.n_params, grad_dev, tail);
+  if (opt) {  // parameters changed and the image already matches them
+    m->wt_dirty = true, m->version++;
+    *image_version = m->version;
+  }
+  return DFRL_OK;
 }
 
 }  // namespace
@@ -1314,10 +1590,15 @@ int dfrl_fused_try_attach(dfrl_trainer *t) {
     return DFRL_ERR_UNSUPPORTED;
   if (t->L > TILE || t->B != 8)
     return DFRL_ERR_UNSUPPORTED;
-  if (!is_pow2(t->env->cfg.cap_w) || !is_pow2(t->env->cfg.cap_h) || t->env->cfg.cap_w > 64 ||
-      t->env->cfg.cap_h > 64)
-    return DFRL_ERR_UNSUPPORTED;  // observations must be exact in bf16
+  const dfrl_env_config &ec = t->env->cfg;
+  // observations must be exact in 16 bits and bounded by 1 in magnitude (prep kernel's bounds)
+  if (!is_pow2(ec.cap_w) || !is_pow2(ec.cap_h) || ec.cap_w > 64 || ec.cap_h > 64)
+    return DFRL_ERR_UNSUPPORTED;
+  for (int s = 0; s < 2; ++s)
+    if (ec.item_w[s] < 0 || ec.item_h[s] < 0 || ec.item_w[s] > ec.cap_w || ec.item_h[s] > ec.cap_h)
+      return DFRL_ERR_UNSUPPORTED;
   fused_state *f = new fused_state();
+  memset(f, 0, sizeof(*f));
   int ptail = -1, vtail = -1;
   f->policy_ok = parse_net3(t->policy, &f->pnet, &ptail) && ptail != -1 && f->pnet.d3 == 8 && widths_ok(f->pnet);
   f->value_ok = t->value && parse_net3(t->value, &f->vnet, &vtail) && vtail == -1 && f->vnet.d3 == 1 &&
@@ -1332,10 +1613,23 @@ int dfrl_fused_try_attach(dfrl_trainer *t) {
   int maxp = t->policy->n_params;
   if (t->value && t->value->n_params > maxp)
     maxp = t->value->n_params;
-  if (cudaMalloc(&f->partials, sizeof(float) * (size_t)f->ctas * maxp) != cudaSuccess) {
+  bool ok = cudaMalloc(&f->partials, sizeof(float) * (size_t)f->ctas * maxp) == cudaSuccess;
+  if (ok)
+    ok = cudaMalloc(&f->ticket, sizeof(unsigned)) == cudaSuccess &&
+         cudaMemsetAsync(f->ticket, 0, sizeof(unsigned), t->ctx->stream) == cudaSuccess;
+  if (ok && f->policy_ok)
+    ok = cudaMalloc(&f->pimage, image_bytes(f->pnet)) == cudaSuccess;
+  if (ok && f->value_ok)
+    ok = cudaMalloc(&f->vimage, image_bytes(f->vnet)) == cudaSuccess;
+  if (!ok) {
+    cudaFree(f->ticket);
+    cudaFree(f->partials);
+    cudaFree(f->pimage);
+    cudaFree(f->vimage);
     delete f;
     return DFRL_ERR_CUDA;
   }
+  f->pimage_version = f->vimage_version = ~0ull;
   t->fused_impl = f;
   return DFRL_OK;
 }
@@ -1344,58 +1638,68 @@ void dfrl_fused_detach(dfrl_trainer *t) {
   fused_state *f = (fused_state *)t->fused_impl;
   if (f) {
     cudaFree(f->partials);
+    cudaFree(f->pimage);
+    cudaFree(f->vimage);
+    cudaFree(f->clk);
+    cudaFree(f->ticket);
     delete f;
   }
   t->fused_impl = nullptr;
 }
 
+// Phase clocks (SM cycles) of CTA 0 of the fused policy step: 12 stamps per tile, first 8 tiles.
+// The first call arms the instrumentation (returns zeros); later calls return the last launch.
+extern "C" int dfrl_debug_policy_clocks(dfrl_trainer *t, long long *out_host, int n) {
+  DFRL_CHECK(t && out_host && n > 0 && n <= 96, "bad argument");
+  fused_state *f = (fused_state *)t->fused_impl;
+  DFRL_CHECK(f, "fused path not attached");
+  if (!f->clk) {
+    DFRL_CUDA(cudaMalloc(&f->clk, sizeof(long long) * 96));
+    DFRL_CUDA(cudaMemsetAsync(f->clk, 0, sizeof(long long) * 96, t->ctx->stream));
+  }
+  DFRL_CUDA(cudaMemcpyAsync(out_host, f->clk, sizeof(long long) * n, cudaMemcpyDeviceToHost, t->ctx->stream));
+  DFRL_CUDA(cudaStreamSynchronize(t->ctx->stream));
+  return DFRL_OK;
+}
+
 // One policy gradient (forward + loss + backward over all L*n rows) into grad_dev.
-int dfrl_fused_policy_gradient(dfrl_trainer *t, int loss_kind, float *grad_dev) {
+int dfrl_fused_policy_gradient(dfrl_trainer *t, int loss_kind, float *grad_dev, const dfrl_opt_spec *opt) {
   fused_state *f = (fused_state *)t->fused_impl;
   if (!f || !f->policy_ok || loss_kind == DFRL_LOSS_KL)
     return DFRL_ERR_UNSUPPORTED;
+  DFRL_TRY(refresh_image(t->ctx, t->policy, f->pnet, f->pimage, &f->pimage_version));
   policy_step_args a;
-  a.params = t->policy->params;
+  a.image = f->pimage;
   a.net = f->pnet;
-  a.rec_state = t->rec_state;
-  a.rec_action = t->rec_action;
+  a.rows = make_rows(t);
   a.adv = t->adv;
   a.p_old = t->rec_probs;
-  a.n = t->n;
-  a.stride = t->stride;
-  a.T = t->L;
-  a.E = TILE / t->L;
-  a.n_tiles = ceil_div(t->n, a.E);
-  a.B = t->B;
-  a.inv_w = 1.0f / (float)t->env->cfg.cap_w;
-  a.inv_h = 1.0f / (float)t->env->cfg.cap_h;
+  a.n_tiles = ceil_div(t->n, a.rows.E);
   a.loss_kind = loss_kind;
   a.head_bwd = f->head_bwd;
   a.partials = f->partials;
+  a.clk = f->clk;
   int ctas = a.n_tiles < f->ctas ? a.n_tiles : f->ctas;
   if (f->pnet.d1 == 64)
     DFRL_TRY((launch_policy_step<32, 64, 64, 8>(t->ctx, a, ctas)));
   else
     DFRL_TRY((launch_policy_step<32, 16, 16, 8>(t->ctx, a, ctas)));
-  DFRL_LAUNCH(t->ctx, fused_reduce_partials_kernel, ceil_div(f->pnet.n_params, 256), 256, 0,
-              (const float *)f->partials, ctas, f->pnet.n_params, grad_dev);
-  return DFRL_OK;
+  return launch_reduce(t, f, t->policy, f->pnet, ctas, grad_dev, opt, f->pimage, &f->pimage_version);
 }
 
 // update_value_model (policy_gradient.h:196-218) up to the gradient: writes t->targets and grad_dev.
-int dfrl_fused_critic_gradient(dfrl_trainer *t, float *grad_dev) {
+int dfrl_fused_critic_gradient(dfrl_trainer *t, float *grad_dev, const dfrl_opt_spec *opt) {
   fused_state *f = (fused_state *)t->fused_impl;
   if (!f || !f->value_ok)
     return DFRL_ERR_UNSUPPORTED;
+  DFRL_TRY(refresh_image(t->ctx, t->value, f->vnet, f->vimage, &f->vimage_version));
   critic_args a = make_critic_args(t, f);
   int ctas = a.n_tiles < f->ctas ? a.n_tiles : f->ctas;
   if (f->vnet.d1 == 64)
     DFRL_TRY((launch_critic_step<32, 64, 64>(t->ctx, a, ctas)));
   else
     DFRL_TRY((launch_critic_step<32, 16, 16>(t->ctx, a, ctas)));
-  DFRL_LAUNCH(t->ctx, fused_reduce_partials_kernel, ceil_div(f->vnet.n_params, 256), 256, 0,
-              (const float *)f->partials, ctas, f->vnet.n_params, grad_dev);
-  return DFRL_OK;
+  return launch_reduce(t, f, t->value, f->vnet, ctas, grad_dev, opt, f->vimage, &f->vimage_version);
 }
 
 // calculate_advantage (policy_gradient.h:220-281) with the current (updated) critic: writes t->adv.
@@ -1403,8 +1707,9 @@ int dfrl_fused_gae(dfrl_trainer *t) {
   fused_state *f = (fused_state *)t->fused_impl;
   if (!f || !f->value_ok)
     return DFRL_ERR_UNSUPPORTED;
+  DFRL_TRY(refresh_image(t->ctx, t->value, f->vnet, f->vimage, &f->vimage_version));
   critic_args a = make_critic_args(t, f);
-  int ctas = a.n_tiles < f->ctas ? a.n_tiles : f->ctas;
+  int ctas = a.n_tiles < 2 * f->ctas ? a.n_tiles : 2 * f->ctas;
   if (f->vnet.d1 == 64)
     DFRL_TRY((launch_gae<32, 64, 64>(t->ctx, a, ctas)));
   else
@@ -1418,9 +1723,10 @@ int dfrl_fused_rollout(dfrl_trainer *t, const uint8_t *items_dev, const uint8_t 
   fused_state *f = (fused_state *)t->fused_impl;
   if (!f || !f->rollout_ok)
     return DFRL_ERR_UNSUPPORTED;
+  DFRL_TRY(refresh_image(t->ctx, t->policy, f->pnet, f->pimage, &f->pimage_version));
   dfrl_env *e = t->env;
   rollout_args a;
-  a.params = t->policy->params;
+  a.image = f->pimage;
   a.net = f->pnet;
   a.ep = make_params(e);
   a.state = e->state;

@@ -587,7 +587,7 @@ extern "C" int dfrl_mlp_create(dfrl_ctx *ctx, int n_layers, const int *kinds, co
   m->n_params = (int)poff;
   m->params = nullptr;
   m->wt = nullptr;
-  m->wt_dirty = true;
+  m->wt_dirty = true, m->version++;
   m->act_arena = nullptr;
   m->act_arena_bytes = 0;
   m->kept_rows = 0;
@@ -616,7 +616,7 @@ extern "C" int dfrl_mlp_param_count(dfrl_mlp *m) { return m ? m->n_params : 0; }
 extern "C" int dfrl_mlp_output_cols(dfrl_mlp *m) { return m ? m->output_cols : 0; }
 extern "C" float *dfrl_mlp_params_dev(dfrl_mlp *m) {
   if (m)
-    m->wt_dirty = true;  // the caller may write through the pointer
+    m->wt_dirty = true, m->version++;  // the caller may write through the pointer
   return m ? m->params : nullptr;
 }
 
@@ -626,7 +626,7 @@ extern "C" int dfrl_mlp_set_params(dfrl_mlp *m, const float *params_host, int n)
   DFRL_CUDA(cudaMemcpyAsync(m->params, params_host, sizeof(float) * n, cudaMemcpyHostToDevice,
                             m->ctx->stream));
   DFRL_CUDA(cudaStreamSynchronize(m->ctx->stream));
-  m->wt_dirty = true;
+  m->wt_dirty = true, m->version++;
   return DFRL_OK;
 }
 extern "C" int dfrl_mlp_get_params(dfrl_mlp *m, float *params_host, int n) {
@@ -653,7 +653,7 @@ extern "C" int dfrl_mlp_init_params(dfrl_mlp *m, uint64_t seed) {
     DFRL_LAUNCH(m->ctx, init_normal_kernel, ceil_div(n, 256), 256, 0, m->params + L.param_off, n, sd,
                 seed, (uint32_t)l);
   }
-  m->wt_dirty = true;
+  m->wt_dirty = true, m->version++;
   return DFRL_OK;
 }
 

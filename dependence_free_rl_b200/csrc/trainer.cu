@@ -440,8 +440,29 @@ static int apply_opt(dfrl_trainer *t, dfrl_mlp *m, int kind, float *grad, float 
                          t->cfg.adam_beta1, t->cfg.adam_beta2, *adam_t));
   if (kind == DFRL_OPT_ADAM)
     *adam_t += 1.f;  // nn.h:686
-  m->wt_dirty = true;
+  m->wt_dirty = true, m->version++;
   return DFRL_OK;
+}
+
+// Single rank: the optimizer update rides in the fused gradient-reduction kernel.
+static bool fuse_opt(dfrl_trainer *t, dfrl_mlp *m, int kind, float *state, float lr, float wd, float adam_t,
+                     dfrl_opt_spec *spec) {
+  if (t->ctx->nranks != 1)
+    return false;
+  spec->kind = kind;
+  spec->params = m->params;
+  spec->state = state;
+  spec->lr = lr;
+  spec->wd = wd;
+  spec->beta1 = t->cfg.adam_beta1;
+  spec->beta2 = t->cfg.adam_beta2;
+  spec->c1 = 1.f - powf(t->cfg.adam_beta1, adam_t);  // nn.h:683-684
+  spec->c2 = 1.f - powf(t->cfg.adam_beta2, adam_t);
+  return true;
+}
+static void after_fused_opt(dfrl_mlp *, int kind, float *adam_t) {
+  if (kind == DFRL_OPT_ADAM)
+    *adam_t += 1.f;  // nn.h:686 (fused.cu already marked the parameters as changed)
 }
 
 static int learn_layered(dfrl_trainer *t) {
@@ -476,9 +497,14 @@ static int learn_layered(dfrl_trainer *t) {
   }
 
   // actor_critic_learner::learn (policy_gradient.h:159-185)
-  int frc = dfrl_fused_critic_gradient(t, t->vgrad);  // tcgen05 fused critic step (fused.cu)
+  dfrl_opt_spec vspec;
+  const bool vfo = fuse_opt(t, t->value, c.value_opt, t->vstate, c.value_lr, c.value_wd, t->v_adam_t, &vspec);
+  int frc = dfrl_fused_critic_gradient(t, t->vgrad, vfo ? &vspec : nullptr);  // tcgen05 fused critic step
   if (frc == DFRL_OK) {
-    DFRL_TRY(apply_opt(t, t->value, c.value_opt, t->vgrad, t->vstate, c.value_lr, c.value_wd, &t->v_adam_t));
+    if (vfo)
+      after_fused_opt(t->value, c.value_opt, &t->v_adam_t);
+    else
+      DFRL_TRY(apply_opt(t, t->value, c.value_opt, t->vgrad, t->vstate, c.value_lr, c.value_wd, &t->v_adam_t));
     DFRL_TRY(dfrl_fused_gae(t));
   } else if (frc != DFRL_ERR_UNSUPPORTED) {
     return frc;
@@ -510,9 +536,14 @@ static int learn_layered(dfrl_trainer *t) {
     {
       // tcgen05 fused forward + loss + backward (fused.cu); layered kernels otherwise
       float *g = t->pgrad_log + (size_t)ep * t->policy->n_params;
-      int rc = dfrl_fused_policy_gradient(t, kind, g);
+      dfrl_opt_spec pspec;
+      const bool pfo = fuse_opt(t, t->policy, c.policy_opt, t->pstate, c.policy_lr, c.policy_wd, t->p_adam_t, &pspec);
+      int rc = dfrl_fused_policy_gradient(t, kind, g, pfo ? &pspec : nullptr);
       if (rc == DFRL_OK) {
-        DFRL_TRY(apply_opt(t, t->policy, c.policy_opt, g, t->pstate, c.policy_lr, c.policy_wd, &t->p_adam_t));
+        if (pfo)
+          after_fused_opt(t->policy, c.policy_opt, &t->p_adam_t);
+        else
+          DFRL_TRY(apply_opt(t, t->policy, c.policy_opt, g, t->pstate, c.policy_lr, c.policy_wd, &t->p_adam_t));
         continue;
       }
       if (rc != DFRL_ERR_UNSUPPORTED)

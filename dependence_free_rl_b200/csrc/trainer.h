@@ -35,16 +35,24 @@ struct dfrl_trainer {
   void *fused_impl;  // non-null when the fused kernels drive this trainer
 };
 
+// Optimizer update fused behind the gradient reduction (single rank). params == null: none.
+struct dfrl_opt_spec {
+  int kind;
+  float *params, *state;
+  float lr, wd, beta1, beta2, c1, c2;
+};
+
 // fused.cu
 int dfrl_fused_try_attach(dfrl_trainer *t);
 void dfrl_fused_detach(dfrl_trainer *t);
 int dfrl_fused_rollout(dfrl_trainer *t, const uint8_t *items_dev, const uint8_t *actions_dev,
                        const double *u_dev);
 // update_value_model up to the flat gradient (writes t->targets) / calculate_advantage (t->adv).
-int dfrl_fused_critic_gradient(dfrl_trainer *t, float *grad_dev);
+int dfrl_fused_critic_gradient(dfrl_trainer *t, float *grad_dev, const dfrl_opt_spec *opt);
 int dfrl_fused_gae(dfrl_trainer *t);
 // One policy gradient over all recorded rows (forward + loss gradient + backward), SUM over rows.
 // Returns DFRL_ERR_UNSUPPORTED when the fused policy kernel does not cover this trainer.
-int dfrl_fused_policy_gradient(dfrl_trainer *t, int loss_kind, float *grad_dev);
+// opt != null: the optimizer update runs inside the reduction kernel (caller bumps adam_t).
+int dfrl_fused_policy_gradient(dfrl_trainer *t, int loss_kind, float *grad_dev, const dfrl_opt_spec *opt);
 int dfrl_fused_eval_argmax(dfrl_ctx *ctx, dfrl_env *env, dfrl_mlp *policy, int episodes,
                            double *mean_reward, long long *env_steps);

@@ -145,19 +145,34 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16 &hi, __nv_bflo
   hi = __float2bfloat16_rn(x);
   lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
+// Two fp32 -> packed bf16x2 hi and lo words (low half = a): one cvt.rn.bf16x2.f32 per word.
+__device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t &lo) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  hi = *reinterpret_cast<uint32_t *>(&h);
+  float ah = __uint_as_float(hi << 16), bh = __uint_as_float(hi & 0xffff0000u);
+  __nv_bfloat162 l = __floats2bfloat162_rn(a - ah, b - bh);
+  lo = *reinterpret_cast<uint32_t *>(&l);
+}
 // 8 consecutive fp32 -> one 16-byte chunk of hi and one of lo
 __device__ __forceinline__ void split8(const float *x, uint4 &hi, uint4 &lo) {
   uint32_t h[4], l[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    __nv_bfloat16 h0, l0, h1, l1;
-    split_bf16(x[2 * i], h0, l0);
-    split_bf16(x[2 * i + 1], h1, l1);
-    h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-    l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-  }
+  for (int i = 0; i < 4; ++i)
+    split2(x[2 * i], x[2 * i + 1], h[i], l[i]);
   hi = make_uint4(h[0], h[1], h[2], h[3]);
   lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// One lane of a fully converged warp.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n" : "=r"(pred));
+  return pred != 0;
 }
 
 }  // namespace umma

@@ -351,6 +351,10 @@ typedef struct {
   float kl_beta;           /* current beta (KL-PPO) */
 } dfrl_trainer_stats;
 int dfrl_trainer_get_stats(dfrl_trainer *tr, dfrl_trainer_stats *out);
+/* Profiling aid (no reference counterpart): SM-cycle stamps at the phase boundaries of CTA 0 of the
+ * fused policy-step kernel, 12 per row tile for its first 8 tiles (n <= 96). The first call arms
+ * the instrumentation and returns zeros; later calls return the stamps of the last launch. */
+int dfrl_debug_policy_clocks(dfrl_trainer *tr, long long *out_host, int n);
 
 /* deep_agent.cc:28-41 / the periodic eval of the trainer mains (ppo_training.cc:67-81): every
  * env of `env` plays `episodes` episodes with policy_gradient_deterministic_policy (argmax) on
