@@ -71,6 +71,9 @@ PROTOTYPES = {
     "dfrl_env_reset": (i32, [vp]),
     "dfrl_env_load_item_tape": (i32, [vp, vp, i32]),
     "dfrl_env_step": (i32, [vp, vp, vp, vp]),
+    "dfrl_env_apply_one": (i32, [vp, i32, i32]),
+    "dfrl_env_reset_one": (i32, [vp, i32]),
+    "dfrl_env_view_one": (i32, [vp, i32, vp]),
     "dfrl_env_state_dev": (vp, [vp]),
     "dfrl_env_state_stride": (i32, [vp]),
     "dfrl_env_get_state": (i32, [vp, vp]),

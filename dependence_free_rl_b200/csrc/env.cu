@@ -296,6 +296,36 @@ __global__ void heuristic_play_kernel(env_params p, int8_t *__restrict__ state,
   }
 }
 
+// Per-id forms of the reference triple environment::apply / view / reset (bin_packing.h:53-70):
+// one thread, one environment. apply() leaves an overflowed bin negative and draws no item
+// (bin_packing.h:59-61); reset() refills every bin and draws the next item.
+__global__ void env_apply_one_kernel(env_params p, int8_t *__restrict__ state, uint32_t *__restrict__ draws,
+                                     uint32_t *__restrict__ steps, int i, int a) {
+  const size_t S = p.stride;
+  int iw = state[(size_t)(2 * p.B) * S + i], ih = state[(size_t)(2 * p.B + 1) * S + i];
+  int bw = state[(size_t)(2 * a) * S + i] - iw, bh = state[(size_t)(2 * a + 1) * S + i] - ih;
+  state[(size_t)(2 * a) * S + i] = (int8_t)bw;
+  state[(size_t)(2 * a + 1) * S + i] = (int8_t)bh;
+  steps[i] += 1;
+  if (bw < 0 || bh < 0)
+    return;
+  int s1 = draw_shape1(p, i, draws[i]);
+  draws[i] += 1;
+  state[(size_t)(2 * p.B) * S + i] = (int8_t)(s1 ? p.iw0 : p.iw1);
+  state[(size_t)(2 * p.B + 1) * S + i] = (int8_t)(s1 ? p.ih0 : p.ih1);
+}
+__global__ void env_reset_one_kernel(env_params p, int8_t *__restrict__ state, uint32_t *__restrict__ draws, int i) {
+  const size_t S = p.stride;
+  for (int b = 0; b < p.B; ++b) {
+    state[(size_t)(2 * b) * S + i] = (int8_t)p.cap_w;
+    state[(size_t)(2 * b + 1) * S + i] = (int8_t)p.cap_h;
+  }
+  int s1 = draw_shape1(p, i, draws[i]);
+  draws[i] += 1;
+  state[(size_t)(2 * p.B) * S + i] = (int8_t)(s1 ? p.iw0 : p.iw1);
+  state[(size_t)(2 * p.B + 1) * S + i] = (int8_t)(s1 ? p.ih0 : p.ih1);
+}
+
 }  // namespace
 
 extern "C" void dfrl_env_config_default(dfrl_env_config *cfg) {
@@ -404,6 +434,32 @@ extern "C" int dfrl_env_step(dfrl_env *e, const uint8_t *actions_dev, uint8_t *d
   // Public buffers are [N] (done) / [2B+2][stride] (terminal). The vector kernel reads and
   // writes whole 4-env words, which is safe when N is a multiple of 4.
   return dfrl_env_step_internal(e, actions_dev, done_dev, terminal_state_dev, e->n % 4 == 0);
+}
+
+extern "C" int dfrl_env_apply_one(dfrl_env *e, int id, int action) {
+  DFRL_CHECK(e, "null argument");
+  DFRL_CHECK(id >= 0 && id < e->n, "environment id %d out of range", id);
+  DFRL_CHECK(action >= 0 && action < e->B, "action %d out of range", action);
+  env_params p = make_params(e);
+  DFRL_LAUNCH(e->ctx, env_apply_one_kernel, 1, 1, 0, p, e->state, e->draws, e->steps, id, action);
+  return DFRL_OK;
+}
+
+extern "C" int dfrl_env_reset_one(dfrl_env *e, int id) {
+  DFRL_CHECK(e, "null argument");
+  DFRL_CHECK(id >= 0 && id < e->n, "environment id %d out of range", id);
+  env_params p = make_params(e);
+  DFRL_LAUNCH(e->ctx, env_reset_one_kernel, 1, 1, 0, p, e->state, e->draws, id);
+  return DFRL_OK;
+}
+
+extern "C" int dfrl_env_view_one(dfrl_env *e, int id, int8_t *state_host) {
+  DFRL_CHECK(e && state_host, "null argument");
+  DFRL_CHECK(id >= 0 && id < e->n, "environment id %d out of range", id);
+  DFRL_CUDA(cudaMemcpy2DAsync(state_host, 1, e->state + id, e->stride, 1, e->P, cudaMemcpyDeviceToHost,
+                              e->ctx->stream));
+  DFRL_CUDA(cudaStreamSynchronize(e->ctx->stream));
+  return DFRL_OK;
 }
 
 extern "C" int8_t *dfrl_env_state_dev(dfrl_env *e) { return e ? e->state : nullptr; }

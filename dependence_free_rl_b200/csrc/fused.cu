@@ -568,13 +568,16 @@ __device__ __forceinline__ void stash_x0(int8_t *raw_s, int8_t *raw_e, const lea
 // END state of step (t, e) in RAW_E (after stash_x0 + __syncthreads): overflowed terminal state
 // when done (bin[a] -= item, item kept: bin_packing.h:54-61), live env state at the rollout's last
 // step (already there), zeros (row unused) otherwise. One thread per row.
-__device__ __forceinline__ void fix_end_rows(int8_t *raw_e, const learner_rows &L, const x0_pref &x) {
+__device__ __forceinline__ void fix_end_rows(const int8_t *raw_s, int8_t *raw_e, const learner_rows &L,
+                                             const x0_pref &x) {
   if (threadIdx.x < TILE) {
     const int r = threadIdx.x, tt = r / L.E, P = 2 * L.B + 2;
     if (x.done) {
       int a = x.act;
-      raw_e[(2 * a) * TILE + r] -= raw_e[(2 * L.B) * TILE + r];
-      raw_e[(2 * a + 1) * TILE + r] -= raw_e[(2 * L.B + 1) * TILE + r];
+      for (int q = 0; q < P; ++q)  // (the last step's slot holds the live, already reset, state)
+        raw_e[q * TILE + r] = raw_s[q * TILE + r];
+      raw_e[(2 * a) * TILE + r] -= raw_s[(2 * L.B) * TILE + r];
+      raw_e[(2 * a + 1) * TILE + r] -= raw_s[(2 * L.B + 1) * TILE + r];
     } else if (tt != L.T - 1) {
       for (int q = 0; q < P; ++q)
         raw_e[q * TILE + r] = 0;
@@ -657,7 +660,7 @@ __global__ void __launch_bounds__(256, 1) fused_critic_step_kernel(critic_args a
     }
     stash_x0<true>(raw_s, raw_e, L, tile, xp);
     __syncthreads();
-    fix_end_rows(raw_e, L, xp);
+    fix_end_rows(raw_s, raw_e, L, xp);
     __syncthreads();
     encode_x0(smem + SM::X0, raw_e, L.B, L.inv_w, L.inv_h);
     sync_after_smem_writes();
@@ -843,7 +846,7 @@ __global__ void __launch_bounds__(256, 2) fused_gae_kernel(critic_args a) {
     float y2[DC2];
     stash_x0<true>(raw_s, raw_e, L, tile, xp);
     __syncthreads();
-    fix_end_rows(raw_e, L, xp);
+    fix_end_rows(raw_s, raw_e, L, xp);
     __syncthreads();
     encode_x0(smem + SM::X0, raw_e, L.B, L.inv_w, L.inv_h);
     sync_after_smem_writes();

@@ -1,0 +1,150 @@
+// host_api_test -- exercises the C++ mirror of the reference classes on the device and prints
+// "key value" lines that tests/test_host_cpp.py compares with the Python binding of the same C ABI.
+#include <cmath>
+#include <cstdio>
+#include <memory>
+
+#include <apps/bin_packing/bin_packing.h>
+
+static int fails = 0;
+#define EXPECT(c)                                                  \
+  do {                                                             \
+    if (!(c)) {                                                    \
+      std::printf("FAIL %s:%d %s\n", __FILE__, __LINE__, #c);      \
+      ++fails;                                                     \
+    }                                                              \
+  } while (0)
+
+int main() {
+  // ---- per-id environment triple: apply / view / reset (bin_packing.h:53-70)
+  {
+    bp::environment env(3, 7);
+    bp::observation o = env.view(1);
+    EXPECT(o.bins.size() == bp::num_bins && o.bins[0] == std::make_pair(8, 8));
+    EXPECT((o.item == std::make_pair(4, 2)) || (o.item == std::make_pair(1, 2)));
+    bp::action a;
+    a.choice = 2;
+    int placed = 0;
+    while (true) {  // keep filling bin 2 of env 1 until it overflows
+      bp::observation before = env.view(1);
+      env.apply(a, 1);
+      bp::observation after = env.view(1);
+      EXPECT(after.bins[2].first == before.bins[2].first - before.item.first);
+      EXPECT(after.bins[2].second == before.bins[2].second - before.item.second);
+      if (after.bins[2].first < 0 || after.bins[2].second < 0) {
+        EXPECT(after.item == before.item);  // overflow: the item is kept (bin_packing.h:59-61)
+        break;
+      }
+      ++placed;
+    }
+    EXPECT(placed >= 1 && placed <= 4);
+    EXPECT(env.view(0).bins[2] == std::make_pair(8, 8));  // other slots untouched
+    env.reset(1);
+    EXPECT(env.view(1).bins[2] == std::make_pair(8, 8));
+    std::printf("env_triple placed %d\n", placed);
+  }
+  // ---- layers vs model, parameters round trip, observation::to_vector
+  {
+    xylo::model m;
+    m.add_layer(std::make_unique<xylo::full_layer>(32, 16));
+    m.add_layer(std::make_unique<xylo::relu_activation>());
+    m.add_layer(std::make_unique<xylo::full_layer>(16, 8));
+    m.add_layer(std::make_unique<xylo::softmax_layer>());
+    m.set_init_seed(5);
+    xylo::vector p = m.parameters();
+    EXPECT(p.size() == 32 * 16 + 16 + 16 * 8 + 8);
+    for (std::size_t i = 0; i < p.size(); ++i)
+      p[i] = 0.05f * std::sin(0.37f * float(i));
+    m.set_parameters(p);
+    xylo::vector q = m.parameters();
+    double diff = 0;
+    for (std::size_t i = 0; i < p.size(); ++i)
+      diff += std::fabs(p[i] - q[i]);
+    EXPECT(diff == 0);
+    bp::observation ob({8, 8});
+    ob.item = {4, 2};
+    ob.bins[3] = {1, 6};
+    xylo::vector x = xylo::to_vector(ob);
+    EXPECT(x[12] == 0.125f && x[13] == 0.75f && x[14] == 0.5f && x[15] == 0.25f);
+    xylo::matrix out = m.eval(xylo::matrix_view(x.data(), {1, 32}));
+    float s = 0;
+    for (std::size_t j = 0; j < 8; ++j)
+      s += out[0][j];
+    EXPECT(std::fabs(s - 1.f) < 1e-5f);
+    // layer-by-layer forward (reference model::forward) agrees with the fused device eval
+    auto acts = m.forward(xylo::matrix_view(x.data(), {1, 32}));
+    EXPECT(acts.size() == 5);
+    for (std::size_t j = 0; j < 8; ++j)
+      EXPECT(std::fabs(acts.back()[0][j] - out[0][j]) < 1e-6f);
+    // one SGD step through optimizer::step with a host loss-gradient callback (nn.h:594-605)
+    xylo::sgd_optimizer opt(m, 0.1f);
+    opt.step(xylo::matrix_view(x.data(), {1, 32}), [](xylo::matrix_view o) {
+      xylo::matrix g(o.shape());
+      g[0][1] = 1.f;  // d loss / d p1 = 1
+      return g;
+    });
+    xylo::matrix out2 = m.eval(xylo::matrix_view(x.data(), {1, 32}));
+    EXPECT(out2[0][1] < out[0][1]);  // descending on p1
+    std::printf("model_p1 %.9g %.9g\n", out[0][1], out2[0][1]);
+    // discrete_action rules (rl.h:45-74): KAT of SURVEY appendix A
+    bp::action a;
+    a.choice = 2;
+    xylo::vector pr({8});
+    pr = 0.1f;
+    pr[2] = 0.3f;
+    xylo::vector g({8});
+    a.softmax_gradient_log(pr, g, 2.f);
+    EXPECT(std::fabs(g[0] - 0.2f) < 1e-6f && std::fabs(g[2] + 1.4f) < 1e-6f);
+    a.distrib = xylo::vector({8});
+    *a.distrib = 0.125f;
+    pr = 0.1f;
+    pr[2] = 0.2f;
+    a.clipped_gradient(pr, g, 1.5f);
+    EXPECT(std::fabs(g[2] + 9.f) < 1e-5f && g[0] == 0.f);
+    a.clipped_gradient(pr, g, -1.5f);
+    EXPECT(std::fabs(g[2] - 12.f) < 1e-5f);
+  }
+  // ---- the PPO trainer loop through the mirrored classes (same nets / seeds as the Python side)
+  {
+    const std::size_t n = 4096;
+    const int T = 4, iters = 5;
+    const float row_scale = 32.f / float(n * T);
+    xylo::model pm, vm;
+    pm.add_layer(std::make_unique<xylo::full_layer>(32, 64));
+    pm.add_layer(std::make_unique<xylo::relu_activation>());
+    pm.add_layer(std::make_unique<xylo::full_layer>(64, 64));
+    pm.add_layer(std::make_unique<xylo::relu_activation>());
+    pm.add_layer(std::make_unique<xylo::full_layer>(64, 8));
+    pm.add_layer(std::make_unique<xylo::softmax_layer>());
+    vm.add_layer(std::make_unique<xylo::full_layer>(32, 64));
+    vm.add_layer(std::make_unique<xylo::relu_activation>());
+    vm.add_layer(std::make_unique<xylo::full_layer>(64, 64));
+    vm.add_layer(std::make_unique<xylo::relu_activation>());
+    vm.add_layer(std::make_unique<xylo::full_layer>(64, 1));
+    pm.set_init_seed(1234);
+    vm.set_init_seed(1235);
+    xylo::sgd_optimizer po(pm, 1e-4f * row_scale), vo(vm, 1e-5f * row_scale);
+    xylo::replay_buffer<bp::action, bp::observation> rb;
+    bp::environment env(n, 1234);
+    xylo::policy_gradient_policy<bp::action, bp::observation> policy(pm);
+    bp::agent agent(policy, env, rb);
+    bp::ppo_learner learner(rb, pm, po, vm, vo, 0.99f);
+    for (int it = 0; it < iters; ++it) {
+      agent.play_steps(T);
+      learner.step();
+      rb.forget();
+    }
+    dfrl_trainer_stats s = rb.stats();
+    xylo::vector p = pm.parameters(), v = vm.parameters();
+    double ps = 0, vs = 0;
+    for (std::size_t i = 0; i < p.size(); ++i)
+      ps += (double)p[i] * (double)(i % 7 + 1);
+    for (std::size_t i = 0; i < v.size(); ++i)
+      vs += (double)v[i] * (double)(i % 7 + 1);
+    EXPECT(s.env_steps == (long long)(n * T * iters));
+    std::printf("ppo env_steps %lld episodes %lld reward_sum %.0f policy_sum %.17g value_sum %.17g\n", s.env_steps,
+                s.episodes, s.reward_sum, ps, vs);
+  }
+  std::printf(fails ? "FAILED %d\n" : "OK\n", fails);
+  return fails ? 1 : 0;
+}

@@ -1,0 +1,291 @@
+// xylo/rl.h -- environment / agent / policy / learner / replay_buffer with the reference's
+// signatures (xylo/rl.h:22-392), batched on the device.
+//
+// What changes underneath: the reference runs one environment object per agent and one pthread per
+// agent (ppo_training.cc:28-61). Here ONE environment object holds N independent slots in HBM and
+// `id` (already a parameter of environment::apply / view / reset, rl.h:163-170) selects a slot;
+// ONE agent drives every slot, so agent::step() is one transition of every environment and
+// play_steps(n) is the whole rollout phase of a trainer iteration in one launch. The replay buffer
+// is the struct-of-arrays rollout record on the device (dfrl_trainer); sample_td() has no host-side
+// meaning any more, forget() is implicit (the next rollout overwrites the records and open
+// trajectories continue from the live state, rl.h:274-291).
+#ifndef XYLO_RL_
+#define XYLO_RL_
+
+#include <optional>
+#include <random>
+#include <vector>
+
+#include <xylo/nn.h>
+#include <xylo/tensor.h>
+
+namespace xylo {
+
+// The reference's global generator (tensor.h:17, tensor.cc:71-75): only the per-id slow path draws
+// from it (one uniform per sampled action); batched rollouts use Philox keyed by (seed, env, step).
+inline std::minstd_rand0 &default_generator() {
+  static std::minstd_rand0 g(std::random_device{}());
+  return g;
+}
+
+template <typename T> vector to_vector(const T &t) {
+  vector result({t.length()});
+  t.to_vector(result);
+  return result;
+}
+
+template <std::size_t range> struct discrete_action {
+  static std::size_t cardinality() { return range; }
+  std::size_t choice = 0;
+  std::optional<vector> distrib;
+
+  // std::discrete_distribution semantics (tensor.cc:467-470), evaluated by dfrl_sample.
+  void from_vector(vector_view a) {
+    if (a.size() != range)
+      throw xeno::error("action vector has the wrong size");
+    double u = std::generate_canonical<double, 53>(default_generator());
+    device_buffer p(range), ud(2), act(1);
+    p.upload(a.data(), range);
+    check(dfrl_memcpy_h2d(device::get(), ud.get(), &u, sizeof(double)));
+    check(dfrl_sample(device::get(), p.get(), 1, (int)range, reinterpret_cast<const double *>(ud.get()),
+                      reinterpret_cast<uint8_t *>(act.get()), nullptr));
+    uint8_t c = 0;
+    check(dfrl_memcpy_d2h(device::get(), &c, act.get(), 1));
+    choice = c;
+    distrib = vector(a);
+  }
+  void from_vector_deterministic(vector_view a) { choice = argmax(a); }
+
+  // Loss-gradient rules of one row (rl.h:45-74), evaluated by dfrl_loss_grad.
+  void softmax_gradient_log(vector_view input, vector_view output, float advantage) const {
+    row_rule(DFRL_LOSS_SOFTMAX_LOG, input, output, advantage);
+  }
+  void clipped_gradient(vector_view input, vector_view output, float advantage) const {
+    row_rule(DFRL_LOSS_CLIPPED, input, output, advantage);
+  }
+
+private:
+  void row_rule(int kind, vector_view input, vector_view output, float advantage) const {
+    if (input.size() != range || output.size() != range)
+      throw xeno::error("action vector has the wrong size");
+    device_buffer p(range), o(range), adv(1), act(1), po(1);
+    p.upload(input.data(), range);
+    adv.upload(&advantage, 1);
+    uint8_t c = (uint8_t)choice;
+    check(dfrl_memcpy_h2d(device::get(), act.get(), &c, 1));
+    float pold = distrib ? (*distrib)[choice] : 1.f;
+    po.upload(&pold, 1);
+    check(dfrl_loss_grad(device::get(), kind, p.get(), reinterpret_cast<const uint8_t *>(act.get()), adv.get(),
+                         po.get(), 0.f, 1, (int)range, o.get()));
+    o.download(output.data(), range);
+  }
+};
+
+template <typename A, typename S> class environment {
+public:
+  virtual ~environment() = default;
+
+  virtual void apply(const A &action, std::size_t id) = 0;
+  virtual S view(std::size_t id) const = 0;
+  virtual void reset(std::size_t id) = 0;
+
+  // Batched extension: the device object holding every slot, and how many there are.
+  virtual dfrl_env *device_env() { return nullptr; }
+  virtual std::size_t size() const { return 1; }
+};
+
+template <typename A, typename S> class policy {
+public:
+  virtual ~policy() = default;
+
+  virtual A react(const S &state) const = 0;
+
+  // NN-backed policies run inside the rollout kernel: the net, and sample vs argmax.
+  virtual model *backing_model() const { return nullptr; }
+  virtual bool deterministic() const { return false; }
+};
+
+// What the agent (rollout side) and the learner (update side) share through the replay buffer:
+// the pieces of one dfrl_trainer. The trainer is created by the first rollout.
+struct rollout_store {
+  dfrl_env *env = nullptr;
+  model *policy_model = nullptr;
+  bool deterministic = false;
+  std::size_t obs_cols = 0;
+  int algo = -1;  // DFRL_ALGO_*, -1: no learner attached (evaluation only)
+  model *value_model = nullptr;
+  optimizer *policy_opt = nullptr, *value_opt = nullptr;
+  float gamma = 0.99f, lambda = 0.95f;
+  int epochs = 4;
+  float kl_target = 1e-9f, kl_beta0 = 1.f;
+  dfrl_trainer *trainer = nullptr;
+  int work = 0;
+  bool rolled = false;
+  // evaluation-only bookkeeping (agent::play_one_episode with a deterministic policy)
+  double eval_reward = 0;
+  long long eval_episodes = 0;
+
+  ~rollout_store() { drop(); }
+  void drop() {
+    if (trainer)
+      dfrl_trainer_destroy(trainer);
+    trainer = nullptr;
+  }
+  void ensure_trainer(int w) {
+    if (trainer && w == work)
+      return;
+    if (algo < 0)
+      throw xeno::error("no learner is attached to this replay buffer");
+    if (!env || !policy_model)
+      throw xeno::error("no agent is attached to this replay buffer");
+    drop();
+    dfrl_trainer_config c;
+    dfrl_trainer_config_default(&c);
+    c.algo = algo;
+    c.work = w;
+    c.gamma = gamma;
+    c.lambda = lambda;
+    c.epochs = epochs;
+    c.kl_target = kl_target;
+    c.kl_beta0 = kl_beta0;
+    c.policy_opt = policy_opt->kind();
+    c.policy_lr = policy_opt->rate();
+    c.policy_wd = policy_opt->weight_decay();
+    c.adam_beta1 = policy_opt->beta1();
+    c.adam_beta2 = policy_opt->beta2();
+    if (value_opt) {
+      c.value_opt = value_opt->kind();
+      c.value_lr = value_opt->rate();
+      c.value_wd = value_opt->weight_decay();
+    }
+    c.action_mode = deterministic ? DFRL_ACT_ARGMAX : DFRL_ACT_SAMPLE;
+    check(dfrl_trainer_create(device::get(), &c, env, policy_model->handle(obs_cols),
+                              value_model ? value_model->handle(obs_cols) : nullptr, &trainer));
+    work = w;
+  }
+};
+
+template <typename A, typename S> class replay_buffer {
+public:
+  // learner::step() then forget() (ppo_training.cc:63-65): the device records are overwritten by
+  // the next rollout; open trajectories continue from the live environment state.
+  void forget() {}
+
+  dfrl_trainer_stats stats() {
+    dfrl_trainer_stats s{};
+    if (store_.trainer)
+      check(dfrl_trainer_get_stats(store_.trainer, &s));
+    return s;
+  }
+  rollout_store &store() { return store_; }
+
+private:
+  rollout_store store_;
+};
+
+// total_rewards(rb.sample_td()) of the evaluation loop (ppo_training.cc:75-79).
+template <typename A, typename S> float total_rewards(replay_buffer<A, S> &rb) {
+  rollout_store &s = rb.store();
+  if (s.algo < 0)
+    return (float)s.eval_reward;
+  return (float)rb.stats().reward_sum;
+}
+
+template <typename A, typename S> class agent {
+public:
+  explicit agent(const policy<A, S> &p, environment<A, S> &env, replay_buffer<A, S> &rb, std::size_t id = 0)
+      : id_(id), policy_(p), env_(env), replay_buffer_(rb) {
+    rollout_store &s = rb.store();
+    s.env = env.device_env();
+    s.policy_model = p.backing_model();
+    s.deterministic = p.deterministic();
+    s.obs_cols = S::length();
+    if (!s.env || !s.policy_model)
+      throw xeno::error("the agent needs a device environment and a model-backed policy (no CPU path)");
+  }
+  virtual ~agent() = default;
+
+  // One transition of EVERY environment slot. Returns whether any episode is still open (always
+  // true for the batched environment: finished slots are reset on the device, rl.h:341-346).
+  bool step() {
+    play_steps(1);
+    return true;
+  }
+
+  // agent::play_one_episode (rl.h:351-354) for every slot. With a REINFORCE learner attached this
+  // is the rollout of one trainer iteration; with a deterministic policy and no learner it is the
+  // evaluation loop of the trainer mains / deep_agent.cc.
+  void play_one_episode() {
+    rollout_store &s = replay_buffer_.store();
+    if (s.algo < 0) {
+      double mean = 0;
+      long long steps = 0;
+      check(dfrl_eval_argmax(device::get(), s.env, s.policy_model->handle(s.obs_cols), 1, &mean, &steps));
+      s.eval_reward += mean * (double)env_.size();
+      s.eval_episodes += (long long)env_.size();
+      return;
+    }
+    if (s.algo != DFRL_ALGO_REINFORCE)
+      throw xeno::error("play_one_episode needs the REINFORCE learner (episodic records)");
+    s.ensure_trainer(1);
+    check(dfrl_trainer_rollout(s.trainer, nullptr, nullptr, nullptr));
+    s.rolled = true;
+  }
+
+  void play_steps(std::size_t n) {
+    rollout_store &s = replay_buffer_.store();
+    if (s.algo == DFRL_ALGO_REINFORCE)
+      throw xeno::error("the REINFORCE learner records whole episodes: use play_one_episode()");
+    s.ensure_trainer((int)n);
+    check(dfrl_trainer_rollout(s.trainer, nullptr, nullptr, nullptr));
+    s.rolled = true;
+  }
+
+  // Parity runs: teacher-forced rollout from host tapes, all [n][size()] step-major (dfrl.h).
+  void play_steps(std::size_t n, const uint8_t *items, const uint8_t *actions, const double *uniforms) {
+    rollout_store &s = replay_buffer_.store();
+    s.ensure_trainer((int)n);
+    check(dfrl_trainer_rollout(s.trainer, items, actions, uniforms));
+    s.rolled = true;
+  }
+
+  std::size_t id() { return id_; }
+
+protected:
+  // Kept for signature compatibility; the bin-packing rules they express (bin_packing.h:94-106)
+  // run inside the environment kernel.
+  virtual bool game_over(const S &state) = 0;
+  virtual float get_reward(const S &state1, const S &state2) = 0;
+
+  std::size_t id_;
+  const policy<A, S> &policy_;
+  environment<A, S> &env_;
+  replay_buffer<A, S> &replay_buffer_;
+};
+
+template <typename A, typename S> class learner {
+public:
+  explicit learner(replay_buffer<A, S> &rb, model &policy_model, optimizer &policy_optimizer, float gamma = 0.99)
+      : replay_buffer_(rb), policy_model_(policy_model), policy_optimizer_(policy_optimizer), gamma_(gamma) {}
+  virtual ~learner() = default;
+
+  void step() { learn(); }
+
+  virtual void learn() = 0;
+
+protected:
+  void learn_on_device() {
+    rollout_store &s = replay_buffer_.store();
+    if (!s.trainer || !s.rolled)
+      throw xeno::error("learn() before any rollout");
+    check(dfrl_trainer_learn(s.trainer));
+  }
+  replay_buffer<A, S> &replay_buffer_;
+  model &policy_model_;
+  optimizer &policy_optimizer_;
+  float gamma_;
+};
+
+} // namespace xylo
+
+#endif // XYLO_RL_

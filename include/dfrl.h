@@ -162,6 +162,13 @@ int dfrl_env_load_item_tape(dfrl_env *env, const uint8_t *tape_host, int len);
  * next item is drawn. actions_dev: uint8 [N]. done_dev (optional): uint8 [N]. */
 int dfrl_env_step(dfrl_env *env, const uint8_t *actions_dev, uint8_t *done_dev,
                   int8_t *terminal_state_dev);
+/* The reference triple for ONE environment id (bin_packing.h:53-70; rl.h:163-170): apply() leaves
+ * an overflowed bin negative and draws no item, reset() refills the bins and draws the next item,
+ * view() copies the int8 [2B+2] state of `id` to the host (synchronising). The batched calls above
+ * are the fast path; these keep environment<A,S>'s per-id signatures usable. */
+int dfrl_env_apply_one(dfrl_env *env, int id, int action);
+int dfrl_env_reset_one(dfrl_env *env, int id);
+int dfrl_env_view_one(dfrl_env *env, int id, int8_t *state_host /* [2B+2] */);
 /* view(id) for all ids (bin_packing.h:65): device pointer to the int8 [2B+2][stride] planes;
  * stride = N rounded up to 16 so that every plane starts 16-byte aligned. Device-side buffers
  * shaped like the state (terminal_state_dev) use the same stride. */

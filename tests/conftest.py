@@ -28,3 +28,24 @@ def pytest_collection_modifyitems(config, items):
     for it in items:
         if "gpu" in it.keywords:
             it.add_marker(skip)
+
+
+# ---- fixtures shared by the GPU suites -------------------------------------------------------
+@pytest.fixture(scope="module")
+def D():
+    import dependence_free_rl_b200 as d
+    return d
+
+
+@pytest.fixture(scope="module")
+def ctx(D):
+    c = D.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def orc():
+    from oracle import orc as o
+    o.build()
+    return o

@@ -15,24 +15,6 @@ pytestmark = pytest.mark.gpu
 U = dict(np.load(os.path.join(refcases.GOLDEN_DIR, "units.npz")))
 
 
-@pytest.fixture(scope="module")
-def D():
-    import dependence_free_rl_b200 as d
-    return d
-
-
-@pytest.fixture(scope="module")
-def ctx(D):
-    c = D.Context(0)
-    yield c
-    c.close()
-
-
-@pytest.fixture(scope="module")
-def orc():
-    from oracle import orc as o
-    o.build()
-    return o
 
 
 def test_device_is_blackwell(ctx):
@@ -445,8 +427,23 @@ def test_trainer_vs_oracle_with_uniform_tape(D, ctx, orc):
     pl = D.fc_layers([32, 64, 64, 8], D.SOFTMAX)
     vl = D.fc_layers([32, 64, 64, 1])
     pnet, vnet = orc.Net(pl, 32), orc.Net(vl, 32)
-    pp = (rng.standard_normal(pnet.param_count()) * 0.1).astype(np.float32)
-    vp = (rng.standard_normal(vnet.param_count()) * 0.1).astype(np.float32)
+    # relu'(x) is discontinuous at 0: a pre-activation within rounding distance of zero can take
+    # either sign under equally valid summation orders (the fused kernels use bf16 hi/lo split
+    # operands, ~1e-5 relative) and then moves a whole gradient row. Hidden biases of +-5 with small
+    # weights keep every pre-activation far from zero -- half of the units always on, half always
+    # off -- so both mask states are exercised and the comparison below is a strict 1e-4 one.
+    def safe_params(dims, seed):
+        r = np.random.default_rng(seed)
+        parts = []
+        for li, (a, b) in enumerate(zip(dims[:-1], dims[1:])):
+            parts.append((r.standard_normal(a * b) * 0.05).astype(np.float32))
+            bias = (r.standard_normal(b) * 0.05).astype(np.float32)
+            if li < len(dims) - 2:
+                bias += np.where(np.arange(b) % 2 == 0, 5.0, -5.0).astype(np.float32)
+            parts.append(bias)
+        return np.concatenate(parts)
+    pp, vp = safe_params([32, 64, 64, 8], 1), safe_params([32, 64, 64, 1], 2)
+    assert pp.size == pnet.param_count() and vp.size == vnet.param_count()
     policy, value = D.Model(ctx, pl, 32), D.Model(ctx, vl, 32)
     policy.set_parameters(pp)
     value.set_parameters(vp)
@@ -455,13 +452,17 @@ def test_trainer_vs_oracle_with_uniform_tape(D, ctx, orc):
     st = orc.env_reset_all(ecfg, n, first)
     env = D.Environment(ctx, n)
     env.set_state(st)
-    tr = D.Trainer(ctx, env, policy, value, algo=D.PPO, work=T, policy_lr=1e-5, value_lr=1e-5,
+    # (activations of ~5 make the SUM gradients large: rates scaled down so that 20 updates stay tame)
+    tr = D.Trainer(ctx, env, policy, value, algo=D.PPO, work=T, policy_lr=2e-8, value_lr=2e-8,
                    action_mode=D.ACT_SAMPLE)
-    lr = orc.Learner(orc.train_cfg(orc.PPO, T, policy_lr=1e-5, value_lr=1e-5), ecfg, pnet, pp, vnet, vp)
-    for it in range(3):
+    lr = orc.Learner(orc.train_cfg(orc.PPO, T, policy_lr=2e-8, value_lr=2e-8), ecfg, pnet, pp, vnet, vp)
+    done_at_last_step = done_mid = 0
+    for it in range(5):
         items = rng.integers(0, 2, (T, n)).astype(np.uint8)
         u = rng.random((T, n))
         ro = orc.rollout(ecfg, st, pnet, lr.pparams, T, 0, items, u=u)
+        done_at_last_step += int(ro["done"][T - 1].sum())
+        done_mid += int(ro["done"][:T - 1].sum())
         tr.rollout(items=items, u=u)
         ga = tr.read(D.F_REC_ACTION)
         agree = np.mean(ga == ro["action"])
@@ -473,15 +474,13 @@ def test_trainer_vs_oracle_with_uniform_tape(D, ctx, orc):
         tr.learn()
         close(tr.read(D.F_ADVANTAGE), out["adv"], what="adv")
         close(tr.read(D.F_VALUE_TARGET), out["targets"], what="targets")
-        # The fused tensor-core kernels evaluate the nets with bf16 hi/lo split operands (~1e-5
-        # relative): a relu pre-activation within that distance of zero can take the other sign
-        # and move the few gradient entries fed by that one row. Norm-wise 1e-4 + bulk criterion.
-        refcases.close_bulk(tr.read(D.F_VALUE_GRAD), out["value_grad"], what="vgrad")
-        refcases.close_bulk(tr.read(D.F_POLICY_GRAD_LOG), out["policy_grads"], what="pgrads")
+        close(tr.read(D.F_VALUE_GRAD), out["value_grad"], what="vgrad")
+        close(tr.read(D.F_POLICY_GRAD_LOG), out["policy_grads"], what="pgrads")
         close(policy.parameters(), lr.pparams, what="pparams")
         close(value.parameters(), lr.vparams, what="vparams")
+    assert done_at_last_step > 10 and done_mid > 10  # both kinds of end rows were exercised
     s = tr.stats()
-    assert s["env_steps"] == 3 * n * T
+    assert s["env_steps"] == 5 * n * T
     assert s["reward_sum"] + s["episodes"] == s["env_steps"]
     tr.close(); env.close(); policy.close(); value.close()
 

@@ -1,0 +1,104 @@
+"""The C++20 host mirror of the reference classes (dependence_free_rl_b200/host): builds with g++
+against include/dfrl.h only, and on a GPU produces exactly what the Python binding of the same C
+ABI produces for the same configuration."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import refcases
+
+ROOT = refcases.ROOT
+HOST = os.path.join(ROOT, "dependence_free_rl_b200", "host")
+BINS = ["ppo_training", "ac_training", "pg_training", "deep_agent", "host_api_test"]
+
+
+def _build():
+    subprocess.check_call(["make", "-C", HOST, "-j8"], stdout=subprocess.DEVNULL)
+
+
+def test_host_mirror_builds_and_keeps_reference_signatures():
+    _build()
+    for b in BINS:
+        assert os.path.exists(os.path.join(HOST, ".out", b)), b
+    rl = open(os.path.join(HOST, "xylo", "rl.h")).read()
+    pg = open(os.path.join(HOST, "xylo", "policy_gradient.h")).read()
+    nn = open(os.path.join(HOST, "xylo", "nn.h")).read()
+    # signatures the north star names (reference rl.h:163-170, 317-392; policy_gradient.h:92-317; nn.h:20-33)
+    for sig in ["virtual void apply(const A &action, std::size_t id) = 0;", "virtual S view(std::size_t id) const = 0;",
+                "virtual void reset(std::size_t id) = 0;", "virtual A react(const S &state) const = 0;",
+                "explicit agent(const policy<A, S> &p, environment<A, S> &env, replay_buffer<A, S> &rb, std::size_t id = 0)",
+                "void play_steps(std::size_t n)", "void play_one_episode()", "virtual void learn() = 0;"]:
+        assert sig in rl, sig
+    for cls in ["policy_gradient_learner", "actor_critic_learner", "ppo_learner", "kl_ppo_learner",
+                "policy_gradient_policy", "policy_gradient_deterministic_policy"]:
+        assert f"class {cls}" in pg, cls
+    for sig in ["virtual matrix forward(matrix_view t) = 0;", "virtual matrix backward(matrix_view input, matrix_view loss) = 0;",
+                "virtual vector gradient(matrix_view input, matrix_view backprop) = 0;",
+                "void step(matrix_view input, const loss_grad_func &loss_grad)",
+                "sgd_optimizer(model &m, float rate, float weight_decay = 0.0f)",
+                "adam_optimizer(model &m, float rate, float beta1 = 0.9, float beta2 = 0.999)"]:
+        assert sig in nn, sig
+    # the host side reaches CUDA only through the C ABI
+    for dirpath, _, files in os.walk(HOST):
+        for f in files:
+            if f.endswith((".h", ".cc")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "cuda_runtime" not in txt and "<<<" not in txt, f
+
+
+@pytest.mark.gpu
+def test_host_api_matches_python_binding(D, ctx):
+    _build()
+    out = subprocess.run([os.path.join(HOST, ".out", "host_api_test")], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    lines = {l.split()[0]: l.split()[1:] for l in out.stdout.splitlines() if l and not l.startswith("OK")}
+    assert "FAIL" not in out.stdout
+    got = dict(zip(lines["ppo"][0::2], lines["ppo"][1::2]))
+    # the same run through the Python binding
+    n, T, iters = 4096, 4, 5
+    rs = np.float32(32.0) / np.float32(n * T)
+    policy = D.Model(ctx, D.fc_layers([32, 64, 64, 8], D.SOFTMAX), 32)
+    value = D.Model(ctx, D.fc_layers([32, 64, 64, 1]), 32)
+    policy.init_parameters(1234)
+    value.init_parameters(1235)
+    env = D.Environment(ctx, n, seed=1234)
+    tr = D.Trainer(ctx, env, policy, value, algo=D.PPO, work=T, policy_lr=float(np.float32(1e-4) * rs),
+                   value_lr=float(np.float32(1e-5) * rs))
+    tr.iterate(iters)
+    s = tr.stats()
+    w = (np.arange(policy.n_params) % 7 + 1).astype(np.float64)
+    wv = (np.arange(value.n_params) % 7 + 1).astype(np.float64)
+    assert int(got["env_steps"]) == s["env_steps"] == n * T * iters
+    assert int(got["episodes"]) == s["episodes"]
+    assert float(got["reward_sum"]) == s["reward_sum"]
+    assert float(got["policy_sum"]) == float(np.sum(policy.parameters().astype(np.float64) * w))
+    assert float(got["value_sum"]) == float(np.sum(value.parameters().astype(np.float64) * wv))
+    tr.close(); env.close(); policy.close(); value.close()
+
+
+@pytest.mark.gpu
+def test_deep_agent_cpp_known_answer(tmp_path):
+    # deep_agent.cc with weights.20: 26.553 +- 0.028 per 10 000-episode round (reference deep.log)
+    _build()
+    U = np.load(os.path.join(refcases.GOLDEN_DIR, "units.npz"))
+    wf = tmp_path / "weights.20"
+    U["weights20"].astype("<f4").tofile(wf)
+    out = subprocess.run([os.path.join(HOST, ".out", "deep_agent"), str(wf), "8192", "4"], capture_output=True,
+                         text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    mean = float(out.stdout.split()[1])
+    assert 26.45 < mean < 26.65, out.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("binary,args", [("ppo_training", ["4096", "6", "5"]), ("ac_training", ["2048", "4"]),
+                                         ("pg_training", ["256", "3"])])
+def test_trainer_mains_run(binary, args):
+    _build()
+    out = subprocess.run([os.path.join(HOST, ".out", binary)] + args, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    last = out.stdout.strip().splitlines()[-1].split()
+    kv = dict(zip(last[0::2], last[1::2]))
+    assert int(kv["env_steps"]) > 0 and float(kv["reward_sum"]) + int(kv["episodes"]) == int(kv["env_steps"])
