@@ -354,7 +354,7 @@ def run_ours(args):
     dist = None
     nccl_id = None
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: ONE JSON line only
+        os.environ.pop("NCCL_DEBUG", None)  # keep NCCL's version banner off stdout: ONE JSON line only
         import torch.distributed as dist_mod
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist_mod.init_process_group("gloo", rank=rank, world_size=world)
@@ -363,6 +363,15 @@ def run_ours(args):
         dist.broadcast_object_list(obj, src=0)
         nccl_id = obj[0]
     ctx = D.Context(local_rank, world, rank, nccl_id)
+    exchange = "none (single rank)"
+    if world > 1:
+        exchange = "ncclAllReduce + optimizer kernel"
+        if not args.no_p2p:
+            # fused exchange: IPC handles of every rank's buffer -> peers mapped over NVLink
+            handles = [None] * world
+            dist.all_gather_object(handles, ctx.p2p_export())
+            ctx.p2p_attach(handles)
+            exchange = "peer-memory pull over NVLink fused with the optimizer (one kernel per update)"
     peaks = load_peaks()
 
     main = measure(D, ctx, dist, args, args.envs_per_gpu, world, rank, args.steps, args.warmup, True)
@@ -395,7 +404,7 @@ def run_ours(args):
             "metric": "ppo_binpacking_env_steps_per_sec", "value": main["value"], "unit": "env-steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": main["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": workload_config(args),
+            "data": "synthetic", "config": {**workload_config(args), "gradient_exchange": exchange},
             "e2e": main["e2e"], "gpu_launches": int(round(main["launches_per_step"] * args.steps)),
             "clocks": {"sm_mhz": clocks.get("sm_mhz"), "sm_max_mhz": clocks.get("sm_max_mhz"),
                        "reasons": clocks.get("reasons", []), "samples": clocks.get("samples", 0)},
@@ -421,6 +430,7 @@ def main():
     ap.add_argument("--ref-iters", type=int, default=10)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-c2", action="store_true")
+    ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: NCCL all-reduce instead of the fused peer-memory exchange")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -65,6 +65,9 @@ PROTOTYPES = {
     "dfrl_launch_count": (C.c_longlong, [vp]),
     "dfrl_umma_selftest": (i32, [vp, i32, i32, i32, C.POINTER(f32)]),
     "dfrl_debug_policy_clocks": (i32, [vp, vp, i32]),
+    "dfrl_p2p_export": (i32, [vp, vp]),
+    "dfrl_p2p_attach": (i32, [vp, vp]),
+    "dfrl_p2p_attached": (i32, [vp]),
     "dfrl_env_config_default": (None, [C.POINTER(EnvConfig)]),
     "dfrl_env_create": (i32, [vp, C.POINTER(EnvConfig), C.POINTER(vp)]),
     "dfrl_env_destroy": (i32, [vp]),

@@ -42,6 +42,22 @@ class Context:
         check(lib.dfrl_nccl_unique_id(buf))
         return bytes(buf)
 
+    # ---- flat-gradient exchange over NVLink peer memory (dfrl_p2p_*) ----
+    def p2p_export(self):
+        """64-byte CUDA IPC handle of this rank's exchange buffer (gather these over all ranks)."""
+        buf = (C.c_char * 64)()
+        check(lib.dfrl_p2p_export(self.h, buf))
+        return bytes(buf)
+
+    def p2p_attach(self, handles):
+        """handles: the exported handle of every rank, in rank order."""
+        assert len(handles) == self.nranks
+        buf = (C.c_char * (64 * self.nranks)).from_buffer_copy(b"".join(handles))
+        check(lib.dfrl_p2p_attach(self.h, buf))
+
+    def p2p_attached(self):
+        return bool(lib.dfrl_p2p_attached(self.h))
+
     def close(self):
         if self.h:
             lib.dfrl_destroy(self.h)

@@ -57,6 +57,19 @@ void dfrl_set_error(const char *fmt, ...);
 // ------------------------------------------------------------------ context -----------------
 struct dfrl_ctx;
 void dfrl_profile_mark(dfrl_ctx *ctx, const char *name, int end);
+
+// Flat-gradient exchange over NVLink peer memory (context.cu, fused.cu). Every rank owns one
+// allocation [2 slots][cap floats] + flags, IPC-mapped by every other rank of the node.
+constexpr int DFRL_P2P_MAX_RANKS = 8;
+constexpr size_t DFRL_P2P_CAP = 1 << 18;  // floats per slot (1 MB): >= the largest flat gradient
+struct dfrl_p2p {
+  float *local = nullptr;            // [2][DFRL_P2P_CAP] floats, then 2 unsigned flags
+  float *peer[DFRL_P2P_MAX_RANKS];   // peer[r]: rank r's allocation mapped here (own rank: local)
+  unsigned epoch = 0;                // exchanges issued so far (identical on every rank)
+  bool attached = false;
+};
+static inline unsigned *dfrl_p2p_flags(float *base) { return reinterpret_cast<unsigned *>(base + 2 * DFRL_P2P_CAP); }
+
 struct dfrl_ctx {
   int device = 0;
   int nranks = 1, rank = 0;
@@ -70,8 +83,7 @@ struct dfrl_ctx {
   // scratch arena (grown on demand, never shrunk): transient kernel workspaces
   void *scratch = nullptr;
   size_t scratch_bytes = 0;
-  // P2P all-reduce state (see allreduce.cu)
-  void *p2p = nullptr;
+  dfrl_p2p p2p;
   // per-kernel event timing (dfrl_profile_*)
   int profiling = 0;
   void *prof = nullptr;

@@ -135,6 +135,11 @@ extern "C" int dfrl_destroy(dfrl_ctx *ctx) {
     g_nccl.destroy(ctx->nccl_comm);
   if (ctx->scratch)
     cudaFree(ctx->scratch);
+  for (int r = 0; r < ctx->nranks && ctx->p2p.attached; ++r)
+    if (r != ctx->rank && ctx->p2p.peer[r])
+      cudaIpcCloseMemHandle(ctx->p2p.peer[r]);
+  if (ctx->p2p.local)
+    cudaFree(ctx->p2p.local);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->stream);
@@ -326,6 +331,48 @@ extern "C" int dfrl_timer_stop(dfrl_ctx *ctx, float *ms_out) {
   DFRL_CUDA(cudaEventElapsedTime(ms_out, ctx->ev0, ctx->ev1));
   return DFRL_OK;
 }
+
+// ------------------------------------------------------------------ peer memory --------------
+// One node, one process per GPU: every rank cudaMalloc's its exchange buffer, exports a CUDA IPC
+// handle, the host side gathers the handles of all ranks (any transport) and every rank maps its
+// peers' buffers. The fused kernels then read peer gradients straight over NVLink.
+extern "C" int dfrl_p2p_export(dfrl_ctx *ctx, void *handle64_host) {
+  DFRL_CHECK(ctx && handle64_host, "null argument");
+  DFRL_CHECK(ctx->nranks <= DFRL_P2P_MAX_RANKS, "at most %d ranks per node", DFRL_P2P_MAX_RANKS);
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  DFRL_CUDA(cudaSetDevice(ctx->device));
+  if (!ctx->p2p.local) {
+    const size_t bytes = sizeof(float) * 2 * DFRL_P2P_CAP + 64;
+    DFRL_CUDA(cudaMalloc(&ctx->p2p.local, bytes));
+    DFRL_CUDA(cudaMemset(ctx->p2p.local, 0, bytes));
+  }
+  cudaIpcMemHandle_t h;
+  DFRL_CUDA(cudaIpcGetMemHandle(&h, ctx->p2p.local));
+  memcpy(handle64_host, &h, 64);
+  return DFRL_OK;
+}
+
+extern "C" int dfrl_p2p_attach(dfrl_ctx *ctx, const void *all_handles_host) {
+  DFRL_CHECK(ctx && all_handles_host, "null argument");
+  DFRL_CHECK(ctx->p2p.local, "dfrl_p2p_export must be called first");
+  DFRL_CHECK(!ctx->p2p.attached, "peers already attached");
+  DFRL_CUDA(cudaSetDevice(ctx->device));
+  for (int r = 0; r < ctx->nranks; ++r) {
+    if (r == ctx->rank) {
+      ctx->p2p.peer[r] = ctx->p2p.local;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char *)all_handles_host + 64 * r, 64);
+    void *p = nullptr;
+    DFRL_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->p2p.peer[r] = (float *)p;
+  }
+  ctx->p2p.attached = true;
+  return DFRL_OK;
+}
+
+extern "C" int dfrl_p2p_attached(dfrl_ctx *ctx) { return ctx && ctx->p2p.attached ? 1 : 0; }
 
 // ------------------------------------------------------------------ collectives --------------
 extern "C" int dfrl_allreduce_sum(dfrl_ctx *ctx, float *buf_dev, size_t n) {

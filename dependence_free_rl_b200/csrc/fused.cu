@@ -337,11 +337,11 @@ constexpr uint32_t TC_L1 = 0, TC_L2 = 64, TC_L3 = 128, TC_DH2 = 160, TC_DH1 = 22
 
 // TMEM accumulator -> y = acc * c + bias_scaled, relu -> forward-format hi/lo panel. Returns the relu mask
 // of this thread's columns (bit j = column col0 + j was > 0); optionally hands y back.
-template <int D, bool WRITE_PANEL, bool KEEP>
+template <int D, int NWG, bool WRITE_PANEL, bool KEEP>
 __device__ __forceinline__ uint32_t epi_hidden_fwd(uint32_t tmem_acc, const tid_t &t, float c,
                                                    const float *__restrict__ bias, uint8_t *hi, uint8_t *lo,
                                                    float *keep) {
-  constexpr int DC = D / 2;
+  constexpr int DC = D / NWG;  // columns per thread: the NWG warpgroups split the row
   const int col0 = t.wg * DC;
   float v[DC];
   tmem_load<DC>(tmem_acc + t.lane_base + col0, v);
@@ -378,10 +378,10 @@ __device__ __forceinline__ uint32_t epi_hidden_fwd(uint32_t tmem_acc, const tid_
   return mask;
 }
 // TMEM accumulator -> (* c, . relu mask) -> BF16 hi/lo panel (input-gradient epilogue).
-template <int D>
+template <int D, int NWG>
 __device__ __forceinline__ void epi_hidden_bwd(uint32_t tmem_acc, const tid_t &t, float c, uint32_t mask,
                                                uint8_t *hi, uint8_t *lo) {
-  constexpr int DC = D / 2;
+  constexpr int DC = D / NWG;
   const int col0 = t.wg * DC;
   float v[DC];
   tmem_load<DC>(tmem_acc + t.lane_base + col0, v);
@@ -423,9 +423,9 @@ template <int N> struct ID {
 
 // Layers 1 and 2 of a tile whose X0 panel is staged and synchronised. Leaves H1 (and, if
 // WRITE_H2, H2) panels written but NOT yet synchronised. y2 = sh2 * H2 of this thread's columns.
-template <int D0, int D1, int D2, typename SM, uint32_t TL1, uint32_t TL2, bool H2_IN_PLACE, bool WRITE_H2>
+template <int D0, int D1, int D2, int NWG, typename SM, uint32_t TL1, uint32_t TL2, bool H2_IN_PLACE, bool WRITE_H2>
 __device__ __forceinline__ void fwd_hidden(tile_ctx &c, const float *fl, uint32_t &mask1, uint32_t &mask2,
-                                           float (&y2)[D2 / 2]) {
+                                           float (&y2)[D2 / NWG]) {
   using IM = image_map<D1, D2>;
   const float *b1s = fl + IM::F_B1, *b2s = fl + IM::F_B2, *k = fl + IM::F_K;
   constexpr uint32_t H2_OFF = H2_IN_PLACE ? 0 : PANEL;
@@ -435,8 +435,8 @@ __device__ __forceinline__ void fwd_hidden(tile_ctx &c, const float *fl, uint32_
     umma::commit(c.bar);
   }
   c.wait();
-  mask1 = epi_hidden_fwd<D1, true, false>(c.tmem + TL1, c.t, k[K_C1], b1s, c.smem + SM::H_HI, c.smem + SM::H_LO,
-                                          nullptr);
+  mask1 = epi_hidden_fwd<D1, NWG, true, false>(c.tmem + TL1, c.t, k[K_C1], b1s, c.smem + SM::H_HI,
+                                               c.smem + SM::H_LO, nullptr);
   sync_after_smem_writes();
   if (mma_thread(c.t)) {
     issue_gemm<D1 / 16, false, false, true, true>(c.tmem + TL2, c.sbase + SM::H_HI, c.sbase + SM::H_LO,
@@ -444,23 +444,27 @@ __device__ __forceinline__ void fwd_hidden(tile_ctx &c, const float *fl, uint32_
     umma::commit(c.bar);
   }
   c.wait();
-  mask2 = epi_hidden_fwd<D2, WRITE_H2, true>(c.tmem + TL2, c.t, k[K_C2], b2s, c.smem + SM::H_HI + H2_OFF,
-                                             c.smem + SM::H_LO + H2_OFF, y2);
+  mask2 = epi_hidden_fwd<D2, NWG, WRITE_H2, true>(c.tmem + TL2, c.t, k[K_C2], b2s, c.smem + SM::H_HI + H2_OFF,
+                                                  c.smem + SM::H_LO + H2_OFF, y2);
 }
 
-// Value head (D2 -> 1) in fp32 registers: each row is held by two threads (one per warpgroup,
-// D2/2 columns each); partial dot products meet in shared memory. Contains one __syncthreads.
-template <int D2>
-__device__ __forceinline__ float value_head(const tid_t &t, const float (&y2)[D2 / 2],
+// Value head (D2 -> 1) in fp32 registers: each row is held by NWG threads (one per warpgroup,
+// D2/NWG columns each); partial dot products meet in shared memory. Contains one __syncthreads.
+template <int D2, int NWG>
+__device__ __forceinline__ float value_head(const tid_t &t, const float (&y2)[D2 / NWG],
                                             const float *__restrict__ w3s, float b3, float *vpart) {
-  constexpr int DC = D2 / 2;
+  constexpr int DC = D2 / NWG;
   float s = 0.f;
 #pragma unroll
   for (int j = 0; j < DC; ++j)
     s = fmaf(y2[j], w3s[t.wg * DC + j], s);
   vpart[t.wg * TILE + t.row] = s;
   __syncthreads();
-  return vpart[t.row] + vpart[TILE + t.row] + b3;
+  float v = b3;
+#pragma unroll
+  for (int g = NWG - 1; g >= 0; --g)
+    v += vpart[g * TILE + t.row];
+  return v;
 }
 
 // Common one-time setup: TMEM, barrier, image -> smem, zeroed panels, ones column of X0.
@@ -587,11 +591,7 @@ __device__ __forceinline__ void fix_end_rows(const int8_t *raw_s, int8_t *raw_e,
 // RAW planes -> X0 panel: two 16-byte chunks (two bins each) per thread.
 __device__ __forceinline__ void encode_x0(uint8_t *x0, const int8_t *raw, int B, float inv_w, float inv_h) {
   const int cpr = B / 2;
-#pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    int task = threadIdx.x + q * 256;
-    if (task >= TILE * cpr)
-      continue;
+  for (int task = threadIdx.x; task < TILE * cpr; task += blockDim.x) {
     int row = task % TILE, ch = task / TILE;  // a warp = 32 consecutive rows: conflict-free LDS / STS
     const uint32_t it = pack2_fwd((float)raw[(2 * B) * TILE + row] * inv_w, (float)raw[(2 * B + 1) * TILE + row] * inv_h);
     uint32_t out[2];
@@ -619,17 +619,17 @@ struct critic_args {
 // update_value_model (policy_gradient.h:196-218) minus the optimizer update: V on start and end
 // rows with the current critic, targets r + gamma V_next (unmasked), dY = V - target, backward,
 // dW partials.
-template <int D0, int D1, int D2>
-__global__ void __launch_bounds__(256, 1) fused_critic_step_kernel(critic_args a) {
+template <int D0, int D1, int D2, int NWG>
+__global__ void __launch_bounds__(128 * NWG, 1) fused_critic_step_kernel(critic_args a) {
   using SM = smem_map<D1, D2>;
   using IM = image_map<D1, D2>;
-  constexpr int DC2 = D2 / 2;
+  constexpr int DC2 = D2 / NWG;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const float *fl = reinterpret_cast<const float *>(smem + IM::FLOATS);
   const float *w3 = fl + IM::F_W3, *w3s = fl + IM::F_W3S, *kk = fl + IM::F_K;
   float *scr = reinterpret_cast<float *>(smem + SM::SCRATCH);
-  float *vpart = scr, *ve = scr + 2 * TILE, *vs = scr + 3 * TILE;
+  float *vpart = scr, *ve = scr + NWG * TILE, *vs = scr + (NWG + 1) * TILE;
   uint64_t *bar = reinterpret_cast<uint64_t *>(smem + SM::BARS);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + SM::BARS + 16);
   const net3 net = a.net;
@@ -670,8 +670,8 @@ __global__ void __launch_bounds__(256, 1) fused_critic_step_kernel(critic_args a
     const bool valid = tt < L.T && i < L.n;
     const size_t k = (size_t)tt * L.n + i;
     const int d = valid ? L.rec_done[k] : 0;
-    fwd_hidden<D0, D1, D2, SM, TC_L1, TC_L2, false, false>(c, fl, m1, m2, y2);
-    float v_end = value_head<D2>(t, y2, w3s, b3, vpart);
+    fwd_hidden<D0, D1, D2, NWG, SM, TC_L1, TC_L2, false, false>(c, fl, m1, m2, y2);
+    float v_end = value_head<D2, NWG>(t, y2, w3s, b3, vpart);
     if (t.wg == 0)
       ve[t.row] = v_end;
     // ---- pass 2: start rows, activations kept
@@ -680,8 +680,8 @@ __global__ void __launch_bounds__(256, 1) fused_critic_step_kernel(critic_args a
     const int next = tile + gridDim.x;
     if (next < a.n_tiles)  // prefetch the next tile's state bytes behind this tile's math
       load_x0<true>(L, next, xp);
-    fwd_hidden<D0, D1, D2, SM, TC_L1, TC_L2, false, false>(c, fl, m1, m2, y2);
-    float v = value_head<D2>(t, y2, w3s, b3, vpart);
+    fwd_hidden<D0, D1, D2, NWG, SM, TC_L1, TC_L2, false, false>(c, fl, m1, m2, y2);
+    float v = value_head<D2, NWG>(t, y2, w3s, b3, vpart);
     if (t.wg == 0)
       vs[t.row] = v;
     __syncthreads();
@@ -725,7 +725,7 @@ __global__ void __launch_bounds__(256, 1) fused_critic_step_kernel(critic_args a
                                             c.sbase + SM::H_HI, c.sbase + SM::H_LO, ID<64>::BM_FM, !first_tile);
     }
     c.wait();
-    epi_hidden_bwd<D1>(c.tmem + TC_DH1, t, kk[K_ISW2], m1, smem + SM::DH_HI, smem + SM::DH_LO);
+    epi_hidden_bwd<D1, NWG>(c.tmem + TC_DH1, t, kk[K_ISW2], m1, smem + SM::DH_HI, smem + SM::DH_LO);
     sync_after_smem_writes();
     if (mma_thread(t)) {
       issue_gemm<8, true, true, true, false>(c.tmem + TC_DB, c.sbase + SM::DH_HI, c.sbase + SM::DH_LO,
@@ -744,7 +744,7 @@ __global__ void __launch_bounds__(256, 1) fused_critic_step_kernel(critic_args a
       part[i] = 0.f;
   } else {
     {
-      constexpr int DC = D1 / 2;
+      constexpr int DC = D1 / NWG;
       float v[DC];
       tmem_load<DC>(c.tmem + TC_DA + t.lane_base + t.wg * DC, v);
       int nrow = t.row - 64;
@@ -754,7 +754,7 @@ __global__ void __launch_bounds__(256, 1) fused_critic_step_kernel(critic_args a
         for (int j = 0; j < DC; ++j)
           part[net.o_w2 + nrow * D1 + t.wg * DC + j] = v[j] * s;
     }
-    {
+    if (t.wg < 2) {
       constexpr int DC = (D0 + 16) / 2;
       float v[DC];
       tmem_load<DC>(c.tmem + TC_DB + t.lane_base + t.wg * DC, v);
@@ -855,8 +855,8 @@ __global__ void __launch_bounds__(256, 2) fused_gae_kernel(critic_args a) {
     if ((int)threadIdx.x < L.E && tile * L.E + (int)threadIdx.x < L.n)
       for (int tt = 0; tt < L.T && tt < 32; ++tt)
         dmask |= (uint32_t)(L.rec_done[(size_t)tt * L.n + tile * L.E + threadIdx.x] != 0) << tt;
-    fwd_hidden<D0, D1, D2, SM, TF_L1, TF_L2, true, false>(c, fl, m1, m2, y2);
-    float v_end = value_head<D2>(t, y2, w3s, b3, vpart);
+    fwd_hidden<D0, D1, D2, 2, SM, TF_L1, TF_L2, true, false>(c, fl, m1, m2, y2);
+    float v_end = value_head<D2, 2>(t, y2, w3s, b3, vpart);
     if (t.wg == 0)
       ve[t.row] = v_end;
     encode_x0(smem + SM::X0, raw_s, L.B, L.inv_w, L.inv_h);
@@ -864,8 +864,8 @@ __global__ void __launch_bounds__(256, 2) fused_gae_kernel(critic_args a) {
     const int next = tile + gridDim.x;
     if (next < a.n_tiles)
       load_x0<true>(L, next, xp);
-    fwd_hidden<D0, D1, D2, SM, TF_L1, TF_L2, true, false>(c, fl, m1, m2, y2);
-    float v = value_head<D2>(t, y2, w3s, b3, vpart);
+    fwd_hidden<D0, D1, D2, 2, SM, TF_L1, TF_L2, true, false>(c, fl, m1, m2, y2);
+    float v = value_head<D2, 2>(t, y2, w3s, b3, vpart);
     if (t.wg == 0)
       vs[t.row] = v;
     __syncthreads();
@@ -912,8 +912,8 @@ struct policy_step_args {
 
 // ---------------------------------------------------------------------------------------------
 // One policy optimizer::step minus the update: forward + loss gradient + backward + dW partials.
-template <int D0, int D1, int D2, int NOUT>
-__global__ void __launch_bounds__(256, 1) fused_policy_step_kernel(policy_step_args a) {
+template <int D0, int D1, int D2, int NOUT, int NWG>
+__global__ void __launch_bounds__(128 * NWG, 1) fused_policy_step_kernel(policy_step_args a) {
   using SM = smem_map<D1, D2>;
   using IM = image_map<D1, D2>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -937,7 +937,7 @@ __global__ void __launch_bounds__(256, 1) fused_policy_step_kernel(policy_step_a
     db3[j] = 0.f;
 
   // optional phase clocks of CTA 0 (dfrl_debug_policy_clocks): 12 stamps per tile, first 8 tiles
-  long long *clk = (a.clk && blockIdx.x == 0 && threadIdx.x == 64) ? a.clk : nullptr;
+  long long *clk = (a.clk && blockIdx.x == 0 && threadIdx.x == 32 * (4 * NWG - 1)) ? a.clk : nullptr;
   int clk_n = 0;
 #define STAMP() do { if (clk && clk_n < 96) clk[clk_n++] = clock64(); } while (0)
 
@@ -986,7 +986,7 @@ __global__ void __launch_bounds__(256, 1) fused_policy_step_kernel(policy_step_a
       load_x0<false>(L, next, xp);
     c.wait();
     STAMP();
-    const uint32_t mask1 = epi_hidden_fwd<D1, true, false>(tmem + TC_L1, t, kk[K_C1], fl + IM::F_B1,
+    const uint32_t mask1 = epi_hidden_fwd<D1, NWG, true, false>(tmem + TC_L1, t, kk[K_C1], fl + IM::F_B1,
                                                            smem + SM::H_HI, smem + SM::H_LO, nullptr);
     sync_after_smem_writes();
     STAMP();
@@ -997,7 +997,7 @@ __global__ void __launch_bounds__(256, 1) fused_policy_step_kernel(policy_step_a
     }
     c.wait();
     STAMP();
-    const uint32_t mask2 = epi_hidden_fwd<D2, true, false>(tmem + TC_L2, t, kk[K_C2], fl + IM::F_B2,
+    const uint32_t mask2 = epi_hidden_fwd<D2, NWG, true, false>(tmem + TC_L2, t, kk[K_C2], fl + IM::F_B2,
                                                            smem + SM::H_HI + PANEL, smem + SM::H_LO + PANEL, nullptr);
     sync_after_smem_writes();
     STAMP();
@@ -1083,7 +1083,7 @@ __global__ void __launch_bounds__(256, 1) fused_policy_step_kernel(policy_step_a
     }
     c.wait();
     STAMP();
-    epi_hidden_bwd<D2>(tmem + TC_DH2, t, kk[K_ISW3], mask2, smem + SM::DH_HI + PANEL, smem + SM::DH_LO + PANEL);
+    epi_hidden_bwd<D2, NWG>(tmem + TC_DH2, t, kk[K_ISW3], mask2, smem + SM::DH_HI + PANEL, smem + SM::DH_LO + PANEL);
     sync_after_smem_writes();
     STAMP();
     // ---- dH1 = dH2 . W2; dW2 += [dH1|dH2]^T . H1 (rows 64.. only are used, so the stale dH1
@@ -1097,7 +1097,7 @@ __global__ void __launch_bounds__(256, 1) fused_policy_step_kernel(policy_step_a
     }
     c.wait();
     STAMP();
-    epi_hidden_bwd<D1>(tmem + TC_DH1, t, kk[K_ISW2], mask1, smem + SM::DH_HI, smem + SM::DH_LO);
+    epi_hidden_bwd<D1, NWG>(tmem + TC_DH1, t, kk[K_ISW2], mask1, smem + SM::DH_HI, smem + SM::DH_LO);
     sync_after_smem_writes();
     STAMP();
     //   DB[128 x D0+16] += [dH1|dH2]^T . [X0|1]   rows 0.. = [dW1 | db1], rows 64.. col D0 = db2
@@ -1120,7 +1120,7 @@ __global__ void __launch_bounds__(256, 1) fused_policy_step_kernel(policy_step_a
   } else {
     // dW2[n][k]: DA row 64 + n, col k
     {
-      constexpr int DC = D1 / 2;
+      constexpr int DC = D1 / NWG;
       float v[DC];
       tmem_load<DC>(tmem + TC_DA + t.lane_base + t.wg * DC, v);
       int nrow = t.row - 64;
@@ -1131,7 +1131,7 @@ __global__ void __launch_bounds__(256, 1) fused_policy_step_kernel(policy_step_a
           part[net.o_w2 + nrow * D1 + t.wg * DC + j] = v[j] * s;
     }
     // dW1[n][k] + db1[n]: DB row n, cols 0..D0-1 and D0; db2[n]: DB row 64 + n, col D0
-    {
+    if (t.wg < 2) {
       constexpr int DC = (D0 + 16) / 2;
       float v[DC];
       tmem_load<DC>(tmem + TC_DB + t.lane_base + t.wg * DC, v);
@@ -1188,6 +1188,8 @@ struct reduce_tail {
   uint8_t *image;      // null: no rebuild
   net3 net;
   unsigned *ticket;    // zero before the launch, zero again after it
+  unsigned *publish;   // multi-rank: flag of the exchange slot `grad` points into, set to
+  unsigned epoch;      //   `epoch` by the last block once the whole gradient is visible system-wide
 };
 template <int D0, int D1, int D2>
 __global__ void __launch_bounds__(256) fused_reduce_partials_kernel(const float *__restrict__ part, int ctas,
@@ -1214,9 +1216,65 @@ __global__ void __launch_bounds__(256) fused_reduce_partials_kernel(const float 
     if (opt.params)
       opt_update(opt.kind, opt.params, grad, opt.state, n, i, opt.lr, opt.wd, opt.beta1, opt.beta2, opt.c1, opt.c2);
   }
+  if (!tail.image && !tail.publish)
+    return;
+  __threadfence_system();  // this block's writes (parameters / exchange slot) before its ticket
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned tk = atomicAdd(tail.ticket, 1u);
+    is_last = tk == gridDim.x - 1;
+    if (is_last)
+      *tail.ticket = 0;
+  }
+  __syncthreads();
+  if (!is_last)
+    return;
+  __threadfence_system();
+  if (tail.publish) {
+    if (threadIdx.x == 0)
+      *reinterpret_cast<volatile unsigned *>(tail.publish) = tail.epoch;
+    return;
+  }
+  prep_body<D0, D1, D2>(tail.opt.params, tail.net, tail.image, prep_params);
+}
+
+// K8 + K7 over NVLink peer memory: pull every rank's published gradient, sum in rank order
+// (bit-identical on every rank), optimizer update, and the last block rebuilds the panel image.
+// Waits (bounded) for the peers' publish flags: every rank runs the same launch sequence on its own
+// GPU, and a peer's producer kernel never depends on this rank.
+struct p2p_view {
+  const float *peer[DFRL_P2P_MAX_RANKS];
+  int nranks, slot;
+  unsigned epoch;
+};
+template <int D0, int D1, int D2>
+__global__ void __launch_bounds__(256) fused_p2p_sum_opt_kernel(p2p_view v, int n, float *__restrict__ grad,
+                                                                reduce_tail tail) {
+  __shared__ int is_last;
+  extern __shared__ float prep_params[];
+  if ((int)threadIdx.x < v.nranks) {
+    const volatile unsigned *flag =
+        reinterpret_cast<const volatile unsigned *>(v.peer[threadIdx.x] + 2 * DFRL_P2P_CAP) + v.slot;
+    unsigned spins = 0;
+    while (*flag < v.epoch)
+      if (++spins > (1u << 28))
+        __trap();  // a peer never published: report a launch failure instead of hanging the GPU
+    __threadfence_system();
+  }
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    float s = 0.f;
+    for (int r = 0; r < v.nranks; ++r)
+      s += *reinterpret_cast<const volatile float *>(v.peer[r] + (size_t)v.slot * DFRL_P2P_CAP + i);
+    grad[i] = s;
+    const dfrl_opt_spec &opt = tail.opt;
+    if (opt.params)
+      opt_update(opt.kind, opt.params, grad, opt.state, n, i, opt.lr, opt.wd, opt.beta1, opt.beta2, opt.c1, opt.c2);
+  }
   if (!tail.image)
     return;
-  __threadfence();  // this block's parameter writes before its ticket
+  __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
     unsigned tk = atomicAdd(tail.ticket, 1u);
@@ -1316,7 +1374,7 @@ __global__ void __launch_bounds__(256, 2) fused_rollout_kernel(rollout_args a) {
       // ---- forward
       uint32_t m1, m2;
       float y2[D2 / 2];
-      fwd_hidden<D0, D1, D2, SM, TF_L1, TF_L2, true, true>(c, fl, m1, m2, y2);
+      fwd_hidden<D0, D1, D2, 2, SM, TF_L1, TF_L2, true, true>(c, fl, m1, m2, y2);
       sync_after_smem_writes();
       if (mma_thread(t)) {
         issue_gemm<D2 / 16, false, false, true, true>(tmem + TF_L3, sbase + SM::H_HI, sbase + SM::H_LO,
@@ -1466,21 +1524,27 @@ int set_smem_once(K kernel, int smem, bool *done) {
   return DFRL_OK;
 }
 
+// Learner kernels run 2 warpgroups. 4 (NWG = 4, 16 warps) measured SLOWER on B200 (11 700 vs
+// 11 200 cycles per tile): the epilogues are bound by the TMEM read port (128 x 64 fp32 = 32 KB per
+// epilogue at 64 B/clk) and the shared-memory stores, not by issue latency, and the 512-thread
+// barriers cost more.
 template <int D0, int D1, int D2, int NOUT>
 int launch_policy_step(dfrl_ctx *ctx, const policy_step_args &a, int ctas) {
   constexpr int smem = smem_map<D1, D2>::TOTAL + 1024;
+  constexpr int NWG = 2;
   static bool attr = false;
-  DFRL_TRY(set_smem_once(fused_policy_step_kernel<D0, D1, D2, NOUT>, smem, &attr));
-  DFRL_LAUNCH(ctx, (fused_policy_step_kernel<D0, D1, D2, NOUT>), ctas, 256, smem, a);
+  DFRL_TRY(set_smem_once(fused_policy_step_kernel<D0, D1, D2, NOUT, NWG>, smem, &attr));
+  DFRL_LAUNCH(ctx, (fused_policy_step_kernel<D0, D1, D2, NOUT, NWG>), ctas, 128 * NWG, smem, a);
   return DFRL_OK;
 }
 
 template <int D0, int D1, int D2>
 int launch_critic_step(dfrl_ctx *ctx, const critic_args &a, int ctas) {
   constexpr int smem = smem_map<D1, D2>::TOTAL + 1024;
+  constexpr int NWG = 2;
   static bool attr = false;
-  DFRL_TRY(set_smem_once(fused_critic_step_kernel<D0, D1, D2>, smem, &attr));
-  DFRL_LAUNCH(ctx, (fused_critic_step_kernel<D0, D1, D2>), ctas, 256, smem, a);
+  DFRL_TRY(set_smem_once(fused_critic_step_kernel<D0, D1, D2, NWG>, smem, &attr));
+  DFRL_LAUNCH(ctx, (fused_critic_step_kernel<D0, D1, D2, NWG>), ctas, 128 * NWG, smem, a);
   return DFRL_OK;
 }
 
@@ -1557,12 +1621,26 @@ critic_args make_critic_args(dfrl_trainer *t, fused_state *f) {
 }
 
 // Partials -> gradient (-> optimizer update -> rebuilt panel image when `opt` is given).
+// Several ranks (opt given means the peers are attached): the reduced gradient goes to this rank's
+// exchange slot and a second kernel pulls all ranks' slots over NVLink before the update.
 int launch_reduce(dfrl_trainer *t, fused_state *f, dfrl_mlp *m, const net3 &net, int ctas, float *grad_dev,
                   const dfrl_opt_spec *opt, uint8_t *image, uint64_t *image_version) {
+  dfrl_ctx *ctx = t->ctx;
+  const bool exchange = opt && ctx->nranks > 1;
   reduce_tail tail;
   memset(&tail, 0, sizeof(tail));
   size_t smem = 0;
-  if (opt) {
+  float *dst = grad_dev;
+  int slot = 0;
+  if (exchange) {
+    DFRL_CHECK((size_t)net.n_params <= DFRL_P2P_CAP, "flat gradient exceeds the exchange slot");
+    ctx->p2p.epoch += 1;
+    slot = (int)(ctx->p2p.epoch & 1u);
+    dst = ctx->p2p.local + (size_t)slot * DFRL_P2P_CAP;
+    tail.ticket = f->ticket;
+    tail.publish = dfrl_p2p_flags(ctx->p2p.local) + slot;
+    tail.epoch = ctx->p2p.epoch;
+  } else if (opt) {
     tail.opt = *opt;
     tail.image = image;
     tail.net = net;
@@ -1571,11 +1649,33 @@ int launch_reduce(dfrl_trainer *t, fused_state *f, dfrl_mlp *m, const net3 &net,
   }
   const int grid = ceil_div(net.n_params, 32);
   if (net.d1 == 64)
-    DFRL_LAUNCH(t->ctx, (fused_reduce_partials_kernel<32, 64, 64>), grid, 256, smem, (const float *)f->partials,
-                ctas, net.n_params, grad_dev, tail);
+    DFRL_LAUNCH(ctx, (fused_reduce_partials_kernel<32, 64, 64>), grid, 256, smem, (const float *)f->partials,
+                ctas, net.n_params, dst, tail);
   else
-    DFRL_LAUNCH(t->ctx, (fused_reduce_partials_kernel<32, 16, 16>), grid, 256, smem, (const float *)f->partials,
-                ctas, net.n_params, grad_dev, tail);
+    DFRL_LAUNCH(ctx, (fused_reduce_partials_kernel<32, 16, 16>), grid, 256, smem, (const float *)f->partials,
+                ctas, net.n_params, dst, tail);
+  if (exchange) {
+    p2p_view v;
+    memset(&v, 0, sizeof(v));
+    for (int r = 0; r < ctx->nranks; ++r)
+      v.peer[r] = ctx->p2p.peer[r];
+    v.nranks = ctx->nranks;
+    v.slot = slot;
+    v.epoch = ctx->p2p.epoch;
+    reduce_tail t2;
+    memset(&t2, 0, sizeof(t2));
+    t2.opt = *opt;
+    t2.image = image;
+    t2.net = net;
+    t2.ticket = f->ticket;
+    const size_t smem2 = sizeof(float) * net.n_params;
+    if (net.d1 == 64)
+      DFRL_LAUNCH(ctx, (fused_p2p_sum_opt_kernel<32, 64, 64>), ceil_div(net.n_params, 256), 256, smem2, v,
+                  net.n_params, grad_dev, t2);
+    else
+      DFRL_LAUNCH(ctx, (fused_p2p_sum_opt_kernel<32, 16, 16>), ceil_div(net.n_params, 256), 256, smem2, v,
+                  net.n_params, grad_dev, t2);
+  }
   if (opt) {  // parameters changed and the image already matches them
     m->wt_dirty = true, m->version++;
     *image_version = m->version;

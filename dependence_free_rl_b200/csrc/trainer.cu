@@ -444,10 +444,11 @@ static int apply_opt(dfrl_trainer *t, dfrl_mlp *m, int kind, float *grad, float 
   return DFRL_OK;
 }
 
-// Single rank: the optimizer update rides in the fused gradient-reduction kernel.
+// The optimizer update rides in the fused gradient-reduction kernel (single rank) or in the
+// peer-memory exchange kernel (several ranks with attached peers); otherwise NCCL + opt kernel.
 static bool fuse_opt(dfrl_trainer *t, dfrl_mlp *m, int kind, float *state, float lr, float wd, float adam_t,
                      dfrl_opt_spec *spec) {
-  if (t->ctx->nranks != 1)
+  if (t->ctx->nranks != 1 && !t->ctx->p2p.attached)
     return false;
   spec->kind = kind;
   spec->params = m->params;

@@ -293,6 +293,15 @@ int dfrl_opt_step(dfrl_ctx *ctx, int kind, float *params_dev, const float *grad_
 int dfrl_allreduce_sum(dfrl_ctx *ctx, float *buf_dev, size_t n);
 int dfrl_allreduce_sum_f64(dfrl_ctx *ctx, double *buf_dev, size_t n);
 int dfrl_barrier(dfrl_ctx *ctx);
+/* The same exchange over NVLink peer memory, fused with the optimizer (fused.cu): every rank of the
+ * node exports a 64-byte CUDA IPC handle of its exchange buffer, the host gathers them by any
+ * transport into [nranks][64] and every rank attaches. Once attached, the fused learner kernels
+ * publish their reduced gradient in the local buffer and ONE kernel per optimizer step pulls the
+ * peers' buffers over NVLink, sums them in rank order (bit-identical on every rank), applies the
+ * optimizer update and rebuilds the weight panels -- no NCCL call on that path. */
+int dfrl_p2p_export(dfrl_ctx *ctx, void *handle64_host);
+int dfrl_p2p_attach(dfrl_ctx *ctx, const void *all_handles_host /* [nranks][64] */);
+int dfrl_p2p_attached(dfrl_ctx *ctx);
 
 /* ------------------------------------------------------------ trainer (fused loop) -------- */
 
