@@ -420,9 +420,12 @@ def test_trainer_default_path_vs_reference_trace(D, ctx, name):
     _run_case(D, ctx, name, fused=True)
 
 
-def test_trainer_vs_oracle_with_uniform_tape(D, ctx, orc):
-    # sampling mode driven by a tape of uniforms: GPU and oracle must pick identical actions
-    n, T, B = 512, 4, 8
+@pytest.mark.parametrize("n,T", [(512, 4), (200, 4), (96, 8), (70, 5)])
+def test_trainer_vs_oracle_with_uniform_tape(D, ctx, orc, n, T):
+    # sampling mode driven by a tape of uniforms: GPU and oracle must pick identical actions.
+    # (200, 4): ragged last tiles of the rollout (128 envs) and learner (32 envs) kernels;
+    # (96, 8): 16 envs per learner tile; (70, 5): 25 envs per tile, the byte-wise staging path.
+    B = 8
     rng = np.random.default_rng(17)
     pl = D.fc_layers([32, 64, 64, 8], D.SOFTMAX)
     vl = D.fc_layers([32, 64, 64, 1])
@@ -478,7 +481,7 @@ def test_trainer_vs_oracle_with_uniform_tape(D, ctx, orc):
         close(tr.read(D.F_POLICY_GRAD_LOG), out["policy_grads"], what="pgrads")
         close(policy.parameters(), lr.pparams, what="pparams")
         close(value.parameters(), lr.vparams, what="vparams")
-    assert done_at_last_step > 10 and done_mid > 10  # both kinds of end rows were exercised
+    assert done_at_last_step > 0 and done_mid > 0  # both kinds of end rows were exercised
     s = tr.stats()
     assert s["env_steps"] == 5 * n * T
     assert s["reward_sum"] + s["episodes"] == s["env_steps"]
@@ -518,3 +521,25 @@ def test_free_running_ppo_at_c2_size_invariants(D, ctx):
     done = tr.read(D.F_REC_DONE)
     assert 0.02 < done.mean() < 0.2   # near-random policy: ~1 episode end per 12.6 steps
     tr.close(); env.close(); policy.close(); value.close()
+
+
+def test_free_running_ppo_is_bitwise_reproducible(D, ctx):
+    # fixed-order reductions everywhere (per-CTA partials, slice sums): two runs of the same
+    # configuration give identical bits, also across the rollout / learner tile boundaries
+    def run():
+        n, T = 4096 + 40, 4   # not a multiple of the 128-env rollout tile nor of the 32-env learner tile
+        policy = D.Model(ctx, D.fc_layers([32, 64, 64, 8], D.SOFTMAX), 32)
+        value = D.Model(ctx, D.fc_layers([32, 64, 64, 1]), 32)
+        policy.init_parameters(3)
+        value.init_parameters(4)
+        env = D.Environment(ctx, n, seed=77)
+        tr = D.Trainer(ctx, env, policy, value, algo=D.PPO, work=T, policy_lr=1e-4 * 32 / (n * T),
+                       value_lr=1e-5 * 32 / (n * T))
+        tr.iterate(8)
+        out = (policy.parameters().copy(), value.parameters().copy(), env.state().copy(), tr.stats())
+        tr.close(); env.close(); policy.close(); value.close()
+        return out
+    a, b = run(), run()
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    assert a[3]["reward_sum"] == b[3]["reward_sum"] and a[3]["episodes"] == b[3]["episodes"]
+    assert np.all(np.isfinite(a[0])) and np.all(np.isfinite(a[1]))

@@ -68,13 +68,16 @@ def test_host_api_matches_python_binding(D, ctx):
                    value_lr=float(np.float32(1e-5) * rs))
     tr.iterate(iters)
     s = tr.stats()
-    w = (np.arange(policy.n_params) % 7 + 1).astype(np.float64)
-    wv = (np.arange(value.n_params) % 7 + 1).astype(np.float64)
+    def checksum(p):  # the C++ side's left-to-right double sum of p[i] * (i % 7 + 1)
+        acc = 0.0
+        for i, x in enumerate(p.astype(np.float64)):
+            acc += x * float(i % 7 + 1)
+        return acc
     assert int(got["env_steps"]) == s["env_steps"] == n * T * iters
     assert int(got["episodes"]) == s["episodes"]
     assert float(got["reward_sum"]) == s["reward_sum"]
-    assert float(got["policy_sum"]) == float(np.sum(policy.parameters().astype(np.float64) * w))
-    assert float(got["value_sum"]) == float(np.sum(value.parameters().astype(np.float64) * wv))
+    assert float(got["policy_sum"]) == checksum(policy.parameters())   # bit-identical parameters
+    assert float(got["value_sum"]) == checksum(value.parameters())
     tr.close(); env.close(); policy.close(); value.close()
 
 
