@@ -604,6 +604,77 @@ __device__ __forceinline__ void encode_x0(uint8_t *x0, const int8_t *raw, int B,
   }
 }
 
+// ---- staging of the NEXT tile's observations by warpgroup 1 while warpgroup 0 runs the head
+// epilogue (policy step kernel; X0 is double buffered). j = thread index inside the warpgroup.
+// The unit -> (plane, step, 16-env group) decode is tile independent and done once per thread.
+struct x0_units {
+  int raw_off[2];     // byte offset of the unit in the RAW planes, -1: no unit
+  size_t g_off[2];    // byte offset in rec_state, without the tile's env offset
+  int env_off[2];     // 16 * h
+  bool fast;          // E % 16 == 0 (otherwise byte loads at stash time)
+};
+struct x0_pref_wg {
+  uint4 r[2];  // units j and 128 + j (18 planes x 128 rows / 16 bytes = 144 units)
+};
+__device__ __forceinline__ x0_units wg_units(const learner_rows &L, int j) {
+  const int P = 2 * L.B + 2;
+  x0_units U;
+  U.fast = L.E % 16 == 0;
+  const int upr = U.fast ? L.E / 16 : 1, units = U.fast ? L.T * P * upr : 0;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int u = j + q * TILE;
+    U.raw_off[q] = -1;
+    U.g_off[q] = 0;
+    U.env_off[q] = 0;
+    if (j >= 0 && u < units) {
+      int h = u % upr, plane = (u / upr) % P, tt = u / (upr * P);
+      U.raw_off[q] = plane * TILE + tt * L.E + 16 * h;
+      U.g_off[q] = ((size_t)tt * P + plane) * L.stride + 16 * h;
+      U.env_off[q] = 16 * h;
+    }
+  }
+  return U;
+}
+__device__ __forceinline__ void wg_load_x0(const learner_rows &L, const x0_units &U, int tile, x0_pref_wg &x) {
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    x.r[q] = make_uint4(0, 0, 0, 0);
+    if (U.raw_off[q] >= 0 && tile * L.E + U.env_off[q] < L.stride)
+      x.r[q] = *reinterpret_cast<const uint4 *>(L.rec_state + U.g_off[q] + (size_t)tile * L.E);
+  }
+}
+__device__ __forceinline__ void wg_stash_x0(int8_t *raw, const learner_rows &L, const x0_units &U, int tile, int j,
+                                            const x0_pref_wg &x) {
+  if (U.fast) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+      if (U.raw_off[q] >= 0)
+        *reinterpret_cast<uint4 *>(raw + U.raw_off[q]) = x.r[q];
+  } else {
+    const int P = 2 * L.B + 2;
+    for (int u = j; u < P * TILE; u += TILE) {
+      int plane = u / TILE, r = u % TILE;
+      int tt = r / L.E, e = r % L.E, i = tile * L.E + e;
+      raw[u] = (tt < L.T && i < L.n) ? L.rec_state[((size_t)tt * P + plane) * L.stride + i] : (int8_t)0;
+    }
+  }
+}
+// Thread j encodes row j (all B / 2 chunks) of the X0 panel from the RAW planes.
+template <int B>
+__device__ __forceinline__ void wg_encode_x0(uint8_t *x0, const int8_t *raw, float inv_w, float inv_h, int j) {
+  float v[2 * B + 2];
+#pragma unroll
+  for (int q = 0; q < 2 * B + 2; ++q)
+    v[q] = (float)raw[q * TILE + j] * ((q & 1) ? inv_h : inv_w);
+  const uint32_t it = pack2_fwd(v[2 * B], v[2 * B + 1]);
+#pragma unroll
+  for (int ch = 0; ch < B / 2; ++ch)
+    *reinterpret_cast<uint4 *>(x0 + umma::panel_chunk_off(j, ch)) =
+        make_uint4(pack2_fwd(v[4 * ch], v[4 * ch + 1]), it, pack2_fwd(v[4 * ch + 2], v[4 * ch + 3]), it);
+}
+__device__ __forceinline__ void wg_barrier_1() { asm volatile("bar.sync 1, 128;\n" ::: "memory"); }
+
 struct critic_args {
   const uint8_t *image;
   net3 net;
@@ -625,7 +696,7 @@ __global__ void __launch_bounds__(128 * NWG, 1) fused_critic_step_kernel(critic_
   using IM = image_map<D1, D2>;
   constexpr int DC2 = D2 / NWG;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t *smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);  // stays a shared-space pointer
   const float *fl = reinterpret_cast<const float *>(smem + IM::FLOATS);
   const float *w3 = fl + IM::F_W3, *w3s = fl + IM::F_W3S, *kk = fl + IM::F_K;
   float *scr = reinterpret_cast<float *>(smem + SM::SCRATCH);
@@ -825,7 +896,7 @@ __global__ void __launch_bounds__(256, 2) fused_gae_kernel(critic_args a) {
   using IM = image_map<D1, D2>;
   constexpr int DC2 = D2 / 2;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t *smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);  // stays a shared-space pointer
   const float *fl = reinterpret_cast<const float *>(smem + IM::FLOATS);
   const float *w3s = fl + IM::F_W3S, *kk = fl + IM::F_K;
   float *scr = reinterpret_cast<float *>(smem + SM::SCRATCH);
@@ -917,7 +988,7 @@ __global__ void __launch_bounds__(128 * NWG, 1) fused_policy_step_kernel(policy_
   using SM = smem_map<D1, D2>;
   using IM = image_map<D1, D2>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t *smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);  // stays a shared-space pointer
   const float *fl = reinterpret_cast<const float *>(smem + IM::FLOATS);
   const float *b3 = fl + IM::F_B3, *kk = fl + IM::F_K;
   float *red = reinterpret_cast<float *>(smem + SM::SCRATCH);
@@ -939,27 +1010,36 @@ __global__ void __launch_bounds__(128 * NWG, 1) fused_policy_step_kernel(policy_
   // optional phase clocks of CTA 0 (dfrl_debug_policy_clocks): 12 stamps per tile, first 8 tiles
   long long *clk = (a.clk && blockIdx.x == 0 && threadIdx.x == 32 * (4 * NWG - 1)) ? a.clk : nullptr;
   int clk_n = 0;
-#define STAMP() do { if (clk && clk_n < 96) clk[clk_n++] = clock64(); } while (0)
+#define STAMP() do { if (clk && clk_n < 112) clk[clk_n++] = clock64(); } while (0)
 
+  // X0 is double buffered (second buffer = the slot a separate lo panel of dY would take: dY is
+  // a packed panel, hi in columns 0..15, lo in 16..31): warpgroup 1 stages tile i+1 while
+  // warpgroup 0 runs the head epilogue of tile i, and no tile waits for the previous one's dW GEMMs.
+  static_assert(NWG == 2, "the staging / head split assumes two warpgroups");
+  constexpr uint32_t X0_A = SM::X0, X0_B = SM::DY_LO;
+  constexpr uint32_t DY = SM::DY_HI, DY_LOFF = 32;  // byte offset of the lo half inside the panel
   int8_t *raw_s = reinterpret_cast<int8_t *>(smem + SM::RAW_S);
-  x0_pref xp;
-  if ((int)blockIdx.x < a.n_tiles)
+  const int j1 = (int)threadIdx.x - TILE;  // index inside warpgroup 1
+  const x0_units xu = wg_units(L, j1);
+  if (threadIdx.x < TILE)  // ones column of the second X0 buffer
+    *reinterpret_cast<uint16_t *>(smem + X0_B + umma::panel_off(threadIdx.x, D0)) = ONE_FWD;
+  if ((int)blockIdx.x < a.n_tiles) {  // first tile: staged by everybody
+    x0_pref xp;
     load_x0<false>(L, blockIdx.x, xp);
-  for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-    if (dw_pending) {  // the previous tile's dW GEMMs still read the panels
-      c.wait();
-      dw_pending = false;
-    }
-    STAMP();
-    stash_x0<false>(raw_s, nullptr, L, tile, xp);
+    stash_x0<false>(raw_s, nullptr, L, blockIdx.x, xp);
     __syncthreads();
-    encode_x0(smem + SM::X0, raw_s, L.B, L.inv_w, L.inv_h);
-    sync_after_smem_writes();
+    encode_x0(smem + X0_A, raw_s, L.B, L.inv_w, L.inv_h);
+  }
+  sync_after_smem_writes();
+  int buf = 0;
+  for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, buf ^= 1) {
+    const uint32_t x0_cur = buf ? X0_B : X0_A, x0_next = buf ? X0_A : X0_B;
+    STAMP();
     STAMP();
     // ---- layer 1 issue first, then the global loads that are consumed later: row data for the
     // head epilogue and the next tile's observation chunks
     if (mma_thread(t)) {
-      issue_gemm<D0 / 16, false, false, false, true>(tmem + TC_L1, sbase + SM::X0, 0, sbase + IM::W1_HI,
+      issue_gemm<D0 / 16, false, false, false, true>(tmem + TC_L1, sbase + x0_cur, 0, sbase + IM::W1_HI,
                                                      sbase + IM::W1_LO, ID<D1>::FK_FK, false);
       umma::commit(c.bar);
     }
@@ -982,8 +1062,9 @@ __global__ void __launch_bounds__(128 * NWG, 1) fused_policy_step_kernel(policy_
         po[j] = pr[j];
     }
     const int next = tile + gridDim.x;
-    if (next < a.n_tiles)
-      load_x0<false>(L, next, xp);
+    x0_pref_wg xw;
+    if (t.wg == 1 && next < a.n_tiles)
+      wg_load_x0(L, xu, next, xw);
     c.wait();
     STAMP();
     const uint32_t mask1 = epi_hidden_fwd<D1, NWG, true, false>(tmem + TC_L1, t, kk[K_C1], fl + IM::F_B1,
@@ -1066,20 +1147,27 @@ __global__ void __launch_bounds__(128 * NWG, 1) fused_policy_step_kernel(policy_
       }
       uint4 h, l;
       split8<false>(dl, h, l);
-      uint32_t off = umma::panel_chunk_off(t.row, 0);
-      *reinterpret_cast<uint4 *>(smem + SM::DY_HI + off) = h;
-      *reinterpret_cast<uint4 *>(smem + SM::DY_LO + off) = l;
+      *reinterpret_cast<uint4 *>(smem + DY + umma::panel_chunk_off(t.row, 0)) = h;
+      *reinterpret_cast<uint4 *>(smem + DY + umma::panel_chunk_off(t.row, 2)) = l;
+    } else if (next < a.n_tiles) {
+      // ---- meanwhile warpgroup 1: observations of the next tile into the other X0 buffer (its last
+      // reader, the previous tile's dW1 GEMM, completed before this tile's layer-1 GEMM did)
+      wg_stash_x0(raw_s, L, xu, next, j1, xw);
+      wg_barrier_1();
+      STAMP();
+      wg_encode_x0<NOUT>(smem + x0_next, raw_s, L.inv_w, L.inv_h, j1);
+      STAMP();
     }
     sync_after_smem_writes();
     STAMP();
     // ---- dH2 = dY . W3 (contraction over the 16 padded outputs); dW3^T += [H1|H2]^T . dY runs
     // behind the dH2 epilogue
     if (mma_thread(t)) {
-      issue_gemm<1, false, true, true, true>(tmem + TC_DH2, sbase + SM::DY_HI, sbase + SM::DY_LO, sbase + IM::W3_HI,
+      issue_gemm<1, false, true, true, true>(tmem + TC_DH2, sbase + DY, sbase + DY + DY_LOFF, sbase + IM::W3_HI,
                                              sbase + IM::W3_LO, ID<D2>::BK_FM, false);
       umma::commit(c.bar);
-      issue_gemm<8, true, true, true, true>(tmem + TC_DC, sbase + SM::H_HI, sbase + SM::H_LO, sbase + SM::DY_HI,
-                                            sbase + SM::DY_LO, ID<16>::FM_BM, !first_tile);
+      issue_gemm<8, true, true, true, true>(tmem + TC_DC, sbase + SM::H_HI, sbase + SM::H_LO, sbase + DY,
+                                            sbase + DY + DY_LOFF, ID<16>::FM_BM, !first_tile);
     }
     c.wait();
     STAMP();
@@ -1102,11 +1190,14 @@ __global__ void __launch_bounds__(128 * NWG, 1) fused_policy_step_kernel(policy_
     STAMP();
     //   DB[128 x D0+16] += [dH1|dH2]^T . [X0|1]   rows 0.. = [dW1 | db1], rows 64.. col D0 = db2
     if (mma_thread(t)) {
-      issue_gemm<8, true, true, true, false>(tmem + TC_DB, sbase + SM::DH_HI, sbase + SM::DH_LO, sbase + SM::X0, 0,
+      issue_gemm<8, true, true, true, false>(tmem + TC_DB, sbase + SM::DH_HI, sbase + SM::DH_LO, sbase + x0_cur, 0,
                                              ID<D0 + 16>::BM_FM, !first_tile);
-      umma::commit(c.bar);
+      // the next tile's layer-1 commit also covers these MMAs (one wait per commit, in order);
+      // only the CTA's last tile commits here, for the drain
+      if (next >= a.n_tiles)
+        umma::commit(c.bar);
     }
-    dw_pending = true;
+    dw_pending = next >= a.n_tiles;
     first_tile = false;
   }
 
@@ -1318,7 +1409,7 @@ __global__ void __launch_bounds__(256, 2) fused_rollout_kernel(rollout_args a) {
   using IM = image_map<D1, D2>;
   constexpr int B = NOUT, P = 2 * B + 2;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t *smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);  // stays a shared-space pointer
   const float *fl = reinterpret_cast<const float *>(smem + IM::FLOATS);
   const float *b3 = fl + IM::F_B3, *kk = fl + IM::F_K;
   int8_t *sst = reinterpret_cast<int8_t *>(smem + SM::STATE);
@@ -1753,12 +1844,12 @@ void dfrl_fused_detach(dfrl_trainer *t) {
 // Phase clocks (SM cycles) of CTA 0 of the fused policy step: 12 stamps per tile, first 8 tiles.
 // The first call arms the instrumentation (returns zeros); later calls return the last launch.
 extern "C" int dfrl_debug_policy_clocks(dfrl_trainer *t, long long *out_host, int n) {
-  DFRL_CHECK(t && out_host && n > 0 && n <= 96, "bad argument");
+  DFRL_CHECK(t && out_host && n > 0 && n <= 112, "bad argument");
   fused_state *f = (fused_state *)t->fused_impl;
   DFRL_CHECK(f, "fused path not attached");
   if (!f->clk) {
-    DFRL_CUDA(cudaMalloc(&f->clk, sizeof(long long) * 96));
-    DFRL_CUDA(cudaMemsetAsync(f->clk, 0, sizeof(long long) * 96, t->ctx->stream));
+    DFRL_CUDA(cudaMalloc(&f->clk, sizeof(long long) * 112));
+    DFRL_CUDA(cudaMemsetAsync(f->clk, 0, sizeof(long long) * 112, t->ctx->stream));
   }
   DFRL_CUDA(cudaMemcpyAsync(out_host, f->clk, sizeof(long long) * n, cudaMemcpyDeviceToHost, t->ctx->stream));
   DFRL_CUDA(cudaStreamSynchronize(t->ctx->stream));

@@ -4,6 +4,10 @@
 //   variant 0  D[128 x N]  = X[128 x K] . W[N x K]^T      A K-major,  B K-major   (forward)
 //   variant 1  D[128 x Ko] = dY[128 x N] . W[N x Ko]      A K-major,  B MN-major  (input gradient)
 //   variant 2  D[128 x N2] = G[128 x 128]^T . H[128 x N2] A MN-major, B MN-major  (weight gradient)
+// and the "packed" operand used for the 16-column loss-gradient panel: hi in columns 0..15 and lo
+// in columns 16..31 of ONE panel, addressed by descriptor start offsets of 0 and 32 bytes:
+//   variant 3  D[128 x 16] = G[128 x 128]^T . Y[128 x 16]  B = packed Y, MN-major
+//   variant 4  D[128 x N]  = Y[128 x 16] . W[16 x N]       A = packed Y, K-major
 #include <math.h>
 #include <stdlib.h>
 
@@ -38,6 +42,21 @@ __device__ void stage_panels(const float *__restrict__ src, int rows, int cols, 
   }
 }
 
+// fp32 [rows][16] -> ONE panel: hi in columns 0..15, lo in columns 16..31
+__device__ void stage_packed16(const float *__restrict__ src, int rows, uint8_t *panel) {
+  for (int c = threadIdx.x; c < rows * 2; c += blockDim.x) {
+    int row = c >> 1, half = c & 1;
+    float x[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      x[j] = src[(size_t)row * 16 + half * 8 + j];
+    uint4 h, l;
+    umma::split8(x, h, l);
+    *reinterpret_cast<uint4 *>(panel + umma::panel_chunk_off(row, half)) = h;
+    *reinterpret_cast<uint4 *>(panel + umma::panel_chunk_off(row, 2 + half)) = l;
+  }
+}
+
 __global__ void __launch_bounds__(128)
 umma_selftest_kernel(int variant, const float *__restrict__ A, int a_rows, int a_cols,
                      const float *__restrict__ Bm, int b_rows, int b_cols, float *__restrict__ D,
@@ -57,8 +76,18 @@ umma_selftest_kernel(int variant, const float *__restrict__ A, int a_rows, int a
     umma::mbar_init(&mbar, 1);
     umma::fence_mbar_init();
   }
-  stage_panels(A, a_rows, a_cols, a_hi, a_lo, 128);
-  stage_panels(Bm, b_rows, b_cols, b_hi, b_lo, 128);
+  if (variant == 4) {
+    stage_packed16(A, a_rows, a_hi);
+    a_lo = a_hi + 32;
+  } else {
+    stage_panels(A, a_rows, a_cols, a_hi, a_lo, 128);
+  }
+  if (variant == 3) {
+    stage_packed16(Bm, b_rows, b_hi);
+    b_lo = b_hi + 32;
+  } else {
+    stage_panels(Bm, b_rows, b_cols, b_hi, b_lo, 128);
+  }
   umma::fence_proxy_async();
   umma::fence_before_sync();
   __syncthreads();
@@ -71,7 +100,7 @@ umma_selftest_kernel(int variant, const float *__restrict__ A, int a_rows, int a
     if (variant == 0) {
       idesc = umma::make_idesc_bf16(128, n_out, 0, 0);
       ksteps = a_cols / 16;
-    } else if (variant == 1) {
+    } else if (variant == 1 || variant == 4) {
       idesc = umma::make_idesc_bf16(128, n_out, 0, 1);
       ksteps = a_cols / 16;
     } else {
@@ -84,7 +113,7 @@ umma_selftest_kernel(int variant, const float *__restrict__ A, int a_rows, int a
       if (variant == 0) {  // both K-major: K runs along the panel row
         a_off = (k / 4) * PANEL + (k % 4) * umma::KSTEP_BYTES_KMAJOR;
         b_off = (k / 4) * PANEL + (k % 4) * umma::KSTEP_BYTES_KMAJOR;
-      } else if (variant == 1) {  // A K-major, B MN-major: B's K runs along panel rows
+      } else if (variant == 1 || variant == 4) {  // A K-major, B MN-major: B's K runs along panel rows
         a_off = (k / 4) * PANEL + (k % 4) * umma::KSTEP_BYTES_KMAJOR;
         b_off = k * umma::KSTEP_BYTES_MNMAJOR;
       } else {  // both MN-major
@@ -92,7 +121,7 @@ umma_selftest_kernel(int variant, const float *__restrict__ A, int a_rows, int a
         b_off = k * umma::KSTEP_BYTES_MNMAJOR;
       }
       // LBO: K-major swizzled -> 16 B (unused); MN-major -> stride between 64-element MN blocks
-      uint32_t a_lbo = variant == 2 ? PANEL : 16, b_lbo = variant == 0 ? 16 : PANEL;
+      uint32_t a_lbo = (variant == 2 || variant == 3) ? PANEL : 16, b_lbo = variant == 0 ? 16 : PANEL;
       uint64_t ah = umma::make_desc_sw128(umma::smem_u32(a_hi) + a_off, a_lbo, 1024);
       uint64_t al = umma::make_desc_sw128(umma::smem_u32(a_lo) + a_off, a_lbo, 1024);
       uint64_t bh = umma::make_desc_sw128(umma::smem_u32(b_hi) + b_off, b_lbo, 1024);
@@ -132,12 +161,14 @@ float lcg(uint32_t &s) {
 // columns (multiple of 16, <= 64). Returns max |D - ref| / max |ref| through *rel_err.
 extern "C" int dfrl_umma_selftest(dfrl_ctx *ctx, int variant, int k, int n, float *rel_err) {
   DFRL_CHECK(ctx && rel_err, "null argument");
-  DFRL_CHECK(variant >= 0 && variant <= 2, "variant 0..2");
+  DFRL_CHECK(variant >= 0 && variant <= 4, "variant 0..4");
   DFRL_CHECK(k % 16 == 0 && k >= 16 && k <= 128 && n % 16 == 0 && n >= 16 && n <= 64, "bad k / n");
-  DFRL_CHECK(variant != 2 || k == 128, "variant 2 contracts over the 128 tile rows");
+  DFRL_CHECK((variant != 2 && variant != 3) || k == 128, "variants 2, 3 contract over the 128 tile rows");
+  DFRL_CHECK(variant != 3 || n == 16, "variant 3 has 16 output columns");
+  DFRL_CHECK(variant != 4 || k == 16, "variant 4 contracts over 16 columns");
   int a_rows, a_cols, b_rows, b_cols;
   if (variant == 0) { a_rows = ROWS; a_cols = k; b_rows = n; b_cols = k; }
-  else if (variant == 1) { a_rows = ROWS; a_cols = k; b_rows = k; b_cols = n; }
+  else if (variant == 1 || variant == 4) { a_rows = ROWS; a_cols = k; b_rows = k; b_cols = n; }
   else { a_rows = ROWS; a_cols = 128; b_rows = ROWS; b_cols = n; }
   std::vector<float> A((size_t)a_rows * a_cols), B((size_t)b_rows * b_cols), D((size_t)ROWS * n);
   uint32_t s = 12345u + variant * 77 + k * 3 + n;
@@ -162,7 +193,7 @@ extern "C" int dfrl_umma_selftest(dfrl_ctx *ctx, int variant, int k, int n, floa
       double ref = 0;
       if (variant == 0)
         for (int q = 0; q < k; ++q) ref += (double)A[(size_t)i * k + q] * B[(size_t)j * k + q];
-      else if (variant == 1)
+      else if (variant == 1 || variant == 4)
         for (int q = 0; q < k; ++q) ref += (double)A[(size_t)i * k + q] * B[(size_t)q * n + j];
       else
         for (int r = 0; r < ROWS; ++r) ref += (double)A[(size_t)r * 128 + i] * B[(size_t)r * n + j];

@@ -129,7 +129,9 @@ int dfrl_profile_report(dfrl_ctx *ctx, char *buf, size_t cap);
 /* Self-test of the tcgen05 / TMEM building blocks the fused MLP kernels are made of: one 128-row
  * tile GEMM with bf16 hi/lo split operands in SWIZZLE_128B shared-memory panels, checked against
  * a host fp64 reference. variant 0: X.W^T (both K-major), 1: dY.W (B MN-major), 2: G^T.H (both
- * MN-major, contraction over the 128 tile rows). Writes max|D-ref| / max|ref|. */
+ * MN-major, contraction over the 128 tile rows), 3 / 4: the same as 2 / 1 with a 16-column operand
+ * whose hi and lo halves share one panel (descriptor start offsets 0 / 32 B). Writes
+ * max|D-ref| / max|ref|. */
 int dfrl_umma_selftest(dfrl_ctx *ctx, int variant, int k, int n, float *rel_err);
 
 /* ------------------------------------------------------------- K1: batched environment ---- */

@@ -6,17 +6,10 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def ctx():
-    import dependence_free_rl_b200 as D
-    c = D.Context(0)
-    yield c
-    c.close()
-
-
 @pytest.mark.parametrize("variant,k,n", [(0, 32, 64), (0, 64, 64), (0, 64, 16), (0, 128, 32),
                                          (1, 64, 64), (1, 16, 64), (1, 64, 32),
-                                         (2, 128, 64), (2, 128, 32)])
+                                         (2, 128, 64), (2, 128, 32),
+                                         (3, 128, 16), (4, 16, 64), (4, 16, 32)])
 def test_umma_tile_gemm(ctx, variant, k, n):
     import dependence_free_rl_b200 as D
     err = C.c_float(-1.0)
