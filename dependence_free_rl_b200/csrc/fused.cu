@@ -419,6 +419,10 @@ template <int N> struct ID {
   static constexpr uint32_t BK_FM = make_idesc(128, N, 1, FB, 0, 1);   // dX: A bf16 K-major, B fwd MN-major
   static constexpr uint32_t BM_FM = make_idesc(128, N, 1, FB, 1, 1);   // dW: A = dH^T (bf16), B = H / X0 (fwd)
   static constexpr uint32_t FM_BM = make_idesc(128, N, FB, 1, 1, 1);   // dW3^T: A = H^T (fwd), B = dY (bf16)
+  // M = 64 forms of the two weight-gradient GEMMs whose upper 64 output rows would be unused: half
+  // the A-operand shared-memory traffic. D row r lives in TMEM lane 32 (r / 16) + r % 16.
+  static constexpr uint32_t BM_FM_64 = make_idesc(64, N, 1, FB, 1, 1);
+  static constexpr uint32_t FM_BM_64 = make_idesc(64, N, FB, 1, 1, 1);
 };
 
 // Layers 1 and 2 of a tile whose X0 panel is staged and synchronised. Leaves H1 (and, if
@@ -792,8 +796,8 @@ __global__ void __launch_bounds__(128 * NWG, 1) fused_critic_step_kernel(critic_
                                                    c.sbase + SM::DH_LO + PANEL, c.sbase + IM::W2_HI,
                                                    c.sbase + IM::W2_LO, ID<D1>::BK_FM, false);
       umma::commit(c.bar);
-      issue_gemm<8, true, true, true, true>(c.tmem + TC_DA, c.sbase + SM::DH_HI, c.sbase + SM::DH_LO,
-                                            c.sbase + SM::H_HI, c.sbase + SM::H_LO, ID<64>::BM_FM, !first_tile);
+      issue_gemm<8, true, true, true, true>(c.tmem + TC_DA, c.sbase + SM::DH_HI + PANEL, c.sbase + SM::DH_LO + PANEL,
+                                            c.sbase + SM::H_HI, c.sbase + SM::H_LO, ID<64>::BM_FM_64, !first_tile);
     }
     c.wait();
     epi_hidden_bwd<D1, NWG>(c.tmem + TC_DH1, t, kk[K_ISW2], m1, smem + SM::DH_HI, smem + SM::DH_LO);
@@ -818,7 +822,7 @@ __global__ void __launch_bounds__(128 * NWG, 1) fused_critic_step_kernel(critic_
       constexpr int DC = D1 / NWG;
       float v[DC];
       tmem_load<DC>(c.tmem + TC_DA + t.lane_base + t.wg * DC, v);
-      int nrow = t.row - 64;
+      int nrow = t.lane < 16 ? t.w * 16 + t.lane : -1;  // M = 64: row n in TMEM lane 32 (n / 16) + n % 16
       const float s = kk[K_ISH1];
       if (nrow >= 0 && nrow < D2)
 #pragma unroll
@@ -1160,28 +1164,27 @@ __global__ void __launch_bounds__(128 * NWG, 1) fused_policy_step_kernel(policy_
     }
     sync_after_smem_writes();
     STAMP();
-    // ---- dH2 = dY . W3 (contraction over the 16 padded outputs); dW3^T += [H1|H2]^T . dY runs
+    // ---- dH2 = dY . W3 (contraction over the 16 padded outputs); dW3^T += H2^T . dY (M = 64) runs
     // behind the dH2 epilogue
     if (mma_thread(t)) {
       issue_gemm<1, false, true, true, true>(tmem + TC_DH2, sbase + DY, sbase + DY + DY_LOFF, sbase + IM::W3_HI,
                                              sbase + IM::W3_LO, ID<D2>::BK_FM, false);
       umma::commit(c.bar);
-      issue_gemm<8, true, true, true, true>(tmem + TC_DC, sbase + SM::H_HI, sbase + SM::H_LO, sbase + DY,
-                                            sbase + DY + DY_LOFF, ID<16>::FM_BM, !first_tile);
+      issue_gemm<8, true, true, true, true>(tmem + TC_DC, sbase + SM::H_HI + PANEL, sbase + SM::H_LO + PANEL,
+                                            sbase + DY, sbase + DY + DY_LOFF, ID<16>::FM_BM_64, !first_tile);
     }
     c.wait();
     STAMP();
     epi_hidden_bwd<D2, NWG>(tmem + TC_DH2, t, kk[K_ISW3], mask2, smem + SM::DH_HI + PANEL, smem + SM::DH_LO + PANEL);
     sync_after_smem_writes();
     STAMP();
-    // ---- dH1 = dH2 . W2; dW2 += [dH1|dH2]^T . H1 (rows 64.. only are used, so the stale dH1
-    // half is harmless) runs behind the dH1 epilogue
+    // ---- dH1 = dH2 . W2; dW2 += dH2^T . H1 (M = 64) runs behind the dH1 epilogue
     if (mma_thread(t)) {
       issue_gemm<D2 / 16, false, true, true, true>(tmem + TC_DH1, sbase + SM::DH_HI + PANEL, sbase + SM::DH_LO + PANEL,
                                                    sbase + IM::W2_HI, sbase + IM::W2_LO, ID<D1>::BK_FM, false);
       umma::commit(c.bar);
-      issue_gemm<8, true, true, true, true>(tmem + TC_DA, sbase + SM::DH_HI, sbase + SM::DH_LO, sbase + SM::H_HI,
-                                            sbase + SM::H_LO, ID<64>::BM_FM, !first_tile);
+      issue_gemm<8, true, true, true, true>(tmem + TC_DA, sbase + SM::DH_HI + PANEL, sbase + SM::DH_LO + PANEL,
+                                            sbase + SM::H_HI, sbase + SM::H_LO, ID<64>::BM_FM_64, !first_tile);
     }
     c.wait();
     STAMP();
@@ -1209,12 +1212,12 @@ __global__ void __launch_bounds__(128 * NWG, 1) fused_policy_step_kernel(policy_
     for (int i = threadIdx.x; i < net.n_params; i += blockDim.x)
       part[i] = 0.f;
   } else {
-    // dW2[n][k]: DA row 64 + n, col k
+    // dW2[n][k]: DA (M = 64) row n = TMEM lane 32 (n / 16) + n % 16, col k
     {
       constexpr int DC = D1 / NWG;
       float v[DC];
       tmem_load<DC>(tmem + TC_DA + t.lane_base + t.wg * DC, v);
-      int nrow = t.row - 64;
+      int nrow = t.lane < 16 ? t.w * 16 + t.lane : -1;
       const float s = kk[K_ISH1];
       if (nrow >= 0 && nrow < D2)
 #pragma unroll
@@ -1239,11 +1242,11 @@ __global__ void __launch_bounds__(128 * NWG, 1) fused_policy_step_kernel(policy_
         }
       }
     }
-    // dW3[n][k] = DC row 64 + k, col n
+    // dW3[n][k] = DC (M = 64) row k, col n
     if (t.wg == 0) {
       float v[8];
       tmem_load<8>(tmem + TC_DC + t.lane_base, v);
-      int krow = t.row - 64;
+      int krow = t.lane < 16 ? t.w * 16 + t.lane : -1;
       const float s = kk[K_ISH2];
       if (krow >= 0 && krow < D2)
 #pragma unroll
