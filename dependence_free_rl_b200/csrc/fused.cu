@@ -18,8 +18,8 @@
 // by powers of two (22 significant bits); it is off because tcgen05.mma kind::f16 raised an
 // illegal-instruction fault on B200 when the A and B formats differ, which the weight-gradient
 // GEMMs (gradient^T x activation) would need.
-// The split weight panels are built once per parameter update by fused_prep_kernel into a "panel
-// image" in global memory that every CTA copies into its shared memory.
+// Every CTA splits the fp32 weights (27 KB, L2 resident) into its own shared-memory panels at
+// start-up: no separate preparation kernel sits on the optimizer-step critical path.
 //
 // Row tiles are env-blocked: a tile holds E = 128 / T environments x all T steps (row = t * E + e)
 // so that the critic target r + gamma V(s_{t+1}) and GAE only need values of the same tile.
@@ -165,8 +165,8 @@ __device__ __forceinline__ void sync_after_smem_writes() {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Panel image: what fused_prep_kernel leaves in global memory for one net and every CTA copies
-// into shared memory (same offsets). Weight panels are forward-format hi/lo of (scale * W), swizzled.
+// Panel image: the head of every fused kernel's shared memory. Weight panels are forward-format
+// hi/lo of (scale * W), swizzled; then biases, the fp32 value-head row and the scale constants.
 template <int D1, int D2>
 struct image_map {
   static constexpr uint32_t W1_HI = 0, W1_LO = W1_HI + D1 * 128;
@@ -179,7 +179,7 @@ struct image_map {
                        F_K = F_W3S + 64, N_FLOATS = F_K + 16;
   static constexpr uint32_t BYTES = FLOATS + N_FLOATS * 4;
   static_assert((D1 * 128) % 1024 == 0 && (D2 * 128) % 1024 == 0, "panel alignment");
-  static_assert(BYTES % 16 == 0, "image is copied in 16-byte words");
+  static_assert(BYTES % 16 == 0, "16-byte aligned float region");
 };
 enum {
   K_C1 = 0,     // sh1 / sw1          : y1 = acc1 * C1 + b1s   (= sh1 * pre-activation 1)
@@ -220,10 +220,17 @@ __device__ void stage_weight_f16(const float *__restrict__ W, int N, int K, int 
   for (int c = threadIdx.x; c < rows_alloc * 8; c += blockDim.x) {
     int row = c >> 3, chunk = c & 7;
     float x[8];
+    const float *src = W + (size_t)row * K + chunk * 8;
+    if (row < N && chunk * 8 + 8 <= K && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+      float4 a = __ldg(reinterpret_cast<const float4 *>(src)), b = __ldg(reinterpret_cast<const float4 *>(src) + 1);
+      x[0] = a.x * scale, x[1] = a.y * scale, x[2] = a.z * scale, x[3] = a.w * scale;
+      x[4] = b.x * scale, x[5] = b.y * scale, x[6] = b.z * scale, x[7] = b.w * scale;
+    } else {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      int col = chunk * 8 + j;
-      x[j] = (row < N && col < K) ? W[(size_t)row * K + col] * scale : 0.f;
+      for (int j = 0; j < 8; ++j) {
+        int col = chunk * 8 + j;
+        x[j] = (row < N && col < K) ? W[(size_t)row * K + col] * scale : 0.f;
+      }
     }
     uint4 h, l;
     split8<FWD_F16>(x, h, l);
@@ -233,18 +240,15 @@ __device__ void stage_weight_f16(const float *__restrict__ W, int N, int K, int 
   }
 }
 
-// One CTA per net. Bounds (FWD_F16 scaling only): |obs| <= 1 (bins and items never exceed the capacity), so
+// Bounds (FWD_F16 scaling only): |obs| <= 1 (bins and items never exceed the capacity), so
 // |H1_j| <= |b1_j| + sum_k |W1_jk| =: h1max and |H2_j| <= |b2_j| + h1max sum_k |W2_jk|.
 template <int D0, int D1, int D2>
-__device__ void prep_body(const float *gparams, const net3 &net, uint8_t *__restrict__ image, float *params) {
+__device__ void build_image(const float *__restrict__ params, const net3 &net, uint8_t *image) {
   using IM = image_map<D1, D2>;
-  __shared__ float red[8];
-  for (int i = threadIdx.x; i < net.n_params; i += blockDim.x)
-    params[i] = gparams[i];
-  __syncthreads();
   const float *W1 = params + net.o_w1, *W2 = params + net.o_w2, *W3 = params + net.o_w3;
   float sw1 = 1.f, sw2 = 1.f, sw3 = 1.f, sh1 = 1.f, sh2 = 1.f;
   if (FWD_F16) {
+    __shared__ float red[8];
     float m1 = 0.f, m2 = 0.f, m3 = 0.f;
     for (int i = threadIdx.x; i < D1 * D0; i += blockDim.x) m1 = fmaxf(m1, fabsf(W1[i]));
     for (int i = threadIdx.x; i < D2 * D1; i += blockDim.x) m2 = fmaxf(m2, fabsf(W2[i]));
@@ -295,20 +299,6 @@ __device__ void prep_body(const float *gparams, const net3 &net, uint8_t *__rest
     k[K_B3V] = params[net.o_b3];
     for (int i = 8; i < 16; ++i) k[i] = 0.f;
   }
-}
-template <int D0, int D1, int D2>
-__global__ void __launch_bounds__(256) fused_prep_kernel(const float *__restrict__ gparams, net3 net,
-                                                        uint8_t *__restrict__ image) {
-  extern __shared__ float prep_params[];  // the whole flat parameter vector (<= 27 KB)
-  prep_body<D0, D1, D2>(gparams, net, image, prep_params);
-}
-
-// Copies the panel image into shared memory (same offsets) -- 16-byte words, all threads.
-__device__ __forceinline__ void load_image(uint8_t *smem, const uint8_t *__restrict__ image, uint32_t bytes) {
-  const uint4 *src = reinterpret_cast<const uint4 *>(image);
-  uint4 *dst = reinterpret_cast<uint4 *>(smem);
-  for (uint32_t i = threadIdx.x; i < bytes / 16; i += blockDim.x)
-    dst[i] = __ldg(src + i);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -429,12 +419,12 @@ template <int N> struct ID {
 // WRITE_H2, H2) panels written but NOT yet synchronised. y2 = sh2 * H2 of this thread's columns.
 template <int D0, int D1, int D2, int NWG, typename SM, uint32_t TL1, uint32_t TL2, bool H2_IN_PLACE, bool WRITE_H2>
 __device__ __forceinline__ void fwd_hidden(tile_ctx &c, const float *fl, uint32_t &mask1, uint32_t &mask2,
-                                           float (&y2)[D2 / NWG]) {
+                                           float (&y2)[D2 / NWG], uint32_t x0_off = SM::X0) {
   using IM = image_map<D1, D2>;
   const float *b1s = fl + IM::F_B1, *b2s = fl + IM::F_B2, *k = fl + IM::F_K;
   constexpr uint32_t H2_OFF = H2_IN_PLACE ? 0 : PANEL;
   if (mma_thread(c.t)) {
-    issue_gemm<D0 / 16, false, false, false, true>(c.tmem + TL1, c.sbase + SM::X0, 0, c.sbase + IM::W1_HI,
+    issue_gemm<D0 / 16, false, false, false, true>(c.tmem + TL1, c.sbase + x0_off, 0, c.sbase + IM::W1_HI,
                                                    c.sbase + IM::W1_LO, ID<D1>::FK_FK, false);
     umma::commit(c.bar);
   }
@@ -471,11 +461,11 @@ __device__ __forceinline__ float value_head(const tid_t &t, const float (&y2)[D2
   return v;
 }
 
-// Common one-time setup: TMEM, barrier, image -> smem, zeroed panels, ones column of X0.
+// Common one-time setup: TMEM, barrier, weights -> panel image, zeroed panels, ones column of X0.
 template <int D0, int D1, int D2, typename SM>
-__device__ __forceinline__ void setup_common(tile_ctx &c, uint8_t *smem, const uint8_t *image, uint32_t zero_from,
-                                             uint32_t zero_bytes_n, uint32_t tmem_cols, uint32_t *tmem_slot,
-                                             uint64_t *bar) {
+__device__ __forceinline__ void setup_common(tile_ctx &c, uint8_t *smem, const float *params, const net3 &net,
+                                             uint32_t zero_from, uint32_t zero_bytes_n, uint32_t tmem_cols,
+                                             uint32_t *tmem_slot, uint64_t *bar) {
   using IM = image_map<D1, D2>;
   c.smem = smem;
   c.sbase = umma::smem_u32(smem);
@@ -488,7 +478,7 @@ __device__ __forceinline__ void setup_common(tile_ctx &c, uint8_t *smem, const u
     umma::mbar_init(bar, 1);
     umma::fence_mbar_init();
   }
-  load_image(smem, image, IM::BYTES);
+  build_image<D0, D1, D2>(params, net, smem);
   zero_bytes(smem + zero_from, zero_bytes_n);
   __syncthreads();
   // ones column (col D0) of the X0 panel: [dH1|dH2]^T . 1 = bias gradients for free
@@ -680,7 +670,7 @@ __device__ __forceinline__ void wg_encode_x0(uint8_t *x0, const int8_t *raw, flo
 __device__ __forceinline__ void wg_barrier_1() { asm volatile("bar.sync 1, 128;\n" ::: "memory"); }
 
 struct critic_args {
-  const uint8_t *image;
+  const float *params;  // flat fp32 parameters of the net
   net3 net;
   learner_rows rows;
   int n_tiles;
@@ -709,7 +699,7 @@ __global__ void __launch_bounds__(128 * NWG, 1) fused_critic_step_kernel(critic_
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + SM::BARS + 16);
   const net3 net = a.net;
   tile_ctx c;
-  setup_common<D0, D1, D2, SM>(c, smem, a.image, SM::X0, SM::SCRATCH - SM::X0, TC_COLS, tmem_slot, bar);
+  setup_common<D0, D1, D2, SM>(c, smem, a.params, a.net, SM::X0, SM::SCRATCH - SM::X0, TC_COLS, tmem_slot, bar);
   const float b3 = kk[K_B3V];
   const tid_t t = c.t;
   const learner_rows &L = a.rows;
@@ -722,6 +712,12 @@ __global__ void __launch_bounds__(128 * NWG, 1) fused_critic_step_kernel(critic_
   float db3 = 0.f;
 
   int8_t *raw_s = reinterpret_cast<int8_t *>(smem + SM::RAW_S), *raw_e = reinterpret_cast<int8_t *>(smem + SM::RAW_E);
+  // separate observation panels for the end rows (pass 1) and the start rows (pass 2, also the B
+  // operand of the dW1 GEMM; the critic has no dY panel, its slot holds it): a tile never has to
+  // wait for the previous tile's weight-gradient GEMMs
+  constexpr uint32_t X0E = SM::X0, X0S = SM::DY_HI;
+  if (threadIdx.x < TILE)
+    *reinterpret_cast<uint16_t *>(smem + X0S + umma::panel_off(threadIdx.x, D0)) = ONE_FWD;
   x0_pref xp;
   if ((int)blockIdx.x < a.n_tiles)
     load_x0<true>(L, blockIdx.x, xp);
@@ -729,15 +725,11 @@ __global__ void __launch_bounds__(128 * NWG, 1) fused_critic_step_kernel(critic_
     uint32_t m1, m2;
     float y2[DC2];
     // ---- pass 1: V of the end rows
-    if (dw_pending) {  // the previous tile's dW GEMMs still read the panels
-      c.wait();
-      dw_pending = false;
-    }
     stash_x0<true>(raw_s, raw_e, L, tile, xp);
     __syncthreads();
     fix_end_rows(raw_s, raw_e, L, xp);
     __syncthreads();
-    encode_x0(smem + SM::X0, raw_e, L.B, L.inv_w, L.inv_h);
+    encode_x0(smem + X0E, raw_e, L.B, L.inv_w, L.inv_h);
     sync_after_smem_writes();
     // row data of this tile (used after the forward passes): issue the loads now
     const int tt = t.row / L.E, e = t.row % L.E;
@@ -745,17 +737,17 @@ __global__ void __launch_bounds__(128 * NWG, 1) fused_critic_step_kernel(critic_
     const bool valid = tt < L.T && i < L.n;
     const size_t k = (size_t)tt * L.n + i;
     const int d = valid ? L.rec_done[k] : 0;
-    fwd_hidden<D0, D1, D2, NWG, SM, TC_L1, TC_L2, false, false>(c, fl, m1, m2, y2);
+    fwd_hidden<D0, D1, D2, NWG, SM, TC_L1, TC_L2, false, false>(c, fl, m1, m2, y2, X0E);
     float v_end = value_head<D2, NWG>(t, y2, w3s, b3, vpart);
     if (t.wg == 0)
       ve[t.row] = v_end;
     // ---- pass 2: start rows, activations kept
-    encode_x0(smem + SM::X0, raw_s, L.B, L.inv_w, L.inv_h);
+    encode_x0(smem + X0S, raw_s, L.B, L.inv_w, L.inv_h);
     sync_after_smem_writes();
     const int next = tile + gridDim.x;
     if (next < a.n_tiles)  // prefetch the next tile's state bytes behind this tile's math
       load_x0<true>(L, next, xp);
-    fwd_hidden<D0, D1, D2, NWG, SM, TC_L1, TC_L2, false, false>(c, fl, m1, m2, y2);
+    fwd_hidden<D0, D1, D2, NWG, SM, TC_L1, TC_L2, false, false>(c, fl, m1, m2, y2, X0S);
     float v = value_head<D2, NWG>(t, y2, w3s, b3, vpart);
     if (t.wg == 0)
       vs[t.row] = v;
@@ -804,10 +796,11 @@ __global__ void __launch_bounds__(128 * NWG, 1) fused_critic_step_kernel(critic_
     sync_after_smem_writes();
     if (mma_thread(t)) {
       issue_gemm<8, true, true, true, false>(c.tmem + TC_DB, c.sbase + SM::DH_HI, c.sbase + SM::DH_LO,
-                                             c.sbase + SM::X0, 0, ID<D0 + 16>::BM_FM, !first_tile);
-      umma::commit(c.bar);
+                                             c.sbase + X0S, 0, ID<D0 + 16>::BM_FM, !first_tile);
+      if (next >= a.n_tiles)  // otherwise the next tile's first commit covers these MMAs
+        umma::commit(c.bar);
     }
-    dw_pending = true;
+    dw_pending = next >= a.n_tiles;
     first_tile = false;
   }
 
@@ -908,7 +901,7 @@ __global__ void __launch_bounds__(256, 2) fused_gae_kernel(critic_args a) {
   uint64_t *bar = reinterpret_cast<uint64_t *>(smem + SM::BARS);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + SM::BARS + 16);
   tile_ctx c;
-  setup_common<D0, D1, D2, SM>(c, smem, a.image, SM::X0, SM::SCRATCH - SM::X0, TF_COLS, tmem_slot, bar);
+  setup_common<D0, D1, D2, SM>(c, smem, a.params, a.net, SM::X0, SM::SCRATCH - SM::X0, TF_COLS, tmem_slot, bar);
   const float b3 = kk[K_B3V];
   const tid_t t = c.t;
   const learner_rows &L = a.rows;
@@ -974,7 +967,7 @@ __global__ void __launch_bounds__(256, 2) fused_gae_kernel(critic_args a) {
 enum { HEAD_JACOBIAN = 0, HEAD_IDENTITY = 1 };
 
 struct policy_step_args {
-  const uint8_t *image;
+  const float *params;  // flat fp32 parameters of the net
   net3 net;
   learner_rows rows;
   const float *adv;    // [T][n]
@@ -1000,7 +993,7 @@ __global__ void __launch_bounds__(128 * NWG, 1) fused_policy_step_kernel(policy_
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + SM::BARS + 16);
   const net3 net = a.net;
   tile_ctx c;
-  setup_common<D0, D1, D2, SM>(c, smem, a.image, SM::X0, SM::SCRATCH - SM::X0, TC_COLS, tmem_slot, bar);
+  setup_common<D0, D1, D2, SM>(c, smem, a.params, a.net, SM::X0, SM::SCRATCH - SM::X0, TC_COLS, tmem_slot, bar);
   const tid_t t = c.t;
   const learner_rows &L = a.rows;
   const uint32_t tmem = c.tmem, sbase = c.sbase;
@@ -1275,23 +1268,18 @@ __global__ void __launch_bounds__(128 * NWG, 1) fused_policy_step_kernel(policy_
 
 // Second stage of the gradient: fixed-order sum of the per-CTA partials. Block = 32 parameters x 8
 // slices of the CTA range; the 8 slice sums are combined in a fixed order. With a single rank the
-// optimizer update (nn.h:616-698) of the same 32 parameters follows in the same kernel, and the
-// block that finishes last rebuilds the net's panel image from the updated parameters.
+// optimizer update (nn.h:616-698) of the same 32 parameters follows in the same kernel.
 struct reduce_tail {
   dfrl_opt_spec opt;   // params == null: no update
-  uint8_t *image;      // null: no rebuild
-  net3 net;
-  unsigned *ticket;    // zero before the launch, zero again after it
+  unsigned *ticket;    // multi-rank publish: zero before the launch, zero again after it
   unsigned *publish;   // multi-rank: flag of the exchange slot `grad` points into, set to
   unsigned epoch;      //   `epoch` by the last block once the whole gradient is visible system-wide
 };
-template <int D0, int D1, int D2>
 __global__ void __launch_bounds__(256) fused_reduce_partials_kernel(const float *__restrict__ part, int ctas,
                                                                     int n, float *__restrict__ grad,
                                                                     reduce_tail tail) {
   __shared__ float sm[8][33];
   __shared__ int is_last;
-  extern __shared__ float prep_params[];
   const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + lane;
   float s = 0.f;
@@ -1310,9 +1298,9 @@ __global__ void __launch_bounds__(256) fused_reduce_partials_kernel(const float 
     if (opt.params)
       opt_update(opt.kind, opt.params, grad, opt.state, n, i, opt.lr, opt.wd, opt.beta1, opt.beta2, opt.c1, opt.c2);
   }
-  if (!tail.image && !tail.publish)
+  if (!tail.publish)
     return;
-  __threadfence_system();  // this block's writes (parameters / exchange slot) before its ticket
+  __threadfence_system();  // this block's writes to the exchange slot before its ticket
   __syncthreads();
   if (threadIdx.x == 0) {
     unsigned tk = atomicAdd(tail.ticket, 1u);
@@ -1324,16 +1312,12 @@ __global__ void __launch_bounds__(256) fused_reduce_partials_kernel(const float 
   if (!is_last)
     return;
   __threadfence_system();
-  if (tail.publish) {
-    if (threadIdx.x == 0)
-      *reinterpret_cast<volatile unsigned *>(tail.publish) = tail.epoch;
-    return;
-  }
-  prep_body<D0, D1, D2>(tail.opt.params, tail.net, tail.image, prep_params);
+  if (threadIdx.x == 0)
+    *reinterpret_cast<volatile unsigned *>(tail.publish) = tail.epoch;
 }
 
 // K8 + K7 over NVLink peer memory: pull every rank's published gradient, sum in rank order
-// (bit-identical on every rank), optimizer update, and the last block rebuilds the panel image.
+// (bit-identical on every rank), optimizer update.
 // Waits (bounded) for the peers' publish flags: every rank runs the same launch sequence on its own
 // GPU, and a peer's producer kernel never depends on this rank.
 struct p2p_view {
@@ -1341,11 +1325,8 @@ struct p2p_view {
   int nranks, slot;
   unsigned epoch;
 };
-template <int D0, int D1, int D2>
 __global__ void __launch_bounds__(256) fused_p2p_sum_opt_kernel(p2p_view v, int n, float *__restrict__ grad,
                                                                 reduce_tail tail) {
-  __shared__ int is_last;
-  extern __shared__ float prep_params[];
   if ((int)threadIdx.x < v.nranks) {
     const volatile unsigned *flag =
         reinterpret_cast<const volatile unsigned *>(v.peer[threadIdx.x] + 2 * DFRL_P2P_CAP) + v.slot;
@@ -1366,21 +1347,6 @@ __global__ void __launch_bounds__(256) fused_p2p_sum_opt_kernel(p2p_view v, int 
     if (opt.params)
       opt_update(opt.kind, opt.params, grad, opt.state, n, i, opt.lr, opt.wd, opt.beta1, opt.beta2, opt.c1, opt.c2);
   }
-  if (!tail.image)
-    return;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned tk = atomicAdd(tail.ticket, 1u);
-    is_last = tk == gridDim.x - 1;
-    if (is_last)
-      *tail.ticket = 0;
-  }
-  __syncthreads();
-  if (!is_last)
-    return;
-  __threadfence();
-  prep_body<D0, D1, D2>(tail.opt.params, tail.net, tail.image, prep_params);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1390,7 +1356,7 @@ __global__ void __launch_bounds__(256) fused_p2p_sum_opt_kernel(p2p_view v, int 
 // forward GEMMs on the tensor cores, and one thread per environment does softmax -> action
 // (sample / argmax / forced) -> environment::apply -> reward / done / reset / next item.
 struct rollout_args {
-  const uint8_t *image;
+  const float *params;  // flat fp32 parameters of the net
   net3 net;
   env_params ep;
   int8_t *state;             // live planes [P][stride]
@@ -1420,7 +1386,7 @@ __global__ void __launch_bounds__(256, 2) fused_rollout_kernel(rollout_args a) {
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + SM::BARS + 16);
   const env_params &ep = a.ep;
   tile_ctx c;
-  setup_common<D0, D1, D2, SM>(c, smem, a.image, SM::X0, SM::SCRATCH - SM::X0, TF_COLS, tmem_slot, bar);
+  setup_common<D0, D1, D2, SM>(c, smem, a.params, a.net, SM::X0, SM::SCRATCH - SM::X0, TF_COLS, tmem_slot, bar);
   const tid_t t = c.t;
   const uint32_t tmem = c.tmem, sbase = c.sbase;
 
@@ -1571,8 +1537,6 @@ struct fused_state {
   bool policy_ok, value_ok, rollout_ok;
   int head_bwd;
   float *partials;  // [ctas][max params]
-  uint8_t *pimage, *vimage;
-  uint64_t pimage_version, vimage_version;  // dfrl_mlp::version the image was built from
   unsigned *ticket;  // last-block election of the reduction kernel
   int ctas;
   long long *clk;  // [96] phase clocks of the last policy step (allocated on first request)
@@ -1664,25 +1628,9 @@ bool widths_ok(const net3 &n) {
   return n.d0 == 32 && ((n.d1 == 64 && n.d2 == 64) || (n.d1 == 16 && n.d2 == 16));
 }
 
-size_t image_bytes(const net3 &n) { return n.d1 == 64 ? image_map<64, 64>::BYTES : image_map<16, 16>::BYTES; }
-
-// (Re)build the panel image of `m` when its parameters changed since the last build.
-int refresh_image(dfrl_ctx *ctx, dfrl_mlp *m, const net3 &net, uint8_t *image, uint64_t *built_version) {
-  if (*built_version == m->version)
-    return DFRL_OK;
-  if (net.d1 == 64)
-    DFRL_LAUNCH(ctx, (fused_prep_kernel<32, 64, 64>), 1, 256, sizeof(float) * net.n_params,
-                (const float *)m->params, net, image);
-  else
-    DFRL_LAUNCH(ctx, (fused_prep_kernel<32, 16, 16>), 1, 256, sizeof(float) * net.n_params,
-                (const float *)m->params, net, image);
-  *built_version = m->version;
-  return DFRL_OK;
-}
-
 struct fused_state;
 int launch_reduce(dfrl_trainer *t, fused_state *f, dfrl_mlp *m, const net3 &net, int ctas, float *grad_dev,
-                  const dfrl_opt_spec *opt, uint8_t *image, uint64_t *image_version);
+                  const dfrl_opt_spec *opt);
 
 learner_rows make_rows(dfrl_trainer *t) {
   learner_rows r;
@@ -1702,7 +1650,7 @@ learner_rows make_rows(dfrl_trainer *t) {
 
 critic_args make_critic_args(dfrl_trainer *t, fused_state *f) {
   critic_args a;
-  a.image = f->vimage;
+  a.params = t->value->params;
   a.net = f->vnet;
   a.rows = make_rows(t);
   a.n_tiles = ceil_div(t->n, a.rows.E);
@@ -1714,16 +1662,15 @@ critic_args make_critic_args(dfrl_trainer *t, fused_state *f) {
   return a;
 }
 
-// Partials -> gradient (-> optimizer update -> rebuilt panel image when `opt` is given).
+// Partials -> gradient (-> optimizer update when `opt` is given).
 // Several ranks (opt given means the peers are attached): the reduced gradient goes to this rank's
 // exchange slot and a second kernel pulls all ranks' slots over NVLink before the update.
 int launch_reduce(dfrl_trainer *t, fused_state *f, dfrl_mlp *m, const net3 &net, int ctas, float *grad_dev,
-                  const dfrl_opt_spec *opt, uint8_t *image, uint64_t *image_version) {
+                  const dfrl_opt_spec *opt) {
   dfrl_ctx *ctx = t->ctx;
   const bool exchange = opt && ctx->nranks > 1;
   reduce_tail tail;
   memset(&tail, 0, sizeof(tail));
-  size_t smem = 0;
   float *dst = grad_dev;
   int slot = 0;
   if (exchange) {
@@ -1736,18 +1683,9 @@ int launch_reduce(dfrl_trainer *t, fused_state *f, dfrl_mlp *m, const net3 &net,
     tail.epoch = ctx->p2p.epoch;
   } else if (opt) {
     tail.opt = *opt;
-    tail.image = image;
-    tail.net = net;
-    tail.ticket = f->ticket;
-    smem = sizeof(float) * net.n_params;
   }
-  const int grid = ceil_div(net.n_params, 32);
-  if (net.d1 == 64)
-    DFRL_LAUNCH(ctx, (fused_reduce_partials_kernel<32, 64, 64>), grid, 256, smem, (const float *)f->partials,
-                ctas, net.n_params, dst, tail);
-  else
-    DFRL_LAUNCH(ctx, (fused_reduce_partials_kernel<32, 16, 16>), grid, 256, smem, (const float *)f->partials,
-                ctas, net.n_params, dst, tail);
+  DFRL_LAUNCH(ctx, fused_reduce_partials_kernel, ceil_div(net.n_params, 32), 256, 0, (const float *)f->partials, ctas,
+              net.n_params, dst, tail);
   if (exchange) {
     p2p_view v;
     memset(&v, 0, sizeof(v));
@@ -1759,21 +1697,10 @@ int launch_reduce(dfrl_trainer *t, fused_state *f, dfrl_mlp *m, const net3 &net,
     reduce_tail t2;
     memset(&t2, 0, sizeof(t2));
     t2.opt = *opt;
-    t2.image = image;
-    t2.net = net;
-    t2.ticket = f->ticket;
-    const size_t smem2 = sizeof(float) * net.n_params;
-    if (net.d1 == 64)
-      DFRL_LAUNCH(ctx, (fused_p2p_sum_opt_kernel<32, 64, 64>), ceil_div(net.n_params, 256), 256, smem2, v,
-                  net.n_params, grad_dev, t2);
-    else
-      DFRL_LAUNCH(ctx, (fused_p2p_sum_opt_kernel<32, 16, 16>), ceil_div(net.n_params, 256), 256, smem2, v,
-                  net.n_params, grad_dev, t2);
+    DFRL_LAUNCH(ctx, fused_p2p_sum_opt_kernel, ceil_div(net.n_params, 256), 256, 0, v, net.n_params, grad_dev, t2);
   }
-  if (opt) {  // parameters changed and the image already matches them
+  if (opt)
     m->wt_dirty = true, m->version++;
-    *image_version = m->version;
-  }
   return DFRL_OK;
 }
 
@@ -1814,19 +1741,12 @@ int dfrl_fused_try_attach(dfrl_trainer *t) {
   if (ok)
     ok = cudaMalloc(&f->ticket, sizeof(unsigned)) == cudaSuccess &&
          cudaMemsetAsync(f->ticket, 0, sizeof(unsigned), t->ctx->stream) == cudaSuccess;
-  if (ok && f->policy_ok)
-    ok = cudaMalloc(&f->pimage, image_bytes(f->pnet)) == cudaSuccess;
-  if (ok && f->value_ok)
-    ok = cudaMalloc(&f->vimage, image_bytes(f->vnet)) == cudaSuccess;
   if (!ok) {
     cudaFree(f->ticket);
     cudaFree(f->partials);
-    cudaFree(f->pimage);
-    cudaFree(f->vimage);
     delete f;
     return DFRL_ERR_CUDA;
   }
-  f->pimage_version = f->vimage_version = ~0ull;
   t->fused_impl = f;
   return DFRL_OK;
 }
@@ -1835,8 +1755,6 @@ void dfrl_fused_detach(dfrl_trainer *t) {
   fused_state *f = (fused_state *)t->fused_impl;
   if (f) {
     cudaFree(f->partials);
-    cudaFree(f->pimage);
-    cudaFree(f->vimage);
     cudaFree(f->clk);
     cudaFree(f->ticket);
     delete f;
@@ -1864,9 +1782,8 @@ int dfrl_fused_policy_gradient(dfrl_trainer *t, int loss_kind, float *grad_dev, 
   fused_state *f = (fused_state *)t->fused_impl;
   if (!f || !f->policy_ok || loss_kind == DFRL_LOSS_KL)
     return DFRL_ERR_UNSUPPORTED;
-  DFRL_TRY(refresh_image(t->ctx, t->policy, f->pnet, f->pimage, &f->pimage_version));
   policy_step_args a;
-  a.image = f->pimage;
+  a.params = t->policy->params;
   a.net = f->pnet;
   a.rows = make_rows(t);
   a.adv = t->adv;
@@ -1881,7 +1798,7 @@ int dfrl_fused_policy_gradient(dfrl_trainer *t, int loss_kind, float *grad_dev, 
     DFRL_TRY((launch_policy_step<32, 64, 64, 8>(t->ctx, a, ctas)));
   else
     DFRL_TRY((launch_policy_step<32, 16, 16, 8>(t->ctx, a, ctas)));
-  return launch_reduce(t, f, t->policy, f->pnet, ctas, grad_dev, opt, f->pimage, &f->pimage_version);
+  return launch_reduce(t, f, t->policy, f->pnet, ctas, grad_dev, opt);
 }
 
 // update_value_model (policy_gradient.h:196-218) up to the gradient: writes t->targets and grad_dev.
@@ -1889,14 +1806,13 @@ int dfrl_fused_critic_gradient(dfrl_trainer *t, float *grad_dev, const dfrl_opt_
   fused_state *f = (fused_state *)t->fused_impl;
   if (!f || !f->value_ok)
     return DFRL_ERR_UNSUPPORTED;
-  DFRL_TRY(refresh_image(t->ctx, t->value, f->vnet, f->vimage, &f->vimage_version));
   critic_args a = make_critic_args(t, f);
   int ctas = a.n_tiles < f->ctas ? a.n_tiles : f->ctas;
   if (f->vnet.d1 == 64)
     DFRL_TRY((launch_critic_step<32, 64, 64>(t->ctx, a, ctas)));
   else
     DFRL_TRY((launch_critic_step<32, 16, 16>(t->ctx, a, ctas)));
-  return launch_reduce(t, f, t->value, f->vnet, ctas, grad_dev, opt, f->vimage, &f->vimage_version);
+  return launch_reduce(t, f, t->value, f->vnet, ctas, grad_dev, opt);
 }
 
 // calculate_advantage (policy_gradient.h:220-281) with the current (updated) critic: writes t->adv.
@@ -1904,7 +1820,6 @@ int dfrl_fused_gae(dfrl_trainer *t) {
   fused_state *f = (fused_state *)t->fused_impl;
   if (!f || !f->value_ok)
     return DFRL_ERR_UNSUPPORTED;
-  DFRL_TRY(refresh_image(t->ctx, t->value, f->vnet, f->vimage, &f->vimage_version));
   critic_args a = make_critic_args(t, f);
   int ctas = a.n_tiles < 2 * f->ctas ? a.n_tiles : 2 * f->ctas;
   if (f->vnet.d1 == 64)
@@ -1920,10 +1835,9 @@ int dfrl_fused_rollout(dfrl_trainer *t, const uint8_t *items_dev, const uint8_t 
   fused_state *f = (fused_state *)t->fused_impl;
   if (!f || !f->rollout_ok)
     return DFRL_ERR_UNSUPPORTED;
-  DFRL_TRY(refresh_image(t->ctx, t->policy, f->pnet, f->pimage, &f->pimage_version));
   dfrl_env *e = t->env;
   rollout_args a;
-  a.image = f->pimage;
+  a.params = t->policy->params;
   a.net = f->pnet;
   a.ep = make_params(e);
   a.state = e->state;
