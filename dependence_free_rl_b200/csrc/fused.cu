@@ -1751,6 +1751,11 @@ int dfrl_fused_try_attach(dfrl_trainer *t) {
   return DFRL_OK;
 }
 
+bool dfrl_fused_covers_iteration(const dfrl_trainer *t) {
+  const fused_state *f = (const fused_state *)t->fused_impl;
+  return f && f->policy_ok && f->value_ok && f->rollout_ok && t->cfg.algo != DFRL_ALGO_KL_PPO;
+}
+
 void dfrl_fused_detach(dfrl_trainer *t) {
   fused_state *f = (fused_state *)t->fused_impl;
   if (f) {

@@ -33,7 +33,14 @@ struct dfrl_trainer {
   void *pin;  // 64 B pinned host staging
   long long last_rollout_steps, last_rollout_reward;
   void *fused_impl;  // non-null when the fused kernels drive this trainer
+  // one free-running iteration captured as a CUDA graph (dfrl_trainer_iterate), see trainer.cu
+  void *graph_exec;        // cudaGraphExec_t
+  long long graph_launches;  // kernels per captured iteration
+  int plain_iterations;    // iterations run launch by launch so far
 };
+
+// fused.cu: true when rollout, critic step, GAE and policy steps all run on the fused kernels
+bool dfrl_fused_covers_iteration(const dfrl_trainer *t);
 
 // Optimizer update fused behind the gradient reduction (single rank). params == null: none.
 struct dfrl_opt_spec {
