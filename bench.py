@@ -168,12 +168,17 @@ def workload_config(args, n_envs_note=None):
 
 # ------------------------------------------------------------------ our arm ------------------
 
-def make_trainer(D, ctx, n_envs, env_offset, global_rows, seed=1234, fused=1):
-    policy = D.Model(ctx, D.fc_layers(POLICY_DIMS, D.SOFTMAX), 32)
-    value = D.Model(ctx, D.fc_layers(VALUE_DIMS), 32)
+C5_POLICY_DIMS = [128, 256, 256, 256, 32]   # BASELINE configs[4]: 32 bins, 3 hidden layers of 256
+C5_VALUE_DIMS = [128, 256, 256, 256, 1]
+
+
+def make_trainer(D, ctx, n_envs, env_offset, global_rows, seed=1234, fused=1, pdims=None, vdims=None, n_bins=8):
+    pdims, vdims = pdims or POLICY_DIMS, vdims or VALUE_DIMS
+    policy = D.Model(ctx, D.fc_layers(pdims, D.SOFTMAX), 4 * n_bins)
+    value = D.Model(ctx, D.fc_layers(vdims), 4 * n_bins)
     policy.init_parameters(seed)       # identical on every rank (replicated parameters)
     value.init_parameters(seed + 1)
-    env = D.Environment(ctx, n_envs, seed=seed, env_offset=env_offset)
+    env = D.Environment(ctx, n_envs, n_bins=n_bins, seed=seed, env_offset=env_offset)
     tr = D.Trainer(ctx, env, policy, value, algo=D.PPO, work=T_STEPS,
                    policy_lr=REF_LR_P * REF_ROWS / global_rows, value_lr=REF_LR_V * REF_ROWS / global_rows,
                    fused=fused)
@@ -382,6 +387,29 @@ def run_ours(args):
         o.close()
 
     extra = {}
+    if world == 1 and not args.no_c5:
+        # BASELINE configs[4] (GEMM-bound): 32 bins, 128-256-256-256-{32,1} nets; layered path whose
+        # dense products run on the tcgen05 GEMMs of csrc/gemm_umma.cu
+        n5 = args.c5_envs
+        tr5, env5, p5, v5 = make_trainer(D, ctx, n5, 0, n5 * T_STEPS, pdims=C5_POLICY_DIMS, vdims=C5_VALUE_DIMS, n_bins=32)
+        tr5.iterate(2)
+        ctx.sync()
+        ctx.timer_start()
+        tr5.iterate(5)
+        ms5 = ctx.timer_stop() / 5
+        prof5 = kernel_profile(D, ctx, tr5, 2)
+        f5 = flops_per_env_step(C5_POLICY_DIMS, C5_VALUE_DIMS) * n5 * T_STEPS
+        gemm_ms = sum(v["ms"] for k, v in prof5.items() if "umma_gemm" in k)
+        extra["c5_32bins_256hidden"] = {
+            "value": n5 * T_STEPS / (ms5 * 1e-3), "unit": "env-steps/s", "envs": n5, "ms_per_step": ms5,
+            "algorithmic_tflops_whole_step": f5 / (ms5 * 1e-3) / 1e12,
+            "umma_gemm_ms_per_step": gemm_ms,
+            "umma_gemm_tflops": f5 / (gemm_ms * 1e-3) / 1e12 if gemm_ms else None,
+            "umma_gemm_frac_of_bf16_peak": f5 / (gemm_ms * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"] if gemm_ms else None,
+            "per_kernel_ms": {k.split("(")[-1].split("<")[0].strip("() "): round(v["ms"], 3)
+                              for k, v in sorted(prof5.items(), key=lambda kv: -kv[1]["ms"])[:8]}}
+        for o in (tr5, env5, p5, v5):
+            o.close()
     if world == 1 and not args.no_c2:
         # BASELINE configs[1] verbatim: PPO, 4096 parallel envs, 1 GPU (latency-bound size)
         c2 = measure(D, ctx, None, args, 4096, 1, 0, max(args.steps, 50), max(args.warmup, 5), False)
@@ -430,6 +458,8 @@ def main():
     ap.add_argument("--ref-iters", type=int, default=10)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-c2", action="store_true")
+    ap.add_argument("--no-c5", action="store_true")
+    ap.add_argument("--c5-envs", type=int, default=32768)
     ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: NCCL all-reduce instead of the fused peer-memory exchange")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -83,6 +83,9 @@ struct dfrl_ctx {
   // scratch arena (grown on demand, never shrunk): transient kernel workspaces
   void *scratch = nullptr;
   size_t scratch_bytes = 0;
+  // second arena for the tcgen05 GEMMs (their B image / partials must not alias a caller's scratch)
+  void *umma_ws = nullptr;
+  size_t umma_ws_bytes = 0;
   dfrl_p2p p2p;
   // per-kernel event timing (dfrl_profile_*)
   int profiling = 0;
@@ -93,6 +96,7 @@ struct dfrl_ctx;
 void dfrl_profile_mark(dfrl_ctx *ctx, const char *name, int end);
 
 int dfrl_scratch(dfrl_ctx *ctx, size_t bytes, void **out);
+int dfrl_umma_workspace(dfrl_ctx *ctx, size_t bytes, void **out);
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 static inline size_t round_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
@@ -166,6 +170,11 @@ struct dfrl_mlp {
   int kept_rows;
   const float *kept_input;
 };
+
+// gemm_umma.cu: tcgen05 GEMMs of the layered path; DFRL_ERR_UNSUPPORTED = use the FFMA kernels
+int umma_gemm_nn(dfrl_ctx *ctx, const float *A, const float *Bm, const float *bias, const float *mask, float *C,
+                 int M, int N, int K, int relu);
+int umma_gemm_tn(dfrl_ctx *ctx, const float *dY, const float *X, int M, int N, int K, float *grad, int accumulate);
 
 int dfrl_mlp_refresh_wt(dfrl_mlp *m);
 int dfrl_mlp_forward_keep(dfrl_mlp *m, const float *x_dev, int rows, float **out_dev);

@@ -135,6 +135,8 @@ extern "C" int dfrl_destroy(dfrl_ctx *ctx) {
     g_nccl.destroy(ctx->nccl_comm);
   if (ctx->scratch)
     cudaFree(ctx->scratch);
+  if (ctx->umma_ws)
+    cudaFree(ctx->umma_ws);
   for (int r = 0; r < ctx->nranks && ctx->p2p.attached; ++r)
     if (r != ctx->rank && ctx->p2p.peer[r])
       cudaIpcCloseMemHandle(ctx->p2p.peer[r]);
@@ -180,6 +182,21 @@ int dfrl_scratch(dfrl_ctx *ctx, size_t bytes, void **out) {
     ctx->scratch_bytes = want;
   }
   *out = ctx->scratch;
+  return DFRL_OK;
+}
+
+int dfrl_umma_workspace(dfrl_ctx *ctx, size_t bytes, void **out) {
+  if (bytes > ctx->umma_ws_bytes) {
+    DFRL_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->umma_ws)
+      DFRL_CUDA(cudaFree(ctx->umma_ws));
+    ctx->umma_ws = nullptr;
+    ctx->umma_ws_bytes = 0;
+    size_t want = round_up(bytes + bytes / 4, 1 << 20);
+    DFRL_CUDA(cudaMalloc(&ctx->umma_ws, want));
+    ctx->umma_ws_bytes = want;
+  }
+  *out = ctx->umma_ws;
   return DFRL_OK;
 }
 

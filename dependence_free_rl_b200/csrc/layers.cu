@@ -182,6 +182,11 @@ int gemm_nn(dfrl_ctx *ctx, const float *A, const float *Bm, const float *bias, c
             float *C, int M, int N, int K, int relu) {
   if (M <= 0 || N <= 0)
     return DFRL_OK;
+  {  // large, GEMM-shaped problems go to the tensor cores (gemm_umma.cu)
+    int rc = umma_gemm_nn(ctx, A, Bm, bias, mask, C, M, N, K, relu);
+    if (rc != DFRL_ERR_UNSUPPORTED)
+      return rc;
+  }
   if (K <= 8) {
     if (N > 32) return launch_gemm_nn<128, 64, 8>(ctx, A, Bm, bias, mask, C, M, N, K, relu);
     if (N > 8) return launch_gemm_nn<256, 32, 8>(ctx, A, Bm, bias, mask, C, M, N, K, relu);
@@ -371,6 +376,11 @@ int launch_gemm_tn(dfrl_ctx *ctx, const float *dY, const float *X, int M, int N,
 
 int gemm_tn(dfrl_ctx *ctx, const float *dY, const float *X, int M, int N, int K, float *grad,
             int accumulate) {
+  {
+    int rc = umma_gemm_tn(ctx, dY, X, M, N, K, grad, accumulate);
+    if (rc != DFRL_ERR_UNSUPPORTED)
+      return rc;
+  }
   // pick the smallest tile covering N x K (capped at 64 x 64)
   int tn = N > 32 ? 64 : N > 16 ? 32 : N > 8 ? 16 : 8;
   int tk = K > 32 ? 64 : K > 16 ? 32 : K > 8 ? 16 : 8;
@@ -425,6 +435,38 @@ __global__ void softmax_fwd_kernel(const float *__restrict__ x, int rows, int co
     yi[c] = yi[c] / s;
 }
 // softmax_layer::backward (nn.h:393-417) from the probabilities s: dx_j = s_j (g_j - sum s_k g_k).
+// Wide rows (cols > 8, e.g. 32 bins): 8 lanes per row, lane j owns columns j, j + 8, ... so that a
+// warp reads 4 rows as contiguous 32-byte pieces; fixed-order xor-shuffle sums (deterministic).
+__global__ void softmax_fwd_wide_kernel(const float *__restrict__ x, int rows, int cols,
+                                        float *__restrict__ y) {
+  long long g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const int j = threadIdx.x & 7;
+  const bool ok = g < rows;
+  const float *xi = x + (size_t)(ok ? g : 0) * cols;
+  float s = 0.f;
+  for (int c = j; c < cols && ok; c += 8)
+    s += expf(xi[c]);
+  for (int o = 4; o > 0; o >>= 1)
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (ok)
+    for (int c = j; c < cols; c += 8)
+      y[(size_t)g * cols + c] = expf(xi[c]) / s;
+}
+__global__ void softmax_bwd_probs_wide_kernel(const float *__restrict__ s, const float *__restrict__ dy,
+                                              int rows, int cols, float *__restrict__ dx) {
+  long long g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const int j = threadIdx.x & 7;
+  const bool ok = g < rows;
+  const float *si = s + (size_t)(ok ? g : 0) * cols, *gi = dy + (size_t)(ok ? g : 0) * cols;
+  float dot = 0.f;
+  for (int c = j; c < cols && ok; c += 8)
+    dot = fmaf(si[c], gi[c], dot);
+  for (int o = 4; o > 0; o >>= 1)
+    dot += __shfl_xor_sync(0xffffffffu, dot, o);
+  if (ok)
+    for (int c = j; c < cols; c += 8)
+      dx[(size_t)g * cols + c] = si[c] * (gi[c] - dot);
+}
 __global__ void softmax_bwd_probs_kernel(const float *__restrict__ s, const float *__restrict__ dy,
                                          int rows, int cols, float *__restrict__ dx) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -515,7 +557,10 @@ extern "C" int dfrl_softmax_forward(dfrl_ctx *ctx, const float *x_dev, int rows,
   DFRL_CHECK(ctx && x_dev && y_dev, "null argument");
   DFRL_CHECK(rows >= 0 && cols > 0, "bad shape");
   if (rows)
-    DFRL_LAUNCH(ctx, softmax_fwd_kernel, ceil_div(rows, 128), 128, 0, x_dev, rows, cols, y_dev);
+    if (cols > 8)
+      DFRL_LAUNCH(ctx, softmax_fwd_wide_kernel, ceil_div((long long)rows * 8, 256), 256, 0, x_dev, rows, cols, y_dev);
+    else
+      DFRL_LAUNCH(ctx, softmax_fwd_kernel, ceil_div(rows, 128), 128, 0, x_dev, rows, cols, y_dev);
   return DFRL_OK;
 }
 extern "C" int dfrl_softmax_backward(dfrl_ctx *ctx, const float *x_dev, const float *dy_dev,
@@ -727,7 +772,10 @@ int dfrl_mlp_forward_keep(dfrl_mlp *m, const float *x_dev, int rows, float **out
       size_t cnt = (size_t)rows * L.out_cols;
       DFRL_LAUNCH(ctx, relu_fwd_kernel, ceil_div((long long)cnt, 256), 256, 0, in, cnt, dst);
     } else {
-      DFRL_LAUNCH(ctx, softmax_fwd_kernel, ceil_div(rows, 128), 128, 0, in, rows, L.out_cols, dst);
+      if (L.out_cols > 8)
+        DFRL_LAUNCH(ctx, softmax_fwd_wide_kernel, ceil_div((long long)rows * 8, 256), 256, 0, in, rows, L.out_cols, dst);
+      else
+        DFRL_LAUNCH(ctx, softmax_fwd_kernel, ceil_div(rows, 128), 128, 0, in, rows, L.out_cols, dst);
     }
     in = dst;
   }
@@ -792,8 +840,12 @@ int dfrl_mlp_backward(dfrl_mlp *m, const float *dy_dev, float *grad_dev) {
         break;
       float *dst = buf[which];
       which ^= 1;
-      DFRL_LAUNCH(ctx, softmax_bwd_probs_kernel, ceil_div(rows, 128), 128, 0, m->acts[l], back, rows,
-                  L.out_cols, dst);
+      if (L.out_cols > 8)
+        DFRL_LAUNCH(ctx, softmax_bwd_probs_wide_kernel, ceil_div((long long)rows * 8, 256), 256, 0, m->acts[l], back,
+                    rows, L.out_cols, dst);
+      else
+        DFRL_LAUNCH(ctx, softmax_bwd_probs_kernel, ceil_div(rows, 128), 128, 0, m->acts[l], back, rows,
+                    L.out_cols, dst);
       back = dst;
     } else {
       // softmax_cross_entropy_layer::backward is the identity (nn.h:428-430)

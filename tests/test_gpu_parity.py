@@ -144,7 +144,12 @@ def _dense_case(D, ctx, orc, rows, n_in, n_out, seed, relu=False):
 
 @pytest.mark.parametrize("rows,n_in,n_out", [(1, 32, 64), (37, 32, 64), (1000, 64, 64), (333, 64, 8),
                                              (129, 64, 1), (4, 5, 3), (777, 4, 128), (513, 128, 64),
-                                             (260, 256, 256), (100, 128, 32), (64, 64, 32), (50, 32, 16)])
+                                             (260, 256, 256), (100, 128, 32), (64, 64, 32), (50, 32, 16),
+                                             # >= 4096 rows: the tcgen05 GEMMs of gemm_umma.cu (C5 shapes,
+                                             # ragged last tile, M = 64 / 128 / 2 x 128 output blocks)
+                                             (5000, 128, 256), (4100, 256, 256), (6001, 256, 32),
+                                             (4096, 32, 64), (4500, 64, 16), (8192, 256, 128),
+                                             (4097, 48, 64), (4200, 64, 8)])
 def test_dense_layer_vs_oracle(D, ctx, orc, rows, n_in, n_out):
     _dense_case(D, ctx, orc, rows, n_in, n_out, rows + n_in + n_out)
     _dense_case(D, ctx, orc, rows, n_in, n_out, 3, relu=True)
