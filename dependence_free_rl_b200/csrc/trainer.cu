@@ -589,73 +589,72 @@ static int learn_layered(dfrl_trainer *t) {
   return DFRL_OK;
 }
 
-extern "C" int dfrl_trainer_learn(dfrl_trainer *t) {
-  DFRL_CHECK(t, "null trainer");
-  return learn_layered(t);
-}
 
-static int iterate_once(dfrl_trainer *t) {
-  int rc = t->fused_impl ? dfrl_fused_rollout(t, nullptr, nullptr, nullptr) : DFRL_ERR_UNSUPPORTED;
-  if (rc == DFRL_ERR_UNSUPPORTED)
-    rc = rollout_layered(t, nullptr, nullptr, nullptr);
-  DFRL_TRY(rc);
-  return learn_layered(t);
-}
-
-// A free-running iteration of the fully fused path is a fixed sequence of kernel launches with
-// constant arguments (no host round trip, no memset / memcpy): it is captured once as a CUDA
-// graph and replayed, which removes the per-launch CPU and scheduling gaps that dominate at small
-// environment counts (C2: 12 launches of ~10 us each). Not eligible: several ranks (the exchange
+// The learn phase of the fully fused path is a fixed sequence of kernel launches with constant
+// arguments (no host round trip, no memset / memcpy): it is captured once as a CUDA graph and
+// replayed, which removes the per-launch CPU and scheduling gaps that dominate at small
+// environment counts (C2: 11 launches of ~10 us each). Not eligible: several ranks (the exchange
 // epoch is a kernel argument), Adam (the bias corrections 1 - beta^t change every step), per-kernel
-// profiling, learners with host decisions inside the iteration (REINFORCE, KL-PPO).
+// profiling, learners with host decisions inside the phase (REINFORCE, KL-PPO).
 static bool graph_eligible(const dfrl_trainer *t) {
   const dfrl_trainer_config &c = t->cfg;
   return dfrl_fused_covers_iteration(t) && t->ctx->nranks == 1 && !t->ctx->profiling &&
-         c.policy_opt != DFRL_OPT_ADAM && c.value_opt != DFRL_OPT_ADAM && c.action_mode != DFRL_ACT_FORCED;
+         c.policy_opt != DFRL_OPT_ADAM && c.value_opt != DFRL_OPT_ADAM;
+}
+
+static int learn_graphed(dfrl_trainer *t) {
+  dfrl_ctx *ctx = t->ctx;
+  if (!graph_eligible(t))
+    return learn_layered(t);
+  if (t->plain_iterations < 1) {  // the first learn runs launch by launch (shared-memory attributes)
+    ++t->plain_iterations;
+    return learn_layered(t);
+  }
+  if (!t->graph_exec) {
+    cudaGraph_t graph = nullptr;
+    const long long before = ctx->launches;
+    DFRL_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = learn_layered(t);
+    cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+    t->graph_launches = ctx->launches - before;
+    ctx->launches = before;  // nothing ran yet
+    if (rc != DFRL_OK || e != cudaSuccess || !graph) {
+      if (graph)
+        cudaGraphDestroy(graph);
+      cudaGetLastError();
+      if (rc == DFRL_OK)
+        dfrl_set_error("graph capture of the learn phase failed: %s", cudaGetErrorString(e));
+      return rc != DFRL_OK ? rc : DFRL_ERR_CUDA;
+    }
+    cudaGraphExec_t exec = nullptr;
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) {
+      dfrl_set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+      return DFRL_ERR_CUDA;
+    }
+    t->graph_exec = exec;
+  }
+  DFRL_CUDA(cudaGraphLaunch((cudaGraphExec_t)t->graph_exec, ctx->stream));
+  ctx->launches += t->graph_launches;
+  return DFRL_OK;
+}
+
+extern "C" int dfrl_trainer_learn(dfrl_trainer *t) {
+  DFRL_CHECK(t, "null trainer");
+  return learn_graphed(t);
 }
 
 extern "C" int dfrl_trainer_iterate(dfrl_trainer *t, int iters) {
   DFRL_CHECK(t, "null trainer");
   DFRL_CHECK(t->cfg.action_mode != DFRL_ACT_FORCED, "iterate() cannot teacher-force");
-  dfrl_ctx *ctx = t->ctx;
-  int it = 0;
-  if (graph_eligible(t)) {
-    // the first iteration runs launch by launch (it sets the kernels' shared-memory attributes)
-    for (; it < iters && t->plain_iterations < 1; ++it, ++t->plain_iterations)
-      DFRL_TRY(iterate_once(t));
-    if (it < iters && !t->graph_exec) {
-      cudaGraph_t graph = nullptr;
-      const long long before = ctx->launches;
-      DFRL_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-      int rc = iterate_once(t);
-      cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
-      t->graph_launches = ctx->launches - before;
-      ctx->launches = before;  // nothing ran yet
-      if (rc != DFRL_OK || e != cudaSuccess || !graph) {
-        if (graph)
-          cudaGraphDestroy(graph);
-        cudaGetLastError();
-        if (rc == DFRL_OK)
-          dfrl_set_error("graph capture of the training iteration failed: %s", cudaGetErrorString(e));
-        return rc != DFRL_OK ? rc : DFRL_ERR_CUDA;
-      }
-      cudaGraphExec_t exec = nullptr;
-      e = cudaGraphInstantiate(&exec, graph, 0);
-      cudaGraphDestroy(graph);
-      if (e != cudaSuccess) {
-        dfrl_set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
-        return DFRL_ERR_CUDA;
-      }
-      t->graph_exec = exec;
-    }
-    for (; it < iters; ++it) {
-      DFRL_CUDA(cudaGraphLaunch((cudaGraphExec_t)t->graph_exec, ctx->stream));
-      ctx->launches += t->graph_launches;
-    }
-    return DFRL_OK;
+  for (int it = 0; it < iters; ++it) {
+    int rc = t->fused_impl ? dfrl_fused_rollout(t, nullptr, nullptr, nullptr) : DFRL_ERR_UNSUPPORTED;
+    if (rc == DFRL_ERR_UNSUPPORTED)
+      rc = rollout_layered(t, nullptr, nullptr, nullptr);
+    DFRL_TRY(rc);
+    DFRL_TRY(learn_graphed(t));
   }
-  for (; it < iters; ++it)
-    DFRL_TRY(iterate_once(t));
   return DFRL_OK;
 }
 
