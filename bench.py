@@ -59,7 +59,7 @@ class ClockSampler:
                     self.rows.append([c.strip() for c in line.split(",")])
             except Exception:
                 pass
-            self.stop.wait(0.2)
+            self.stop.wait(0.05)
 
     def __enter__(self):
         self.th = threading.Thread(target=self._run, daemon=True)
@@ -132,7 +132,11 @@ def run_reference_arm(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
+    # Bounded sample: the reference's cost is flat per transition (~0.45 ms), so
+    # the envs per step are sized for about one minute of CPU work over the whole W + K run.
     n_envs = args.ref_envs
+    if n_envs <= 0:
+        n_envs = int(max(16, min(256, 60.0 * 2200.0 / (T_STEPS * (args.steps + max(1, args.warmup))))))
     # warm-up then K steps; one step = one PPO iteration on the bounded sample of n_envs envs
     cpu_reference_rate(n_envs, max(1, args.warmup), cores)
     rate, secs, kind, used = cpu_reference_rate(n_envs, args.steps, cores)
@@ -204,19 +208,20 @@ def measure(D, ctx, dist, args, n_envs, world, rank, steps, warmup, sample_clock
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t[0])
 
-    # ---- device-resident throughput: `steps` iterations, no host round trips inside
-    tr.iterate(warmup)
-    barrier()
+    # ---- device-resident throughput: `steps` iterations, no host round trips inside.
+    # The clock sampler (nvidia-smi every 50 ms) runs from the warm-up to the end of the e2e
+    # measurement: one step is ~1 ms, so the timed region alone is shorter than a sampling period
+    # unless --steps is in the hundreds.
     sampler = ClockSampler(ctx_device(ctx)) if sample_clocks else None
-    l0 = ctx.launches()
     if sampler:
         sampler.__enter__()
+    tr.iterate(warmup)
+    barrier()
+    l0 = ctx.launches()
     ctx.timer_start()
     tr.iterate(steps)
     ms = ctx.timer_stop()
     barrier()
-    if sampler:
-        sampler.__exit__()
     launches = ctx.launches() - l0
     ms = max_over_ranks(ms)
     value_rate = n_envs * world * T_STEPS * steps / (ms * 1e-3)
@@ -247,6 +252,8 @@ def measure(D, ctx, dist, args, n_envs, world, rank, steps, warmup, sample_clock
     dt = time.perf_counter() - t0
     dt = max_over_ranks(dt)
     e2e_rate = n_envs * world * T_STEPS * steps / dt
+    if sampler:
+        sampler.__exit__()
     D._lib.check(lib.dfrl_free_host(ctx.h, hp))
     res = {"value": value_rate, "ms_per_step": ms / steps, "launches_per_step": launches / steps,
            "e2e": {"value": e2e_rate, "unit": "env-steps/s", "h2d_bytes_per_step": nbytes * world,
@@ -421,9 +428,10 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        rate, secs, kind, used = cpu_reference_rate(args.ref_envs, args.ref_iters, cores)
+        ref_envs = args.ref_envs if args.ref_envs > 0 else 256
+        rate, secs, kind, used = cpu_reference_rate(ref_envs, args.ref_iters, cores)
         cpu = {"value": rate, "unit": "env-steps/s", "cores": used, "kind": kind,
-               "sample": f"{args.ref_iters} PPO iterations of {args.ref_envs} envs x {T_STEPS} steps ({secs:.1f} s), "
+               "sample": f"{args.ref_iters} PPO iterations of {ref_envs} envs x {T_STEPS} steps ({secs:.1f} s), "
                          f"same nets; rollouts on {used} threads, learner single-threaded as in the reference"}
 
     if rank == 0:
@@ -449,12 +457,13 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=400)   # ~0.4 s timed at ~1 ms per PPO iteration
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=131072)
     ap.add_argument("--fused", type=int, default=1)
-    ap.add_argument("--ref-envs", type=int, default=256, help="bounded CPU sample: envs per PPO iteration")
+    ap.add_argument("--ref-envs", type=int, default=0,
+                    help="bounded CPU sample: envs per PPO iteration (0: sized from --steps for ~1 min of CPU work)")
     ap.add_argument("--ref-iters", type=int, default=10)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-c2", action="store_true")
