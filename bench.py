@@ -176,14 +176,15 @@ C5_POLICY_DIMS = [128, 256, 256, 256, 32]   # BASELINE configs[4]: 32 bins, 3 hi
 C5_VALUE_DIMS = [128, 256, 256, 256, 1]
 
 
-def make_trainer(D, ctx, n_envs, env_offset, global_rows, seed=1234, fused=1, pdims=None, vdims=None, n_bins=8):
+def make_trainer(D, ctx, n_envs, env_offset, global_rows, seed=1234, fused=1, pdims=None, vdims=None, n_bins=8,
+                 algo=None, work=T_STEPS, last=None):
     pdims, vdims = pdims or POLICY_DIMS, vdims or VALUE_DIMS
-    policy = D.Model(ctx, D.fc_layers(pdims, D.SOFTMAX), 4 * n_bins)
+    policy = D.Model(ctx, D.fc_layers(pdims, last if last is not None else D.SOFTMAX), 4 * n_bins)
     value = D.Model(ctx, D.fc_layers(vdims), 4 * n_bins)
     policy.init_parameters(seed)       # identical on every rank (replicated parameters)
     value.init_parameters(seed + 1)
     env = D.Environment(ctx, n_envs, n_bins=n_bins, seed=seed, env_offset=env_offset)
-    tr = D.Trainer(ctx, env, policy, value, algo=D.PPO, work=T_STEPS,
+    tr = D.Trainer(ctx, env, policy, value, algo=algo if algo is not None else D.PPO, work=work,
                    policy_lr=REF_LR_P * REF_ROWS / global_rows, value_lr=REF_LR_V * REF_ROWS / global_rows,
                    fused=fused)
     return tr, env, policy, value
@@ -416,6 +417,21 @@ def run_ours(args):
             "per_kernel_ms": {k.split("(")[-1].split("<")[0].strip("() "): round(v["ms"], 3)
                               for k, v in sorted(prof5.items(), key=lambda kv: -kv[1]["ms"])[:8]}}
         for o in (tr5, env5, p5, v5):
+            o.close()
+    if world == 1 and not args.no_c2:
+        # BASELINE configs[2]: online actor-critic (one critic step, GAE, one policy step with
+        # A (p - onehot)), 65 536 envs, T = 8 (ac_training.cc:30). The reference's sequential `model`
+        # cannot express a shared trunk: separate 32-64-64 policy / value nets.
+        n3, T3 = 65536, 8
+        tr3, env3, p3, v3 = make_trainer(D, ctx, n3, 0, n3 * T3, algo=D.ACTOR_CRITIC, work=T3, last=D.SOFTMAX_CE)
+        tr3.iterate(5)
+        ctx.sync()
+        ctx.timer_start()
+        tr3.iterate(50)
+        ms3 = ctx.timer_stop() / 50
+        extra["c3_actor_critic_65536_envs"] = {"value": n3 * T3 / (ms3 * 1e-3), "unit": "env-steps/s",
+                                               "ms_per_step": ms3, "steps_per_iter": T3}
+        for o in (tr3, env3, p3, v3):
             o.close()
     if world == 1 and not args.no_c2:
         # BASELINE configs[1] verbatim: PPO, 4096 parallel envs, 1 GPU (latency-bound size)

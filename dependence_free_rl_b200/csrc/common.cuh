@@ -63,12 +63,11 @@ void dfrl_profile_mark(dfrl_ctx *ctx, const char *name, int end);
 constexpr int DFRL_P2P_MAX_RANKS = 8;
 constexpr size_t DFRL_P2P_CAP = 1 << 18;  // floats per slot (1 MB): >= the largest flat gradient
 struct dfrl_p2p {
-  float *local = nullptr;            // [2][DFRL_P2P_CAP] floats, then 2 unsigned flags
+  float *local = nullptr;            // [2][DFRL_P2P_CAP] floats, 2 slot flags, the exchange counter
   float *peer[DFRL_P2P_MAX_RANKS];   // peer[r]: rank r's allocation mapped here (own rank: local)
-  unsigned epoch = 0;                // exchanges issued so far (identical on every rank)
   bool attached = false;
 };
-static inline unsigned *dfrl_p2p_flags(float *base) { return reinterpret_cast<unsigned *>(base + 2 * DFRL_P2P_CAP); }
+__host__ __device__ static inline unsigned *dfrl_p2p_flags(float *base) { return reinterpret_cast<unsigned *>(base + 2 * DFRL_P2P_CAP); }
 
 struct dfrl_ctx {
   int device = 0;

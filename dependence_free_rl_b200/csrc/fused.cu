@@ -1272,8 +1272,11 @@ __global__ void __launch_bounds__(128 * NWG, 1) fused_policy_step_kernel(policy_
 struct reduce_tail {
   dfrl_opt_spec opt;   // params == null: no update
   unsigned *ticket;    // multi-rank publish: zero before the launch, zero again after it
-  unsigned *publish;   // multi-rank: flag of the exchange slot `grad` points into, set to
-  unsigned epoch;      //   `epoch` by the last block once the whole gradient is visible system-wide
+  // multi-rank publish: exchange buffer of this rank ([2 slots][DFRL_P2P_CAP] floats, 2 flags, the
+  // exchange counter). The counter lives on the device so that the launch arguments are constant
+  // (CUDA-graph capturable): exchange e = counter + 1 uses slot e & 1; the last block sets the
+  // slot's flag to e once the whole gradient is visible system-wide, then bumps the counter.
+  float *exchange;
 };
 __global__ void __launch_bounds__(256) fused_reduce_partials_kernel(const float *__restrict__ part, int ctas,
                                                                     int n, float *__restrict__ grad,
@@ -1281,6 +1284,11 @@ __global__ void __launch_bounds__(256) fused_reduce_partials_kernel(const float 
   __shared__ float sm[8][33];
   __shared__ int is_last;
   const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  unsigned epoch = 0;
+  if (tail.exchange) {  // every block reads the counter before its ticket; the last block bumps it
+    epoch = *reinterpret_cast<volatile unsigned *>(dfrl_p2p_flags(tail.exchange) + 2) + 1;
+    grad = tail.exchange + (size_t)(epoch & 1u) * DFRL_P2P_CAP;
+  }
   const int i = blockIdx.x * 32 + lane;
   float s = 0.f;
   if (i < n)
@@ -1298,7 +1306,7 @@ __global__ void __launch_bounds__(256) fused_reduce_partials_kernel(const float 
     if (opt.params)
       opt_update(opt.kind, opt.params, grad, opt.state, n, i, opt.lr, opt.wd, opt.beta1, opt.beta2, opt.c1, opt.c2);
   }
-  if (!tail.publish)
+  if (!tail.exchange)
     return;
   __threadfence_system();  // this block's writes to the exchange slot before its ticket
   __syncthreads();
@@ -1312,8 +1320,11 @@ __global__ void __launch_bounds__(256) fused_reduce_partials_kernel(const float 
   if (!is_last)
     return;
   __threadfence_system();
-  if (threadIdx.x == 0)
-    *reinterpret_cast<volatile unsigned *>(tail.publish) = tail.epoch;
+  if (threadIdx.x == 0) {
+    volatile unsigned *flags = reinterpret_cast<volatile unsigned *>(dfrl_p2p_flags(tail.exchange));
+    flags[epoch & 1u] = epoch;
+    flags[2] = epoch;
+  }
 }
 
 // K8 + K7 over NVLink peer memory: pull every rank's published gradient, sum in rank order
@@ -1322,16 +1333,18 @@ __global__ void __launch_bounds__(256) fused_reduce_partials_kernel(const float 
 // GPU, and a peer's producer kernel never depends on this rank.
 struct p2p_view {
   const float *peer[DFRL_P2P_MAX_RANKS];
-  int nranks, slot;
-  unsigned epoch;
+  const float *local;  // this rank's buffer: its exchange counter names the exchange to complete
+  int nranks;
 };
 __global__ void __launch_bounds__(256) fused_p2p_sum_opt_kernel(p2p_view v, int n, float *__restrict__ grad,
                                                                 reduce_tail tail) {
+  const unsigned epoch = *reinterpret_cast<const volatile unsigned *>(v.local + 2 * DFRL_P2P_CAP + 2);
+  const int slot = (int)(epoch & 1u);
   if ((int)threadIdx.x < v.nranks) {
     const volatile unsigned *flag =
-        reinterpret_cast<const volatile unsigned *>(v.peer[threadIdx.x] + 2 * DFRL_P2P_CAP) + v.slot;
+        reinterpret_cast<const volatile unsigned *>(v.peer[threadIdx.x] + 2 * DFRL_P2P_CAP) + slot;
     unsigned spins = 0;
-    while (*flag < v.epoch)
+    while (*flag < epoch)
       if (++spins > (1u << 28))
         __trap();  // a peer never published: report a launch failure instead of hanging the GPU
     __threadfence_system();
@@ -1341,7 +1354,7 @@ __global__ void __launch_bounds__(256) fused_p2p_sum_opt_kernel(p2p_view v, int 
   if (i < n) {
     float s = 0.f;
     for (int r = 0; r < v.nranks; ++r)
-      s += *reinterpret_cast<const volatile float *>(v.peer[r] + (size_t)v.slot * DFRL_P2P_CAP + i);
+      s += *reinterpret_cast<const volatile float *>(v.peer[r] + (size_t)slot * DFRL_P2P_CAP + i);
     grad[i] = s;
     const dfrl_opt_spec &opt = tail.opt;
     if (opt.params)
@@ -1672,15 +1685,10 @@ int launch_reduce(dfrl_trainer *t, fused_state *f, dfrl_mlp *m, const net3 &net,
   reduce_tail tail;
   memset(&tail, 0, sizeof(tail));
   float *dst = grad_dev;
-  int slot = 0;
   if (exchange) {
     DFRL_CHECK((size_t)net.n_params <= DFRL_P2P_CAP, "flat gradient exceeds the exchange slot");
-    ctx->p2p.epoch += 1;
-    slot = (int)(ctx->p2p.epoch & 1u);
-    dst = ctx->p2p.local + (size_t)slot * DFRL_P2P_CAP;
     tail.ticket = f->ticket;
-    tail.publish = dfrl_p2p_flags(ctx->p2p.local) + slot;
-    tail.epoch = ctx->p2p.epoch;
+    tail.exchange = ctx->p2p.local;
   } else if (opt) {
     tail.opt = *opt;
   }
@@ -1692,8 +1700,7 @@ int launch_reduce(dfrl_trainer *t, fused_state *f, dfrl_mlp *m, const net3 &net,
     for (int r = 0; r < ctx->nranks; ++r)
       v.peer[r] = ctx->p2p.peer[r];
     v.nranks = ctx->nranks;
-    v.slot = slot;
-    v.epoch = ctx->p2p.epoch;
+    v.local = ctx->p2p.local;
     reduce_tail t2;
     memset(&t2, 0, sizeof(t2));
     t2.opt = *opt;

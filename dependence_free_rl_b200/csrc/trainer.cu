@@ -593,12 +593,13 @@ static int learn_layered(dfrl_trainer *t) {
 // The learn phase of the fully fused path is a fixed sequence of kernel launches with constant
 // arguments (no host round trip, no memset / memcpy): it is captured once as a CUDA graph and
 // replayed, which removes the per-launch CPU and scheduling gaps that dominate at small
-// environment counts (C2: 11 launches of ~10 us each). Not eligible: several ranks (the exchange
-// epoch is a kernel argument), Adam (the bias corrections 1 - beta^t change every step), per-kernel
-// profiling, learners with host decisions inside the phase (REINFORCE, KL-PPO).
+// environment counts (C2: 11 launches of ~10 us each). Several ranks qualify when the gradient
+// exchange runs over attached peer memory (its exchange counter lives on the device). Not eligible:
+// NCCL exchanges, Adam (the bias corrections 1 - beta^t change every step), per-kernel profiling,
+// learners with host decisions inside the phase (REINFORCE, KL-PPO).
 static bool graph_eligible(const dfrl_trainer *t) {
   const dfrl_trainer_config &c = t->cfg;
-  return dfrl_fused_covers_iteration(t) && t->ctx->nranks == 1 && !t->ctx->profiling &&
+  return dfrl_fused_covers_iteration(t) && (t->ctx->nranks == 1 || t->ctx->p2p.attached) && !t->ctx->profiling &&
          c.policy_opt != DFRL_OPT_ADAM && c.value_opt != DFRL_OPT_ADAM;
 }
 
