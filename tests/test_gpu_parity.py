@@ -548,3 +548,119 @@ def test_free_running_ppo_is_bitwise_reproducible(D, ctx):
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
     assert a[3]["reward_sum"] == b[3]["reward_sum"] and a[3]["episodes"] == b[3]["episodes"]
     assert np.all(np.isfinite(a[0])) and np.all(np.isfinite(a[1]))
+
+
+def _safe_params(dims, seed, bias=5.0):
+    """Hidden biases of +-bias with small weights: every pre-activation is far from zero (half of
+    the units always on, half always off), so relu masks cannot flip under rounding differences."""
+    r = np.random.default_rng(seed)
+    parts = []
+    for li, (a, b) in enumerate(zip(dims[:-1], dims[1:])):
+        parts.append((r.standard_normal(a * b) * 0.05).astype(np.float32))
+        bvec = (r.standard_normal(b) * 0.05).astype(np.float32)
+        if li < len(dims) - 2:
+            bvec += np.where(np.arange(b) % 2 == 0, bias, -bias).astype(np.float32)
+        parts.append(bvec)
+    return np.concatenate(parts)
+
+
+@pytest.mark.parametrize("algo_name,n,T,B,pdims,vdims", [
+    # 32 bins (O = 128): layered path; 1200 x 4 = 4800 learner rows put the 64-wide products on
+    # the tcgen05 GEMMs of gemm_umma.cu, the rest on the FFMA kernels
+    ("ppo", 1200, 4, 32, [128, 64, 64, 32], [128, 64, 64, 1]),
+    # online actor-critic on the fused kernels (softmax-CE head: identity backward), T = 8
+    ("ac", 300, 8, 8, [32, 64, 64, 8], [32, 64, 64, 1]),
+])
+def test_trainer_variants_vs_oracle(D, ctx, orc, algo_name, n, T, B, pdims, vdims):
+    algo, oalgo = (D.PPO, orc.PPO) if algo_name == "ppo" else (D.ACTOR_CRITIC, orc.ACTOR_CRITIC)
+    last = D.SOFTMAX if algo_name == "ppo" else D.SOFTMAX_CE
+    rng = np.random.default_rng(5)
+    pl, vl = D.fc_layers(pdims, last), D.fc_layers(vdims)
+    pnet, vnet = orc.Net(pl, 4 * B), orc.Net(vl, 4 * B)
+    pp, vp = _safe_params(pdims, 11), _safe_params(vdims, 12)
+    policy, value = D.Model(ctx, pl, 4 * B), D.Model(ctx, vl, 4 * B)
+    policy.set_parameters(pp)
+    value.set_parameters(vp)
+    ecfg = orc.env_cfg(B)
+    st = orc.env_reset_all(ecfg, n, rng.integers(0, 2, n).astype(np.uint8))
+    env = D.Environment(ctx, n, n_bins=B)
+    env.set_state(st)
+    tr = D.Trainer(ctx, env, policy, value, algo=algo, work=T, policy_lr=2e-8, value_lr=2e-8,
+                   action_mode=D.ACT_SAMPLE)
+    lr = orc.Learner(orc.train_cfg(oalgo, T, policy_lr=2e-8, value_lr=2e-8), ecfg, pnet, pp, vnet, vp)
+    for it in range(3):
+        items = rng.integers(0, 2, (T, n)).astype(np.uint8)
+        u = rng.random((T, n))
+        ro = orc.rollout(ecfg, st, pnet, lr.pparams, T, 0, items, u=u)
+        tr.rollout(items=items, u=u)
+        assert np.array_equal(tr.read(D.F_REC_ACTION), ro["action"])
+        assert np.array_equal(tr.read(D.F_REC_DONE), ro["done"])
+        assert np.array_equal(env.state(), st)
+        close(tr.read(D.F_REC_PROBS), ro["probs"], what="p_old")
+        out = lr.learn(ro["state"], st, ro["action"], ro["done"], ro["probs"])
+        tr.learn()
+        close(tr.read(D.F_ADVANTAGE), out["adv"], what="adv")
+        close(tr.read(D.F_VALUE_GRAD), out["value_grad"], what="vgrad")
+        close(tr.read(D.F_POLICY_GRAD_LOG), out["policy_grads"], what="pgrads")
+        close(policy.parameters(), lr.pparams, what="pparams")
+        close(value.parameters(), lr.vparams, what="vparams")
+    tr.close(); env.close(); policy.close(); value.close()
+
+
+def test_abi_error_paths(D, ctx):
+    """Status codes + dfrl_last_error(), the convention the C++ mirror rethrows as xeno::error
+    (reference: shape checks throwing xeno::error, tensor.cc:41-69)."""
+    import ctypes as C
+    lib = D._lib.lib
+    h = C.c_void_p()
+    # model whose widths do not chain
+    kinds = (C.c_int * 2)(D.DENSE, D.DENSE)
+    ins, outs = (C.c_int * 2)(32, 48), (C.c_int * 2)(64, 8)
+    rc = lib.dfrl_mlp_create(ctx.h, 2, kinds, ins, outs, 32, C.byref(h))
+    assert rc == -1 and lib.dfrl_last_error()
+    # environment id / action out of range (per-id triple)
+    env = D.Environment(ctx, 4)
+    assert lib.dfrl_env_apply_one(env.h, 7, 0) == -1 and b"out of range" in lib.dfrl_last_error()
+    assert lib.dfrl_env_apply_one(env.h, 0, 9) == -1
+    # trainer: policy output width != bins
+    bad = D.Model(ctx, D.fc_layers([32, 16, 4], D.SOFTMAX), 32)
+    val = D.Model(ctx, D.fc_layers([32, 16, 1]), 32)
+    with pytest.raises(D._lib.DfrlError, match="action.cardinality"):
+        D.Trainer(ctx, env, bad, val, algo=D.PPO, work=4)
+    # forced mode without an action tape, learn before rollout is allowed to run on empty records
+    good = D.Model(ctx, D.fc_layers([32, 16, 8], D.SOFTMAX), 32)
+    tr = D.Trainer(ctx, env, good, val, algo=D.PPO, work=4, action_mode=D.ACT_FORCED)
+    with pytest.raises(D._lib.DfrlError, match="action tape"):
+        tr.rollout()
+    with pytest.raises(D._lib.DfrlError, match="teacher-force"):
+        tr.iterate(1)
+    tr.close(); env.close(); bad.close(); val.close(); good.close()
+
+
+def test_single_environment_trainer(D, ctx, orc):
+    # N = 1 (BASELINE configs[0] shape): one environment, every kernel with a single row tile
+    pl, vl = D.fc_layers([32, 64, 64, 8], D.SOFTMAX), D.fc_layers([32, 64, 64, 1])
+    pnet, vnet = orc.Net(pl, 32), orc.Net(vl, 32)
+    pp, vp = _safe_params([32, 64, 64, 8], 1), _safe_params([32, 64, 64, 1], 2)
+    policy, value = D.Model(ctx, pl, 32), D.Model(ctx, vl, 32)
+    policy.set_parameters(pp)
+    value.set_parameters(vp)
+    ecfg = orc.env_cfg(8)
+    st = orc.env_reset_all(ecfg, 1, np.array([1], np.uint8))
+    env = D.Environment(ctx, 1)
+    env.set_state(st)
+    tr = D.Trainer(ctx, env, policy, value, algo=D.PPO, work=4, policy_lr=1e-7, value_lr=1e-7)
+    lr = orc.Learner(orc.train_cfg(orc.PPO, 4, policy_lr=1e-7, value_lr=1e-7), ecfg, pnet, pp, vnet, vp)
+    rng = np.random.default_rng(9)
+    for it in range(6):
+        items = rng.integers(0, 2, (4, 1)).astype(np.uint8)
+        u = rng.random((4, 1))
+        ro = orc.rollout(ecfg, st, pnet, lr.pparams, 4, 0, items, u=u)
+        tr.rollout(items=items, u=u)
+        assert np.array_equal(tr.read(D.F_REC_ACTION), ro["action"])
+        assert np.array_equal(env.state(), st)
+        out = lr.learn(ro["state"], st, ro["action"], ro["done"], ro["probs"])
+        tr.learn()
+        close(tr.read(D.F_POLICY_GRAD_LOG), out["policy_grads"], what="pgrads")
+        close(value.parameters(), lr.vparams, what="vparams")
+    tr.close(); env.close(); policy.close(); value.close()
