@@ -150,6 +150,68 @@ umma_selftest_kernel(int variant, const float *__restrict__ A, int a_rows, int a
     umma::tmem_dealloc(tmem, 128);
 }
 
+// M = 64 accumulator + tcgen05.ld.16x256b: D[64 x N] = X[64 x K] . W[N x K]^T (both K-major).
+// Assumed layouts (what this test pins): D row r lives in TMEM lane 32 (r / 16) + r % 16; a
+// 16x256b.x1 load by warp w returns to thread t the 2 x 2 block rows {t / 4, t / 4 + 8} x columns
+// {2 (t % 4), 2 (t % 4) + 1} of the 16 lanes x 8 columns it addresses.
+__global__ void __launch_bounds__(128)
+umma_m64_selftest_kernel(const float *__restrict__ A, int k, const float *__restrict__ Bm, int n, float *__restrict__ D) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
+  const uint32_t PANEL = 128 * 128;
+  uint8_t *a_hi = smem, *a_lo = smem + 2 * PANEL, *b_hi = smem + 4 * PANEL, *b_lo = smem + 6 * PANEL;
+  __shared__ uint64_t mbar;
+  __shared__ uint32_t tmem_base_slot;
+  const int warp = threadIdx.x / 32, t = threadIdx.x & 31;
+  if (warp == 0)
+    umma::tmem_alloc(&tmem_base_slot, 128);
+  if (threadIdx.x == 0) {
+    umma::mbar_init(&mbar, 1);
+    umma::fence_mbar_init();
+  }
+  stage_panels(A, 64, k, a_hi, a_lo, 128);
+  stage_panels(Bm, n, k, b_hi, b_lo, 128);
+  umma::fence_proxy_async();
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem = tmem_base_slot;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = umma::make_idesc_bf16(64, n, 0, 0);
+    uint32_t acc = 0;
+    for (int ks = 0; ks < k / 16; ++ks) {
+      uint32_t off = (ks / 4) * PANEL + (ks % 4) * umma::KSTEP_BYTES_KMAJOR;
+      uint64_t ah = umma::make_desc_sw128(umma::smem_u32(a_hi) + off, 16, 1024);
+      uint64_t al = umma::make_desc_sw128(umma::smem_u32(a_lo) + off, 16, 1024);
+      uint64_t bh = umma::make_desc_sw128(umma::smem_u32(b_hi) + off, 16, 1024);
+      uint64_t bl = umma::make_desc_sw128(umma::smem_u32(b_lo) + off, 16, 1024);
+      umma::mma_bf16(tmem, ah, bh, idesc, acc);
+      acc = 1;
+      umma::mma_bf16(tmem, ah, bl, idesc, 1);
+      umma::mma_bf16(tmem, al, bh, idesc, 1);
+    }
+    umma::commit(&mbar);
+  }
+  umma::mbar_wait(&mbar, 0);
+  umma::fence_after_sync();
+  for (int c0 = 0; c0 < n; c0 += 8) {
+    uint32_t r[4];
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0, %1, %2, %3}, [%4];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(tmem + ((uint32_t)(warp * 32) << 16) + c0) : "memory");
+    umma::tmem_ld_wait();
+    const int row = warp * 16 + t / 4, col = c0 + 2 * (t % 4);
+    D[(size_t)row * n + col] = __uint_as_float(r[0]);
+    D[(size_t)row * n + col + 1] = __uint_as_float(r[1]);
+    D[(size_t)(row + 8) * n + col] = __uint_as_float(r[2]);
+    D[(size_t)(row + 8) * n + col + 1] = __uint_as_float(r[3]);
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0)
+    umma::tmem_dealloc(tmem, 128);
+}
+
 float lcg(uint32_t &s) {
   s = s * 1664525u + 1013904223u;
   return ((s >> 8) & 0xffff) / 32768.0f - 1.0f;
@@ -161,6 +223,37 @@ float lcg(uint32_t &s) {
 // columns (multiple of 16, <= 64). Returns max |D - ref| / max |ref| through *rel_err.
 extern "C" int dfrl_umma_selftest(dfrl_ctx *ctx, int variant, int k, int n, float *rel_err) {
   DFRL_CHECK(ctx && rel_err, "null argument");
+  if (variant == 5) {  // M = 64 accumulator read with 16x256b loads
+    DFRL_CHECK(k % 16 == 0 && k >= 16 && k <= 128 && n % 16 == 0 && n >= 16 && n <= 64, "bad k / n");
+    std::vector<float> A((size_t)64 * k), B((size_t)n * k), D((size_t)64 * n);
+    uint32_t s = 999u + k * 3 + n;
+    for (float &x : A) x = lcg(s) * 1.7f;
+    for (float &x : B) x = lcg(s) * 0.9f;
+    float *dA, *dB, *dD;
+    DFRL_CUDA(cudaMalloc(&dA, A.size() * 4));
+    DFRL_CUDA(cudaMalloc(&dB, B.size() * 4));
+    DFRL_CUDA(cudaMalloc(&dD, D.size() * 4));
+    DFRL_CUDA(cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice));
+    DFRL_CUDA(cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice));
+    DFRL_CUDA(cudaMemset(dD, 0, D.size() * 4));
+    const int smem = 8 * 128 * 128 + 1024;
+    DFRL_CUDA(cudaFuncSetAttribute(umma_m64_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    DFRL_LAUNCH(ctx, umma_m64_selftest_kernel, 1, 128, smem, dA, k, dB, n, dD);
+    DFRL_CUDA(cudaStreamSynchronize(ctx->stream));
+    DFRL_CUDA(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
+    cudaFree(dA); cudaFree(dB); cudaFree(dD);
+    double max_ref = 0, max_err = 0;
+    for (int i = 0; i < 64; ++i)
+      for (int j = 0; j < n; ++j) {
+        double ref = 0;
+        for (int q = 0; q < k; ++q) ref += (double)A[(size_t)i * k + q] * B[(size_t)j * k + q];
+        double err = fabs(ref - (double)D[(size_t)i * n + j]);
+        if (fabs(ref) > max_ref) max_ref = fabs(ref);
+        if (err > max_err) max_err = err;
+      }
+    *rel_err = (float)(max_err / (max_ref + 1e-30));
+    return DFRL_OK;
+  }
   DFRL_CHECK(variant >= 0 && variant <= 4, "variant 0..4");
   DFRL_CHECK(k % 16 == 0 && k >= 16 && k <= 128 && n % 16 == 0 && n >= 16 && n <= 64, "bad k / n");
   DFRL_CHECK((variant != 2 && variant != 3) || k == 128, "variants 2, 3 contract over the 128 tile rows");
