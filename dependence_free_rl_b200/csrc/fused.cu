@@ -28,7 +28,6 @@
 // Jacobian), nn.h:85-100 (dW = SUM over rows), policy_gradient.h:196-281 (targets, GAE).
 #include <cuda_fp16.h>
 #include <math.h>
-#include <stdlib.h>
 #include <string.h>
 
 #include "device_fns.cuh"
@@ -1546,416 +1545,6 @@ __global__ void __launch_bounds__(256, 2) fused_rollout_kernel(rollout_args a) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// 64-row-tile variant of the policy step: TWO CTAs per SM, so that one CTA's epilogues (ALU / TMEM
-// bound) run under the other's MMA phases (shared-memory-port bound) -- the overlap the serial
-// forward -> loss -> backward chain of a single tile cannot have. Halving the tile halves the
-// activation set (64 KB) so that two CTAs fit in shared memory; every GEMM becomes an M = 64
-// tcgen05.mma (accumulator row r in TMEM lane 32 (r / 16) + r % 16) and the epilogues read the
-// accumulators with tcgen05.ld.16x256b: warp w = (quarter q = w % 4, column half w / 4), thread t
-// holds rows {16 q + t / 4, + 8} x columns {c, c + 1}, c = 8 g + 2 (t % 4), of each 8-column group g.
-template <int D1, int D2>
-struct smem_map64 {
-  using IM = image_map<D1, D2>;
-  static constexpr uint32_t P64 = 64 * 128;                         // bytes of a 64-row panel
-  static constexpr uint32_t X0 = (IM::BYTES + 1023) / 1024 * 1024;  // hi only
-  static constexpr uint32_t H1_HI = X0 + P64, H1_LO = H1_HI + P64;
-  static constexpr uint32_t H2_HI = H1_LO + P64, H2_LO = H2_HI + P64;     // dH1 overwrites H2
-  static constexpr uint32_t DH2_HI = H2_LO + P64, DH2_LO = DH2_HI + P64;  // = H2 + 2 panels: [dH1|dH2] stacks
-  static constexpr uint32_t DY = DH2_LO + P64;                      // packed: hi cols 0..15, lo 16..31
-  static constexpr uint32_t SCRATCH = DY + P64;                     // 64 rows x 8 floats
-  static constexpr uint32_t RAW = SCRATCH + 64 * 8 * 4;             // int8 [18][64]
-  static constexpr uint32_t BARS = RAW + 18 * 64 + 64;
-  static constexpr uint32_t TOTAL = BARS + 64;
-  static_assert(2 * (TOTAL + 1024 + 1024) <= 232448, "two CTAs per SM");
-};
-constexpr uint32_t T64_ACC = 0, T64_L3 = 64, T64_DA = 128, T64_DB = 192, T64_DC = 240, T64_COLS = 256;
-
-__device__ __forceinline__ void tmem_ld_frag(uint32_t taddr, float *v) {  // one 8-column group: 4 values
-  uint32_t r[4];
-  asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0, %1, %2, %3}, [%4];\n"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-    v[i] = __uint_as_float(r[i]);
-}
-struct tid64 {
-  int warp, q, ch, t, row_a;  // row_a = 16 q + t / 4 (the thread's first row; the second is + 8)
-  uint32_t lane_base;
-};
-__device__ __forceinline__ tid64 thread_id64() {
-  tid64 x;
-  x.warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
-  x.q = x.warp & 3;
-  x.ch = x.warp >> 2;
-  x.t = threadIdx.x & 31;
-  x.row_a = 16 * x.q + (x.t >> 2);
-  x.lane_base = (uint32_t)(x.q * 32) << 16;
-  return x;
-}
-// forward epilogue: y = acc * c + bias, relu -> hi / lo panels. D/2 columns per warp, D/16 groups.
-// Returns the relu mask: bit 4 g + {0, 1, 2, 3} = (row a, c), (row a, c + 1), (row b, c), (row b, c + 1).
-template <int D>
-__device__ __forceinline__ uint32_t epi64_fwd(uint32_t acc, const tid64 &x, float c, const float *__restrict__ bias,
-                                              uint8_t *hi, uint8_t *lo) {
-  constexpr int G = D / 16;  // 8-column groups per warp
-  const int col0 = x.ch * (D / 2);
-  float v[G][4];
-#pragma unroll
-  for (int g = 0; g < G; ++g)
-    tmem_ld_frag(acc + x.lane_base + col0 + 8 * g, v[g]);
-  umma::tmem_ld_wait();
-  uint32_t mask = 0;
-#pragma unroll
-  for (int g = 0; g < G; ++g) {
-    const int cc = col0 + 8 * g + 2 * (x.t & 3);
-    const float2 b = *reinterpret_cast<const float2 *>(bias + cc);
-    float y[4] = {fmaf(v[g][0], c, b.x), fmaf(v[g][1], c, b.y), fmaf(v[g][2], c, b.x), fmaf(v[g][3], c, b.y)};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      if (y[i] > 0.f)
-        mask |= 1u << (4 * g + i);
-      else
-        y[i] = 0.f;
-    }
-    uint32_t h0, l0, h1, l1;
-    umma::split2(y[0], y[1], h0, l0);
-    umma::split2(y[2], y[3], h1, l1);
-    const uint32_t oa = umma::panel_off(x.row_a, cc), ob = umma::panel_off(x.row_a + 8, cc);
-    *reinterpret_cast<uint32_t *>(hi + oa) = h0;
-    *reinterpret_cast<uint32_t *>(lo + oa) = l0;
-    *reinterpret_cast<uint32_t *>(hi + ob) = h1;
-    *reinterpret_cast<uint32_t *>(lo + ob) = l1;
-  }
-  return mask;
-}
-template <int D>
-__device__ __forceinline__ void epi64_bwd(uint32_t acc, const tid64 &x, float c, uint32_t mask, uint8_t *hi,
-                                          uint8_t *lo) {
-  constexpr int G = D / 16;
-  const int col0 = x.ch * (D / 2);
-  float v[G][4];
-#pragma unroll
-  for (int g = 0; g < G; ++g)
-    tmem_ld_frag(acc + x.lane_base + col0 + 8 * g, v[g]);
-  umma::tmem_ld_wait();
-#pragma unroll
-  for (int g = 0; g < G; ++g) {
-    const int cc = col0 + 8 * g + 2 * (x.t & 3);
-    float y[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-      y[i] = (mask >> (4 * g + i)) & 1u ? v[g][i] * c : 0.f;
-    uint32_t h0, l0, h1, l1;
-    umma::split2(y[0], y[1], h0, l0);
-    umma::split2(y[2], y[3], h1, l1);
-    const uint32_t oa = umma::panel_off(x.row_a, cc), ob = umma::panel_off(x.row_a + 8, cc);
-    *reinterpret_cast<uint32_t *>(hi + oa) = h0;
-    *reinterpret_cast<uint32_t *>(lo + oa) = l0;
-    *reinterpret_cast<uint32_t *>(hi + ob) = h1;
-    *reinterpret_cast<uint32_t *>(lo + ob) = l1;
-  }
-}
-// M = 64 instruction descriptors (same operand conventions as ID<N>)
-template <int N> struct ID64 {
-  static constexpr uint32_t FK_FK = make_idesc(64, N, 1, 1, 0, 0);
-  static constexpr uint32_t BK_FM = make_idesc(64, N, 1, 1, 0, 1);
-  static constexpr uint32_t BM_FM = make_idesc(64, N, 1, 1, 1, 1);
-};
-// MN-major GEMMs over a 64-row tile: 4 k-steps of 16 rows.
-template <bool A_LO, bool B_LO>
-__device__ __forceinline__ void issue_dw64(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t a_lbo,
-                                           uint32_t b_hi, uint32_t b_lo, uint32_t idesc, bool accumulate) {
-  const uint32_t ah0 = desc_lo(a_hi, a_lbo), al0 = desc_lo(a_lo, a_lbo);
-  const uint32_t bh0 = desc_lo(b_hi, 16), bl0 = desc_lo(b_lo, 16);
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const uint32_t st = k * (umma::KSTEP_BYTES_MNMAJOR >> 4);
-    uint64_t ah = desc_lo_hi(ah0 + st), bh = desc_lo_hi(bh0 + st);
-    umma::mma_bf16(tmem_d, ah, bh, idesc, (k > 0 || accumulate) ? 1u : 0u);
-    if (B_LO)
-      umma::mma_bf16(tmem_d, ah, desc_lo_hi(bl0 + st), idesc, 1);
-    if (A_LO)
-      umma::mma_bf16(tmem_d, desc_lo_hi(al0 + st), bh, idesc, 1);
-  }
-}
-
-template <int D0, int D1, int D2, int NOUT>
-__global__ void __launch_bounds__(256, 2) fused_policy_step64_kernel(policy_step_args a) {
-  using SM = smem_map64<D1, D2>;
-  using IM = image_map<D1, D2>;
-  constexpr int R = 64;  // rows per tile
-  static_assert(NOUT == 8 && !FWD_F16, "8 actions, bf16 operands");
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t *smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
-  const uint32_t sbase = umma::smem_u32(smem);
-  const float *fl = reinterpret_cast<const float *>(smem + IM::FLOATS);
-  const float *b3 = fl + IM::F_B3, *kk = fl + IM::F_K;
-  float *red = reinterpret_cast<float *>(smem + SM::SCRATCH);
-  int8_t *raw = reinterpret_cast<int8_t *>(smem + SM::RAW);
-  uint64_t *bar = reinterpret_cast<uint64_t *>(smem + SM::BARS);
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + SM::BARS + 16);
-  const net3 net = a.net;
-  const learner_rows L = a.rows;  // L.E = 64 / T environments per tile
-  const tid64 x = thread_id64();
-
-  if (x.warp == 0)
-    umma::tmem_alloc(tmem_slot, T64_COLS);
-  if (threadIdx.x == 0) {
-    umma::mbar_init(bar, 1);
-    umma::fence_mbar_init();
-  }
-  build_image<D0, D1, D2>(a.params, net, smem);
-  zero_bytes(smem + SM::X0, SM::SCRATCH - SM::X0);
-  __syncthreads();
-  if (threadIdx.x < R)  // ones column (col D0) of X0: [dH1|dH2]^T . 1 = bias gradients
-    *reinterpret_cast<uint16_t *>(smem + SM::X0 + umma::panel_off(threadIdx.x, D0)) = ONE_FWD;
-  sync_after_smem_writes();
-  const uint32_t tmem = *tmem_slot;
-  uint32_t phase = 0;
-  auto wait_mma = [&]() {
-    umma::mbar_wait(bar, phase);
-    phase ^= 1;
-    umma::fence_after_sync();
-  };
-  auto mma_lane = [&]() { return x.warp == 0 && umma::elect_one(); };
-
-  // staging: 18 planes x 64 rows = 72 units of 16 bytes (E % 16 == 0, checked by the host)
-  const int P = 2 * NOUT + 2, upr = L.E / 16, units = L.T * P * upr;
-  int u_raw = -1, u_env = 0;
-  size_t u_g = 0;
-  if ((int)threadIdx.x < units) {
-    int u = threadIdx.x, h = u % upr, plane = (u / upr) % P, tt = u / (upr * P);
-    u_raw = plane * R + tt * L.E + 16 * h;
-    u_g = ((size_t)tt * P + plane) * L.stride + 16 * h;
-    u_env = 16 * h;
-  }
-  auto load_unit = [&](int tile) {
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (u_raw >= 0 && tile * L.E + u_env < L.stride)
-      v = *reinterpret_cast<const uint4 *>(L.rec_state + u_g + (size_t)tile * L.E);
-    return v;
-  };
-  auto encode = [&]() {  // thread = (row, chunk): 64 rows x 4 chunks
-    const int row = threadIdx.x & 63, ch = threadIdx.x >> 6;
-    const uint32_t it = pack2_fwd((float)raw[(2 * NOUT) * R + row] * L.inv_w, (float)raw[(2 * NOUT + 1) * R + row] * L.inv_h);
-    const uint32_t o0 = pack2_fwd((float)raw[(4 * ch) * R + row] * L.inv_w, (float)raw[(4 * ch + 1) * R + row] * L.inv_h);
-    const uint32_t o1 = pack2_fwd((float)raw[(4 * ch + 2) * R + row] * L.inv_w, (float)raw[(4 * ch + 3) * R + row] * L.inv_h);
-    *reinterpret_cast<uint4 *>(smem + SM::X0 + umma::panel_chunk_off(row, ch)) = make_uint4(o0, it, o1, it);
-  };
-
-  bool first_tile = true, dw_pending = false;
-  float db3[4] = {0.f, 0.f, 0.f, 0.f};  // (row a, c), (row a, c+1), (row b, c), (row b, c+1) partial sums
-  uint4 unit = make_uint4(0, 0, 0, 0);
-  if ((int)blockIdx.x < a.n_tiles)
-    unit = load_unit(blockIdx.x);
-
-  for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-    if (u_raw >= 0)
-      *reinterpret_cast<uint4 *>(raw + u_raw) = unit;
-    if (dw_pending) {  // the previous tile's dW1 GEMM still reads X0
-      wait_mma();
-      dw_pending = false;
-    }
-    __syncthreads();
-    encode();
-    sync_after_smem_writes();
-    // ---- layer 1, then the loads that are consumed later
-    if (mma_lane()) {
-      issue_gemm<D0 / 16, false, false, false, true>(tmem + T64_ACC, sbase + SM::X0, 0, sbase + IM::W1_HI,
-                                                     sbase + IM::W1_LO, ID64<D1>::FK_FK, false);
-      umma::commit(bar);
-    }
-    // head data of this thread's two rows (warps with ch == 0 run the head)
-    int act[2] = {0, 0};
-    float adv[2] = {0.f, 0.f};
-    float2 pold[2] = {make_float2(1.f, 1.f), make_float2(1.f, 1.f)};
-    bool valid[2] = {false, false};
-    if (x.ch == 0) {
-#pragma unroll
-      for (int rr = 0; rr < 2; ++rr) {
-        const int r = x.row_a + 8 * rr, tt = r / L.E, e = r % L.E, i = tile * L.E + e;
-        valid[rr] = tt < L.T && i < L.n;
-        if (valid[rr]) {
-          const size_t k = (size_t)tt * L.n + i;
-          act[rr] = L.rec_action[k];
-          adv[rr] = a.adv[k];
-          pold[rr] = *reinterpret_cast<const float2 *>(a.p_old + k * NOUT + 2 * (x.t & 3));
-        }
-      }
-    }
-    const int next = tile + gridDim.x;
-    if (next < a.n_tiles)
-      unit = load_unit(next);
-    wait_mma();
-    const uint32_t mask1 = epi64_fwd<D1>(tmem + T64_ACC, x, kk[K_C1], fl + IM::F_B1, smem + SM::H1_HI, smem + SM::H1_LO);
-    sync_after_smem_writes();
-    if (mma_lane()) {
-      issue_gemm<D1 / 16, false, false, true, true>(tmem + T64_ACC, sbase + SM::H1_HI, sbase + SM::H1_LO,
-                                                    sbase + IM::W2_HI, sbase + IM::W2_LO, ID64<D2>::FK_FK, false);
-      umma::commit(bar);
-    }
-    wait_mma();
-    const uint32_t mask2 = epi64_fwd<D2>(tmem + T64_ACC, x, kk[K_C2], fl + IM::F_B2, smem + SM::H2_HI, smem + SM::H2_LO);
-    sync_after_smem_writes();
-    if (mma_lane()) {
-      issue_gemm<D2 / 16, false, false, true, true>(tmem + T64_L3, sbase + SM::H2_HI, sbase + SM::H2_LO,
-                                                    sbase + IM::W3_HI, sbase + IM::W3_LO, ID64<16>::FK_FK, false);
-      umma::commit(bar);
-    }
-    wait_mma();
-    // ---- head: softmax over the 8 logits of a row (spread over the 4 threads of a quad), loss
-    // gradient, softmax Jacobian -> packed dY panel
-    if (x.ch == 0) {
-      float v[4];
-      tmem_ld_frag(tmem + T64_L3 + x.lane_base, v);
-      umma::tmem_ld_wait();
-      const int cc = 2 * (x.t & 3);
-      const float c3 = kk[K_C3], bb0 = b3[cc], bb1 = b3[cc + 1];
-      uint32_t hw[2], lw[2];
-#pragma unroll
-      for (int rr = 0; rr < 2; ++rr) {
-        float p0 = expf(fmaf(v[2 * rr], c3, bb0)), p1 = expf(fmaf(v[2 * rr + 1], c3, bb1));  // no max subtraction
-        float s = p0 + p1;
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        const float inv_s = 1.f / s;
-        p0 *= inv_s;
-        p1 *= inv_s;
-        const float A = adv[rr];
-        const int ai = act[rr] - cc;  // 0 / 1: this thread holds the action's column
-        float g0, g1;
-        if (a.loss_kind == DFRL_LOSS_CLIPPED) {
-          g0 = ai == 0 ? clipped_grad(p0, pold[rr].x, A) : 0.f;
-          g1 = ai == 1 ? clipped_grad(p1, pold[rr].y, A) : 0.f;
-        } else {
-          g0 = p0 * A - (ai == 0 ? A : 0.f);
-          g1 = p1 * A - (ai == 1 ? A : 0.f);
-        }
-        float d0 = g0, d1 = g1;
-        if (a.head_bwd == HEAD_JACOBIAN) {
-          float dot = fmaf(p0, g0, p1 * g1);
-          dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-          dot += __shfl_xor_sync(0xffffffffu, dot, 2);
-          d0 = p0 * (g0 - dot);
-          d1 = p1 * (g1 - dot);
-        }
-        if (!valid[rr])
-          d0 = d1 = 0.f;
-        db3[2 * rr] += d0;
-        db3[2 * rr + 1] += d1;
-        umma::split2(d0, d1, hw[rr], lw[rr]);
-      }
-      // lo half: columns 16..31 (the swizzle XORs the chunk index: not simply + 32 bytes)
-      *reinterpret_cast<uint32_t *>(smem + SM::DY + umma::panel_off(x.row_a, cc)) = hw[0];
-      *reinterpret_cast<uint32_t *>(smem + SM::DY + umma::panel_off(x.row_a, 16 + cc)) = lw[0];
-      *reinterpret_cast<uint32_t *>(smem + SM::DY + umma::panel_off(x.row_a + 8, cc)) = hw[1];
-      *reinterpret_cast<uint32_t *>(smem + SM::DY + umma::panel_off(x.row_a + 8, 16 + cc)) = lw[1];
-    }
-    sync_after_smem_writes();
-    // ---- dH2 = dY . W3; dW3^T += H2^T . dY behind the dH2 epilogue
-    if (mma_lane()) {
-      issue_gemm<1, false, true, true, true>(tmem + T64_ACC, sbase + SM::DY, sbase + SM::DY + 32, sbase + IM::W3_HI,
-                                             sbase + IM::W3_LO, ID64<D2>::BK_FM, false);
-      umma::commit(bar);
-      issue_dw64<true, true>(tmem + T64_DC, sbase + SM::H2_HI, sbase + SM::H2_LO, 16, sbase + SM::DY,
-                             sbase + SM::DY + 32, ID64<16>::BM_FM, !first_tile);
-    }
-    wait_mma();
-    epi64_bwd<D2>(tmem + T64_ACC, x, kk[K_ISW3], mask2, smem + SM::DH2_HI, smem + SM::DH2_LO);
-    sync_after_smem_writes();
-    // ---- dH1 = dH2 . W2 (dW3 is complete by its commit: H2 may be overwritten by dH1);
-    // dW2 += dH2^T . H1 behind the dH1 epilogue
-    if (mma_lane()) {
-      issue_gemm<D2 / 16, false, true, true, true>(tmem + T64_ACC, sbase + SM::DH2_HI, sbase + SM::DH2_LO,
-                                                   sbase + IM::W2_HI, sbase + IM::W2_LO, ID64<D1>::BK_FM, false);
-      umma::commit(bar);
-      issue_dw64<true, true>(tmem + T64_DA, sbase + SM::DH2_HI, sbase + SM::DH2_LO, 16, sbase + SM::H1_HI,
-                             sbase + SM::H1_LO, ID64<64>::BM_FM, !first_tile);
-    }
-    wait_mma();
-    epi64_bwd<D1>(tmem + T64_ACC, x, kk[K_ISW2], mask1, smem + SM::H2_HI, smem + SM::H2_LO);  // dH1 over H2
-    sync_after_smem_writes();
-    // ---- DB[128 x D0+16] += [dH1|dH2]^T . [X0|1]: rows 0.. = [dW1 | db1], rows 64.. col D0 = db2
-    if (mma_lane()) {
-      issue_dw64<true, false>(tmem + T64_DB, sbase + SM::H2_HI, sbase + SM::H2_LO, 2 * SM::P64, sbase + SM::X0, 0,
-                              make_idesc(128, D0 + 16, 1, 1, 1, 1), !first_tile);
-      umma::commit(bar);
-    }
-    dw_pending = true;
-    first_tile = false;
-  }
-
-  // ---- drain
-  float *part = a.partials + (size_t)blockIdx.x * net.n_params;
-  if (dw_pending)
-    wait_mma();
-  if (first_tile) {
-    for (int i = threadIdx.x; i < net.n_params; i += blockDim.x)
-      part[i] = 0.f;
-  } else {
-    const int wg = threadIdx.x >> 7, w = (threadIdx.x >> 5) & 3, lane = threadIdx.x & 31;
-    const uint32_t lb = (uint32_t)(w * 32) << 16;
-    {  // dW2[n][k]: DA (M = 64) row n in lane 32 (n / 16) + n % 16
-      constexpr int DC = D1 / 2;
-      float v[DC];
-      tmem_load<DC>(tmem + T64_DA + lb + wg * DC, v);
-      const int nrow = lane < 16 ? w * 16 + lane : -1;
-      const float sc = kk[K_ISH1];
-      if (nrow >= 0 && nrow < D2)
-#pragma unroll
-        for (int j = 0; j < DC; ++j)
-          part[net.o_w2 + nrow * D1 + wg * DC + j] = v[j] * sc;
-    }
-    {  // DB (M = 128): row = 32 w + lane
-      constexpr int DC = (D0 + 16) / 2;
-      float v[DC];
-      tmem_load<DC>(tmem + T64_DB + lb + wg * DC, v);
-      const int row = w * 32 + lane;
-#pragma unroll
-      for (int j = 0; j < DC; ++j) {
-        int col = wg * DC + j;
-        if (row < D1) {
-          if (col < D0)
-            part[net.o_w1 + row * D0 + col] = v[j];
-          else if (col == D0)
-            part[net.o_b1 + row] = v[j];
-        } else if (row >= 64 && row - 64 < D2 && col == D0) {
-          part[net.o_b2 + row - 64] = v[j];
-        }
-      }
-    }
-    if (wg == 0) {  // dW3[n][k] = DC (M = 64) row k, col n
-      float v[8];
-      tmem_load<8>(tmem + T64_DC + lb, v);
-      const int krow = lane < 16 ? w * 16 + lane : -1;
-      const float sc = kk[K_ISH2];
-      if (krow >= 0 && krow < D2)
-#pragma unroll
-        for (int j = 0; j < NOUT; ++j)
-          part[net.o_w3 + j * D2 + krow] = v[j] * sc;
-    }
-    // db3: thread (q, t) holds partial sums of columns c, c + 1 over its two rows of every tile
-    if (x.ch == 0) {
-      red[(x.row_a) * 8 + 2 * (x.t & 3)] = db3[0];
-      red[(x.row_a) * 8 + 2 * (x.t & 3) + 1] = db3[1];
-      red[(x.row_a + 8) * 8 + 2 * (x.t & 3)] = db3[2];
-      red[(x.row_a + 8) * 8 + 2 * (x.t & 3) + 1] = db3[3];
-    }
-    __syncthreads();
-    if (threadIdx.x < NOUT) {
-      float sacc = 0.f;
-      for (int r = 0; r < R; ++r)
-        sacc += red[r * 8 + threadIdx.x];
-      part[net.o_b3 + threadIdx.x] = sacc;
-    }
-  }
-  umma::fence_before_sync();
-  __syncthreads();
-  if (x.warp == 0)
-    umma::tmem_dealloc(tmem, T64_COLS);
-}
-
-// ---------------------------------------------------------------------------------------------
 struct fused_state {
   net3 pnet, vnet;
   bool policy_ok, value_ok, rollout_ok;
@@ -2017,15 +1606,6 @@ int launch_policy_step(dfrl_ctx *ctx, const policy_step_args &a, int ctas) {
   static bool attr = false;
   DFRL_TRY(set_smem_once(fused_policy_step_kernel<D0, D1, D2, NOUT, NWG>, smem, &attr));
   DFRL_LAUNCH(ctx, (fused_policy_step_kernel<D0, D1, D2, NOUT, NWG>), ctas, 128 * NWG, smem, a);
-  return DFRL_OK;
-}
-
-template <int D0, int D1, int D2, int NOUT>
-int launch_policy_step64(dfrl_ctx *ctx, const policy_step_args &a, int ctas) {
-  constexpr int smem = smem_map64<D1, D2>::TOTAL + 1024;
-  static bool attr = false;
-  DFRL_TRY(set_smem_once(fused_policy_step64_kernel<D0, D1, D2, NOUT>, smem, &attr));
-  DFRL_LAUNCH(ctx, (fused_policy_step64_kernel<D0, D1, D2, NOUT>), ctas, 256, smem, a);
   return DFRL_OK;
 }
 
@@ -2164,8 +1744,7 @@ int dfrl_fused_try_attach(dfrl_trainer *t) {
   int maxp = t->policy->n_params;
   if (t->value && t->value->n_params > maxp)
     maxp = t->value->n_params;
-  // (the 64-row-tile kernels run two CTAs per SM)
-  bool ok = cudaMalloc(&f->partials, sizeof(float) * (size_t)2 * f->ctas * maxp) == cudaSuccess;
+  bool ok = cudaMalloc(&f->partials, sizeof(float) * (size_t)f->ctas * maxp) == cudaSuccess;
   if (ok)
     ok = cudaMalloc(&f->ticket, sizeof(unsigned)) == cudaSuccess &&
          cudaMemsetAsync(f->ticket, 0, sizeof(unsigned), t->ctx->stream) == cudaSuccess;
@@ -2227,16 +1806,7 @@ int dfrl_fused_policy_gradient(dfrl_trainer *t, int loss_kind, float *grad_dev, 
   a.partials = f->partials;
   a.clk = f->clk;
   int ctas = a.n_tiles < f->ctas ? a.n_tiles : f->ctas;
-  // 64-row tiles, two CTAs per SM (see fused_policy_step64_kernel): needs whole 16-environment
-  // staging units per step, i.e. T in {1, 2, 4}. DFRL_POLICY_TILE=128 forces the 128-row kernel.
-  static const bool force128 = getenv("DFRL_POLICY_TILE") && atoi(getenv("DFRL_POLICY_TILE")) == 128;
-  const bool tile64 = !force128 && f->pnet.d1 == 64 && 64 % t->L == 0 && (64 / t->L) % 16 == 0;
-  if (tile64) {
-    a.rows.E = 64 / t->L;
-    a.n_tiles = ceil_div(t->n, a.rows.E);
-    ctas = a.n_tiles < 2 * f->ctas ? a.n_tiles : 2 * f->ctas;
-    DFRL_TRY((launch_policy_step64<32, 64, 64, 8>(t->ctx, a, ctas)));
-  } else if (f->pnet.d1 == 64)
+  if (f->pnet.d1 == 64)
     DFRL_TRY((launch_policy_step<32, 64, 64, 8>(t->ctx, a, ctas)));
   else
     DFRL_TRY((launch_policy_step<32, 16, 16, 8>(t->ctx, a, ctas)));
