@@ -36,6 +36,11 @@ public:
       throw xeno::error("device context already created");
     check(dfrl_init(ordinal, nranks, rank, nccl_id128, &d.ctx_));
   }
+  // Multi-GPU, after install(): exchange buffers over NVLink peer memory. export_peer_handle()
+  // gives this rank's 64-byte CUDA IPC handle; gather the handles of all ranks (any transport) in
+  // rank order and attach them. The fused learners then exchange gradients without NCCL.
+  static void export_peer_handle(void *handle64) { check(dfrl_p2p_export(get(), handle64)); }
+  static void attach_peers(const void *all_handles) { check(dfrl_p2p_attach(get(), all_handles)); }
   static void sync() { check(dfrl_sync(get())); }
 
 private:
