@@ -28,6 +28,7 @@
 // Jacobian), nn.h:85-100 (dW = SUM over rows), policy_gradient.h:196-281 (targets, GAE).
 #include <cuda_fp16.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "device_fns.cuh"
@@ -1266,6 +1267,521 @@ __global__ void __launch_bounds__(128 * NWG, 1) fused_policy_step_kernel(policy_
     umma::tmem_dealloc(tmem, TC_COLS);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Policy step, two tile pipelines per CTA.
+//
+// A tile's work is a strictly dependent chain  MMA -> epilogue -> MMA -> ...  (8 GEMMs, 5 epilogues),
+// so a CTA that runs one tile at a time leaves the tensor pipe idle during the epilogues and the
+// ALUs idle during the GEMMs. Here each of the two warpgroups owns a whole tile (one thread per
+// row, all columns) and runs the chain on its own: while one warpgroup is in an epilogue the
+// other one's MMAs execute. Each warpgroup has its own MMA-issuing lane, mbarrier, named barrier,
+// 256 TMEM columns (accumulators incl. its own dW partial sums: the drain adds the two in a fixed
+// order) and five activation panels; what makes two tiles fit in 227 KB:
+//   * X0 | 1 | dY share ONE panel: observations in bytes 0..63 of a row, the ones column (bias
+//     gradients) at column 32, dY as [hi(8) | lo(8)] in bytes 96..127 = a single K = 16 step whose
+//     B operand stacks [hi(W3); hi(W3)] (and [lo(W3); 0]): 2 MMAs instead of 3; the dW3 GEMM
+//     (N = 16) yields H2^T dY_hi and H2^T dY_lo in separate columns, summed in the drain;
+//   * dH2 overwrites H2 (after the dW3 GEMM, which is therefore issued BEFORE the dH2 GEMM under
+//     the same commit);
+//   * dH1 lives in one slot shared by both warpgroups, handed over by an mbarrier that the dW1
+//     GEMM's tcgen05.commit arrives on (the slot is held for ~1/6 of a tile);
+//   * hi(W1) / lo(W1) share a panel (K = 32 = 64 bytes each).
+template <int D1, int D2>
+struct pmap {
+  static constexpr uint32_t W1P = 0;  // [D1 rows]: hi in bytes 0..63, lo in bytes 64..127
+  static constexpr uint32_t W2_HI = W1P + D1 * 128, W2_LO = W2_HI + D2 * 128;
+  static constexpr uint32_t W3A = W2_LO + D2 * 128;  // rows 0..7 = rows 8..15 = hi(W3)
+  static constexpr uint32_t W3B = W3A + 16 * 128;    // rows 0..7 = lo(W3), rows 8..15 = 0
+  static constexpr uint32_t FLOATS = W3B + 16 * 128;
+  static constexpr int F_B1 = 0, F_B2 = D1, F_B3 = D1 + D2, N_FLOATS = D1 + D2 + 16;
+  static constexpr uint32_t DH1_HI = (FLOATS + N_FLOATS * 4 + 1023) / 1024 * 1024;  // shared slot
+  static constexpr uint32_t DH1_LO = DH1_HI + PANEL;
+  static constexpr uint32_t WG0 = DH1_LO + PANEL;  // per-warpgroup blocks follow
+  static constexpr uint32_t XD = 0, H1_HI = PANEL, H1_LO = 2 * PANEL, H2_HI = 3 * PANEL, H2_LO = 4 * PANEL;
+  static constexpr uint32_t WG_BYTES = 5 * PANEL;
+  static constexpr uint32_t BARS = WG0 + 2 * WG_BYTES;
+  static constexpr uint32_t TOTAL = BARS + 64;
+  static constexpr uint32_t DY_OFF = 96;  // byte offset of [dY_hi | dY_lo] in a row of the XD panel
+  static_assert((D1 * 128) % 1024 == 0 && (D2 * 128) % 1024 == 0, "panel alignment");
+  static_assert(TOTAL + 1024 <= 232448, "exceeds the 227 KB shared memory of an SM");
+};
+// TMEM columns of one warpgroup (base = 256 * wg)
+constexpr uint32_t P2_ACC0 = 0, P2_ACC1 = 64, P2_DA = 128, P2_DB = 192, P2_DC = 240;
+
+template <int D0, int D1, int D2, int NOUT>
+__device__ void build_image2(const float *__restrict__ params, const net3 &net, uint8_t *smem) {
+  using PM = pmap<D1, D2>;
+  const float *W1 = params + net.o_w1, *W2 = params + net.o_w2, *W3 = params + net.o_w3;
+  static_assert(D0 == 32 && NOUT == 8, "packed W1 / stacked W3 panels assume 32 inputs, 8 outputs");
+  for (int c = threadIdx.x; c < D1 * 4; c += blockDim.x) {
+    int row = c >> 2, chunk = c & 3;
+    float x[8];
+    const float4 *src = reinterpret_cast<const float4 *>(W1 + (size_t)row * D0 + chunk * 8);
+    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+      float4 p = __ldg(src), q = __ldg(src + 1);
+      x[0] = p.x, x[1] = p.y, x[2] = p.z, x[3] = p.w, x[4] = q.x, x[5] = q.y, x[6] = q.z, x[7] = q.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        x[j] = W1[(size_t)row * D0 + chunk * 8 + j];
+    }
+    uint4 h, l;
+    split8<false>(x, h, l);
+    *reinterpret_cast<uint4 *>(smem + PM::W1P + umma::panel_chunk_off(row, chunk)) = h;
+    *reinterpret_cast<uint4 *>(smem + PM::W1P + umma::panel_chunk_off(row, 4 + chunk)) = l;
+  }
+  stage_weight_f16(W2, D2, D1, D2, 1.f, smem + PM::W2_HI, smem + PM::W2_LO);
+  for (int c = threadIdx.x; c < 16 * 8; c += blockDim.x) {
+    int row = c >> 3, chunk = c & 7;
+    float x[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int col = chunk * 8 + j;
+      x[j] = col < D2 ? W3[(size_t)(row & 7) * D2 + col] : 0.f;
+    }
+    uint4 h, l;
+    split8<false>(x, h, l);
+    uint32_t off = umma::panel_chunk_off(row, chunk);
+    *reinterpret_cast<uint4 *>(smem + PM::W3A + off) = h;
+    *reinterpret_cast<uint4 *>(smem + PM::W3B + off) = row < 8 ? l : make_uint4(0, 0, 0, 0);
+  }
+  float *fl = reinterpret_cast<float *>(smem + PM::FLOATS);
+  for (int i = threadIdx.x; i < D1; i += blockDim.x) fl[PM::F_B1 + i] = params[net.o_b1 + i];
+  for (int i = threadIdx.x; i < D2; i += blockDim.x) fl[PM::F_B2 + i] = params[net.o_b2 + i];
+  for (int i = threadIdx.x; i < 16; i += blockDim.x) fl[PM::F_B3 + i] = i < net.d3 ? params[net.o_b3 + i] : 0.f;
+}
+
+// issue_gemm with a run-time leading byte offset of the A operand (M = 128 spanning two panels
+// that are not adjacent) and no lo pass of B.
+template <int KSTEPS>
+__device__ __forceinline__ void issue_gemm_mn_lbo(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t a_lbo,
+                                                  uint32_t b_hi, uint32_t idesc, bool accumulate) {
+  constexpr uint32_t step = umma::KSTEP_BYTES_MNMAJOR >> 4;
+  const uint32_t ah0 = desc_lo(a_hi, a_lbo), al0 = desc_lo(a_lo, a_lbo), bh0 = desc_lo(b_hi, PANEL);
+#pragma unroll
+  for (int k = 0; k < KSTEPS; ++k) {
+    uint64_t bh = desc_lo_hi(bh0 + k * step);
+    umma::mma_bf16(tmem_d, desc_lo_hi(ah0 + k * step), bh, idesc, (k > 0 || accumulate) ? 1u : 0u);
+    umma::mma_bf16(tmem_d, desc_lo_hi(al0 + k * step), bh, idesc, 1);
+  }
+}
+
+__device__ __forceinline__ void wg_bar(int wg) { asm volatile("bar.sync %0, 128;\n" ::"r"(wg + 1) : "memory"); }
+__device__ __forceinline__ void wg_sync_after_smem_writes(int wg) {
+  umma::fence_proxy_async();
+  umma::fence_before_sync();
+  wg_bar(wg);
+  umma::fence_after_sync();
+}
+// One lane of warp 0 of each warpgroup issues that warpgroup's MMAs (warp-uniform test).
+__device__ __forceinline__ bool wg_mma_thread(const tid_t &t) { return (t.warp & 3) == 0 && umma::elect_one(); }
+
+// TMEM accumulator (this thread's row, all D columns) -> + bias, relu -> hi/lo panels; relu masks.
+template <int D>
+__device__ __forceinline__ void epi2_fwd(uint32_t acc, const tid_t &t, const float *__restrict__ bias, uint8_t *hi,
+                                         uint8_t *lo, uint32_t (&mask)[2]) {
+  constexpr int CH = D < 32 ? D : 32;
+  mask[0] = mask[1] = 0;
+#pragma unroll
+  for (int h = 0; h < D / CH; ++h) {
+    float v[CH];
+    tmem_load<CH>(acc + t.lane_base + h * CH, v);
+    uint32_t m = 0;
+#pragma unroll
+    for (int j4 = 0; j4 < CH; j4 += 4) {
+      float4 b = *reinterpret_cast<const float4 *>(bias + h * CH + j4);
+      float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float x = v[j4 + q] + bb[q];
+        if (x > 0.f)
+          m |= 1u << (j4 + q);
+        else
+          x = 0.f;
+        v[j4 + q] = x;
+      }
+    }
+    mask[h] = m;
+#pragma unroll
+    for (int cc = 0; cc < CH / 8; ++cc) {
+      uint4 hh, ll;
+      split8<false>(&v[8 * cc], hh, ll);
+      uint32_t off = umma::panel_chunk_off(t.row, h * (CH / 8) + cc);
+      *reinterpret_cast<uint4 *>(hi + off) = hh;
+      *reinterpret_cast<uint4 *>(lo + off) = ll;
+    }
+  }
+}
+// TMEM accumulator -> . relu mask -> hi/lo panels (input-gradient epilogue).
+template <int D>
+__device__ __forceinline__ void epi2_bwd(uint32_t acc, const tid_t &t, const uint32_t (&mask)[2], uint8_t *hi,
+                                         uint8_t *lo) {
+  constexpr int CH = D < 32 ? D : 32;
+#pragma unroll
+  for (int h = 0; h < D / CH; ++h) {
+    float v[CH];
+    tmem_load<CH>(acc + t.lane_base + h * CH, v);
+#pragma unroll
+    for (int j = 0; j < CH; ++j)
+      v[j] = (mask[h] >> j) & 1u ? v[j] : 0.f;
+#pragma unroll
+    for (int cc = 0; cc < CH / 8; ++cc) {
+      uint4 hh, ll;
+      split8<false>(&v[8 * cc], hh, ll);
+      uint32_t off = umma::panel_chunk_off(t.row, h * (CH / 8) + cc);
+      *reinterpret_cast<uint4 *>(hi + off) = hh;
+      *reinterpret_cast<uint4 *>(lo + off) = ll;
+    }
+  }
+}
+
+// The raw start state (2B + 2 int8 planes) of one learner row, global -> registers (4 planes per
+// register: the values wait a whole tile for their turn).
+template <int B>
+struct row_state {
+  uint32_t w[(2 * B + 2 + 3) / 4];
+};
+template <int B>
+__device__ __forceinline__ void load_row_state(const learner_rows &L, int tile, int row, row_state<B> &x) {
+  constexpr int P = 2 * B + 2;
+  const int tt = row / L.E, e = row % L.E, i = tile * L.E + e;
+  const bool ok = tt < L.T && i < L.n;
+  const uint8_t *src = reinterpret_cast<const uint8_t *>(L.rec_state) + (size_t)tt * P * L.stride + i;
+#pragma unroll
+  for (int q4 = 0; q4 < (P + 3) / 4; ++q4) {
+    uint32_t w = 0;
+#pragma unroll
+    for (int q = 4 * q4; q < 4 * q4 + 4 && q < P; ++q)
+      w |= (ok ? (uint32_t)src[(size_t)q * L.stride] : 0u) << (8 * (q & 3));
+    x.w[q4] = w;
+  }
+}
+// observation::to_vector (bin_packing.h:31-40) of this row into bytes 0..63 of its XD panel row.
+template <int B>
+__device__ __forceinline__ void encode_row(uint8_t *xd, int row, const row_state<B> &x, float inv_w, float inv_h) {
+  float v[2 * B + 2];
+#pragma unroll
+  for (int q = 0; q < 2 * B + 2; ++q)
+    v[q] = (float)(int8_t)(x.w[q >> 2] >> (8 * (q & 3))) * ((q & 1) ? inv_h : inv_w);
+  const uint32_t it = pack2_fwd(v[2 * B], v[2 * B + 1]);
+#pragma unroll
+  for (int ch = 0; ch < B / 2; ++ch)
+    *reinterpret_cast<uint4 *>(xd + umma::panel_chunk_off(row, ch)) =
+        make_uint4(pack2_fwd(v[4 * ch], v[4 * ch + 1]), it, pack2_fwd(v[4 * ch + 2], v[4 * ch + 3]), it);
+}
+
+template <int D0, int D1, int D2, int NOUT>
+__global__ void __launch_bounds__(256, 1) fused_policy_step2_kernel(policy_step_args a) {
+  using PM = pmap<D1, D2>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);  // stays a shared-space pointer
+  const float *fl = reinterpret_cast<const float *>(smem + PM::FLOATS);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + PM::BARS);  // [wg]: MMA completion, [2]: dH1 slot free
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + PM::BARS + 32);
+  const net3 net = a.net;
+  const learner_rows &L = a.rows;
+  const tid_t t = thread_id();
+  const int wg = t.warp >> 2;  // warp-uniform
+  const uint32_t sbase = umma::smem_u32(smem);
+
+  if (t.warp == 0)
+    umma::tmem_alloc(tmem_slot, 512);
+  if (threadIdx.x == 0) {
+    umma::mbar_init(bars + 0, 1);
+    umma::mbar_init(bars + 1, 1);
+    umma::mbar_init(bars + 2, 1);
+    umma::fence_mbar_init();
+  }
+  build_image2<D0, D1, D2, NOUT>(a.params, net, smem);
+  zero_bytes(smem + PM::DH1_HI, PM::BARS - PM::DH1_HI);
+  __syncthreads();
+  // ones column (col D0) of both XD panels: [dH1|dH2]^T . 1 = bias gradients for free
+  *reinterpret_cast<uint16_t *>(smem + PM::WG0 + wg * PM::WG_BYTES + PM::XD + umma::panel_off(t.row, D0)) = 0x3F80;
+  sync_after_smem_writes();
+  const uint32_t tmem = *tmem_slot;
+
+  // this CTA's tiles: blockIdx.x + j * gridDim.x, j < nt; warpgroup wg takes j = wg, wg + 2, ...
+  const int nt = (int)blockIdx.x < a.n_tiles ? (a.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  uint8_t *wsm = smem + PM::WG0 + wg * PM::WG_BYTES;
+  const uint32_t wbase = sbase + PM::WG0 + wg * PM::WG_BYTES;
+  const uint32_t tm = tmem + 256u * wg;
+  const uint32_t dh1_lbo = PM::WG0 + wg * PM::WG_BYTES + PM::H2_HI - PM::DH1_HI;  // dH1 panel -> own dH2 panel
+  uint64_t *bar = bars + wg;
+  uint32_t phase = 0;
+  auto wait_mma = [&]() {
+    umma::mbar_wait(bar, phase);
+    phase ^= 1;
+    umma::fence_after_sync();
+  };
+
+  long long *clk = (a.clk && blockIdx.x == 0 && threadIdx.x == 96) ? a.clk : nullptr;
+  int clk_n = 0;
+#define STAMP() do { if (clk && clk_n < 112) clk[clk_n++] = clock64(); } while (0)
+
+  float db3[NOUT];
+#pragma unroll
+  for (int j = 0; j < NOUT; ++j)
+    db3[j] = 0.f;
+  bool first = true;
+  row_state<NOUT> xr;
+  if (wg < nt) {
+    load_row_state<NOUT>(L, blockIdx.x + wg * gridDim.x, t.row, xr);
+    encode_row<NOUT>(wsm + PM::XD, t.row, xr, L.inv_w, L.inv_h);
+  }
+  wg_sync_after_smem_writes(wg);
+
+  for (int j = wg; j < nt; j += 2) {
+    const int tile = blockIdx.x + j * gridDim.x;
+    STAMP();
+    // ---- layer 1 issue first, then the global loads that are consumed later
+    if (wg_mma_thread(t)) {
+      issue_gemm<D0 / 16, false, false, false, true>(tm + P2_ACC0, wbase + PM::XD, 0, sbase + PM::W1P,
+                                                     sbase + PM::W1P + 64, ID<D1>::FK_FK, false);
+      umma::commit(bar);
+    }
+    const int tt = t.row / L.E, e = t.row % L.E;
+    const int i = tile * L.E + e;
+    const bool valid = tt < L.T && i < L.n;
+    const size_t k = (size_t)tt * L.n + i;
+    int act = 0;
+    float A = 0.f;
+    float4 po[NOUT / 4];
+#pragma unroll
+    for (int q = 0; q < NOUT / 4; ++q)
+      po[q] = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (valid) {
+      act = L.rec_action[k];
+      A = a.adv[k];
+      const float4 *pr = reinterpret_cast<const float4 *>(a.p_old + k * NOUT);
+#pragma unroll
+      for (int q = 0; q < NOUT / 4; ++q)
+        po[q] = pr[q];
+    }
+    const bool has_next = j + 2 < nt;
+    if (has_next)
+      load_row_state<NOUT>(L, tile + 2 * gridDim.x, t.row, xr);
+    wait_mma();
+    STAMP();
+    uint32_t mask1[2], mask2[2];
+    epi2_fwd<D1>(tm + P2_ACC0, t, fl + PM::F_B1, wsm + PM::H1_HI, wsm + PM::H1_LO, mask1);
+    wg_sync_after_smem_writes(wg);
+    STAMP();
+    if (wg_mma_thread(t)) {
+      issue_gemm<D1 / 16, false, false, true, true>(tm + P2_ACC1, wbase + PM::H1_HI, wbase + PM::H1_LO,
+                                                    sbase + PM::W2_HI, sbase + PM::W2_LO, ID<D2>::FK_FK, false);
+      umma::commit(bar);
+    }
+    wait_mma();
+    STAMP();
+    epi2_fwd<D2>(tm + P2_ACC1, t, fl + PM::F_B2, wsm + PM::H2_HI, wsm + PM::H2_LO, mask2);
+    wg_sync_after_smem_writes(wg);
+    STAMP();
+    // ---- layer 3 (head): columns 8..15 of the result repeat 0..7 (stacked B operand), unused
+    if (wg_mma_thread(t)) {
+      issue_gemm<D2 / 16, false, false, true, true>(tm + P2_ACC0, wbase + PM::H2_HI, wbase + PM::H2_LO,
+                                                    sbase + PM::W3A, sbase + PM::W3B, ID<16>::FK_FK, false);
+      umma::commit(bar);
+    }
+    wait_mma();
+    STAMP();
+    // ---- head epilogue: softmax, loss gradient, softmax backward -> dY = [hi | lo] in the XD panel
+    {
+      float v[8];
+      tmem_load<8>(tm + P2_ACC0 + t.lane_base, v);
+      float dl[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        dl[q] = 0.f;
+      if (valid) {
+        const float *b3 = fl + PM::F_B3;
+        float p[NOUT], s = 0.f;
+#pragma unroll
+        for (int q = 0; q < NOUT; ++q) {
+          p[q] = expf(v[q] + b3[q]);  // no max subtraction (nn.h:382-392)
+          s += p[q];
+        }
+        const float inv_s = 1.f / s;
+#pragma unroll
+        for (int q = 0; q < NOUT; ++q)
+          p[q] = p[q] * inv_s;
+        float g[NOUT];
+        if (a.loss_kind == DFRL_LOSS_CLIPPED) {
+          float pa = 0.f, pold = 1.f;
+          const float *pof = reinterpret_cast<const float *>(po);
+#pragma unroll
+          for (int q = 0; q < NOUT; ++q) {
+            pa = (q == act) ? p[q] : pa;
+            pold = (q == act) ? pof[q] : pold;
+          }
+          float gc = clipped_grad(pa, pold, A);
+#pragma unroll
+          for (int q = 0; q < NOUT; ++q)
+            g[q] = (q == act) ? gc : 0.f;
+        } else {
+#pragma unroll
+          for (int q = 0; q < NOUT; ++q)
+            g[q] = p[q] * A - (q == act ? A : 0.f);
+        }
+        if (a.head_bwd == HEAD_JACOBIAN) {
+          float dot = 0.f;
+#pragma unroll
+          for (int q = 0; q < NOUT; ++q)
+            dot = fmaf(p[q], g[q], dot);
+#pragma unroll
+          for (int q = 0; q < NOUT; ++q)
+            dl[q] = p[q] * (g[q] - dot);
+        } else {
+#pragma unroll
+          for (int q = 0; q < NOUT; ++q)
+            dl[q] = g[q];
+        }
+#pragma unroll
+        for (int q = 0; q < NOUT; ++q)
+          db3[q] += dl[q];
+      }
+      uint4 h, l;
+      split8<false>(dl, h, l);
+      *reinterpret_cast<uint4 *>(wsm + PM::XD + umma::panel_chunk_off(t.row, 6)) = h;
+      *reinterpret_cast<uint4 *>(wsm + PM::XD + umma::panel_chunk_off(t.row, 7)) = l;
+    }
+    wg_sync_after_smem_writes(wg);
+    STAMP();
+    // ---- dW3^T += H2^T . [dY_hi | dY_lo] (M = 64, N = 16) first: the dH2 epilogue overwrites H2;
+    // dH2 = [dY_hi | dY_lo] . [hi(W3); hi(W3)] + [dY_hi | dY_lo] . [lo(W3); 0]
+    if (wg_mma_thread(t)) {
+      issue_gemm<8, true, true, true, false>(tm + P2_DC, wbase + PM::H2_HI, wbase + PM::H2_LO,
+                                             wbase + PM::XD + PM::DY_OFF, 0, ID<16>::FM_BM_64, !first);
+      issue_gemm<1, false, true, false, true>(tm + P2_ACC0, wbase + PM::XD + PM::DY_OFF, 0, sbase + PM::W3A,
+                                              sbase + PM::W3B, ID<D2>::BK_FM, false);
+      umma::commit(bar);
+    }
+    wait_mma();
+    STAMP();
+    epi2_bwd<D2>(tm + P2_ACC0, t, mask2, wsm + PM::H2_HI, wsm + PM::H2_LO);
+    wg_sync_after_smem_writes(wg);
+    STAMP();
+    // ---- dH1 = dH2 . W2; dW2 += dH2^T . H1 (M = 64) runs behind the dH1 epilogue
+    if (wg_mma_thread(t)) {
+      issue_gemm<D2 / 16, false, true, true, true>(tm + P2_ACC1, wbase + PM::H2_HI, wbase + PM::H2_LO,
+                                                   sbase + PM::W2_HI, sbase + PM::W2_LO, ID<D1>::BK_FM, false);
+      umma::commit(bar);
+      issue_gemm<8, true, true, true, true>(tm + P2_DA, wbase + PM::H2_HI, wbase + PM::H2_LO, wbase + PM::H1_HI,
+                                            wbase + PM::H1_LO, ID<D1>::BM_FM_64, !first);
+    }
+    wait_mma();
+    // the shared dH1 slot: free once the previous tile of this CTA (the other warpgroup's) has
+    // finished its dW1 GEMM (completion j - 1 of bars[2])
+    if (j > 0) {
+      umma::mbar_wait(bars + 2, (uint32_t)(j - 1) & 1u);
+      umma::fence_after_sync();
+    }
+    STAMP();
+    epi2_bwd<D1>(tm + P2_ACC1, t, mask1, smem + PM::DH1_HI, smem + PM::DH1_LO);
+    wg_sync_after_smem_writes(wg);
+    STAMP();
+    //   DB[128 x D0+16] += [dH1|dH2]^T . [X0|1]   rows 0.. = [dW1 | db1], rows 64.. col D0 = db2
+    if (wg_mma_thread(t)) {
+      issue_gemm_mn_lbo<8>(tm + P2_DB, sbase + PM::DH1_HI, sbase + PM::DH1_LO, dh1_lbo, wbase + PM::XD,
+                           ID<D0 + 16>::BM_FM, !first);
+      umma::commit(bar);
+      umma::commit(bars + 2);
+    }
+    wait_mma();  // X0 (dW1), H1 (dW2) and the accumulators are free again
+    STAMP();
+    if (has_next)
+      encode_row<NOUT>(wsm + PM::XD, t.row, xr, L.inv_w, L.inv_h);
+    wg_sync_after_smem_writes(wg);
+    STAMP();
+    first = false;
+  }
+#undef STAMP
+
+  // ---- drain: partial gradient of this CTA (warpgroup 0's sums + warpgroup 1's) -> global
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  float *part = a.partials + (size_t)blockIdx.x * net.n_params;
+  const bool two = nt > 1;  // warpgroup 1 had at least one tile
+  if (nt == 0) {
+    for (int q = threadIdx.x; q < net.n_params; q += blockDim.x)
+      part[q] = 0.f;
+  } else {
+    // dW2[n][k]: DA (M = 64) row n = TMEM lane 32 (n / 16) + n % 16, col k
+    {
+      constexpr int DC = D1 / 2;
+      float v[DC], w[DC];
+      tmem_load<DC>(tmem + P2_DA + t.lane_base + t.wg * DC, v);
+      if (two) {
+        tmem_load<DC>(tmem + 256 + P2_DA + t.lane_base + t.wg * DC, w);
+#pragma unroll
+        for (int q = 0; q < DC; ++q)
+          v[q] += w[q];
+      }
+      int nrow = t.lane < 16 ? t.w * 16 + t.lane : -1;
+      if (nrow >= 0 && nrow < D2)
+#pragma unroll
+        for (int q = 0; q < DC; ++q)
+          part[net.o_w2 + nrow * D1 + t.wg * DC + q] = v[q];
+    }
+    // dW1[n][k] + db1[n]: DB row n, cols 0..D0-1 and D0; db2[n]: DB row 64 + n, col D0
+    {
+      constexpr int DC = (D0 + 16) / 2;
+      float v[DC], w[DC];
+      tmem_load<DC>(tmem + P2_DB + t.lane_base + t.wg * DC, v);
+      if (two) {
+        tmem_load<DC>(tmem + 256 + P2_DB + t.lane_base + t.wg * DC, w);
+#pragma unroll
+        for (int q = 0; q < DC; ++q)
+          v[q] += w[q];
+      }
+#pragma unroll
+      for (int q = 0; q < DC; ++q) {
+        int col = t.wg * DC + q;
+        if (t.row < D1) {
+          if (col < D0)
+            part[net.o_w1 + t.row * D0 + col] = v[q];
+          else if (col == D0)
+            part[net.o_b1 + t.row] = v[q];
+        } else if (t.row >= 64 && t.row - 64 < D2 && col == D0) {
+          part[net.o_b2 + t.row - 64] = v[q];
+        }
+      }
+    }
+    // dW3[n][k] = DC (M = 64) row k, cols n (H2^T dY_hi) and 8 + n (H2^T dY_lo)
+    if (t.wg == 0) {
+      float v[16], w[16];
+      tmem_load<16>(tmem + P2_DC + t.lane_base, v);
+      if (two) {
+        tmem_load<16>(tmem + 256 + P2_DC + t.lane_base, w);
+#pragma unroll
+        for (int q = 0; q < 16; ++q)
+          v[q] += w[q];
+      }
+      int krow = t.lane < 16 ? t.w * 16 + t.lane : -1;
+      if (krow >= 0 && krow < D2)
+#pragma unroll
+        for (int q = 0; q < NOUT; ++q)
+          part[net.o_w3 + q * D2 + krow] = v[q] + v[8 + q];
+    }
+    // db3: per-thread partial sums -> fixed-order block sum (scratch = warpgroup 0's H1 panels)
+    float *red = reinterpret_cast<float *>(smem + PM::WG0 + PM::H1_HI);
+#pragma unroll
+    for (int q = 0; q < NOUT; ++q)
+      red[threadIdx.x * 8 + q] = db3[q];
+    __syncthreads();
+    if (threadIdx.x < NOUT) {
+      float s = 0.f;
+      for (int r = 0; r < 2 * TILE; ++r)
+        s += red[r * 8 + threadIdx.x];
+      part[net.o_b3 + threadIdx.x] = s;
+    }
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (t.warp == 0)
+    umma::tmem_dealloc(tmem, 512);
+}
+
 // Second stage of the gradient: fixed-order sum of the per-CTA partials. Block = 32 parameters x 8
 // slices of the CTA range; the 8 slice sums are combined in a fixed order. With a single rank the
 // optimizer update (nn.h:616-698) of the same 32 parameters follows in the same kernel.
@@ -1601,6 +2117,14 @@ int set_smem_once(K kernel, int smem, bool *done) {
 // barriers cost more.
 template <int D0, int D1, int D2, int NOUT>
 int launch_policy_step(dfrl_ctx *ctx, const policy_step_args &a, int ctas) {
+  static const bool v1 = getenv("DFRL_POLICY_V1") != nullptr;  // A/B switch: one tile at a time
+  if (!v1) {
+    constexpr int smem2 = pmap<D1, D2>::TOTAL + 1024;
+    static bool attr2 = false;
+    DFRL_TRY(set_smem_once(fused_policy_step2_kernel<D0, D1, D2, NOUT>, smem2, &attr2));
+    DFRL_LAUNCH(ctx, (fused_policy_step2_kernel<D0, D1, D2, NOUT>), ctas, 256, smem2, a);
+    return DFRL_OK;
+  }
   constexpr int smem = smem_map<D1, D2>::TOTAL + 1024;
   constexpr int NWG = 2;
   static bool attr = false;
