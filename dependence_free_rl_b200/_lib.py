@@ -64,6 +64,7 @@ PROTOTYPES = {
     "dfrl_timer_stop": (i32, [vp, C.POINTER(f32)]),
     "dfrl_launch_count": (C.c_longlong, [vp]),
     "dfrl_umma_selftest": (i32, [vp, i32, i32, i32, C.POINTER(f32)]),
+    "dfrl_umma_microbench": (i32, [vp, i32, i32, i32, i32, i32, C.POINTER(C.c_longlong)]),
     "dfrl_debug_policy_clocks": (i32, [vp, vp, i32]),
     "dfrl_p2p_export": (i32, [vp, vp]),
     "dfrl_p2p_attach": (i32, [vp, vp]),

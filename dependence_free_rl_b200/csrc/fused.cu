@@ -1376,45 +1376,10 @@ __device__ __forceinline__ void wg_sync_after_smem_writes(int wg) {
 // One lane of warp 0 of each warpgroup issues that warpgroup's MMAs (warp-uniform test).
 __device__ __forceinline__ bool wg_mma_thread(const tid_t &t) { return (t.warp & 3) == 0 && umma::elect_one(); }
 
-// TMEM accumulator (this thread's row, all D columns) -> + bias, relu -> hi/lo panels; relu masks.
+// TMEM accumulator (this thread's row, all D columns) -> + bias, relu -> hi/lo panels. No relu mask
+// is kept: the backward epilogue of the same thread reads it off the hi panel (H > 0 <=> hi(H) > 0).
 template <int D>
 __device__ __forceinline__ void epi2_fwd(uint32_t acc, const tid_t &t, const float *__restrict__ bias, uint8_t *hi,
-                                         uint8_t *lo, uint32_t (&mask)[2]) {
-  constexpr int CH = D < 32 ? D : 32;
-  mask[0] = mask[1] = 0;
-#pragma unroll
-  for (int h = 0; h < D / CH; ++h) {
-    float v[CH];
-    tmem_load<CH>(acc + t.lane_base + h * CH, v);
-    uint32_t m = 0;
-#pragma unroll
-    for (int j4 = 0; j4 < CH; j4 += 4) {
-      float4 b = *reinterpret_cast<const float4 *>(bias + h * CH + j4);
-      float bb[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float x = v[j4 + q] + bb[q];
-        if (x > 0.f)
-          m |= 1u << (j4 + q);
-        else
-          x = 0.f;
-        v[j4 + q] = x;
-      }
-    }
-    mask[h] = m;
-#pragma unroll
-    for (int cc = 0; cc < CH / 8; ++cc) {
-      uint4 hh, ll;
-      split8<false>(&v[8 * cc], hh, ll);
-      uint32_t off = umma::panel_chunk_off(t.row, h * (CH / 8) + cc);
-      *reinterpret_cast<uint4 *>(hi + off) = hh;
-      *reinterpret_cast<uint4 *>(lo + off) = ll;
-    }
-  }
-}
-// TMEM accumulator -> . relu mask -> hi/lo panels (input-gradient epilogue).
-template <int D>
-__device__ __forceinline__ void epi2_bwd(uint32_t acc, const tid_t &t, const uint32_t (&mask)[2], uint8_t *hi,
                                          uint8_t *lo) {
   constexpr int CH = D < 32 ? D : 32;
 #pragma unroll
@@ -1422,8 +1387,13 @@ __device__ __forceinline__ void epi2_bwd(uint32_t acc, const tid_t &t, const uin
     float v[CH];
     tmem_load<CH>(acc + t.lane_base + h * CH, v);
 #pragma unroll
-    for (int j = 0; j < CH; ++j)
-      v[j] = (mask[h] >> j) & 1u ? v[j] : 0.f;
+    for (int j4 = 0; j4 < CH; j4 += 4) {
+      float4 b = *reinterpret_cast<const float4 *>(bias + h * CH + j4);
+      v[j4] = fmaxf(v[j4] + b.x, 0.f);
+      v[j4 + 1] = fmaxf(v[j4 + 1] + b.y, 0.f);
+      v[j4 + 2] = fmaxf(v[j4 + 2] + b.z, 0.f);
+      v[j4 + 3] = fmaxf(v[j4 + 3] + b.w, 0.f);
+    }
 #pragma unroll
     for (int cc = 0; cc < CH / 8; ++cc) {
       uint4 hh, ll;
@@ -1434,26 +1404,53 @@ __device__ __forceinline__ void epi2_bwd(uint32_t acc, const tid_t &t, const uin
     }
   }
 }
+// 0xffff in each half whose bf16 value is > 0
+__device__ __forceinline__ uint32_t pos_mask2(uint32_t w) {
+  uint32_t m;
+  asm("set.gt.u32.bf16x2 %0, %1, %2;\n" : "=r"(m) : "r"(w), "r"(0u));
+  return m;
+}
+// TMEM accumulator -> . relu mask (taken from the forward activation's hi panel `act_hi`) -> hi/lo
+// panels (input-gradient epilogue). `act_hi` may be the destination `hi` itself: every thread reads
+// a 16-byte chunk before it overwrites that same chunk.
+template <int D>
+__device__ __forceinline__ void epi2_bwd(uint32_t acc, const tid_t &t, const uint8_t *act_hi, uint8_t *hi,
+                                         uint8_t *lo) {
+  constexpr int CH = D < 32 ? D : 32;
+#pragma unroll
+  for (int h = 0; h < D / CH; ++h) {
+    float v[CH];
+    tmem_load<CH>(acc + t.lane_base + h * CH, v);
+#pragma unroll
+    for (int cc = 0; cc < CH / 8; ++cc) {
+      uint32_t off = umma::panel_chunk_off(t.row, h * (CH / 8) + cc);
+      const uint4 aw = *reinterpret_cast<const uint4 *>(act_hi + off);
+      uint4 hh, ll;
+      split8<false>(&v[8 * cc], hh, ll);
+      const uint32_t m0 = pos_mask2(aw.x), m1 = pos_mask2(aw.y), m2 = pos_mask2(aw.z), m3 = pos_mask2(aw.w);
+      *reinterpret_cast<uint4 *>(hi + off) = make_uint4(hh.x & m0, hh.y & m1, hh.z & m2, hh.w & m3);
+      *reinterpret_cast<uint4 *>(lo + off) = make_uint4(ll.x & m0, ll.y & m1, ll.z & m2, ll.w & m3);
+    }
+  }
+}
 
-// The raw start state (2B + 2 int8 planes) of one learner row, global -> registers (4 planes per
-// register: the values wait a whole tile for their turn).
+// The raw start state (2B + 2 int8 planes) of one learner row, global -> registers. Nothing touches
+// the loaded values before encode_row: the loads stay in flight behind the tile's math.
 template <int B>
 struct row_state {
-  uint32_t w[(2 * B + 2 + 3) / 4];
+  int v[2 * B + 2];
 };
 template <int B>
 __device__ __forceinline__ void load_row_state(const learner_rows &L, int tile, int row, row_state<B> &x) {
   constexpr int P = 2 * B + 2;
   const int tt = row / L.E, e = row % L.E, i = tile * L.E + e;
   const bool ok = tt < L.T && i < L.n;
-  const uint8_t *src = reinterpret_cast<const uint8_t *>(L.rec_state) + (size_t)tt * P * L.stride + i;
+  const int8_t *src = L.rec_state + (size_t)tt * P * L.stride + i;
 #pragma unroll
-  for (int q4 = 0; q4 < (P + 3) / 4; ++q4) {
-    uint32_t w = 0;
-#pragma unroll
-    for (int q = 4 * q4; q < 4 * q4 + 4 && q < P; ++q)
-      w |= (ok ? (uint32_t)src[(size_t)q * L.stride] : 0u) << (8 * (q & 3));
-    x.w[q4] = w;
+  for (int q = 0; q < P; ++q) {
+    x.v[q] = 0;
+    if (ok)
+      x.v[q] = src[(size_t)q * L.stride];
   }
 }
 // observation::to_vector (bin_packing.h:31-40) of this row into bytes 0..63 of its XD panel row.
@@ -1462,7 +1459,7 @@ __device__ __forceinline__ void encode_row(uint8_t *xd, int row, const row_state
   float v[2 * B + 2];
 #pragma unroll
   for (int q = 0; q < 2 * B + 2; ++q)
-    v[q] = (float)(int8_t)(x.w[q >> 2] >> (8 * (q & 3))) * ((q & 1) ? inv_h : inv_w);
+    v[q] = (float)x.v[q] * ((q & 1) ? inv_h : inv_w);
   const uint32_t it = pack2_fwd(v[2 * B], v[2 * B + 1]);
 #pragma unroll
   for (int ch = 0; ch < B / 2; ++ch)
@@ -1470,231 +1467,300 @@ __device__ __forceinline__ void encode_row(uint8_t *xd, int row, const row_state
         make_uint4(pack2_fwd(v[4 * ch], v[4 * ch + 1]), it, pack2_fwd(v[4 * ch + 2], v[4 * ch + 3]), it);
 }
 
+// Operands-ready handshake between a warpgroup's 128 epilogue threads (arrive) and its MMA-issuing
+// warp (sync): named barriers 1 + 2 wg + parity, 160 threads. Two alternating ids: an epilogue
+// thread is never more than one hand-over ahead of the issuer.
+__device__ __forceinline__ void ready_arrive(int wg, uint32_t &parity) {
+  umma::fence_proxy_async();
+  umma::fence_before_sync();
+  asm volatile("bar.arrive %0, 160;\n" ::"r"(1 + 2 * wg + (int)parity) : "memory");
+  parity ^= 1;
+}
+__device__ __forceinline__ void ready_sync(int wg, uint32_t &parity) {
+  asm volatile("bar.sync %0, 160;\n" ::"r"(1 + 2 * wg + (int)parity) : "memory");
+  parity ^= 1;
+  umma::fence_after_sync();
+}
+
+// 320 threads: warps 0..3 / 4..7 = the epilogue threads of pipeline 0 / 1 (one thread per tile row),
+// warps 8 / 9 = their MMA issuers. tcgen05.mma issue blocks the issuing thread for about the pipe
+// time of the instruction (measured: tools/mma_microbench.py), so a GEMM that is meant to run behind
+// an epilogue must not be issued by a thread that takes part in that epilogue.
 template <int D0, int D1, int D2, int NOUT>
-__global__ void __launch_bounds__(256, 1) fused_policy_step2_kernel(policy_step_args a) {
+__global__ void __launch_bounds__(320, 1) fused_policy_step2_kernel(policy_step_args a) {
   using PM = pmap<D1, D2>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);  // stays a shared-space pointer
   const float *fl = reinterpret_cast<const float *>(smem + PM::FLOATS);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + PM::BARS);  // [wg]: MMA completion, [2]: dH1 slot free
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + PM::BARS + 32);
+  // mbarriers: [wg] MMA completion on the chain, [2] dH1 slot free, [3 + wg] dW2 GEMM done (H1 free),
+  // [5 + wg] dW1 GEMM done (XD free)
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + PM::BARS);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + PM::BARS + 56);
   const net3 net = a.net;
   const learner_rows &L = a.rows;
   const tid_t t = thread_id();
-  const int wg = t.warp >> 2;  // warp-uniform
+  const bool issuer = t.warp >= 8;                    // warp-uniform
+  const int wg = issuer ? t.warp - 8 : t.warp >> 2;   // pipeline index
   const uint32_t sbase = umma::smem_u32(smem);
+  const long long clk_entry = clock64();
 
   if (t.warp == 0)
     umma::tmem_alloc(tmem_slot, 512);
   if (threadIdx.x == 0) {
-    umma::mbar_init(bars + 0, 1);
-    umma::mbar_init(bars + 1, 1);
-    umma::mbar_init(bars + 2, 1);
+    for (int q = 0; q < 7; ++q)
+      umma::mbar_init(bars + q, 1);
     umma::fence_mbar_init();
   }
   build_image2<D0, D1, D2, NOUT>(a.params, net, smem);
   zero_bytes(smem + PM::DH1_HI, PM::BARS - PM::DH1_HI);
   __syncthreads();
   // ones column (col D0) of both XD panels: [dH1|dH2]^T . 1 = bias gradients for free
-  *reinterpret_cast<uint16_t *>(smem + PM::WG0 + wg * PM::WG_BYTES + PM::XD + umma::panel_off(t.row, D0)) = 0x3F80;
+  if (!issuer)
+    *reinterpret_cast<uint16_t *>(smem + PM::WG0 + wg * PM::WG_BYTES + PM::XD + umma::panel_off(t.row, D0)) = 0x3F80;
   sync_after_smem_writes();
   const uint32_t tmem = *tmem_slot;
 
-  // this CTA's tiles: blockIdx.x + j * gridDim.x, j < nt; warpgroup wg takes j = wg, wg + 2, ...
+  // this CTA's tiles: blockIdx.x + j * gridDim.x, j < nt; pipeline wg takes j = wg, wg + 2, ...
   const int nt = (int)blockIdx.x < a.n_tiles ? (a.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   uint8_t *wsm = smem + PM::WG0 + wg * PM::WG_BYTES;
   const uint32_t wbase = sbase + PM::WG0 + wg * PM::WG_BYTES;
   const uint32_t tm = tmem + 256u * wg;
   const uint32_t dh1_lbo = PM::WG0 + wg * PM::WG_BYTES + PM::H2_HI - PM::DH1_HI;  // dH1 panel -> own dH2 panel
-  uint64_t *bar = bars + wg;
-  uint32_t phase = 0;
-  auto wait_mma = [&]() {
-    umma::mbar_wait(bar, phase);
-    phase ^= 1;
-    umma::fence_after_sync();
-  };
+  uint64_t *bar = bars + wg, *bar_dw2 = bars + 3 + wg, *bar_dw1 = bars + 5 + wg;
+  uint32_t rp = 0;  // parity of the operands-ready barrier
 
   long long *clk = (a.clk && blockIdx.x == 0 && threadIdx.x == 96) ? a.clk : nullptr;
   int clk_n = 0;
-#define STAMP() do { if (clk && clk_n < 112) clk[clk_n++] = clock64(); } while (0)
+#define STAMP() do { if (clk && clk_n < 104) clk[clk_n++] = clock64(); } while (0)
+  if (clk)
+    clk[104] = clk_entry, clk[105] = clock64();
 
   float db3[NOUT];
 #pragma unroll
-  for (int j = 0; j < NOUT; ++j)
-    db3[j] = 0.f;
-  bool first = true;
-  row_state<NOUT> xr;
-  if (wg < nt) {
-    load_row_state<NOUT>(L, blockIdx.x + wg * gridDim.x, t.row, xr);
-    encode_row<NOUT>(wsm + PM::XD, t.row, xr, L.inv_w, L.inv_h);
-  }
-  wg_sync_after_smem_writes(wg);
+  for (int q = 0; q < NOUT; ++q)
+    db3[q] = 0.f;
 
-  for (int j = wg; j < nt; j += 2) {
-    const int tile = blockIdx.x + j * gridDim.x;
-    STAMP();
-    // ---- layer 1 issue first, then the global loads that are consumed later
-    if (wg_mma_thread(t)) {
-      issue_gemm<D0 / 16, false, false, false, true>(tm + P2_ACC0, wbase + PM::XD, 0, sbase + PM::W1P,
-                                                     sbase + PM::W1P + 64, ID<D1>::FK_FK, false);
-      umma::commit(bar);
+  if (issuer) {
+    // ================= MMA issuer of pipeline wg: one GEMM (group) per operands-ready hand-over
+    bool first = true;
+    if (wg < nt) {
+      ready_sync(wg, rp);  // X0 of the first tile staged in the H1_LO panel
+      if (umma::elect_one()) {
+        issue_gemm<D0 / 16, false, false, false, true>(tm + P2_ACC0, wbase + PM::H1_LO, 0, sbase + PM::W1P,
+                                                       sbase + PM::W1P + 64, ID<D1>::FK_FK, false);
+        umma::commit(bar);
+      }
+      __syncwarp();
     }
-    const int tt = t.row / L.E, e = t.row % L.E;
-    const int i = tile * L.E + e;
-    const bool valid = tt < L.T && i < L.n;
-    const size_t k = (size_t)tt * L.n + i;
-    int act = 0;
-    float A = 0.f;
-    float4 po[NOUT / 4];
-#pragma unroll
-    for (int q = 0; q < NOUT / 4; ++q)
-      po[q] = make_float4(1.f, 1.f, 1.f, 1.f);
-    if (valid) {
-      act = L.rec_action[k];
-      A = a.adv[k];
-      const float4 *pr = reinterpret_cast<const float4 *>(a.p_old + k * NOUT);
+    for (int j = wg; j < nt; j += 2) {
+      ready_sync(wg, rp);  // H1
+      if (umma::elect_one()) {
+        issue_gemm<D1 / 16, false, false, true, true>(tm + P2_ACC1, wbase + PM::H1_HI, wbase + PM::H1_LO,
+                                                      sbase + PM::W2_HI, sbase + PM::W2_LO, ID<D2>::FK_FK, false);
+        umma::commit(bar);
+      }
+      __syncwarp();
+      ready_sync(wg, rp);  // H2; head: columns 8..15 of the result repeat 0..7 (stacked B operand), unused
+      if (umma::elect_one()) {
+        issue_gemm<D2 / 16, false, false, true, true>(tm + P2_ACC0, wbase + PM::H2_HI, wbase + PM::H2_LO,
+                                                      sbase + PM::W3A, sbase + PM::W3B, ID<16>::FK_FK, false);
+        umma::commit(bar);
+      }
+      __syncwarp();
+      ready_sync(wg, rp);  // dY
+      // dW3^T += H2^T . [dY_hi | dY_lo] (M = 64, N = 16) first: the dH2 epilogue overwrites H2;
+      // dH2 = [dY_hi | dY_lo] . [hi(W3); hi(W3)] + [dY_hi | dY_lo] . [lo(W3); 0]
+      if (umma::elect_one()) {
+        issue_gemm<8, true, true, true, false>(tm + P2_DC, wbase + PM::H2_HI, wbase + PM::H2_LO,
+                                               wbase + PM::XD + PM::DY_OFF, 0, ID<16>::FM_BM_64, !first);
+        issue_gemm<1, false, true, false, true>(tm + P2_ACC0, wbase + PM::XD + PM::DY_OFF, 0, sbase + PM::W3A,
+                                                sbase + PM::W3B, ID<D2>::BK_FM, false);
+        umma::commit(bar);
+      }
+      __syncwarp();
+      ready_sync(wg, rp);  // dH2 (in the H2 slot)
+      // dH1 = dH2 . W2; dW2 += dH2^T . H1 (M = 64) runs behind the dH1 epilogue
+      if (umma::elect_one()) {
+        issue_gemm<D2 / 16, false, true, true, true>(tm + P2_ACC1, wbase + PM::H2_HI, wbase + PM::H2_LO,
+                                                     sbase + PM::W2_HI, sbase + PM::W2_LO, ID<D1>::BK_FM, false);
+        umma::commit(bar);
+        issue_gemm<8, true, true, true, true>(tm + P2_DA, wbase + PM::H2_HI, wbase + PM::H2_LO, wbase + PM::H1_HI,
+                                              wbase + PM::H1_LO, ID<D1>::BM_FM_64, !first);
+        umma::commit(bar_dw2);
+      }
+      __syncwarp();
+      ready_sync(wg, rp);  // dH1 (shared slot) and the next tile's X0 (H1_LO panel)
+      // layer 1 of the NEXT tile goes first: the in-order pipe would otherwise put this tile's dW1
+      // GEMM on the next tile's critical path; dW1 runs behind the next tile's first epilogue.
+      //   DB[128 x D0+16] += [dH1|dH2]^T . [X0|1]   rows 0.. = [dW1 | db1], rows 64.. col D0 = db2
+      if (umma::elect_one()) {
+        if (j + 2 < nt) {
+          issue_gemm<D0 / 16, false, false, false, true>(tm + P2_ACC0, wbase + PM::H1_LO, 0, sbase + PM::W1P,
+                                                         sbase + PM::W1P + 64, ID<D1>::FK_FK, false);
+          umma::commit(bar);
+        }
+        issue_gemm_mn_lbo<8>(tm + P2_DB, sbase + PM::DH1_HI, sbase + PM::DH1_LO, dh1_lbo, wbase + PM::XD,
+                             ID<D0 + 16>::BM_FM, !first);
+        umma::commit(bar_dw1);
+        umma::commit(bars + 2);
+      }
+      __syncwarp();
+      first = false;
+    }
+  } else {
+    // ================= epilogue threads of pipeline wg: thread = one row of the tile
+    uint32_t phase = 0, phase_dw2 = 0, phase_dw1 = 0;
+    auto wait_mma = [&]() {
+      umma::mbar_wait(bar, phase);
+      phase ^= 1;
+      umma::fence_after_sync();
+    };
+    bool first = true;
+    row_state<NOUT> xr, xn;  // raw state of this tile / of the next tile
+    // The observations of a tile are encoded twice: into the (dead) H1_LO panel for the layer-1
+    // GEMM, so that the tile can start while the previous tile's dW1 GEMM still reads its XD panel,
+    // and, behind the layer-2 GEMM, into the XD panel for this tile's own dW1 GEMM.
+    if (wg < nt) {
+      load_row_state<NOUT>(L, blockIdx.x + wg * gridDim.x, t.row, xr);
+      encode_row<NOUT>(wsm + PM::H1_LO, t.row, xr, L.inv_w, L.inv_h);
+      ready_arrive(wg, rp);
+    }
+    for (int j = wg; j < nt; j += 2) {
+      const int tile = blockIdx.x + j * gridDim.x;
+      STAMP();
+      // global loads that are consumed later: row data for the head, the next tile's state
+      const int tt = t.row / L.E, e = t.row % L.E;
+      const int i = tile * L.E + e;
+      const bool valid = tt < L.T && i < L.n;
+      const size_t k = (size_t)tt * L.n + i;
+      int act = 0;
+      float A = 0.f;
+      float4 po[NOUT / 4];
 #pragma unroll
       for (int q = 0; q < NOUT / 4; ++q)
-        po[q] = pr[q];
-    }
-    const bool has_next = j + 2 < nt;
-    if (has_next)
-      load_row_state<NOUT>(L, tile + 2 * gridDim.x, t.row, xr);
-    wait_mma();
-    STAMP();
-    uint32_t mask1[2], mask2[2];
-    epi2_fwd<D1>(tm + P2_ACC0, t, fl + PM::F_B1, wsm + PM::H1_HI, wsm + PM::H1_LO, mask1);
-    wg_sync_after_smem_writes(wg);
-    STAMP();
-    if (wg_mma_thread(t)) {
-      issue_gemm<D1 / 16, false, false, true, true>(tm + P2_ACC1, wbase + PM::H1_HI, wbase + PM::H1_LO,
-                                                    sbase + PM::W2_HI, sbase + PM::W2_LO, ID<D2>::FK_FK, false);
-      umma::commit(bar);
-    }
-    wait_mma();
-    STAMP();
-    epi2_fwd<D2>(tm + P2_ACC1, t, fl + PM::F_B2, wsm + PM::H2_HI, wsm + PM::H2_LO, mask2);
-    wg_sync_after_smem_writes(wg);
-    STAMP();
-    // ---- layer 3 (head): columns 8..15 of the result repeat 0..7 (stacked B operand), unused
-    if (wg_mma_thread(t)) {
-      issue_gemm<D2 / 16, false, false, true, true>(tm + P2_ACC0, wbase + PM::H2_HI, wbase + PM::H2_LO,
-                                                    sbase + PM::W3A, sbase + PM::W3B, ID<16>::FK_FK, false);
-      umma::commit(bar);
-    }
-    wait_mma();
-    STAMP();
-    // ---- head epilogue: softmax, loss gradient, softmax backward -> dY = [hi | lo] in the XD panel
-    {
-      float v[8];
-      tmem_load<8>(tm + P2_ACC0 + t.lane_base, v);
-      float dl[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q)
-        dl[q] = 0.f;
+        po[q] = make_float4(1.f, 1.f, 1.f, 1.f);
       if (valid) {
-        const float *b3 = fl + PM::F_B3;
-        float p[NOUT], s = 0.f;
+        act = L.rec_action[k];
+        A = a.adv[k];
+        const float4 *pr = reinterpret_cast<const float4 *>(a.p_old + k * NOUT);
 #pragma unroll
-        for (int q = 0; q < NOUT; ++q) {
-          p[q] = expf(v[q] + b3[q]);  // no max subtraction (nn.h:382-392)
-          s += p[q];
-        }
-        const float inv_s = 1.f / s;
+        for (int q = 0; q < NOUT / 4; ++q)
+          po[q] = pr[q];
+      }
+      const bool has_next = j + 2 < nt;
+      if (has_next)
+        load_row_state<NOUT>(L, tile + 2 * gridDim.x, t.row, xn);
+      wait_mma();  // layer 1
+      STAMP();
+      epi2_fwd<D1>(tm + P2_ACC0, t, fl + PM::F_B1, wsm + PM::H1_HI, wsm + PM::H1_LO);
+      ready_arrive(wg, rp);
+      if (!first) {  // the previous tile's dW1 GEMM (XD, dH2 in the H2 slot) ran behind this epilogue
+        umma::mbar_wait(bar_dw1, phase_dw1);
+        phase_dw1 ^= 1;
+      }
+      encode_row<NOUT>(wsm + PM::XD, t.row, xr, L.inv_w, L.inv_h);
+      STAMP();
+      wait_mma();  // layer 2
+      STAMP();
+      epi2_fwd<D2>(tm + P2_ACC1, t, fl + PM::F_B2, wsm + PM::H2_HI, wsm + PM::H2_LO);
+      ready_arrive(wg, rp);
+      STAMP();
+      wait_mma();  // layer 3
+      STAMP();
+      // ---- head epilogue: softmax, loss gradient, softmax backward -> dY = [hi | lo] in the XD panel
+      {
+        float v[8];
+        tmem_load<8>(tm + P2_ACC0 + t.lane_base, v);
+        float dl[8];
 #pragma unroll
-        for (int q = 0; q < NOUT; ++q)
-          p[q] = p[q] * inv_s;
-        float g[NOUT];
-        if (a.loss_kind == DFRL_LOSS_CLIPPED) {
-          float pa = 0.f, pold = 1.f;
-          const float *pof = reinterpret_cast<const float *>(po);
+        for (int q = 0; q < 8; ++q)
+          dl[q] = 0.f;
+        if (valid) {
+          const float *b3 = fl + PM::F_B3;
+          float p[NOUT], s = 0.f;
 #pragma unroll
           for (int q = 0; q < NOUT; ++q) {
-            pa = (q == act) ? p[q] : pa;
-            pold = (q == act) ? pof[q] : pold;
+            p[q] = expf(v[q] + b3[q]);  // no max subtraction (nn.h:382-392)
+            s += p[q];
           }
-          float gc = clipped_grad(pa, pold, A);
+          const float inv_s = 1.f / s;
 #pragma unroll
           for (int q = 0; q < NOUT; ++q)
-            g[q] = (q == act) ? gc : 0.f;
-        } else {
+            p[q] = p[q] * inv_s;
+          float g[NOUT];
+          if (a.loss_kind == DFRL_LOSS_CLIPPED) {
+            float pa = 0.f, pold = 1.f;
+            const float *pof = reinterpret_cast<const float *>(po);
+#pragma unroll
+            for (int q = 0; q < NOUT; ++q) {
+              pa = (q == act) ? p[q] : pa;
+              pold = (q == act) ? pof[q] : pold;
+            }
+            float gc = clipped_grad(pa, pold, A);
+#pragma unroll
+            for (int q = 0; q < NOUT; ++q)
+              g[q] = (q == act) ? gc : 0.f;
+          } else {
+#pragma unroll
+            for (int q = 0; q < NOUT; ++q)
+              g[q] = p[q] * A - (q == act ? A : 0.f);
+          }
+          if (a.head_bwd == HEAD_JACOBIAN) {
+            float dot = 0.f;
+#pragma unroll
+            for (int q = 0; q < NOUT; ++q)
+              dot = fmaf(p[q], g[q], dot);
+#pragma unroll
+            for (int q = 0; q < NOUT; ++q)
+              dl[q] = p[q] * (g[q] - dot);
+          } else {
+#pragma unroll
+            for (int q = 0; q < NOUT; ++q)
+              dl[q] = g[q];
+          }
 #pragma unroll
           for (int q = 0; q < NOUT; ++q)
-            g[q] = p[q] * A - (q == act ? A : 0.f);
+            db3[q] += dl[q];
         }
-        if (a.head_bwd == HEAD_JACOBIAN) {
-          float dot = 0.f;
-#pragma unroll
-          for (int q = 0; q < NOUT; ++q)
-            dot = fmaf(p[q], g[q], dot);
-#pragma unroll
-          for (int q = 0; q < NOUT; ++q)
-            dl[q] = p[q] * (g[q] - dot);
-        } else {
-#pragma unroll
-          for (int q = 0; q < NOUT; ++q)
-            dl[q] = g[q];
-        }
-#pragma unroll
-        for (int q = 0; q < NOUT; ++q)
-          db3[q] += dl[q];
+        uint4 h, l;
+        split8<false>(dl, h, l);
+        *reinterpret_cast<uint4 *>(wsm + PM::XD + umma::panel_chunk_off(t.row, 6)) = h;
+        *reinterpret_cast<uint4 *>(wsm + PM::XD + umma::panel_chunk_off(t.row, 7)) = l;
       }
-      uint4 h, l;
-      split8<false>(dl, h, l);
-      *reinterpret_cast<uint4 *>(wsm + PM::XD + umma::panel_chunk_off(t.row, 6)) = h;
-      *reinterpret_cast<uint4 *>(wsm + PM::XD + umma::panel_chunk_off(t.row, 7)) = l;
+      ready_arrive(wg, rp);
+      STAMP();
+      wait_mma();  // dW3, dH2
+      STAMP();
+      epi2_bwd<D2>(tm + P2_ACC0, t, wsm + PM::H2_HI, wsm + PM::H2_HI, wsm + PM::H2_LO);
+      ready_arrive(wg, rp);
+      STAMP();
+      wait_mma();  // dH1
+      // the shared dH1 slot: free once the previous tile of this CTA (the other pipeline's) has
+      // finished its dW1 GEMM (completion j - 1 of bars[2])
+      if (j > 0)
+        umma::mbar_wait(bars + 2, (uint32_t)(j - 1) & 1u);
+      STAMP();
+      epi2_bwd<D1>(tm + P2_ACC1, t, wsm + PM::H1_HI, smem + PM::DH1_HI, smem + PM::DH1_LO);
+      STAMP();
+      umma::mbar_wait(bar_dw2, phase_dw2);  // H1 is free (the dW2 GEMM ran behind the dH1 epilogue)
+      phase_dw2 ^= 1;
+      STAMP();
+      if (has_next) {
+        encode_row<NOUT>(wsm + PM::H1_LO, t.row, xn, L.inv_w, L.inv_h);
+        xr = xn;
+      }
+      ready_arrive(wg, rp);
+      STAMP();
+      first = false;
     }
-    wg_sync_after_smem_writes(wg);
-    STAMP();
-    // ---- dW3^T += H2^T . [dY_hi | dY_lo] (M = 64, N = 16) first: the dH2 epilogue overwrites H2;
-    // dH2 = [dY_hi | dY_lo] . [hi(W3); hi(W3)] + [dY_hi | dY_lo] . [lo(W3); 0]
-    if (wg_mma_thread(t)) {
-      issue_gemm<8, true, true, true, false>(tm + P2_DC, wbase + PM::H2_HI, wbase + PM::H2_LO,
-                                             wbase + PM::XD + PM::DY_OFF, 0, ID<16>::FM_BM_64, !first);
-      issue_gemm<1, false, true, false, true>(tm + P2_ACC0, wbase + PM::XD + PM::DY_OFF, 0, sbase + PM::W3A,
-                                              sbase + PM::W3B, ID<D2>::BK_FM, false);
-      umma::commit(bar);
-    }
-    wait_mma();
-    STAMP();
-    epi2_bwd<D2>(tm + P2_ACC0, t, mask2, wsm + PM::H2_HI, wsm + PM::H2_LO);
-    wg_sync_after_smem_writes(wg);
-    STAMP();
-    // ---- dH1 = dH2 . W2; dW2 += dH2^T . H1 (M = 64) runs behind the dH1 epilogue
-    if (wg_mma_thread(t)) {
-      issue_gemm<D2 / 16, false, true, true, true>(tm + P2_ACC1, wbase + PM::H2_HI, wbase + PM::H2_LO,
-                                                   sbase + PM::W2_HI, sbase + PM::W2_LO, ID<D1>::BK_FM, false);
-      umma::commit(bar);
-      issue_gemm<8, true, true, true, true>(tm + P2_DA, wbase + PM::H2_HI, wbase + PM::H2_LO, wbase + PM::H1_HI,
-                                            wbase + PM::H1_LO, ID<D1>::BM_FM_64, !first);
-    }
-    wait_mma();
-    // the shared dH1 slot: free once the previous tile of this CTA (the other warpgroup's) has
-    // finished its dW1 GEMM (completion j - 1 of bars[2])
-    if (j > 0) {
-      umma::mbar_wait(bars + 2, (uint32_t)(j - 1) & 1u);
+    if (!first) {  // the last tile's dW1 GEMM
+      umma::mbar_wait(bar_dw1, phase_dw1);
       umma::fence_after_sync();
     }
-    STAMP();
-    epi2_bwd<D1>(tm + P2_ACC1, t, mask1, smem + PM::DH1_HI, smem + PM::DH1_LO);
-    wg_sync_after_smem_writes(wg);
-    STAMP();
-    //   DB[128 x D0+16] += [dH1|dH2]^T . [X0|1]   rows 0.. = [dW1 | db1], rows 64.. col D0 = db2
-    if (wg_mma_thread(t)) {
-      issue_gemm_mn_lbo<8>(tm + P2_DB, sbase + PM::DH1_HI, sbase + PM::DH1_LO, dh1_lbo, wbase + PM::XD,
-                           ID<D0 + 16>::BM_FM, !first);
-      umma::commit(bar);
-      umma::commit(bars + 2);
-    }
-    wait_mma();  // X0 (dW1), H1 (dW2) and the accumulators are free again
-    STAMP();
-    if (has_next)
-      encode_row<NOUT>(wsm + PM::XD, t.row, xr, L.inv_w, L.inv_h);
-    wg_sync_after_smem_writes(wg);
-    STAMP();
-    first = false;
   }
 #undef STAMP
+  if (clk)
+    clk[106] = clock64();
 
   // ---- drain: partial gradient of this CTA (warpgroup 0's sums + warpgroup 1's) -> global
   umma::fence_before_sync();
@@ -1707,7 +1773,7 @@ __global__ void __launch_bounds__(256, 1) fused_policy_step2_kernel(policy_step_
       part[q] = 0.f;
   } else {
     // dW2[n][k]: DA (M = 64) row n = TMEM lane 32 (n / 16) + n % 16, col k
-    {
+    if (!issuer) {
       constexpr int DC = D1 / 2;
       float v[DC], w[DC];
       tmem_load<DC>(tmem + P2_DA + t.lane_base + t.wg * DC, v);
@@ -1724,7 +1790,7 @@ __global__ void __launch_bounds__(256, 1) fused_policy_step2_kernel(policy_step_
           part[net.o_w2 + nrow * D1 + t.wg * DC + q] = v[q];
     }
     // dW1[n][k] + db1[n]: DB row n, cols 0..D0-1 and D0; db2[n]: DB row 64 + n, col D0
-    {
+    if (!issuer) {
       constexpr int DC = (D0 + 16) / 2;
       float v[DC], w[DC];
       tmem_load<DC>(tmem + P2_DB + t.lane_base + t.wg * DC, v);
@@ -1748,7 +1814,7 @@ __global__ void __launch_bounds__(256, 1) fused_policy_step2_kernel(policy_step_
       }
     }
     // dW3[n][k] = DC (M = 64) row k, cols n (H2^T dY_hi) and 8 + n (H2^T dY_lo)
-    if (t.wg == 0) {
+    if (!issuer && t.wg == 0) {
       float v[16], w[16];
       tmem_load<16>(tmem + P2_DC + t.lane_base, v);
       if (two) {
@@ -1763,21 +1829,30 @@ __global__ void __launch_bounds__(256, 1) fused_policy_step2_kernel(policy_step_
         for (int q = 0; q < NOUT; ++q)
           part[net.o_w3 + q * D2 + krow] = v[q] + v[8 + q];
     }
-    // db3: per-thread partial sums -> fixed-order block sum (scratch = warpgroup 0's H1 panels)
+    // db3: fixed-order tree inside each warp, then the 8 warps in order (scratch = warpgroup 0's H1)
     float *red = reinterpret_cast<float *>(smem + PM::WG0 + PM::H1_HI);
 #pragma unroll
-    for (int q = 0; q < NOUT; ++q)
-      red[threadIdx.x * 8 + q] = db3[q];
+    for (int q = 0; q < NOUT; ++q) {
+      float s = db3[q];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (t.lane == 0 && !issuer)
+        red[t.warp * 8 + q] = s;
+    }
     __syncthreads();
     if (threadIdx.x < NOUT) {
       float s = 0.f;
-      for (int r = 0; r < 2 * TILE; ++r)
-        s += red[r * 8 + threadIdx.x];
+#pragma unroll
+      for (int w = 0; w < 8; ++w)
+        s += red[w * 8 + threadIdx.x];
       part[net.o_b3 + threadIdx.x] = s;
     }
   }
   umma::fence_before_sync();
   __syncthreads();
+  if (clk)
+    clk[107] = clock64();
   if (t.warp == 0)
     umma::tmem_dealloc(tmem, 512);
 }
@@ -2122,7 +2197,7 @@ int launch_policy_step(dfrl_ctx *ctx, const policy_step_args &a, int ctas) {
     constexpr int smem2 = pmap<D1, D2>::TOTAL + 1024;
     static bool attr2 = false;
     DFRL_TRY(set_smem_once(fused_policy_step2_kernel<D0, D1, D2, NOUT>, smem2, &attr2));
-    DFRL_LAUNCH(ctx, (fused_policy_step2_kernel<D0, D1, D2, NOUT>), ctas, 256, smem2, a);
+    DFRL_LAUNCH(ctx, (fused_policy_step2_kernel<D0, D1, D2, NOUT>), ctas, 320, smem2, a);
     return DFRL_OK;
   }
   constexpr int smem = smem_map<D1, D2>::TOTAL + 1024;

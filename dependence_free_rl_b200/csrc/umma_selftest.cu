@@ -297,3 +297,67 @@ extern "C" int dfrl_umma_selftest(dfrl_ctx *ctx, int variant, int k, int n, floa
   *rel_err = (float)(max_err / (max_ref + 1e-30));
   return DFRL_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Pipe cost of one tcgen05.mma (kind::f16, bf16, K = 16) per operand form: `count` instructions
+// issued back to back by one lane over zeroed panels, one commit, SM cycles from the first issue
+// to the mbarrier flip. Two counts give the per-instruction slope.
+namespace {
+__global__ void __launch_bounds__(128) umma_microbench_kernel(int M, int N, int a_mn, int b_mn, int count,
+                                                              long long *out) {
+  extern __shared__ __align__(1024) uint8_t mb_raw[];
+  uint8_t *smem = mb_raw + ((1024u - (umma::smem_u32(mb_raw) & 1023u)) & 1023u);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  for (uint32_t o = threadIdx.x * 16; o < 8 * 16384; o += blockDim.x * 16)
+    *reinterpret_cast<uint4 *>(smem + o) = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x < 32)
+    umma::tmem_alloc(&slot, 256);
+  if (threadIdx.x == 0) {
+    umma::mbar_init(&bar, 1);
+    umma::fence_mbar_init();
+  }
+  umma::fence_proxy_async();
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem = slot, sb = umma::smem_u32(smem);
+  const uint32_t idesc = umma::make_idesc_bf16(M, N, a_mn, b_mn);
+  long long t0 = 0;
+  if (threadIdx.x < 32 && umma::elect_one()) {
+    // A: panels 0..3 (MN-major M = 128 spans two panels, LBO = 16 KB), B: panels 4..7
+    const uint32_t a_lbo = a_mn ? 16384u : 16u, b_lbo = b_mn ? 16384u : 16u;
+    const uint32_t a_step = a_mn ? 2048u : 32u, b_step = b_mn ? 2048u : 32u;
+    t0 = clock64();
+    for (int i = 0; i < count; ++i) {
+      const uint32_t k = (uint32_t)(i & 3);
+      uint64_t ad = umma::make_desc_sw128(sb + k * a_step, a_lbo, 1024);
+      uint64_t bd = umma::make_desc_sw128(sb + 4 * 16384 + k * b_step, b_lbo, 1024);
+      umma::mma_bf16(tmem, ad, bd, idesc, i > 0);
+    }
+    umma::commit(&bar);
+    out[1] = clock64() - t0;  // issue time
+  }
+  umma::mbar_wait(&bar, 0);
+  if (threadIdx.x < 32 && t0 != 0)
+    out[0] = clock64() - t0;
+  umma::fence_before_sync();
+  __syncthreads();
+  if (threadIdx.x < 32)
+    umma::tmem_dealloc(tmem, 256);
+}
+}  // namespace
+
+extern "C" int dfrl_umma_microbench(dfrl_ctx *ctx, int M, int N, int a_mn, int b_mn, int count, long long *cycles2) {
+  DFRL_CHECK(ctx && cycles2 && (M == 64 || M == 128) && N >= 8 && N <= 256 && N % 8 == 0 && count > 0, "bad argument");
+  long long *d;
+  DFRL_CUDA(cudaMalloc(&d, 16));
+  DFRL_CUDA(cudaMemset(d, 0, 16));
+  const int smem = 8 * 16384 + 1024;
+  DFRL_CUDA(cudaFuncSetAttribute(umma_microbench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  DFRL_LAUNCH(ctx, umma_microbench_kernel, 1, 128, smem, M, N, a_mn, b_mn, count, d);
+  DFRL_CUDA(cudaStreamSynchronize(ctx->stream));
+  DFRL_CUDA(cudaMemcpy(cycles2, d, 16, cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  return DFRL_OK;
+}
