@@ -1308,11 +1308,10 @@ struct pmap {
 // TMEM columns of one warpgroup (base = 256 * wg)
 constexpr uint32_t P2_ACC0 = 0, P2_ACC1 = 64, P2_DA = 128, P2_DB = 192, P2_DC = 240;
 
-template <int D0, int D1, int D2, int NOUT>
-__device__ void build_image2(const float *__restrict__ params, const net3 &net, uint8_t *smem) {
-  using PM = pmap<D1, D2>;
-  const float *W1 = params + net.o_w1, *W2 = params + net.o_w2, *W3 = params + net.o_w3;
-  static_assert(D0 == 32 && NOUT == 8, "packed W1 / stacked W3 panels assume 32 inputs, 8 outputs");
+// fp32 W1 [D1][32] -> ONE panel: hi(W1) in bytes 0..63 of a row, lo(W1) in bytes 64..127.
+template <int D1>
+__device__ void stage_w1_packed(const float *__restrict__ W1, uint8_t *panel) {
+  constexpr int D0 = 32;
   for (int c = threadIdx.x; c < D1 * 4; c += blockDim.x) {
     int row = c >> 2, chunk = c & 3;
     float x[8];
@@ -1327,9 +1326,17 @@ __device__ void build_image2(const float *__restrict__ params, const net3 &net, 
     }
     uint4 h, l;
     split8<false>(x, h, l);
-    *reinterpret_cast<uint4 *>(smem + PM::W1P + umma::panel_chunk_off(row, chunk)) = h;
-    *reinterpret_cast<uint4 *>(smem + PM::W1P + umma::panel_chunk_off(row, 4 + chunk)) = l;
+    *reinterpret_cast<uint4 *>(panel + umma::panel_chunk_off(row, chunk)) = h;
+    *reinterpret_cast<uint4 *>(panel + umma::panel_chunk_off(row, 4 + chunk)) = l;
   }
+}
+
+template <int D0, int D1, int D2, int NOUT>
+__device__ void build_image2(const float *__restrict__ params, const net3 &net, uint8_t *smem) {
+  using PM = pmap<D1, D2>;
+  const float *W1 = params + net.o_w1, *W2 = params + net.o_w2, *W3 = params + net.o_w3;
+  static_assert(D0 == 32 && NOUT == 8, "packed W1 / stacked W3 panels assume 32 inputs, 8 outputs");
+  stage_w1_packed<D1>(W1, smem + PM::W1P);
   stage_weight_f16(W2, D2, D1, D2, 1.f, smem + PM::W2_HI, smem + PM::W2_LO);
   for (int c = threadIdx.x; c < 16 * 8; c += blockDim.x) {
     int row = c >> 3, chunk = c & 7;
@@ -1857,6 +1864,483 @@ __global__ void __launch_bounds__(320, 1) fused_policy_step2_kernel(policy_step_
     umma::tmem_dealloc(tmem, 512);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Critic step (update_value_model, policy_gradient.h:196-218, minus the optimizer update) and GAE
+// (calculate_advantage, 220-281) with the structure of fused_policy_step2_kernel: two tile
+// pipelines per CTA, one epilogue thread per row, one MMA-issuing warp per pipeline.
+// Per tile: V(end rows) [layer 1, layer 2, value head in fp32 registers], V(start rows), exchange
+// of the values inside the tile, then
+//   CRITIC_STEP: targets r + gamma V_next (unmasked, quirk 6), dY = V - target, dH2 = dY w3 . relu'
+//                (rank 1, registers), dW3 / db3 (registers), dH1 GEMM, dW2 (M = 64) and
+//                [dW1|db1|db2] GEMMs accumulated in TMEM;
+//   CRITIC_GAE:  thread e < E walks its environment backwards.
+// Shared memory per pipeline: XS (start observations | 1), H1 hi/lo, dH2 hi/lo; the end-row
+// observations are staged in the dead H1_LO panel; dH1 in one slot shared by both pipelines.
+enum { CRITIC_STEP = 0, CRITIC_GAE = 1 };
+template <int D1, int D2>
+struct cmap {
+  static constexpr uint32_t W1P = 0;
+  static constexpr uint32_t W2_HI = W1P + D1 * 128, W2_LO = W2_HI + D2 * 128;
+  static constexpr uint32_t FLOATS = W2_LO + D2 * 128;  // b1[D1] b2[D2] w3[64] b3[4]
+  static constexpr int F_B1 = 0, F_B2 = D1, F_W3 = D1 + D2, F_B3 = D1 + D2 + 64, N_FLOATS = D1 + D2 + 68;
+  static constexpr uint32_t SCR = FLOATS + N_FLOATS * 4;  // per pipeline: ve[128], vs[128]
+  static constexpr uint32_t DH1_HI = (SCR + 2 * 2 * TILE * 4 + 1023) / 1024 * 1024;  // shared slot
+  static constexpr uint32_t DH1_LO = DH1_HI + PANEL;
+  static constexpr uint32_t WG0 = DH1_LO + PANEL;
+  static constexpr uint32_t XS = 0, H1_HI = PANEL, H1_LO = 2 * PANEL, G2_HI = 3 * PANEL, G2_LO = 4 * PANEL;
+  static constexpr uint32_t WG_BYTES = 5 * PANEL;
+  static constexpr uint32_t BARS = WG0 + 2 * WG_BYTES;
+  static constexpr uint32_t TOTAL = BARS + 128;
+  static_assert((D1 * 128) % 1024 == 0 && (D2 * 128) % 1024 == 0, "panel alignment");
+  static_assert(TOTAL + 1024 <= 232448, "exceeds the 227 KB shared memory of an SM");
+};
+constexpr uint32_t C2_ACC0 = 0, C2_ACC1 = 64, C2_DA = 128, C2_DB = 192;  // TMEM columns of a pipeline
+
+// 2B + 2 int8 planes, four per register
+template <int B>
+struct packed_state {
+  uint32_t w[(2 * B + 2 + 3) / 4];
+};
+template <int B>
+__device__ __forceinline__ void pack_state(const row_state<B> &x, packed_state<B> &p) {
+#pragma unroll
+  for (int q4 = 0; q4 < (2 * B + 2 + 3) / 4; ++q4) {
+    uint32_t w = 0;
+#pragma unroll
+    for (int q = 4 * q4; q < 4 * q4 + 4 && q < 2 * B + 2; ++q)
+      w |= ((uint32_t)x.v[q] & 0xffu) << (8 * (q & 3));
+    p.w[q4] = w;
+  }
+}
+template <int B>
+__device__ __forceinline__ void unpack_state(const packed_state<B> &p, row_state<B> &x) {
+#pragma unroll
+  for (int q = 0; q < 2 * B + 2; ++q)
+    x.v[q] = (int)(int8_t)(p.w[q >> 2] >> (8 * (q & 3)));
+}
+// live env state of a row of the rollout's last step (its end state unless the episode ended)
+template <int B>
+__device__ __forceinline__ void load_live_state(const learner_rows &L, int tile, int row, row_state<B> &x) {
+  constexpr int P = 2 * B + 2;
+  const int tt = row / L.E, e = row % L.E, i = tile * L.E + e;
+  const bool ok = tt == L.T - 1 && i < L.n;
+  const int8_t *src = L.live_state + i;
+#pragma unroll
+  for (int q = 0; q < P; ++q) {
+    x.v[q] = 0;
+    if (ok)
+      x.v[q] = src[(size_t)q * L.stride];
+  }
+}
+// END state of a row: overflowed terminal state when done (bin[a] -= item, item kept:
+// bin_packing.h:54-61), the live state at the rollout's last step, zeros (row unused) otherwise.
+template <int B>
+__device__ __forceinline__ void end_state(const row_state<B> &start, const row_state<B> &live, int done, int act,
+                                          bool last, row_state<B> &out) {
+#pragma unroll
+  for (int q = 0; q < 2 * B + 2; ++q)
+    out.v[q] = done ? start.v[q] : (last ? live.v[q] : 0);
+  if (done) {
+#pragma unroll
+    for (int b = 0; b < B; ++b)
+      if (b == act) {
+        out.v[2 * b] -= start.v[2 * B];
+        out.v[2 * b + 1] -= start.v[2 * B + 1];
+      }
+  }
+}
+// Layer-2 accumulator -> relu(acc + b2) (registers only) -> value head in fp32.
+template <int D2, bool KEEP>
+__device__ __forceinline__ float epi2_value(uint32_t acc, const tid_t &t, const float *__restrict__ b2,
+                                            const float *__restrict__ w3, float b3, float *keep) {
+  constexpr int CH = D2 < 32 ? D2 : 32;
+  float s = 0.f;
+#pragma unroll
+  for (int h = 0; h < D2 / CH; ++h) {
+    float v[CH];
+    tmem_load<CH>(acc + t.lane_base + h * CH, v);
+#pragma unroll
+    for (int j4 = 0; j4 < CH; j4 += 4) {
+      const float4 b = *reinterpret_cast<const float4 *>(b2 + h * CH + j4);
+      const float4 w = *reinterpret_cast<const float4 *>(w3 + h * CH + j4);
+      const float y0 = fmaxf(v[j4] + b.x, 0.f), y1 = fmaxf(v[j4 + 1] + b.y, 0.f);
+      const float y2 = fmaxf(v[j4 + 2] + b.z, 0.f), y3 = fmaxf(v[j4 + 3] + b.w, 0.f);
+      s = fmaf(y0, w.x, s), s = fmaf(y1, w.y, s), s = fmaf(y2, w.z, s), s = fmaf(y3, w.w, s);
+      if (KEEP)
+        keep[h * CH + j4] = y0, keep[h * CH + j4 + 1] = y1, keep[h * CH + j4 + 2] = y2, keep[h * CH + j4 + 3] = y3;
+    }
+  }
+  return s + b3;
+}
+
+template <int D0, int D1, int D2, int MODE>
+__global__ void __launch_bounds__(320, 1) fused_critic2_kernel(critic_args a) {
+  using CM = cmap<D1, D2>;
+  constexpr int NB = 8;  // bins (the fused path covers the 8-bin problem)
+  static_assert(D0 == 4 * NB, "observation width");
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);  // stays a shared-space pointer
+  float *fl = reinterpret_cast<float *>(smem + CM::FLOATS);
+  // mbarriers: [wg] MMA completion on the chain, [2] dH1 slot free, [3 + wg] dW2 GEMM done (H1 free),
+  // [5 + wg] dW1 GEMM done (XS, dH2 free), [7 + wg] layer 1 of the start rows (issued right behind
+  // layer 2 of the end rows: a parity wait cannot tell two outstanding completions of one mbarrier apart)
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + CM::BARS);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + CM::BARS + 120);
+  const net3 net = a.net;
+  const learner_rows &L = a.rows;
+  const tid_t t = thread_id();
+  const bool issuer = t.warp >= 8;                   // warp-uniform
+  const int wg = issuer ? t.warp - 8 : t.warp >> 2;  // pipeline index
+  const uint32_t sbase = umma::smem_u32(smem);
+
+  if (t.warp == 0)
+    umma::tmem_alloc(tmem_slot, 512);
+  if (threadIdx.x == 0) {
+    for (int q = 0; q < 9; ++q)
+      umma::mbar_init(bars + q, 1);
+    umma::fence_mbar_init();
+  }
+  {
+    const float *P = a.params;
+    stage_w1_packed<D1>(P + net.o_w1, smem + CM::W1P);
+    stage_weight_f16(P + net.o_w2, D2, D1, D2, 1.f, smem + CM::W2_HI, smem + CM::W2_LO);
+    for (int i = threadIdx.x; i < D1; i += blockDim.x) fl[CM::F_B1 + i] = P[net.o_b1 + i];
+    for (int i = threadIdx.x; i < D2; i += blockDim.x) fl[CM::F_B2 + i] = P[net.o_b2 + i];
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) fl[CM::F_W3 + i] = i < D2 ? P[net.o_w3 + i] : 0.f;
+    if (threadIdx.x == 0)
+      fl[CM::F_B3] = P[net.o_b3];
+  }
+  zero_bytes(smem + CM::DH1_HI, CM::BARS - CM::DH1_HI);
+  __syncthreads();
+  if (!issuer)  // ones column (col D0) of both XS panels: bias gradients for free
+    *reinterpret_cast<uint16_t *>(smem + CM::WG0 + wg * CM::WG_BYTES + CM::XS + umma::panel_off(t.row, D0)) = 0x3F80;
+  sync_after_smem_writes();
+  const uint32_t tmem = *tmem_slot;
+
+  const int nt = (int)blockIdx.x < a.n_tiles ? (a.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  uint8_t *wsm = smem + CM::WG0 + wg * CM::WG_BYTES;
+  const uint32_t wbase = sbase + CM::WG0 + wg * CM::WG_BYTES;
+  const uint32_t tm = tmem + 256u * wg;
+  const uint32_t dh1_lbo = CM::WG0 + wg * CM::WG_BYTES + CM::G2_HI - CM::DH1_HI;  // dH1 panel -> own dH2 panel
+  uint64_t *bar = bars + wg, *bar_dw2 = bars + 3 + wg, *bar_dw1 = bars + 5 + wg, *bar_l1s = bars + 7 + wg;
+  uint32_t rp = 0;
+  float dw3[MODE == CRITIC_STEP ? D2 : 1];
+#pragma unroll
+  for (int q = 0; q < (MODE == CRITIC_STEP ? D2 : 1); ++q)
+    dw3[q] = 0.f;
+  float db3 = 0.f;
+
+  if (issuer) {
+    // ================= MMA issuer of pipeline wg
+    auto layer1 = [&](uint32_t x0, uint64_t *done_bar) {
+      issue_gemm<D0 / 16, false, false, false, true>(tm + C2_ACC0, x0, 0, sbase + CM::W1P, sbase + CM::W1P + 64,
+                                                     ID<D1>::FK_FK, false);
+      umma::commit(done_bar);
+    };
+    auto layer2 = [&]() {
+      issue_gemm<D1 / 16, false, false, true, true>(tm + C2_ACC1, wbase + CM::H1_HI, wbase + CM::H1_LO,
+                                                    sbase + CM::W2_HI, sbase + CM::W2_LO, ID<D2>::FK_FK, false);
+      umma::commit(bar);
+    };
+    bool first = true;
+    if (wg < nt) {
+      ready_sync(wg, rp);  // end-row observations of the first tile staged in the H1_LO panel
+      if (umma::elect_one())
+        layer1(wbase + CM::H1_LO, bar);
+      __syncwarp();
+    }
+    for (int j = wg; j < nt; j += 2) {
+      ready_sync(wg, rp);  // H1 (end rows)
+      if (umma::elect_one())
+        layer2();
+      __syncwarp();
+      ready_sync(wg, rp);  // start-row observations in the XS panel
+      if (umma::elect_one())
+        layer1(wbase + CM::XS, bar_l1s);
+      __syncwarp();
+      ready_sync(wg, rp);  // H1 (start rows)
+      if (umma::elect_one())
+        layer2();
+      __syncwarp();
+      if (MODE == CRITIC_STEP) {
+        ready_sync(wg, rp);  // dH2
+        // dH1 = dH2 . W2; dW2 += dH2^T . H1 (M = 64) runs behind the dH1 epilogue
+        if (umma::elect_one()) {
+          issue_gemm<D2 / 16, false, true, true, true>(tm + C2_ACC0, wbase + CM::G2_HI, wbase + CM::G2_LO,
+                                                       sbase + CM::W2_HI, sbase + CM::W2_LO, ID<D1>::BK_FM, false);
+          umma::commit(bar);
+          issue_gemm<8, true, true, true, true>(tm + C2_DA, wbase + CM::G2_HI, wbase + CM::G2_LO, wbase + CM::H1_HI,
+                                                wbase + CM::H1_LO, ID<D1>::BM_FM_64, !first);
+          umma::commit(bar_dw2);
+        }
+        __syncwarp();
+      }
+      ready_sync(wg, rp);  // (dH1 in the shared slot and) the next tile's end-row observations
+      if (umma::elect_one()) {
+        if (j + 2 < nt)  // ahead of dW1: see fused_policy_step2_kernel
+          layer1(wbase + CM::H1_LO, bar);
+        if (MODE == CRITIC_STEP) {
+          //   DB[128 x D0+16] += [dH1|dH2]^T . [X0|1]   rows 0.. = [dW1 | db1], rows 64.. col D0 = db2
+          issue_gemm_mn_lbo<8>(tm + C2_DB, sbase + CM::DH1_HI, sbase + CM::DH1_LO, dh1_lbo, wbase + CM::XS,
+                               ID<D0 + 16>::BM_FM, !first);
+          umma::commit(bar_dw1);
+          umma::commit(bars + 2);
+        }
+      }
+      __syncwarp();
+      first = false;
+    }
+  } else {
+    // ================= epilogue threads of pipeline wg: thread = one row of the tile
+    const float *b1 = fl + CM::F_B1, *b2 = fl + CM::F_B2, *w3 = fl + CM::F_W3;
+    const float b3 = fl[CM::F_B3];
+    float *ve = reinterpret_cast<float *>(smem + CM::SCR) + wg * 2 * TILE, *vs = ve + TILE;
+    uint32_t phase = 0, phase_dw2 = 0, phase_dw1 = 0, phase_l1s = 0;
+    auto wait_mma = [&]() {
+      umma::mbar_wait(bar, phase);
+      phase ^= 1;
+      umma::fence_after_sync();
+    };
+    const int tt = t.row / L.E, e = t.row % L.E;
+    const bool last = tt == L.T - 1;
+    bool first = true;
+    packed_state<NB> ps;  // start state of this tile's row
+    int done = 0;
+    {
+      row_state<NB> xs, xl, xe;
+      int act = 0;
+      if (wg < nt) {
+        const int tile0 = blockIdx.x + wg * gridDim.x, i0 = tile0 * L.E + e;
+        load_row_state<NB>(L, tile0, t.row, xs);
+        load_live_state<NB>(L, tile0, t.row, xl);
+        if (tt < L.T && i0 < L.n) {
+          done = L.rec_done[(size_t)tt * L.n + i0];
+          act = L.rec_action[(size_t)tt * L.n + i0];
+        }
+        end_state<NB>(xs, xl, done, act, last, xe);
+        encode_row<NB>(wsm + CM::H1_LO, t.row, xe, L.inv_w, L.inv_h);
+        pack_state<NB>(xs, ps);
+        ready_arrive(wg, rp);
+      }
+    }
+    for (int j = wg; j < nt; j += 2) {
+      const int tile = blockIdx.x + j * gridDim.x;
+      const int i = tile * L.E + e;
+      const bool valid = tt < L.T && i < L.n;
+      const size_t k = (size_t)tt * L.n + i;
+      // the next tile's state: loads now, first use after this tile's first epilogue
+      const bool has_next = j + 2 < nt;
+      row_state<NB> ns, nl;
+      int ndone = 0, nact = 0;
+      if (has_next) {
+        const int ntile = tile + 2 * gridDim.x, ni = ntile * L.E + e;
+        load_row_state<NB>(L, ntile, t.row, ns);
+        load_live_state<NB>(L, ntile, t.row, nl);
+        if (tt < L.T && ni < L.n) {
+          ndone = L.rec_done[(size_t)tt * L.n + ni];
+          nact = L.rec_action[(size_t)tt * L.n + ni];
+        }
+      }
+      // GAE: done flags of the env this thread walks (threads < E)
+      uint32_t dmask = 0;
+      if (MODE == CRITIC_GAE && t.row < L.E && i < L.n)
+        for (int q = 0; q < L.T && q < 32; ++q)
+          dmask |= (uint32_t)(L.rec_done[(size_t)q * L.n + tile * L.E + t.row] != 0) << q;
+      // ---- pass 1: V of the end rows
+      wait_mma();  // layer 1 (end rows)
+      epi2_fwd<D1>(tm + C2_ACC0, t, b1, wsm + CM::H1_HI, wsm + CM::H1_LO);
+      ready_arrive(wg, rp);
+      // start-row observations -> XS (the previous tile's dW1 GEMM ran behind the epilogue above)
+      if (MODE == CRITIC_STEP && !first) {
+        umma::mbar_wait(bar_dw1, phase_dw1);
+        phase_dw1 ^= 1;
+      }
+      {
+        row_state<NB> xs;
+        unpack_state<NB>(ps, xs);
+        encode_row<NB>(wsm + CM::XS, t.row, xs, L.inv_w, L.inv_h);
+      }
+      ready_arrive(wg, rp);
+      // the next tile's end state, packed (its loads have arrived by now)
+      packed_state<NB> pn, pe;
+      if (has_next) {
+        row_state<NB> xe;
+        end_state<NB>(ns, nl, ndone, nact, last, xe);
+        pack_state<NB>(xe, pe);
+        pack_state<NB>(ns, pn);
+      }
+      wait_mma();  // layer 2 (end rows)
+      const float v_end = epi2_value<D2, false>(tm + C2_ACC1, t, b2, w3, b3, nullptr);
+      ve[t.row] = v_end;
+      // ---- pass 2: start rows, H1 kept for the dW2 GEMM
+      umma::mbar_wait(bar_l1s, phase_l1s);  // layer 1 (start rows)
+      phase_l1s ^= 1;
+      umma::fence_after_sync();
+      epi2_fwd<D1>(tm + C2_ACC0, t, b1, wsm + CM::H1_HI, wsm + CM::H1_LO);
+      ready_arrive(wg, rp);
+      wait_mma();  // layer 2 (start rows)
+      float y2[MODE == CRITIC_STEP ? D2 : 1];
+      const float v = epi2_value<D2, MODE == CRITIC_STEP>(tm + C2_ACC1, t, b2, w3, b3, y2);
+      vs[t.row] = v;
+      asm volatile("bar.sync %0, 128;\n" ::"r"(5 + wg) : "memory");  // ve / vs of the tile visible
+      if (MODE == CRITIC_GAE) {
+        // thread e < E walks its env backwards (same recurrence as device_fns.cuh gae_env)
+        if (t.row < L.E && i < L.n) {
+          float a_next = 0.f;
+          for (int q = L.T - 1; q >= 0; --q) {
+            const size_t kq = (size_t)q * L.n + i;
+            const int r = q * L.E + t.row;
+            const int d = L.T <= 32 ? (int)((dmask >> q) & 1u) : (int)L.rec_done[kq];
+            const bool ends = d || q == L.T - 1;
+            const float vn = ends ? ve[r] : vs[r + L.E];
+            const float vn_adv = d ? 0.f : vn;
+            const float delta = (d ? 0.f : 1.f) + a.gamma * vn_adv - vs[r];
+            const float adv = delta + (ends ? 0.f : a.lambda * a.gamma * a_next);
+            a.adv_out[kq] = adv;
+            a_next = adv;
+          }
+        }
+        asm volatile("bar.sync %0, 128;\n" ::"r"(5 + wg) : "memory");  // ve / vs may be overwritten
+      } else {
+        // ---- targets and dY = V - target (square_loss_grad, nn.h:548-550)
+        float dy = 0.f;
+        if (valid) {
+          const bool ends = done || last;
+          const float vn = ends ? v_end : vs[t.row + L.E];
+          const float tgt = (done ? 0.f : 1.f) + a.gamma * vn;  // not masked at terminals (quirk 6)
+          dy = v - tgt;
+          if (a.targets_out)
+            a.targets_out[k] = tgt;
+        }
+        db3 += dy;
+        // dH2 = dY w3 . relu'(H2) (rank 1: no GEMM) -> panels; dW3 += dY H2
+#pragma unroll
+        for (int cc = 0; cc < D2 / 8; ++cc) {
+          float g[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            g[q] = y2[8 * cc + q] > 0.f ? dy * w3[8 * cc + q] : 0.f;
+            dw3[8 * cc + q] = fmaf(dy, y2[8 * cc + q], dw3[8 * cc + q]);
+          }
+          uint4 h, l;
+          split8<false>(g, h, l);
+          const uint32_t off = umma::panel_chunk_off(t.row, cc);
+          *reinterpret_cast<uint4 *>(wsm + CM::G2_HI + off) = h;
+          *reinterpret_cast<uint4 *>(wsm + CM::G2_LO + off) = l;
+        }
+        ready_arrive(wg, rp);
+        wait_mma();  // dH1
+        if (j > 0)   // the shared dH1 slot (see fused_policy_step2_kernel)
+          umma::mbar_wait(bars + 2, (uint32_t)(j - 1) & 1u);
+        epi2_bwd<D1>(tm + C2_ACC0, t, wsm + CM::H1_HI, smem + CM::DH1_HI, smem + CM::DH1_LO);
+        umma::mbar_wait(bar_dw2, phase_dw2);  // H1 is free (the dW2 GEMM ran behind the dH1 epilogue)
+        phase_dw2 ^= 1;
+      }
+      if (has_next) {
+        row_state<NB> xe;
+        unpack_state<NB>(pe, xe);
+        encode_row<NB>(wsm + CM::H1_LO, t.row, xe, L.inv_w, L.inv_h);
+        ps = pn;
+        done = ndone;
+      }
+      ready_arrive(wg, rp);
+      first = false;
+    }
+    if (MODE == CRITIC_STEP && !first) {  // the last tile's dW1 GEMM
+      umma::mbar_wait(bar_dw1, phase_dw1);
+      umma::fence_after_sync();
+    }
+  }
+
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  if (MODE == CRITIC_STEP) {
+    // ---- drain: partial gradient of this CTA (pipeline 0's sums + pipeline 1's) -> global
+    float *part = a.partials + (size_t)blockIdx.x * net.n_params;
+    const bool two = nt > 1;
+    if (nt == 0) {
+      for (int q = threadIdx.x; q < net.n_params; q += blockDim.x)
+        part[q] = 0.f;
+    } else {
+      if (!issuer) {  // dW2[n][k]: DA (M = 64) row n = TMEM lane 32 (n / 16) + n % 16, col k
+        constexpr int DC = D1 / 2;
+        float v[DC], w[DC];
+        tmem_load<DC>(tmem + C2_DA + t.lane_base + t.wg * DC, v);
+        if (two) {
+          tmem_load<DC>(tmem + 256 + C2_DA + t.lane_base + t.wg * DC, w);
+#pragma unroll
+          for (int q = 0; q < DC; ++q)
+            v[q] += w[q];
+        }
+        int nrow = t.lane < 16 ? t.w * 16 + t.lane : -1;
+        if (nrow >= 0 && nrow < D2)
+#pragma unroll
+          for (int q = 0; q < DC; ++q)
+            part[net.o_w2 + nrow * D1 + t.wg * DC + q] = v[q];
+      }
+      if (!issuer) {  // dW1[n][k] + db1[n]: DB row n, cols 0..D0-1 and D0; db2[n]: DB row 64 + n, col D0
+        constexpr int DC = (D0 + 16) / 2;
+        float v[DC], w[DC];
+        tmem_load<DC>(tmem + C2_DB + t.lane_base + t.wg * DC, v);
+        if (two) {
+          tmem_load<DC>(tmem + 256 + C2_DB + t.lane_base + t.wg * DC, w);
+#pragma unroll
+          for (int q = 0; q < DC; ++q)
+            v[q] += w[q];
+        }
+#pragma unroll
+        for (int q = 0; q < DC; ++q) {
+          int col = t.wg * DC + q;
+          if (t.row < D1) {
+            if (col < D0)
+              part[net.o_w1 + t.row * D0 + col] = v[q];
+            else if (col == D0)
+              part[net.o_b1 + t.row] = v[q];
+          } else if (t.row >= 64 && t.row - 64 < D2 && col == D0) {
+            part[net.o_b2 + t.row - 64] = v[q];
+          }
+        }
+      }
+      // dW3 / db3: thread-local sums -> fixed-order column sums through shared memory (the panels
+      // are free): red[256 rows][D2 + 1], 4 row quarters per column, combined in order
+      float *red = reinterpret_cast<float *>(smem + CM::WG0);
+      constexpr int W = D2 + 1;
+      if (!issuer) {
+#pragma unroll
+        for (int q = 0; q < D2; ++q)
+          red[threadIdx.x * W + q] = dw3[q];
+        red[threadIdx.x * W + D2] = db3;
+      }
+      __syncthreads();
+      float *quart = red + 256 * W;
+      for (int u = threadIdx.x; u < 4 * W; u += blockDim.x) {
+        const int c = u % W, qr = u / W;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        for (int r = 0; r < 64; r += 4) {
+          s0 += red[(qr * 64 + r) * W + c];
+          s1 += red[(qr * 64 + r + 1) * W + c];
+          s2 += red[(qr * 64 + r + 2) * W + c];
+          s3 += red[(qr * 64 + r + 3) * W + c];
+        }
+        quart[u] = (s0 + s1) + (s2 + s3);
+      }
+      __syncthreads();
+      if (threadIdx.x < W) {
+        const float s = (quart[threadIdx.x] + quart[W + threadIdx.x]) + (quart[2 * W + threadIdx.x] + quart[3 * W + threadIdx.x]);
+        if (threadIdx.x < D2)
+          part[net.o_w3 + threadIdx.x] = s;
+        else
+          part[net.o_b3] = s;
+      }
+    }
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (t.warp == 0)
+    umma::tmem_dealloc(tmem, 512);
+}
+
 // Second stage of the gradient: fixed-order sum of the per-CTA partials. Block = 32 parameters x 8
 // slices of the CTA range; the 8 slice sums are combined in a fixed order. With a single rank the
 // optimizer update (nn.h:616-698) of the same 32 parameters follows in the same kernel.
@@ -2210,6 +2694,14 @@ int launch_policy_step(dfrl_ctx *ctx, const policy_step_args &a, int ctas) {
 
 template <int D0, int D1, int D2>
 int launch_critic_step(dfrl_ctx *ctx, const critic_args &a, int ctas) {
+  static const bool v1 = getenv("DFRL_CRITIC_V1") != nullptr;  // A/B switch: one tile at a time
+  if (!v1) {
+    constexpr int smem2 = cmap<D1, D2>::TOTAL + 1024;
+    static bool attr2 = false;
+    DFRL_TRY(set_smem_once(fused_critic2_kernel<D0, D1, D2, CRITIC_STEP>, smem2, &attr2));
+    DFRL_LAUNCH(ctx, (fused_critic2_kernel<D0, D1, D2, CRITIC_STEP>), ctas, 320, smem2, a);
+    return DFRL_OK;
+  }
   constexpr int smem = smem_map<D1, D2>::TOTAL + 1024;
   constexpr int NWG = 2;
   static bool attr = false;
@@ -2220,6 +2712,14 @@ int launch_critic_step(dfrl_ctx *ctx, const critic_args &a, int ctas) {
 
 template <int D0, int D1, int D2>
 int launch_gae(dfrl_ctx *ctx, const critic_args &a, int ctas) {
+  static const bool v1 = getenv("DFRL_CRITIC_V1") != nullptr;
+  if (!v1) {
+    constexpr int smem2 = cmap<D1, D2>::TOTAL + 1024;
+    static bool attr2 = false;
+    DFRL_TRY(set_smem_once(fused_critic2_kernel<D0, D1, D2, CRITIC_GAE>, smem2, &attr2));
+    DFRL_LAUNCH(ctx, (fused_critic2_kernel<D0, D1, D2, CRITIC_GAE>), ctas, 320, smem2, a);
+    return DFRL_OK;
+  }
   constexpr int smem = smem_fwd<D1, D2>::TOTAL + 1024;
   static bool attr = false;
   DFRL_TRY(set_smem_once(fused_gae_kernel<D0, D1, D2>, smem, &attr));
@@ -2373,6 +2873,16 @@ void dfrl_fused_detach(dfrl_trainer *t) {
   t->fused_impl = nullptr;
 }
 
+// Test hook: caps the grid of the fused learner kernels (persistent CTAs) so that small problems
+// exercise the multi-tile steady state of both tile pipelines. ctas <= 0 restores one CTA per SM.
+extern "C" int dfrl_debug_set_fused_ctas(dfrl_trainer *t, int ctas) {
+  DFRL_CHECK(t, "null trainer");
+  fused_state *f = (fused_state *)t->fused_impl;
+  DFRL_CHECK(f, "fused path not attached");
+  f->ctas = (ctas > 0 && ctas < t->ctx->sm_count) ? ctas : t->ctx->sm_count;
+  return DFRL_OK;
+}
+
 // Phase clocks (SM cycles) of CTA 0 of the fused policy step: 12 stamps per tile, first 8 tiles.
 // The first call arms the instrumentation (returns zeros); later calls return the last launch.
 extern "C" int dfrl_debug_policy_clocks(dfrl_trainer *t, long long *out_host, int n) {
@@ -2432,7 +2942,9 @@ int dfrl_fused_gae(dfrl_trainer *t) {
   if (!f || !f->value_ok)
     return DFRL_ERR_UNSUPPORTED;
   critic_args a = make_critic_args(t, f);
-  int ctas = a.n_tiles < 2 * f->ctas ? a.n_tiles : 2 * f->ctas;
+  // one 320-thread CTA per SM (two tile pipelines each); the one-tile-at-a-time kernel ran two
+  const int per_sm = getenv("DFRL_CRITIC_V1") ? 2 : 1;
+  int ctas = a.n_tiles < per_sm * f->ctas ? a.n_tiles : per_sm * f->ctas;
   if (f->vnet.d1 == 64)
     DFRL_TRY((launch_gae<32, 64, 64>(t->ctx, a, ctas)));
   else

@@ -374,9 +374,15 @@ typedef struct {
 } dfrl_trainer_stats;
 int dfrl_trainer_get_stats(dfrl_trainer *tr, dfrl_trainer_stats *out);
 /* Profiling aid (no reference counterpart): SM-cycle stamps at the phase boundaries of CTA 0 of the
- * fused policy-step kernel, 12 per row tile for its first 8 tiles (n <= 96). The first call arms
+ * fused policy-step kernel (pipeline 0), 13 per row tile for its first 8 tiles, then entry / setup /
+ * loop-end / exit stamps at 104..107 (n <= 112). The first call arms
  * the instrumentation and returns zeros; later calls return the stamps of the last launch. */
 int dfrl_debug_policy_clocks(dfrl_trainer *tr, long long *out_host, int n);
+/* Test hook (no reference counterpart): caps the number of persistent CTAs of the fused learner
+ * kernels, so that a small problem runs many row tiles per CTA (the steady state of the two tile
+ * pipelines). ctas <= 0 restores one CTA per SM. Results do not depend on the grid size beyond the
+ * summation order of the per-CTA partial gradients. */
+int dfrl_debug_set_fused_ctas(dfrl_trainer *tr, int ctas);
 
 /* deep_agent.cc:28-41 / the periodic eval of the trainer mains (ppo_training.cc:67-81): every
  * env of `env` plays `episodes` episodes with policy_gradient_deterministic_policy (argmax) on

@@ -425,8 +425,14 @@ def test_trainer_default_path_vs_reference_trace(D, ctx, name):
     _run_case(D, ctx, name, fused=True)
 
 
-@pytest.mark.parametrize("n,T", [(512, 4), (200, 4), (96, 8), (70, 5)])
-def test_trainer_vs_oracle_with_uniform_tape(D, ctx, orc, n, T):
+@pytest.mark.parametrize("n,T,ctas", [(512, 4, 0), (200, 4, 0), (96, 8, 0), (70, 5, 0),
+                                      (512, 4, 3), (544, 4, 2), (200, 4, 1), (416, 8, 4), (2048, 4, 5)])
+def test_trainer_vs_oracle_with_uniform_tape(D, ctx, orc, n, T, ctas):
+    # ctas > 0: the persistent learner kernels run on that many CTAs only, so that every CTA works
+    # through several row tiles per tile pipeline (the steady state of the large configurations):
+    # (512, 4, 3) 16 tiles on 3 CTAs; (544, 4, 2) 17 tiles: an odd tile count per CTA, the two
+    # pipelines get different numbers of tiles; (200, 4, 1) 7 tiles on one CTA with a ragged last
+    # tile; (416, 8, 4) 16 envs per tile; (2048, 4, 5) 64 tiles, 12-13 per CTA.
     # sampling mode driven by a tape of uniforms: GPU and oracle must pick identical actions.
     # (200, 4): ragged last tiles of the rollout (128 envs) and learner (32 envs) kernels;
     # (96, 8): 16 envs per learner tile; (70, 5): 25 envs per tile, the byte-wise staging path.
@@ -463,6 +469,8 @@ def test_trainer_vs_oracle_with_uniform_tape(D, ctx, orc, n, T):
     # (activations of ~5 make the SUM gradients large: rates scaled down so that 20 updates stay tame)
     tr = D.Trainer(ctx, env, policy, value, algo=D.PPO, work=T, policy_lr=2e-8, value_lr=2e-8,
                    action_mode=D.ACT_SAMPLE)
+    if ctas:
+        D._lib.check(D._lib.lib.dfrl_debug_set_fused_ctas(tr.h, ctas))
     lr = orc.Learner(orc.train_cfg(orc.PPO, T, policy_lr=2e-8, value_lr=2e-8), ecfg, pnet, pp, vnet, vp)
     done_at_last_step = done_mid = 0
     for it in range(5):
