@@ -314,6 +314,8 @@ def roofline_from_profile(prof, n_envs, peaks):
     P = 2 * 8 + 2
     work = {  # kernel substring -> (algorithmic FLOPs per launch, algorithmic HBM bytes per launch)
         "fused_policy_step": (rows * 3 * fp, rows * (P + 1 + 4 + 4 * 8)),
+        "CRITIC_STEP": (rows * 3 * fv + n_envs * fv, rows * (P + 2 + 4) + n_envs * P),  # fused_critic2_kernel
+        "CRITIC_GAE": ((rows + n_envs) * fv, rows * (P + 2 + 4) + n_envs * P),          # fused_critic2_kernel
         "fused_critic_step": (rows * 3 * fv + n_envs * fv, rows * (P + 2 + 4) + n_envs * P),
         "fused_gae": ((rows + n_envs) * fv, rows * (P + 2 + 4) + n_envs * P),
         "fused_rollout": (rows * fp, rows * (P + 2 + 4 * 8) + n_envs * (2 * P + 16)),
@@ -323,6 +325,9 @@ def roofline_from_profile(prof, n_envs, peaks):
     table = {}
     for name, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
         short = name.split("<")[0].strip("() ")
+        for mode in ("CRITIC_STEP", "CRITIC_GAE"):  # two instantiations of one kernel template
+            if mode in name:
+                short += "<" + mode + ">"
         w = next((w for k, w in work.items() if k in name), None)
         per_launch_ms = v["ms"] / max(v["launches"], 1e-9)
         row = {"launches_per_step": v["launches"], "ms_per_step": round(v["ms"], 4),

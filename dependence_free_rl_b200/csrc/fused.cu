@@ -2128,19 +2128,7 @@ __global__ void __launch_bounds__(320, 1) fused_critic2_kernel(critic_args a) {
       const int i = tile * L.E + e;
       const bool valid = tt < L.T && i < L.n;
       const size_t k = (size_t)tt * L.n + i;
-      // the next tile's state: loads now, first use after this tile's first epilogue
       const bool has_next = j + 2 < nt;
-      row_state<NB> ns, nl;
-      int ndone = 0, nact = 0;
-      if (has_next) {
-        const int ntile = tile + 2 * gridDim.x, ni = ntile * L.E + e;
-        load_row_state<NB>(L, ntile, t.row, ns);
-        load_live_state<NB>(L, ntile, t.row, nl);
-        if (tt < L.T && ni < L.n) {
-          ndone = L.rec_done[(size_t)tt * L.n + ni];
-          nact = L.rec_action[(size_t)tt * L.n + ni];
-        }
-      }
       // GAE: done flags of the env this thread walks (threads < E)
       uint32_t dmask = 0;
       if (MODE == CRITIC_GAE && t.row < L.E && i < L.n)
@@ -2161,7 +2149,20 @@ __global__ void __launch_bounds__(320, 1) fused_critic2_kernel(critic_args a) {
         encode_row<NB>(wsm + CM::XS, t.row, xs, L.inv_w, L.inv_h);
       }
       ready_arrive(wg, rp);
-      // the next tile's end state, packed (its loads have arrived by now)
+      // the next tile's state: loads in flight behind the layer-2 GEMM, packed right after it (the
+      // raw bytes would cost 38 registers during the epilogues)
+      row_state<NB> ns, nl;
+      int ndone = 0, nact = 0;
+      if (has_next) {
+        const int ntile = tile + 2 * gridDim.x, ni = ntile * L.E + e;
+        load_row_state<NB>(L, ntile, t.row, ns);
+        load_live_state<NB>(L, ntile, t.row, nl);
+        if (tt < L.T && ni < L.n) {
+          ndone = L.rec_done[(size_t)tt * L.n + ni];
+          nact = L.rec_action[(size_t)tt * L.n + ni];
+        }
+      }
+      wait_mma();  // layer 2 (end rows)
       packed_state<NB> pn, pe;
       if (has_next) {
         row_state<NB> xe;
@@ -2169,7 +2170,6 @@ __global__ void __launch_bounds__(320, 1) fused_critic2_kernel(critic_args a) {
         pack_state<NB>(xe, pe);
         pack_state<NB>(ns, pn);
       }
-      wait_mma();  // layer 2 (end rows)
       const float v_end = epi2_value<D2, false>(tm + C2_ACC1, t, b2, w3, b3, nullptr);
       ve[t.row] = v_end;
       // ---- pass 2: start rows, H1 kept for the dW2 GEMM
@@ -2179,8 +2179,7 @@ __global__ void __launch_bounds__(320, 1) fused_critic2_kernel(critic_args a) {
       epi2_fwd<D1>(tm + C2_ACC0, t, b1, wsm + CM::H1_HI, wsm + CM::H1_LO);
       ready_arrive(wg, rp);
       wait_mma();  // layer 2 (start rows)
-      float y2[MODE == CRITIC_STEP ? D2 : 1];
-      const float v = epi2_value<D2, MODE == CRITIC_STEP>(tm + C2_ACC1, t, b2, w3, b3, y2);
+      const float v = epi2_value<D2, false>(tm + C2_ACC1, t, b2, w3, b3, nullptr);
       vs[t.row] = v;
       asm volatile("bar.sync %0, 128;\n" ::"r"(5 + wg) : "memory");  // ve / vs of the tile visible
       if (MODE == CRITIC_GAE) {
@@ -2213,20 +2212,32 @@ __global__ void __launch_bounds__(320, 1) fused_critic2_kernel(critic_args a) {
             a.targets_out[k] = tgt;
         }
         db3 += dy;
-        // dH2 = dY w3 . relu'(H2) (rank 1: no GEMM) -> panels; dW3 += dY H2
+        // dH2 = dY w3 . relu'(H2) (rank 1: no GEMM) -> panels; dW3 += dY H2. H2 = relu(acc + b2) is
+        // recomputed from the layer-2 accumulator, which stays in TMEM until the next tile's layer 2
+        // (64 registers less than keeping the row across the value exchange)
+        {
+          constexpr int CH = D2 < 32 ? D2 : 32;
 #pragma unroll
-        for (int cc = 0; cc < D2 / 8; ++cc) {
-          float g[8];
+          for (int h = 0; h < D2 / CH; ++h) {
+            float y[CH];
+            tmem_load<CH>(tm + C2_ACC1 + t.lane_base + h * CH, y);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            g[q] = y2[8 * cc + q] > 0.f ? dy * w3[8 * cc + q] : 0.f;
-            dw3[8 * cc + q] = fmaf(dy, y2[8 * cc + q], dw3[8 * cc + q]);
+            for (int cc = 0; cc < CH / 8; ++cc) {
+              float g[8];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const int c = h * CH + 8 * cc + q;
+                const float yy = fmaxf(y[8 * cc + q] + b2[c], 0.f);
+                g[q] = yy > 0.f ? dy * w3[c] : 0.f;
+                dw3[c] = fmaf(dy, yy, dw3[c]);
+              }
+              uint4 hh, ll;
+              split8<false>(g, hh, ll);
+              const uint32_t off = umma::panel_chunk_off(t.row, h * (CH / 8) + cc);
+              *reinterpret_cast<uint4 *>(wsm + CM::G2_HI + off) = hh;
+              *reinterpret_cast<uint4 *>(wsm + CM::G2_LO + off) = ll;
+            }
           }
-          uint4 h, l;
-          split8<false>(g, h, l);
-          const uint32_t off = umma::panel_chunk_off(t.row, cc);
-          *reinterpret_cast<uint4 *>(wsm + CM::G2_HI + off) = h;
-          *reinterpret_cast<uint4 *>(wsm + CM::G2_LO + off) = l;
         }
         ready_arrive(wg, rp);
         wait_mma();  // dH1
