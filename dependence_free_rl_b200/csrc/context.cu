@@ -359,7 +359,7 @@ extern "C" int dfrl_p2p_export(dfrl_ctx *ctx, void *handle64_host) {
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
   DFRL_CUDA(cudaSetDevice(ctx->device));
   if (!ctx->p2p.local) {
-    const size_t bytes = sizeof(float) * 2 * DFRL_P2P_CAP + 64;
+    const size_t bytes = DFRL_P2P_BYTES;
     DFRL_CUDA(cudaMalloc(&ctx->p2p.local, bytes));
     DFRL_CUDA(cudaMemset(ctx->p2p.local, 0, bytes));
   }

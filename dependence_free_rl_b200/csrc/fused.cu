@@ -2357,24 +2357,18 @@ __global__ void __launch_bounds__(320, 1) fused_critic2_kernel(critic_args a) {
 // optimizer update (nn.h:616-698) of the same 32 parameters follows in the same kernel.
 struct reduce_tail {
   dfrl_opt_spec opt;   // params == null: no update
-  unsigned *ticket;    // multi-rank publish: zero before the launch, zero again after it
-  // multi-rank publish: exchange buffer of this rank ([2 slots][DFRL_P2P_CAP] floats, 2 flags, the
-  // exchange counter). The counter lives on the device so that the launch arguments are constant
-  // (CUDA-graph capturable): exchange e = counter + 1 uses slot e & 1; the last block sets the
-  // slot's flag to e once the whole gradient is visible system-wide, then bumps the counter.
+  unsigned *ticket;    // multi-rank exchange: zero before the launch, zero again after it
+  // multi-rank exchange (fused_reduce_exchange_kernel): this rank's exchange buffer ([2 slots]
+  // [DFRL_P2P_CAP] floats, flag words incl. the exchange counter, per-block publish flags). The
+  // counter lives on the device so that the launch arguments are constant (CUDA-graph capturable):
+  // exchange e = counter + 1 uses slot e & 1; the block that takes the last ticket bumps the counter.
   float *exchange;
 };
 __global__ void __launch_bounds__(256) fused_reduce_partials_kernel(const float *__restrict__ part, int ctas,
                                                                     int n, float *__restrict__ grad,
                                                                     reduce_tail tail) {
   __shared__ float sm[8][33];
-  __shared__ int is_last;
   const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
-  unsigned epoch = 0;
-  if (tail.exchange) {  // every block reads the counter before its ticket; the last block bumps it
-    epoch = *reinterpret_cast<volatile unsigned *>(dfrl_p2p_flags(tail.exchange) + 2) + 1;
-    grad = tail.exchange + (size_t)(epoch & 1u) * DFRL_P2P_CAP;
-  }
   const int i = blockIdx.x * 32 + lane;
   float s = 0.f;
   if (i < n)
@@ -2392,56 +2386,68 @@ __global__ void __launch_bounds__(256) fused_reduce_partials_kernel(const float 
     if (opt.params)
       opt_update(opt.kind, opt.params, grad, opt.state, n, i, opt.lr, opt.wd, opt.beta1, opt.beta2, opt.c1, opt.c2);
   }
-  if (!tail.exchange)
-    return;
-  __threadfence_system();  // this block's writes to the exchange slot before its ticket
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned tk = atomicAdd(tail.ticket, 1u);
-    is_last = tk == gridDim.x - 1;
-    if (is_last)
-      *tail.ticket = 0;
-  }
-  __syncthreads();
-  if (!is_last)
-    return;
-  __threadfence_system();
-  if (threadIdx.x == 0) {
-    volatile unsigned *flags = reinterpret_cast<volatile unsigned *>(dfrl_p2p_flags(tail.exchange));
-    flags[epoch & 1u] = epoch;
-    flags[2] = epoch;
-  }
 }
 
-// K8 + K7 over NVLink peer memory: pull every rank's published gradient, sum in rank order
-// (bit-identical on every rank), optimizer update.
-// Waits (bounded) for the peers' publish flags: every rank runs the same launch sequence on its own
-// GPU, and a peer's producer kernel never depends on this rank.
+// Reduction + exchange + optimizer in ONE kernel (several ranks), PUSH protocol: block b sums the
+// per-CTA partials of its 32 gradient entries; warp q then stores them into rank q's exchange buffer
+// (remote stores over NVLink, own rank included), fences and raises flag [source = this rank][b]
+// THERE. The block then polls its LOCAL flags of all source ranks, sums the local copies in rank
+// order (bit-identical on every rank) and applies the optimizer. Nothing on the receive side
+// crosses NVLink, and no grid-wide hand-over sits between a rank's reduction and the exchange; the
+// ticket only elects the block that advances the exchange counter for the next launch. A block
+// never waits for another block of its own grid, and a peer's producer never depends on this rank
+// (bounded spin -> trap instead of a hung GPU).
 struct p2p_view {
-  const float *peer[DFRL_P2P_MAX_RANKS];
-  const float *local;  // this rank's buffer: its exchange counter names the exchange to complete
-  int nranks;
+  float *peer[DFRL_P2P_MAX_RANKS];
+  int nranks, rank;
 };
-__global__ void __launch_bounds__(256) fused_p2p_sum_opt_kernel(p2p_view v, int n, float *__restrict__ grad,
-                                                                reduce_tail tail) {
-  const unsigned epoch = *reinterpret_cast<const volatile unsigned *>(v.local + 2 * DFRL_P2P_CAP + 2);
+__global__ void __launch_bounds__(256) fused_reduce_exchange_kernel(const float *__restrict__ part, int ctas, int n,
+                                                                    float *__restrict__ grad, p2p_view v,
+                                                                    reduce_tail tail) {
+  __shared__ float sm[8][33];
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  float *local = v.peer[v.rank];
+  volatile unsigned *words = reinterpret_cast<volatile unsigned *>(dfrl_p2p_flags(local));
+  const unsigned epoch = words[2] + 1;  // every block reads the counter before its ticket
   const int slot = (int)(epoch & 1u);
-  if ((int)threadIdx.x < v.nranks) {
-    const volatile unsigned *flag =
-        reinterpret_cast<const volatile unsigned *>(v.peer[threadIdx.x] + 2 * DFRL_P2P_CAP) + slot;
+  const int i = blockIdx.x * 32 + lane;
+  float s = 0.f;
+  if (i < n)
+    for (int c = slice; c < ctas; c += 8)
+      s += part[(size_t)c * n + i];
+  sm[slice][lane] = s;
+  __syncthreads();
+  float r = 0.f;
+#pragma unroll
+  for (int q = 0; q < 8; ++q)  // every warp forms the same sum (fixed order)
+    r += sm[q][lane];
+  static_assert(DFRL_P2P_MAX_RANKS <= 8, "one warp per destination rank");
+  if (slice < v.nranks) {
+    if (i < n)
+      dfrl_p2p_data(v.peer[slice], slot, v.rank)[i] = r;
+    __threadfence_system();
+    __syncwarp();
+    if (lane == 0)
+      *reinterpret_cast<volatile unsigned *>(dfrl_p2p_block_flags(v.peer[slice], slot, v.rank) + blockIdx.x) = epoch;
+  }
+  if (threadIdx.x == 0 && atomicAdd(tail.ticket, 1u) == gridDim.x - 1) {  // all blocks have read the counter
+    *tail.ticket = 0;
+    words[2] = epoch;
+  }
+  if (slice < v.nranks && lane == 0) {
+    const volatile unsigned *pf = reinterpret_cast<const volatile unsigned *>(dfrl_p2p_block_flags(local, slot, slice)) + blockIdx.x;
     unsigned spins = 0;
-    while (*flag < epoch)
+    while (*pf < epoch)
       if (++spins > (1u << 28))
-        __trap();  // a peer never published: report a launch failure instead of hanging the GPU
+        __trap();
     __threadfence_system();
   }
   __syncthreads();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) {
-    float s = 0.f;
-    for (int r = 0; r < v.nranks; ++r)
-      s += *reinterpret_cast<const volatile float *>(v.peer[r] + (size_t)slot * DFRL_P2P_CAP + i);
-    grad[i] = s;
+  if (slice == 0 && i < n) {
+    float g = 0.f;
+    for (int q = 0; q < v.nranks; ++q)
+      g += *reinterpret_cast<const volatile float *>(dfrl_p2p_data(local, slot, q) + i);
+    grad[i] = g;
     const dfrl_opt_spec &opt = tail.opt;
     if (opt.params)
       opt_update(opt.kind, opt.params, grad, opt.state, n, i, opt.lr, opt.wd, opt.beta1, opt.beta2, opt.c1, opt.c2);
@@ -2786,8 +2792,8 @@ critic_args make_critic_args(dfrl_trainer *t, fused_state *f) {
 }
 
 // Partials -> gradient (-> optimizer update when `opt` is given).
-// Several ranks (opt given means the peers are attached): the reduced gradient goes to this rank's
-// exchange slot and a second kernel pulls all ranks' slots over NVLink before the update.
+// Several ranks (opt given means the peers are attached): reduction, exchange over NVLink peer
+// memory and update in one kernel (fused_reduce_exchange_kernel).
 int launch_reduce(dfrl_trainer *t, fused_state *f, dfrl_mlp *m, const net3 &net, int ctas, float *grad_dev,
                   const dfrl_opt_spec *opt) {
   dfrl_ctx *ctx = t->ctx;
@@ -2802,19 +2808,20 @@ int launch_reduce(dfrl_trainer *t, fused_state *f, dfrl_mlp *m, const net3 &net,
   } else if (opt) {
     tail.opt = *opt;
   }
-  DFRL_LAUNCH(ctx, fused_reduce_partials_kernel, ceil_div(net.n_params, 32), 256, 0, (const float *)f->partials, ctas,
-              net.n_params, dst, tail);
   if (exchange) {
+    DFRL_CHECK((size_t)ceil_div(net.n_params, 32) <= DFRL_P2P_BLOCKS, "flat gradient exceeds the exchange slot");
     p2p_view v;
     memset(&v, 0, sizeof(v));
     for (int r = 0; r < ctx->nranks; ++r)
       v.peer[r] = ctx->p2p.peer[r];
     v.nranks = ctx->nranks;
-    v.local = ctx->p2p.local;
-    reduce_tail t2;
-    memset(&t2, 0, sizeof(t2));
-    t2.opt = *opt;
-    DFRL_LAUNCH(ctx, fused_p2p_sum_opt_kernel, ceil_div(net.n_params, 256), 256, 0, v, net.n_params, grad_dev, t2);
+    v.rank = ctx->rank;
+    tail.opt = *opt;
+    DFRL_LAUNCH(ctx, fused_reduce_exchange_kernel, ceil_div(net.n_params, 32), 256, 0, (const float *)f->partials, ctas,
+                net.n_params, grad_dev, v, tail);
+  } else {
+    DFRL_LAUNCH(ctx, fused_reduce_partials_kernel, ceil_div(net.n_params, 32), 256, 0, (const float *)f->partials, ctas,
+                net.n_params, dst, tail);
   }
   if (opt)
     m->wt_dirty = true, m->version++;
