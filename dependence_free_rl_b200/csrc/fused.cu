@@ -2637,6 +2637,257 @@ __global__ void __launch_bounds__(256, 2) fused_rollout_kernel(rollout_args a) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Rollout with NP tile pipelines per CTA (same structure as fused_policy_step2_kernel): a pipeline
+// = 128 environments, one epilogue thread per environment that keeps the env state in REGISTERS for
+// all T steps, plus one MMA-issuing warp. Shared memory per pipeline: one hi/lo panel pair (the
+// observations are staged in the lo panel's bytes 0..63, H1 then overwrites both, H2 is written in
+// place); the layer-3 B operand stacks [hi(W3); lo(W3)] (N = 16: two MMAs per K step, the head adds
+// columns j and 8 + j).
+template <int D1, int D2, int NP>
+struct rmap {
+  static constexpr uint32_t W1P = 0;
+  static constexpr uint32_t W2_HI = W1P + D1 * 128, W2_LO = W2_HI + D2 * 128;
+  static constexpr uint32_t W3C = W2_LO + D2 * 128;  // rows 0..7 = hi(W3), rows 8..15 = lo(W3)
+  static constexpr uint32_t W3D = W3C + 16 * 128;    // rows 0..7 = hi(W3), rows 8..15 = 0
+  static constexpr uint32_t FLOATS = W3D + 16 * 128;  // b1[D1] b2[D2] b3[16]
+  static constexpr int F_B1 = 0, F_B2 = D1, F_B3 = D1 + D2, N_FLOATS = D1 + D2 + 16;
+  static constexpr uint32_t WG0 = (FLOATS + N_FLOATS * 4 + 1023) / 1024 * 1024;
+  static constexpr uint32_t H_HI = 0, H_LO = PANEL, WG_BYTES = 2 * PANEL;
+  static constexpr uint32_t BARS = WG0 + NP * WG_BYTES;
+  static constexpr uint32_t TOTAL = BARS + 64;
+  static_assert(TOTAL + 1024 <= 232448, "exceeds the 227 KB shared memory of an SM");
+};
+
+template <int D0, int D1, int D2, int NOUT, int NP>
+__global__ void __launch_bounds__(160 * NP, 1) fused_rollout2_kernel(rollout_args a) {
+  using RM = rmap<D1, D2, NP>;
+  constexpr int B = NOUT, P = 2 * B + 2;
+  static_assert(D0 == 4 * B && NOUT == 8, "observation width");
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);  // stays a shared-space pointer
+  float *fl = reinterpret_cast<float *>(smem + RM::FLOATS);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + RM::BARS);  // [wg]: MMA completion
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + RM::BARS + 56);
+  const net3 net = a.net;
+  const env_params &ep = a.ep;
+  const tid_t t = thread_id();
+  const bool issuer = t.warp >= 4 * NP;                    // warp-uniform
+  const int wg = issuer ? t.warp - 4 * NP : t.warp >> 2;   // pipeline index
+  const uint32_t sbase = umma::smem_u32(smem);
+  constexpr uint32_t TCOLS = NP <= 2 ? 256 : 512;
+
+  if (t.warp == 0)
+    umma::tmem_alloc(tmem_slot, TCOLS);
+  if (threadIdx.x == 0) {
+    for (int q = 0; q < NP; ++q)
+      umma::mbar_init(bars + q, 1);
+    umma::fence_mbar_init();
+  }
+  {
+    const float *Pm = a.params;
+    const float *W3 = Pm + net.o_w3;
+    stage_w1_packed<D1>(Pm + net.o_w1, smem + RM::W1P);
+    stage_weight_f16(Pm + net.o_w2, D2, D1, D2, 1.f, smem + RM::W2_HI, smem + RM::W2_LO);
+    for (int c = threadIdx.x; c < 16 * 8; c += blockDim.x) {
+      int row = c >> 3, chunk = c & 7;
+      float x[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        int col = chunk * 8 + j;
+        x[j] = col < D2 ? W3[(size_t)(row & 7) * D2 + col] : 0.f;
+      }
+      uint4 h, l;
+      split8<false>(x, h, l);
+      uint32_t off = umma::panel_chunk_off(row, chunk);
+      *reinterpret_cast<uint4 *>(smem + RM::W3C + off) = row < 8 ? h : l;
+      *reinterpret_cast<uint4 *>(smem + RM::W3D + off) = row < 8 ? h : make_uint4(0, 0, 0, 0);
+    }
+    for (int i = threadIdx.x; i < D1; i += blockDim.x) fl[RM::F_B1 + i] = Pm[net.o_b1 + i];
+    for (int i = threadIdx.x; i < D2; i += blockDim.x) fl[RM::F_B2 + i] = Pm[net.o_b2 + i];
+    for (int i = threadIdx.x; i < 16; i += blockDim.x) fl[RM::F_B3 + i] = i < net.d3 ? Pm[net.o_b3 + i] : 0.f;
+  }
+  zero_bytes(smem + RM::WG0, RM::BARS - RM::WG0);
+  sync_after_smem_writes();
+  const uint32_t tmem = *tmem_slot;
+
+  // this CTA's tiles: blockIdx.x + j * gridDim.x, j < nt; pipeline wg takes j = wg, wg + NP, ...
+  const int nt = (int)blockIdx.x < a.n_tiles ? (a.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  uint8_t *wsm = smem + RM::WG0 + wg * RM::WG_BYTES;
+  const uint32_t wbase = sbase + RM::WG0 + wg * RM::WG_BYTES;
+  const uint32_t tm = tmem + 128u * wg;  // ACC0 (layers 1, 3) at +0, ACC1 (layer 2) at +64
+  uint64_t *bar = bars + wg;
+  uint32_t rp = 0;
+
+  if (issuer) {
+    for (int j = wg; j < nt; j += NP)
+      for (int tt = 0; tt < a.T; ++tt) {
+        ready_sync(wg, rp);  // observations staged in the lo panel
+        if (umma::elect_one()) {
+          issue_gemm<D0 / 16, false, false, false, true>(tm, wbase + RM::H_LO, 0, sbase + RM::W1P,
+                                                         sbase + RM::W1P + 64, ID<D1>::FK_FK, false);
+          umma::commit(bar);
+        }
+        __syncwarp();
+        ready_sync(wg, rp);  // H1
+        if (umma::elect_one()) {
+          issue_gemm<D1 / 16, false, false, true, true>(tm + 64, wbase + RM::H_HI, wbase + RM::H_LO,
+                                                        sbase + RM::W2_HI, sbase + RM::W2_LO, ID<D2>::FK_FK, false);
+          umma::commit(bar);
+        }
+        __syncwarp();
+        ready_sync(wg, rp);  // H2 (in place)
+        if (umma::elect_one()) {
+          // hi(H2) . [hi(W3); lo(W3)] + lo(H2) . [hi(W3); 0]
+          issue_gemm<D2 / 16, false, false, true, false>(tm, wbase + RM::H_HI, wbase + RM::H_LO, sbase + RM::W3C, 0,
+                                                         ID<16>::FK_FK, false);
+          umma::commit(bar);
+        }
+        __syncwarp();
+      }
+  } else {
+    const float *b1 = fl + RM::F_B1, *b2 = fl + RM::F_B2, *b3 = fl + RM::F_B3;
+    uint32_t phase = 0;
+    auto wait_mma = [&]() {
+      umma::mbar_wait(bar, phase);
+      phase ^= 1;
+      umma::fence_after_sync();
+    };
+    unsigned long long c_eps = 0, c_reward = 0, c_steps = 0;
+    const size_t S = ep.stride;
+    for (int j = wg; j < nt; j += NP) {
+      const int tile = blockIdx.x + j * gridDim.x;
+      const int i = tile * TILE + t.row;
+      const bool owner = i < ep.n;
+      row_state<B> st;  // live state of this thread's environment
+      uint32_t my_draws = 0, my_steps = 0;
+#pragma unroll
+      for (int q = 0; q < P; ++q)
+        st.v[q] = 0;
+      if (owner) {
+#pragma unroll
+        for (int q = 0; q < P; ++q)
+          st.v[q] = a.state[(size_t)q * S + i];
+        my_draws = a.draws[i];
+        my_steps = a.steps[i];
+      }
+      for (int tt = 0; tt < a.T; ++tt) {
+        // ---- record the start state of step tt, stage the observations
+        if (owner) {
+#pragma unroll
+          for (int q = 0; q < P; ++q)
+            a.rec_state[((size_t)tt * P + q) * S + i] = (int8_t)st.v[q];
+        }
+        encode_row<B>(wsm + RM::H_LO, t.row, st, a.inv_w, a.inv_h);
+        ready_arrive(wg, rp);
+        // tape entries of this step (loads issued before the GEMMs, used in the head)
+        const size_t k = (size_t)tt * ep.n + i;
+        int forced_a = 0, tape_item = 0;
+        double tape_u = 0.0;
+        if (owner) {
+          if (a.mode == DFRL_ACT_FORCED)
+            forced_a = a.forced[k];
+          else if (a.mode == DFRL_ACT_SAMPLE && a.u_tape)
+            tape_u = a.u_tape[k];
+          if (a.item_tape)
+            tape_item = a.item_tape[k];
+        }
+        wait_mma();  // layer 1
+        epi2_fwd<D1>(tm, t, b1, wsm + RM::H_HI, wsm + RM::H_LO);
+        ready_arrive(wg, rp);
+        wait_mma();  // layer 2
+        epi2_fwd<D2>(tm + 64, t, b2, wsm + RM::H_HI, wsm + RM::H_LO);
+        ready_arrive(wg, rp);
+        wait_mma();  // layer 3
+        // ---- head: softmax (no max subtraction, nn.h:382-392), action, environment::apply
+        float v[16];
+        tmem_load<16>(tm + t.lane_base, v);
+        if (owner) {
+          float p[NOUT], s = 0.f;
+#pragma unroll
+          for (int q = 0; q < NOUT; ++q) {
+            p[q] = expf((v[q] + v[8 + q]) + b3[q]);
+            s += p[q];
+          }
+#pragma unroll
+          for (int q = 0; q < NOUT; ++q)
+            p[q] = p[q] / s;
+          float4 *pr = reinterpret_cast<float4 *>(a.rec_probs + k * B);
+#pragma unroll
+          for (int q = 0; q < NOUT / 4; ++q)
+            pr[q] = make_float4(p[4 * q], p[4 * q + 1], p[4 * q + 2], p[4 * q + 3]);
+          int act;
+          if (a.mode == DFRL_ACT_FORCED) {
+            act = forced_a;
+          } else if (a.mode == DFRL_ACT_ARGMAX) {
+            act = argmax_first(p, B);
+          } else {
+            double u = tape_u;
+            if (!a.u_tape) {
+              philox4 rr = philox4x32_10(ep.seed, (uint64_t)(ep.env_offset + i), my_steps, DFRL_STREAM_ACTION);
+              u = philox_u53(rr.x, rr.y);
+            }
+            act = discrete_sample(p, B, u);
+          }
+          act = act < B ? act : B - 1;
+          a.rec_action[k] = (uint8_t)act;
+          // environment::apply (bin_packing.h:53-64) on the registers of this environment
+          const int iw = st.v[2 * B], ih = st.v[2 * B + 1];
+          int bw = 0, bh = 0;
+#pragma unroll
+          for (int b = 0; b < B; ++b)
+            if (b == act) {
+              bw = st.v[2 * b] - iw;
+              bh = st.v[2 * b + 1] - ih;
+            }
+          const bool over = bw < 0 || bh < 0;
+          const int s1 = a.item_tape ? (tape_item != 0) : draw_shape1(ep, i, my_draws);
+#pragma unroll
+          for (int b = 0; b < B; ++b) {
+            if (over) {
+              st.v[2 * b] = ep.cap_w;
+              st.v[2 * b + 1] = ep.cap_h;
+            } else if (b == act) {
+              st.v[2 * b] = bw;
+              st.v[2 * b + 1] = bh;
+            }
+          }
+          st.v[2 * B] = s1 ? ep.iw0 : ep.iw1;
+          st.v[2 * B + 1] = s1 ? ep.ih0 : ep.ih1;
+          a.rec_done[k] = over;
+          my_draws += 1;
+          my_steps += 1;
+          c_steps += 1;
+          c_eps += over ? 1 : 0;
+          c_reward += over ? 0 : 1;
+        }
+      }
+      // ---- live state back to the environment
+      if (owner) {
+#pragma unroll
+        for (int q = 0; q < P; ++q)
+          a.state[(size_t)q * S + i] = (int8_t)st.v[q];
+        a.draws[i] = my_draws;
+        a.steps[i] = my_steps;
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      c_steps += __shfl_down_sync(0xffffffffu, c_steps, o);
+      c_eps += __shfl_down_sync(0xffffffffu, c_eps, o);
+      c_reward += __shfl_down_sync(0xffffffffu, c_reward, o);
+    }
+    if (t.lane == 0 && c_steps) {
+      atomicAdd(&a.counters[0], c_steps);
+      atomicAdd(&a.counters[1], c_eps);
+      atomicAdd(&a.counters[2], c_reward);
+    }
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (t.warp == 0)
+    umma::tmem_dealloc(tmem, TCOLS);
+}
+
+// ---------------------------------------------------------------------------------------------
 struct fused_state {
   net3 pnet, vnet;
   bool policy_ok, value_ok, rollout_ok;
@@ -2746,6 +2997,15 @@ int launch_gae(dfrl_ctx *ctx, const critic_args &a, int ctas) {
 
 template <int D0, int D1, int D2, int NOUT>
 int launch_rollout(dfrl_ctx *ctx, const rollout_args &a, int ctas) {
+  static const bool v1 = getenv("DFRL_ROLLOUT_V1") != nullptr;  // A/B switch: one tile at a time per CTA
+  if (!v1) {
+    constexpr int NP = 3;
+    constexpr int smem2 = rmap<D1, D2, NP>::TOTAL + 1024;
+    static bool attr2 = false;
+    DFRL_TRY(set_smem_once(fused_rollout2_kernel<D0, D1, D2, NOUT, NP>, smem2, &attr2));
+    DFRL_LAUNCH(ctx, (fused_rollout2_kernel<D0, D1, D2, NOUT, NP>), ctas, 160 * NP, smem2, a);
+    return DFRL_OK;
+  }
   constexpr int smem = smem_fwd<D1, D2>::TOTAL + 1024;
   static bool attr = false;
   DFRL_TRY(set_smem_once(fused_rollout_kernel<D0, D1, D2, NOUT>, smem, &attr));
@@ -2997,7 +3257,8 @@ int dfrl_fused_rollout(dfrl_trainer *t, const uint8_t *items_dev, const uint8_t 
   a.counters = t->counters;
   a.inv_w = 1.0f / (float)e->cfg.cap_w;
   a.inv_h = 1.0f / (float)e->cfg.cap_h;
-  int ctas = a.n_tiles < 2 * f->ctas ? a.n_tiles : 2 * f->ctas;
+  const int per_sm = getenv("DFRL_ROLLOUT_V1") ? 2 : 1;  // the multi-pipeline kernel: one CTA per SM
+  int ctas = a.n_tiles < per_sm * f->ctas ? a.n_tiles : per_sm * f->ctas;
   if (f->pnet.d1 == 64)
     DFRL_TRY((launch_rollout<32, 64, 64, 8>(t->ctx, a, ctas)));
   else
