@@ -2999,7 +2999,7 @@ template <int D0, int D1, int D2, int NOUT>
 int launch_rollout(dfrl_ctx *ctx, const rollout_args &a, int ctas) {
   static const bool v1 = getenv("DFRL_ROLLOUT_V1") != nullptr;  // A/B switch: one tile at a time per CTA
   if (!v1) {
-    constexpr int NP = 3;
+    constexpr int NP = 4;
     constexpr int smem2 = rmap<D1, D2, NP>::TOTAL + 1024;
     static bool attr2 = false;
     DFRL_TRY(set_smem_once(fused_rollout2_kernel<D0, D1, D2, NOUT, NP>, smem2, &attr2));
