@@ -314,8 +314,8 @@ def roofline_from_profile(prof, n_envs, peaks):
     P = 2 * 8 + 2
     work = {  # kernel substring -> (algorithmic FLOPs per launch, algorithmic HBM bytes per launch)
         "fused_policy_step": (rows * 3 * fp, rows * (P + 1 + 4 + 4 * 8)),
-        "CRITIC_STEP": (rows * 3 * fv + n_envs * fv, rows * (P + 2 + 4) + n_envs * P),  # fused_critic2_kernel
-        "CRITIC_GAE": ((rows + n_envs) * fv, rows * (P + 2 + 4) + n_envs * P),          # fused_critic2_kernel
+        "CRITIC_STEP": (rows * 3 * fv + n_envs * fv, rows * (P + 2 + 4) + n_envs * P),  # fused_critic_kernel
+        "CRITIC_GAE": ((rows + n_envs) * fv, rows * (P + 2 + 4) + n_envs * P),          # fused_critic_kernel
         "fused_critic_step": (rows * 3 * fv + n_envs * fv, rows * (P + 2 + 4) + n_envs * P),
         "fused_gae": ((rows + n_envs) * fv, rows * (P + 2 + 4) + n_envs * P),
         "fused_rollout": (rows * fp, rows * (P + 2 + 4 * 8) + n_envs * (2 * P + 16)),

@@ -1,8 +1,7 @@
 // fused.cu -- fused small-MLP kernels on the 5th-generation tensor cores (tcgen05 + TMEM).
 //
-// For 3-dense-layer nets  D0 -> D1 -relu-> D2 -relu-> D3  (C2/C4: 32-64-64-{8,1}) one CTA owns a
-// tile of 128 learner rows and runs the WHOLE optimizer::step body for them without touching HBM
-// for activations:
+// For 3-dense-layer nets  D0 -> D1 -relu-> D2 -relu-> D3  (C2/C4: 32-64-64-{8,1}) a tile of 128
+// learner rows runs the WHOLE optimizer::step body without touching HBM for activations:
 //   forward  H1 = relu(X0 W1^T + b1), H2 = relu(H1 W2^T + b2), out = H2 W3^T + b3     (3 UMMA GEMMs)
 //   loss gradient at the output (PPO clipped surrogate / policy_loss / square loss), softmax
 //   Jacobian                                                                         (registers)
@@ -11,13 +10,18 @@
 // Activations live in shared memory as SWIZZLE_128B 16-bit panels (umma.cuh): the same panel is
 // the K-major A operand of the forward GEMM and the MN-major operand of the weight-gradient GEMM.
 //
-// FP32-level accuracy on the 16-bit tensor pipe: every operand is split into hi + lo halves and a
-// product is accumulated as hi*hi + hi*lo + lo*hi in FP32 (TMEM); the dropped lo*lo term is ~2^-17.
-// All operands are BF16 pairs (fp32 exponent range: loss and input gradients span many orders of
-// magnitude). FWD_F16 switches the forward operands (weights, activations) to FP16 pairs pre-scaled
-// by powers of two (22 significant bits); it is off because tcgen05.mma kind::f16 raised an
-// illegal-instruction fault on B200 when the A and B formats differ, which the weight-gradient
-// GEMMs (gradient^T x activation) would need.
+// Every kernel here has the same structure: a CTA runs several tile PIPELINES; a pipeline is 128
+// epilogue threads (one per tile row, all columns) plus one MMA-issuing warp, with its own
+// activation panels, TMEM accumulators, mbarriers and named barriers. A tile's work is a strictly
+// dependent chain MMA -> epilogue -> MMA ...; while one pipeline is in an epilogue the other
+// pipelines' MMAs execute. tcgen05.mma issue blocks the issuing thread for about the pipe time of
+// the instruction (tools/mma_microbench.py), hence the dedicated issuer warps.
+//
+// FP32-level accuracy on the 16-bit tensor pipe: every operand is split into bf16 hi + lo halves
+// and a product is accumulated as hi*hi + hi*lo + lo*hi in FP32 (TMEM); the dropped lo*lo term is
+// ~2^-17. (FP16 pairs with power-of-two pre-scaling, 22 significant bits, were tried for the
+// forward operands in round 1c: tcgen05.mma kind::f16 raised an illegal-instruction fault on B200
+// when the A and B formats differ, which the weight-gradient GEMMs would need.)
 // Every CTA splits the fp32 weights (27 KB, L2 resident) into its own shared-memory panels at
 // start-up: no separate preparation kernel sits on the optimizer-step critical path.
 //
@@ -28,7 +32,6 @@
 // Jacobian), nn.h:85-100 (dW = SUM over rows), policy_gradient.h:196-281 (targets, GAE).
 #include <cuda_fp16.h>
 #include <math.h>
-#include <stdlib.h>
 #include <string.h>
 
 #include "device_fns.cuh"
@@ -39,7 +42,6 @@
 namespace {
 
 constexpr int TILE = 128;
-constexpr bool FWD_F16 = false;  // see the header comment
 constexpr uint32_t PANEL = 128 * 128;  // bytes of one 128-row panel
 
 struct net3 {
@@ -64,9 +66,6 @@ __device__ __forceinline__ tid_t thread_id() {
   return t;
 }
 
-// The single MMA-issuing lane: warp 0 (warp-uniform test), one elected lane.
-__device__ __forceinline__ bool mma_thread(const tid_t &t) { return t.warp == 0 && umma::elect_one(); }
-
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float *v) {
   uint32_t r[8];
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
@@ -85,39 +84,16 @@ __device__ __forceinline__ void tmem_load(uint32_t taddr, float (&v)[DC]) {
   umma::tmem_ld_wait();
 }
 
-// ---- fp32 -> 16-bit hi/lo pairs -------------------------------------------------------------
-// FP16 pair (forward operands; the caller pre-scales so that hi and lo are normal numbers).
-__device__ __forceinline__ void split2_f16(float a, float b, uint32_t &hi, uint32_t &lo) {
-  __half2 h = __floats2half2_rn(a, b);
-  float2 hf = __half22float2(h);
-  __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
-  hi = *reinterpret_cast<uint32_t *>(&h);
-  lo = *reinterpret_cast<uint32_t *>(&l);
-}
-template <bool F16>
+// ---- fp32 -> bf16 hi/lo pairs ------------------------------------------------------------------
+template <bool UNUSED>
 __device__ __forceinline__ void split8(const float *x, uint4 &hi, uint4 &lo) {
-  uint32_t h[4], l[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    if (F16)
-      split2_f16(x[2 * i], x[2 * i + 1], h[i], l[i]);
-    else
-      umma::split2(x[2 * i], x[2 * i + 1], h[i], l[i]);
-  }
-  hi = make_uint4(h[0], h[1], h[2], h[3]);
-  lo = make_uint4(l[0], l[1], l[2], l[3]);
+  umma::split8(x, hi, lo);
 }
-
-// Two fp32 values that are exact in 16 bits -> one packed word in the forward operand format.
+// Two fp32 values that are exact in bf16 -> one packed word.
 __device__ __forceinline__ uint32_t pack2_fwd(float a, float b) {
-  if (FWD_F16) {
-    __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<uint32_t *>(&h);
-  }
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t *>(&h);
 }
-constexpr uint16_t ONE_FWD = FWD_F16 ? 0x3C00 : 0x3F80;
 
 __device__ void zero_bytes(uint8_t *p, uint32_t bytes) {
   for (uint32_t o = threadIdx.x * 16; o < bytes; o += blockDim.x * 16)
@@ -165,56 +141,6 @@ __device__ __forceinline__ void sync_after_smem_writes() {
   umma::fence_after_sync();
 }
 
-// ---------------------------------------------------------------------------------------------
-// Panel image: the head of every fused kernel's shared memory. Weight panels are forward-format
-// hi/lo of (scale * W), swizzled; then biases, the fp32 value-head row and the scale constants.
-template <int D1, int D2>
-struct image_map {
-  static constexpr uint32_t W1_HI = 0, W1_LO = W1_HI + D1 * 128;
-  static constexpr uint32_t W2_HI = W1_LO + D1 * 128, W2_LO = W2_HI + D2 * 128;
-  static constexpr uint32_t W3_HI = W2_LO + D2 * 128, W3_LO = W3_HI + 16 * 128;
-  static constexpr uint32_t FLOATS = W3_LO + 16 * 128;
-  // floats: b1s[D1] (= sh1 b1), b2s[D2] (= sh2 b2), b3[16], w3[64] (fp32 value head), w3s[64]
-  // (= w3 / sh2), k[16] scale constants (see K_*)
-  static constexpr int F_B1 = 0, F_B2 = D1, F_B3 = D1 + D2, F_W3 = D1 + D2 + 16, F_W3S = F_W3 + 64,
-                       F_K = F_W3S + 64, N_FLOATS = F_K + 16;
-  static constexpr uint32_t BYTES = FLOATS + N_FLOATS * 4;
-  static_assert((D1 * 128) % 1024 == 0 && (D2 * 128) % 1024 == 0, "panel alignment");
-  static_assert(BYTES % 16 == 0, "16-byte aligned float region");
-};
-enum {
-  K_C1 = 0,     // sh1 / sw1          : y1 = acc1 * C1 + b1s   (= sh1 * pre-activation 1)
-  K_C2 = 1,     // sh2 / (sh1 sw2)    : y2 = acc2 * C2 + b2s
-  K_C3 = 2,     // 1 / (sh2 sw3)      : logits = acc3 * C3 + b3
-  K_ISW3 = 3,   // 1 / sw3            : dH2 = acc * ISW3
-  K_ISW2 = 4,   // 1 / sw2            : dH1 = acc * ISW2
-  K_ISH1 = 5,   // 1 / sh1            : dW2 = DA * ISH1
-  K_ISH2 = 6,   // 1 / sh2            : dW3 = DC * ISH2
-  K_B3V = 7     // b3[0] (value head bias)
-};
-
-__device__ __forceinline__ float block_max(float v, float *red) {
-  for (int o = 16; o > 0; o >>= 1)
-    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0)
-    red[threadIdx.x >> 5] = v;
-  __syncthreads();
-  float m = red[0];
-  for (int i = 1; i < (int)(blockDim.x >> 5); ++i)
-    m = fmaxf(m, red[i]);
-  return m;
-}
-// Largest power of two s with s * bound < 2^target_exp (bound > 0), exponent clamped.
-__device__ __forceinline__ float pow2_scale(float bound, int target_exp) {
-  if (!(bound > 0.f) || !isfinite(bound))
-    return 1.f;
-  int e = ilogbf(bound);  // 2^e <= bound < 2^(e+1)
-  int k = target_exp - 1 - e;
-  k = k > 60 ? 60 : (k < -60 ? -60 : k);
-  return ldexpf(1.f, k);
-}
-
 // fp32 [N][K] row-major -> forward-format hi / lo panels [rows_alloc][64] of (scale * W), zero padded.
 __device__ void stage_weight_f16(const float *__restrict__ W, int N, int K, int rows_alloc, float scale,
                                  uint8_t *hi, uint8_t *lo) {
@@ -234,178 +160,16 @@ __device__ void stage_weight_f16(const float *__restrict__ W, int N, int K, int 
       }
     }
     uint4 h, l;
-    split8<FWD_F16>(x, h, l);
+    split8<false>(x, h, l);
     uint32_t off = umma::panel_chunk_off(row, chunk);
     *reinterpret_cast<uint4 *>(hi + off) = h;
     *reinterpret_cast<uint4 *>(lo + off) = l;
   }
 }
 
-// Bounds (FWD_F16 scaling only): |obs| <= 1 (bins and items never exceed the capacity), so
-// |H1_j| <= |b1_j| + sum_k |W1_jk| =: h1max and |H2_j| <= |b2_j| + h1max sum_k |W2_jk|.
-template <int D0, int D1, int D2>
-__device__ void build_image(const float *__restrict__ params, const net3 &net, uint8_t *image) {
-  using IM = image_map<D1, D2>;
-  const float *W1 = params + net.o_w1, *W2 = params + net.o_w2, *W3 = params + net.o_w3;
-  float sw1 = 1.f, sw2 = 1.f, sw3 = 1.f, sh1 = 1.f, sh2 = 1.f;
-  if (FWD_F16) {
-    __shared__ float red[8];
-    float m1 = 0.f, m2 = 0.f, m3 = 0.f;
-    for (int i = threadIdx.x; i < D1 * D0; i += blockDim.x) m1 = fmaxf(m1, fabsf(W1[i]));
-    for (int i = threadIdx.x; i < D2 * D1; i += blockDim.x) m2 = fmaxf(m2, fabsf(W2[i]));
-    for (int i = threadIdx.x; i < net.d3 * D2; i += blockDim.x) m3 = fmaxf(m3, fabsf(W3[i]));
-    m1 = block_max(m1, red);
-    m2 = block_max(m2, red);
-    m3 = block_max(m3, red);
-    float h = 0.f;
-    if (threadIdx.x < D1) {
-      float s = fabsf(params[net.o_b1 + threadIdx.x]);
-      for (int k = 0; k < D0; ++k) s += fabsf(W1[threadIdx.x * D0 + k]);
-      h = s;
-    }
-    const float h1max = block_max(h, red);
-    h = 0.f;
-    if (threadIdx.x < D2) {
-      float s = 0.f;
-      for (int k = 0; k < D1; ++k) s += fabsf(W2[threadIdx.x * D1 + k]);
-      h = fabsf(params[net.o_b2 + threadIdx.x]) + h1max * s;
-    }
-    const float h2max = block_max(h, red);
-    // weights -> [512, 1024), activations -> < 2^14: hi and lo halves of everything that matters
-    // are normal FP16 numbers and nothing can overflow (max FP16 = 65504).
-    sw1 = pow2_scale(m1, 10), sw2 = pow2_scale(m2, 10), sw3 = pow2_scale(m3, 10);
-    sh1 = pow2_scale(h1max, 14), sh2 = pow2_scale(h2max, 14);
-  }
-  stage_weight_f16(W1, D1, D0, D1, sw1, image + IM::W1_HI, image + IM::W1_LO);
-  stage_weight_f16(W2, D2, D1, D2, sw2, image + IM::W2_HI, image + IM::W2_LO);
-  stage_weight_f16(W3, net.d3, D2, 16, sw3, image + IM::W3_HI, image + IM::W3_LO);
-  float *fl = reinterpret_cast<float *>(image + IM::FLOATS);
-  for (int i = threadIdx.x; i < D1; i += blockDim.x) fl[IM::F_B1 + i] = params[net.o_b1 + i] * sh1;
-  for (int i = threadIdx.x; i < D2; i += blockDim.x) fl[IM::F_B2 + i] = params[net.o_b2 + i] * sh2;
-  for (int i = threadIdx.x; i < 16; i += blockDim.x) fl[IM::F_B3 + i] = i < net.d3 ? params[net.o_b3 + i] : 0.f;
-  for (int i = threadIdx.x; i < 64; i += blockDim.x) {
-    float w = i < D2 ? W3[i] : 0.f;  // row 0 of W3 (value head)
-    fl[IM::F_W3 + i] = w;
-    fl[IM::F_W3S + i] = w / sh2;
-  }
-  if (threadIdx.x == 0) {
-    float *k = fl + IM::F_K;
-    k[K_C1] = sh1 / sw1;
-    k[K_C2] = sh2 / (sh1 * sw2);
-    k[K_C3] = 1.f / (sh2 * sw3);
-    k[K_ISW3] = 1.f / sw3;
-    k[K_ISW2] = 1.f / sw2;
-    k[K_ISH1] = 1.f / sh1;
-    k[K_ISH2] = 1.f / sh2;
-    k[K_B3V] = params[net.o_b3];
-    for (int i = 8; i < 16; ++i) k[i] = 0.f;
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Shared-memory map of the learner kernels: the image first, then the activation panels.
-template <int D1, int D2>
-struct smem_map {
-  using IM = image_map<D1, D2>;
-  static constexpr uint32_t X0 = (IM::BYTES + 1023) / 1024 * 1024;  // hi only (k/cap is exact in 16 bits)
-  static constexpr uint32_t H_HI = X0 + PANEL;                      // [H1 | H2]   (forward format)
-  static constexpr uint32_t H_LO = H_HI + 2 * PANEL;
-  static constexpr uint32_t DH_HI = H_LO + 2 * PANEL;               // [dH1 | dH2] (bf16)
-  static constexpr uint32_t DH_LO = DH_HI + 2 * PANEL;
-  static constexpr uint32_t DY_HI = DH_LO + 2 * PANEL;              // bf16
-  static constexpr uint32_t DY_LO = DY_HI + PANEL;
-  static constexpr uint32_t SCRATCH = DY_LO + PANEL;                // 8 * TILE floats
-  static constexpr uint32_t RAW_S = SCRATCH + 8 * TILE * 4;         // int8 [18][128] start states
-  static constexpr uint32_t RAW_E = RAW_S + 18 * TILE;              // int8 [18][128] end states
-  static constexpr uint32_t BARS = RAW_E + 18 * TILE;
-  static constexpr uint32_t TOTAL = BARS + 64;
-  static_assert(TOTAL + 1024 <= 232448, "exceeds the 227 KB shared memory of an SM");
-};
-
-// TMEM column map (learner kernels)
-constexpr uint32_t TC_L1 = 0, TC_L2 = 64, TC_L3 = 128, TC_DH2 = 160, TC_DH1 = 224, TC_DA = 288,
-                   TC_DB = 352, TC_DC = 416, TC_COLS = 512;
-
-// TMEM accumulator -> y = acc * c + bias_scaled, relu -> forward-format hi/lo panel. Returns the relu mask
-// of this thread's columns (bit j = column col0 + j was > 0); optionally hands y back.
-template <int D, int NWG, bool WRITE_PANEL, bool KEEP>
-__device__ __forceinline__ uint32_t epi_hidden_fwd(uint32_t tmem_acc, const tid_t &t, float c,
-                                                   const float *__restrict__ bias, uint8_t *hi, uint8_t *lo,
-                                                   float *keep) {
-  constexpr int DC = D / NWG;  // columns per thread: the NWG warpgroups split the row
-  const int col0 = t.wg * DC;
-  float v[DC];
-  tmem_load<DC>(tmem_acc + t.lane_base + col0, v);
-  uint32_t mask = 0;
-#pragma unroll
-  for (int j4 = 0; j4 < DC; j4 += 4) {
-    float4 b = *reinterpret_cast<const float4 *>(bias + col0 + j4);
-    float bb[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      float x = fmaf(v[j4 + q], c, bb[q]);
-      if (x > 0.f)
-        mask |= 1u << (j4 + q);
-      else
-        x = 0.f;
-      v[j4 + q] = x;
-    }
-  }
-  if (KEEP) {
-#pragma unroll
-    for (int j = 0; j < DC; ++j)
-      keep[j] = v[j];
-  }
-  if (WRITE_PANEL) {
-#pragma unroll
-    for (int cc = 0; cc < DC / 8; ++cc) {
-      uint4 h, l;
-      split8<FWD_F16>(&v[8 * cc], h, l);
-      uint32_t off = umma::panel_chunk_off(t.row, col0 / 8 + cc);
-      *reinterpret_cast<uint4 *>(hi + off) = h;
-      *reinterpret_cast<uint4 *>(lo + off) = l;
-    }
-  }
-  return mask;
-}
-// TMEM accumulator -> (* c, . relu mask) -> BF16 hi/lo panel (input-gradient epilogue).
-template <int D, int NWG>
-__device__ __forceinline__ void epi_hidden_bwd(uint32_t tmem_acc, const tid_t &t, float c, uint32_t mask,
-                                               uint8_t *hi, uint8_t *lo) {
-  constexpr int DC = D / NWG;
-  const int col0 = t.wg * DC;
-  float v[DC];
-  tmem_load<DC>(tmem_acc + t.lane_base + col0, v);
-#pragma unroll
-  for (int j = 0; j < DC; ++j)
-    v[j] = (mask >> j) & 1u ? v[j] * c : 0.f;
-#pragma unroll
-  for (int cc = 0; cc < DC / 8; ++cc) {
-    uint4 h, l;
-    split8<false>(&v[8 * cc], h, l);
-    uint32_t off = umma::panel_chunk_off(t.row, col0 / 8 + cc);
-    *reinterpret_cast<uint4 *>(hi + off) = h;
-    *reinterpret_cast<uint4 *>(lo + off) = l;
-  }
-}
-
-// Per-CTA context of the fused kernels.
-struct tile_ctx {
-  uint8_t *smem;
-  uint32_t sbase, tmem;
-  uint64_t *bar;
-  uint32_t phase;
-  tid_t t;
-  __device__ __forceinline__ void wait() {
-    umma::mbar_wait(bar, phase);
-    phase ^= 1;
-    umma::fence_after_sync();
-  }
-};
-
 // idesc shorthands: F = forward-format operand, B = bf16 operand; K = K-major, M = MN-major
 template <int N> struct ID {
-  static constexpr int FB = FWD_F16 ? 0 : 1;  // format code of the forward operands
+  static constexpr int FB = 1;  // format code of the forward operands (bf16)
   static constexpr uint32_t FK_FK = make_idesc(128, N, FB, FB, 0, 0);  // forward: A fwd K, B fwd K
   static constexpr uint32_t BK_FM = make_idesc(128, N, 1, FB, 0, 1);   // dX: A bf16 K-major, B fwd MN-major
   static constexpr uint32_t BM_FM = make_idesc(128, N, 1, FB, 1, 1);   // dW: A = dH^T (bf16), B = H / X0 (fwd)
@@ -416,79 +180,6 @@ template <int N> struct ID {
   static constexpr uint32_t FM_BM_64 = make_idesc(64, N, FB, 1, 1, 1);
 };
 
-// Layers 1 and 2 of a tile whose X0 panel is staged and synchronised. Leaves H1 (and, if
-// WRITE_H2, H2) panels written but NOT yet synchronised. y2 = sh2 * H2 of this thread's columns.
-template <int D0, int D1, int D2, int NWG, typename SM, uint32_t TL1, uint32_t TL2, bool H2_IN_PLACE, bool WRITE_H2>
-__device__ __forceinline__ void fwd_hidden(tile_ctx &c, const float *fl, uint32_t &mask1, uint32_t &mask2,
-                                           float (&y2)[D2 / NWG], uint32_t x0_off = SM::X0) {
-  using IM = image_map<D1, D2>;
-  const float *b1s = fl + IM::F_B1, *b2s = fl + IM::F_B2, *k = fl + IM::F_K;
-  constexpr uint32_t H2_OFF = H2_IN_PLACE ? 0 : PANEL;
-  if (mma_thread(c.t)) {
-    issue_gemm<D0 / 16, false, false, false, true>(c.tmem + TL1, c.sbase + x0_off, 0, c.sbase + IM::W1_HI,
-                                                   c.sbase + IM::W1_LO, ID<D1>::FK_FK, false);
-    umma::commit(c.bar);
-  }
-  c.wait();
-  mask1 = epi_hidden_fwd<D1, NWG, true, false>(c.tmem + TL1, c.t, k[K_C1], b1s, c.smem + SM::H_HI,
-                                               c.smem + SM::H_LO, nullptr);
-  sync_after_smem_writes();
-  if (mma_thread(c.t)) {
-    issue_gemm<D1 / 16, false, false, true, true>(c.tmem + TL2, c.sbase + SM::H_HI, c.sbase + SM::H_LO,
-                                                  c.sbase + IM::W2_HI, c.sbase + IM::W2_LO, ID<D2>::FK_FK, false);
-    umma::commit(c.bar);
-  }
-  c.wait();
-  mask2 = epi_hidden_fwd<D2, NWG, WRITE_H2, true>(c.tmem + TL2, c.t, k[K_C2], b2s, c.smem + SM::H_HI + H2_OFF,
-                                                  c.smem + SM::H_LO + H2_OFF, y2);
-}
-
-// Value head (D2 -> 1) in fp32 registers: each row is held by NWG threads (one per warpgroup,
-// D2/NWG columns each); partial dot products meet in shared memory. Contains one __syncthreads.
-template <int D2, int NWG>
-__device__ __forceinline__ float value_head(const tid_t &t, const float (&y2)[D2 / NWG],
-                                            const float *__restrict__ w3s, float b3, float *vpart) {
-  constexpr int DC = D2 / NWG;
-  float s = 0.f;
-#pragma unroll
-  for (int j = 0; j < DC; ++j)
-    s = fmaf(y2[j], w3s[t.wg * DC + j], s);
-  vpart[t.wg * TILE + t.row] = s;
-  __syncthreads();
-  float v = b3;
-#pragma unroll
-  for (int g = NWG - 1; g >= 0; --g)
-    v += vpart[g * TILE + t.row];
-  return v;
-}
-
-// Common one-time setup: TMEM, barrier, weights -> panel image, zeroed panels, ones column of X0.
-template <int D0, int D1, int D2, typename SM>
-__device__ __forceinline__ void setup_common(tile_ctx &c, uint8_t *smem, const float *params, const net3 &net,
-                                             uint32_t zero_from, uint32_t zero_bytes_n, uint32_t tmem_cols,
-                                             uint32_t *tmem_slot, uint64_t *bar) {
-  using IM = image_map<D1, D2>;
-  c.smem = smem;
-  c.sbase = umma::smem_u32(smem);
-  c.bar = bar;
-  c.phase = 0;
-  c.t = thread_id();
-  if (c.t.warp == 0)
-    umma::tmem_alloc(tmem_slot, tmem_cols);
-  if (threadIdx.x == 0) {
-    umma::mbar_init(bar, 1);
-    umma::fence_mbar_init();
-  }
-  build_image<D0, D1, D2>(params, net, smem);
-  zero_bytes(smem + zero_from, zero_bytes_n);
-  __syncthreads();
-  // ones column (col D0) of the X0 panel: [dH1|dH2]^T . 1 = bias gradients for free
-  if (threadIdx.x < TILE)
-    *reinterpret_cast<uint16_t *>(smem + SM::X0 + umma::panel_off(threadIdx.x, D0)) = ONE_FWD;  // 1.0
-  sync_after_smem_writes();
-  c.tmem = *tmem_slot;
-}
-
 // Learner rows of a tile (row = t * E + e). end_rows: observation of the END state of step (t, e):
 // overflowed terminal state when done, live env state at the rollout's last step, zeros (unused)
 // otherwise.
@@ -498,178 +189,6 @@ struct learner_rows {
   int n, stride, T, E, B;
   float inv_w, inv_h;
 };
-// Staging of a tile's observations. The int8 state planes of the tile's rows are moved
-// global -> registers (prefetch, one tile ahead) -> shared memory RAW [18][128] (plane, row) ->
-// observation::to_vector (bin_packing.h:31-40) into the X0 panel. With E % 16 == 0 each thread
-// moves ONE 16-byte unit (plane, step, 16 environments); nothing consumes a loaded value before
-// the next tile starts, so the loads stay in flight behind the current tile's math.
-struct x0_pref {
-  uint4 rs, rl;   // start-state unit, live-state unit (end rows of the rollout's last step)
-  int done, act;  // of this thread's row (threads < 128, end rows only)
-};
-template <bool END_ROWS>
-__device__ __forceinline__ void load_x0(const learner_rows &L, int tile, x0_pref &x) {
-  const int P = 2 * L.B + 2;
-  x.rs = x.rl = make_uint4(0, 0, 0, 0);
-  x.done = x.act = 0;
-  if (L.E % 16 == 0) {
-    const int upr = L.E / 16;  // units per (step, plane)
-    const int u = threadIdx.x;
-    if (u < L.T * P * upr) {
-      int h = u % upr, plane = (u / upr) % P, tt = u / (upr * P);
-      int i = tile * L.E + 16 * h;
-      if (i < L.stride) {
-        x.rs = *reinterpret_cast<const uint4 *>(L.rec_state + ((size_t)tt * P + plane) * L.stride + i);
-        if (END_ROWS && tt == L.T - 1)
-          x.rl = *reinterpret_cast<const uint4 *>(L.live_state + (size_t)plane * L.stride + i);
-      }
-    }
-  }
-  if (END_ROWS && threadIdx.x < TILE) {
-    int tt = threadIdx.x / L.E, e = threadIdx.x % L.E, i = tile * L.E + e;
-    if (tt < L.T && i < L.n) {
-      size_t k = (size_t)tt * L.n + i;
-      x.done = L.rec_done[k];
-      x.act = L.rec_action[k];
-    }
-  }
-}
-// Registers -> RAW planes in shared memory (followed by a __syncthreads of the caller).
-template <bool END_ROWS>
-__device__ __forceinline__ void stash_x0(int8_t *raw_s, int8_t *raw_e, const learner_rows &L, int tile,
-                                         const x0_pref &x) {
-  const int P = 2 * L.B + 2;
-  if (L.E % 16 == 0) {
-    const int upr = L.E / 16;
-    const int u = threadIdx.x;
-    if (u < L.T * P * upr) {
-      int h = u % upr, plane = (u / upr) % P, tt = u / (upr * P);
-      int off = plane * TILE + tt * L.E + 16 * h;
-      *reinterpret_cast<uint4 *>(raw_s + off) = x.rs;
-      if (END_ROWS)
-        *reinterpret_cast<uint4 *>(raw_e + off) = tt == L.T - 1 ? x.rl : x.rs;
-    }
-  } else {  // generic step counts: byte loads, no prefetch
-    for (int u = threadIdx.x; u < P * TILE; u += blockDim.x) {
-      int plane = u / TILE, r = u % TILE;
-      int tt = r / L.E, e = r % L.E, i = tile * L.E + e;
-      int8_t vs = 0, ve = 0;
-      if (tt < L.T && i < L.n) {
-        vs = L.rec_state[((size_t)tt * P + plane) * L.stride + i];
-        ve = (END_ROWS && tt == L.T - 1) ? L.live_state[(size_t)plane * L.stride + i] : vs;
-      }
-      raw_s[u] = vs;
-      if (END_ROWS)
-        raw_e[u] = ve;
-    }
-  }
-}
-// END state of step (t, e) in RAW_E (after stash_x0 + __syncthreads): overflowed terminal state
-// when done (bin[a] -= item, item kept: bin_packing.h:54-61), live env state at the rollout's last
-// step (already there), zeros (row unused) otherwise. One thread per row.
-__device__ __forceinline__ void fix_end_rows(const int8_t *raw_s, int8_t *raw_e, const learner_rows &L,
-                                             const x0_pref &x) {
-  if (threadIdx.x < TILE) {
-    const int r = threadIdx.x, tt = r / L.E, P = 2 * L.B + 2;
-    if (x.done) {
-      int a = x.act;
-      for (int q = 0; q < P; ++q)  // (the last step's slot holds the live, already reset, state)
-        raw_e[q * TILE + r] = raw_s[q * TILE + r];
-      raw_e[(2 * a) * TILE + r] -= raw_s[(2 * L.B) * TILE + r];
-      raw_e[(2 * a + 1) * TILE + r] -= raw_s[(2 * L.B + 1) * TILE + r];
-    } else if (tt != L.T - 1) {
-      for (int q = 0; q < P; ++q)
-        raw_e[q * TILE + r] = 0;
-    }
-  }
-}
-// RAW planes -> X0 panel: two 16-byte chunks (two bins each) per thread.
-__device__ __forceinline__ void encode_x0(uint8_t *x0, const int8_t *raw, int B, float inv_w, float inv_h) {
-  const int cpr = B / 2;
-  for (int task = threadIdx.x; task < TILE * cpr; task += blockDim.x) {
-    int row = task % TILE, ch = task / TILE;  // a warp = 32 consecutive rows: conflict-free LDS / STS
-    const uint32_t it = pack2_fwd((float)raw[(2 * B) * TILE + row] * inv_w, (float)raw[(2 * B + 1) * TILE + row] * inv_h);
-    uint32_t out[2];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      int b = 2 * ch + h;
-      out[h] = pack2_fwd((float)raw[(2 * b) * TILE + row] * inv_w, (float)raw[(2 * b + 1) * TILE + row] * inv_h);
-    }
-    *reinterpret_cast<uint4 *>(x0 + umma::panel_chunk_off(row, ch)) = make_uint4(out[0], it, out[1], it);
-  }
-}
-
-// ---- staging of the NEXT tile's observations by warpgroup 1 while warpgroup 0 runs the head
-// epilogue (policy step kernel; X0 is double buffered). j = thread index inside the warpgroup.
-// The unit -> (plane, step, 16-env group) decode is tile independent and done once per thread.
-struct x0_units {
-  int raw_off[2];     // byte offset of the unit in the RAW planes, -1: no unit
-  size_t g_off[2];    // byte offset in rec_state, without the tile's env offset
-  int env_off[2];     // 16 * h
-  bool fast;          // E % 16 == 0 (otherwise byte loads at stash time)
-};
-struct x0_pref_wg {
-  uint4 r[2];  // units j and 128 + j (18 planes x 128 rows / 16 bytes = 144 units)
-};
-__device__ __forceinline__ x0_units wg_units(const learner_rows &L, int j) {
-  const int P = 2 * L.B + 2;
-  x0_units U;
-  U.fast = L.E % 16 == 0;
-  const int upr = U.fast ? L.E / 16 : 1, units = U.fast ? L.T * P * upr : 0;
-#pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    const int u = j + q * TILE;
-    U.raw_off[q] = -1;
-    U.g_off[q] = 0;
-    U.env_off[q] = 0;
-    if (j >= 0 && u < units) {
-      int h = u % upr, plane = (u / upr) % P, tt = u / (upr * P);
-      U.raw_off[q] = plane * TILE + tt * L.E + 16 * h;
-      U.g_off[q] = ((size_t)tt * P + plane) * L.stride + 16 * h;
-      U.env_off[q] = 16 * h;
-    }
-  }
-  return U;
-}
-__device__ __forceinline__ void wg_load_x0(const learner_rows &L, const x0_units &U, int tile, x0_pref_wg &x) {
-#pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    x.r[q] = make_uint4(0, 0, 0, 0);
-    if (U.raw_off[q] >= 0 && tile * L.E + U.env_off[q] < L.stride)
-      x.r[q] = *reinterpret_cast<const uint4 *>(L.rec_state + U.g_off[q] + (size_t)tile * L.E);
-  }
-}
-__device__ __forceinline__ void wg_stash_x0(int8_t *raw, const learner_rows &L, const x0_units &U, int tile, int j,
-                                            const x0_pref_wg &x) {
-  if (U.fast) {
-#pragma unroll
-    for (int q = 0; q < 2; ++q)
-      if (U.raw_off[q] >= 0)
-        *reinterpret_cast<uint4 *>(raw + U.raw_off[q]) = x.r[q];
-  } else {
-    const int P = 2 * L.B + 2;
-    for (int u = j; u < P * TILE; u += TILE) {
-      int plane = u / TILE, r = u % TILE;
-      int tt = r / L.E, e = r % L.E, i = tile * L.E + e;
-      raw[u] = (tt < L.T && i < L.n) ? L.rec_state[((size_t)tt * P + plane) * L.stride + i] : (int8_t)0;
-    }
-  }
-}
-// Thread j encodes row j (all B / 2 chunks) of the X0 panel from the RAW planes.
-template <int B>
-__device__ __forceinline__ void wg_encode_x0(uint8_t *x0, const int8_t *raw, float inv_w, float inv_h, int j) {
-  float v[2 * B + 2];
-#pragma unroll
-  for (int q = 0; q < 2 * B + 2; ++q)
-    v[q] = (float)raw[q * TILE + j] * ((q & 1) ? inv_h : inv_w);
-  const uint32_t it = pack2_fwd(v[2 * B], v[2 * B + 1]);
-#pragma unroll
-  for (int ch = 0; ch < B / 2; ++ch)
-    *reinterpret_cast<uint4 *>(x0 + umma::panel_chunk_off(j, ch)) =
-        make_uint4(pack2_fwd(v[4 * ch], v[4 * ch + 1]), it, pack2_fwd(v[4 * ch + 2], v[4 * ch + 3]), it);
-}
-__device__ __forceinline__ void wg_barrier_1() { asm volatile("bar.sync 1, 128;\n" ::: "memory"); }
-
 struct critic_args {
   const float *params;  // flat fp32 parameters of the net
   net3 net;
@@ -680,290 +199,6 @@ struct critic_args {
   float *adv_out;      // [T][n] (GAE kernel)
   float *partials;
 };
-
-// ---------------------------------------------------------------------------------------------
-// update_value_model (policy_gradient.h:196-218) minus the optimizer update: V on start and end
-// rows with the current critic, targets r + gamma V_next (unmasked), dY = V - target, backward,
-// dW partials.
-template <int D0, int D1, int D2, int NWG>
-__global__ void __launch_bounds__(128 * NWG, 1) fused_critic_step_kernel(critic_args a) {
-  using SM = smem_map<D1, D2>;
-  using IM = image_map<D1, D2>;
-  constexpr int DC2 = D2 / NWG;
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t *smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);  // stays a shared-space pointer
-  const float *fl = reinterpret_cast<const float *>(smem + IM::FLOATS);
-  const float *w3 = fl + IM::F_W3, *w3s = fl + IM::F_W3S, *kk = fl + IM::F_K;
-  float *scr = reinterpret_cast<float *>(smem + SM::SCRATCH);
-  float *vpart = scr, *ve = scr + NWG * TILE, *vs = scr + (NWG + 1) * TILE;
-  uint64_t *bar = reinterpret_cast<uint64_t *>(smem + SM::BARS);
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + SM::BARS + 16);
-  const net3 net = a.net;
-  tile_ctx c;
-  setup_common<D0, D1, D2, SM>(c, smem, a.params, a.net, SM::X0, SM::SCRATCH - SM::X0, TC_COLS, tmem_slot, bar);
-  const float b3 = kk[K_B3V];
-  const tid_t t = c.t;
-  const learner_rows &L = a.rows;
-
-  bool dw_pending = false, first_tile = true;
-  float dw3[DC2];
-#pragma unroll
-  for (int j = 0; j < DC2; ++j)
-    dw3[j] = 0.f;
-  float db3 = 0.f;
-
-  int8_t *raw_s = reinterpret_cast<int8_t *>(smem + SM::RAW_S), *raw_e = reinterpret_cast<int8_t *>(smem + SM::RAW_E);
-  // separate observation panels for the end rows (pass 1) and the start rows (pass 2, also the B
-  // operand of the dW1 GEMM; the critic has no dY panel, its slot holds it): a tile never has to
-  // wait for the previous tile's weight-gradient GEMMs
-  constexpr uint32_t X0E = SM::X0, X0S = SM::DY_HI;
-  if (threadIdx.x < TILE)
-    *reinterpret_cast<uint16_t *>(smem + X0S + umma::panel_off(threadIdx.x, D0)) = ONE_FWD;
-  x0_pref xp;
-  if ((int)blockIdx.x < a.n_tiles)
-    load_x0<true>(L, blockIdx.x, xp);
-  for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-    uint32_t m1, m2;
-    float y2[DC2];
-    // ---- pass 1: V of the end rows
-    stash_x0<true>(raw_s, raw_e, L, tile, xp);
-    __syncthreads();
-    fix_end_rows(raw_s, raw_e, L, xp);
-    __syncthreads();
-    encode_x0(smem + X0E, raw_e, L.B, L.inv_w, L.inv_h);
-    sync_after_smem_writes();
-    // row data of this tile (used after the forward passes): issue the loads now
-    const int tt = t.row / L.E, e = t.row % L.E;
-    const int i = tile * L.E + e;
-    const bool valid = tt < L.T && i < L.n;
-    const size_t k = (size_t)tt * L.n + i;
-    const int d = valid ? L.rec_done[k] : 0;
-    fwd_hidden<D0, D1, D2, NWG, SM, TC_L1, TC_L2, false, false>(c, fl, m1, m2, y2, X0E);
-    float v_end = value_head<D2, NWG>(t, y2, w3s, b3, vpart);
-    if (t.wg == 0)
-      ve[t.row] = v_end;
-    // ---- pass 2: start rows, activations kept
-    encode_x0(smem + X0S, raw_s, L.B, L.inv_w, L.inv_h);
-    sync_after_smem_writes();
-    const int next = tile + gridDim.x;
-    if (next < a.n_tiles)  // prefetch the next tile's state bytes behind this tile's math
-      load_x0<true>(L, next, xp);
-    fwd_hidden<D0, D1, D2, NWG, SM, TC_L1, TC_L2, false, false>(c, fl, m1, m2, y2, X0S);
-    float v = value_head<D2, NWG>(t, y2, w3s, b3, vpart);
-    if (t.wg == 0)
-      vs[t.row] = v;
-    __syncthreads();
-    // ---- targets and dY = V - target (square_loss_grad, nn.h:548-550)
-    {
-      float dy = 0.f;
-      if (valid) {
-        bool ends = d || tt == L.T - 1;
-        float vn = ends ? ve[t.row] : vs[t.row + L.E];
-        float tgt = (d ? 0.f : 1.f) + a.gamma * vn;  // not masked at terminals (quirk 6)
-        dy = v - tgt;
-        if (t.wg == 0 && a.targets_out)
-          a.targets_out[k] = tgt;
-      }
-      // dH2 = dY w3 . relu'(H2) (rank-1: no GEMM); dW3 += dY H2; db3 += dY
-      float g[DC2];
-#pragma unroll
-      for (int j = 0; j < DC2; ++j) {
-        g[j] = (m2 >> j) & 1u ? dy * w3[t.wg * DC2 + j] : 0.f;
-        dw3[j] = fmaf(dy, y2[j], dw3[j]);
-      }
-      if (t.wg == 0)
-        db3 += dy;
-#pragma unroll
-      for (int cc = 0; cc < DC2 / 8; ++cc) {
-        uint4 h, l;
-        split8<false>(&g[8 * cc], h, l);
-        uint32_t off = umma::panel_chunk_off(t.row, (t.wg * DC2) / 8 + cc);
-        *reinterpret_cast<uint4 *>(smem + SM::DH_HI + PANEL + off) = h;
-        *reinterpret_cast<uint4 *>(smem + SM::DH_LO + PANEL + off) = l;
-      }
-    }
-    sync_after_smem_writes();
-    // ---- dH1 = dH2 . W2, relu mask; dW2 += dH2^T . H1 runs behind the dH1 epilogue
-    if (mma_thread(t)) {
-      issue_gemm<D2 / 16, false, true, true, true>(c.tmem + TC_DH1, c.sbase + SM::DH_HI + PANEL,
-                                                   c.sbase + SM::DH_LO + PANEL, c.sbase + IM::W2_HI,
-                                                   c.sbase + IM::W2_LO, ID<D1>::BK_FM, false);
-      umma::commit(c.bar);
-      issue_gemm<8, true, true, true, true>(c.tmem + TC_DA, c.sbase + SM::DH_HI + PANEL, c.sbase + SM::DH_LO + PANEL,
-                                            c.sbase + SM::H_HI, c.sbase + SM::H_LO, ID<64>::BM_FM_64, !first_tile);
-    }
-    c.wait();
-    epi_hidden_bwd<D1, NWG>(c.tmem + TC_DH1, t, kk[K_ISW2], m1, smem + SM::DH_HI, smem + SM::DH_LO);
-    sync_after_smem_writes();
-    if (mma_thread(t)) {
-      issue_gemm<8, true, true, true, false>(c.tmem + TC_DB, c.sbase + SM::DH_HI, c.sbase + SM::DH_LO,
-                                             c.sbase + X0S, 0, ID<D0 + 16>::BM_FM, !first_tile);
-      if (next >= a.n_tiles)  // otherwise the next tile's first commit covers these MMAs
-        umma::commit(c.bar);
-    }
-    dw_pending = next >= a.n_tiles;
-    first_tile = false;
-  }
-
-  float *part = a.partials + (size_t)blockIdx.x * net.n_params;
-  if (dw_pending)
-    c.wait();
-  if (first_tile) {  // CTA had no tile
-    for (int i = threadIdx.x; i < net.n_params; i += blockDim.x)
-      part[i] = 0.f;
-  } else {
-    {
-      constexpr int DC = D1 / NWG;
-      float v[DC];
-      tmem_load<DC>(c.tmem + TC_DA + t.lane_base + t.wg * DC, v);
-      int nrow = t.lane < 16 ? t.w * 16 + t.lane : -1;  // M = 64: row n in TMEM lane 32 (n / 16) + n % 16
-      const float s = kk[K_ISH1];
-      if (nrow >= 0 && nrow < D2)
-#pragma unroll
-        for (int j = 0; j < DC; ++j)
-          part[net.o_w2 + nrow * D1 + t.wg * DC + j] = v[j] * s;
-    }
-    if (t.wg < 2) {
-      constexpr int DC = (D0 + 16) / 2;
-      float v[DC];
-      tmem_load<DC>(c.tmem + TC_DB + t.lane_base + t.wg * DC, v);
-#pragma unroll
-      for (int j = 0; j < DC; ++j) {
-        int col = t.wg * DC + j;
-        if (t.row < D1) {
-          if (col < D0)
-            part[net.o_w1 + t.row * D0 + col] = v[j];
-          else if (col == D0)
-            part[net.o_b1 + t.row] = v[j];
-        } else if (t.row >= 64 && t.row - 64 < D2 && col == D0) {
-          part[net.o_b2 + t.row - 64] = v[j];
-        }
-      }
-    }
-    // dW3 / db3: thread-local sums -> fixed-order column sums through shared memory (reuse the H
-    // panels as fp32 scratch: [128 rows][D2 + 1])
-    __syncthreads();
-    float *red = reinterpret_cast<float *>(smem + SM::H_HI);
-    const float s2 = kk[K_ISH2];
-#pragma unroll
-    for (int j = 0; j < DC2; ++j)
-      red[t.row * (D2 + 1) + t.wg * DC2 + j] = dw3[j] * s2;
-    if (t.wg == 0)
-      red[t.row * (D2 + 1) + D2] = db3;
-    __syncthreads();
-    if (threadIdx.x <= D2) {
-      float s = 0.f;
-      for (int r = 0; r < TILE; ++r)
-        s += red[r * (D2 + 1) + threadIdx.x];
-      if (threadIdx.x < D2)
-        part[net.o_w3 + threadIdx.x] = s;
-      else
-        part[net.o_b3] = s;
-    }
-  }
-  umma::fence_before_sync();
-  __syncthreads();
-  if (t.warp == 0)
-    umma::tmem_dealloc(c.tmem, TC_COLS);
-}
-
-// ---------------------------------------------------------------------------------------------
-// Forward-only kernels (rollout, GAE): image + X0 + one H panel pair (H2 overwrites H1).
-// 2 CTAs per SM (<= 100 KB shared memory, 256 TMEM columns each) so that one CTA's epilogue
-// overlaps the other's MMAs.
-template <int D1, int D2>
-struct smem_fwd {
-  using IM = image_map<D1, D2>;
-  static constexpr uint32_t X0 = (IM::BYTES + 1023) / 1024 * 1024;
-  static constexpr uint32_t H_HI = X0 + PANEL, H_LO = H_HI + PANEL;  // H1, then H2 in place
-  static constexpr uint32_t SCRATCH = H_LO + PANEL;                  // 4 * TILE floats
-  static constexpr uint32_t STATE = SCRATCH + 4 * TILE * 4;          // int8 [18][128] (rollout: live tile state)
-  static constexpr uint32_t RAW_S = STATE;                           // GAE: start states
-  static constexpr uint32_t RAW_E = STATE + 18 * TILE;               // GAE: end states
-  static constexpr uint32_t BARS = RAW_E + 18 * TILE;
-  static constexpr uint32_t TOTAL = BARS + 64;
-  static_assert(2 * (TOTAL + 1024 + 1024) <= 232448, "two CTAs per SM");
-};
-constexpr uint32_t TF_L1 = 0, TF_L2 = 64, TF_L3 = 128, TF_COLS = 256;
-
-// calculate_advantage (policy_gradient.h:220-281) with the updated critic: V of start / end
-// rows, then GAE per environment (all T steps of an env live in the tile).
-template <int D0, int D1, int D2>
-__global__ void __launch_bounds__(256, 2) fused_gae_kernel(critic_args a) {
-  using SM = smem_fwd<D1, D2>;
-  using IM = image_map<D1, D2>;
-  constexpr int DC2 = D2 / 2;
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t *smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);  // stays a shared-space pointer
-  const float *fl = reinterpret_cast<const float *>(smem + IM::FLOATS);
-  const float *w3s = fl + IM::F_W3S, *kk = fl + IM::F_K;
-  float *scr = reinterpret_cast<float *>(smem + SM::SCRATCH);
-  float *vpart = scr, *ve = scr + 2 * TILE, *vs = scr + 3 * TILE;
-  uint64_t *bar = reinterpret_cast<uint64_t *>(smem + SM::BARS);
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + SM::BARS + 16);
-  tile_ctx c;
-  setup_common<D0, D1, D2, SM>(c, smem, a.params, a.net, SM::X0, SM::SCRATCH - SM::X0, TF_COLS, tmem_slot, bar);
-  const float b3 = kk[K_B3V];
-  const tid_t t = c.t;
-  const learner_rows &L = a.rows;
-  int8_t *raw_s = reinterpret_cast<int8_t *>(smem + SM::RAW_S), *raw_e = reinterpret_cast<int8_t *>(smem + SM::RAW_E);
-  x0_pref xp;
-  if ((int)blockIdx.x < a.n_tiles)
-    load_x0<true>(L, blockIdx.x, xp);
-  for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-    uint32_t m1, m2;
-    float y2[DC2];
-    stash_x0<true>(raw_s, raw_e, L, tile, xp);
-    __syncthreads();
-    fix_end_rows(raw_s, raw_e, L, xp);
-    __syncthreads();
-    encode_x0(smem + SM::X0, raw_e, L.B, L.inv_w, L.inv_h);
-    sync_after_smem_writes();
-    // done flags of the env this thread walks in the GAE step (threads < E), loaded early
-    uint32_t dmask = 0;
-    if ((int)threadIdx.x < L.E && tile * L.E + (int)threadIdx.x < L.n)
-      for (int tt = 0; tt < L.T && tt < 32; ++tt)
-        dmask |= (uint32_t)(L.rec_done[(size_t)tt * L.n + tile * L.E + threadIdx.x] != 0) << tt;
-    fwd_hidden<D0, D1, D2, 2, SM, TF_L1, TF_L2, true, false>(c, fl, m1, m2, y2);
-    float v_end = value_head<D2, 2>(t, y2, w3s, b3, vpart);
-    if (t.wg == 0)
-      ve[t.row] = v_end;
-    encode_x0(smem + SM::X0, raw_s, L.B, L.inv_w, L.inv_h);
-    sync_after_smem_writes();
-    const int next = tile + gridDim.x;
-    if (next < a.n_tiles)
-      load_x0<true>(L, next, xp);
-    fwd_hidden<D0, D1, D2, 2, SM, TF_L1, TF_L2, true, false>(c, fl, m1, m2, y2);
-    float v = value_head<D2, 2>(t, y2, w3s, b3, vpart);
-    if (t.wg == 0)
-      vs[t.row] = v;
-    __syncthreads();
-    // GAE: thread e < E walks its env backwards (same recurrence as device_fns.cuh gae_env)
-    if ((int)threadIdx.x < L.E) {
-      int e = threadIdx.x, i = tile * L.E + e;
-      if (i < L.n) {
-        float a_next = 0.f;
-        for (int tt = L.T - 1; tt >= 0; --tt) {
-          size_t k = (size_t)tt * L.n + i;
-          int r = tt * L.E + e;
-          int d = L.T <= 32 ? (int)((dmask >> tt) & 1u) : (int)L.rec_done[k];
-          bool ends = d || tt == L.T - 1;
-          float vn = ends ? ve[r] : vs[r + L.E];
-          float vn_adv = d ? 0.f : vn;
-          float delta = (d ? 0.f : 1.f) + a.gamma * vn_adv - vs[r];
-          float adv = delta + (ends ? 0.f : a.lambda * a.gamma * a_next);
-          a.adv_out[k] = adv;
-          a_next = adv;
-        }
-      }
-    }
-    __syncthreads();
-  }
-  umma::fence_before_sync();
-  __syncthreads();
-  if (t.warp == 0)
-    umma::tmem_dealloc(c.tmem, TF_COLS);
-}
 
 enum { HEAD_JACOBIAN = 0, HEAD_IDENTITY = 1 };
 
@@ -978,294 +213,6 @@ struct policy_step_args {
   float *partials;     // [gridDim.x][n_params]
   long long *clk;      // optional: phase clocks of CTA 0 (debug)
 };
-
-// ---------------------------------------------------------------------------------------------
-// One policy optimizer::step minus the update: forward + loss gradient + backward + dW partials.
-template <int D0, int D1, int D2, int NOUT, int NWG>
-__global__ void __launch_bounds__(128 * NWG, 1) fused_policy_step_kernel(policy_step_args a) {
-  using SM = smem_map<D1, D2>;
-  using IM = image_map<D1, D2>;
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t *smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);  // stays a shared-space pointer
-  const float *fl = reinterpret_cast<const float *>(smem + IM::FLOATS);
-  const float *b3 = fl + IM::F_B3, *kk = fl + IM::F_K;
-  float *red = reinterpret_cast<float *>(smem + SM::SCRATCH);
-  uint64_t *bar = reinterpret_cast<uint64_t *>(smem + SM::BARS);
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + SM::BARS + 16);
-  const net3 net = a.net;
-  tile_ctx c;
-  setup_common<D0, D1, D2, SM>(c, smem, a.params, a.net, SM::X0, SM::SCRATCH - SM::X0, TC_COLS, tmem_slot, bar);
-  const tid_t t = c.t;
-  const learner_rows &L = a.rows;
-  const uint32_t tmem = c.tmem, sbase = c.sbase;
-
-  bool dw_pending = false, first_tile = true;
-  float db3[NOUT];
-#pragma unroll
-  for (int j = 0; j < NOUT; ++j)
-    db3[j] = 0.f;
-
-  // optional phase clocks of CTA 0 (dfrl_debug_policy_clocks): 12 stamps per tile, first 8 tiles
-  long long *clk = (a.clk && blockIdx.x == 0 && threadIdx.x == 32 * (4 * NWG - 1)) ? a.clk : nullptr;
-  int clk_n = 0;
-#define STAMP() do { if (clk && clk_n < 112) clk[clk_n++] = clock64(); } while (0)
-
-  // X0 is double buffered (second buffer = the slot a separate lo panel of dY would take: dY is
-  // a packed panel, hi in columns 0..15, lo in 16..31): warpgroup 1 stages tile i+1 while
-  // warpgroup 0 runs the head epilogue of tile i, and no tile waits for the previous one's dW GEMMs.
-  static_assert(NWG == 2, "the staging / head split assumes two warpgroups");
-  constexpr uint32_t X0_A = SM::X0, X0_B = SM::DY_LO;
-  constexpr uint32_t DY = SM::DY_HI, DY_LOFF = 32;  // byte offset of the lo half inside the panel
-  int8_t *raw_s = reinterpret_cast<int8_t *>(smem + SM::RAW_S);
-  const int j1 = (int)threadIdx.x - TILE;  // index inside warpgroup 1
-  const x0_units xu = wg_units(L, j1);
-  if (threadIdx.x < TILE)  // ones column of the second X0 buffer
-    *reinterpret_cast<uint16_t *>(smem + X0_B + umma::panel_off(threadIdx.x, D0)) = ONE_FWD;
-  if ((int)blockIdx.x < a.n_tiles) {  // first tile: staged by everybody
-    x0_pref xp;
-    load_x0<false>(L, blockIdx.x, xp);
-    stash_x0<false>(raw_s, nullptr, L, blockIdx.x, xp);
-    __syncthreads();
-    encode_x0(smem + X0_A, raw_s, L.B, L.inv_w, L.inv_h);
-  }
-  sync_after_smem_writes();
-  int buf = 0;
-  for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, buf ^= 1) {
-    const uint32_t x0_cur = buf ? X0_B : X0_A, x0_next = buf ? X0_A : X0_B;
-    STAMP();
-    STAMP();
-    // ---- layer 1 issue first, then the global loads that are consumed later: row data for the
-    // head epilogue and the next tile's observation chunks
-    if (mma_thread(t)) {
-      issue_gemm<D0 / 16, false, false, false, true>(tmem + TC_L1, sbase + x0_cur, 0, sbase + IM::W1_HI,
-                                                     sbase + IM::W1_LO, ID<D1>::FK_FK, false);
-      umma::commit(c.bar);
-    }
-    const int tt = t.row / L.E, e = t.row % L.E;
-    const int i = tile * L.E + e;
-    const bool valid = t.wg == 0 && tt < L.T && i < L.n;
-    const size_t k = (size_t)tt * L.n + i;
-    int act = 0;
-    float A = 0.f;
-    float4 po[NOUT / 4];  // the whole p_old row: no load depends on another load's result
-#pragma unroll
-    for (int j = 0; j < NOUT / 4; ++j)
-      po[j] = make_float4(1.f, 1.f, 1.f, 1.f);
-    if (valid) {
-      act = L.rec_action[k];
-      A = a.adv[k];
-      const float4 *pr = reinterpret_cast<const float4 *>(a.p_old + k * NOUT);
-#pragma unroll
-      for (int j = 0; j < NOUT / 4; ++j)
-        po[j] = pr[j];
-    }
-    const int next = tile + gridDim.x;
-    x0_pref_wg xw;
-    if (t.wg == 1 && next < a.n_tiles)
-      wg_load_x0(L, xu, next, xw);
-    c.wait();
-    STAMP();
-    const uint32_t mask1 = epi_hidden_fwd<D1, NWG, true, false>(tmem + TC_L1, t, kk[K_C1], fl + IM::F_B1,
-                                                           smem + SM::H_HI, smem + SM::H_LO, nullptr);
-    sync_after_smem_writes();
-    STAMP();
-    if (mma_thread(t)) {
-      issue_gemm<D1 / 16, false, false, true, true>(tmem + TC_L2, sbase + SM::H_HI, sbase + SM::H_LO,
-                                                    sbase + IM::W2_HI, sbase + IM::W2_LO, ID<D2>::FK_FK, false);
-      umma::commit(c.bar);
-    }
-    c.wait();
-    STAMP();
-    const uint32_t mask2 = epi_hidden_fwd<D2, NWG, true, false>(tmem + TC_L2, t, kk[K_C2], fl + IM::F_B2,
-                                                           smem + SM::H_HI + PANEL, smem + SM::H_LO + PANEL, nullptr);
-    sync_after_smem_writes();
-    STAMP();
-    // ---- layer 3 (head, N padded to 16)
-    if (mma_thread(t)) {
-      issue_gemm<D2 / 16, false, false, true, true>(tmem + TC_L3, sbase + SM::H_HI + PANEL, sbase + SM::H_LO + PANEL,
-                                                    sbase + IM::W3_HI, sbase + IM::W3_LO, ID<16>::FK_FK, false);
-      umma::commit(c.bar);
-    }
-    c.wait();
-    STAMP();
-    // ---- head epilogue: softmax, loss gradient, softmax backward -> dY panel (cols 0..NOUT-1)
-    if (t.wg == 0) {
-      float v[8];
-      tmem_load<8>(tmem + TC_L3 + t.lane_base, v);
-      float dl[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        dl[j] = 0.f;
-      if (valid) {
-        const float c3 = kk[K_C3];
-        float p[NOUT], s = 0.f;
-#pragma unroll
-        for (int j = 0; j < NOUT; ++j) {
-          p[j] = expf(fmaf(v[j], c3, b3[j]));  // no max subtraction (nn.h:382-392)
-          s += p[j];
-        }
-        const float inv_s = 1.f / s;
-#pragma unroll
-        for (int j = 0; j < NOUT; ++j)
-          p[j] = p[j] * inv_s;
-        float g[NOUT];
-        if (a.loss_kind == DFRL_LOSS_CLIPPED) {
-          float pa = 0.f, pold = 1.f;
-          const float *pof = reinterpret_cast<const float *>(po);
-#pragma unroll
-          for (int j = 0; j < NOUT; ++j) {
-            pa = (j == act) ? p[j] : pa;
-            pold = (j == act) ? pof[j] : pold;
-          }
-          float gc = clipped_grad(pa, pold, A);
-#pragma unroll
-          for (int j = 0; j < NOUT; ++j)
-            g[j] = (j == act) ? gc : 0.f;
-        } else {
-#pragma unroll
-          for (int j = 0; j < NOUT; ++j)
-            g[j] = p[j] * A - (j == act ? A : 0.f);
-        }
-        if (a.head_bwd == HEAD_JACOBIAN) {
-          float dot = 0.f;
-#pragma unroll
-          for (int j = 0; j < NOUT; ++j)
-            dot = fmaf(p[j], g[j], dot);
-#pragma unroll
-          for (int j = 0; j < NOUT; ++j)
-            dl[j] = p[j] * (g[j] - dot);
-        } else {
-#pragma unroll
-          for (int j = 0; j < NOUT; ++j)
-            dl[j] = g[j];
-        }
-#pragma unroll
-        for (int j = 0; j < NOUT; ++j)
-          db3[j] += dl[j];
-      }
-      uint4 h, l;
-      split8<false>(dl, h, l);
-      *reinterpret_cast<uint4 *>(smem + DY + umma::panel_chunk_off(t.row, 0)) = h;
-      *reinterpret_cast<uint4 *>(smem + DY + umma::panel_chunk_off(t.row, 2)) = l;
-    } else if (next < a.n_tiles) {
-      // ---- meanwhile warpgroup 1: observations of the next tile into the other X0 buffer (its last
-      // reader, the previous tile's dW1 GEMM, completed before this tile's layer-1 GEMM did)
-      wg_stash_x0(raw_s, L, xu, next, j1, xw);
-      wg_barrier_1();
-      STAMP();
-      wg_encode_x0<NOUT>(smem + x0_next, raw_s, L.inv_w, L.inv_h, j1);
-      STAMP();
-    }
-    sync_after_smem_writes();
-    STAMP();
-    // ---- dH2 = dY . W3 (contraction over the 16 padded outputs); dW3^T += H2^T . dY (M = 64) runs
-    // behind the dH2 epilogue
-    if (mma_thread(t)) {
-      issue_gemm<1, false, true, true, true>(tmem + TC_DH2, sbase + DY, sbase + DY + DY_LOFF, sbase + IM::W3_HI,
-                                             sbase + IM::W3_LO, ID<D2>::BK_FM, false);
-      umma::commit(c.bar);
-      issue_gemm<8, true, true, true, true>(tmem + TC_DC, sbase + SM::H_HI + PANEL, sbase + SM::H_LO + PANEL,
-                                            sbase + DY, sbase + DY + DY_LOFF, ID<16>::FM_BM_64, !first_tile);
-    }
-    c.wait();
-    STAMP();
-    epi_hidden_bwd<D2, NWG>(tmem + TC_DH2, t, kk[K_ISW3], mask2, smem + SM::DH_HI + PANEL, smem + SM::DH_LO + PANEL);
-    sync_after_smem_writes();
-    STAMP();
-    // ---- dH1 = dH2 . W2; dW2 += dH2^T . H1 (M = 64) runs behind the dH1 epilogue
-    if (mma_thread(t)) {
-      issue_gemm<D2 / 16, false, true, true, true>(tmem + TC_DH1, sbase + SM::DH_HI + PANEL, sbase + SM::DH_LO + PANEL,
-                                                   sbase + IM::W2_HI, sbase + IM::W2_LO, ID<D1>::BK_FM, false);
-      umma::commit(c.bar);
-      issue_gemm<8, true, true, true, true>(tmem + TC_DA, sbase + SM::DH_HI + PANEL, sbase + SM::DH_LO + PANEL,
-                                            sbase + SM::H_HI, sbase + SM::H_LO, ID<64>::BM_FM_64, !first_tile);
-    }
-    c.wait();
-    STAMP();
-    epi_hidden_bwd<D1, NWG>(tmem + TC_DH1, t, kk[K_ISW2], mask1, smem + SM::DH_HI, smem + SM::DH_LO);
-    sync_after_smem_writes();
-    STAMP();
-    //   DB[128 x D0+16] += [dH1|dH2]^T . [X0|1]   rows 0.. = [dW1 | db1], rows 64.. col D0 = db2
-    if (mma_thread(t)) {
-      issue_gemm<8, true, true, true, false>(tmem + TC_DB, sbase + SM::DH_HI, sbase + SM::DH_LO, sbase + x0_cur, 0,
-                                             ID<D0 + 16>::BM_FM, !first_tile);
-      // the next tile's layer-1 commit also covers these MMAs (one wait per commit, in order);
-      // only the CTA's last tile commits here, for the drain
-      if (next >= a.n_tiles)
-        umma::commit(c.bar);
-    }
-    dw_pending = next >= a.n_tiles;
-    first_tile = false;
-  }
-
-  // ---- drain: partial gradient of this CTA -> global, in the flat parameter layout
-  float *part = a.partials + (size_t)blockIdx.x * net.n_params;
-  if (dw_pending)
-    c.wait();
-  if (first_tile) {  // CTA had no tile: contribute zeros
-    for (int i = threadIdx.x; i < net.n_params; i += blockDim.x)
-      part[i] = 0.f;
-  } else {
-    // dW2[n][k]: DA (M = 64) row n = TMEM lane 32 (n / 16) + n % 16, col k
-    {
-      constexpr int DC = D1 / NWG;
-      float v[DC];
-      tmem_load<DC>(tmem + TC_DA + t.lane_base + t.wg * DC, v);
-      int nrow = t.lane < 16 ? t.w * 16 + t.lane : -1;
-      const float s = kk[K_ISH1];
-      if (nrow >= 0 && nrow < D2)
-#pragma unroll
-        for (int j = 0; j < DC; ++j)
-          part[net.o_w2 + nrow * D1 + t.wg * DC + j] = v[j] * s;
-    }
-    // dW1[n][k] + db1[n]: DB row n, cols 0..D0-1 and D0; db2[n]: DB row 64 + n, col D0
-    if (t.wg < 2) {
-      constexpr int DC = (D0 + 16) / 2;
-      float v[DC];
-      tmem_load<DC>(tmem + TC_DB + t.lane_base + t.wg * DC, v);
-#pragma unroll
-      for (int j = 0; j < DC; ++j) {
-        int col = t.wg * DC + j;
-        if (t.row < D1) {
-          if (col < D0)
-            part[net.o_w1 + t.row * D0 + col] = v[j];
-          else if (col == D0)
-            part[net.o_b1 + t.row] = v[j];
-        } else if (t.row >= 64 && t.row - 64 < D2 && col == D0) {
-          part[net.o_b2 + t.row - 64] = v[j];
-        }
-      }
-    }
-    // dW3[n][k] = DC (M = 64) row k, col n
-    if (t.wg == 0) {
-      float v[8];
-      tmem_load<8>(tmem + TC_DC + t.lane_base, v);
-      int krow = t.lane < 16 ? t.w * 16 + t.lane : -1;
-      const float s = kk[K_ISH2];
-      if (krow >= 0 && krow < D2)
-#pragma unroll
-        for (int j = 0; j < NOUT; ++j)
-          part[net.o_w3 + j * D2 + krow] = v[j] * s;
-    }
-    // db3: per-thread partial sums -> fixed-order block sum
-    if (t.wg == 0)
-#pragma unroll
-      for (int j = 0; j < NOUT; ++j)
-        red[t.row * 8 + j] = db3[j];
-    __syncthreads();
-    if (threadIdx.x < NOUT) {
-      float s = 0.f;
-      for (int r = 0; r < TILE; ++r)
-        s += red[r * 8 + threadIdx.x];
-      part[net.o_b3 + threadIdx.x] = s;
-    }
-  }
-#undef STAMP
-  umma::fence_before_sync();
-  __syncthreads();
-  if (t.warp == 0)
-    umma::tmem_dealloc(tmem, TC_COLS);
-}
 
 // ---------------------------------------------------------------------------------------------
 // Policy step, two tile pipelines per CTA.
@@ -1332,7 +279,7 @@ __device__ void stage_w1_packed(const float *__restrict__ W1, uint8_t *panel) {
 }
 
 template <int D0, int D1, int D2, int NOUT>
-__device__ void build_image2(const float *__restrict__ params, const net3 &net, uint8_t *smem) {
+__device__ void build_policy_image(const float *__restrict__ params, const net3 &net, uint8_t *smem) {
   using PM = pmap<D1, D2>;
   const float *W1 = params + net.o_w1, *W2 = params + net.o_w2, *W3 = params + net.o_w3;
   static_assert(D0 == 32 && NOUT == 8, "packed W1 / stacked W3 panels assume 32 inputs, 8 outputs");
@@ -1372,16 +319,6 @@ __device__ __forceinline__ void issue_gemm_mn_lbo(uint32_t tmem_d, uint32_t a_hi
     umma::mma_bf16(tmem_d, desc_lo_hi(al0 + k * step), bh, idesc, 1);
   }
 }
-
-__device__ __forceinline__ void wg_bar(int wg) { asm volatile("bar.sync %0, 128;\n" ::"r"(wg + 1) : "memory"); }
-__device__ __forceinline__ void wg_sync_after_smem_writes(int wg) {
-  umma::fence_proxy_async();
-  umma::fence_before_sync();
-  wg_bar(wg);
-  umma::fence_after_sync();
-}
-// One lane of warp 0 of each warpgroup issues that warpgroup's MMAs (warp-uniform test).
-__device__ __forceinline__ bool wg_mma_thread(const tid_t &t) { return (t.warp & 3) == 0 && umma::elect_one(); }
 
 // TMEM accumulator (this thread's row, all D columns) -> + bias, relu -> hi/lo panels. No relu mask
 // is kept: the backward epilogue of the same thread reads it off the hi panel (H > 0 <=> hi(H) > 0).
@@ -1494,7 +431,7 @@ __device__ __forceinline__ void ready_sync(int wg, uint32_t &parity) {
 // time of the instruction (measured: tools/mma_microbench.py), so a GEMM that is meant to run behind
 // an epilogue must not be issued by a thread that takes part in that epilogue.
 template <int D0, int D1, int D2, int NOUT>
-__global__ void __launch_bounds__(320, 1) fused_policy_step2_kernel(policy_step_args a) {
+__global__ void __launch_bounds__(320, 1) fused_policy_step_kernel(policy_step_args a) {
   using PM = pmap<D1, D2>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);  // stays a shared-space pointer
@@ -1518,7 +455,7 @@ __global__ void __launch_bounds__(320, 1) fused_policy_step2_kernel(policy_step_
       umma::mbar_init(bars + q, 1);
     umma::fence_mbar_init();
   }
-  build_image2<D0, D1, D2, NOUT>(a.params, net, smem);
+  build_policy_image<D0, D1, D2, NOUT>(a.params, net, smem);
   zero_bytes(smem + PM::DH1_HI, PM::BARS - PM::DH1_HI);
   __syncthreads();
   // ones column (col D0) of both XD panels: [dH1|dH2]^T . 1 = bias gradients for free
@@ -1866,7 +803,7 @@ __global__ void __launch_bounds__(320, 1) fused_policy_step2_kernel(policy_step_
 
 // ---------------------------------------------------------------------------------------------
 // Critic step (update_value_model, policy_gradient.h:196-218, minus the optimizer update) and GAE
-// (calculate_advantage, 220-281) with the structure of fused_policy_step2_kernel: two tile
+// (calculate_advantage, 220-281) with the structure of fused_policy_step_kernel: two tile
 // pipelines per CTA, one epilogue thread per row, one MMA-issuing warp per pipeline.
 // Per tile: V(end rows) [layer 1, layer 2, value head in fp32 registers], V(start rows), exchange
 // of the values inside the tile, then
@@ -1974,7 +911,7 @@ __device__ __forceinline__ float epi2_value(uint32_t acc, const tid_t &t, const 
 }
 
 template <int D0, int D1, int D2, int MODE>
-__global__ void __launch_bounds__(320, 1) fused_critic2_kernel(critic_args a) {
+__global__ void __launch_bounds__(320, 1) fused_critic_kernel(critic_args a) {
   using CM = cmap<D1, D2>;
   constexpr int NB = 8;  // bins (the fused path covers the 8-bin problem)
   static_assert(D0 == 4 * NB, "observation width");
@@ -2077,7 +1014,7 @@ __global__ void __launch_bounds__(320, 1) fused_critic2_kernel(critic_args a) {
       }
       ready_sync(wg, rp);  // (dH1 in the shared slot and) the next tile's end-row observations
       if (umma::elect_one()) {
-        if (j + 2 < nt)  // ahead of dW1: see fused_policy_step2_kernel
+        if (j + 2 < nt)  // ahead of dW1: see fused_policy_step_kernel
           layer1(wbase + CM::H1_LO, bar);
         if (MODE == CRITIC_STEP) {
           //   DB[128 x D0+16] += [dH1|dH2]^T . [X0|1]   rows 0.. = [dW1 | db1], rows 64.. col D0 = db2
@@ -2241,7 +1178,7 @@ __global__ void __launch_bounds__(320, 1) fused_critic2_kernel(critic_args a) {
         }
         ready_arrive(wg, rp);
         wait_mma();  // dH1
-        if (j > 0)   // the shared dH1 slot (see fused_policy_step2_kernel)
+        if (j > 0)   // the shared dH1 slot (see fused_policy_step_kernel)
           umma::mbar_wait(bars + 2, (uint32_t)(j - 1) & 1u);
         epi2_bwd<D1>(tm + C2_ACC0, t, wsm + CM::H1_HI, smem + CM::DH1_HI, smem + CM::DH1_LO);
         umma::mbar_wait(bar_dw2, phase_dw2);  // H1 is free (the dW2 GEMM ran behind the dH1 epilogue)
@@ -2477,167 +1414,8 @@ struct rollout_args {
   float inv_w, inv_h;
 };
 
-template <int D0, int D1, int D2, int NOUT>
-__global__ void __launch_bounds__(256, 2) fused_rollout_kernel(rollout_args a) {
-  using SM = smem_fwd<D1, D2>;
-  using IM = image_map<D1, D2>;
-  constexpr int B = NOUT, P = 2 * B + 2;
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t *smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);  // stays a shared-space pointer
-  const float *fl = reinterpret_cast<const float *>(smem + IM::FLOATS);
-  const float *b3 = fl + IM::F_B3, *kk = fl + IM::F_K;
-  int8_t *sst = reinterpret_cast<int8_t *>(smem + SM::STATE);
-  uint64_t *bar = reinterpret_cast<uint64_t *>(smem + SM::BARS);
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + SM::BARS + 16);
-  const env_params &ep = a.ep;
-  tile_ctx c;
-  setup_common<D0, D1, D2, SM>(c, smem, a.params, a.net, SM::X0, SM::SCRATCH - SM::X0, TF_COLS, tmem_slot, bar);
-  const tid_t t = c.t;
-  const uint32_t tmem = c.tmem, sbase = c.sbase;
-
-  unsigned long long c_eps = 0, c_reward = 0, c_steps = 0;
-  const size_t S = ep.stride;
-  // plane copies: thread (q, cc) moves the 16 environments [16cc, 16cc+16) of plane q
-  const int cq = threadIdx.x >> 3, cc = threadIdx.x & 7;
-
-  for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-    const int i0 = tile * TILE;
-    const bool copier = cq < P && i0 + 16 * cc < ep.stride;
-    if (cq < P) {
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (copier)
-        v = *reinterpret_cast<const uint4 *>(a.state + (size_t)cq * S + i0 + 16 * cc);
-      *reinterpret_cast<uint4 *>(sst + cq * TILE + 16 * cc) = v;
-    }
-    const int r = t.row, i = i0 + r;
-    const bool owner = t.wg == 0 && i < ep.n;
-    uint32_t my_draws = 0, my_steps = 0;
-    if (owner) {
-      my_draws = a.draws[i];
-      my_steps = a.steps[i];
-    }
-    __syncthreads();
-    for (int tt = 0; tt < a.T; ++tt) {
-      // ---- record the start state of step tt, encode the observation panel
-      if (copier)
-        *reinterpret_cast<uint4 *>(a.rec_state + ((size_t)tt * P + cq) * S + i0 + 16 * cc) =
-            *reinterpret_cast<const uint4 *>(sst + cq * TILE + 16 * cc);
-      encode_x0(smem + SM::X0, sst, B, a.inv_w, a.inv_h);
-      sync_after_smem_writes();
-      // tape entries of this step (loads issued before the GEMMs, used in the head)
-      const size_t k = (size_t)tt * ep.n + i;
-      int forced_a = 0, tape_item = 0;
-      double tape_u = 0.0;
-      if (owner) {
-        if (a.mode == DFRL_ACT_FORCED)
-          forced_a = a.forced[k];
-        else if (a.mode == DFRL_ACT_SAMPLE && a.u_tape)
-          tape_u = a.u_tape[k];
-        if (a.item_tape)
-          tape_item = a.item_tape[k];
-      }
-      // ---- forward
-      uint32_t m1, m2;
-      float y2[D2 / 2];
-      fwd_hidden<D0, D1, D2, 2, SM, TF_L1, TF_L2, true, true>(c, fl, m1, m2, y2);
-      sync_after_smem_writes();
-      if (mma_thread(t)) {
-        issue_gemm<D2 / 16, false, false, true, true>(tmem + TF_L3, sbase + SM::H_HI, sbase + SM::H_LO,
-                                                      sbase + IM::W3_HI, sbase + IM::W3_LO, ID<16>::FK_FK, false);
-        umma::commit(c.bar);
-      }
-      c.wait();
-      // ---- head: softmax (no max subtraction, nn.h:382-392), action, environment::apply
-      if (t.wg == 0) {
-        float v[8];
-        tmem_load<8>(tmem + TF_L3 + t.lane_base, v);
-        if (owner) {
-          const float c3 = kk[K_C3];
-          float p[NOUT], s = 0.f;
-#pragma unroll
-          for (int j = 0; j < NOUT; ++j) {
-            p[j] = expf(fmaf(v[j], c3, b3[j]));
-            s += p[j];
-          }
-#pragma unroll
-          for (int j = 0; j < NOUT; ++j)
-            p[j] = p[j] / s;
-          float4 *pr = reinterpret_cast<float4 *>(a.rec_probs + k * B);
-#pragma unroll
-          for (int j = 0; j < NOUT / 4; ++j)
-            pr[j] = make_float4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
-          int act;
-          if (a.mode == DFRL_ACT_FORCED) {
-            act = forced_a;
-          } else if (a.mode == DFRL_ACT_ARGMAX) {
-            act = argmax_first(p, B);
-          } else {
-            double u = tape_u;
-            if (!a.u_tape) {
-              philox4 rr = philox4x32_10(ep.seed, (uint64_t)(ep.env_offset + i), my_steps, DFRL_STREAM_ACTION);
-              u = philox_u53(rr.x, rr.y);
-            }
-            act = discrete_sample(p, B, u);
-          }
-          act = act < B ? act : B - 1;
-          a.rec_action[k] = (uint8_t)act;
-          // environment::apply (bin_packing.h:53-64) on this thread's column of the tile
-          int iw = sst[(2 * B) * TILE + r], ih = sst[(2 * B + 1) * TILE + r];
-          int bw = sst[(2 * act) * TILE + r] - iw, bh = sst[(2 * act + 1) * TILE + r] - ih;
-          bool over = bw < 0 || bh < 0;
-          int s1 = a.item_tape ? (tape_item != 0) : draw_shape1(ep, i, my_draws);
-          if (over) {
-#pragma unroll
-            for (int b = 0; b < B; ++b) {
-              sst[(2 * b) * TILE + r] = (int8_t)ep.cap_w;
-              sst[(2 * b + 1) * TILE + r] = (int8_t)ep.cap_h;
-            }
-          } else {
-            sst[(2 * act) * TILE + r] = (int8_t)bw;
-            sst[(2 * act + 1) * TILE + r] = (int8_t)bh;
-          }
-          sst[(2 * B) * TILE + r] = (int8_t)(s1 ? ep.iw0 : ep.iw1);
-          sst[(2 * B + 1) * TILE + r] = (int8_t)(s1 ? ep.ih0 : ep.ih1);
-          a.rec_done[k] = over;
-          my_draws += 1;
-          my_steps += 1;
-          c_steps += 1;
-          c_eps += over ? 1 : 0;
-          c_reward += over ? 0 : 1;
-        }
-      }
-      umma::fence_before_sync();
-      __syncthreads();
-      umma::fence_after_sync();
-    }
-    // ---- live state back to the environment
-    if (copier)
-      *reinterpret_cast<uint4 *>(a.state + (size_t)cq * S + i0 + 16 * cc) =
-          *reinterpret_cast<const uint4 *>(sst + cq * TILE + 16 * cc);
-    if (owner) {
-      a.draws[i] = my_draws;
-      a.steps[i] = my_steps;
-    }
-    __syncthreads();
-  }
-  for (int o = 16; o > 0; o >>= 1) {
-    c_steps += __shfl_down_sync(0xffffffffu, c_steps, o);
-    c_eps += __shfl_down_sync(0xffffffffu, c_eps, o);
-    c_reward += __shfl_down_sync(0xffffffffu, c_reward, o);
-  }
-  if (t.lane == 0 && c_steps) {
-    atomicAdd(&a.counters[0], c_steps);
-    atomicAdd(&a.counters[1], c_eps);
-    atomicAdd(&a.counters[2], c_reward);
-  }
-  umma::fence_before_sync();
-  __syncthreads();
-  if (t.warp == 0)
-    umma::tmem_dealloc(tmem, TF_COLS);
-}
-
 // ---------------------------------------------------------------------------------------------
-// Rollout with NP tile pipelines per CTA (same structure as fused_policy_step2_kernel): a pipeline
+// Rollout with NP tile pipelines per CTA (same structure as fused_policy_step_kernel): a pipeline
 // = 128 environments, one epilogue thread per environment that keeps the env state in REGISTERS for
 // all T steps, plus one MMA-issuing warp. Shared memory per pipeline: one hi/lo panel pair (the
 // observations are staged in the lo panel's bytes 0..63, H1 then overwrites both, H2 is written in
@@ -2659,7 +1437,7 @@ struct rmap {
 };
 
 template <int D0, int D1, int D2, int NOUT, int NP>
-__global__ void __launch_bounds__(160 * NP, 1) fused_rollout2_kernel(rollout_args a) {
+__global__ void __launch_bounds__(160 * NP, 1) fused_rollout_kernel(rollout_args a) {
   using RM = rmap<D1, D2, NP>;
   constexpr int B = NOUT, P = 2 * B + 2;
   static_assert(D0 == 4 * B && NOUT == 8, "observation width");
@@ -2938,78 +1716,42 @@ int set_smem_once(K kernel, int smem, bool *done) {
   return DFRL_OK;
 }
 
-// Learner kernels run 2 warpgroups. 4 (NWG = 4, 16 warps) measured SLOWER on B200 (11 700 vs
-// 11 200 cycles per tile): the epilogues are bound by the TMEM read port (128 x 64 fp32 = 32 KB per
-// epilogue at 64 B/clk) and the shared-memory stores, not by issue latency, and the 512-thread
-// barriers cost more.
 template <int D0, int D1, int D2, int NOUT>
 int launch_policy_step(dfrl_ctx *ctx, const policy_step_args &a, int ctas) {
-  static const bool v1 = getenv("DFRL_POLICY_V1") != nullptr;  // A/B switch: one tile at a time
-  if (!v1) {
-    constexpr int smem2 = pmap<D1, D2>::TOTAL + 1024;
-    static bool attr2 = false;
-    DFRL_TRY(set_smem_once(fused_policy_step2_kernel<D0, D1, D2, NOUT>, smem2, &attr2));
-    DFRL_LAUNCH(ctx, (fused_policy_step2_kernel<D0, D1, D2, NOUT>), ctas, 320, smem2, a);
-    return DFRL_OK;
-  }
-  constexpr int smem = smem_map<D1, D2>::TOTAL + 1024;
-  constexpr int NWG = 2;
+  constexpr int smem = pmap<D1, D2>::TOTAL + 1024;
   static bool attr = false;
-  DFRL_TRY(set_smem_once(fused_policy_step_kernel<D0, D1, D2, NOUT, NWG>, smem, &attr));
-  DFRL_LAUNCH(ctx, (fused_policy_step_kernel<D0, D1, D2, NOUT, NWG>), ctas, 128 * NWG, smem, a);
+  DFRL_TRY(set_smem_once(fused_policy_step_kernel<D0, D1, D2, NOUT>, smem, &attr));
+  DFRL_LAUNCH(ctx, (fused_policy_step_kernel<D0, D1, D2, NOUT>), ctas, 320, smem, a);
   return DFRL_OK;
 }
 
 template <int D0, int D1, int D2>
 int launch_critic_step(dfrl_ctx *ctx, const critic_args &a, int ctas) {
-  static const bool v1 = getenv("DFRL_CRITIC_V1") != nullptr;  // A/B switch: one tile at a time
-  if (!v1) {
-    constexpr int smem2 = cmap<D1, D2>::TOTAL + 1024;
-    static bool attr2 = false;
-    DFRL_TRY(set_smem_once(fused_critic2_kernel<D0, D1, D2, CRITIC_STEP>, smem2, &attr2));
-    DFRL_LAUNCH(ctx, (fused_critic2_kernel<D0, D1, D2, CRITIC_STEP>), ctas, 320, smem2, a);
-    return DFRL_OK;
-  }
-  constexpr int smem = smem_map<D1, D2>::TOTAL + 1024;
-  constexpr int NWG = 2;
+  constexpr int smem = cmap<D1, D2>::TOTAL + 1024;
   static bool attr = false;
-  DFRL_TRY(set_smem_once(fused_critic_step_kernel<D0, D1, D2, NWG>, smem, &attr));
-  DFRL_LAUNCH(ctx, (fused_critic_step_kernel<D0, D1, D2, NWG>), ctas, 128 * NWG, smem, a);
+  DFRL_TRY(set_smem_once(fused_critic_kernel<D0, D1, D2, CRITIC_STEP>, smem, &attr));
+  DFRL_LAUNCH(ctx, (fused_critic_kernel<D0, D1, D2, CRITIC_STEP>), ctas, 320, smem, a);
   return DFRL_OK;
 }
 
 template <int D0, int D1, int D2>
 int launch_gae(dfrl_ctx *ctx, const critic_args &a, int ctas) {
-  static const bool v1 = getenv("DFRL_CRITIC_V1") != nullptr;
-  if (!v1) {
-    constexpr int smem2 = cmap<D1, D2>::TOTAL + 1024;
-    static bool attr2 = false;
-    DFRL_TRY(set_smem_once(fused_critic2_kernel<D0, D1, D2, CRITIC_GAE>, smem2, &attr2));
-    DFRL_LAUNCH(ctx, (fused_critic2_kernel<D0, D1, D2, CRITIC_GAE>), ctas, 320, smem2, a);
-    return DFRL_OK;
-  }
-  constexpr int smem = smem_fwd<D1, D2>::TOTAL + 1024;
+  constexpr int smem = cmap<D1, D2>::TOTAL + 1024;
   static bool attr = false;
-  DFRL_TRY(set_smem_once(fused_gae_kernel<D0, D1, D2>, smem, &attr));
-  DFRL_LAUNCH(ctx, (fused_gae_kernel<D0, D1, D2>), ctas, 256, smem, a);
+  DFRL_TRY(set_smem_once(fused_critic_kernel<D0, D1, D2, CRITIC_GAE>, smem, &attr));
+  DFRL_LAUNCH(ctx, (fused_critic_kernel<D0, D1, D2, CRITIC_GAE>), ctas, 320, smem, a);
   return DFRL_OK;
 }
 
+// Four rollout pipelines: 131 072 envs = 1024 tiles = 6.9 per SM, i.e. two tile rounds (three
+// pipelines need three rounds: measured 74 us vs 64 us).
 template <int D0, int D1, int D2, int NOUT>
 int launch_rollout(dfrl_ctx *ctx, const rollout_args &a, int ctas) {
-  static const bool v1 = getenv("DFRL_ROLLOUT_V1") != nullptr;  // A/B switch: one tile at a time per CTA
-  if (!v1) {
-    constexpr int NP = 4;
-    constexpr int smem2 = rmap<D1, D2, NP>::TOTAL + 1024;
-    static bool attr2 = false;
-    DFRL_TRY(set_smem_once(fused_rollout2_kernel<D0, D1, D2, NOUT, NP>, smem2, &attr2));
-    DFRL_LAUNCH(ctx, (fused_rollout2_kernel<D0, D1, D2, NOUT, NP>), ctas, 160 * NP, smem2, a);
-    return DFRL_OK;
-  }
-  constexpr int smem = smem_fwd<D1, D2>::TOTAL + 1024;
+  constexpr int NP = 4;
+  constexpr int smem = rmap<D1, D2, NP>::TOTAL + 1024;
   static bool attr = false;
-  DFRL_TRY(set_smem_once(fused_rollout_kernel<D0, D1, D2, NOUT>, smem, &attr));
-  DFRL_LAUNCH(ctx, (fused_rollout_kernel<D0, D1, D2, NOUT>), ctas, 256, smem, a);
+  DFRL_TRY(set_smem_once(fused_rollout_kernel<D0, D1, D2, NOUT, NP>, smem, &attr));
+  DFRL_LAUNCH(ctx, (fused_rollout_kernel<D0, D1, D2, NOUT, NP>), ctas, 160 * NP, smem, a);
   return DFRL_OK;
 }
 
@@ -3220,9 +1962,7 @@ int dfrl_fused_gae(dfrl_trainer *t) {
   if (!f || !f->value_ok)
     return DFRL_ERR_UNSUPPORTED;
   critic_args a = make_critic_args(t, f);
-  // one 320-thread CTA per SM (two tile pipelines each); the one-tile-at-a-time kernel ran two
-  const int per_sm = getenv("DFRL_CRITIC_V1") ? 2 : 1;
-  int ctas = a.n_tiles < per_sm * f->ctas ? a.n_tiles : per_sm * f->ctas;
+  int ctas = a.n_tiles < f->ctas ? a.n_tiles : f->ctas;
   if (f->vnet.d1 == 64)
     DFRL_TRY((launch_gae<32, 64, 64>(t->ctx, a, ctas)));
   else
@@ -3257,8 +1997,7 @@ int dfrl_fused_rollout(dfrl_trainer *t, const uint8_t *items_dev, const uint8_t 
   a.counters = t->counters;
   a.inv_w = 1.0f / (float)e->cfg.cap_w;
   a.inv_h = 1.0f / (float)e->cfg.cap_h;
-  const int per_sm = getenv("DFRL_ROLLOUT_V1") ? 2 : 1;  // the multi-pipeline kernel: one CTA per SM
-  int ctas = a.n_tiles < per_sm * f->ctas ? a.n_tiles : per_sm * f->ctas;
+  int ctas = a.n_tiles < f->ctas ? a.n_tiles : f->ctas;
   if (f->pnet.d1 == 64)
     DFRL_TRY((launch_rollout<32, 64, 64, 8>(t->ctx, a, ctas)));
   else

@@ -1,4 +1,4 @@
-# Phase clocks (SM cycles) of warpgroup 0 of CTA 0 of fused_policy_step2_kernel: 13 stamps per tile.
+# Phase clocks (SM cycles) of warpgroup 0 of CTA 0 of fused_policy_step_kernel: 13 stamps per tile.
 import sys, ctypes as C, numpy as np
 sys.path.insert(0, '/root/repo')
 import dependence_free_rl_b200 as D
