@@ -230,32 +230,46 @@ def measure(D, ctx, dist, args, n_envs, world, rank, steps, warmup, sample_clock
     # ---- e2e through the public call with HOST buffers: per step the item stream of the step
     # (uint8 [T][n], pinned) goes host->device inside rollout(), learn() runs, and the step's
     # result (env-steps / episodes / reward counters) comes back device->host.
+    # The loop keeps one step in flight, as a training loop that logs statistics would: step i's
+    # result is read (stats_begin: async D2H + event) and waited for only after step i + 1 has been
+    # submitted, and the host fills the OTHER of two pinned tapes meanwhile. Every step's tape copy
+    # and result read happen inside the timed region.
     nbytes = T_STEPS * n_envs
-    hp = C.c_void_p()
-    D._lib.check(lib.dfrl_malloc_host(ctx.h, nbytes, C.byref(hp)))
-    host_items = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_uint8)), shape=(nbytes,))
+    hps, tapes = [], []
+    for _ in range(2):
+        hp = C.c_void_p()
+        D._lib.check(lib.dfrl_malloc_host(ctx.h, nbytes, C.byref(hp)))
+        hps.append(hp)
+        tapes.append(np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_uint8)), shape=(nbytes,)))
     rng = np.random.default_rng(rank)
     streams = [(rng.random(nbytes) < 0.4).astype(np.uint8) for _ in range(4)]
 
-    def e2e_step(i):
-        host_items[:] = streams[i % 4]           # the producer filling the pinned tape
-        tr.rollout_raw(hp, None, None)           # H2D of the tape + rollout
+    def submit(i):
+        tapes[i & 1][:] = streams[i % 4]         # the producer filling a pinned tape
+        tr.rollout_raw(hps[i & 1], None, None)   # H2D of the tape + rollout
         tr.learn()
-        return tr.stats()                        # D2H of the step's result (synchronises)
+        tr.stats_begin()                         # D2H of the step's result (asynchronous)
 
-    for i in range(max(1, warmup)):
-        e2e_step(i)
+    def run(n):
+        s = None
+        submit(0)
+        for i in range(1, n):
+            submit(i)
+            s = tr.stats_end()                   # result of step i - 1 (tape (i - 1) & 1 is free again)
+        return tr.stats_end() if n else s
+
+    run(max(2, warmup))
     barrier()
     t0 = time.perf_counter()
-    for i in range(steps):
-        s = e2e_step(i)
+    s = run(steps)
     ctx.sync()
     dt = time.perf_counter() - t0
     dt = max_over_ranks(dt)
     e2e_rate = n_envs * world * T_STEPS * steps / dt
     if sampler:
         sampler.__exit__()
-    D._lib.check(lib.dfrl_free_host(ctx.h, hp))
+    for hp in hps:
+        D._lib.check(lib.dfrl_free_host(ctx.h, hp))
     res = {"value": value_rate, "ms_per_step": ms / steps, "launches_per_step": launches / steps,
            "e2e": {"value": e2e_rate, "unit": "env-steps/s", "h2d_bytes_per_step": nbytes * world,
                    "d2h_bytes_per_step": 32 * world, "ms_per_step": 1e3 * dt / steps},

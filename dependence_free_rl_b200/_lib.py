@@ -123,6 +123,8 @@ PROTOTYPES = {
     "dfrl_trainer_field_size": (i32, [vp, i32, C.POINTER(sz)]),
     "dfrl_trainer_read": (i32, [vp, i32, vp, sz]),
     "dfrl_trainer_get_stats": (i32, [vp, C.POINTER(TrainerStats)]),
+    "dfrl_trainer_stats_begin": (i32, [vp]),
+    "dfrl_trainer_stats_end": (i32, [vp, C.POINTER(TrainerStats)]),
     "dfrl_eval_argmax": (i32, [vp, vp, vp, i32, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
 }
 

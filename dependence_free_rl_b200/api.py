@@ -359,11 +359,25 @@ class Trainer:
             return buf.view(np.float32).reshape(-1, self.policy.n_params)
         return buf.view(np.float32)
 
+    @staticmethod
+    def _stats_dict(s):
+        return {"env_steps": s.env_steps, "episodes": s.episodes, "reward_sum": s.reward_sum,
+                "last_mean_reward": s.last_mean_reward, "kl_beta": s.kl_beta}
+
     def stats(self):
         s = _lib.TrainerStats()
         check(lib.dfrl_trainer_get_stats(self.h, C.byref(s)))
-        return {"env_steps": s.env_steps, "episodes": s.episodes, "reward_sum": s.reward_sum,
-                "last_mean_reward": s.last_mean_reward, "kl_beta": s.kl_beta}
+        return self._stats_dict(s)
+
+    def stats_begin(self):
+        """Enqueue the device->host read of the counters (non-blocking); pair with stats_end()."""
+        check(lib.dfrl_trainer_stats_begin(self.h))
+
+    def stats_end(self):
+        """Wait for the oldest stats_begin() and return its result."""
+        s = _lib.TrainerStats()
+        check(lib.dfrl_trainer_stats_end(self.h, C.byref(s)))
+        return self._stats_dict(s)
 
 
 def eval_argmax(ctx, env, policy, episodes):

@@ -297,9 +297,30 @@ extern "C" int dfrl_trainer_create(dfrl_ctx *ctx, const dfrl_trainer_config *cfg
   DFRL_CUDA(cudaMemsetAsync(t->counters, 0, sizeof(unsigned long long) * 8, ctx->stream));
   DFRL_CUDA(cudaMalloc(&t->acc, sizeof(double) * 4));
   DFRL_CUDA(cudaMalloc(&t->tape_items, LN));
+  DFRL_CUDA(cudaMalloc(&t->tape_items2, LN));
+  {
+    cudaStream_t cs;
+    DFRL_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    t->copy_stream = cs;
+    for (int b = 0; b < 2; ++b) {
+      cudaEvent_t e1, e2;
+      DFRL_CUDA(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+      DFRL_CUDA(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+      t->tape_copied[b] = e1;
+      t->tape_free[b] = e2;
+    }
+    t->tape_flip = 0;
+  }
   DFRL_CUDA(cudaMalloc(&t->tape_actions, LN));
   DFRL_CUDA(cudaMalloc(&t->tape_u, sizeof(double) * LN));
   DFRL_CUDA(cudaMallocHost(&t->pin, 64));
+  DFRL_CUDA(cudaMallocHost(&t->stats_pin, 4 * 32));
+  for (int i = 0; i < 4; ++i) {
+    cudaEvent_t e;
+    DFRL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    t->stats_event[i] = e;
+  }
+  t->stats_head = t->stats_tail = 0;
   t->p_adam_t = 1.f;  // nn.h:693
   t->v_adam_t = 1.f;
   t->kl_beta = cfg->kl_beta0;
@@ -330,8 +351,25 @@ extern "C" int dfrl_trainer_destroy(dfrl_trainer *t) {
   for (void *p : ptrs)
     if (p)
       cudaFree(p);
+  if (t->tape_items2)
+    cudaFree(t->tape_items2);
+  if (t->copy_stream) {
+    cudaStreamSynchronize((cudaStream_t)t->copy_stream);
+    cudaStreamDestroy((cudaStream_t)t->copy_stream);
+  }
+  for (int b = 0; b < 2; ++b) {
+    if (t->tape_copied[b])
+      cudaEventDestroy((cudaEvent_t)t->tape_copied[b]);
+    if (t->tape_free[b])
+      cudaEventDestroy((cudaEvent_t)t->tape_free[b]);
+  }
   if (t->pin)
     cudaFreeHost(t->pin);
+  if (t->stats_pin)
+    cudaFreeHost(t->stats_pin);
+  for (int i = 0; i < 4; ++i)
+    if (t->stats_event[i])
+      cudaEventDestroy((cudaEvent_t)t->stats_event[i]);
   delete t;
   return DFRL_OK;
 }
@@ -418,9 +456,19 @@ extern "C" int dfrl_trainer_rollout(dfrl_trainer *t, const uint8_t *items_host,
   DFRL_CHECK(t->cfg.action_mode != DFRL_ACT_FORCED || actions_host, "forced mode needs an action tape");
   const uint8_t *items_dev = nullptr, *actions_dev = nullptr;
   const double *u_dev = nullptr;
+  int tape_buf = -1;
   if (items_host) {
-    DFRL_CUDA(cudaMemcpyAsync(t->tape_items, items_host, LN, cudaMemcpyHostToDevice, ctx->stream));
-    items_dev = t->tape_items;
+    // copy stream: waits until the rollout that last read this buffer is done, copies, and the
+    // compute stream waits for the copy only -- the copy itself runs beside the previous step
+    tape_buf = t->tape_flip;
+    t->tape_flip ^= 1;
+    uint8_t *dst = tape_buf ? t->tape_items2 : t->tape_items;
+    cudaStream_t cs = (cudaStream_t)t->copy_stream;
+    DFRL_CUDA(cudaStreamWaitEvent(cs, (cudaEvent_t)t->tape_free[tape_buf], 0));
+    DFRL_CUDA(cudaMemcpyAsync(dst, items_host, LN, cudaMemcpyHostToDevice, cs));
+    DFRL_CUDA(cudaEventRecord((cudaEvent_t)t->tape_copied[tape_buf], cs));
+    DFRL_CUDA(cudaStreamWaitEvent(ctx->stream, (cudaEvent_t)t->tape_copied[tape_buf], 0));
+    items_dev = dst;
   }
   if (actions_host) {
     DFRL_CUDA(cudaMemcpyAsync(t->tape_actions, actions_host, LN, cudaMemcpyHostToDevice, ctx->stream));
@@ -434,6 +482,8 @@ extern "C" int dfrl_trainer_rollout(dfrl_trainer *t, const uint8_t *items_host,
   if (rc == DFRL_ERR_UNSUPPORTED)
     rc = rollout_layered(t, items_dev, actions_dev, u_dev);
   DFRL_TRY(rc);
+  if (tape_buf >= 0)
+    DFRL_CUDA(cudaEventRecord((cudaEvent_t)t->tape_free[tape_buf], ctx->stream));
   return DFRL_OK;
 }
 
@@ -711,10 +761,42 @@ extern "C" int dfrl_trainer_read(dfrl_trainer *t, int field, void *dst_host, siz
   return DFRL_OK;
 }
 
+static void fill_stats(dfrl_trainer *t, const unsigned long long *h, dfrl_trainer_stats *out);
+
+// Asynchronous form of dfrl_trainer_get_stats: _begin enqueues the device->host copy of the
+// counters as they stand after the work submitted so far and returns at once; _end waits for the
+// OLDEST begun read only. A training loop that calls _begin(step i), submits step i + 1 and then
+// calls _end keeps the device busy while the host prepares the next step. At most 4 reads in flight.
+extern "C" int dfrl_trainer_stats_begin(dfrl_trainer *t) {
+  DFRL_CHECK(t, "null trainer");
+  DFRL_CHECK(t->stats_head - t->stats_tail < 4, "4 statistics reads already in flight");
+  const unsigned slot = t->stats_head & 3u;
+  DFRL_CUDA(cudaMemcpyAsync((char *)t->stats_pin + 32 * slot, t->counters, 32, cudaMemcpyDeviceToHost, t->ctx->stream));
+  DFRL_CUDA(cudaEventRecord((cudaEvent_t)t->stats_event[slot], t->ctx->stream));
+  t->stats_head++;
+  return DFRL_OK;
+}
+extern "C" int dfrl_trainer_stats_end(dfrl_trainer *t, dfrl_trainer_stats *out) {
+  DFRL_CHECK(t && out, "null argument");
+  DFRL_CHECK(t->stats_head != t->stats_tail, "no statistics read in flight");
+  const unsigned slot = t->stats_tail & 3u;
+  DFRL_CUDA(cudaEventSynchronize((cudaEvent_t)t->stats_event[slot]));
+  unsigned long long h[4];
+  memcpy(h, (char *)t->stats_pin + 32 * slot, 32);
+  t->stats_tail++;
+  fill_stats(t, h, out);
+  return DFRL_OK;
+}
+
 extern "C" int dfrl_trainer_get_stats(dfrl_trainer *t, dfrl_trainer_stats *out) {
   DFRL_CHECK(t && out, "null argument");
   unsigned long long h[4];
   DFRL_TRY(read_counters(t, h));
+  fill_stats(t, h, out);
+  return DFRL_OK;
+}
+
+static void fill_stats(dfrl_trainer *t, const unsigned long long *h, dfrl_trainer_stats *out) {
   out->env_steps = (long long)h[0];
   out->episodes = (long long)h[1];
   out->reward_sum = (double)h[2];
@@ -724,7 +806,6 @@ extern "C" int dfrl_trainer_get_stats(dfrl_trainer *t, dfrl_trainer_stats *out) 
   t->last_rollout_steps = (long long)h[0];
   t->last_rollout_reward = (long long)h[2];
   out->kl_beta = t->kl_beta;
-  return DFRL_OK;
 }
 
 // deep_agent.cc:28-41: argmax policy, `episodes` episodes per env, mean reward per episode.

@@ -29,8 +29,19 @@ struct dfrl_trainer {
   double *acc;  // [4] device accumulators (baseline, KL)
   // device copies of the host tapes
   uint8_t *tape_items, *tape_actions;
+  // item tapes go host->device on a copy stream into two alternating device buffers, so that the
+  // copy for step i + 1 overlaps step i when the caller runs ahead (dfrl_trainer_stats_begin/_end)
+  uint8_t *tape_items2;       // second buffer (first = tape_items)
+  void *copy_stream;          // cudaStream_t
+  void *tape_copied[2];       // cudaEvent_t: copy into buffer b finished
+  void *tape_free[2];         // cudaEvent_t: the rollout that read buffer b has been submitted / finished
+  int tape_flip;
   double *tape_u;
   void *pin;  // 64 B pinned host staging
+  // asynchronous statistics reads (dfrl_trainer_stats_begin / _end): ring of pinned slots + events
+  void *stats_pin;            // [DFRL_STATS_RING][32 B]
+  void *stats_event[4];       // cudaEvent_t
+  unsigned stats_head, stats_tail;
   long long last_rollout_steps, last_rollout_reward;
   void *fused_impl;  // non-null when the fused kernels drive this trainer
   // one free-running iteration captured as a CUDA graph (dfrl_trainer_iterate), see trainer.cu

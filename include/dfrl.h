@@ -373,6 +373,13 @@ typedef struct {
   float kl_beta;           /* current beta (KL-PPO) */
 } dfrl_trainer_stats;
 int dfrl_trainer_get_stats(dfrl_trainer *tr, dfrl_trainer_stats *out);
+/* Asynchronous form: _begin enqueues the device->host read of the counters as they stand after the
+ * work submitted so far and returns immediately; _end waits for the OLDEST begun read only (at most
+ * 4 in flight). Loop: rollout(i); learn(i); stats_begin(); [submit step i + 1;] stats_end(&s_i) --
+ * the device stays busy while the host prepares the next step (the reference's trainer mains print
+ * the mean reward of finished iterations the same way: ppo_training.cc:67-81). */
+int dfrl_trainer_stats_begin(dfrl_trainer *tr);
+int dfrl_trainer_stats_end(dfrl_trainer *tr, dfrl_trainer_stats *out);
 /* Profiling aid (no reference counterpart): SM-cycle stamps at the phase boundaries of CTA 0 of the
  * fused policy-step kernel (pipeline 0), 13 per row tile for its first 8 tiles, then entry / setup /
  * loop-end / exit stamps at 104..107 (n <= 112). The first call arms

@@ -558,6 +558,43 @@ def test_free_running_ppo_is_bitwise_reproducible(D, ctx):
     assert np.all(np.isfinite(a[0])) and np.all(np.isfinite(a[1]))
 
 
+def test_async_stats_pipeline_matches_blocking_reads(D, ctx):
+    # stats_begin / stats_end with one step in flight (the e2e loop of bench.py) must return, step
+    # for step, what the blocking stats() returns; host tapes are double buffered by the caller
+    def run(pipelined):
+        n, T, steps = 1000, 4, 6
+        rng = np.random.default_rng(5)
+        policy = D.Model(ctx, D.fc_layers([32, 64, 64, 8], D.SOFTMAX), 32)
+        value = D.Model(ctx, D.fc_layers([32, 64, 64, 1]), 32)
+        policy.init_parameters(3)
+        value.init_parameters(4)
+        env = D.Environment(ctx, n, seed=9)
+        tr = D.Trainer(ctx, env, policy, value, algo=D.PPO, work=T, policy_lr=1e-6, value_lr=1e-6)
+        tapes = [rng.integers(0, 2, (T, n)).astype(np.uint8) for _ in range(steps)]
+        out = []
+        if pipelined:
+            for i in range(steps):
+                tr.rollout(items=tapes[i])
+                tr.learn()
+                tr.stats_begin()
+                if i:
+                    out.append(tr.stats_end())
+            out.append(tr.stats_end())
+            with pytest.raises(D._lib.DfrlError):
+                tr.stats_end()  # nothing in flight
+        else:
+            for i in range(steps):
+                tr.rollout(items=tapes[i])
+                tr.learn()
+                out.append(tr.stats())
+        params = policy.parameters().copy()
+        tr.close(); env.close(); policy.close(); value.close()
+        return out, params
+    (a, pa), (b, pb) = run(True), run(False)
+    assert a == b and a[-1]["env_steps"] == 6 * 1000 * 4
+    assert np.array_equal(pa, pb)
+
+
 def _safe_params(dims, seed, bias=5.0):
     """Hidden biases of +-bias with small weights: every pre-activation is far from zero (half of
     the units always on, half always off), so relu masks cannot flip under rounding differences."""
