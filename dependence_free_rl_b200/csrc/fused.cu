@@ -322,7 +322,37 @@ __device__ __forceinline__ void issue_gemm_mn_lbo(uint32_t tmem_d, uint32_t a_hi
 
 // TMEM accumulator (this thread's row, all D columns) -> + bias, relu -> hi/lo panels. No relu mask
 // is kept: the backward epilogue of the same thread reads it off the hi panel (H > 0 <=> hi(H) > 0).
-template <int D>
+// TMEM copy of an activation (A operand of the next GEMM read from tensor memory instead of shared
+// memory: 2 KB instead of 6 KB of shared-memory traffic per M128.N64 instruction): the packed hi / lo
+// words of a 32-column chunk h overwrite the chunk's own (already read) accumulator columns, hi of
+// K step kk at column h * CH + 8 kk, lo at + CH / 2.
+template <int CH>
+__device__ __forceinline__ void tmem_put_chunk(uint32_t taddr, int cc, const uint4 &hh, const uint4 &ll) {
+  // 8 columns of the tile = 4 packed words; cc = 8-column group inside the chunk
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(taddr + 4 * cc), "r"(hh.x),
+               "r"(hh.y), "r"(hh.z), "r"(hh.w) : "memory");
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(taddr + CH / 2 + 4 * cc),
+               "r"(ll.x), "r"(ll.y), "r"(ll.z), "r"(ll.w) : "memory");
+}
+// GEMM with the A operand (hi / lo pairs, layout of tmem_put_chunk) in tensor memory.
+template <int D, int KSTEPS, bool B_MN>
+__device__ __forceinline__ void issue_gemm_ta(uint32_t tmem_d, uint32_t a_tmem, uint32_t b_hi, uint32_t b_lo,
+                                              uint32_t idesc) {
+  constexpr int CH = D < 32 ? D : 32;
+  constexpr uint32_t b_step = (B_MN ? umma::KSTEP_BYTES_MNMAJOR : umma::KSTEP_BYTES_KMAJOR) >> 4;
+  constexpr uint32_t b_lbo = B_MN ? PANEL : 16;
+  const uint32_t bh0 = desc_lo(b_hi, b_lbo), bl0 = desc_lo(b_lo, b_lbo);
+#pragma unroll
+  for (int k = 0; k < KSTEPS; ++k) {
+    const uint32_t ah = a_tmem + (16 * k / CH) * CH + ((16 * k % CH) / 16) * 8, al = ah + CH / 2;
+    const uint64_t bh = desc_lo_hi(bh0 + k * b_step), bl = desc_lo_hi(bl0 + k * b_step);
+    umma::mma_bf16_ta(tmem_d, ah, bh, idesc, k > 0 ? 1u : 0u);
+    umma::mma_bf16_ta(tmem_d, ah, bl, idesc, 1);
+    umma::mma_bf16_ta(tmem_d, al, bh, idesc, 1);
+  }
+}
+
+template <int D, bool TMEM_COPY = false>
 __device__ __forceinline__ void epi2_fwd(uint32_t acc, const tid_t &t, const float *__restrict__ bias, uint8_t *hi,
                                          uint8_t *lo) {
   constexpr int CH = D < 32 ? D : 32;
@@ -345,8 +375,12 @@ __device__ __forceinline__ void epi2_fwd(uint32_t acc, const tid_t &t, const flo
       uint32_t off = umma::panel_chunk_off(t.row, h * (CH / 8) + cc);
       *reinterpret_cast<uint4 *>(hi + off) = hh;
       *reinterpret_cast<uint4 *>(lo + off) = ll;
+      if (TMEM_COPY)
+        tmem_put_chunk<CH>(acc + t.lane_base + h * CH, cc, hh, ll);
     }
   }
+  if (TMEM_COPY)
+    umma::tmem_st_wait();
 }
 // 0xffff in each half whose bf16 value is > 0
 __device__ __forceinline__ uint32_t pos_mask2(uint32_t w) {
@@ -357,7 +391,7 @@ __device__ __forceinline__ uint32_t pos_mask2(uint32_t w) {
 // TMEM accumulator -> . relu mask (taken from the forward activation's hi panel `act_hi`) -> hi/lo
 // panels (input-gradient epilogue). `act_hi` may be the destination `hi` itself: every thread reads
 // a 16-byte chunk before it overwrites that same chunk.
-template <int D>
+template <int D, bool TMEM_COPY = false>
 __device__ __forceinline__ void epi2_bwd(uint32_t acc, const tid_t &t, const uint8_t *act_hi, uint8_t *hi,
                                          uint8_t *lo) {
   constexpr int CH = D < 32 ? D : 32;
@@ -372,10 +406,16 @@ __device__ __forceinline__ void epi2_bwd(uint32_t acc, const tid_t &t, const uin
       uint4 hh, ll;
       split8<false>(&v[8 * cc], hh, ll);
       const uint32_t m0 = pos_mask2(aw.x), m1 = pos_mask2(aw.y), m2 = pos_mask2(aw.z), m3 = pos_mask2(aw.w);
-      *reinterpret_cast<uint4 *>(hi + off) = make_uint4(hh.x & m0, hh.y & m1, hh.z & m2, hh.w & m3);
-      *reinterpret_cast<uint4 *>(lo + off) = make_uint4(ll.x & m0, ll.y & m1, ll.z & m2, ll.w & m3);
+      hh = make_uint4(hh.x & m0, hh.y & m1, hh.z & m2, hh.w & m3);
+      ll = make_uint4(ll.x & m0, ll.y & m1, ll.z & m2, ll.w & m3);
+      *reinterpret_cast<uint4 *>(hi + off) = hh;
+      *reinterpret_cast<uint4 *>(lo + off) = ll;
+      if (TMEM_COPY)
+        tmem_put_chunk<CH>(acc + t.lane_base + h * CH, cc, hh, ll);
     }
   }
+  if (TMEM_COPY)
+    umma::tmem_st_wait();
 }
 
 // The raw start state (2B + 2 int8 planes) of one learner row, global -> registers. Nothing touches
@@ -498,16 +538,15 @@ __global__ void __launch_bounds__(320, 1) fused_policy_step_kernel(policy_step_a
     }
     for (int j = wg; j < nt; j += 2) {
       ready_sync(wg, rp);  // H1
-      if (umma::elect_one()) {
-        issue_gemm<D1 / 16, false, false, true, true>(tm + P2_ACC1, wbase + PM::H1_HI, wbase + PM::H1_LO,
-                                                      sbase + PM::W2_HI, sbase + PM::W2_LO, ID<D2>::FK_FK, false);
+      if (umma::elect_one()) {  // A = H1 from tensor memory (the epilogue's copy in ACC0)
+        issue_gemm_ta<D1, D1 / 16, false>(tm + P2_ACC1, tm + P2_ACC0, sbase + PM::W2_HI, sbase + PM::W2_LO,
+                                          ID<D2>::FK_FK);
         umma::commit(bar);
       }
       __syncwarp();
       ready_sync(wg, rp);  // H2; head: columns 8..15 of the result repeat 0..7 (stacked B operand), unused
-      if (umma::elect_one()) {
-        issue_gemm<D2 / 16, false, false, true, true>(tm + P2_ACC0, wbase + PM::H2_HI, wbase + PM::H2_LO,
-                                                      sbase + PM::W3A, sbase + PM::W3B, ID<16>::FK_FK, false);
+      if (umma::elect_one()) {  // A = H2 from tensor memory (ACC1)
+        issue_gemm_ta<D2, D2 / 16, false>(tm + P2_ACC0, tm + P2_ACC1, sbase + PM::W3A, sbase + PM::W3B, ID<16>::FK_FK);
         umma::commit(bar);
       }
       __syncwarp();
@@ -525,8 +564,8 @@ __global__ void __launch_bounds__(320, 1) fused_policy_step_kernel(policy_step_a
       ready_sync(wg, rp);  // dH2 (in the H2 slot)
       // dH1 = dH2 . W2; dW2 += dH2^T . H1 (M = 64) runs behind the dH1 epilogue
       if (umma::elect_one()) {
-        issue_gemm<D2 / 16, false, true, true, true>(tm + P2_ACC1, wbase + PM::H2_HI, wbase + PM::H2_LO,
-                                                     sbase + PM::W2_HI, sbase + PM::W2_LO, ID<D1>::BK_FM, false);
+        // A = dH2 from tensor memory (the epilogue's copy in ACC0)
+        issue_gemm_ta<D2, D2 / 16, true>(tm + P2_ACC1, tm + P2_ACC0, sbase + PM::W2_HI, sbase + PM::W2_LO, ID<D1>::BK_FM);
         umma::commit(bar);
         issue_gemm<8, true, true, true, true>(tm + P2_DA, wbase + PM::H2_HI, wbase + PM::H2_LO, wbase + PM::H1_HI,
                                               wbase + PM::H1_LO, ID<D1>::BM_FM_64, !first);
@@ -596,7 +635,7 @@ __global__ void __launch_bounds__(320, 1) fused_policy_step_kernel(policy_step_a
         load_row_state<NOUT>(L, tile + 2 * gridDim.x, t.row, xn);
       wait_mma();  // layer 1
       STAMP();
-      epi2_fwd<D1>(tm + P2_ACC0, t, fl + PM::F_B1, wsm + PM::H1_HI, wsm + PM::H1_LO);
+      epi2_fwd<D1, true>(tm + P2_ACC0, t, fl + PM::F_B1, wsm + PM::H1_HI, wsm + PM::H1_LO);
       ready_arrive(wg, rp);
       if (!first) {  // the previous tile's dW1 GEMM (XD, dH2 in the H2 slot) ran behind this epilogue
         umma::mbar_wait(bar_dw1, phase_dw1);
@@ -606,7 +645,7 @@ __global__ void __launch_bounds__(320, 1) fused_policy_step_kernel(policy_step_a
       STAMP();
       wait_mma();  // layer 2
       STAMP();
-      epi2_fwd<D2>(tm + P2_ACC1, t, fl + PM::F_B2, wsm + PM::H2_HI, wsm + PM::H2_LO);
+      epi2_fwd<D2, true>(tm + P2_ACC1, t, fl + PM::F_B2, wsm + PM::H2_HI, wsm + PM::H2_LO);
       ready_arrive(wg, rp);
       STAMP();
       wait_mma();  // layer 3
@@ -675,7 +714,7 @@ __global__ void __launch_bounds__(320, 1) fused_policy_step_kernel(policy_step_a
       STAMP();
       wait_mma();  // dW3, dH2
       STAMP();
-      epi2_bwd<D2>(tm + P2_ACC0, t, wsm + PM::H2_HI, wsm + PM::H2_HI, wsm + PM::H2_LO);
+      epi2_bwd<D2, true>(tm + P2_ACC0, t, wsm + PM::H2_HI, wsm + PM::H2_HI, wsm + PM::H2_LO);
       ready_arrive(wg, rp);
       STAMP();
       wait_mma();  // dH1

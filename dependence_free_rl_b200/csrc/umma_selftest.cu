@@ -150,6 +150,84 @@ umma_selftest_kernel(int variant, const float *__restrict__ A, int a_rows, int a
     umma::tmem_dealloc(tmem, 128);
 }
 
+// A operand from TENSOR MEMORY: D[128 x N] = X[128 x K] . W[N x K]^T, X = hi + lo packed bf16 pairs
+// written with tcgen05.st (hi in columns 128.., lo in columns 160..), W in shared-memory panels.
+// b_mn = 1: D[128 x N] = X[128 x K] . W[K x N] with W as an MN-major operand (input gradient form).
+__global__ void __launch_bounds__(128)
+umma_tmem_a_selftest_kernel(const float *__restrict__ A, int k, const float *__restrict__ Bm, int n, int b_mn,
+                            float *__restrict__ D) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
+  const uint32_t PANEL = 128 * 128;
+  uint8_t *b_hi = smem, *b_lo = smem + PANEL;
+  __shared__ uint64_t mbar;
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x & 31, row = warp * 32 + lane;
+  if (warp == 0)
+    umma::tmem_alloc(&slot, 256);
+  if (threadIdx.x == 0) {
+    umma::mbar_init(&mbar, 1);
+    umma::fence_mbar_init();
+  }
+  for (uint32_t o = threadIdx.x * 16; o < 2 * PANEL; o += blockDim.x * 16)
+    *reinterpret_cast<uint4 *>(smem + o) = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  if (b_mn)
+    stage_panels(Bm, k, n, b_hi, b_lo, 128);  // rows = K, columns = N
+  else
+    stage_panels(Bm, n, k, b_hi, b_lo, 128);  // rows = N, columns = K
+  umma::fence_proxy_async();
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem = slot, lane_base = (uint32_t)(warp * 32) << 16;
+  // this thread's row of X -> packed hi / lo words -> TMEM
+  for (int c = 0; c < k; c += 16) {
+    float x[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      x[j] = A[(size_t)row * k + c + j];
+    uint4 h0, l0, h1, l1;
+    umma::split8(x, h0, l0);
+    umma::split8(x + 8, h1, l1);
+    uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+    uint32_t lw[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+    umma::tmem_st8(tmem + lane_base + 128 + c / 2, hw);
+    umma::tmem_st8(tmem + lane_base + 160 + c / 2, lw);
+  }
+  umma::tmem_st_wait();
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = umma::make_idesc_bf16(128, n, 0, b_mn);
+    for (int q = 0; q < k / 16; ++q) {
+      const uint32_t b_off = b_mn ? q * umma::KSTEP_BYTES_MNMAJOR : q * umma::KSTEP_BYTES_KMAJOR;
+      const uint32_t b_lbo = b_mn ? PANEL : 16;
+      uint64_t bh = umma::make_desc_sw128(umma::smem_u32(b_hi) + b_off, b_lbo, 1024);
+      uint64_t bl = umma::make_desc_sw128(umma::smem_u32(b_lo) + b_off, b_lbo, 1024);
+      umma::mma_bf16_ta(tmem, tmem + 128 + 8 * q, bh, idesc, q > 0);
+      umma::mma_bf16_ta(tmem, tmem + 128 + 8 * q, bl, idesc, 1);
+      umma::mma_bf16_ta(tmem, tmem + 160 + 8 * q, bh, idesc, 1);
+    }
+    umma::commit(&mbar);
+  }
+  umma::mbar_wait(&mbar, 0);
+  umma::fence_after_sync();
+  for (int c0 = 0; c0 < n; c0 += 16) {
+    float v[16];
+    umma::tmem_ld16(tmem + lane_base + c0, v);
+    umma::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      D[(size_t)row * n + c0 + j] = v[j];
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0)
+    umma::tmem_dealloc(tmem, 256);
+}
+
 // M = 64 accumulator + tcgen05.ld.16x256b: D[64 x N] = X[64 x K] . W[N x K]^T (both K-major).
 // Assumed layouts (what this test pins): D row r lives in TMEM lane 32 (r / 16) + r % 16; a
 // 16x256b.x1 load by warp w returns to thread t the 2 x 2 block rows {t / 4, t / 4 + 8} x columns
@@ -223,6 +301,38 @@ float lcg(uint32_t &s) {
 // columns (multiple of 16, <= 64). Returns max |D - ref| / max |ref| through *rel_err.
 extern "C" int dfrl_umma_selftest(dfrl_ctx *ctx, int variant, int k, int n, float *rel_err) {
   DFRL_CHECK(ctx && rel_err, "null argument");
+  if (variant == 6 || variant == 7) {  // A operand from tensor memory (6: B K-major, 7: B MN-major)
+    DFRL_CHECK(k % 16 == 0 && k >= 16 && k <= 64 && n % 16 == 0 && n >= 16 && n <= 64, "bad k / n");
+    const int b_mn = variant == 7;
+    std::vector<float> A((size_t)128 * k), B((size_t)n * k), D((size_t)128 * n);
+    uint32_t s = 4242u + k * 3 + n + variant;
+    for (float &x : A) x = lcg(s) * 1.7f;
+    for (float &x : B) x = lcg(s) * 0.9f;
+    float *dA, *dB, *dD;
+    DFRL_CUDA(cudaMalloc(&dA, A.size() * 4));
+    DFRL_CUDA(cudaMalloc(&dB, B.size() * 4));
+    DFRL_CUDA(cudaMalloc(&dD, D.size() * 4));
+    DFRL_CUDA(cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice));
+    DFRL_CUDA(cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice));
+    DFRL_CUDA(cudaMemset(dD, 0, D.size() * 4));
+    const int smem = 2 * 128 * 128 + 1024;
+    DFRL_LAUNCH(ctx, umma_tmem_a_selftest_kernel, 1, 128, smem, dA, k, dB, n, b_mn, dD);
+    DFRL_CUDA(cudaStreamSynchronize(ctx->stream));
+    DFRL_CUDA(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
+    cudaFree(dA); cudaFree(dB); cudaFree(dD);
+    double max_ref = 0, max_err = 0;
+    for (int i = 0; i < 128; ++i)
+      for (int j = 0; j < n; ++j) {
+        double ref = 0;
+        for (int q = 0; q < k; ++q)  // B: [n][k] (K-major) or [k][n] (MN-major)
+          ref += (double)A[(size_t)i * k + q] * (b_mn ? B[(size_t)q * n + j] : B[(size_t)j * k + q]);
+        double err = fabs(ref - (double)D[(size_t)i * n + j]);
+        if (fabs(ref) > max_ref) max_ref = fabs(ref);
+        if (err > max_err) max_err = err;
+      }
+    *rel_err = (float)(max_err / (max_ref + 1e-30));
+    return DFRL_OK;
+  }
   if (variant == 5) {  // M = 64 accumulator read with 16x256b loads
     DFRL_CHECK(k % 16 == 0 && k >= 16 && k <= 128 && n % 16 == 0 && n >= 16 && n <= 64, "bad k / n");
     std::vector<float> A((size_t)64 * k), B((size_t)n * k), D((size_t)64 * n);
@@ -322,7 +432,7 @@ __global__ void __launch_bounds__(128) umma_microbench_kernel(int M, int N, int 
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tmem = slot, sb = umma::smem_u32(smem);
-  const uint32_t idesc = umma::make_idesc_bf16(M, N, a_mn, b_mn);
+  const uint32_t idesc = umma::make_idesc_bf16(M, N, a_mn == 1, b_mn);
   long long t0 = 0;
   if (threadIdx.x < 32 && umma::elect_one()) {
     // A: panels 0..3 (MN-major M = 128 spans two panels, LBO = 16 KB), B: panels 4..7
@@ -333,7 +443,10 @@ __global__ void __launch_bounds__(128) umma_microbench_kernel(int M, int N, int 
       const uint32_t k = (uint32_t)(i & 3);
       uint64_t ad = umma::make_desc_sw128(sb + k * a_step, a_lbo, 1024);
       uint64_t bd = umma::make_desc_sw128(sb + 4 * 16384 + k * b_step, b_lbo, 1024);
-      umma::mma_bf16(tmem, ad, bd, idesc, i > 0);
+      if (a_mn == 2)  // A operand from tensor memory (columns 192.., whatever they hold)
+        umma::mma_bf16_ta(tmem, tmem + 192 + 8 * k, bd, idesc, i > 0);
+      else
+        umma::mma_bf16(tmem, ad, bd, idesc, i > 0);
     }
     umma::commit(&bar);
     out[1] = clock64() - t0;  // issue time

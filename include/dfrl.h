@@ -134,7 +134,7 @@ int dfrl_profile_report(dfrl_ctx *ctx, char *buf, size_t cap);
  * max|D-ref| / max|ref|. */
 int dfrl_umma_selftest(dfrl_ctx *ctx, int variant, int k, int n, float *rel_err);
 /* Profiling aid: SM cycles for `count` back-to-back tcgen05.mma (bf16, K = 16, M x N, operand
- * major-ness a_mn / b_mn: 0 = K-major, 1 = MN-major) on one SM; cycles2[0] = first issue -> all
+ * major-ness a_mn / b_mn: 0 = K-major, 1 = MN-major, a_mn = 2: A from tensor memory) on one SM; cycles2[0] = first issue -> all
  * complete, cycles2[1] = issue loop only. */
 int dfrl_umma_microbench(dfrl_ctx *ctx, int M, int N, int a_mn, int b_mn, int count, long long *cycles2);
 

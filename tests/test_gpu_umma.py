@@ -10,7 +10,8 @@ pytestmark = pytest.mark.gpu
                                          (1, 64, 64), (1, 16, 64), (1, 64, 32),
                                          (2, 128, 64), (2, 128, 32),
                                          (3, 128, 16), (4, 16, 64), (4, 16, 32),
-                                         (5, 64, 64), (5, 32, 16)])
+                                         (5, 64, 64), (5, 32, 16),
+                                         (6, 64, 64), (6, 32, 16), (6, 64, 16), (7, 64, 64), (7, 16, 64)])
 def test_umma_tile_gemm(ctx, variant, k, n):
     import dependence_free_rl_b200 as D
     err = C.c_float(-1.0)

@@ -10,7 +10,8 @@ def run(M, N, a, b, n):
     return out[0], out[1]
 print("M N a_mn b_mn | cycles/MMA (slope 64->256) | fixed | issue cycles/MMA")
 for (M, N, a, b) in [(128, 64, 0, 0), (128, 16, 0, 0), (128, 64, 0, 1), (128, 32, 0, 0), (128, 128, 0, 0), (128, 256, 0, 0),
-                     (64, 64, 1, 1), (64, 16, 1, 1), (128, 48, 1, 1), (128, 64, 1, 1), (64, 64, 0, 0), (64, 128, 1, 1), (128, 128, 1, 1)]:
+                     (64, 64, 1, 1), (64, 16, 1, 1), (128, 48, 1, 1), (128, 64, 1, 1), (64, 64, 0, 0), (64, 128, 1, 1), (128, 128, 1, 1),
+                     (128, 64, 2, 0), (128, 64, 2, 1), (128, 16, 2, 0), (128, 128, 2, 0)]:  # a_mn = 2: A from TMEM
     run(M, N, a, b, 8)
     c1, i1 = run(M, N, a, b, 64)
     c2, i2 = run(M, N, a, b, 256)
