@@ -335,7 +335,7 @@ __device__ __forceinline__ void tmem_put_chunk(uint32_t taddr, int cc, const uin
                "r"(ll.x), "r"(ll.y), "r"(ll.z), "r"(ll.w) : "memory");
 }
 // GEMM with the A operand (hi / lo pairs, layout of tmem_put_chunk) in tensor memory.
-template <int D, int KSTEPS, bool B_MN>
+template <int D, int KSTEPS, bool B_MN, bool B_LO = true>
 __device__ __forceinline__ void issue_gemm_ta(uint32_t tmem_d, uint32_t a_tmem, uint32_t b_hi, uint32_t b_lo,
                                               uint32_t idesc) {
   constexpr int CH = D < 32 ? D : 32;
@@ -347,12 +347,13 @@ __device__ __forceinline__ void issue_gemm_ta(uint32_t tmem_d, uint32_t a_tmem, 
     const uint32_t ah = a_tmem + (16 * k / CH) * CH + ((16 * k % CH) / 16) * 8, al = ah + CH / 2;
     const uint64_t bh = desc_lo_hi(bh0 + k * b_step), bl = desc_lo_hi(bl0 + k * b_step);
     umma::mma_bf16_ta(tmem_d, ah, bh, idesc, k > 0 ? 1u : 0u);
-    umma::mma_bf16_ta(tmem_d, ah, bl, idesc, 1);
+    if (B_LO)
+      umma::mma_bf16_ta(tmem_d, ah, bl, idesc, 1);
     umma::mma_bf16_ta(tmem_d, al, bh, idesc, 1);
   }
 }
 
-template <int D, bool TMEM_COPY = false>
+template <int D, bool TMEM_COPY = false, bool SMEM_STORE = true>
 __device__ __forceinline__ void epi2_fwd(uint32_t acc, const tid_t &t, const float *__restrict__ bias, uint8_t *hi,
                                          uint8_t *lo) {
   constexpr int CH = D < 32 ? D : 32;
@@ -372,9 +373,11 @@ __device__ __forceinline__ void epi2_fwd(uint32_t acc, const tid_t &t, const flo
     for (int cc = 0; cc < CH / 8; ++cc) {
       uint4 hh, ll;
       split8<false>(&v[8 * cc], hh, ll);
-      uint32_t off = umma::panel_chunk_off(t.row, h * (CH / 8) + cc);
-      *reinterpret_cast<uint4 *>(hi + off) = hh;
-      *reinterpret_cast<uint4 *>(lo + off) = ll;
+      if (SMEM_STORE) {
+        uint32_t off = umma::panel_chunk_off(t.row, h * (CH / 8) + cc);
+        *reinterpret_cast<uint4 *>(hi + off) = hh;
+        *reinterpret_cast<uint4 *>(lo + off) = ll;
+      }
       if (TMEM_COPY)
         tmem_put_chunk<CH>(acc + t.lane_base + h * CH, cc, hh, ll);
     }
@@ -1013,9 +1016,8 @@ __global__ void __launch_bounds__(320, 1) fused_critic_kernel(critic_args a) {
                                                      ID<D1>::FK_FK, false);
       umma::commit(done_bar);
     };
-    auto layer2 = [&]() {
-      issue_gemm<D1 / 16, false, false, true, true>(tm + C2_ACC1, wbase + CM::H1_HI, wbase + CM::H1_LO,
-                                                    sbase + CM::W2_HI, sbase + CM::W2_LO, ID<D2>::FK_FK, false);
+    auto layer2 = [&]() {  // A = H1 from tensor memory (the epilogue's copy in ACC0)
+      issue_gemm_ta<D1, D1 / 16, false>(tm + C2_ACC1, tm + C2_ACC0, sbase + CM::W2_HI, sbase + CM::W2_LO, ID<D2>::FK_FK);
       umma::commit(bar);
     };
     bool first = true;
@@ -1042,8 +1044,8 @@ __global__ void __launch_bounds__(320, 1) fused_critic_kernel(critic_args a) {
         ready_sync(wg, rp);  // dH2
         // dH1 = dH2 . W2; dW2 += dH2^T . H1 (M = 64) runs behind the dH1 epilogue
         if (umma::elect_one()) {
-          issue_gemm<D2 / 16, false, true, true, true>(tm + C2_ACC0, wbase + CM::G2_HI, wbase + CM::G2_LO,
-                                                       sbase + CM::W2_HI, sbase + CM::W2_LO, ID<D1>::BK_FM, false);
+          // A = dH2 from tensor memory (the targets phase's copy in ACC1)
+          issue_gemm_ta<D2, D2 / 16, true>(tm + C2_ACC0, tm + C2_ACC1, sbase + CM::W2_HI, sbase + CM::W2_LO, ID<D1>::BK_FM);
           umma::commit(bar);
           issue_gemm<8, true, true, true, true>(tm + C2_DA, wbase + CM::G2_HI, wbase + CM::G2_LO, wbase + CM::H1_HI,
                                                 wbase + CM::H1_LO, ID<D1>::BM_FM_64, !first);
@@ -1111,8 +1113,8 @@ __global__ void __launch_bounds__(320, 1) fused_critic_kernel(critic_args a) {
         for (int q = 0; q < L.T && q < 32; ++q)
           dmask |= (uint32_t)(L.rec_done[(size_t)q * L.n + tile * L.E + t.row] != 0) << q;
       // ---- pass 1: V of the end rows
-      wait_mma();  // layer 1 (end rows)
-      epi2_fwd<D1>(tm + C2_ACC0, t, b1, wsm + CM::H1_HI, wsm + CM::H1_LO);
+      wait_mma();  // layer 1 (end rows): H1 only as a TMEM A operand
+      epi2_fwd<D1, true, false>(tm + C2_ACC0, t, b1, nullptr, nullptr);
       ready_arrive(wg, rp);
       // start-row observations -> XS (the previous tile's dW1 GEMM ran behind the epilogue above)
       if (MODE == CRITIC_STEP && !first) {
@@ -1152,7 +1154,7 @@ __global__ void __launch_bounds__(320, 1) fused_critic_kernel(critic_args a) {
       umma::mbar_wait(bar_l1s, phase_l1s);  // layer 1 (start rows)
       phase_l1s ^= 1;
       umma::fence_after_sync();
-      epi2_fwd<D1>(tm + C2_ACC0, t, b1, wsm + CM::H1_HI, wsm + CM::H1_LO);
+      epi2_fwd<D1, true, MODE == CRITIC_STEP>(tm + C2_ACC0, t, b1, wsm + CM::H1_HI, wsm + CM::H1_LO);  // panels: dW2
       ready_arrive(wg, rp);
       wait_mma();  // layer 2 (start rows)
       const float v = epi2_value<D2, false>(tm + C2_ACC1, t, b2, w3, b3, nullptr);
@@ -1212,8 +1214,10 @@ __global__ void __launch_bounds__(320, 1) fused_critic_kernel(critic_args a) {
               const uint32_t off = umma::panel_chunk_off(t.row, h * (CH / 8) + cc);
               *reinterpret_cast<uint4 *>(wsm + CM::G2_HI + off) = hh;
               *reinterpret_cast<uint4 *>(wsm + CM::G2_LO + off) = ll;
+              tmem_put_chunk<CH>(tm + C2_ACC1 + t.lane_base + h * CH, cc, hh, ll);  // A operand of the dH1 GEMM
             }
           }
+          umma::tmem_st_wait();
         }
         ready_arrive(wg, rp);
         wait_mma();  // dH1
@@ -1456,20 +1460,20 @@ struct rollout_args {
 // ---------------------------------------------------------------------------------------------
 // Rollout with NP tile pipelines per CTA (same structure as fused_policy_step_kernel): a pipeline
 // = 128 environments, one epilogue thread per environment that keeps the env state in REGISTERS for
-// all T steps, plus one MMA-issuing warp. Shared memory per pipeline: one hi/lo panel pair (the
-// observations are staged in the lo panel's bytes 0..63, H1 then overwrites both, H2 is written in
-// place); the layer-3 B operand stacks [hi(W3); lo(W3)] (N = 16: two MMAs per K step, the head adds
-// columns j and 8 + j).
+// all T steps, plus one MMA-issuing warp. The hidden activations exist ONLY in tensor memory: the
+// epilogues write their packed bf16 hi / lo words over the accumulator columns they just read and
+// the next GEMM takes its A operand from there; shared memory per pipeline = the observation panel.
+// The layer-3 B operand stacks [hi(W3); lo(W3)] (N = 16: two MMAs per K step, the head adds columns
+// j and 8 + j).
 template <int D1, int D2, int NP>
 struct rmap {
   static constexpr uint32_t W1P = 0;
   static constexpr uint32_t W2_HI = W1P + D1 * 128, W2_LO = W2_HI + D2 * 128;
   static constexpr uint32_t W3C = W2_LO + D2 * 128;  // rows 0..7 = hi(W3), rows 8..15 = lo(W3)
-  static constexpr uint32_t W3D = W3C + 16 * 128;    // rows 0..7 = hi(W3), rows 8..15 = 0
-  static constexpr uint32_t FLOATS = W3D + 16 * 128;  // b1[D1] b2[D2] b3[16]
+  static constexpr uint32_t FLOATS = W3C + 16 * 128;  // b1[D1] b2[D2] b3[16]
   static constexpr int F_B1 = 0, F_B2 = D1, F_B3 = D1 + D2, N_FLOATS = D1 + D2 + 16;
   static constexpr uint32_t WG0 = (FLOATS + N_FLOATS * 4 + 1023) / 1024 * 1024;
-  static constexpr uint32_t H_HI = 0, H_LO = PANEL, WG_BYTES = 2 * PANEL;
+  static constexpr uint32_t X0 = 0, WG_BYTES = PANEL;  // per pipeline: the observation panel only
   static constexpr uint32_t BARS = WG0 + NP * WG_BYTES;
   static constexpr uint32_t TOTAL = BARS + 64;
   static_assert(TOTAL + 1024 <= 232448, "exceeds the 227 KB shared memory of an SM");
@@ -1517,7 +1521,6 @@ __global__ void __launch_bounds__(160 * NP, 1) fused_rollout_kernel(rollout_args
       split8<false>(x, h, l);
       uint32_t off = umma::panel_chunk_off(row, chunk);
       *reinterpret_cast<uint4 *>(smem + RM::W3C + off) = row < 8 ? h : l;
-      *reinterpret_cast<uint4 *>(smem + RM::W3D + off) = row < 8 ? h : make_uint4(0, 0, 0, 0);
     }
     for (int i = threadIdx.x; i < D1; i += blockDim.x) fl[RM::F_B1 + i] = Pm[net.o_b1 + i];
     for (int i = threadIdx.x; i < D2; i += blockDim.x) fl[RM::F_B2 + i] = Pm[net.o_b2 + i];
@@ -1540,23 +1543,22 @@ __global__ void __launch_bounds__(160 * NP, 1) fused_rollout_kernel(rollout_args
       for (int tt = 0; tt < a.T; ++tt) {
         ready_sync(wg, rp);  // observations staged in the lo panel
         if (umma::elect_one()) {
-          issue_gemm<D0 / 16, false, false, false, true>(tm, wbase + RM::H_LO, 0, sbase + RM::W1P,
+          issue_gemm<D0 / 16, false, false, false, true>(tm, wbase + RM::X0, 0, sbase + RM::W1P,
                                                          sbase + RM::W1P + 64, ID<D1>::FK_FK, false);
           umma::commit(bar);
         }
         __syncwarp();
         ready_sync(wg, rp);  // H1
         if (umma::elect_one()) {
-          issue_gemm<D1 / 16, false, false, true, true>(tm + 64, wbase + RM::H_HI, wbase + RM::H_LO,
-                                                        sbase + RM::W2_HI, sbase + RM::W2_LO, ID<D2>::FK_FK, false);
+          // A = H1 from tensor memory (the epilogue's copy in ACC0)
+          issue_gemm_ta<D1, D1 / 16, false>(tm + 64, tm, sbase + RM::W2_HI, sbase + RM::W2_LO, ID<D2>::FK_FK);
           umma::commit(bar);
         }
         __syncwarp();
         ready_sync(wg, rp);  // H2 (in place)
         if (umma::elect_one()) {
-          // hi(H2) . [hi(W3); lo(W3)] + lo(H2) . [hi(W3); 0]
-          issue_gemm<D2 / 16, false, false, true, false>(tm, wbase + RM::H_HI, wbase + RM::H_LO, sbase + RM::W3C, 0,
-                                                         ID<16>::FK_FK, false);
+          // (hi(H2) + lo(H2)) . [hi(W3); lo(W3)], A = H2 from tensor memory (ACC1)
+          issue_gemm_ta<D2, D2 / 16, false, false>(tm, tm + 64, sbase + RM::W3C, 0, ID<16>::FK_FK);
           umma::commit(bar);
         }
         __syncwarp();
@@ -1594,7 +1596,7 @@ __global__ void __launch_bounds__(160 * NP, 1) fused_rollout_kernel(rollout_args
           for (int q = 0; q < P; ++q)
             a.rec_state[((size_t)tt * P + q) * S + i] = (int8_t)st.v[q];
         }
-        encode_row<B>(wsm + RM::H_LO, t.row, st, a.inv_w, a.inv_h);
+        encode_row<B>(wsm + RM::X0, t.row, st, a.inv_w, a.inv_h);
         ready_arrive(wg, rp);
         // tape entries of this step (loads issued before the GEMMs, used in the head)
         const size_t k = (size_t)tt * ep.n + i;
@@ -1609,10 +1611,10 @@ __global__ void __launch_bounds__(160 * NP, 1) fused_rollout_kernel(rollout_args
             tape_item = a.item_tape[k];
         }
         wait_mma();  // layer 1
-        epi2_fwd<D1>(tm, t, b1, wsm + RM::H_HI, wsm + RM::H_LO);
+        epi2_fwd<D1, true, false>(tm, t, b1, nullptr, nullptr);  // H1 only as a TMEM A operand
         ready_arrive(wg, rp);
         wait_mma();  // layer 2
-        epi2_fwd<D2>(tm + 64, t, b2, wsm + RM::H_HI, wsm + RM::H_LO);
+        epi2_fwd<D2, true, false>(tm + 64, t, b2, nullptr, nullptr);
         ready_arrive(wg, rp);
         wait_mma();  // layer 3
         // ---- head: softmax (no max subtraction, nn.h:382-392), action, environment::apply
