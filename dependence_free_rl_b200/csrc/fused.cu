@@ -856,20 +856,26 @@ __global__ void __launch_bounds__(320, 1) fused_policy_step_kernel(policy_step_a
 // Shared memory per pipeline: XS (start observations | 1), H1 hi/lo, dH2 hi/lo; the end-row
 // observations are staged in the dead H1_LO panel; dH1 in one slot shared by both pipelines.
 enum { CRITIC_STEP = 0, CRITIC_GAE = 1 };
-template <int D1, int D2>
+template <int D1, int D2, int MODE>
 struct cmap {
+  // CRITIC_STEP: 2 pipelines x 5 panels + the shared dH1 slot; CRITIC_GAE (forward only, hidden
+  // activations in tensor memory): 3 pipelines x one observation panel (end rows, then start rows)
+  static constexpr int NP = MODE == 0 ? 2 : 3;
   static constexpr uint32_t W1P = 0;
   static constexpr uint32_t W2_HI = W1P + D1 * 128, W2_LO = W2_HI + D2 * 128;
   static constexpr uint32_t FLOATS = W2_LO + D2 * 128;  // b1[D1] b2[D2] w3[64] b3[4]
   static constexpr int F_B1 = 0, F_B2 = D1, F_W3 = D1 + D2, F_B3 = D1 + D2 + 64, N_FLOATS = D1 + D2 + 68;
   static constexpr uint32_t SCR = FLOATS + N_FLOATS * 4;  // per pipeline: ve[128], vs[128]
-  static constexpr uint32_t DH1_HI = (SCR + 2 * 2 * TILE * 4 + 1023) / 1024 * 1024;  // shared slot
+  static constexpr uint32_t DH1_HI = (SCR + NP * 2 * TILE * 4 + 1023) / 1024 * 1024;  // shared slot
   static constexpr uint32_t DH1_LO = DH1_HI + PANEL;
-  static constexpr uint32_t WG0 = DH1_LO + PANEL;
-  static constexpr uint32_t XS = 0, H1_HI = PANEL, H1_LO = 2 * PANEL, G2_HI = 3 * PANEL, G2_LO = 4 * PANEL;
-  static constexpr uint32_t WG_BYTES = 5 * PANEL;
-  static constexpr uint32_t BARS = WG0 + 2 * WG_BYTES;
+  static constexpr uint32_t WG0 = MODE == 0 ? DH1_LO + PANEL : DH1_HI;
+  // CRITIC_STEP: XS, H1 hi/lo (lo = staging panel of the end-row observations), dH2 hi/lo
+  static constexpr uint32_t XS = 0, H1_HI = PANEL, H1_LO = MODE == 0 ? 2 * PANEL : 0, G2_HI = 3 * PANEL,
+                            G2_LO = 4 * PANEL;
+  static constexpr uint32_t WG_BYTES = MODE == 0 ? 5 * PANEL : PANEL;
+  static constexpr uint32_t BARS = WG0 + NP * WG_BYTES;
   static constexpr uint32_t TOTAL = BARS + 128;
+  static constexpr uint32_t TCOLS_PER = MODE == 0 ? 256 : 128;  // TMEM columns of a pipeline
   static_assert((D1 * 128) % 1024 == 0 && (D2 * 128) % 1024 == 0, "panel alignment");
   static_assert(TOTAL + 1024 <= 232448, "exceeds the 227 KB shared memory of an SM");
 };
@@ -953,29 +959,31 @@ __device__ __forceinline__ float epi2_value(uint32_t acc, const tid_t &t, const 
 }
 
 template <int D0, int D1, int D2, int MODE>
-__global__ void __launch_bounds__(320, 1) fused_critic_kernel(critic_args a) {
-  using CM = cmap<D1, D2>;
+__global__ void __launch_bounds__(160 * (MODE == CRITIC_STEP ? 2 : 3), 1) fused_critic_kernel(critic_args a) {
+  using CM = cmap<D1, D2, MODE>;
+  constexpr int NP = CM::NP;
   constexpr int NB = 8;  // bins (the fused path covers the 8-bin problem)
   static_assert(D0 == 4 * NB, "observation width");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);  // stays a shared-space pointer
   float *fl = reinterpret_cast<float *>(smem + CM::FLOATS);
-  // mbarriers: [wg] MMA completion on the chain, [2] dH1 slot free, [3 + wg] dW2 GEMM done (H1 free),
-  // [5 + wg] dW1 GEMM done (XS, dH2 free), [7 + wg] layer 1 of the start rows (issued right behind
-  // layer 2 of the end rows: a parity wait cannot tell two outstanding completions of one mbarrier apart)
+  // mbarriers: [wg] MMA completion on the chain, [NP + wg] dW2 GEMM done (H1 free), [2 NP + wg] dW1
+  // GEMM done (XS, dH2 free), [3 NP + wg] layer 1 of the start rows (issued right behind layer 2 of
+  // the end rows: a parity wait cannot tell two outstanding completions of one mbarrier apart),
+  // [4 NP] dH1 slot free
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + CM::BARS);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + CM::BARS + 120);
   const net3 net = a.net;
   const learner_rows &L = a.rows;
   const tid_t t = thread_id();
-  const bool issuer = t.warp >= 8;                   // warp-uniform
-  const int wg = issuer ? t.warp - 8 : t.warp >> 2;  // pipeline index
+  const bool issuer = t.warp >= 4 * NP;                   // warp-uniform
+  const int wg = issuer ? t.warp - 4 * NP : t.warp >> 2;  // pipeline index
   const uint32_t sbase = umma::smem_u32(smem);
 
   if (t.warp == 0)
     umma::tmem_alloc(tmem_slot, 512);
   if (threadIdx.x == 0) {
-    for (int q = 0; q < 9; ++q)
+    for (int q = 0; q < 4 * NP + 1; ++q)
       umma::mbar_init(bars + q, 1);
     umma::fence_mbar_init();
   }
@@ -991,7 +999,7 @@ __global__ void __launch_bounds__(320, 1) fused_critic_kernel(critic_args a) {
   }
   zero_bytes(smem + CM::DH1_HI, CM::BARS - CM::DH1_HI);
   __syncthreads();
-  if (!issuer)  // ones column (col D0) of both XS panels: bias gradients for free
+  if (!issuer && MODE == CRITIC_STEP)  // ones column (col D0) of both XS panels: bias gradients for free
     *reinterpret_cast<uint16_t *>(smem + CM::WG0 + wg * CM::WG_BYTES + CM::XS + umma::panel_off(t.row, D0)) = 0x3F80;
   sync_after_smem_writes();
   const uint32_t tmem = *tmem_slot;
@@ -999,9 +1007,10 @@ __global__ void __launch_bounds__(320, 1) fused_critic_kernel(critic_args a) {
   const int nt = (int)blockIdx.x < a.n_tiles ? (a.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   uint8_t *wsm = smem + CM::WG0 + wg * CM::WG_BYTES;
   const uint32_t wbase = sbase + CM::WG0 + wg * CM::WG_BYTES;
-  const uint32_t tm = tmem + 256u * wg;
+  const uint32_t tm = tmem + CM::TCOLS_PER * wg;
   const uint32_t dh1_lbo = CM::WG0 + wg * CM::WG_BYTES + CM::G2_HI - CM::DH1_HI;  // dH1 panel -> own dH2 panel
-  uint64_t *bar = bars + wg, *bar_dw2 = bars + 3 + wg, *bar_dw1 = bars + 5 + wg, *bar_l1s = bars + 7 + wg;
+  uint64_t *bar = bars + wg, *bar_dw2 = bars + NP + wg, *bar_dw1 = bars + 2 * NP + wg, *bar_l1s = bars + 3 * NP + wg,
+           *bar_slot = bars + 4 * NP;
   uint32_t rp = 0;
   float dw3[MODE == CRITIC_STEP ? D2 : 1];
 #pragma unroll
@@ -1027,7 +1036,7 @@ __global__ void __launch_bounds__(320, 1) fused_critic_kernel(critic_args a) {
         layer1(wbase + CM::H1_LO, bar);
       __syncwarp();
     }
-    for (int j = wg; j < nt; j += 2) {
+    for (int j = wg; j < nt; j += NP) {
       ready_sync(wg, rp);  // H1 (end rows)
       if (umma::elect_one())
         layer2();
@@ -1055,14 +1064,14 @@ __global__ void __launch_bounds__(320, 1) fused_critic_kernel(critic_args a) {
       }
       ready_sync(wg, rp);  // (dH1 in the shared slot and) the next tile's end-row observations
       if (umma::elect_one()) {
-        if (j + 2 < nt)  // ahead of dW1: see fused_policy_step_kernel
+        if (j + NP < nt)  // ahead of dW1: see fused_policy_step_kernel
           layer1(wbase + CM::H1_LO, bar);
         if (MODE == CRITIC_STEP) {
           //   DB[128 x D0+16] += [dH1|dH2]^T . [X0|1]   rows 0.. = [dW1 | db1], rows 64.. col D0 = db2
           issue_gemm_mn_lbo<8>(tm + C2_DB, sbase + CM::DH1_HI, sbase + CM::DH1_LO, dh1_lbo, wbase + CM::XS,
                                ID<D0 + 16>::BM_FM, !first);
           umma::commit(bar_dw1);
-          umma::commit(bars + 2);
+          umma::commit(bar_slot);
         }
       }
       __syncwarp();
@@ -1101,12 +1110,12 @@ __global__ void __launch_bounds__(320, 1) fused_critic_kernel(critic_args a) {
         ready_arrive(wg, rp);
       }
     }
-    for (int j = wg; j < nt; j += 2) {
+    for (int j = wg; j < nt; j += NP) {
       const int tile = blockIdx.x + j * gridDim.x;
       const int i = tile * L.E + e;
       const bool valid = tt < L.T && i < L.n;
       const size_t k = (size_t)tt * L.n + i;
-      const bool has_next = j + 2 < nt;
+      const bool has_next = j + NP < nt;
       // GAE: done flags of the env this thread walks (threads < E)
       uint32_t dmask = 0;
       if (MODE == CRITIC_GAE && t.row < L.E && i < L.n)
@@ -1132,7 +1141,7 @@ __global__ void __launch_bounds__(320, 1) fused_critic_kernel(critic_args a) {
       row_state<NB> ns, nl;
       int ndone = 0, nact = 0;
       if (has_next) {
-        const int ntile = tile + 2 * gridDim.x, ni = ntile * L.E + e;
+        const int ntile = tile + NP * gridDim.x, ni = ntile * L.E + e;
         load_row_state<NB>(L, ntile, t.row, ns);
         load_live_state<NB>(L, ntile, t.row, nl);
         if (tt < L.T && ni < L.n) {
@@ -1159,7 +1168,7 @@ __global__ void __launch_bounds__(320, 1) fused_critic_kernel(critic_args a) {
       wait_mma();  // layer 2 (start rows)
       const float v = epi2_value<D2, false>(tm + C2_ACC1, t, b2, w3, b3, nullptr);
       vs[t.row] = v;
-      asm volatile("bar.sync %0, 128;\n" ::"r"(5 + wg) : "memory");  // ve / vs of the tile visible
+      asm volatile("bar.sync %0, 128;\n" ::"r"(9 + wg) : "memory");  // ve / vs of the tile visible
       if (MODE == CRITIC_GAE) {
         // thread e < E walks its env backwards (same recurrence as device_fns.cuh gae_env)
         if (t.row < L.E && i < L.n) {
@@ -1177,7 +1186,7 @@ __global__ void __launch_bounds__(320, 1) fused_critic_kernel(critic_args a) {
             a_next = adv;
           }
         }
-        asm volatile("bar.sync %0, 128;\n" ::"r"(5 + wg) : "memory");  // ve / vs may be overwritten
+        asm volatile("bar.sync %0, 128;\n" ::"r"(9 + wg) : "memory");  // ve / vs may be overwritten
       } else {
         // ---- targets and dY = V - target (square_loss_grad, nn.h:548-550)
         float dy = 0.f;
@@ -1222,7 +1231,7 @@ __global__ void __launch_bounds__(320, 1) fused_critic_kernel(critic_args a) {
         ready_arrive(wg, rp);
         wait_mma();  // dH1
         if (j > 0)   // the shared dH1 slot (see fused_policy_step_kernel)
-          umma::mbar_wait(bars + 2, (uint32_t)(j - 1) & 1u);
+          umma::mbar_wait(bar_slot, (uint32_t)(j - 1) & 1u);
         epi2_bwd<D1>(tm + C2_ACC0, t, wsm + CM::H1_HI, smem + CM::DH1_HI, smem + CM::DH1_LO);
         umma::mbar_wait(bar_dw2, phase_dw2);  // H1 is free (the dW2 GEMM ran behind the dH1 epilogue)
         phase_dw2 ^= 1;
@@ -1768,7 +1777,7 @@ int launch_policy_step(dfrl_ctx *ctx, const policy_step_args &a, int ctas) {
 
 template <int D0, int D1, int D2>
 int launch_critic_step(dfrl_ctx *ctx, const critic_args &a, int ctas) {
-  constexpr int smem = cmap<D1, D2>::TOTAL + 1024;
+  constexpr int smem = cmap<D1, D2, CRITIC_STEP>::TOTAL + 1024;
   static bool attr = false;
   DFRL_TRY(set_smem_once(fused_critic_kernel<D0, D1, D2, CRITIC_STEP>, smem, &attr));
   DFRL_LAUNCH(ctx, (fused_critic_kernel<D0, D1, D2, CRITIC_STEP>), ctas, 320, smem, a);
@@ -1777,10 +1786,10 @@ int launch_critic_step(dfrl_ctx *ctx, const critic_args &a, int ctas) {
 
 template <int D0, int D1, int D2>
 int launch_gae(dfrl_ctx *ctx, const critic_args &a, int ctas) {
-  constexpr int smem = cmap<D1, D2>::TOTAL + 1024;
+  constexpr int smem = cmap<D1, D2, CRITIC_GAE>::TOTAL + 1024;
   static bool attr = false;
   DFRL_TRY(set_smem_once(fused_critic_kernel<D0, D1, D2, CRITIC_GAE>, smem, &attr));
-  DFRL_LAUNCH(ctx, (fused_critic_kernel<D0, D1, D2, CRITIC_GAE>), ctas, 320, smem, a);
+  DFRL_LAUNCH(ctx, (fused_critic_kernel<D0, D1, D2, CRITIC_GAE>), ctas, 480, smem, a);
   return DFRL_OK;
 }
 
