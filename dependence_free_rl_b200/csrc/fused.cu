@@ -860,7 +860,7 @@ template <int D1, int D2, int MODE>
 struct cmap {
   // CRITIC_STEP: 2 pipelines x 5 panels + the shared dH1 slot; CRITIC_GAE (forward only, hidden
   // activations in tensor memory): 3 pipelines x one observation panel (end rows, then start rows)
-  static constexpr int NP = MODE == 0 ? 2 : 3;
+  static constexpr int NP = MODE == 0 ? 2 : 4;
   static constexpr uint32_t W1P = 0;
   static constexpr uint32_t W2_HI = W1P + D1 * 128, W2_LO = W2_HI + D2 * 128;
   static constexpr uint32_t FLOATS = W2_LO + D2 * 128;  // b1[D1] b2[D2] w3[64] b3[4]
@@ -874,7 +874,7 @@ struct cmap {
                             G2_LO = 4 * PANEL;
   static constexpr uint32_t WG_BYTES = MODE == 0 ? 5 * PANEL : PANEL;
   static constexpr uint32_t BARS = WG0 + NP * WG_BYTES;
-  static constexpr uint32_t TOTAL = BARS + 128;
+  static constexpr uint32_t TOTAL = BARS + 256;
   static constexpr uint32_t TCOLS_PER = MODE == 0 ? 256 : 128;  // TMEM columns of a pipeline
   static_assert((D1 * 128) % 1024 == 0 && (D2 * 128) % 1024 == 0, "panel alignment");
   static_assert(TOTAL + 1024 <= 232448, "exceeds the 227 KB shared memory of an SM");
@@ -959,7 +959,7 @@ __device__ __forceinline__ float epi2_value(uint32_t acc, const tid_t &t, const 
 }
 
 template <int D0, int D1, int D2, int MODE>
-__global__ void __launch_bounds__(160 * (MODE == CRITIC_STEP ? 2 : 3), 1) fused_critic_kernel(critic_args a) {
+__global__ void __launch_bounds__(160 * (MODE == CRITIC_STEP ? 2 : 4), 1) fused_critic_kernel(critic_args a) {
   using CM = cmap<D1, D2, MODE>;
   constexpr int NP = CM::NP;
   constexpr int NB = 8;  // bins (the fused path covers the 8-bin problem)
@@ -972,7 +972,7 @@ __global__ void __launch_bounds__(160 * (MODE == CRITIC_STEP ? 2 : 3), 1) fused_
   // the end rows: a parity wait cannot tell two outstanding completions of one mbarrier apart),
   // [4 NP] dH1 slot free
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + CM::BARS);
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + CM::BARS + 120);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + CM::BARS + 248);
   const net3 net = a.net;
   const learner_rows &L = a.rows;
   const tid_t t = thread_id();
@@ -1789,7 +1789,7 @@ int launch_gae(dfrl_ctx *ctx, const critic_args &a, int ctas) {
   constexpr int smem = cmap<D1, D2, CRITIC_GAE>::TOTAL + 1024;
   static bool attr = false;
   DFRL_TRY(set_smem_once(fused_critic_kernel<D0, D1, D2, CRITIC_GAE>, smem, &attr));
-  DFRL_LAUNCH(ctx, (fused_critic_kernel<D0, D1, D2, CRITIC_GAE>), ctas, 480, smem, a);
+  DFRL_LAUNCH(ctx, (fused_critic_kernel<D0, D1, D2, CRITIC_GAE>), ctas, 640, smem, a);
   return DFRL_OK;
 }
 
