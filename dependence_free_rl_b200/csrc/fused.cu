@@ -353,12 +353,14 @@ __device__ __forceinline__ void issue_gemm_ta(uint32_t tmem_d, uint32_t a_tmem, 
   }
 }
 
+// [h0, h1): the 32-column chunks this thread handles (all of them with one thread per row; chunk
+// `half` with two threads per row).
 template <int D, bool TMEM_COPY = false, bool SMEM_STORE = true>
 __device__ __forceinline__ void epi2_fwd(uint32_t acc, const tid_t &t, const float *__restrict__ bias, uint8_t *hi,
-                                         uint8_t *lo) {
+                                         uint8_t *lo, int h0 = 0, int h1 = D / (D < 32 ? D : 32)) {
   constexpr int CH = D < 32 ? D : 32;
 #pragma unroll
-  for (int h = 0; h < D / CH; ++h) {
+  for (int h = h0; h < h1; ++h) {
     float v[CH];
     tmem_load<CH>(acc + t.lane_base + h * CH, v);
 #pragma unroll
@@ -396,10 +398,10 @@ __device__ __forceinline__ uint32_t pos_mask2(uint32_t w) {
 // a 16-byte chunk before it overwrites that same chunk.
 template <int D, bool TMEM_COPY = false>
 __device__ __forceinline__ void epi2_bwd(uint32_t acc, const tid_t &t, const uint8_t *act_hi, uint8_t *hi,
-                                         uint8_t *lo) {
+                                         uint8_t *lo, int h0 = 0, int h1 = D / (D < 32 ? D : 32)) {
   constexpr int CH = D < 32 ? D : 32;
 #pragma unroll
-  for (int h = 0; h < D / CH; ++h) {
+  for (int h = h0; h < h1; ++h) {
     float v[CH];
     tmem_load<CH>(acc + t.lane_base + h * CH, v);
 #pragma unroll
@@ -457,14 +459,14 @@ __device__ __forceinline__ void encode_row(uint8_t *xd, int row, const row_state
 // Operands-ready handshake between a warpgroup's 128 epilogue threads (arrive) and its MMA-issuing
 // warp (sync): named barriers 1 + 2 wg + parity, 160 threads. Two alternating ids: an epilogue
 // thread is never more than one hand-over ahead of the issuer.
-__device__ __forceinline__ void ready_arrive(int wg, uint32_t &parity) {
+__device__ __forceinline__ void ready_arrive(int wg, uint32_t &parity, int threads = 160) {
   umma::fence_proxy_async();
   umma::fence_before_sync();
-  asm volatile("bar.arrive %0, 160;\n" ::"r"(1 + 2 * wg + (int)parity) : "memory");
+  asm volatile("bar.arrive %0, %1;\n" ::"r"(1 + 2 * wg + (int)parity), "r"(threads) : "memory");
   parity ^= 1;
 }
-__device__ __forceinline__ void ready_sync(int wg, uint32_t &parity) {
-  asm volatile("bar.sync %0, 160;\n" ::"r"(1 + 2 * wg + (int)parity) : "memory");
+__device__ __forceinline__ void ready_sync(int wg, uint32_t &parity, int threads = 160) {
+  asm volatile("bar.sync %0, %1;\n" ::"r"(1 + 2 * wg + (int)parity), "r"(threads) : "memory");
   parity ^= 1;
   umma::fence_after_sync();
 }
@@ -861,12 +863,17 @@ struct cmap {
   // CRITIC_STEP: 2 pipelines x 5 panels + the shared dH1 slot; CRITIC_GAE (forward only, hidden
   // activations in tensor memory): 3 pipelines x one observation panel (end rows, then start rows)
   static constexpr int NP = MODE == 0 ? 2 : 4;
+  // CRITIC_STEP with 64-wide layers: TWO epilogue threads per row (one 32-column chunk each): the
+  // critic's epilogues are instruction-heavy and two pipelines of 4 warps leave the SM's issue slots
+  // two thirds empty
+  static constexpr int NH = (MODE == 0 && D1 == 64 && D2 == 64) ? 2 : 1;
+  static constexpr int THREADS = 32 * (4 * NH + 1) * NP;
   static constexpr uint32_t W1P = 0;
   static constexpr uint32_t W2_HI = W1P + D1 * 128, W2_LO = W2_HI + D2 * 128;
   static constexpr uint32_t FLOATS = W2_LO + D2 * 128;  // b1[D1] b2[D2] w3[64] b3[4]
   static constexpr int F_B1 = 0, F_B2 = D1, F_W3 = D1 + D2, F_B3 = D1 + D2 + 64, N_FLOATS = D1 + D2 + 68;
-  static constexpr uint32_t SCR = FLOATS + N_FLOATS * 4;  // per pipeline: ve[128], vs[128]
-  static constexpr uint32_t DH1_HI = (SCR + NP * 2 * TILE * 4 + 1023) / 1024 * 1024;  // shared slot
+  static constexpr uint32_t SCR = FLOATS + N_FLOATS * 4;  // per pipeline: ve[NH][128], vs[NH][128] (partial values)
+  static constexpr uint32_t DH1_HI = (SCR + NP * 2 * NH * TILE * 4 + 1023) / 1024 * 1024;  // shared slot
   static constexpr uint32_t DH1_LO = DH1_HI + PANEL;
   static constexpr uint32_t WG0 = MODE == 0 ? DH1_LO + PANEL : DH1_HI;
   // CRITIC_STEP: XS, H1 hi/lo (lo = staging panel of the end-row observations), dH2 hi/lo
@@ -937,11 +944,12 @@ __device__ __forceinline__ void end_state(const row_state<B> &start, const row_s
 // Layer-2 accumulator -> relu(acc + b2) (registers only) -> value head in fp32.
 template <int D2, bool KEEP>
 __device__ __forceinline__ float epi2_value(uint32_t acc, const tid_t &t, const float *__restrict__ b2,
-                                            const float *__restrict__ w3, float b3, float *keep) {
+                                            const float *__restrict__ w3, float b3, float *keep, int h0 = 0,
+                                            int h1 = D2 / (D2 < 32 ? D2 : 32)) {
   constexpr int CH = D2 < 32 ? D2 : 32;
   float s = 0.f;
 #pragma unroll
-  for (int h = 0; h < D2 / CH; ++h) {
+  for (int h = h0; h < h1; ++h) {
     float v[CH];
     tmem_load<CH>(acc + t.lane_base + h * CH, v);
 #pragma unroll
@@ -959,9 +967,10 @@ __device__ __forceinline__ float epi2_value(uint32_t acc, const tid_t &t, const 
 }
 
 template <int D0, int D1, int D2, int MODE>
-__global__ void __launch_bounds__(160 * (MODE == CRITIC_STEP ? 2 : 4), 1) fused_critic_kernel(critic_args a) {
+__global__ void __launch_bounds__((cmap<D1, D2, MODE>::THREADS), 1) fused_critic_kernel(critic_args a) {
   using CM = cmap<D1, D2, MODE>;
-  constexpr int NP = CM::NP;
+  constexpr int NP = CM::NP, NH = CM::NH;
+  constexpr int RT = 32 + 128 * NH;  // threads of an operands-ready hand-over
   constexpr int NB = 8;  // bins (the fused path covers the 8-bin problem)
   static_assert(D0 == 4 * NB, "observation width");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -976,8 +985,9 @@ __global__ void __launch_bounds__(160 * (MODE == CRITIC_STEP ? 2 : 4), 1) fused_
   const net3 net = a.net;
   const learner_rows &L = a.rows;
   const tid_t t = thread_id();
-  const bool issuer = t.warp >= 4 * NP;                   // warp-uniform
-  const int wg = issuer ? t.warp - 4 * NP : t.warp >> 2;  // pipeline index
+  const bool issuer = t.warp >= 4 * NH * NP;                          // warp-uniform
+  const int wg = issuer ? t.warp - 4 * NH * NP : t.warp / (4 * NH);  // pipeline index
+  const int half = NH == 2 ? (t.warp >> 2) & 1 : 0;                   // which 32-column chunk (NH = 2)
   const uint32_t sbase = umma::smem_u32(smem);
 
   if (t.warp == 0)
@@ -1012,9 +1022,10 @@ __global__ void __launch_bounds__(160 * (MODE == CRITIC_STEP ? 2 : 4), 1) fused_
   uint64_t *bar = bars + wg, *bar_dw2 = bars + NP + wg, *bar_dw1 = bars + 2 * NP + wg, *bar_l1s = bars + 3 * NP + wg,
            *bar_slot = bars + 4 * NP;
   uint32_t rp = 0;
-  float dw3[MODE == CRITIC_STEP ? D2 : 1];
+  constexpr int NDW3 = MODE == CRITIC_STEP ? D2 / NH : 1;  // this thread's columns of dW3
+  float dw3[NDW3];
 #pragma unroll
-  for (int q = 0; q < (MODE == CRITIC_STEP ? D2 : 1); ++q)
+  for (int q = 0; q < NDW3; ++q)
     dw3[q] = 0.f;
   float db3 = 0.f;
 
@@ -1031,26 +1042,26 @@ __global__ void __launch_bounds__(160 * (MODE == CRITIC_STEP ? 2 : 4), 1) fused_
     };
     bool first = true;
     if (wg < nt) {
-      ready_sync(wg, rp);  // end-row observations of the first tile staged in the H1_LO panel
+      ready_sync(wg, rp, RT);  // end-row observations of the first tile staged in the H1_LO panel
       if (umma::elect_one())
         layer1(wbase + CM::H1_LO, bar);
       __syncwarp();
     }
     for (int j = wg; j < nt; j += NP) {
-      ready_sync(wg, rp);  // H1 (end rows)
+      ready_sync(wg, rp, RT);  // H1 (end rows)
       if (umma::elect_one())
         layer2();
       __syncwarp();
-      ready_sync(wg, rp);  // start-row observations in the XS panel
+      ready_sync(wg, rp, RT);  // start-row observations in the XS panel
       if (umma::elect_one())
         layer1(wbase + CM::XS, bar_l1s);
       __syncwarp();
-      ready_sync(wg, rp);  // H1 (start rows)
+      ready_sync(wg, rp, RT);  // H1 (start rows)
       if (umma::elect_one())
         layer2();
       __syncwarp();
       if (MODE == CRITIC_STEP) {
-        ready_sync(wg, rp);  // dH2
+        ready_sync(wg, rp, RT);  // dH2
         // dH1 = dH2 . W2; dW2 += dH2^T . H1 (M = 64) runs behind the dH1 epilogue
         if (umma::elect_one()) {
           // A = dH2 from tensor memory (the targets phase's copy in ACC1)
@@ -1062,7 +1073,7 @@ __global__ void __launch_bounds__(160 * (MODE == CRITIC_STEP ? 2 : 4), 1) fused_
         }
         __syncwarp();
       }
-      ready_sync(wg, rp);  // (dH1 in the shared slot and) the next tile's end-row observations
+      ready_sync(wg, rp, RT);  // (dH1 in the shared slot and) the next tile's end-row observations
       if (umma::elect_one()) {
         if (j + NP < nt)  // ahead of dW1: see fused_policy_step_kernel
           layer1(wbase + CM::H1_LO, bar);
@@ -1081,7 +1092,13 @@ __global__ void __launch_bounds__(160 * (MODE == CRITIC_STEP ? 2 : 4), 1) fused_
     // ================= epilogue threads of pipeline wg: thread = one row of the tile
     const float *b1 = fl + CM::F_B1, *b2 = fl + CM::F_B2, *w3 = fl + CM::F_W3;
     const float b3 = fl[CM::F_B3];
-    float *ve = reinterpret_cast<float *>(smem + CM::SCR) + wg * 2 * TILE, *vs = ve + TILE;
+    // partial values of the tile's rows: ve[half][row], vs[half][row]; V = (sum of the partials) + b3
+    float *ve = reinterpret_cast<float *>(smem + CM::SCR) + wg * 2 * NH * TILE, *vs = ve + NH * TILE;
+    auto value_of = [&](const float *vp, int r) { return NH == 2 ? (vp[r] + vp[TILE + r]) + b3 : vp[r] + b3; };
+    const int h0 = NH == 2 ? half : 0, h1d1 = NH == 2 ? half + 1 : D1 / (D1 < 32 ? D1 : 32),
+              h1d2 = NH == 2 ? half + 1 : D2 / (D2 < 32 ? D2 : 32);
+    const bool stager = half == 0;  // observation encodes, state prefetch, target / db3 bookkeeping
+    constexpr int XT = 128 * NH;    // threads of the value-exchange barrier
     uint32_t phase = 0, phase_dw2 = 0, phase_dw1 = 0, phase_l1s = 0;
     auto wait_mma = [&]() {
       umma::mbar_wait(bar, phase);
@@ -1098,16 +1115,18 @@ __global__ void __launch_bounds__(160 * (MODE == CRITIC_STEP ? 2 : 4), 1) fused_
       int act = 0;
       if (wg < nt) {
         const int tile0 = blockIdx.x + wg * gridDim.x, i0 = tile0 * L.E + e;
-        load_row_state<NB>(L, tile0, t.row, xs);
-        load_live_state<NB>(L, tile0, t.row, xl);
         if (tt < L.T && i0 < L.n) {
           done = L.rec_done[(size_t)tt * L.n + i0];
           act = L.rec_action[(size_t)tt * L.n + i0];
         }
-        end_state<NB>(xs, xl, done, act, last, xe);
-        encode_row<NB>(wsm + CM::H1_LO, t.row, xe, L.inv_w, L.inv_h);
-        pack_state<NB>(xs, ps);
-        ready_arrive(wg, rp);
+        if (stager) {
+          load_row_state<NB>(L, tile0, t.row, xs);
+          load_live_state<NB>(L, tile0, t.row, xl);
+          end_state<NB>(xs, xl, done, act, last, xe);
+          encode_row<NB>(wsm + CM::H1_LO, t.row, xe, L.inv_w, L.inv_h);
+          pack_state<NB>(xs, ps);
+        }
+        ready_arrive(wg, rp, RT);
       }
     }
     for (int j = wg; j < nt; j += NP) {
@@ -1123,27 +1142,29 @@ __global__ void __launch_bounds__(160 * (MODE == CRITIC_STEP ? 2 : 4), 1) fused_
           dmask |= (uint32_t)(L.rec_done[(size_t)q * L.n + tile * L.E + t.row] != 0) << q;
       // ---- pass 1: V of the end rows
       wait_mma();  // layer 1 (end rows): H1 only as a TMEM A operand
-      epi2_fwd<D1, true, false>(tm + C2_ACC0, t, b1, nullptr, nullptr);
-      ready_arrive(wg, rp);
+      epi2_fwd<D1, true, false>(tm + C2_ACC0, t, b1, nullptr, nullptr, h0, h1d1);
+      ready_arrive(wg, rp, RT);
       // start-row observations -> XS (the previous tile's dW1 GEMM ran behind the epilogue above)
       if (MODE == CRITIC_STEP && !first) {
         umma::mbar_wait(bar_dw1, phase_dw1);
         phase_dw1 ^= 1;
       }
-      {
+      if (stager) {
         row_state<NB> xs;
         unpack_state<NB>(ps, xs);
         encode_row<NB>(wsm + CM::XS, t.row, xs, L.inv_w, L.inv_h);
       }
-      ready_arrive(wg, rp);
+      ready_arrive(wg, rp, RT);
       // the next tile's state: loads in flight behind the layer-2 GEMM, packed right after it (the
       // raw bytes would cost 38 registers during the epilogues)
       row_state<NB> ns, nl;
       int ndone = 0, nact = 0;
       if (has_next) {
         const int ntile = tile + NP * gridDim.x, ni = ntile * L.E + e;
-        load_row_state<NB>(L, ntile, t.row, ns);
-        load_live_state<NB>(L, ntile, t.row, nl);
+        if (stager) {
+          load_row_state<NB>(L, ntile, t.row, ns);
+          load_live_state<NB>(L, ntile, t.row, nl);
+        }
         if (tt < L.T && ni < L.n) {
           ndone = L.rec_done[(size_t)tt * L.n + ni];
           nact = L.rec_action[(size_t)tt * L.n + ni];
@@ -1151,24 +1172,22 @@ __global__ void __launch_bounds__(160 * (MODE == CRITIC_STEP ? 2 : 4), 1) fused_
       }
       wait_mma();  // layer 2 (end rows)
       packed_state<NB> pn, pe;
-      if (has_next) {
+      if (has_next && stager) {
         row_state<NB> xe;
         end_state<NB>(ns, nl, ndone, nact, last, xe);
         pack_state<NB>(xe, pe);
         pack_state<NB>(ns, pn);
       }
-      const float v_end = epi2_value<D2, false>(tm + C2_ACC1, t, b2, w3, b3, nullptr);
-      ve[t.row] = v_end;
+      ve[half * TILE + t.row] = epi2_value<D2, false>(tm + C2_ACC1, t, b2, w3, 0.f, nullptr, h0, h1d2);
       // ---- pass 2: start rows, H1 kept for the dW2 GEMM
       umma::mbar_wait(bar_l1s, phase_l1s);  // layer 1 (start rows)
       phase_l1s ^= 1;
       umma::fence_after_sync();
-      epi2_fwd<D1, true, MODE == CRITIC_STEP>(tm + C2_ACC0, t, b1, wsm + CM::H1_HI, wsm + CM::H1_LO);  // panels: dW2
-      ready_arrive(wg, rp);
+      epi2_fwd<D1, true, MODE == CRITIC_STEP>(tm + C2_ACC0, t, b1, wsm + CM::H1_HI, wsm + CM::H1_LO, h0, h1d1);  // panels: dW2
+      ready_arrive(wg, rp, RT);
       wait_mma();  // layer 2 (start rows)
-      const float v = epi2_value<D2, false>(tm + C2_ACC1, t, b2, w3, b3, nullptr);
-      vs[t.row] = v;
-      asm volatile("bar.sync %0, 128;\n" ::"r"(9 + wg) : "memory");  // ve / vs of the tile visible
+      vs[half * TILE + t.row] = epi2_value<D2, false>(tm + C2_ACC1, t, b2, w3, 0.f, nullptr, h0, h1d2);
+      asm volatile("bar.sync %0, %1;\n" ::"r"(9 + wg), "r"(XT) : "memory");  // ve / vs of the tile visible
       if (MODE == CRITIC_GAE) {
         // thread e < E walks its env backwards (same recurrence as device_fns.cuh gae_env)
         if (t.row < L.E && i < L.n) {
@@ -1178,34 +1197,37 @@ __global__ void __launch_bounds__(160 * (MODE == CRITIC_STEP ? 2 : 4), 1) fused_
             const int r = q * L.E + t.row;
             const int d = L.T <= 32 ? (int)((dmask >> q) & 1u) : (int)L.rec_done[kq];
             const bool ends = d || q == L.T - 1;
-            const float vn = ends ? ve[r] : vs[r + L.E];
+            const float vn = ends ? value_of(ve, r) : value_of(vs, r + L.E);
             const float vn_adv = d ? 0.f : vn;
-            const float delta = (d ? 0.f : 1.f) + a.gamma * vn_adv - vs[r];
+            const float delta = (d ? 0.f : 1.f) + a.gamma * vn_adv - value_of(vs, r);
             const float adv = delta + (ends ? 0.f : a.lambda * a.gamma * a_next);
             a.adv_out[kq] = adv;
             a_next = adv;
           }
         }
-        asm volatile("bar.sync %0, 128;\n" ::"r"(9 + wg) : "memory");  // ve / vs may be overwritten
+        asm volatile("bar.sync %0, %1;\n" ::"r"(9 + wg), "r"(XT) : "memory");  // ve / vs may be overwritten
       } else {
         // ---- targets and dY = V - target (square_loss_grad, nn.h:548-550)
+        // (with two threads per row both compute the same dY; thread `stager` keeps the books)
         float dy = 0.f;
         if (valid) {
           const bool ends = done || last;
-          const float vn = ends ? v_end : vs[t.row + L.E];
+          const float vn = ends ? value_of(ve, t.row) : value_of(vs, t.row + L.E);
           const float tgt = (done ? 0.f : 1.f) + a.gamma * vn;  // not masked at terminals (quirk 6)
-          dy = v - tgt;
-          if (a.targets_out)
+          dy = value_of(vs, t.row) - tgt;
+          if (a.targets_out && stager)
             a.targets_out[k] = tgt;
         }
-        db3 += dy;
+        if (stager)
+          db3 += dy;
+        // the next tile overwrites ve / vs only after hand-overs that every thread takes part in
         // dH2 = dY w3 . relu'(H2) (rank 1: no GEMM) -> panels; dW3 += dY H2. H2 = relu(acc + b2) is
         // recomputed from the layer-2 accumulator, which stays in TMEM until the next tile's layer 2
         // (64 registers less than keeping the row across the value exchange)
         {
           constexpr int CH = D2 < 32 ? D2 : 32;
 #pragma unroll
-          for (int h = 0; h < D2 / CH; ++h) {
+          for (int h = h0; h < h1d2; ++h) {
             float y[CH];
             tmem_load<CH>(tm + C2_ACC1 + t.lane_base + h * CH, y);
 #pragma unroll
@@ -1213,10 +1235,11 @@ __global__ void __launch_bounds__(160 * (MODE == CRITIC_STEP ? 2 : 4), 1) fused_
               float g[8];
 #pragma unroll
               for (int q = 0; q < 8; ++q) {
-                const int c = h * CH + 8 * cc + q;
+                const int c = h * CH + 8 * cc + q;  // column; dw3 is indexed by the thread's own columns
                 const float yy = fmaxf(y[8 * cc + q] + b2[c], 0.f);
                 g[q] = yy > 0.f ? dy * w3[c] : 0.f;
-                dw3[c] = fmaf(dy, yy, dw3[c]);
+                const int lc = NH == 2 ? 8 * cc + q : c;
+                dw3[lc] = fmaf(dy, yy, dw3[lc]);
               }
               uint4 hh, ll;
               split8<false>(g, hh, ll);
@@ -1228,22 +1251,24 @@ __global__ void __launch_bounds__(160 * (MODE == CRITIC_STEP ? 2 : 4), 1) fused_
           }
           umma::tmem_st_wait();
         }
-        ready_arrive(wg, rp);
+        ready_arrive(wg, rp, RT);
         wait_mma();  // dH1
         if (j > 0)   // the shared dH1 slot (see fused_policy_step_kernel)
           umma::mbar_wait(bar_slot, (uint32_t)(j - 1) & 1u);
-        epi2_bwd<D1>(tm + C2_ACC0, t, wsm + CM::H1_HI, smem + CM::DH1_HI, smem + CM::DH1_LO);
+        epi2_bwd<D1>(tm + C2_ACC0, t, wsm + CM::H1_HI, smem + CM::DH1_HI, smem + CM::DH1_LO, h0, h1d1);
         umma::mbar_wait(bar_dw2, phase_dw2);  // H1 is free (the dW2 GEMM ran behind the dH1 epilogue)
         phase_dw2 ^= 1;
       }
       if (has_next) {
-        row_state<NB> xe;
-        unpack_state<NB>(pe, xe);
-        encode_row<NB>(wsm + CM::H1_LO, t.row, xe, L.inv_w, L.inv_h);
-        ps = pn;
+        if (stager) {
+          row_state<NB> xe;
+          unpack_state<NB>(pe, xe);
+          encode_row<NB>(wsm + CM::H1_LO, t.row, xe, L.inv_w, L.inv_h);
+          ps = pn;
+        }
         done = ndone;
       }
-      ready_arrive(wg, rp);
+      ready_arrive(wg, rp, RT);
       first = false;
     }
     if (MODE == CRITIC_STEP && !first) {  // the last tile's dW1 GEMM
@@ -1263,7 +1288,8 @@ __global__ void __launch_bounds__(160 * (MODE == CRITIC_STEP ? 2 : 4), 1) fused_
       for (int q = threadIdx.x; q < net.n_params; q += blockDim.x)
         part[q] = 0.f;
     } else {
-      if (!issuer) {  // dW2[n][k]: DA (M = 64) row n = TMEM lane 32 (n / 16) + n % 16, col k
+      const bool drainer = threadIdx.x < 256;  // 256 threads read the TMEM accumulators (t.wg = 0, 1)
+      if (drainer) {  // dW2[n][k]: DA (M = 64) row n = TMEM lane 32 (n / 16) + n % 16, col k
         constexpr int DC = D1 / 2;
         float v[DC], w[DC];
         tmem_load<DC>(tmem + C2_DA + t.lane_base + t.wg * DC, v);
@@ -1279,7 +1305,7 @@ __global__ void __launch_bounds__(160 * (MODE == CRITIC_STEP ? 2 : 4), 1) fused_
           for (int q = 0; q < DC; ++q)
             part[net.o_w2 + nrow * D1 + t.wg * DC + q] = v[q];
       }
-      if (!issuer) {  // dW1[n][k] + db1[n]: DB row n, cols 0..D0-1 and D0; db2[n]: DB row 64 + n, col D0
+      if (drainer) {  // dW1[n][k] + db1[n]: DB row n, cols 0..D0-1 and D0; db2[n]: DB row 64 + n, col D0
         constexpr int DC = (D0 + 16) / 2;
         float v[DC], w[DC];
         tmem_load<DC>(tmem + C2_DB + t.lane_base + t.wg * DC, v);
@@ -1306,11 +1332,13 @@ __global__ void __launch_bounds__(160 * (MODE == CRITIC_STEP ? 2 : 4), 1) fused_
       // are free): red[256 rows][D2 + 1], 4 row quarters per column, combined in order
       float *red = reinterpret_cast<float *>(smem + CM::WG0);
       constexpr int W = D2 + 1;
-      if (!issuer) {
+      if (!issuer) {  // row = pipeline * 128 + tile row; a thread holds NDW3 columns from half * NDW3
+        const int rr = wg * TILE + t.row;
 #pragma unroll
-        for (int q = 0; q < D2; ++q)
-          red[threadIdx.x * W + q] = dw3[q];
-        red[threadIdx.x * W + D2] = db3;
+        for (int q = 0; q < NDW3; ++q)
+          red[rr * W + half * NDW3 + q] = dw3[q];
+        if (half == 0)
+          red[rr * W + D2] = db3;
       }
       __syncthreads();
       float *quart = red + 256 * W;
@@ -1780,7 +1808,7 @@ int launch_critic_step(dfrl_ctx *ctx, const critic_args &a, int ctas) {
   constexpr int smem = cmap<D1, D2, CRITIC_STEP>::TOTAL + 1024;
   static bool attr = false;
   DFRL_TRY(set_smem_once(fused_critic_kernel<D0, D1, D2, CRITIC_STEP>, smem, &attr));
-  DFRL_LAUNCH(ctx, (fused_critic_kernel<D0, D1, D2, CRITIC_STEP>), ctas, 320, smem, a);
+  DFRL_LAUNCH(ctx, (fused_critic_kernel<D0, D1, D2, CRITIC_STEP>), ctas, (cmap<D1, D2, CRITIC_STEP>::THREADS), smem, a);
   return DFRL_OK;
 }
 
@@ -1789,7 +1817,7 @@ int launch_gae(dfrl_ctx *ctx, const critic_args &a, int ctas) {
   constexpr int smem = cmap<D1, D2, CRITIC_GAE>::TOTAL + 1024;
   static bool attr = false;
   DFRL_TRY(set_smem_once(fused_critic_kernel<D0, D1, D2, CRITIC_GAE>, smem, &attr));
-  DFRL_LAUNCH(ctx, (fused_critic_kernel<D0, D1, D2, CRITIC_GAE>), ctas, 640, smem, a);
+  DFRL_LAUNCH(ctx, (fused_critic_kernel<D0, D1, D2, CRITIC_GAE>), ctas, (cmap<D1, D2, CRITIC_GAE>::THREADS), smem, a);
   return DFRL_OK;
 }
 
