@@ -249,6 +249,11 @@ struct pmap {
   static constexpr uint32_t BARS = WG0 + 2 * WG_BYTES;
   static constexpr uint32_t TOTAL = BARS + 64;
   static constexpr uint32_t DY_OFF = 96;  // byte offset of [dY_hi | dY_lo] in a row of the XD panel
+  // Epilogue threads per row. Two (one 32-column chunk each, 576 threads) were measured SLOWER here:
+  // 103 us vs 95.5 us per launch -- unlike the critic step, this kernel is bound by shared-memory
+  // bandwidth (MMA operand fetch + epilogue stores) and the tensor pipe, not by instruction issue.
+  static constexpr int NH = 1;
+  static constexpr int THREADS = 32 * (4 * NH + 1) * 2;
   static_assert((D1 * 128) % 1024 == 0 && (D2 * 128) % 1024 == 0, "panel alignment");
   static_assert(TOTAL + 1024 <= 232448, "exceeds the 227 KB shared memory of an SM");
 };
@@ -476,8 +481,10 @@ __device__ __forceinline__ void ready_sync(int wg, uint32_t &parity, int threads
 // time of the instruction (measured: tools/mma_microbench.py), so a GEMM that is meant to run behind
 // an epilogue must not be issued by a thread that takes part in that epilogue.
 template <int D0, int D1, int D2, int NOUT>
-__global__ void __launch_bounds__(320, 1) fused_policy_step_kernel(policy_step_args a) {
+__global__ void __launch_bounds__((pmap<D1, D2>::THREADS), 1) fused_policy_step_kernel(policy_step_args a) {
   using PM = pmap<D1, D2>;
+  constexpr int NH = PM::NH;          // epilogue threads per row
+  constexpr int RT = 32 + 128 * NH;   // threads of an operands-ready hand-over
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);  // stays a shared-space pointer
   const float *fl = reinterpret_cast<const float *>(smem + PM::FLOATS);
@@ -488,8 +495,9 @@ __global__ void __launch_bounds__(320, 1) fused_policy_step_kernel(policy_step_a
   const net3 net = a.net;
   const learner_rows &L = a.rows;
   const tid_t t = thread_id();
-  const bool issuer = t.warp >= 8;                    // warp-uniform
-  const int wg = issuer ? t.warp - 8 : t.warp >> 2;   // pipeline index
+  const bool issuer = t.warp >= 8 * NH;                          // warp-uniform
+  const int wg = issuer ? t.warp - 8 * NH : t.warp / (4 * NH);  // pipeline index
+  const int half = NH == 2 ? (t.warp >> 2) & 1 : 0;             // which 32-column chunk (NH = 2)
   const uint32_t sbase = umma::smem_u32(smem);
   const long long clk_entry = clock64();
 
@@ -504,7 +512,7 @@ __global__ void __launch_bounds__(320, 1) fused_policy_step_kernel(policy_step_a
   zero_bytes(smem + PM::DH1_HI, PM::BARS - PM::DH1_HI);
   __syncthreads();
   // ones column (col D0) of both XD panels: [dH1|dH2]^T . 1 = bias gradients for free
-  if (!issuer)
+  if (!issuer && half == 0)
     *reinterpret_cast<uint16_t *>(smem + PM::WG0 + wg * PM::WG_BYTES + PM::XD + umma::panel_off(t.row, D0)) = 0x3F80;
   sync_after_smem_writes();
   const uint32_t tmem = *tmem_slot;
@@ -518,7 +526,7 @@ __global__ void __launch_bounds__(320, 1) fused_policy_step_kernel(policy_step_a
   uint64_t *bar = bars + wg, *bar_dw2 = bars + 3 + wg, *bar_dw1 = bars + 5 + wg;
   uint32_t rp = 0;  // parity of the operands-ready barrier
 
-  long long *clk = (a.clk && blockIdx.x == 0 && threadIdx.x == 96) ? a.clk : nullptr;
+  long long *clk = (a.clk && blockIdx.x == 0 && threadIdx.x == 96) ? a.clk : nullptr;  // pipeline 0, chunk 0
   int clk_n = 0;
 #define STAMP() do { if (clk && clk_n < 104) clk[clk_n++] = clock64(); } while (0)
   if (clk)
@@ -533,7 +541,7 @@ __global__ void __launch_bounds__(320, 1) fused_policy_step_kernel(policy_step_a
     // ================= MMA issuer of pipeline wg: one GEMM (group) per operands-ready hand-over
     bool first = true;
     if (wg < nt) {
-      ready_sync(wg, rp);  // X0 of the first tile staged in the H1_LO panel
+      ready_sync(wg, rp, RT);  // X0 of the first tile staged in the H1_LO panel
       if (umma::elect_one()) {
         issue_gemm<D0 / 16, false, false, false, true>(tm + P2_ACC0, wbase + PM::H1_LO, 0, sbase + PM::W1P,
                                                        sbase + PM::W1P + 64, ID<D1>::FK_FK, false);
@@ -542,20 +550,20 @@ __global__ void __launch_bounds__(320, 1) fused_policy_step_kernel(policy_step_a
       __syncwarp();
     }
     for (int j = wg; j < nt; j += 2) {
-      ready_sync(wg, rp);  // H1
+      ready_sync(wg, rp, RT);  // H1
       if (umma::elect_one()) {  // A = H1 from tensor memory (the epilogue's copy in ACC0)
         issue_gemm_ta<D1, D1 / 16, false>(tm + P2_ACC1, tm + P2_ACC0, sbase + PM::W2_HI, sbase + PM::W2_LO,
                                           ID<D2>::FK_FK);
         umma::commit(bar);
       }
       __syncwarp();
-      ready_sync(wg, rp);  // H2; head: columns 8..15 of the result repeat 0..7 (stacked B operand), unused
+      ready_sync(wg, rp, RT);  // H2; head: columns 8..15 of the result repeat 0..7 (stacked B operand), unused
       if (umma::elect_one()) {  // A = H2 from tensor memory (ACC1)
         issue_gemm_ta<D2, D2 / 16, false>(tm + P2_ACC0, tm + P2_ACC1, sbase + PM::W3A, sbase + PM::W3B, ID<16>::FK_FK);
         umma::commit(bar);
       }
       __syncwarp();
-      ready_sync(wg, rp);  // dY
+      ready_sync(wg, rp, RT);  // dY
       // dW3^T += H2^T . [dY_hi | dY_lo] (M = 64, N = 16) first: the dH2 epilogue overwrites H2;
       // dH2 = [dY_hi | dY_lo] . [hi(W3); hi(W3)] + [dY_hi | dY_lo] . [lo(W3); 0]
       if (umma::elect_one()) {
@@ -566,7 +574,7 @@ __global__ void __launch_bounds__(320, 1) fused_policy_step_kernel(policy_step_a
         umma::commit(bar);
       }
       __syncwarp();
-      ready_sync(wg, rp);  // dH2 (in the H2 slot)
+      ready_sync(wg, rp, RT);  // dH2 (in the H2 slot)
       // dH1 = dH2 . W2; dW2 += dH2^T . H1 (M = 64) runs behind the dH1 epilogue
       if (umma::elect_one()) {
         // A = dH2 from tensor memory (the epilogue's copy in ACC0)
@@ -577,7 +585,7 @@ __global__ void __launch_bounds__(320, 1) fused_policy_step_kernel(policy_step_a
         umma::commit(bar_dw2);
       }
       __syncwarp();
-      ready_sync(wg, rp);  // dH1 (shared slot) and the next tile's X0 (H1_LO panel)
+      ready_sync(wg, rp, RT);  // dH1 (shared slot) and the next tile's X0 (H1_LO panel)
       // layer 1 of the NEXT tile goes first: the in-order pipe would otherwise put this tile's dW1
       // GEMM on the next tile's critical path; dW1 runs behind the next tile's first epilogue.
       //   DB[128 x D0+16] += [dH1|dH2]^T . [X0|1]   rows 0.. = [dW1 | db1], rows 64.. col D0 = db2
@@ -603,15 +611,23 @@ __global__ void __launch_bounds__(320, 1) fused_policy_step_kernel(policy_step_a
       phase ^= 1;
       umma::fence_after_sync();
     };
+    // Two threads per row (NH = 2): each handles one 32-column chunk in the hidden-layer epilogues;
+    // chunk 0's threads also run the head (softmax, loss gradient) and keep db3, chunk 1's threads
+    // prefetch the next tile's state and encode the observations.
+    const int h0 = NH == 2 ? half : 0, h1d1 = NH == 2 ? half + 1 : D1 / (D1 < 32 ? D1 : 32),
+              h1d2 = NH == 2 ? half + 1 : D2 / (D2 < 32 ? D2 : 32);
+    const bool header = half == 0, stager = half == NH - 1;
     bool first = true;
     row_state<NOUT> xr, xn;  // raw state of this tile / of the next tile
     // The observations of a tile are encoded twice: into the (dead) H1_LO panel for the layer-1
     // GEMM, so that the tile can start while the previous tile's dW1 GEMM still reads its XD panel,
     // and, behind the layer-2 GEMM, into the XD panel for this tile's own dW1 GEMM.
     if (wg < nt) {
-      load_row_state<NOUT>(L, blockIdx.x + wg * gridDim.x, t.row, xr);
-      encode_row<NOUT>(wsm + PM::H1_LO, t.row, xr, L.inv_w, L.inv_h);
-      ready_arrive(wg, rp);
+      if (stager) {
+        load_row_state<NOUT>(L, blockIdx.x + wg * gridDim.x, t.row, xr);
+        encode_row<NOUT>(wsm + PM::H1_LO, t.row, xr, L.inv_w, L.inv_h);
+      }
+      ready_arrive(wg, rp, RT);
     }
     for (int j = wg; j < nt; j += 2) {
       const int tile = blockIdx.x + j * gridDim.x;
@@ -619,7 +635,7 @@ __global__ void __launch_bounds__(320, 1) fused_policy_step_kernel(policy_step_a
       // global loads that are consumed later: row data for the head, the next tile's state
       const int tt = t.row / L.E, e = t.row % L.E;
       const int i = tile * L.E + e;
-      const bool valid = tt < L.T && i < L.n;
+      const bool valid = header && tt < L.T && i < L.n;
       const size_t k = (size_t)tt * L.n + i;
       int act = 0;
       float A = 0.f;
@@ -636,27 +652,28 @@ __global__ void __launch_bounds__(320, 1) fused_policy_step_kernel(policy_step_a
           po[q] = pr[q];
       }
       const bool has_next = j + 2 < nt;
-      if (has_next)
+      if (has_next && stager)
         load_row_state<NOUT>(L, tile + 2 * gridDim.x, t.row, xn);
       wait_mma();  // layer 1
       STAMP();
-      epi2_fwd<D1, true>(tm + P2_ACC0, t, fl + PM::F_B1, wsm + PM::H1_HI, wsm + PM::H1_LO);
-      ready_arrive(wg, rp);
+      epi2_fwd<D1, true>(tm + P2_ACC0, t, fl + PM::F_B1, wsm + PM::H1_HI, wsm + PM::H1_LO, h0, h1d1);
+      ready_arrive(wg, rp, RT);
       if (!first) {  // the previous tile's dW1 GEMM (XD, dH2 in the H2 slot) ran behind this epilogue
         umma::mbar_wait(bar_dw1, phase_dw1);
         phase_dw1 ^= 1;
       }
-      encode_row<NOUT>(wsm + PM::XD, t.row, xr, L.inv_w, L.inv_h);
+      if (stager)
+        encode_row<NOUT>(wsm + PM::XD, t.row, xr, L.inv_w, L.inv_h);
       STAMP();
       wait_mma();  // layer 2
       STAMP();
-      epi2_fwd<D2, true>(tm + P2_ACC1, t, fl + PM::F_B2, wsm + PM::H2_HI, wsm + PM::H2_LO);
-      ready_arrive(wg, rp);
+      epi2_fwd<D2, true>(tm + P2_ACC1, t, fl + PM::F_B2, wsm + PM::H2_HI, wsm + PM::H2_LO, h0, h1d2);
+      ready_arrive(wg, rp, RT);
       STAMP();
       wait_mma();  // layer 3
       STAMP();
       // ---- head epilogue: softmax, loss gradient, softmax backward -> dY = [hi | lo] in the XD panel
-      {
+      if (header) {
         float v[8];
         tmem_load<8>(tm + P2_ACC0 + t.lane_base, v);
         float dl[8];
@@ -715,12 +732,12 @@ __global__ void __launch_bounds__(320, 1) fused_policy_step_kernel(policy_step_a
         *reinterpret_cast<uint4 *>(wsm + PM::XD + umma::panel_chunk_off(t.row, 6)) = h;
         *reinterpret_cast<uint4 *>(wsm + PM::XD + umma::panel_chunk_off(t.row, 7)) = l;
       }
-      ready_arrive(wg, rp);
+      ready_arrive(wg, rp, RT);
       STAMP();
       wait_mma();  // dW3, dH2
       STAMP();
-      epi2_bwd<D2, true>(tm + P2_ACC0, t, wsm + PM::H2_HI, wsm + PM::H2_HI, wsm + PM::H2_LO);
-      ready_arrive(wg, rp);
+      epi2_bwd<D2, true>(tm + P2_ACC0, t, wsm + PM::H2_HI, wsm + PM::H2_HI, wsm + PM::H2_LO, h0, h1d2);
+      ready_arrive(wg, rp, RT);
       STAMP();
       wait_mma();  // dH1
       // the shared dH1 slot: free once the previous tile of this CTA (the other pipeline's) has
@@ -728,16 +745,16 @@ __global__ void __launch_bounds__(320, 1) fused_policy_step_kernel(policy_step_a
       if (j > 0)
         umma::mbar_wait(bars + 2, (uint32_t)(j - 1) & 1u);
       STAMP();
-      epi2_bwd<D1>(tm + P2_ACC1, t, wsm + PM::H1_HI, smem + PM::DH1_HI, smem + PM::DH1_LO);
+      epi2_bwd<D1>(tm + P2_ACC1, t, wsm + PM::H1_HI, smem + PM::DH1_HI, smem + PM::DH1_LO, h0, h1d1);
       STAMP();
       umma::mbar_wait(bar_dw2, phase_dw2);  // H1 is free (the dW2 GEMM ran behind the dH1 epilogue)
       phase_dw2 ^= 1;
       STAMP();
-      if (has_next) {
+      if (has_next && stager) {
         encode_row<NOUT>(wsm + PM::H1_LO, t.row, xn, L.inv_w, L.inv_h);
         xr = xn;
       }
-      ready_arrive(wg, rp);
+      ready_arrive(wg, rp, RT);
       STAMP();
       first = false;
     }
@@ -761,7 +778,8 @@ __global__ void __launch_bounds__(320, 1) fused_policy_step_kernel(policy_step_a
       part[q] = 0.f;
   } else {
     // dW2[n][k]: DA (M = 64) row n = TMEM lane 32 (n / 16) + n % 16, col k
-    if (!issuer) {
+    const bool drainer = threadIdx.x < 256;  // 256 threads read the TMEM accumulators (t.wg = 0, 1)
+    if (drainer) {
       constexpr int DC = D1 / 2;
       float v[DC], w[DC];
       tmem_load<DC>(tmem + P2_DA + t.lane_base + t.wg * DC, v);
@@ -778,7 +796,7 @@ __global__ void __launch_bounds__(320, 1) fused_policy_step_kernel(policy_step_a
           part[net.o_w2 + nrow * D1 + t.wg * DC + q] = v[q];
     }
     // dW1[n][k] + db1[n]: DB row n, cols 0..D0-1 and D0; db2[n]: DB row 64 + n, col D0
-    if (!issuer) {
+    if (drainer) {
       constexpr int DC = (D0 + 16) / 2;
       float v[DC], w[DC];
       tmem_load<DC>(tmem + P2_DB + t.lane_base + t.wg * DC, v);
@@ -802,7 +820,7 @@ __global__ void __launch_bounds__(320, 1) fused_policy_step_kernel(policy_step_a
       }
     }
     // dW3[n][k] = DC (M = 64) row k, cols n (H2^T dY_hi) and 8 + n (H2^T dY_lo)
-    if (!issuer && t.wg == 0) {
+    if (drainer && t.wg == 0) {
       float v[16], w[16];
       tmem_load<16>(tmem + P2_DC + t.lane_base, v);
       if (two) {
@@ -817,7 +835,7 @@ __global__ void __launch_bounds__(320, 1) fused_policy_step_kernel(policy_step_a
         for (int q = 0; q < NOUT; ++q)
           part[net.o_w3 + q * D2 + krow] = v[q] + v[8 + q];
     }
-    // db3: fixed-order tree inside each warp, then the 8 warps in order (scratch = warpgroup 0's H1)
+    // db3: fixed-order tree inside each warp, then the epilogue warps in order (scratch = pipeline 0's H1)
     float *red = reinterpret_cast<float *>(smem + PM::WG0 + PM::H1_HI);
 #pragma unroll
     for (int q = 0; q < NOUT; ++q) {
@@ -826,13 +844,13 @@ __global__ void __launch_bounds__(320, 1) fused_policy_step_kernel(policy_step_a
       for (int o = 16; o > 0; o >>= 1)
         s += __shfl_xor_sync(0xffffffffu, s, o);
       if (t.lane == 0 && !issuer)
-        red[t.warp * 8 + q] = s;
+        red[t.warp * 8 + q] = s;  // (warps that did not run the head contribute zeros)
     }
     __syncthreads();
     if (threadIdx.x < NOUT) {
       float s = 0.f;
 #pragma unroll
-      for (int w = 0; w < 8; ++w)
+      for (int w = 0; w < 8 * NH; ++w)
         s += red[w * 8 + threadIdx.x];
       part[net.o_b3 + threadIdx.x] = s;
     }
@@ -1155,16 +1173,16 @@ __global__ void __launch_bounds__((cmap<D1, D2, MODE>::THREADS), 1) fused_critic
         encode_row<NB>(wsm + CM::XS, t.row, xs, L.inv_w, L.inv_h);
       }
       ready_arrive(wg, rp, RT);
-      // the next tile's state: loads in flight behind the layer-2 GEMM, packed right after it (the
-      // raw bytes would cost 38 registers during the epilogues)
+      // the next tile's state: the start-state loads fly behind the layer-2 GEMM of the end rows and
+      // are packed right after it; the live-state loads fly behind the start rows' layer 1 / 2 (raw
+      // bytes cost 18 registers per state)
       row_state<NB> ns, nl;
       int ndone = 0, nact = 0;
+      const int ntile = tile + NP * gridDim.x;
       if (has_next) {
-        const int ntile = tile + NP * gridDim.x, ni = ntile * L.E + e;
-        if (stager) {
+        const int ni = ntile * L.E + e;
+        if (stager)
           load_row_state<NB>(L, ntile, t.row, ns);
-          load_live_state<NB>(L, ntile, t.row, nl);
-        }
         if (tt < L.T && ni < L.n) {
           ndone = L.rec_done[(size_t)tt * L.n + ni];
           nact = L.rec_action[(size_t)tt * L.n + ni];
@@ -1173,10 +1191,8 @@ __global__ void __launch_bounds__((cmap<D1, D2, MODE>::THREADS), 1) fused_critic
       wait_mma();  // layer 2 (end rows)
       packed_state<NB> pn, pe;
       if (has_next && stager) {
-        row_state<NB> xe;
-        end_state<NB>(ns, nl, ndone, nact, last, xe);
-        pack_state<NB>(xe, pe);
         pack_state<NB>(ns, pn);
+        load_live_state<NB>(L, ntile, t.row, nl);
       }
       ve[half * TILE + t.row] = epi2_value<D2, false>(tm + C2_ACC1, t, b2, w3, 0.f, nullptr, h0, h1d2);
       // ---- pass 2: start rows, H1 kept for the dW2 GEMM
@@ -1185,6 +1201,12 @@ __global__ void __launch_bounds__((cmap<D1, D2, MODE>::THREADS), 1) fused_critic
       umma::fence_after_sync();
       epi2_fwd<D1, true, MODE == CRITIC_STEP>(tm + C2_ACC0, t, b1, wsm + CM::H1_HI, wsm + CM::H1_LO, h0, h1d1);  // panels: dW2
       ready_arrive(wg, rp, RT);
+      if (has_next && stager) {  // the next tile's end state, packed
+        row_state<NB> xs2, xe;
+        unpack_state<NB>(pn, xs2);
+        end_state<NB>(xs2, nl, ndone, nact, last, xe);
+        pack_state<NB>(xe, pe);
+      }
       wait_mma();  // layer 2 (start rows)
       vs[half * TILE + t.row] = epi2_value<D2, false>(tm + C2_ACC1, t, b2, w3, 0.f, nullptr, h0, h1d2);
       asm volatile("bar.sync %0, %1;\n" ::"r"(9 + wg), "r"(XT) : "memory");  // ve / vs of the tile visible
@@ -1799,7 +1821,7 @@ int launch_policy_step(dfrl_ctx *ctx, const policy_step_args &a, int ctas) {
   constexpr int smem = pmap<D1, D2>::TOTAL + 1024;
   static bool attr = false;
   DFRL_TRY(set_smem_once(fused_policy_step_kernel<D0, D1, D2, NOUT>, smem, &attr));
-  DFRL_LAUNCH(ctx, (fused_policy_step_kernel<D0, D1, D2, NOUT>), ctas, 320, smem, a);
+  DFRL_LAUNCH(ctx, (fused_policy_step_kernel<D0, D1, D2, NOUT>), ctas, (pmap<D1, D2>::THREADS), smem, a);
   return DFRL_OK;
 }
 
