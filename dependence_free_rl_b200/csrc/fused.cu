@@ -1483,9 +1483,14 @@ __global__ void __launch_bounds__(256) fused_reduce_exchange_kernel(const float 
   }
   __syncthreads();
   if (slice == 0 && i < n) {
+    float x[DFRL_P2P_MAX_RANKS];  // all loads in flight before the first add
+#pragma unroll
+    for (int q = 0; q < DFRL_P2P_MAX_RANKS; ++q)
+      x[q] = q < v.nranks ? *reinterpret_cast<const volatile float *>(dfrl_p2p_data(local, slot, q) + i) : 0.f;
     float g = 0.f;
-    for (int q = 0; q < v.nranks; ++q)
-      g += *reinterpret_cast<const volatile float *>(dfrl_p2p_data(local, slot, q) + i);
+#pragma unroll
+    for (int q = 0; q < DFRL_P2P_MAX_RANKS; ++q)  // rank order; ranks >= nranks add +0
+      g += x[q];
     grad[i] = g;
     const dfrl_opt_spec &opt = tail.opt;
     if (opt.params)
