@@ -62,28 +62,22 @@ void dfrl_profile_mark(dfrl_ctx *ctx, const char *name, int end);
 // allocation [2 slots][cap floats] + flags, IPC-mapped by every other rank of the node.
 constexpr int DFRL_P2P_MAX_RANKS = 8;
 constexpr size_t DFRL_P2P_CAP = 1 << 18;  // floats per gradient (1 MB): >= the largest flat gradient
-// Exchange buffer of a rank (PUSH protocol: every rank stores its reduced gradient INTO its peers'
-// buffers, so the receiver polls and reads local memory only):
-//   data   [2 slots][DFRL_P2P_MAX_RANKS source ranks][DFRL_P2P_CAP] floats
+// Exchange buffer of a rank (PUSH protocol, flag-in-data: every rank stores {value, exchange number}
+// pairs INTO its peers' buffers with single 8-byte stores; the receiver polls its local copy until
+// the exchange number matches -- no fence, no separate flag, one NVLink store latency):
+//   data   [2 slots][DFRL_P2P_MAX_RANKS source ranks][DFRL_P2P_CAP] x {float value, unsigned epoch}
 //   words  16 unsigned; word 2 = this rank's exchange counter
-//   flags  [2 slots][DFRL_P2P_MAX_RANKS source ranks][DFRL_P2P_BLOCKS]: block b of source rank r has
-//          delivered its 32 gradient entries of exchange `value`
 struct dfrl_p2p {
   float *local = nullptr;
   float *peer[DFRL_P2P_MAX_RANKS];   // peer[r]: rank r's allocation mapped here (own rank: local)
   bool attached = false;
 };
-constexpr size_t DFRL_P2P_BLOCKS = DFRL_P2P_CAP / 32;
-constexpr size_t DFRL_P2P_DATA_FLOATS = 2 * (size_t)DFRL_P2P_MAX_RANKS * DFRL_P2P_CAP;
-constexpr size_t DFRL_P2P_BYTES =
-    sizeof(float) * DFRL_P2P_DATA_FLOATS + 64 + sizeof(unsigned) * 2 * DFRL_P2P_MAX_RANKS * DFRL_P2P_BLOCKS;
-__host__ __device__ static inline float *dfrl_p2p_data(float *base, int slot, int src) {
-  return base + ((size_t)slot * DFRL_P2P_MAX_RANKS + src) * DFRL_P2P_CAP;
+constexpr size_t DFRL_P2P_DATA_FLOATS = 2 * 2 * (size_t)DFRL_P2P_MAX_RANKS * DFRL_P2P_CAP;  // 8-byte entries
+constexpr size_t DFRL_P2P_BYTES = sizeof(float) * DFRL_P2P_DATA_FLOATS + 64;
+__host__ __device__ static inline unsigned long long *dfrl_p2p_data(float *base, int slot, int src) {
+  return reinterpret_cast<unsigned long long *>(base) + ((size_t)slot * DFRL_P2P_MAX_RANKS + src) * DFRL_P2P_CAP;
 }
 __host__ __device__ static inline unsigned *dfrl_p2p_flags(float *base) { return reinterpret_cast<unsigned *>(base + DFRL_P2P_DATA_FLOATS); }
-__host__ __device__ static inline unsigned *dfrl_p2p_block_flags(float *base, int slot, int src) {
-  return dfrl_p2p_flags(base) + 16 + ((size_t)slot * DFRL_P2P_MAX_RANKS + src) * DFRL_P2P_BLOCKS;
-}
 
 struct dfrl_ctx {
   int device = 0;

@@ -1427,15 +1427,17 @@ __global__ void __launch_bounds__(256) fused_reduce_partials_kernel(const float 
   }
 }
 
-// Reduction + exchange + optimizer in ONE kernel (several ranks), PUSH protocol: block b sums the
-// per-CTA partials of its 32 gradient entries; warp q then stores them into rank q's exchange buffer
-// (remote stores over NVLink, own rank included), fences and raises flag [source = this rank][b]
-// THERE. The block then polls its LOCAL flags of all source ranks, sums the local copies in rank
-// order (bit-identical on every rank) and applies the optimizer. Nothing on the receive side
-// crosses NVLink, and no grid-wide hand-over sits between a rank's reduction and the exchange; the
-// ticket only elects the block that advances the exchange counter for the next launch. A block
-// never waits for another block of its own grid, and a peer's producer never depends on this rank
-// (bounded spin -> trap instead of a hung GPU).
+// Reduction + exchange + optimizer in ONE kernel (several ranks), PUSH protocol with the flag in
+// the data: block b sums the per-CTA partials of its 32 gradient entries; warp q then stores them
+// as {value, exchange number} pairs (one 8-byte store each, single-copy atomic) into rank q's
+// exchange buffer over NVLink (own rank included). The block then polls its LOCAL copies of all
+// source ranks until their exchange number matches, sums the values in rank order (bit-identical on
+// every rank) and applies the optimizer. No fence, no separate flag, nothing on the receive side
+// crosses NVLink: an exchange costs one remote-store latency on top of the reduction. The ticket
+// only elects the block that advances the exchange counter for the next launch. Two slots: a rank is
+// never more than one exchange ahead of a peer (it needs the peer's contribution to finish one). A
+// block never waits for another block of its own grid, and a peer's producer never depends on this
+// rank (bounded spin -> trap instead of a hung GPU).
 struct p2p_view {
   float *peer[DFRL_P2P_MAX_RANKS];
   int nranks, rank;
@@ -1461,36 +1463,33 @@ __global__ void __launch_bounds__(256) fused_reduce_exchange_kernel(const float 
   for (int q = 0; q < 8; ++q)  // every warp forms the same sum (fixed order)
     r += sm[q][lane];
   static_assert(DFRL_P2P_MAX_RANKS <= 8, "one warp per destination rank");
-  if (slice < v.nranks) {
-    if (i < n)
-      dfrl_p2p_data(v.peer[slice], slot, v.rank)[i] = r;
-    __threadfence_system();
-    __syncwarp();
-    if (lane == 0)
-      *reinterpret_cast<volatile unsigned *>(dfrl_p2p_block_flags(v.peer[slice], slot, v.rank) + blockIdx.x) = epoch;
+  if (slice < v.nranks && i < n) {
+    const unsigned long long w = ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(r);
+    *reinterpret_cast<volatile unsigned long long *>(dfrl_p2p_data(v.peer[slice], slot, v.rank) + i) = w;
   }
   if (threadIdx.x == 0 && atomicAdd(tail.ticket, 1u) == gridDim.x - 1) {  // all blocks have read the counter
     *tail.ticket = 0;
     words[2] = epoch;
   }
-  if (slice < v.nranks && lane == 0) {
-    const volatile unsigned *pf = reinterpret_cast<const volatile unsigned *>(dfrl_p2p_block_flags(local, slot, slice)) + blockIdx.x;
-    unsigned spins = 0;
-    while (*pf < epoch)
-      if (++spins > (1u << 28))
-        __trap();
-    __threadfence_system();
-  }
-  __syncthreads();
   if (slice == 0 && i < n) {
-    float x[DFRL_P2P_MAX_RANKS];  // all loads in flight before the first add
+    unsigned long long x[DFRL_P2P_MAX_RANKS];
+    unsigned spins = 0;
+    bool all;
+    do {  // all loads in flight; repeat until every source rank's pair carries this exchange number
+      all = true;
 #pragma unroll
-    for (int q = 0; q < DFRL_P2P_MAX_RANKS; ++q)
-      x[q] = q < v.nranks ? *reinterpret_cast<const volatile float *>(dfrl_p2p_data(local, slot, q) + i) : 0.f;
+      for (int q = 0; q < DFRL_P2P_MAX_RANKS; ++q) {
+        x[q] = q < v.nranks ? *reinterpret_cast<const volatile unsigned long long *>(dfrl_p2p_data(local, slot, q) + i)
+                            : ((unsigned long long)epoch << 32);
+        all = all && (unsigned)(x[q] >> 32) == epoch;
+      }
+      if (!all && ++spins > (1u << 26))
+        __trap();
+    } while (!all);
     float g = 0.f;
 #pragma unroll
     for (int q = 0; q < DFRL_P2P_MAX_RANKS; ++q)  // rank order; ranks >= nranks add +0
-      g += x[q];
+      g += __uint_as_float((unsigned)x[q]);
     grad[i] = g;
     const dfrl_opt_spec &opt = tail.opt;
     if (opt.params)
@@ -1916,7 +1915,6 @@ int launch_reduce(dfrl_trainer *t, fused_state *f, dfrl_mlp *m, const net3 &net,
     tail.opt = *opt;
   }
   if (exchange) {
-    DFRL_CHECK((size_t)ceil_div(net.n_params, 32) <= DFRL_P2P_BLOCKS, "flat gradient exceeds the exchange slot");
     p2p_view v;
     memset(&v, 0, sizeof(v));
     for (int r = 0; r < ctx->nranks; ++r)
