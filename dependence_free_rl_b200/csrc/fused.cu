@@ -1391,9 +1391,38 @@ __global__ void __launch_bounds__((cmap<D1, D2, MODE>::THREADS), 1) fused_critic
     umma::tmem_dealloc(tmem, 512);
 }
 
-// Second stage of the gradient: fixed-order sum of the per-CTA partials. Block = 32 parameters x 8
-// slices of the CTA range; the 8 slice sums are combined in a fixed order. With a single rank the
+// Second stage of the gradient: fixed-order sum of the per-CTA partials. With a single rank the
 // optimizer update (nn.h:616-698) of the same 32 parameters follows in the same kernel.
+// Block = 32 consecutive gradient entries x RS slices of the per-CTA partials (1024 threads):
+// a thread sums <= 5 partials with all its loads in flight (the 8-slice version walked 19 partials
+// one L2 round trip at a time), then the slices are combined in a fixed order: 4 groups of 8
+// serially, then the 4 group sums. Every thread returns the same sum.
+constexpr int RS = 32;
+__device__ __forceinline__ float reduce_block_sum(const float *__restrict__ part, int ctas, int n, int i, int slice,
+                                                  int lane, float (*sm)[33]) {
+  float x[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int c = slice + RS * q;
+    x[q] = (i < n && c < ctas) ? part[(size_t)c * n + i] : 0.f;
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+    s += x[q];
+  sm[slice][lane] = s;
+  __syncthreads();
+  float g[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    float r = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      r += sm[8 * u + q][lane];
+    g[u] = r;
+  }
+  return (g[0] + g[1]) + (g[2] + g[3]);
+}
 struct reduce_tail {
   dfrl_opt_spec opt;   // params == null: no update
   unsigned *ticket;    // multi-rank exchange: zero before the launch, zero again after it
@@ -1403,23 +1432,14 @@ struct reduce_tail {
   // exchange e = counter + 1 uses slot e & 1; the block that takes the last ticket bumps the counter.
   float *exchange;
 };
-__global__ void __launch_bounds__(256) fused_reduce_partials_kernel(const float *__restrict__ part, int ctas,
-                                                                    int n, float *__restrict__ grad,
-                                                                    reduce_tail tail) {
-  __shared__ float sm[8][33];
+__global__ void __launch_bounds__(32 * RS) fused_reduce_partials_kernel(const float *__restrict__ part, int ctas,
+                                                                       int n, float *__restrict__ grad,
+                                                                       reduce_tail tail) {
+  __shared__ float sm[RS][33];
   const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + lane;
-  float s = 0.f;
-  if (i < n)
-    for (int c = slice; c < ctas; c += 8)
-      s += part[(size_t)c * n + i];
-  sm[slice][lane] = s;
-  __syncthreads();
+  const float r = reduce_block_sum(part, ctas, n, i, slice, lane, sm);
   if (slice == 0 && i < n) {
-    float r = 0.f;
-#pragma unroll
-    for (int q = 0; q < 8; ++q)
-      r += sm[q][lane];
     grad[i] = r;
     const dfrl_opt_spec &opt = tail.opt;
     if (opt.params)
@@ -1442,27 +1462,18 @@ struct p2p_view {
   float *peer[DFRL_P2P_MAX_RANKS];
   int nranks, rank;
 };
-__global__ void __launch_bounds__(256) fused_reduce_exchange_kernel(const float *__restrict__ part, int ctas, int n,
-                                                                    float *__restrict__ grad, p2p_view v,
-                                                                    reduce_tail tail) {
-  __shared__ float sm[8][33];
+__global__ void __launch_bounds__(32 * RS) fused_reduce_exchange_kernel(const float *__restrict__ part, int ctas, int n,
+                                                                       float *__restrict__ grad, p2p_view v,
+                                                                       reduce_tail tail) {
+  __shared__ float sm[RS][33];
   const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
   float *local = v.peer[v.rank];
   volatile unsigned *words = reinterpret_cast<volatile unsigned *>(dfrl_p2p_flags(local));
   const unsigned epoch = words[2] + 1;  // every block reads the counter before its ticket
   const int slot = (int)(epoch & 1u);
   const int i = blockIdx.x * 32 + lane;
-  float s = 0.f;
-  if (i < n)
-    for (int c = slice; c < ctas; c += 8)
-      s += part[(size_t)c * n + i];
-  sm[slice][lane] = s;
-  __syncthreads();
-  float r = 0.f;
-#pragma unroll
-  for (int q = 0; q < 8; ++q)  // every warp forms the same sum (fixed order)
-    r += sm[q][lane];
-  static_assert(DFRL_P2P_MAX_RANKS <= 8, "one warp per destination rank");
+  const float r = reduce_block_sum(part, ctas, n, i, slice, lane, sm);  // every warp holds the same sum
+  static_assert(DFRL_P2P_MAX_RANKS <= RS, "one warp per destination rank");
   if (slice < v.nranks && i < n) {
     const unsigned long long w = ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(r);
     *reinterpret_cast<volatile unsigned long long *>(dfrl_p2p_data(v.peer[slice], slot, v.rank) + i) = w;
@@ -1903,6 +1914,7 @@ critic_args make_critic_args(dfrl_trainer *t, fused_state *f) {
 int launch_reduce(dfrl_trainer *t, fused_state *f, dfrl_mlp *m, const net3 &net, int ctas, float *grad_dev,
                   const dfrl_opt_spec *opt) {
   dfrl_ctx *ctx = t->ctx;
+  DFRL_CHECK(ctas <= 8 * RS, "more per-CTA partials than the reduction kernel covers");
   const bool exchange = opt && ctx->nranks > 1;
   reduce_tail tail;
   memset(&tail, 0, sizeof(tail));
@@ -1922,10 +1934,10 @@ int launch_reduce(dfrl_trainer *t, fused_state *f, dfrl_mlp *m, const net3 &net,
     v.nranks = ctx->nranks;
     v.rank = ctx->rank;
     tail.opt = *opt;
-    DFRL_LAUNCH(ctx, fused_reduce_exchange_kernel, ceil_div(net.n_params, 32), 256, 0, (const float *)f->partials, ctas,
+    DFRL_LAUNCH(ctx, fused_reduce_exchange_kernel, ceil_div(net.n_params, 32), 32 * RS, 0, (const float *)f->partials, ctas,
                 net.n_params, grad_dev, v, tail);
   } else {
-    DFRL_LAUNCH(ctx, fused_reduce_partials_kernel, ceil_div(net.n_params, 32), 256, 0, (const float *)f->partials, ctas,
+    DFRL_LAUNCH(ctx, fused_reduce_partials_kernel, ceil_div(net.n_params, 32), 32 * RS, 0, (const float *)f->partials, ctas,
                 net.n_params, dst, tail);
   }
   if (opt)

@@ -426,13 +426,16 @@ def test_trainer_default_path_vs_reference_trace(D, ctx, name):
 
 
 @pytest.mark.parametrize("n,T,ctas", [(512, 4, 0), (200, 4, 0), (96, 8, 0), (70, 5, 0),
-                                      (512, 4, 3), (544, 4, 2), (200, 4, 1), (416, 8, 4), (2048, 4, 5)])
+                                      (512, 4, 3), (544, 4, 2), (200, 4, 1), (416, 8, 4), (2048, 4, 5),
+                                      (300, 1, 2), (150, 16, 2), (60, 32, 1), (40, 128, 0)])
 def test_trainer_vs_oracle_with_uniform_tape(D, ctx, orc, n, T, ctas):
     # ctas > 0: the persistent learner kernels run on that many CTAs only, so that every CTA works
     # through several row tiles per tile pipeline (the steady state of the large configurations):
     # (512, 4, 3) 16 tiles on 3 CTAs; (544, 4, 2) 17 tiles: an odd tile count per CTA, the two
     # pipelines get different numbers of tiles; (200, 4, 1) 7 tiles on one CTA with a ragged last
-    # tile; (416, 8, 4) 16 envs per tile; (2048, 4, 5) 64 tiles, 12-13 per CTA.
+    # tile; (416, 8, 4) 16 envs per tile; (2048, 4, 5) 64 tiles, 12-13 per CTA; (300, 1, 2) single-step
+    # rollouts: 128 envs per learner tile, every row is a last-step row; (150, 16, 2) / (60, 32, 1) 8 / 4
+    # envs per tile; (40, 128, 0) one env per tile, T = the tile height.
     # sampling mode driven by a tape of uniforms: GPU and oracle must pick identical actions.
     # (200, 4): ragged last tiles of the rollout (128 envs) and learner (32 envs) kernels;
     # (96, 8): 16 envs per learner tile; (70, 5): 25 envs per tile, the byte-wise staging path.
@@ -494,7 +497,7 @@ def test_trainer_vs_oracle_with_uniform_tape(D, ctx, orc, n, T, ctas):
         close(tr.read(D.F_POLICY_GRAD_LOG), out["policy_grads"], what="pgrads")
         close(policy.parameters(), lr.pparams, what="pparams")
         close(value.parameters(), lr.vparams, what="vparams")
-    assert done_at_last_step > 0 and done_mid > 0  # both kinds of end rows were exercised
+    assert done_at_last_step > 0 and (done_mid > 0 or T == 1)  # both kinds of end rows were exercised
     s = tr.stats()
     assert s["env_steps"] == 5 * n * T
     assert s["reward_sum"] + s["episodes"] == s["env_steps"]
@@ -615,8 +618,15 @@ def _safe_params(dims, seed, bias=5.0):
     ("ppo", 1200, 4, 32, [128, 64, 64, 32], [128, 64, 64, 1]),
     # online actor-critic on the fused kernels (softmax-CE head: identity backward), T = 8
     ("ac", 300, 8, 8, [32, 64, 64, 8], [32, 64, 64, 1]),
+    # the same on 2 CTAs: 69 learner tiles of 16 envs, 9 rollout tiles -> every tile pipeline of the
+    # rollout (4), GAE (4), critic (2) and policy (2) kernels works through several tiles
+    ("ac@2", 1100, 8, 8, [32, 64, 64, 8], [32, 64, 64, 1]),
+    # 16-wide hidden layers (the second instantiation of the fused kernels: one epilogue thread per
+    # row in the critic step, K = 16 single-chunk TMEM operands), PPO, 3 CTAs
+    ("ppo@3", 700, 4, 8, [32, 16, 16, 8], [32, 16, 16, 1]),
 ])
 def test_trainer_variants_vs_oracle(D, ctx, orc, algo_name, n, T, B, pdims, vdims):
+    algo_name, _, cap = algo_name.partition("@")
     algo, oalgo = (D.PPO, orc.PPO) if algo_name == "ppo" else (D.ACTOR_CRITIC, orc.ACTOR_CRITIC)
     last = D.SOFTMAX if algo_name == "ppo" else D.SOFTMAX_CE
     rng = np.random.default_rng(5)
@@ -632,6 +642,8 @@ def test_trainer_variants_vs_oracle(D, ctx, orc, algo_name, n, T, B, pdims, vdim
     env.set_state(st)
     tr = D.Trainer(ctx, env, policy, value, algo=algo, work=T, policy_lr=2e-8, value_lr=2e-8,
                    action_mode=D.ACT_SAMPLE)
+    if cap:
+        D._lib.check(D._lib.lib.dfrl_debug_set_fused_ctas(tr.h, int(cap)))
     lr = orc.Learner(orc.train_cfg(oalgo, T, policy_lr=2e-8, value_lr=2e-8), ecfg, pnet, pp, vnet, vp)
     for it in range(3):
         items = rng.integers(0, 2, (T, n)).astype(np.uint8)
