@@ -509,7 +509,15 @@ __global__ void __launch_bounds__((pmap<D1, D2>::THREADS), 1) fused_policy_step_
     umma::fence_mbar_init();
   }
   build_policy_image<D0, D1, D2, NOUT>(a.params, net, smem);
-  zero_bytes(smem + PM::DH1_HI, PM::BARS - PM::DH1_HI);
+  // 64-wide layers: every panel byte an MMA reads is written first (epilogues cover all 128 rows x
+  // 64 columns), except columns 32..47 of the XD panels ([1 | 0] for the bias gradients): zeroing
+  // 32 KB instead of 192 KB takes ~0.8 us off every launch
+  if (D1 == 64 && D2 == 64) {
+    zero_bytes(smem + PM::WG0 + PM::XD, PANEL);
+    zero_bytes(smem + PM::WG0 + PM::WG_BYTES + PM::XD, PANEL);
+  } else {
+    zero_bytes(smem + PM::DH1_HI, PM::BARS - PM::DH1_HI);
+  }
   __syncthreads();
   // ones column (col D0) of both XD panels: [dH1|dH2]^T . 1 = bias gradients for free
   if (!issuer && half == 0)
@@ -1025,7 +1033,12 @@ __global__ void __launch_bounds__((cmap<D1, D2, MODE>::THREADS), 1) fused_critic
     if (threadIdx.x == 0)
       fl[CM::F_B3] = P[net.o_b3];
   }
-  zero_bytes(smem + CM::DH1_HI, CM::BARS - CM::DH1_HI);
+  if (MODE == CRITIC_STEP && D1 == 64 && D2 == 64) {  // see fused_policy_step_kernel
+    zero_bytes(smem + CM::WG0 + CM::XS, PANEL);
+    zero_bytes(smem + CM::WG0 + CM::WG_BYTES + CM::XS, PANEL);
+  } else {
+    zero_bytes(smem + CM::DH1_HI, CM::BARS - CM::DH1_HI);
+  }
   __syncthreads();
   if (!issuer && MODE == CRITIC_STEP)  // ones column (col D0) of both XS panels: bias gradients for free
     *reinterpret_cast<uint16_t *>(smem + CM::WG0 + wg * CM::WG_BYTES + CM::XS + umma::panel_off(t.row, D0)) = 0x3F80;
