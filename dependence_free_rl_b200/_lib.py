@@ -66,6 +66,7 @@ PROTOTYPES = {
     "dfrl_umma_selftest": (i32, [vp, i32, i32, i32, C.POINTER(f32)]),
     "dfrl_umma_microbench": (i32, [vp, i32, i32, i32, i32, i32, C.POINTER(C.c_longlong)]),
     "dfrl_debug_policy_clocks": (i32, [vp, vp, i32]),
+    "dfrl_debug_critic_clocks": (i32, [vp, vp, i32]),
     "dfrl_debug_set_fused_ctas": (i32, [vp, i32]),
     "dfrl_p2p_export": (i32, [vp, vp]),
     "dfrl_p2p_attach": (i32, [vp, vp]),

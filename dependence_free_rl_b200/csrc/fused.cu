@@ -198,6 +198,7 @@ struct critic_args {
   float *targets_out;  // [T][n] (critic step) -- introspection + parity
   float *adv_out;      // [T][n] (GAE kernel)
   float *partials;
+  long long *clk;      // optional: phase clocks of CTA 0, pipeline 0 (debug; critic step only)
 };
 
 enum { HEAD_JACOBIAN = 0, HEAD_IDENTITY = 1 };
@@ -967,6 +968,66 @@ __device__ __forceinline__ void end_state(const row_state<B> &start, const row_s
       }
   }
 }
+// Warp-cooperative state prefetch. The 32 rows of a warp need 2B + 2 planes x 32 bytes; with
+// E % 4 == 0 four consecutive rows are four consecutive bytes of a plane, so the warp's state is
+// (2B + 2) x 8 aligned 32-bit words: lane l loads words l, l + 32, ... (5 loads and 5 live registers
+// per thread instead of 18 byte loads / 18 registers), and a row's bytes are gathered with warp
+// shuffles when they are needed (word q * 8 + lane / 4 sits in slot q / 4 of lane (q % 4) * 8 +
+// lane / 4). `tt_fixed` < 0: rec_state planes of each row's own step; otherwise the live planes,
+// meaningful for the rows of step tt_fixed only.
+template <int B>
+struct warp_state {
+  uint32_t w[((2 * B + 2) * 8 + 31) / 32];
+};
+template <int B>
+__device__ __forceinline__ void load_warp_state(const int8_t *__restrict__ base, bool live, const learner_rows &L,
+                                                int tile, int warp_row0, int lane, warp_state<B> &x) {
+  constexpr int P = 2 * B + 2, NW = (P * 8 + 31) / 32;
+#pragma unroll
+  for (int j = 0; j < NW; ++j) {
+    const int w = lane + 32 * j, q = w >> 3, r0 = warp_row0 + 4 * (w & 7);
+    const int tt = r0 / L.E, i0 = tile * L.E + r0 % L.E;
+    x.w[j] = 0;
+    if (q < P && i0 < L.stride && (live ? tt == L.T - 1 : tt < L.T))
+      x.w[j] = *reinterpret_cast<const uint32_t *>(base + ((size_t)(live ? 0 : tt) * P + q) * L.stride + i0);
+  }
+}
+template <int B>
+__device__ __forceinline__ void gather_row_state(const warp_state<B> &x, int lane, bool valid, row_state<B> &out) {
+  constexpr int P = 2 * B + 2;
+#pragma unroll
+  for (int q = 0; q < P; ++q) {
+    const uint32_t word = __shfl_sync(0xffffffffu, x.w[q >> 2], ((q & 3) << 3) + (lane >> 2));
+    out.v[q] = valid ? (int)(int8_t)(word >> (8 * (lane & 3))) : 0;
+  }
+}
+
+// The same from ONE set of loads: a row needs either its start state (done) or the live state
+// (last step, episode not over), never both -- `done` is known when the loads are issued.
+template <int B>
+__device__ __forceinline__ void load_end_source(const learner_rows &L, int tile, int row, int done, row_state<B> &x) {
+  constexpr int P = 2 * B + 2;
+  const int tt = row / L.E, e = row % L.E, i = tile * L.E + e;
+  const bool ok = tt < L.T && i < L.n, from_start = ok && done, from_live = ok && !done && tt == L.T - 1;
+  const int8_t *src = from_start ? L.rec_state + (size_t)tt * P * L.stride + i : L.live_state + i;
+#pragma unroll
+  for (int q = 0; q < P; ++q) {
+    x.v[q] = 0;
+    if (from_start || from_live)
+      x.v[q] = src[(size_t)q * L.stride];
+  }
+}
+template <int B>
+__device__ __forceinline__ void fix_end_state(row_state<B> &x, int done, int act) {
+  if (done) {
+#pragma unroll
+    for (int b = 0; b < B; ++b)
+      if (b == act) {
+        x.v[2 * b] -= x.v[2 * B];
+        x.v[2 * b + 1] -= x.v[2 * B + 1];
+      }
+  }
+}
 // Layer-2 accumulator -> relu(acc + b2) (registers only) -> value head in fp32.
 template <int D2, bool KEEP>
 __device__ __forceinline__ float epi2_value(uint32_t acc, const tid_t &t, const float *__restrict__ b2,
@@ -1053,7 +1114,12 @@ __global__ void __launch_bounds__((cmap<D1, D2, MODE>::THREADS), 1) fused_critic
   uint64_t *bar = bars + wg, *bar_dw2 = bars + NP + wg, *bar_dw1 = bars + 2 * NP + wg, *bar_l1s = bars + 3 * NP + wg,
            *bar_slot = bars + 4 * NP;
   uint32_t rp = 0;
-  constexpr int NDW3 = MODE == CRITIC_STEP ? D2 / NH : 1;  // this thread's columns of dW3
+  // dW3 partial sums. One thread per row: this thread's row-sums of all D2 columns. Two threads per
+  // row: ONE register -- after every tile the 32 lanes of a warp transpose-reduce their 32 columns
+  // (butterfly, fixed order), lane l keeps column 32 half + l summed over the warp's rows (32
+  // accumulators per thread would not fit in the 96 registers of the 576-thread kernel, and spills
+  // go to L2 here: the shared-memory carve-out leaves no L1)
+  constexpr int NDW3 = (MODE == CRITIC_STEP && NH == 1) ? D2 : 1;
   float dw3[NDW3];
 #pragma unroll
   for (int q = 0; q < NDW3; ++q)
@@ -1128,7 +1194,11 @@ __global__ void __launch_bounds__((cmap<D1, D2, MODE>::THREADS), 1) fused_critic
     auto value_of = [&](const float *vp, int r) { return NH == 2 ? (vp[r] + vp[TILE + r]) + b3 : vp[r] + b3; };
     const int h0 = NH == 2 ? half : 0, h1d1 = NH == 2 ? half + 1 : D1 / (D1 < 32 ? D1 : 32),
               h1d2 = NH == 2 ? half + 1 : D2 / (D2 < 32 ? D2 : 32);
-    const bool stager = half == 0;  // observation encodes, state prefetch, target / db3 bookkeeping
+    // two threads per row split the state work: chunk 0's thread prefetches the next START state and
+    // encodes the start-row observations (and keeps the target / db3 books), chunk 1's thread
+    // prefetches the next END state and stages the end-row observations (18 raw bytes in registers
+    // each; with one thread per row the same thread does both)
+    const bool stager = half == 0, xe_role = half == NH - 1;
     constexpr int XT = 128 * NH;    // threads of the value-exchange barrier
     uint32_t phase = 0, phase_dw2 = 0, phase_dw1 = 0, phase_l1s = 0;
     auto wait_mma = [&]() {
@@ -1139,26 +1209,33 @@ __global__ void __launch_bounds__((cmap<D1, D2, MODE>::THREADS), 1) fused_critic
     const int tt = t.row / L.E, e = t.row % L.E;
     const bool last = tt == L.T - 1;
     bool first = true;
-    packed_state<NB> ps;  // start state of this tile's row
+    long long *clk = (MODE == CRITIC_STEP && a.clk && blockIdx.x == 0 && threadIdx.x == 96) ? a.clk : nullptr;
+    int clk_n = 0;
+#define CSTAMP() do { if (clk && clk_n < 112) clk[clk_n++] = clock64(); } while (0)
+    // prefetched state of the rows of this warp (warp_state: 5 words per thread); `fast` = the
+    // word-wise path applies (E % 4 == 0), otherwise byte loads at the point of use
+    const bool fast = L.E % 4 == 0;
+    const int warp_row0 = t.row - t.lane;
+    warp_state<NB> ws;  // start state of this tile (chunk 0's threads)
     int done = 0;
-    {
-      row_state<NB> xs, xl, xe;
+    if (wg < nt) {
+      const int tile0 = blockIdx.x + wg * gridDim.x, i0 = tile0 * L.E + e;
       int act = 0;
-      if (wg < nt) {
-        const int tile0 = blockIdx.x + wg * gridDim.x, i0 = tile0 * L.E + e;
-        if (tt < L.T && i0 < L.n) {
-          done = L.rec_done[(size_t)tt * L.n + i0];
-          act = L.rec_action[(size_t)tt * L.n + i0];
-        }
-        if (stager) {
-          load_row_state<NB>(L, tile0, t.row, xs);
-          load_live_state<NB>(L, tile0, t.row, xl);
-          end_state<NB>(xs, xl, done, act, last, xe);
-          encode_row<NB>(wsm + CM::H1_LO, t.row, xe, L.inv_w, L.inv_h);
-          pack_state<NB>(xs, ps);
-        }
-        ready_arrive(wg, rp, RT);
+      if (tt < L.T && i0 < L.n) {
+        done = L.rec_done[(size_t)tt * L.n + i0];
+        act = L.rec_action[(size_t)tt * L.n + i0];
       }
+      if (xe_role) {
+        row_state<NB> xe;
+        load_end_source<NB>(L, tile0, t.row, done, xe);
+        fix_end_state<NB>(xe, done, act);
+        encode_row<NB>(wsm + CM::H1_LO, t.row, xe, L.inv_w, L.inv_h);
+      }
+      if (stager) {
+        if (fast)
+          load_warp_state<NB>(L.rec_state, false, L, tile0, warp_row0, t.lane, ws);
+      }
+      ready_arrive(wg, rp, RT);
     }
     for (int j = wg; j < nt; j += NP) {
       const int tile = blockIdx.x + j * gridDim.x;
@@ -1172,9 +1249,12 @@ __global__ void __launch_bounds__((cmap<D1, D2, MODE>::THREADS), 1) fused_critic
         for (int q = 0; q < L.T && q < 32; ++q)
           dmask |= (uint32_t)(L.rec_done[(size_t)q * L.n + tile * L.E + t.row] != 0) << q;
       // ---- pass 1: V of the end rows
+      CSTAMP();
       wait_mma();  // layer 1 (end rows): H1 only as a TMEM A operand
+      CSTAMP();
       epi2_fwd<D1, true, false>(tm + C2_ACC0, t, b1, nullptr, nullptr, h0, h1d1);
       ready_arrive(wg, rp, RT);
+      CSTAMP();
       // start-row observations -> XS (the previous tile's dW1 GEMM ran behind the epilogue above)
       if (MODE == CRITIC_STEP && !first) {
         umma::mbar_wait(bar_dw1, phase_dw1);
@@ -1182,47 +1262,56 @@ __global__ void __launch_bounds__((cmap<D1, D2, MODE>::THREADS), 1) fused_critic
       }
       if (stager) {
         row_state<NB> xs;
-        unpack_state<NB>(ps, xs);
+        if (fast)
+          gather_row_state<NB>(ws, t.lane, valid, xs);
+        else
+          load_row_state<NB>(L, tile, t.row, xs);  // step counts with E % 4 != 0: loaded where it is used
         encode_row<NB>(wsm + CM::XS, t.row, xs, L.inv_w, L.inv_h);
       }
       ready_arrive(wg, rp, RT);
+      CSTAMP();
       // the next tile's state: the start-state loads fly behind the layer-2 GEMM of the end rows and
-      // are packed right after it; the live-state loads fly behind the start rows' layer 1 / 2 (raw
-      // bytes cost 18 registers per state)
-      row_state<NB> ns, nl;
+      // are packed right after it; the end-state loads (source chosen by `done`, known by then) fly
+      // behind the start rows' layer 1 / 2
+      warp_state<NB> wn, wes, wel;  // next tile: start words (chunk 0) / start + live words (chunk 1)
       int ndone = 0, nact = 0;
       const int ntile = tile + NP * gridDim.x;
       if (has_next) {
         const int ni = ntile * L.E + e;
-        if (stager)
-          load_row_state<NB>(L, ntile, t.row, ns);
+        if (fast) {
+          if (stager)
+            load_warp_state<NB>(L.rec_state, false, L, ntile, warp_row0, t.lane, wn);
+          if (xe_role) {
+            if (NH == 2)  // (one thread per row: the start words are in wn already)
+              load_warp_state<NB>(L.rec_state, false, L, ntile, warp_row0, t.lane, wes);
+            load_warp_state<NB>(L.live_state, true, L, ntile, warp_row0, t.lane, wel);
+          }
+        }
         if (tt < L.T && ni < L.n) {
           ndone = L.rec_done[(size_t)tt * L.n + ni];
           nact = L.rec_action[(size_t)tt * L.n + ni];
         }
       }
       wait_mma();  // layer 2 (end rows)
-      packed_state<NB> pn, pe;
-      if (has_next && stager) {
-        pack_state<NB>(ns, pn);
-        load_live_state<NB>(L, ntile, t.row, nl);
-      }
+      CSTAMP();
+
       ve[half * TILE + t.row] = epi2_value<D2, false>(tm + C2_ACC1, t, b2, w3, 0.f, nullptr, h0, h1d2);
       // ---- pass 2: start rows, H1 kept for the dW2 GEMM
+      CSTAMP();
       umma::mbar_wait(bar_l1s, phase_l1s);  // layer 1 (start rows)
       phase_l1s ^= 1;
       umma::fence_after_sync();
+      CSTAMP();
       epi2_fwd<D1, true, MODE == CRITIC_STEP>(tm + C2_ACC0, t, b1, wsm + CM::H1_HI, wsm + CM::H1_LO, h0, h1d1);  // panels: dW2
       ready_arrive(wg, rp, RT);
-      if (has_next && stager) {  // the next tile's end state, packed
-        row_state<NB> xs2, xe;
-        unpack_state<NB>(pn, xs2);
-        end_state<NB>(xs2, nl, ndone, nact, last, xe);
-        pack_state<NB>(xe, pe);
-      }
+      CSTAMP();
+
+      CSTAMP();
       wait_mma();  // layer 2 (start rows)
+      CSTAMP();
       vs[half * TILE + t.row] = epi2_value<D2, false>(tm + C2_ACC1, t, b2, w3, 0.f, nullptr, h0, h1d2);
       asm volatile("bar.sync %0, %1;\n" ::"r"(9 + wg), "r"(XT) : "memory");  // ve / vs of the tile visible
+      CSTAMP();
       if (MODE == CRITIC_GAE) {
         // thread e < E walks its env backwards (same recurrence as device_fns.cuh gae_env)
         if (t.row < L.E && i < L.n) {
@@ -1264,6 +1353,7 @@ __global__ void __launch_bounds__((cmap<D1, D2, MODE>::THREADS), 1) fused_critic
 #pragma unroll
           for (int h = h0; h < h1d2; ++h) {
             float y[CH];
+            float contrib[NH == 2 ? CH : 1];  // dY . H2 of this row (NH = 2: reduced over the warp below)
             tmem_load<CH>(tm + C2_ACC1 + t.lane_base + h * CH, y);
 #pragma unroll
             for (int cc = 0; cc < CH / 8; ++cc) {
@@ -1273,8 +1363,10 @@ __global__ void __launch_bounds__((cmap<D1, D2, MODE>::THREADS), 1) fused_critic
                 const int c = h * CH + 8 * cc + q;  // column; dw3 is indexed by the thread's own columns
                 const float yy = fmaxf(y[8 * cc + q] + b2[c], 0.f);
                 g[q] = yy > 0.f ? dy * w3[c] : 0.f;
-                const int lc = NH == 2 ? 8 * cc + q : c;
-                dw3[lc] = fmaf(dy, yy, dw3[lc]);
+                if (NH == 2)
+                  contrib[NH == 2 ? 8 * cc + q : 0] = dy * yy;
+                else
+                  dw3[NH == 2 ? 0 : c] = fmaf(dy, yy, dw3[NH == 2 ? 0 : c]);
               }
               uint4 hh, ll;
               split8<false>(g, hh, ll);
@@ -1283,29 +1375,61 @@ __global__ void __launch_bounds__((cmap<D1, D2, MODE>::THREADS), 1) fused_critic
               *reinterpret_cast<uint4 *>(wsm + CM::G2_LO + off) = ll;
               tmem_put_chunk<CH>(tm + C2_ACC1 + t.lane_base + h * CH, cc, hh, ll);  // A operand of the dH1 GEMM
             }
+            if (NH == 2) {  // transpose-reduce: lane l ends with column l of the chunk, summed over 32 rows
+#pragma unroll
+              for (int sft = CH / 2; sft >= 1; sft >>= 1) {
+                const bool up = (t.lane & sft) != 0;
+#pragma unroll
+                for (int q = 0; q < sft; ++q) {
+                  const float give = up ? contrib[q] : contrib[q + sft];
+                  const float keep = up ? contrib[q + sft] : contrib[q];
+                  contrib[q] = keep + __shfl_xor_sync(0xffffffffu, give, sft);
+                }
+              }
+              dw3[0] += contrib[0];
+            }
           }
           umma::tmem_st_wait();
         }
         ready_arrive(wg, rp, RT);
+        CSTAMP();
         wait_mma();  // dH1
         if (j > 0)   // the shared dH1 slot (see fused_policy_step_kernel)
           umma::mbar_wait(bar_slot, (uint32_t)(j - 1) & 1u);
+        CSTAMP();
         epi2_bwd<D1>(tm + C2_ACC0, t, wsm + CM::H1_HI, smem + CM::DH1_HI, smem + CM::DH1_LO, h0, h1d1);
+        CSTAMP();
         umma::mbar_wait(bar_dw2, phase_dw2);  // H1 is free (the dW2 GEMM ran behind the dH1 epilogue)
         phase_dw2 ^= 1;
       }
       if (has_next) {
-        if (stager) {
+        if (xe_role) {
           row_state<NB> xe;
-          unpack_state<NB>(pe, xe);
+          if (fast) {  // end state of the next tile's row: its start state (done) or the live state (last step)
+            const int ni = ntile * L.E + e;
+            const bool nvalid = tt < L.T && ni < L.n;
+            row_state<NB> xl;
+            gather_row_state<NB>(NH == 2 ? wes : wn, t.lane, nvalid && ndone, xe);
+            gather_row_state<NB>(wel, t.lane, nvalid && !ndone && last, xl);
+#pragma unroll
+            for (int q = 0; q < 2 * NB + 2; ++q)
+              xe.v[q] += xl.v[q];  // at most one of the two is non-zero
+            fix_end_state<NB>(xe, ndone, nact);
+          } else {
+            load_end_source<NB>(L, ntile, t.row, ndone, xe);
+            fix_end_state<NB>(xe, ndone, nact);
+          }
           encode_row<NB>(wsm + CM::H1_LO, t.row, xe, L.inv_w, L.inv_h);
-          ps = pn;
         }
+        if (stager)
+          ws = wn;
         done = ndone;
       }
       ready_arrive(wg, rp, RT);
+      CSTAMP();
       first = false;
     }
+#undef CSTAMP
     if (MODE == CRITIC_STEP && !first) {  // the last tile's dW1 GEMM
       umma::mbar_wait(bar_dw1, phase_dw1);
       umma::fence_after_sync();
@@ -1367,11 +1491,18 @@ __global__ void __launch_bounds__((cmap<D1, D2, MODE>::THREADS), 1) fused_critic
       // are free): red[256 rows][D2 + 1], 4 row quarters per column, combined in order
       float *red = reinterpret_cast<float *>(smem + CM::WG0);
       constexpr int W = D2 + 1;
-      if (!issuer) {  // row = pipeline * 128 + tile row; a thread holds NDW3 columns from half * NDW3
-        const int rr = wg * TILE + t.row;
+      for (int q = threadIdx.x; q < 256 * W; q += blockDim.x)
+        red[q] = 0.f;
+      __syncthreads();
+      if (!issuer) {
+        const int rr = wg * TILE + t.row;  // row = pipeline * 128 + tile row
+        if (NH == 2) {  // lane l of a warp holds column 32 half + l, summed over the warp's rows: row slot rr - l
+          red[(rr - t.lane) * W + half * 32 + t.lane] = dw3[0];
+        } else {
 #pragma unroll
-        for (int q = 0; q < NDW3; ++q)
-          red[rr * W + half * NDW3 + q] = dw3[q];
+          for (int q = 0; q < NDW3; ++q)
+            red[rr * W + q] = dw3[q];
+        }
         if (half == 0)
           red[rr * W + D2] = db3;
       }
@@ -1801,7 +1932,8 @@ struct fused_state {
   float *partials;  // [ctas][max params]
   unsigned *ticket;  // last-block election of the reduction kernel
   int ctas;
-  long long *clk;  // [96] phase clocks of the last policy step (allocated on first request)
+  long long *clk;  // [112] phase clocks of the last policy step (allocated on first request)
+  long long *clk_critic;  // [112] the same for the critic step
 };
 
 // D - R - D - R - D (- softmax / softmax_ce)
@@ -1918,6 +2050,7 @@ critic_args make_critic_args(dfrl_trainer *t, fused_state *f) {
   a.targets_out = t->targets;
   a.adv_out = t->adv;
   a.partials = f->partials;
+  a.clk = f->clk_critic;
   return a;
 }
 
@@ -2015,6 +2148,7 @@ void dfrl_fused_detach(dfrl_trainer *t) {
   if (f) {
     cudaFree(f->partials);
     cudaFree(f->clk);
+    cudaFree(f->clk_critic);
     cudaFree(f->ticket);
     delete f;
   }
@@ -2042,6 +2176,20 @@ extern "C" int dfrl_debug_policy_clocks(dfrl_trainer *t, long long *out_host, in
     DFRL_CUDA(cudaMemsetAsync(f->clk, 0, sizeof(long long) * 112, t->ctx->stream));
   }
   DFRL_CUDA(cudaMemcpyAsync(out_host, f->clk, sizeof(long long) * n, cudaMemcpyDeviceToHost, t->ctx->stream));
+  DFRL_CUDA(cudaStreamSynchronize(t->ctx->stream));
+  return DFRL_OK;
+}
+
+// The same for the critic step (pipeline 0 of CTA 0): 15 stamps per tile, first 7 tiles.
+extern "C" int dfrl_debug_critic_clocks(dfrl_trainer *t, long long *out_host, int n) {
+  DFRL_CHECK(t && out_host && n > 0 && n <= 112, "bad argument");
+  fused_state *f = (fused_state *)t->fused_impl;
+  DFRL_CHECK(f, "fused path not attached");
+  if (!f->clk_critic) {
+    DFRL_CUDA(cudaMalloc(&f->clk_critic, sizeof(long long) * 112));
+    DFRL_CUDA(cudaMemsetAsync(f->clk_critic, 0, sizeof(long long) * 112, t->ctx->stream));
+  }
+  DFRL_CUDA(cudaMemcpyAsync(out_host, f->clk_critic, sizeof(long long) * n, cudaMemcpyDeviceToHost, t->ctx->stream));
   DFRL_CUDA(cudaStreamSynchronize(t->ctx->stream));
   return DFRL_OK;
 }

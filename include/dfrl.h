@@ -385,6 +385,8 @@ int dfrl_trainer_stats_end(dfrl_trainer *tr, dfrl_trainer_stats *out);
  * loop-end / exit stamps at 104..107 (n <= 112). The first call arms
  * the instrumentation and returns zeros; later calls return the stamps of the last launch. */
 int dfrl_debug_policy_clocks(dfrl_trainer *tr, long long *out_host, int n);
+/* The same for the fused critic-step kernel: 15 stamps per row tile, first 7 tiles (n <= 112). */
+int dfrl_debug_critic_clocks(dfrl_trainer *tr, long long *out_host, int n);
 /* Test hook (no reference counterpart): caps the number of persistent CTAs of the fused learner
  * kernels, so that a small problem runs many row tiles per CTA (the steady state of the two tile
  * pipelines). ctas <= 0 restores one CTA per SM. Results do not depend on the grid size beyond the
