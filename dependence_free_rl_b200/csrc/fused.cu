@@ -141,6 +141,32 @@ __device__ __forceinline__ void sync_after_smem_writes() {
   umma::fence_after_sync();
 }
 
+// The flat fp32 parameter vector (<= 32 KB) -> shared-memory scratch with ONE bulk copy
+// (cp.async.bulk, completion on an mbarrier): the panel staging below then reads shared memory
+// instead of paying an L2 round trip per staging loop at every launch. Whole CTA; returns the
+// scratch pointer; contains __syncthreads.
+__device__ __forceinline__ const float *stage_params_bulk(const float *__restrict__ params, int n, uint8_t *scratch,
+                                                          uint64_t *pbar) {
+  float *dst = reinterpret_cast<float *>(scratch);
+  const bool aligned = (reinterpret_cast<uintptr_t>(params) & 15) == 0;
+  const uint32_t bytes = aligned ? ((uint32_t)n * 4u) & ~15u : 0u;
+  if (threadIdx.x == 0) {
+    umma::mbar_init(pbar, 1);
+    umma::fence_mbar_init();
+    if (bytes) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(umma::smem_u32(pbar)), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                       umma::smem_u32(dst)), "l"(params), "r"(bytes), "r"(umma::smem_u32(pbar)) : "memory");
+    }
+  }
+  for (int i = (int)(bytes / 4) + threadIdx.x; i < n; i += blockDim.x)  // tail (or everything if misaligned)
+    dst[i] = params[i];
+  __syncthreads();  // the mbarrier is initialised (and the tail is visible) for every thread
+  if (bytes)
+    umma::mbar_wait(pbar, 0);
+  return dst;
+}
+
 // fp32 [N][K] row-major -> forward-format hi / lo panels [rows_alloc][64] of (scale * W), zero padded.
 __device__ void stage_weight_f16(const float *__restrict__ W, int N, int K, int rows_alloc, float scale,
                                  uint8_t *hi, uint8_t *lo) {
@@ -149,7 +175,7 @@ __device__ void stage_weight_f16(const float *__restrict__ W, int N, int K, int 
     float x[8];
     const float *src = W + (size_t)row * K + chunk * 8;
     if (row < N && chunk * 8 + 8 <= K && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-      float4 a = __ldg(reinterpret_cast<const float4 *>(src)), b = __ldg(reinterpret_cast<const float4 *>(src) + 1);
+      float4 a = *reinterpret_cast<const float4 *>(src), b = *(reinterpret_cast<const float4 *>(src) + 1);
       x[0] = a.x * scale, x[1] = a.y * scale, x[2] = a.z * scale, x[3] = a.w * scale;
       x[4] = b.x * scale, x[5] = b.y * scale, x[6] = b.z * scale, x[7] = b.w * scale;
     } else {
@@ -248,7 +274,7 @@ struct pmap {
   static constexpr uint32_t XD = 0, H1_HI = PANEL, H1_LO = 2 * PANEL, H2_HI = 3 * PANEL, H2_LO = 4 * PANEL;
   static constexpr uint32_t WG_BYTES = 5 * PANEL;
   static constexpr uint32_t BARS = WG0 + 2 * WG_BYTES;
-  static constexpr uint32_t TOTAL = BARS + 64;
+  static constexpr uint32_t TOTAL = BARS + 128;
   static constexpr uint32_t DY_OFF = 96;  // byte offset of [dY_hi | dY_lo] in a row of the XD panel
   // Epilogue threads per row. Two (one 32-column chunk each, 576 threads) were measured SLOWER here:
   // 103 us vs 95.5 us per launch -- unlike the critic step, this kernel is bound by shared-memory
@@ -270,7 +296,7 @@ __device__ void stage_w1_packed(const float *__restrict__ W1, uint8_t *panel) {
     float x[8];
     const float4 *src = reinterpret_cast<const float4 *>(W1 + (size_t)row * D0 + chunk * 8);
     if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-      float4 p = __ldg(src), q = __ldg(src + 1);
+      float4 p = *src, q = *(src + 1);
       x[0] = p.x, x[1] = p.y, x[2] = p.z, x[3] = p.w, x[4] = q.x, x[5] = q.y, x[6] = q.z, x[7] = q.w;
     } else {
 #pragma unroll
@@ -509,7 +535,9 @@ __global__ void __launch_bounds__((pmap<D1, D2>::THREADS), 1) fused_policy_step_
       umma::mbar_init(bars + q, 1);
     umma::fence_mbar_init();
   }
-  build_policy_image<D0, D1, D2, NOUT>(a.params, net, smem);
+  build_policy_image<D0, D1, D2, NOUT>(
+      stage_params_bulk(a.params, net.n_params, smem + PM::WG0 + PM::H1_HI, bars + 8), net, smem);
+  __syncthreads();  // the scratch (pipeline 0's H1 panels) is free again
   // 64-wide layers: every panel byte an MMA reads is written first (epilogues cover all 128 rows x
   // 64 columns), except columns 32..47 of the XD panels ([1 | 0] for the bias gradients): zeroing
   // 32 KB instead of 192 KB takes ~0.8 us off every launch
@@ -1085,7 +1113,8 @@ __global__ void __launch_bounds__((cmap<D1, D2, MODE>::THREADS), 1) fused_critic
     umma::fence_mbar_init();
   }
   {
-    const float *P = a.params;
+    const float *P = stage_params_bulk(a.params, net.n_params, smem + CM::WG0 + (MODE == CRITIC_STEP ? PANEL : 0),
+                                       bars + 29);
     stage_w1_packed<D1>(P + net.o_w1, smem + CM::W1P);
     stage_weight_f16(P + net.o_w2, D2, D1, D2, 1.f, smem + CM::W2_HI, smem + CM::W2_LO);
     for (int i = threadIdx.x; i < D1; i += blockDim.x) fl[CM::F_B1 + i] = P[net.o_b1 + i];
@@ -1093,6 +1122,7 @@ __global__ void __launch_bounds__((cmap<D1, D2, MODE>::THREADS), 1) fused_critic
     for (int i = threadIdx.x; i < 64; i += blockDim.x) fl[CM::F_W3 + i] = i < D2 ? P[net.o_w3 + i] : 0.f;
     if (threadIdx.x == 0)
       fl[CM::F_B3] = P[net.o_b3];
+    __syncthreads();  // the scratch (activation panels) is free again
   }
   if (MODE == CRITIC_STEP && D1 == 64 && D2 == 64) {  // see fused_policy_step_kernel
     zero_bytes(smem + CM::WG0 + CM::XS, PANEL);
@@ -1723,7 +1753,7 @@ __global__ void __launch_bounds__(160 * NP, 1) fused_rollout_kernel(rollout_args
     umma::fence_mbar_init();
   }
   {
-    const float *Pm = a.params;
+    const float *Pm = stage_params_bulk(a.params, net.n_params, smem + RM::WG0, bars + 5);
     const float *W3 = Pm + net.o_w3;
     stage_w1_packed<D1>(Pm + net.o_w1, smem + RM::W1P);
     stage_weight_f16(Pm + net.o_w2, D2, D1, D2, 1.f, smem + RM::W2_HI, smem + RM::W2_LO);
@@ -1744,6 +1774,7 @@ __global__ void __launch_bounds__(160 * NP, 1) fused_rollout_kernel(rollout_args
     for (int i = threadIdx.x; i < D2; i += blockDim.x) fl[RM::F_B2 + i] = Pm[net.o_b2 + i];
     for (int i = threadIdx.x; i < 16; i += blockDim.x) fl[RM::F_B3 + i] = i < net.d3 ? Pm[net.o_b3 + i] : 0.f;
   }
+  __syncthreads();  // the scratch (observation panels) is free again
   zero_bytes(smem + RM::WG0, RM::BARS - RM::WG0);
   sync_after_smem_writes();
   const uint32_t tmem = *tmem_slot;
