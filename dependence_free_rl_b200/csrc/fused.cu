@@ -2092,6 +2092,16 @@ int launch_reduce(dfrl_trainer *t, fused_state *f, dfrl_mlp *m, const net3 &net,
                   const dfrl_opt_spec *opt) {
   dfrl_ctx *ctx = t->ctx;
   DFRL_CHECK(ctas <= 8 * RS, "more per-CTA partials than the reduction kernel covers");
+  // The reduction kernels run between kernels that use the whole shared-memory carve-out: ask for
+  // the same carve-out so that the SMs are not reconfigured (drained) at every kernel boundary.
+  static bool carveout = false;
+  if (!carveout) {
+    DFRL_CUDA(cudaFuncSetAttribute(fused_reduce_partials_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                   cudaSharedmemCarveoutMaxShared));
+    DFRL_CUDA(cudaFuncSetAttribute(fused_reduce_exchange_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                   cudaSharedmemCarveoutMaxShared));
+    carveout = true;
+  }
   const bool exchange = opt && ctx->nranks > 1;
   reduce_tail tail;
   memset(&tail, 0, sizeof(tail));
