@@ -943,66 +943,13 @@ struct cmap {
 };
 constexpr uint32_t C2_ACC0 = 0, C2_ACC1 = 64, C2_DA = 128, C2_DB = 192;  // TMEM columns of a pipeline
 
-// 2B + 2 int8 planes, four per register
-template <int B>
-struct packed_state {
-  uint32_t w[(2 * B + 2 + 3) / 4];
-};
-template <int B>
-__device__ __forceinline__ void pack_state(const row_state<B> &x, packed_state<B> &p) {
-#pragma unroll
-  for (int q4 = 0; q4 < (2 * B + 2 + 3) / 4; ++q4) {
-    uint32_t w = 0;
-#pragma unroll
-    for (int q = 4 * q4; q < 4 * q4 + 4 && q < 2 * B + 2; ++q)
-      w |= ((uint32_t)x.v[q] & 0xffu) << (8 * (q & 3));
-    p.w[q4] = w;
-  }
-}
-template <int B>
-__device__ __forceinline__ void unpack_state(const packed_state<B> &p, row_state<B> &x) {
-#pragma unroll
-  for (int q = 0; q < 2 * B + 2; ++q)
-    x.v[q] = (int)(int8_t)(p.w[q >> 2] >> (8 * (q & 3)));
-}
-// live env state of a row of the rollout's last step (its end state unless the episode ended)
-template <int B>
-__device__ __forceinline__ void load_live_state(const learner_rows &L, int tile, int row, row_state<B> &x) {
-  constexpr int P = 2 * B + 2;
-  const int tt = row / L.E, e = row % L.E, i = tile * L.E + e;
-  const bool ok = tt == L.T - 1 && i < L.n;
-  const int8_t *src = L.live_state + i;
-#pragma unroll
-  for (int q = 0; q < P; ++q) {
-    x.v[q] = 0;
-    if (ok)
-      x.v[q] = src[(size_t)q * L.stride];
-  }
-}
-// END state of a row: overflowed terminal state when done (bin[a] -= item, item kept:
-// bin_packing.h:54-61), the live state at the rollout's last step, zeros (row unused) otherwise.
-template <int B>
-__device__ __forceinline__ void end_state(const row_state<B> &start, const row_state<B> &live, int done, int act,
-                                          bool last, row_state<B> &out) {
-#pragma unroll
-  for (int q = 0; q < 2 * B + 2; ++q)
-    out.v[q] = done ? start.v[q] : (last ? live.v[q] : 0);
-  if (done) {
-#pragma unroll
-    for (int b = 0; b < B; ++b)
-      if (b == act) {
-        out.v[2 * b] -= start.v[2 * B];
-        out.v[2 * b + 1] -= start.v[2 * B + 1];
-      }
-  }
-}
 // Warp-cooperative state prefetch. The 32 rows of a warp need 2B + 2 planes x 32 bytes; with
 // E % 4 == 0 four consecutive rows are four consecutive bytes of a plane, so the warp's state is
 // (2B + 2) x 8 aligned 32-bit words: lane l loads words l, l + 32, ... (5 loads and 5 live registers
 // per thread instead of 18 byte loads / 18 registers), and a row's bytes are gathered with warp
 // shuffles when they are needed (word q * 8 + lane / 4 sits in slot q / 4 of lane (q % 4) * 8 +
-// lane / 4). `tt_fixed` < 0: rec_state planes of each row's own step; otherwise the live planes,
-// meaningful for the rows of step tt_fixed only.
+// lane / 4). live = false: rec_state planes of each row's own step; live = true: the environments'
+// live planes, meaningful for the rows of the rollout's last step only.
 template <int B>
 struct warp_state {
   uint32_t w[((2 * B + 2) * 8 + 31) / 32];
@@ -1030,8 +977,10 @@ __device__ __forceinline__ void gather_row_state(const warp_state<B> &x, int lan
   }
 }
 
-// The same from ONE set of loads: a row needs either its start state (done) or the live state
-// (last step, episode not over), never both -- `done` is known when the loads are issued.
+// Byte-wise path (first tile of a pipeline, step counts with E % 4 != 0). END state of a row:
+// overflowed terminal state when done (bin[a] -= item, item kept: bin_packing.h:54-61), the live
+// state at the rollout's last step, zeros (row unused) otherwise. A row needs either its start state
+// (done) or the live state, never both -- `done` is known when the loads are issued.
 template <int B>
 __device__ __forceinline__ void load_end_source(const learner_rows &L, int tile, int row, int done, row_state<B> &x) {
   constexpr int P = 2 * B + 2;
