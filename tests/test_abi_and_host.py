@@ -83,3 +83,34 @@ def test_reference_arm_prints_contract_line():
     assert d["impl"] == "reference" and d["unit"] == "env-steps/s" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def _fused_object():
+    return os.path.join(ROOT, "dependence_free_rl_b200", "csrc", ".out", "fused.o")
+
+
+@pytest.mark.skipif(not os.path.exists(_fused_object()), reason="library built elsewhere (no object files)")
+def test_fused_kernels_are_tcgen05_code():
+    """SASS of the fused kernels (cross-compiled here, no GPU needed): tensor-core MMAs with operands
+    in shared AND tensor memory, TMEM loads / stores, mbarrier completion, the bulk copy of the
+    parameter vector -- and no wgmma / mma.sync fallback."""
+    sass = subprocess.run(["cuobjdump", "-sass", _fused_object()], capture_output=True, text=True, check=True).stdout
+    for mnemonic in ["UTCHMMA", "LDTM", "STTM", "UTCBAR", "SYNCS.PHASECHK", "UBLKCP"]:
+        assert mnemonic in sass, mnemonic
+    assert "HMMA.16816" not in sass and "HGMMA" not in sass
+    # tcgen05.mma with the A operand in tensor memory ("tmem[" as a source operand of UTCHMMA)
+    assert re.search(r"UTCHMMA\s+tmem\[", sass), "no tcgen05.mma with a TMEM A operand"
+
+
+@pytest.mark.skipif(not os.path.exists(_fused_object().replace("fused.o", "fused.ptxas.log")),
+                    reason="no ptxas log (library built elsewhere)")
+def test_fused_kernels_do_not_spill():
+    """The fused kernels run with the whole shared-memory carve-out, i.e. without an L1: a register
+    spill costs an L2 round trip (the critic step lost 20 % to 136 spilled words). Guard: at most
+    16 bytes of spill stores per kernel."""
+    log = open(_fused_object().replace("fused.o", "fused.ptxas.log")).read()
+    entries = re.findall(r"Function properties for (\S+)\n\s+(\d+) bytes stack frame, (\d+) bytes spill stores", log)
+    fused = [(n, int(st)) for n, _, st in entries if "fused_" in n and "reduce" not in n]
+    assert len(fused) >= 8
+    for name, spill in fused:
+        assert spill <= 16, (name, spill)
