@@ -386,7 +386,8 @@ def run_ours(args):
     dist = None
     nccl_id = None
     if world > 1:
-        os.environ.pop("NCCL_DEBUG", None)  # keep NCCL's version banner off stdout: ONE JSON line only
+        # NCCL_DEBUG output (the driver counts ranks from it) goes to stderr: stdout carries ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist_mod
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist_mod.init_process_group("gloo", rank=rank, world_size=world)
@@ -403,7 +404,8 @@ def run_ours(args):
             handles = [None] * world
             dist.all_gather_object(handles, ctx.p2p_export())
             ctx.p2p_attach(handles)
-            exchange = "peer-memory pull over NVLink fused with the optimizer (one kernel per update)"
+            exchange = ("peer-memory PUSH over NVLink (flag-in-data 8-byte stores into every peer's buffer) fused with "
+                        "the gradient reduction and the optimizer: one kernel per update, no NCCL call on the data path")
     peaks = load_peaks()
 
     main = measure(D, ctx, dist, args, args.envs_per_gpu, world, rank, args.steps, args.warmup, True)

@@ -688,6 +688,12 @@ static int learn_graphed(dfrl_trainer *t) {
   }
   DFRL_CUDA(cudaGraphLaunch((cudaGraphExec_t)t->graph_exec, ctx->stream));
   ctx->launches += t->graph_launches;
+  // the replay changed the parameters of both nets on the device: the host-side bookkeeping that
+  // apply_opt / launch_reduce do launch by launch (transposed-weight cache of the layered kernels)
+  // has to be repeated here, otherwise dfrl_mlp_eval / dfrl_eval_argmax keep using stale weights
+  t->policy->wt_dirty = true, t->policy->version++;
+  if (t->value)
+    t->value->wt_dirty = true, t->value->version++;
   return DFRL_OK;
 }
 

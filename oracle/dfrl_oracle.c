@@ -196,6 +196,11 @@ int orc_heuristic_react(const orc_env_cfg *c, const int8_t *state, int stride, i
  * matmul_transposed = dot of rows (tensor.cc:218-227). */
 void orc_dense_forward(const float *params, int in, int out, const float *x, int rows, float *y) {
   const float *W = params, *b = params + (size_t)in * out;
+  /* rows are independent: the OpenMP build (liboracle64mt.so, large-N yardstick) gives the same
+   * bits for any thread count */
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
   for (int r = 0; r < rows; ++r)
     for (int o = 0; o < out; ++o) {
       acc_t s = 0;
@@ -207,6 +212,9 @@ void orc_dense_forward(const float *params, int in, int out, const float *x, int
 /* matmul_layer::backward (nn.h:81-83): matmul(backprop, a_) = backprop . W. */
 void orc_dense_backward(const float *params, int in, int out, const float *dy, int rows, float *dx) {
   const float *W = params;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
   for (int r = 0; r < rows; ++r)
     for (int k = 0; k < in; ++k) {
       acc_t s = 0;
@@ -216,20 +224,28 @@ void orc_dense_backward(const float *params, int in, int out, const float *dy, i
     }
 }
 /* matmul_layer::gradient (nn.h:85-100): d_a = transpose(backprop) . input (SUM over rows),
- * d_b = sum of backprop rows. */
+ * d_b = sum of backprop rows. Every entry is accumulated over the rows in ascending order; the
+ * row loop is the outer one (cache friendly at large N) and the OpenMP build splits the OUTPUT
+ * index over threads, so the order of additions per entry -- and therefore every bit of the
+ * result -- does not depend on the loop nest or the thread count. */
 void orc_dense_gradient(int in, int out, const float *x, const float *dy, int rows, float *grad) {
+  acc_t *acc = (acc_t *)calloc((size_t)(in + 1) * out, sizeof(acc_t));
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
   for (int o = 0; o < out; ++o) {
-    for (int k = 0; k < in; ++k) {
-      acc_t s = 0;
-      for (int r = 0; r < rows; ++r)
-        s += (acc_t)dy[(size_t)r * out + o] * x[(size_t)r * in + k];
-      grad[(size_t)o * in + k] = (float)s;
+    acc_t *a = acc + (size_t)o * in, *ab = acc + (size_t)in * out + o;
+    for (int r = 0; r < rows; ++r) {
+      const float d = dy[(size_t)r * out + o];
+      const float *xr = x + (size_t)r * in;
+      for (int k = 0; k < in; ++k)
+        a[k] += (acc_t)d * xr[k];
+      *ab += d;
     }
-    acc_t sb = 0;
-    for (int r = 0; r < rows; ++r)
-      sb += dy[(size_t)r * out + o];
-    grad[(size_t)in * out + o] = (float)sb;
   }
+  for (size_t i = 0; i < (size_t)(in + 1) * out; ++i)
+    grad[i] = (float)acc[i];
+  free(acc);
 }
 /* relu_activation::forward / backward (nn.h:354-376): mask by PRE-activation > 0. */
 void orc_relu_forward(const float *x, size_t n, float *y) {

@@ -50,7 +50,9 @@ _libs = {}
 
 
 def lib(f64=False):
-    key = "64" if f64 else ""
+    """f64: False = float accumulators (the reference's), True = double accumulators,
+    "mt" = double accumulators + OpenMP over rows / outputs (same bits as True, any thread count)."""
+    key = "64mt" if f64 == "mt" else "64" if f64 else ""
     if key not in _libs:
         build()
         l = C.CDLL(os.path.join(_HERE, f"liboracle{key}.so"))

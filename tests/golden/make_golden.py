@@ -122,10 +122,15 @@ def units():
 
 
 def main():
+    """No arguments: regenerate everything. With arguments: only the named trainer cases."""
     os.makedirs(refcases.GOLDEN_DIR, exist_ok=True)
-    np.savez_compressed(os.path.join(refcases.GOLDEN_DIR, "units.npz"), **units())
-    print("units.npz written")
+    only = set(sys.argv[1:])
+    if not only:
+        np.savez_compressed(os.path.join(refcases.GOLDEN_DIR, "units.npz"), **units())
+        print("units.npz written")
     for c in refcases._cases():
+        if only and c["name"] not in only:
+            continue
         arrs = refcases.generate_case(c)
         path = os.path.join(refcases.GOLDEN_DIR, f"train_{c['name']}.npz")
         np.savez_compressed(path, **arrs)

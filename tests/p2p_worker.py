@@ -29,7 +29,7 @@ def run(ctx, rank, world, n, iters):
 
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    os.environ.pop("NCCL_DEBUG", None)
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout for the result line
     dist.init_process_group("gloo", rank=rank, world_size=world)
     obj = [D.Context.nccl_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(obj, src=0)

@@ -152,6 +152,11 @@ def _cases():
         dict(name="ppo_adam_small", algo=R.PPO, seed=51, n_envs=4, work=4, iters=3,
              policy=fc([32, 16, 8], R.SOFTMAX), value=fc([32, 16, 1]),
              plr=1e-3, vlr=1e-3, popt=R.ADAM, vopt=R.MOMENTUM),
+        # the fused C2 / C4 nets at a size where every fused kernel runs several row tiles, three
+        # iterations with the reference's initialisation and its rates scaled to SUMS over 1024 rows
+        dict(name="ppo_c2net_256", algo=R.PPO, seed=71, n_envs=256, work=4, iters=3,
+             policy=fc([32, 64, 64, 8], R.SOFTMAX), value=fc([32, 64, 64, 1]),
+             plr=1e-4 * 32 / 1024, vlr=1e-5 * 32 / 1024),
         # long enough for several episode ends inside rollouts (random-ish policy: ~12 steps)
         dict(name="ppo_long", algo=R.PPO, seed=61, n_envs=4, work=16, iters=2,
              policy=fc([32, 8, 8], R.SOFTMAX), value=fc([32, 8, 1]), plr=1e-4, vlr=1e-4),
@@ -194,7 +199,7 @@ def load_case(name):
 
 def case_names():
     return ["ppo_small", "ppo_c2net", "ppo_refnet_conv", "ac_conv_small", "reinforce_small",
-            "klppo_small", "ppo_adam_small", "ppo_long"]
+            "klppo_small", "ppo_adam_small", "ppo_long", "ppo_c2net_256"]
 
 
 def orc_net_from_layers(layers, B=NB):

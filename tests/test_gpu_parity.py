@@ -403,7 +403,25 @@ def _run_case(D, ctx, name, fused):
             vg_i += 1
         log = tr.read(D.F_POLICY_GRAD_LOG)
         for e in range(epochs):
-            close(log[e], c["policy_grads"][pg_i], what=f"{name} it{it} policy grad {e}")
+            try:
+                close(log[e], c["policy_grads"][pg_i], what=f"{name} it{it} policy grad {e}")
+            except AssertionError:
+                # reference initialisation at >= 1024 rows: a relu pre-activation closer to zero than
+                # two fp32 summation orders agree on may flip (tests/flipcheck.py); only the fused
+                # 3-dense-layer PPO nets are large enough for that to happen
+                dims = [int(l[1]) for l in c["policy_layers"] if l[0] == D.DENSE] + [8]
+                if algo != D.PPO or len(dims) != 4 or n * L < 1024:
+                    raise
+                import flipcheck
+                from oracle import orc
+                before = c["pparams0"] if pg_i == 0 else c["policy_params_log"][pg_i - 1]
+                obs = orc.obs_encode(rec["rec_state"].transpose(1, 0, 2).reshape(18, L * n), 8)
+                acts = rec["action"].reshape(-1).astype(np.int64)
+                advs = adv_ref.reshape(-1).astype(np.float64)
+                poa = rec["p_old"].reshape(-1, 8)[np.arange(L * n), acts].astype(np.float64)
+                Dm, _ = flipcheck.ambiguous_directions(
+                    obs, before, dims, lambda rows, o: flipcheck.policy_dlogits(o, acts[rows], advs[rows], poa[rows], flipcheck.PPO))
+                flipcheck.flip_close(log[e], c["policy_grads"][pg_i], Dm, what=f"{name} it{it} policy grad {e}")
             pg_i += 1
         close(policy.parameters(), c["policy_params_log"][pg_i - 1], what=f"{name} it{it} policy params")
     close(policy.parameters(), c["pparams_final"], what="final policy params")

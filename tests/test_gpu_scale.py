@@ -1,0 +1,174 @@
+"""GPU parity at the BASELINE sizes (-m gpu): the fused tcgen05 path through the C ABI against the
+double-accumulating oracle (oracle/liboracle64mt.so = dfrl_oracle.c, -DORC_ACC_DOUBLE, OpenMP over
+rows / outputs, bit-identical to the single-threaded build) with the REFERENCE'S initialisation
+(dfrl_mlp_init_params = N(0, 0.01) weights, zero biases, nn.h:12-14) -- no 'safe' parameters.
+
+  configs[1]  PPO, 4 096 envs x 4 steps, 3 iterations
+  configs[3]  PPO, 131 072 envs x 4 steps (the per-GPU shard of 1 M envs), 1 iteration
+  configs[2]  online actor-critic, 65 536 envs x 8 steps, 1 iteration
+
+Bars: rollout records, sampled actions, done flags, env state bit-exact; probabilities,
+advantages, targets, value gradient, parameters within 1e-4 (refcases.close, elementwise against
+the vector's magnitude + norm-wise); policy gradients within 1e-4 after removing the
+relu-ambiguous directions (tests/flipcheck.py explains why a noise-like gradient over 5 x 10^5
+rows needs that, and why it cannot hide a wrong kernel)."""
+import numpy as np
+import pytest
+
+import flipcheck
+from refcases import close
+
+pytestmark = pytest.mark.gpu
+
+PD, VD = [32, 64, 64, 8], [32, 64, 64, 1]
+
+
+def _setup(D, ctx, orc, n, T, algo, seed):
+    B = 8
+    last = D.SOFTMAX if algo == "ppo" else D.SOFTMAX_CE
+    pl, vl = D.fc_layers(PD, last), D.fc_layers(VD)
+    pnet, vnet = orc.Net(pl, 32), orc.Net(vl, 32)
+    policy, value = D.Model(ctx, pl, 32), D.Model(ctx, vl, 32)
+    policy.init_parameters(seed)
+    value.init_parameters(seed + 1)
+    pp, vp = policy.parameters(), value.parameters()
+    assert abs(pp[:32 * 64].std() - 0.01) < 1e-3 and np.all(pp[32 * 64:32 * 64 + 64] == 0)  # reference init
+    rng = np.random.default_rng(seed + 2)
+    ecfg = orc.env_cfg(B)
+    st = orc.env_reset_all(ecfg, n, rng.integers(0, 2, n).astype(np.uint8))
+    for _ in range(6):  # spread the environments over their episodes
+        orc.env_step(ecfg, st, rng.integers(0, B, n).astype(np.uint8), rng.integers(0, 2, n).astype(np.uint8))
+    env = D.Environment(ctx, n)
+    env.set_state(st)
+    plr, vlr = 1e-4 * 32 / (n * T), 1e-5 * 32 / (n * T)  # reference rates for SUM gradients over 32 rows
+    dalgo, oalgo = (D.PPO, orc.PPO) if algo == "ppo" else (D.ACTOR_CRITIC, orc.ACTOR_CRITIC)
+    tr = D.Trainer(ctx, env, policy, value, algo=dalgo, work=T, policy_lr=plr, value_lr=vlr)
+    lr = orc.Learner(orc.train_cfg(oalgo, T, policy_lr=plr, value_lr=vlr), ecfg, pnet, pp, vnet, vp, f64="mt")
+    return dict(policy=policy, value=value, env=env, tr=tr, lr=lr, st=st, ecfg=ecfg, pnet=pnet, rng=rng, plr=plr)
+
+
+def _iteration(D, orc, S, n, T, algo, it):
+    tr, lr, st, rng = S["tr"], S["lr"], S["st"], S["rng"]
+    items = rng.integers(0, 2, (T, n)).astype(np.uint8)
+    st0 = st.copy()
+    pp0 = lr.pparams.copy()
+
+    def oracle_rollout(u):
+        s = st0.copy()
+        ro = orc.rollout(S["ecfg"], s, S["pnet"], pp0, T, 0, items, u=u)
+        ro["final"] = s
+        return ro
+    ro, u = flipcheck.nudge_uniforms(oracle_rollout, rng.random((T, n)), lambda r: r["probs"], rng)
+    st[:] = ro["final"]
+    tr.rollout(items=items, u=u)
+    # ---- transitions: bit-exact
+    assert np.array_equal(tr.read(D.F_REC_ACTION), ro["action"]), f"it {it}: sampled actions differ"
+    assert np.array_equal(tr.read(D.F_REC_DONE), ro["done"]), f"it {it}: done flags differ"
+    assert np.array_equal(tr.read(D.F_REC_STATE), ro["state"]), f"it {it}: recorded states differ"
+    assert np.array_equal(S["env"].state(), st), f"it {it}: live env state differs"
+    close(tr.read(D.F_REC_PROBS), ro["probs"], what=f"it {it} p_old")
+    # ---- learn
+    out = lr.learn(ro["state"], st, ro["action"], ro["done"], ro["probs"])
+    tr.learn()
+    close(tr.read(D.F_ADVANTAGE), out["adv"], what=f"it {it} advantages")
+    close(tr.read(D.F_VALUE_TARGET), out["targets"], what=f"it {it} targets")
+    close(tr.read(D.F_VALUE_GRAD), out["value_grad"], what=f"it {it} value gradient")
+    # ---- policy gradients, epoch by epoch, flip-aware
+    obs = orc.obs_encode(ro["state"].transpose(1, 0, 2).reshape(18, T * n), 8)   # row k = t * n + i
+    actions = ro["action"].reshape(-1).astype(np.int64)
+    adv = out["adv"].reshape(-1).astype(np.float64)
+    p_old_a = ro["probs"].reshape(-1, 8)[np.arange(T * n), actions].astype(np.float64)
+    log = tr.read(D.F_POLICY_GRAD_LOG)
+    params = pp0.copy()
+    reports = []
+    for e in range(log.shape[0]):
+        def dout(rows, o):
+            return flipcheck.policy_dlogits(o, actions[rows], adv[rows], p_old_a[rows], algo)
+        Dm, cand = flipcheck.ambiguous_directions(obs, params, PD, dout)
+        reports.append(flipcheck.flip_close(log[e], out["policy_grads"][e], Dm, what=f"it {it} policy gradient {e}"))
+        params = (params - out["policy_grads"][e] * np.float32(S["plr"])).astype(np.float32)  # sgd, nn.h:622-625
+    close(S["policy"].parameters(), lr.pparams, what=f"it {it} policy params")
+    close(S["value"].parameters(), lr.vparams, what=f"it {it} value params")
+    return reports
+
+
+@pytest.mark.parametrize("algo,n,T,iters", [
+    ("ppo", 4096, 4, 3),      # BASELINE configs[1]
+    ("ppo", 131072, 4, 1),    # BASELINE configs[3]: one GPU's shard of the 1 M-env run
+    ("ac", 65536, 8, 1),      # BASELINE configs[2]: online actor-critic
+])
+def test_fused_path_vs_oracle64_at_baseline_sizes(D, ctx, orc, algo, n, T, iters):
+    S = _setup(D, ctx, orc, n, T, algo, seed=7)
+    p0 = S["policy"].parameters().copy()
+    total_amb = 0
+    for it in range(iters):
+        for r in _iteration(D, orc, S, n, T, algo, it):
+            total_amb += r["ambiguous"]
+            assert r["ambiguous"] < 0.35 * p0.size, "too many ambiguous directions for a meaningful projection"
+    assert np.any(S["policy"].parameters() != p0)
+    s = S["tr"].stats()
+    assert s["env_steps"] == iters * n * T and s["reward_sum"] + s["episodes"] == s["env_steps"]
+    for k in ("tr", "env", "policy", "value"):
+        S[k].close()
+
+
+def test_env_sharding_is_rank_invariant_on_one_gpu(D, ctx):
+    """'results independent of n'. Two shards of n/2 environments (env_offset 0
+    and n/2, the two ranks of a 2-GPU run) against one shard of n on the same global env ids, all
+    free-running on Philox streams keyed by the GLOBAL env id: rollout records bit-identical,
+    per-shard flat gradients sum to the single-shard gradient within fp32 sum-order tolerance.
+    (lr = 0 keeps the replicated parameters fixed, so the shards need no exchange here; the
+    exchange itself is covered by tests/p2p_worker.py on 2+ GPUs.)"""
+    n, T = 8192, 4
+
+    def run(n_local, offset):
+        policy = D.Model(ctx, D.fc_layers(PD, D.SOFTMAX), 32)
+        value = D.Model(ctx, D.fc_layers(VD), 32)
+        policy.init_parameters(11)
+        value.init_parameters(12)
+        env = D.Environment(ctx, n_local, seed=4321, env_offset=offset)
+        tr = D.Trainer(ctx, env, policy, value, algo=D.PPO, work=T, policy_lr=0.0, value_lr=0.0)
+        outs = []
+        for _ in range(2):
+            tr.rollout()
+            tr.learn()
+            outs.append(dict(state=tr.read(D.F_REC_STATE), action=tr.read(D.F_REC_ACTION), done=tr.read(D.F_REC_DONE),
+                             probs=tr.read(D.F_REC_PROBS), adv=tr.read(D.F_ADVANTAGE),
+                             pg=tr.read(D.F_POLICY_GRAD_LOG).astype(np.float64), vg=tr.read(D.F_VALUE_GRAD).astype(np.float64),
+                             live=env.state()))
+        tr.close(); env.close(); policy.close(); value.close()
+        return outs
+    whole, a, b = run(n, 0), run(n // 2, 0), run(n // 2, n // 2)
+    for it in range(2):
+        w = whole[it]
+        for key, axis in (("state", 2), ("action", 1), ("done", 1), ("probs", 1), ("adv", 1), ("live", 1)):
+            both = np.concatenate([a[it][key], b[it][key]], axis=axis)
+            assert np.array_equal(both, w[key]), f"iteration {it}: {key} depends on the sharding"
+        close(a[it]["pg"] + b[it]["pg"], w["pg"], rtol=1e-5, what="policy gradient, 2 shards vs 1")
+        close(a[it]["vg"] + b[it]["vg"], w["vg"], rtol=1e-5, what="value gradient, 2 shards vs 1")
+
+
+def test_eval_after_graph_replay_uses_current_weights(D, ctx):
+    """The learn phase replays as a CUDA graph from the third learn() on; Model.eval and
+    eval_argmax (layered kernels with a transposed-weight cache) must see the replayed updates."""
+    n, T = 2048, 4
+    policy = D.Model(ctx, D.fc_layers(PD, D.SOFTMAX), 32)
+    value = D.Model(ctx, D.fc_layers(VD), 32)
+    policy.init_parameters(5)
+    value.init_parameters(6)
+    env = D.Environment(ctx, n, seed=3)
+    tr = D.Trainer(ctx, env, policy, value, algo=D.PPO, work=T, policy_lr=1e-2 / (n * T), value_lr=1e-2 / (n * T))
+    x = (np.random.default_rng(0).integers(0, 9, (64, 32)) / 8.0).astype(np.float32)
+    for it in range(6):
+        tr.iterate(1)
+        fresh_p = D.Model(ctx, D.fc_layers(PD, D.SOFTMAX), 32)
+        fresh_v = D.Model(ctx, D.fc_layers(VD), 32)
+        fresh_p.set_parameters(policy.parameters())
+        fresh_v.set_parameters(value.parameters())
+        assert np.array_equal(policy.eval(x), fresh_p.eval(x)), f"policy eval is stale after iteration {it}"
+        assert np.array_equal(value.eval(x), fresh_v.eval(x)), f"value eval is stale after iteration {it}"
+        e1, e2 = D.Environment(ctx, 256, seed=9), D.Environment(ctx, 256, seed=9)
+        assert D.eval_argmax(ctx, e1, policy, 1) == D.eval_argmax(ctx, e2, fresh_p, 1)
+        for o in (fresh_p, fresh_v, e1, e2):
+            o.close()
+    tr.close(); env.close(); policy.close(); value.close()
