@@ -164,6 +164,8 @@ def workload_config(args, n_envs_note=None):
         "steps_per_iter": T_STEPS, "epochs": EPOCHS, "optimizer": "sgd",
         "lr": "reference 1e-4 / 1e-5 scaled by 32 / (global rows) because gradients are SUMS over rows",
         "items": "synthetic Bernoulli(0.4) stream, Philox4x32-10 keyed (seed, global env, draw)",
+        "timing": "value = median of R blocks of exactly --steps iterations (R = repeats: >= --min-timed-s of device time), "
+                  "each block between barrier + synchronize, CUDA events, max over ranks; e2e the same with the wall clock",
         "parallelism": f"dp{args.gpus} (envs sharded, flat-gradient all-reduce SUM)",
         "l2": "activation working set exceeds the 126 MB L2 at 131072 envs/GPU; no flush needed",
         **({"note": n_envs_note} if n_envs_note else {}),
@@ -177,17 +179,117 @@ C5_VALUE_DIMS = [128, 256, 256, 256, 1]
 
 
 def make_trainer(D, ctx, n_envs, env_offset, global_rows, seed=1234, fused=1, pdims=None, vdims=None, n_bins=8,
-                 algo=None, work=T_STEPS, last=None):
+                 algo=None, work=T_STEPS, last=None, opt=None, shared=False, player=None, vlayer=None, lr_scale=1.0):
     pdims, vdims = pdims or POLICY_DIMS, vdims or VALUE_DIMS
-    policy = D.Model(ctx, D.fc_layers(pdims, last if last is not None else D.SOFTMAX), 4 * n_bins)
-    value = D.Model(ctx, D.fc_layers(vdims), 4 * n_bins)
+    policy = D.Model(ctx, player or D.fc_layers(pdims, last if last is not None else D.SOFTMAX), 4 * n_bins)
     policy.init_parameters(seed)       # identical on every rank (replicated parameters)
+    if shared:   # BASELINE configs[2]: one trunk 32-64-64, heads 64-8 and 64-1 (dfrl_mlp_create_shared)
+        value = D.Model.shared(policy, 4, [(D.DENSE, pdims[-2], 1)])
+    else:
+        value = D.Model(ctx, vlayer or D.fc_layers(vdims), 4 * n_bins)
     value.init_parameters(seed + 1)
     env = D.Environment(ctx, n_envs, n_bins=n_bins, seed=seed, env_offset=env_offset)
+    kw = {} if opt is None else {"policy_opt": opt, "value_opt": opt}
     tr = D.Trainer(ctx, env, policy, value, algo=algo if algo is not None else D.PPO, work=work,
-                   policy_lr=REF_LR_P * REF_ROWS / global_rows, value_lr=REF_LR_V * REF_ROWS / global_rows,
-                   fused=fused)
+                   policy_lr=lr_scale * REF_LR_P * REF_ROWS / global_rows, value_lr=lr_scale * REF_LR_V * REF_ROWS / global_rows,
+                   fused=fused, **kw)
     return tr, env, policy, value
+
+
+def quick_rate(D, ctx, objs, n_envs, work, warm, iters):
+    """env-steps/s of `iters` device-resident iterations (CUDA events), then closes the objects."""
+    tr = objs[0]
+    tr.iterate(warm)
+    ctx.sync()
+    l0 = ctx.launches()
+    ctx.timer_start()
+    tr.iterate(iters)
+    ms = ctx.timer_stop() / iters
+    launches = (ctx.launches() - l0) / iters
+    for o in (objs[0], objs[1], objs[3], objs[2]):   # trainer, env, value (a sharer goes first), policy
+        o.close()
+    return {"value": n_envs * work / (ms * 1e-3), "unit": "env-steps/s", "ms_per_step": ms, "envs": n_envs,
+            "steps_per_iter": work, "launches_per_step": launches}
+
+
+def hbm_kernel_rows(D, ctx, peaks):
+    """The HBM-bound kernels north_star names (env step, GAE, optimizer, heuristic play), each timed
+    alone on L2-exceeding inputs: achieved GB/s = SURVEY section 8d's algorithmic bytes / time."""
+    lib, chk = D._lib.lib, D._lib.check
+    rows = {}
+
+    def timed(fn, reps):
+        fn()
+        ctx.sync()
+        ctx.timer_start()
+        for _ in range(reps):
+            fn()
+        return ctx.timer_stop() / reps
+
+    def row(name, ms, nbytes, what):
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        rows[name] = {"us_per_launch": round(1e3 * ms, 2), "algorithmic_mb_per_launch": round(nbytes / 1e6, 2),
+                      "gbs": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peaks["hbm_gbs"], 4), "what": what}
+    # K1 environment::apply + game_over + reset + next item, 8 Mi envs (151 MB of state: > L2)
+    n = 1 << 23
+    env = D.Environment(ctx, n, seed=5)
+    act = ctx.to_device(np.random.default_rng(0).integers(0, 8, n).astype(np.uint8))
+    done = ctx.empty((n,), np.uint8)
+    ms = timed(lambda: chk(lib.dfrl_env_step(env.h, act.p, done.p, None)), 20)
+    row("env_step_vec4_kernel", ms, n * 38, "8 Mi envs, 8 bins: 2 x 18 B state + action + done per env-step (SURVEY 8d K1)")
+    # batched heuristic policy + env, whole episodes on the device (min-waste, 1 episode per env)
+    tot, steps = C.c_double(), C.c_longlong()
+    env.reset()
+    ctx.sync()
+    ctx.timer_start()
+    chk(lib.dfrl_heuristic_play(env.h, D.HEUR_MINWASTE, 1, C.byref(tot), C.byref(steps)))
+    ms = ctx.timer_stop()
+    rows["heuristic_play_kernel"] = {"ms": round(ms, 3), "env_steps": steps.value, "env_steps_per_s": steps.value / (ms * 1e-3),
+                                      "mean_reward": tot.value / n,
+                                      "what": "min-waste policy, 8 Mi envs x 1 episode, state resident in L1/L2 per thread: "
+                                              "latency / instruction bound, not an HBM stream"}
+    for o in (act, done):
+        o.free()
+    env.close()
+    # K4 GAE on [T][n] records, T = 4, 16 Mi envs
+    T, n = 4, 1 << 24
+    d = ctx.zeros((T, n), np.uint8)
+    vs, ve = ctx.zeros((T, n), np.float32), ctx.zeros((T, n), np.float32)
+    tg, adv = ctx.empty((T, n), np.float32), ctx.empty((T, n), np.float32)
+    ms = timed(lambda: chk(lib.dfrl_gae(ctx.h, d.p, vs.p, ve.p, n, T, C.c_float(0.99), C.c_float(0.95), tg.p, adv.p)), 10)
+    row("gae_kernel", ms, T * n * 17, "16 Mi envs x T=4: done + V_t + V_t+1 read, target + advantage written = 17 B/row (K4)")
+    for o in (d, vs, ve, tg, adv):
+        o.free()
+    # K7 optimizers, 64 Mi parameters
+    P = 1 << 26
+    prm, g, st = ctx.zeros((P,), np.float32), ctx.zeros((P,), np.float32), ctx.zeros((2 * P,), np.float32)
+    for kind, name, bpp in ((D.SGD, "opt_kernel<sgd>", 12), (D.ADAM, "opt_kernel<adam>", 28)):
+        ms = timed(lambda: chk(lib.dfrl_opt_step(ctx.h, kind, prm.p, g.p, st.p, P, C.c_float(1e-4), C.c_float(0.0),
+                                                 C.c_float(0.9), C.c_float(0.999), C.c_float(3.0))), 10)
+        row(name, ms, P * bpp, f"64 Mi parameters, {bpp} B/param (K7)")
+    for o in (prm, g, st):
+        o.free()
+    return rows
+
+
+def cpu_reference_rows(cores):
+    """CPU rows of SURVEY section 8d on the box's host cores (compiled reference, oracle/_ref):
+    C1 = REINFORCE, single env, reference default FC policy 32-256-128-8 (BASELINE configs[0]);
+    the reference's own PPO nets (conv1d 4-128-64-1 + FC 32-64-32-1) at 8 workers x 4 steps."""
+    from oracle import ref as R
+    if not R.available():
+        return None
+    out = {}
+    pol = R.fc_net([32, 256, 128, 8], R.SOFTMAX_CE)
+    res = R.train(R.REINFORCE, 1234, 1, 1, 300, pol, R.init_params(pol, 1), 1e-4, record=False, threads=1)
+    out["c1_reinforce_single_env_cpu"] = {"value": res["env_steps"] / res["seconds"], "unit": "env-steps/s", "cores": 1,
+                                          "sample": f"300 updates of 1 env x 1 episode ({res['seconds']:.1f} s), pg_training.cc nets"}
+    pol, val = R.conv_net([4, 128, 64, 1], R.SOFTMAX), R.fc_net([32, 64, 32, 1])
+    res = R.train(R.PPO, 1234, 8, 4, 60, pol, R.init_params(pol, 1), 1e-4, val, R.init_params(val, 2), 1e-5,
+                  record=False, threads=min(8, cores))
+    out["ppo_reference_nets_cpu"] = {"value": res["env_steps"] / res["seconds"], "unit": "env-steps/s", "cores": min(8, cores),
+                                     "sample": f"60 PPO rounds of 8 workers x 4 steps ({res['seconds']:.1f} s), ppo_training.cc nets and rates"}
+    return out
 
 
 def measure(D, ctx, dist, args, n_envs, world, rank, steps, warmup, sample_clocks):
@@ -217,14 +319,25 @@ def measure(D, ctx, dist, args, n_envs, world, rank, steps, warmup, sample_clock
     if sampler:
         sampler.__enter__()
     tr.iterate(warmup)
-    barrier()
+
+    def timed_block():
+        """EXACTLY `steps` iterations between a barrier + synchronize on both sides, device time (CUDA
+        events on the library's stream), max over ranks."""
+        barrier()
+        ctx.timer_start()
+        tr.iterate(steps)
+        ms = ctx.timer_stop()
+        barrier()
+        return max_over_ranks(ms)
     l0 = ctx.launches()
-    ctx.timer_start()
-    tr.iterate(steps)
-    ms = ctx.timer_stop()
-    barrier()
+    first = timed_block()
     launches = ctx.launches() - l0
-    ms = max_over_ranks(ms)
+    # the block is repeated until >= min_timed_s of device time has been measured (a 20-step block is
+    # 12 ms: too short for the clock sampler and for the power state to settle); the MEDIAN block is
+    # reported. Every rank derives the same repeat count from the max-over-ranks first block.
+    repeats = int(min(400, max(1, np.ceil(args.min_timed_s * 1e3 / max(first, 1e-3)))))
+    blocks = [first] + [timed_block() for _ in range(repeats - 1)]
+    ms = float(np.median(blocks))
     value_rate = n_envs * world * T_STEPS * steps / (ms * 1e-3)
 
     # ---- e2e through the public call with HOST buffers: per step the item stream of the step
@@ -259,18 +372,21 @@ def measure(D, ctx, dist, args, n_envs, world, rank, steps, warmup, sample_clock
         return tr.stats_end() if n else s
 
     run(max(2, warmup))
-    barrier()
-    t0 = time.perf_counter()
-    s = run(steps)
-    ctx.sync()
-    dt = time.perf_counter() - t0
-    dt = max_over_ranks(dt)
+    e2e_blocks = []
+    for _ in range(repeats):
+        barrier()
+        t0 = time.perf_counter()
+        s = run(steps)
+        ctx.sync()
+        e2e_blocks.append(max_over_ranks(time.perf_counter() - t0))
+    dt = float(np.median(e2e_blocks))
     e2e_rate = n_envs * world * T_STEPS * steps / dt
     if sampler:
         sampler.__exit__()
     for hp in hps:
         D._lib.check(lib.dfrl_free_host(ctx.h, hp))
     res = {"value": value_rate, "ms_per_step": ms / steps, "launches_per_step": launches / steps,
+           "repeats": repeats, "timed_ms_total": float(sum(blocks)), "block_ms_min_max": [float(min(blocks)), float(max(blocks))],
            "e2e": {"value": e2e_rate, "unit": "env-steps/s", "h2d_bytes_per_step": nbytes * world,
                    "d2h_bytes_per_step": 32 * world, "ms_per_step": 1e3 * dt / steps},
            "clocks": sampler.summary() if sampler else None, "stats": s,
@@ -441,19 +557,29 @@ def run_ours(args):
             o.close()
     if world == 1 and not args.no_c2:
         # BASELINE configs[2]: online actor-critic (one critic step, GAE, one policy step with
-        # A (p - onehot)), 65 536 envs, T = 8 (ac_training.cc:30). The reference's sequential `model`
-        # cannot express a shared trunk: separate 32-64-64 policy / value nets.
+        # A (p - onehot)), 65 536 envs, T = 8 (ac_training.cc:30), SHARED-TRUNK policy / value net
+        # 32-64-64-{8, 1} (P = 6 857; dfrl_mlp_create_shared). The reference's sequential `model` cannot
+        # express it and ac_training.cc builds two nets: that variant is reported beside it.
         n3, T3 = 65536, 8
-        tr3, env3, p3, v3 = make_trainer(D, ctx, n3, 0, n3 * T3, algo=D.ACTOR_CRITIC, work=T3, last=D.SOFTMAX_CE)
-        tr3.iterate(5)
-        ctx.sync()
-        ctx.timer_start()
-        tr3.iterate(50)
-        ms3 = ctx.timer_stop() / 50
-        extra["c3_actor_critic_65536_envs"] = {"value": n3 * T3 / (ms3 * 1e-3), "unit": "env-steps/s",
-                                               "ms_per_step": ms3, "steps_per_iter": T3}
-        for o in (tr3, env3, p3, v3):
-            o.close()
+        extra["c3_actor_critic_65536_envs"] = quick_rate(
+            D, ctx, make_trainer(D, ctx, n3, 0, n3 * T3, algo=D.ACTOR_CRITIC, work=T3, last=D.SOFTMAX_CE, shared=True), n3, T3, 5, 50)
+        extra["c3_actor_critic_65536_envs"]["net"] = "shared trunk 32-64-64, heads 64-8 (softmax-CE) and 64-1"
+        extra["c3_actor_critic_separate_nets"] = quick_rate(
+            D, ctx, make_trainer(D, ctx, n3, 0, n3 * T3, algo=D.ACTOR_CRITIC, work=T3, last=D.SOFTMAX_CE), n3, T3, 5, 50)
+    if world == 1 and not args.no_extra:
+        n = args.envs_per_gpu
+        # T = 32 steps per iteration (SURVEY section 8d "also report T = 32"): 4 envs per learner tile
+        extra["ppo_T32"] = quick_rate(D, ctx, make_trainer(D, ctx, n // 8, 0, (n // 8) * 32, work=32), n // 8, 32, 3, 20)
+        # Adam (north_star names it; the reference apps use SGD): device-side step counter, same CUDA graph
+        extra["ppo_adam"] = quick_rate(D, ctx, make_trainer(D, ctx, n, 0, n * T_STEPS, opt=D.ADAM, lr_scale=0.1), n, T_STEPS, 5, 50)
+        # the reference's own default nets (ppo_training.cc:10-26: conv1d 4-128-64-1 softmax policy, FC
+        # 32-64-32-1 critic) at 4096 envs: layered path (conv1d products on the tcgen05 GEMMs), beside the
+        # reference's CPU rate for the same nets below
+        extra["reference_nets_4096_envs"] = quick_rate(
+            D, ctx, make_trainer(D, ctx, 4096, 0, 4096 * T_STEPS, player=D.conv_layers([4, 128, 64, 1], D.SOFTMAX),
+                                 vlayer=D.fc_layers([32, 64, 32, 1])), 4096, T_STEPS, 3, 20)
+        extra["reference_nets_4096_envs"]["algorithmic_flop_per_env_step"] = 2296208
+        extra["hbm_kernels"] = hbm_kernel_rows(D, ctx, peaks)
     if world == 1 and not args.no_c2:
         # BASELINE configs[1] verbatim: PPO, 4096 parallel envs, 1 GPU (latency-bound size)
         c2 = measure(D, ctx, None, args, 4096, 1, 0, max(args.steps, 50), max(args.warmup, 5), False)
@@ -463,6 +589,10 @@ def run_ours(args):
                                  "e2e": c2["e2e"], "launches_per_step": c2["launches_per_step"]}
 
     cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu and not args.no_extra:
+        rows = cpu_reference_rows(os.cpu_count() or 1)
+        if rows:
+            extra["cpu_reference_rows"] = rows
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
         ref_envs = args.ref_envs if args.ref_envs > 0 else 256
@@ -476,7 +606,9 @@ def run_ours(args):
         line = {
             "metric": "ppo_binpacking_env_steps_per_sec", "value": main["value"], "unit": "env-steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": main["ms_per_step"],
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 via bf16x3 (fp32 operands split hi + lo, 3 tcgen05 bf16 products per fp32 product, fp32 accumulation in TMEM; ~2^-17 relative)",
+            "repeats": main["repeats"], "timed_ms_total": main["timed_ms_total"], "block_ms_min_max": main["block_ms_min_max"],
             "data": "synthetic", "config": {**workload_config(args), "gradient_exchange": exchange},
             "e2e": main["e2e"], "gpu_launches": int(round(main["launches_per_step"] * args.steps)),
             "clocks": {"sm_mhz": clocks.get("sm_mhz"), "sm_max_mhz": clocks.get("sm_max_mhz"),
@@ -505,7 +637,10 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-c2", action="store_true")
     ap.add_argument("--no-c5", action="store_true")
-    ap.add_argument("--c5-envs", type=int, default=32768)
+    ap.add_argument("--c5-envs", type=int, default=131072)  # C5 at 131 072 envs / GPU
+    ap.add_argument("--min-timed-s", type=float, default=0.6,
+                    help="repeat the --steps block until this much device time has been measured; report the median block")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary rows (T=32, Adam, reference nets, HBM kernels, C1)")
     ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: NCCL all-reduce instead of the fused peer-memory exchange")
     args = ap.parse_args()
     if args.impl == "reference":

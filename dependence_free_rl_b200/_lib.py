@@ -95,6 +95,7 @@ PROTOTYPES = {
     "dfrl_softmax_forward": (i32, [vp, vp, i32, i32, vp]),
     "dfrl_softmax_backward": (i32, [vp, vp, vp, i32, i32, vp]),
     "dfrl_mlp_create": (i32, [vp, i32, pi32, pi32, pi32, i32, C.POINTER(vp)]),
+    "dfrl_mlp_create_shared": (i32, [vp, i32, i32, pi32, pi32, pi32, C.POINTER(vp)]),
     "dfrl_mlp_destroy": (i32, [vp]),
     "dfrl_mlp_param_count": (i32, [vp]),
     "dfrl_mlp_output_cols": (i32, [vp]),

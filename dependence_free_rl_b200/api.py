@@ -236,12 +236,35 @@ class Model:
                                   i.ctypes.data_as(_lib.pi32), o.ctypes.data_as(_lib.pi32),
                                   input_cols, C.byref(h)))
         self.ctx, self.h, self.input_cols = ctx, h, input_cols
-        self.n_params = lib.dfrl_mlp_param_count(h)
         self.output_cols = lib.dfrl_mlp_output_cols(h)
+
+    @classmethod
+    def shared(cls, trunk, n_shared, head_layers):
+        """A model whose first n_shared layers are `trunk`'s (same device parameters) followed by its
+        own head_layers (dfrl_mlp_create_shared): the shared-trunk policy / value pair of BASELINE
+        configs[2]. Both models then report the family's whole flat parameter vector."""
+        self = cls.__new__(cls)
+        head = [tuple(int(v) for v in l) for l in head_layers]
+        self.layers = trunk.layers[:n_shared] + head
+        k = np.array([l[0] for l in head], np.int32)
+        i = np.array([l[1] for l in head], np.int32)
+        o = np.array([l[2] for l in head], np.int32)
+        h = C.c_void_p()
+        check(lib.dfrl_mlp_create_shared(trunk.h, n_shared, len(head), k.ctypes.data_as(_lib.pi32),
+                                         i.ctypes.data_as(_lib.pi32), o.ctypes.data_as(_lib.pi32), C.byref(h)))
+        self.ctx, self.h, self.input_cols = trunk.ctx, h, trunk.input_cols
+        self.output_cols = lib.dfrl_mlp_output_cols(h)
+        self._family = trunk
+        trunk._sharers = getattr(trunk, "_sharers", []) + [self]
+        return self
+
+    @property
+    def n_params(self):
+        return lib.dfrl_mlp_param_count(self.h)
 
     def close(self):
         if self.h:
-            lib.dfrl_mlp_destroy(self.h)
+            check(lib.dfrl_mlp_destroy(self.h))
             self.h = None
 
     def set_parameters(self, p):

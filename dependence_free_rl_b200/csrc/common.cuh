@@ -172,6 +172,12 @@ struct dfrl_mlp {
   float *wt;       // W^T per parametric layer, refreshed after every parameter change
   bool wt_dirty;
   uint64_t version = 0;  // bumped on every parameter change (fused.cu panel-image cache)
+  // shared-trunk models (dfrl_mlp_create_shared): every model of a family addresses ONE flat
+  // parameter vector of n_params floats owned by `share_owner` (null: this model owns it); the first
+  // n_shared_layers layers of a sharer carry the owner's parameter offsets
+  dfrl_mlp *share_owner = nullptr;
+  std::vector<dfrl_mlp *> sharers;
+  int n_shared_layers = 0;
   // kept activations of the last forward_keep()
   std::vector<float *> acts;  // acts[l] = output of layer l (device), acts.size() == layers.size()
   float *act_arena;
@@ -179,6 +185,15 @@ struct dfrl_mlp {
   int kept_rows;
   const float *kept_input;
 };
+
+// Parameters changed on the device: invalidate the transposed-weight caches of every model that
+// addresses the same flat vector.
+static inline void dfrl_mlp_params_changed(dfrl_mlp *m) {
+  dfrl_mlp *o = m->share_owner ? m->share_owner : m;
+  o->wt_dirty = true, o->version++;
+  for (dfrl_mlp *s : o->sharers)
+    s->wt_dirty = true, s->version++;
+}
 
 // gemm_umma.cu: tcgen05 GEMMs of the layered path; DFRL_ERR_UNSUPPORTED = use the FFMA kernels
 int umma_gemm_nn(dfrl_ctx *ctx, const float *A, const float *Bm, const float *bias, const float *mask, float *C,

@@ -32,6 +32,7 @@
 // Jacobian), nn.h:85-100 (dW = SUM over rows), policy_gradient.h:196-281 (targets, GAE).
 #include <cuda_fp16.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "device_fns.cuh"
@@ -48,7 +49,12 @@ struct net3 {
   int d0, d1, d2, d3;
   int o_w1, o_b1, o_w2, o_b2, o_w3, o_b3;  // offsets into the flat parameter vector
   int n_params;
+  int shared;  // shared-trunk family (dfrl_mlp_create_shared): the vector holds other heads' parameters too
 };
+// Does this net own entry q of the flat vector? (always true unless the vector is shared)
+__host__ __device__ __forceinline__ bool net_owns(const net3 &n, int q) {
+  return (q >= n.o_w1 && q < n.o_b1 + n.d1) || (q >= n.o_w2 && q < n.o_b2 + n.d2) || (q >= n.o_w3 && q < n.o_b3 + n.d3);
+}
 
 struct tid_t {
   int wg, w, lane, row;
@@ -215,6 +221,24 @@ struct learner_rows {
   int n, stride, T, E, B;
   float inv_w, inv_h;
 };
+// ---- gradient tail: cross-CTA reduction (+ peer exchange) + optimizer update INSIDE the producing
+// kernel. The learner kernels are persistent (one CTA per SM, launched cooperatively): after a CTA
+// has written its partial gradient it arrives on a grid barrier; every CTA then owns a contiguous
+// slice of ceil(P / grid) parameters, sums the grid's partials of that slice in a fixed order (bitwise
+// reproducible), exchanges the slice sums with the peer ranks (PUSH, flag in the data, see below) and
+// applies sgd / momentum / adam (nn.h:616-698) to its slice. This replaces a separate reduction
+// launch per optimizer step (5 per PPO iteration) and the drain -> launch -> reduce hand-over.
+struct p2p_view {
+  float *peer[DFRL_P2P_MAX_RANKS];
+  int nranks, rank;
+};
+struct grad_tail {
+  float *grad;        // [P] reduced flat gradient (all ranks' sum when the exchange runs)
+  unsigned *bar;      // [0] arrivals, [1] generation of the grid barrier (zero at creation)
+  dfrl_opt_spec opt;  // params == null: gradient only (the caller runs NCCL + optimizer kernel)
+  p2p_view v;         // nranks > 1 (and opt given): exchange over NVLink peer memory
+};
+
 struct critic_args {
   const float *params;  // flat fp32 parameters of the net
   net3 net;
@@ -224,6 +248,7 @@ struct critic_args {
   float *targets_out;  // [T][n] (critic step) -- introspection + parity
   float *adv_out;      // [T][n] (GAE kernel)
   float *partials;
+  grad_tail tail;      // critic step only
   long long *clk;      // optional: phase clocks of CTA 0, pipeline 0 (debug; critic step only)
 };
 
@@ -238,8 +263,136 @@ struct policy_step_args {
   int n_tiles;
   int loss_kind, head_bwd;
   float *partials;     // [gridDim.x][n_params]
+  grad_tail tail;
   long long *clk;      // optional: phase clocks of CTA 0 (debug)
 };
+
+// ---- gradient tail (see grad_tail) ------------------------------------------------------------
+// What a thread needs from global memory BEFORE its CTA arrives on the grid barrier: the barrier
+// generation, the exchange number of this launch and the Adam step counter -- all three are advanced
+// by the CTA that releases the barrier, i.e. only after every thread of every CTA has read them
+// (the reads sit in front of the __syncthreads that precedes the arrival).
+struct tail_ctx {
+  unsigned gen, epoch;
+  float c1, c2;
+};
+__device__ __forceinline__ tail_ctx tail_begin(const grad_tail &tl) {
+  tail_ctx c;
+  c.gen = *reinterpret_cast<volatile unsigned *>(tl.bar + 1);
+  c.epoch = 0;
+  if (tl.v.nranks > 1)
+    c.epoch = reinterpret_cast<volatile unsigned *>(dfrl_p2p_flags(tl.v.peer[tl.v.rank]))[2] + 1;
+  c.c1 = tl.opt.c1, c.c2 = tl.opt.c2;
+  if (tl.opt.t_dev) {  // adam bias corrections from the device-side step counter (nn.h:683-684)
+    const float t = *reinterpret_cast<volatile float *>(tl.opt.t_dev);
+    c.c1 = 1.f - powf(tl.opt.beta1, t);
+    c.c2 = 1.f - powf(tl.opt.beta2, t);
+  }
+  return c;
+}
+// Exchange over peer memory, PUSH protocol with the flag in the data: the owner of gradient entry i
+// stores {value, exchange number} -- one 8-byte store, single-copy atomic -- into every rank's
+// exchange buffer over NVLink (own rank included), then polls its LOCAL copies of all source ranks
+// until their exchange number matches and sums them in rank order (bit-identical on every rank). No
+// fence, no separate flag, nothing on the receive side crosses NVLink. Two slots: a rank is never more
+// than one exchange ahead of a peer (it needs the peer's contribution to finish one). Time-bounded
+// wait (a peer that died must turn into a reported launch failure, not a hung GPU).
+__device__ __forceinline__ float exchange_entry(const p2p_view &v, unsigned epoch, int i, float r) {
+  const int slot = (int)(epoch & 1u);
+  const unsigned long long w = ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(r);
+  for (int q = 0; q < v.nranks; ++q)
+    *reinterpret_cast<volatile unsigned long long *>(dfrl_p2p_data(v.peer[q], slot, v.rank) + i) = w;
+  float *local = v.peer[v.rank];
+  unsigned long long x[DFRL_P2P_MAX_RANKS];
+  unsigned long long t0 = 0;
+  unsigned spins = 0;
+  bool all;
+  do {  // all loads in flight; repeat until every source rank's pair carries this exchange number
+    all = true;
+#pragma unroll
+    for (int q = 0; q < DFRL_P2P_MAX_RANKS; ++q) {
+      x[q] = q < v.nranks ? *reinterpret_cast<const volatile unsigned long long *>(dfrl_p2p_data(local, slot, q) + i)
+                          : ((unsigned long long)epoch << 32);
+      all = all && (unsigned)(x[q] >> 32) == epoch;
+    }
+    if (!all && (++spins & 0xfffu) == 0) {  // ranks may skew by seconds (graph instantiation, host tapes)
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(now));
+      if (t0 == 0)
+        t0 = now;
+      else if (now - t0 > 120ull * 1000000000ull)
+        __trap();
+    }
+  } while (!all);
+  float g = 0.f;
+#pragma unroll
+  for (int q = 0; q < DFRL_P2P_MAX_RANKS; ++q)  // rank order; ranks >= nranks add +0
+    g += __uint_as_float((unsigned)x[q]);
+  return g;
+}
+// Whole CTA, after its partial gradient has been written to partials[blockIdx.x][0..n).
+// scratch: (blockDim.x / 64) * 64 floats of shared memory. Contains __syncthreads.
+__device__ __forceinline__ void gradient_tail(const float *__restrict__ partials, const net3 &net, const grad_tail &tl,
+                                              float *scratch) {
+  const int n = net.n_params;
+  const tail_ctx tc = tail_begin(tl);
+  __syncthreads();  // every thread's partial-gradient stores precede thread 0's fence (cumulativity)
+  if (threadIdx.x == 0) {
+    __threadfence();  // ... and are visible device-wide before this CTA arrives
+    if (atomicAdd(tl.bar, 1u) == gridDim.x - 1) {  // last arrival: every CTA has read gen / epoch / t
+      tl.bar[0] = 0;
+      if (tl.v.nranks > 1)
+        reinterpret_cast<volatile unsigned *>(dfrl_p2p_flags(tl.v.peer[tl.v.rank]))[2] = tc.epoch;
+      if (tl.opt.params && tl.opt.t_dev)
+        *tl.opt.t_dev += 1.f;  // nn.h:686
+      __threadfence();
+      atomicExch(tl.bar + 1, tc.gen + 1);  // release
+    } else {
+      unsigned spins = 0;
+      while (*reinterpret_cast<volatile unsigned *>(tl.bar + 1) == tc.gen)
+        if (++spins > (1u << 28))
+          __trap();  // (one CTA per SM, grid <= SM count: every CTA is resident; bounded by the kernel's duration)
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  const int G = (int)gridDim.x, NS = (int)blockDim.x >> 6, s = (int)threadIdx.x >> 6, p = (int)threadIdx.x & 63;
+  const int per = (n + G - 1) / G;
+  const int lo = (int)blockIdx.x * per, hi = min(lo + per, n);
+  const dfrl_opt_spec &opt = tl.opt;
+  const bool exchange = opt.params && tl.v.nranks > 1;
+  constexpr int MAXL = 32;  // loads in flight per thread: one L2 round trip for <= 32 NS partials (160 CTAs at NS = 5)
+  for (int base = lo; base < hi; base += 64) {
+    const int i = base + p;
+    float acc = 0.f;
+    if (i < hi && s < NS)
+      for (int c0 = s; c0 < G; c0 += MAXL * NS) {  // fixed order
+        float x[MAXL];
+#pragma unroll
+        for (int q = 0; q < MAXL; ++q) {
+          const int c = c0 + q * NS;
+          x[q] = c < G ? __ldcg(partials + (size_t)c * n + i) : 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < MAXL; ++q)
+          acc += x[q];
+      }
+    if (s < NS)
+      scratch[s * 64 + p] = acc;
+    __syncthreads();
+    if (s == 0 && i < hi) {
+      float g = 0.f;
+      for (int q = 0; q < NS; ++q)
+        g += scratch[q * 64 + p];
+      if (exchange)
+        g = exchange_entry(tl.v, tc.epoch, i, g);
+      tl.grad[i] = g;
+      if (opt.params && (!net.shared || net_owns(net, i)))  // (another head's slots: zero gradient, left alone)
+        opt_update(opt.kind, opt.params, tl.grad, opt.state, n, i, opt.lr, opt.wd, opt.beta1, opt.beta2, tc.c1, tc.c2);
+    }
+    __syncthreads();
+  }
+}
 
 // ---------------------------------------------------------------------------------------------
 // Policy step, two tile pipelines per CTA.
@@ -814,6 +967,10 @@ __global__ void __launch_bounds__((pmap<D1, D2>::THREADS), 1) fused_policy_step_
     for (int q = threadIdx.x; q < net.n_params; q += blockDim.x)
       part[q] = 0.f;
   } else {
+    if (net.shared)  // the other heads' slots of the flat gradient
+      for (int q = threadIdx.x; q < net.n_params; q += blockDim.x)
+        if (!net_owns(net, q))
+          part[q] = 0.f;
     // dW2[n][k]: DA (M = 64) row n = TMEM lane 32 (n / 16) + n % 16, col k
     const bool drainer = threadIdx.x < 256;  // 256 threads read the TMEM accumulators (t.wg = 0, 1)
     if (drainer) {
@@ -894,10 +1051,12 @@ __global__ void __launch_bounds__((pmap<D1, D2>::THREADS), 1) fused_policy_step_
   }
   umma::fence_before_sync();
   __syncthreads();
-  if (clk)
-    clk[107] = clock64();
   if (t.warp == 0)
     umma::tmem_dealloc(tmem, 512);
+  // ---- cross-CTA reduction (+ exchange) + optimizer update of this CTA's parameter slice
+  gradient_tail(a.partials, net, a.tail, reinterpret_cast<float *>(smem + PM::WG0 + PM::H1_HI));
+  if (clk)
+    clk[107] = clock64();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1426,6 +1585,10 @@ __global__ void __launch_bounds__((cmap<D1, D2, MODE>::THREADS), 1) fused_critic
       for (int q = threadIdx.x; q < net.n_params; q += blockDim.x)
         part[q] = 0.f;
     } else {
+      if (net.shared)  // the other heads' slots of the flat gradient
+        for (int q = threadIdx.x; q < net.n_params; q += blockDim.x)
+          if (!net_owns(net, q))
+            part[q] = 0.f;
       const bool drainer = threadIdx.x < 256;  // 256 threads read the TMEM accumulators (t.wg = 0, 1)
       if (drainer) {  // dW2[n][k]: DA (M = 64) row n = TMEM lane 32 (n / 16) + n % 16, col k
         constexpr int DC = D1 / 2;
@@ -1512,123 +1675,8 @@ __global__ void __launch_bounds__((cmap<D1, D2, MODE>::THREADS), 1) fused_critic
   __syncthreads();
   if (t.warp == 0)
     umma::tmem_dealloc(tmem, 512);
-}
-
-// Second stage of the gradient: fixed-order sum of the per-CTA partials. With a single rank the
-// optimizer update (nn.h:616-698) of the same 32 parameters follows in the same kernel.
-// Block = 32 consecutive gradient entries x RS slices of the per-CTA partials (1024 threads):
-// a thread sums <= 5 partials with all its loads in flight (the 8-slice version walked 19 partials
-// one L2 round trip at a time), then the slices are combined in a fixed order: 4 groups of 8
-// serially, then the 4 group sums. Every thread returns the same sum.
-constexpr int RS = 32;
-__device__ __forceinline__ float reduce_block_sum(const float *__restrict__ part, int ctas, int n, int i, int slice,
-                                                  int lane, float (*sm)[33]) {
-  float x[8];
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const int c = slice + RS * q;
-    x[q] = (i < n && c < ctas) ? part[(size_t)c * n + i] : 0.f;
-  }
-  float s = 0.f;
-#pragma unroll
-  for (int q = 0; q < 8; ++q)
-    s += x[q];
-  sm[slice][lane] = s;
-  __syncthreads();
-  float g[4];
-#pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    float r = 0.f;
-#pragma unroll
-    for (int q = 0; q < 8; ++q)
-      r += sm[8 * u + q][lane];
-    g[u] = r;
-  }
-  return (g[0] + g[1]) + (g[2] + g[3]);
-}
-struct reduce_tail {
-  dfrl_opt_spec opt;   // params == null: no update
-  unsigned *ticket;    // multi-rank exchange: zero before the launch, zero again after it
-  // multi-rank exchange (fused_reduce_exchange_kernel): this rank's exchange buffer ([2 slots]
-  // [DFRL_P2P_CAP] floats, flag words incl. the exchange counter, per-block publish flags). The
-  // counter lives on the device so that the launch arguments are constant (CUDA-graph capturable):
-  // exchange e = counter + 1 uses slot e & 1; the block that takes the last ticket bumps the counter.
-  float *exchange;
-};
-__global__ void __launch_bounds__(32 * RS) fused_reduce_partials_kernel(const float *__restrict__ part, int ctas,
-                                                                       int n, float *__restrict__ grad,
-                                                                       reduce_tail tail) {
-  __shared__ float sm[RS][33];
-  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
-  const int i = blockIdx.x * 32 + lane;
-  const float r = reduce_block_sum(part, ctas, n, i, slice, lane, sm);
-  if (slice == 0 && i < n) {
-    grad[i] = r;
-    const dfrl_opt_spec &opt = tail.opt;
-    if (opt.params)
-      opt_update(opt.kind, opt.params, grad, opt.state, n, i, opt.lr, opt.wd, opt.beta1, opt.beta2, opt.c1, opt.c2);
-  }
-}
-
-// Reduction + exchange + optimizer in ONE kernel (several ranks), PUSH protocol with the flag in
-// the data: block b sums the per-CTA partials of its 32 gradient entries; warp q then stores them
-// as {value, exchange number} pairs (one 8-byte store each, single-copy atomic) into rank q's
-// exchange buffer over NVLink (own rank included). The block then polls its LOCAL copies of all
-// source ranks until their exchange number matches, sums the values in rank order (bit-identical on
-// every rank) and applies the optimizer. No fence, no separate flag, nothing on the receive side
-// crosses NVLink: an exchange costs one remote-store latency on top of the reduction. The ticket
-// only elects the block that advances the exchange counter for the next launch. Two slots: a rank is
-// never more than one exchange ahead of a peer (it needs the peer's contribution to finish one). A
-// block never waits for another block of its own grid, and a peer's producer never depends on this
-// rank (bounded spin -> trap instead of a hung GPU).
-struct p2p_view {
-  float *peer[DFRL_P2P_MAX_RANKS];
-  int nranks, rank;
-};
-__global__ void __launch_bounds__(32 * RS) fused_reduce_exchange_kernel(const float *__restrict__ part, int ctas, int n,
-                                                                       float *__restrict__ grad, p2p_view v,
-                                                                       reduce_tail tail) {
-  __shared__ float sm[RS][33];
-  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
-  float *local = v.peer[v.rank];
-  volatile unsigned *words = reinterpret_cast<volatile unsigned *>(dfrl_p2p_flags(local));
-  const unsigned epoch = words[2] + 1;  // every block reads the counter before its ticket
-  const int slot = (int)(epoch & 1u);
-  const int i = blockIdx.x * 32 + lane;
-  const float r = reduce_block_sum(part, ctas, n, i, slice, lane, sm);  // every warp holds the same sum
-  static_assert(DFRL_P2P_MAX_RANKS <= RS, "one warp per destination rank");
-  if (slice < v.nranks && i < n) {
-    const unsigned long long w = ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(r);
-    *reinterpret_cast<volatile unsigned long long *>(dfrl_p2p_data(v.peer[slice], slot, v.rank) + i) = w;
-  }
-  if (threadIdx.x == 0 && atomicAdd(tail.ticket, 1u) == gridDim.x - 1) {  // all blocks have read the counter
-    *tail.ticket = 0;
-    words[2] = epoch;
-  }
-  if (slice == 0 && i < n) {
-    unsigned long long x[DFRL_P2P_MAX_RANKS];
-    unsigned spins = 0;
-    bool all;
-    do {  // all loads in flight; repeat until every source rank's pair carries this exchange number
-      all = true;
-#pragma unroll
-      for (int q = 0; q < DFRL_P2P_MAX_RANKS; ++q) {
-        x[q] = q < v.nranks ? *reinterpret_cast<const volatile unsigned long long *>(dfrl_p2p_data(local, slot, q) + i)
-                            : ((unsigned long long)epoch << 32);
-        all = all && (unsigned)(x[q] >> 32) == epoch;
-      }
-      if (!all && ++spins > (1u << 26))
-        __trap();
-    } while (!all);
-    float g = 0.f;
-#pragma unroll
-    for (int q = 0; q < DFRL_P2P_MAX_RANKS; ++q)  // rank order; ranks >= nranks add +0
-      g += __uint_as_float((unsigned)x[q]);
-    grad[i] = g;
-    const dfrl_opt_spec &opt = tail.opt;
-    if (opt.params)
-      opt_update(opt.kind, opt.params, grad, opt.state, n, i, opt.lr, opt.wd, opt.beta1, opt.beta2, opt.c1, opt.c2);
-  }
+  if (MODE == CRITIC_STEP)  // cross-CTA reduction (+ exchange) + optimizer update of this CTA's parameter slice
+    gradient_tail(a.partials, net, a.tail, reinterpret_cast<float *>(smem + CM::WG0));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1910,7 +1958,7 @@ struct fused_state {
   bool policy_ok, value_ok, rollout_ok;
   int head_bwd;
   float *partials;  // [ctas][max params]
-  unsigned *ticket;  // last-block election of the reduction kernel
+  unsigned *gridbar;  // [2] grid barrier of the gradient tail (arrivals, generation)
   int ctas;
   long long *clk;  // [112] phase clocks of the last policy step (allocated on first request)
   long long *clk_critic;  // [112] the same for the critic step
@@ -1942,6 +1990,7 @@ bool parse_net3(const dfrl_mlp *m, net3 *out, int *tail_kind) {
   out->o_w3 = (int)L[4].param_off;
   out->o_b3 = out->o_w3 + out->d2 * out->d3;
   out->n_params = m->n_params;
+  out->shared = (m->share_owner || !m->sharers.empty()) ? 1 : 0;
   return true;
 }
 
@@ -1956,13 +2005,33 @@ int set_smem_once(K kernel, int smem, bool *done) {
   return DFRL_OK;
 }
 
+// Cooperative launch (every CTA resident at once: the gradient tail's grid barrier may spin),
+// counted / profiled like DFRL_LAUNCH.
+template <typename K, typename A>
+int launch_cooperative(dfrl_ctx *ctx, K kernel, const char *name, int grid, int block, int smem, const A &args) {
+  if (ctx->profiling)
+    dfrl_profile_mark(ctx, name, 0);
+  void *kargs[] = {const_cast<A *>(&args)};
+  static const bool coop = getenv("DFRL_COOP") && atoi(getenv("DFRL_COOP")) != 0;
+  cudaError_t e = coop ? cudaLaunchCooperativeKernel((const void *)kernel, dim3(grid), dim3(block), kargs, (size_t)smem, ctx->stream)
+                       : cudaLaunchKernel((const void *)kernel, dim3(grid), dim3(block), kargs, (size_t)smem, ctx->stream);
+  ctx->launches++;
+  if (ctx->profiling)
+    dfrl_profile_mark(ctx, name, 1);
+  if (e != cudaSuccess) {
+    dfrl_set_error("cooperative launch of %s failed: %s", name, cudaGetErrorString(e));
+    return DFRL_ERR_CUDA;
+  }
+  return DFRL_OK;
+}
+
 template <int D0, int D1, int D2, int NOUT>
 int launch_policy_step(dfrl_ctx *ctx, const policy_step_args &a, int ctas) {
   constexpr int smem = pmap<D1, D2>::TOTAL + 1024;
   static bool attr = false;
   DFRL_TRY(set_smem_once(fused_policy_step_kernel<D0, D1, D2, NOUT>, smem, &attr));
-  DFRL_LAUNCH(ctx, (fused_policy_step_kernel<D0, D1, D2, NOUT>), ctas, (pmap<D1, D2>::THREADS), smem, a);
-  return DFRL_OK;
+  return launch_cooperative(ctx, fused_policy_step_kernel<D0, D1, D2, NOUT>, "(fused_policy_step_kernel<D0, D1, D2, NOUT>)",
+                            ctas, pmap<D1, D2>::THREADS, smem, a);
 }
 
 template <int D0, int D1, int D2>
@@ -1970,8 +2039,8 @@ int launch_critic_step(dfrl_ctx *ctx, const critic_args &a, int ctas) {
   constexpr int smem = cmap<D1, D2, CRITIC_STEP>::TOTAL + 1024;
   static bool attr = false;
   DFRL_TRY(set_smem_once(fused_critic_kernel<D0, D1, D2, CRITIC_STEP>, smem, &attr));
-  DFRL_LAUNCH(ctx, (fused_critic_kernel<D0, D1, D2, CRITIC_STEP>), ctas, (cmap<D1, D2, CRITIC_STEP>::THREADS), smem, a);
-  return DFRL_OK;
+  return launch_cooperative(ctx, fused_critic_kernel<D0, D1, D2, CRITIC_STEP>, "(fused_critic_kernel<D0, D1, D2, CRITIC_STEP>)",
+                            ctas, cmap<D1, D2, CRITIC_STEP>::THREADS, smem, a);
 }
 
 template <int D0, int D1, int D2>
@@ -1998,10 +2067,6 @@ int launch_rollout(dfrl_ctx *ctx, const rollout_args &a, int ctas) {
 bool widths_ok(const net3 &n) {
   return n.d0 == 32 && ((n.d1 == 64 && n.d2 == 64) || (n.d1 == 16 && n.d2 == 16));
 }
-
-struct fused_state;
-int launch_reduce(dfrl_trainer *t, fused_state *f, dfrl_mlp *m, const net3 &net, int ctas, float *grad_dev,
-                  const dfrl_opt_spec *opt);
 
 learner_rows make_rows(dfrl_trainer *t) {
   learner_rows r;
@@ -2030,54 +2095,32 @@ critic_args make_critic_args(dfrl_trainer *t, fused_state *f) {
   a.targets_out = t->targets;
   a.adv_out = t->adv;
   a.partials = f->partials;
+  memset(&a.tail, 0, sizeof(a.tail));
   a.clk = f->clk_critic;
   return a;
 }
 
-// Partials -> gradient (-> optimizer update when `opt` is given).
-// Several ranks (opt given means the peers are attached): reduction, exchange over NVLink peer
-// memory and update in one kernel (fused_reduce_exchange_kernel).
-int launch_reduce(dfrl_trainer *t, fused_state *f, dfrl_mlp *m, const net3 &net, int ctas, float *grad_dev,
-                  const dfrl_opt_spec *opt) {
+// The gradient tail of a learner kernel: reduction into grad_dev, and -- when `opt` is given --
+// the optimizer update (single rank) or exchange over NVLink peer memory + update (several ranks:
+// opt given means the peers are attached). opt == null: the caller exchanges / updates itself.
+int make_tail(dfrl_trainer *t, fused_state *f, const net3 &net, int ctas, float *grad_dev, const dfrl_opt_spec *opt,
+              grad_tail *tail) {
   dfrl_ctx *ctx = t->ctx;
-  DFRL_CHECK(ctas <= 8 * RS, "more per-CTA partials than the reduction kernel covers");
-  // The reduction kernels run between kernels that use the whole shared-memory carve-out: ask for
-  // the same carve-out so that the SMs are not reconfigured (drained) at every kernel boundary.
-  static bool carveout = false;
-  if (!carveout) {
-    DFRL_CUDA(cudaFuncSetAttribute(fused_reduce_partials_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                   cudaSharedmemCarveoutMaxShared));
-    DFRL_CUDA(cudaFuncSetAttribute(fused_reduce_exchange_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                   cudaSharedmemCarveoutMaxShared));
-    carveout = true;
-  }
-  const bool exchange = opt && ctx->nranks > 1;
-  reduce_tail tail;
-  memset(&tail, 0, sizeof(tail));
-  float *dst = grad_dev;
-  if (exchange) {
-    DFRL_CHECK((size_t)net.n_params <= DFRL_P2P_CAP, "flat gradient exceeds the exchange slot");
-    tail.ticket = f->ticket;
-    tail.exchange = ctx->p2p.local;
-  } else if (opt) {
-    tail.opt = *opt;
-  }
-  if (exchange) {
-    p2p_view v;
-    memset(&v, 0, sizeof(v));
-    for (int r = 0; r < ctx->nranks; ++r)
-      v.peer[r] = ctx->p2p.peer[r];
-    v.nranks = ctx->nranks;
-    v.rank = ctx->rank;
-    tail.opt = *opt;
-    DFRL_LAUNCH(ctx, fused_reduce_exchange_kernel, ceil_div(net.n_params, 32), 32 * RS, 0, (const float *)f->partials, ctas,
-                net.n_params, grad_dev, v, tail);
-  } else {
-    DFRL_LAUNCH(ctx, fused_reduce_partials_kernel, ceil_div(net.n_params, 32), 32 * RS, 0, (const float *)f->partials, ctas,
-                net.n_params, dst, tail);
-  }
+  // a CTA's slice of ceil(P / ctas) parameters is walked 64 entries at a time: any ctas works
+  memset(tail, 0, sizeof(*tail));
+  tail->grad = grad_dev;
+  tail->bar = f->gridbar;
   if (opt)
-    m->wt_dirty = true, m->version++;
+    tail->opt = *opt;
+  if (opt && ctx->nranks > 1) {
+    DFRL_CHECK((size_t)net.n_params <= DFRL_P2P_CAP, "flat gradient exceeds the exchange slot");
+    DFRL_CHECK(ctx->p2p.attached, "gradient exchange without attached peers");
+    for (int r = 0; r < ctx->nranks; ++r)
+      tail->v.peer[r] = ctx->p2p.peer[r];
+    tail->v.nranks = ctx->nranks;
+    tail->v.rank = ctx->rank;
+  }
+  (void)ctas;
   return DFRL_OK;
 }
 
@@ -2116,10 +2159,10 @@ int dfrl_fused_try_attach(dfrl_trainer *t) {
     maxp = t->value->n_params;
   bool ok = cudaMalloc(&f->partials, sizeof(float) * (size_t)f->ctas * maxp) == cudaSuccess;
   if (ok)
-    ok = cudaMalloc(&f->ticket, sizeof(unsigned)) == cudaSuccess &&
-         cudaMemsetAsync(f->ticket, 0, sizeof(unsigned), t->ctx->stream) == cudaSuccess;
+    ok = cudaMalloc(&f->gridbar, 2 * sizeof(unsigned)) == cudaSuccess &&
+         cudaMemsetAsync(f->gridbar, 0, 2 * sizeof(unsigned), t->ctx->stream) == cudaSuccess;
   if (!ok) {
-    cudaFree(f->ticket);
+    cudaFree(f->gridbar);
     cudaFree(f->partials);
     delete f;
     return DFRL_ERR_CUDA;
@@ -2139,7 +2182,7 @@ void dfrl_fused_detach(dfrl_trainer *t) {
     cudaFree(f->partials);
     cudaFree(f->clk);
     cudaFree(f->clk_critic);
-    cudaFree(f->ticket);
+    cudaFree(f->gridbar);
     delete f;
   }
   t->fused_impl = nullptr;
@@ -2201,11 +2244,14 @@ int dfrl_fused_policy_gradient(dfrl_trainer *t, int loss_kind, float *grad_dev, 
   a.partials = f->partials;
   a.clk = f->clk;
   int ctas = a.n_tiles < f->ctas ? a.n_tiles : f->ctas;
+  DFRL_TRY(make_tail(t, f, f->pnet, ctas, grad_dev, opt, &a.tail));
   if (f->pnet.d1 == 64)
     DFRL_TRY((launch_policy_step<32, 64, 64, 8>(t->ctx, a, ctas)));
   else
     DFRL_TRY((launch_policy_step<32, 16, 16, 8>(t->ctx, a, ctas)));
-  return launch_reduce(t, f, t->policy, f->pnet, ctas, grad_dev, opt);
+  if (opt)
+    dfrl_mlp_params_changed(t->policy);
+  return DFRL_OK;
 }
 
 // update_value_model (policy_gradient.h:196-218) up to the gradient: writes t->targets and grad_dev.
@@ -2215,11 +2261,14 @@ int dfrl_fused_critic_gradient(dfrl_trainer *t, float *grad_dev, const dfrl_opt_
     return DFRL_ERR_UNSUPPORTED;
   critic_args a = make_critic_args(t, f);
   int ctas = a.n_tiles < f->ctas ? a.n_tiles : f->ctas;
+  DFRL_TRY(make_tail(t, f, f->vnet, ctas, grad_dev, opt, &a.tail));
   if (f->vnet.d1 == 64)
     DFRL_TRY((launch_critic_step<32, 64, 64>(t->ctx, a, ctas)));
   else
     DFRL_TRY((launch_critic_step<32, 16, 16>(t->ctx, a, ctas)));
-  return launch_reduce(t, f, t->value, f->vnet, ctas, grad_dev, opt);
+  if (opt)
+    dfrl_mlp_params_changed(t->value);
+  return DFRL_OK;
 }
 
 // calculate_advantage (policy_gradient.h:220-281) with the current (updated) critic: writes t->adv.

@@ -575,15 +575,9 @@ extern "C" int dfrl_softmax_backward(dfrl_ctx *ctx, const float *x_dev, const fl
 // ------------------------------------------------------------------ xylo::model -------------
 static bool is_param(int kind) { return kind == DFRL_LAYER_DENSE || kind == DFRL_LAYER_CONV1D_1; }
 
-extern "C" int dfrl_mlp_create(dfrl_ctx *ctx, int n_layers, const int *kinds, const int *ins,
-                               const int *outs, int input_cols, dfrl_mlp **out) {
-  DFRL_CHECK(ctx && kinds && ins && outs && out, "null argument");
-  DFRL_CHECK(n_layers > 0 && n_layers <= 64 && input_cols > 0, "bad layer count / input width");
-  dfrl_mlp *m = new dfrl_mlp();
-  m->ctx = ctx;
-  m->input_cols = input_cols;
-  int cols = input_cols;
-  size_t poff = 0, woff = 0;
+// Appends `n_layers` layers to m (incoming width `cols`), parameters laid out from *poff / *woff on.
+static int append_layers(dfrl_mlp *m, int n_layers, const int *kinds, const int *ins, const int *outs, int cols,
+                         size_t *poff, size_t *woff) {
   for (int l = 0; l < n_layers; ++l) {
     mlp_layer L;
     L.kind = kinds[l];
@@ -591,45 +585,36 @@ extern "C" int dfrl_mlp_create(dfrl_ctx *ctx, int n_layers, const int *kinds, co
     L.out = outs[l];
     L.in_cols = cols;
     L.points = 1;
-    L.param_off = poff;
-    L.wt_off = woff;
+    L.param_off = *poff;
+    L.wt_off = *woff;
     if (L.kind == DFRL_LAYER_DENSE) {
-      if (L.in != cols) {
-        dfrl_set_error("layer %d: dense input %d != incoming width %d", l, L.in, cols);
-        delete m;
-        return DFRL_ERR_INVALID;
-      }
+      DFRL_CHECK(L.in == cols, "layer %d: dense input %d != incoming width %d", l, L.in, cols);
       L.out_cols = L.out;
     } else if (L.kind == DFRL_LAYER_CONV1D_1) {
-      if (L.in <= 0 || cols % L.in != 0) {
-        dfrl_set_error("layer %d: conv1d channels %d do not divide width %d", l, L.in, cols);
-        delete m;
-        return DFRL_ERR_INVALID;
-      }
+      DFRL_CHECK(L.in > 0 && cols % L.in == 0, "layer %d: conv1d channels %d do not divide width %d", l, L.in, cols);
       L.points = cols / L.in;
       L.out_cols = L.points * L.out;
-    } else if (L.kind == DFRL_LAYER_RELU || L.kind == DFRL_LAYER_SOFTMAX ||
-               L.kind == DFRL_LAYER_SOFTMAX_CE) {
+    } else if (L.kind == DFRL_LAYER_RELU || L.kind == DFRL_LAYER_SOFTMAX || L.kind == DFRL_LAYER_SOFTMAX_CE) {
       L.out_cols = cols;
     } else {
       dfrl_set_error("layer %d: unknown kind %d", l, L.kind);
-      delete m;
       return DFRL_ERR_INVALID;
     }
     if (is_param(L.kind)) {
-      if (L.out <= 0) {
-        dfrl_set_error("layer %d: bad output size", l);
-        delete m;
-        return DFRL_ERR_INVALID;
-      }
-      poff += (size_t)(L.in + 1) * L.out;
-      woff += (size_t)L.in * L.out;
+      DFRL_CHECK(L.out > 0, "layer %d: bad output size", l);
+      *poff += (size_t)(L.in + 1) * L.out;
+      *woff += (size_t)L.in * L.out;
     }
     cols = L.out_cols;
     m->layers.push_back(L);
   }
   m->output_cols = cols;
-  m->n_params = (int)poff;
+  return DFRL_OK;
+}
+
+static void init_mlp_fields(dfrl_mlp *m, dfrl_ctx *ctx, int input_cols) {
+  m->ctx = ctx;
+  m->input_cols = input_cols;
   m->params = nullptr;
   m->wt = nullptr;
   m->wt_dirty = true, m->version++;
@@ -637,10 +622,93 @@ extern "C" int dfrl_mlp_create(dfrl_ctx *ctx, int n_layers, const int *kinds, co
   m->act_arena_bytes = 0;
   m->kept_rows = 0;
   m->kept_input = nullptr;
+}
+
+extern "C" int dfrl_mlp_create(dfrl_ctx *ctx, int n_layers, const int *kinds, const int *ins,
+                               const int *outs, int input_cols, dfrl_mlp **out) {
+  DFRL_CHECK(ctx && kinds && ins && outs && out, "null argument");
+  DFRL_CHECK(n_layers > 0 && n_layers <= 64 && input_cols > 0, "bad layer count / input width");
+  dfrl_mlp *m = new dfrl_mlp();
+  init_mlp_fields(m, ctx, input_cols);
+  size_t poff = 0, woff = 0;
+  int rc = append_layers(m, n_layers, kinds, ins, outs, input_cols, &poff, &woff);
+  if (rc != DFRL_OK) {
+    delete m;
+    return rc;
+  }
+  m->n_params = (int)poff;
   m->acts.assign(n_layers, nullptr);
-  DFRL_CUDA(cudaMalloc(&m->params, sizeof(float) * (poff ? poff : 1)));
-  DFRL_CUDA(cudaMemsetAsync(m->params, 0, sizeof(float) * (poff ? poff : 1), ctx->stream));
-  DFRL_CUDA(cudaMalloc(&m->wt, sizeof(float) * (woff ? woff : 1)));
+  if (cudaMalloc(&m->params, sizeof(float) * (poff ? poff : 1)) != cudaSuccess ||
+      cudaMemsetAsync(m->params, 0, sizeof(float) * (poff ? poff : 1), ctx->stream) != cudaSuccess ||
+      cudaMalloc(&m->wt, sizeof(float) * (woff ? woff : 1)) != cudaSuccess) {
+    dfrl_set_error("dfrl_mlp_create: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFree(m->params);
+    cudaFree(m->wt);
+    delete m;
+    return DFRL_ERR_CUDA;
+  }
+  *out = m;
+  return DFRL_OK;
+}
+
+// Shared-trunk model (BASELINE configs[2]: "shared-trunk policy/value MLP"). The reference's `model`
+// is strictly sequential (nn.h:467-542) and its actor-critic mains build two separate nets
+// (ac_training.cc:9-25); this is the extension SURVEY section 8d asks for: a second model whose first
+// `n_shared` layers ARE the first layers of `trunk` -- same parameters, same memory -- followed by
+// its own head layers. Both models address one flat parameter vector
+//   [ trunk model's layers in the reference order | head layers of the sharer | ... ]
+// (dfrl_mlp_param_count / get / set_params of either model see the whole vector; a model's flat
+// gradient has zeros in the other heads' slots), so the learners' sequence "critic step, advantages
+// with the UPDATED critic, actor step" (policy_gradient.h:159-185) moves the trunk twice per
+// iteration, each time through the head whose loss is being optimised.
+extern "C" int dfrl_mlp_create_shared(dfrl_mlp *trunk, int n_shared, int n_layers, const int *kinds, const int *ins,
+                                      const int *outs, dfrl_mlp **out) {
+  DFRL_CHECK(trunk && kinds && ins && outs && out, "null argument");
+  dfrl_mlp *owner = trunk->share_owner ? trunk->share_owner : trunk;
+  DFRL_CHECK(n_shared > 0 && n_shared <= (int)trunk->layers.size(), "n_shared must be in 1..%d", (int)trunk->layers.size());
+  DFRL_CHECK(n_layers > 0 && n_shared + n_layers <= 64, "bad head layer count");
+  dfrl_ctx *ctx = owner->ctx;
+  dfrl_mlp *m = new dfrl_mlp();
+  init_mlp_fields(m, ctx, trunk->input_cols);
+  size_t woff = 0;
+  for (int l = 0; l < n_shared; ++l) {  // the trunk's layers: same parameter offsets, own transposed-weight cache
+    mlp_layer L = trunk->layers[l];
+    L.wt_off = woff;
+    if (is_param(L.kind))
+      woff += (size_t)L.in * L.out;
+    m->layers.push_back(L);
+  }
+  size_t poff = (size_t)owner->n_params;
+  int rc = append_layers(m, n_layers, kinds, ins, outs, trunk->layers[n_shared - 1].out_cols, &poff, &woff);
+  if (rc != DFRL_OK) {
+    delete m;
+    return rc;
+  }
+  // grow the family's flat vector by the head's parameters
+  float *grown = nullptr;
+  cudaStreamSynchronize(ctx->stream);
+  if (cudaMalloc(&grown, sizeof(float) * poff) != cudaSuccess || cudaMalloc(&m->wt, sizeof(float) * (woff ? woff : 1)) != cudaSuccess ||
+      cudaMemsetAsync(grown, 0, sizeof(float) * poff, ctx->stream) != cudaSuccess ||
+      cudaMemcpyAsync(grown, owner->params, sizeof(float) * (size_t)owner->n_params, cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess ||
+      cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+    dfrl_set_error("dfrl_mlp_create_shared: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFree(grown);
+    cudaFree(m->wt);
+    delete m;
+    return DFRL_ERR_CUDA;
+  }
+  cudaFree(owner->params);
+  m->share_owner = owner;
+  m->n_shared_layers = n_shared;
+  owner->sharers.push_back(m);
+  owner->params = grown;
+  owner->n_params = (int)poff;
+  for (dfrl_mlp *s : owner->sharers) {
+    s->params = grown;
+    s->n_params = (int)poff;
+  }
+  m->acts.assign(m->layers.size(), nullptr);
+  dfrl_mlp_params_changed(owner);
   *out = m;
   return DFRL_OK;
 }
@@ -648,8 +716,18 @@ extern "C" int dfrl_mlp_create(dfrl_ctx *ctx, int n_layers, const int *kinds, co
 extern "C" int dfrl_mlp_destroy(dfrl_mlp *m) {
   if (!m)
     return DFRL_OK;
+  DFRL_CHECK(m->sharers.empty(), "destroy the %d model(s) that share this model's trunk first", (int)m->sharers.size());
   cudaStreamSynchronize(m->ctx->stream);
-  cudaFree(m->params);
+  if (m->share_owner) {  // the family's parameter vector stays with its owner
+    std::vector<dfrl_mlp *> &v = m->share_owner->sharers;
+    for (size_t i = 0; i < v.size(); ++i)
+      if (v[i] == m) {
+        v.erase(v.begin() + i);
+        break;
+      }
+  } else {
+    cudaFree(m->params);
+  }
   cudaFree(m->wt);
   if (m->act_arena)
     cudaFree(m->act_arena);
@@ -661,7 +739,7 @@ extern "C" int dfrl_mlp_param_count(dfrl_mlp *m) { return m ? m->n_params : 0; }
 extern "C" int dfrl_mlp_output_cols(dfrl_mlp *m) { return m ? m->output_cols : 0; }
 extern "C" float *dfrl_mlp_params_dev(dfrl_mlp *m) {
   if (m)
-    m->wt_dirty = true, m->version++;  // the caller may write through the pointer
+    dfrl_mlp_params_changed(m);  // the caller may write through the pointer
   return m ? m->params : nullptr;
 }
 
@@ -671,7 +749,7 @@ extern "C" int dfrl_mlp_set_params(dfrl_mlp *m, const float *params_host, int n)
   DFRL_CUDA(cudaMemcpyAsync(m->params, params_host, sizeof(float) * n, cudaMemcpyHostToDevice,
                             m->ctx->stream));
   DFRL_CUDA(cudaStreamSynchronize(m->ctx->stream));
-  m->wt_dirty = true, m->version++;
+  dfrl_mlp_params_changed(m);
   return DFRL_OK;
 }
 extern "C" int dfrl_mlp_get_params(dfrl_mlp *m, float *params_host, int n) {
@@ -685,12 +763,12 @@ extern "C" int dfrl_mlp_get_params(dfrl_mlp *m, float *params_host, int n) {
 
 extern "C" int dfrl_mlp_init_params(dfrl_mlp *m, uint64_t seed) {
   DFRL_CHECK(m, "null model");
-  DFRL_CUDA(cudaMemsetAsync(m->params, 0, sizeof(float) * (m->n_params ? m->n_params : 1),
-                            m->ctx->stream));
-  for (size_t l = 0; l < m->layers.size(); ++l) {
+  // (a sharer initialises its own head layers only; the trunk belongs to the model it was built on)
+  for (size_t l = (size_t)m->n_shared_layers; l < m->layers.size(); ++l) {
     const mlp_layer &L = m->layers[l];
     if (!is_param(L.kind))
       continue;
+    DFRL_CUDA(cudaMemsetAsync(m->params + L.param_off, 0, sizeof(float) * (size_t)(L.in + 1) * L.out, m->ctx->stream));
     // normal_initialize: N(0, 0.01) regardless of fan-in (nn.h:12-14);
     // he_initialize: N(0, sqrt(2 / in_channels)) (nn.h:16-18)
     float sd = L.kind == DFRL_LAYER_DENSE ? 0.01f : sqrtf(2.0f / (float)L.in);
@@ -698,7 +776,7 @@ extern "C" int dfrl_mlp_init_params(dfrl_mlp *m, uint64_t seed) {
     DFRL_LAUNCH(m->ctx, init_normal_kernel, ceil_div(n, 256), 256, 0, m->params + L.param_off, n, sd,
                 seed, (uint32_t)l);
   }
-  m->wt_dirty = true, m->version++;
+  dfrl_mlp_params_changed(m);
   return DFRL_OK;
 }
 
@@ -794,6 +872,8 @@ int dfrl_mlp_backward(dfrl_mlp *m, const float *dy_dev, float *grad_dev) {
   dfrl_ctx *ctx = m->ctx;
   const int n = (int)m->layers.size();
   const int rows = m->kept_rows;
+  if (m->share_owner || !m->sharers.empty())  // the other heads' slots of the flat gradient are zero
+    DFRL_CUDA(cudaMemsetAsync(grad_dev, 0, sizeof(float) * (size_t)m->n_params, ctx->stream));
   int max_cols = m->input_cols;
   for (int l = 0; l < n; ++l)
     if (m->layers[l].out_cols > max_cols)

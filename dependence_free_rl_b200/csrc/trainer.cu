@@ -296,6 +296,12 @@ extern "C" int dfrl_trainer_create(dfrl_ctx *ctx, const dfrl_trainer_config *cfg
   DFRL_CUDA(cudaMalloc(&t->counters, sizeof(unsigned long long) * 8));
   DFRL_CUDA(cudaMemsetAsync(t->counters, 0, sizeof(unsigned long long) * 8, ctx->stream));
   DFRL_CUDA(cudaMalloc(&t->acc, sizeof(double) * 4));
+  {
+    const float ones[2] = {1.f, 1.f};  // nn.h:693
+    DFRL_CUDA(cudaMalloc(&t->adam_t_dev, sizeof(ones)));
+    DFRL_CUDA(cudaMemcpyAsync(t->adam_t_dev, ones, sizeof(ones), cudaMemcpyHostToDevice, ctx->stream));
+    DFRL_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
   DFRL_CUDA(cudaMalloc(&t->tape_items, LN));
   DFRL_CUDA(cudaMalloc(&t->tape_items2, LN));
   {
@@ -346,7 +352,7 @@ extern "C" int dfrl_trainer_destroy(dfrl_trainer *t) {
   dfrl_fused_detach(t);
   void *ptrs[] = {t->rec_state, t->rec_action, t->rec_done, t->rec_probs, t->rec_len, t->ep_done,
                   t->obs, t->v_start, t->v_end, t->targets, t->adv, t->dyv, t->dprobs, t->pgrad_log,
-                  t->vgrad, t->pstate, t->vstate, t->counters, t->acc, t->tape_items,
+                  t->vgrad, t->pstate, t->vstate, t->counters, t->acc, t->adam_t_dev, t->tape_items,
                   t->tape_actions, t->tape_u};
   for (void *p : ptrs)
     if (p)
@@ -495,7 +501,7 @@ static int apply_opt(dfrl_trainer *t, dfrl_mlp *m, int kind, float *grad, float 
                          t->cfg.adam_beta1, t->cfg.adam_beta2, *adam_t));
   if (kind == DFRL_OPT_ADAM)
     *adam_t += 1.f;  // nn.h:686
-  m->wt_dirty = true, m->version++;
+  dfrl_mlp_params_changed(m);
   return DFRL_OK;
 }
 
@@ -505,6 +511,8 @@ static bool fuse_opt(dfrl_trainer *t, dfrl_mlp *m, int kind, float *state, float
                      dfrl_opt_spec *spec) {
   if (t->ctx->nranks != 1 && !t->ctx->p2p.attached)
     return false;
+  // (the device-side counter mirrors the host's: both start at 1 and advance once per update)
+  spec->t_dev = kind == DFRL_OPT_ADAM ? t->adam_t_dev + (m == t->policy ? 0 : 1) : nullptr;
   spec->kind = kind;
   spec->params = m->params;
   spec->state = state;
@@ -644,13 +652,12 @@ static int learn_layered(dfrl_trainer *t) {
 // arguments (no host round trip, no memset / memcpy): it is captured once as a CUDA graph and
 // replayed, which removes the per-launch CPU and scheduling gaps that dominate at small
 // environment counts (C2: 11 launches of ~10 us each). Several ranks qualify when the gradient
-// exchange runs over attached peer memory (its exchange counter lives on the device). Not eligible:
-// NCCL exchanges, Adam (the bias corrections 1 - beta^t change every step), per-kernel profiling,
-// learners with host decisions inside the phase (REINFORCE, KL-PPO).
+// exchange runs over attached peer memory (its exchange counter lives on the device). Adam qualifies:
+// its step counter t lives on the device and the kernels derive the bias corrections 1 - beta^t from
+// it. Not eligible: NCCL exchanges, per-kernel profiling, learners with host decisions inside the
+// phase (REINFORCE, KL-PPO).
 static bool graph_eligible(const dfrl_trainer *t) {
-  const dfrl_trainer_config &c = t->cfg;
-  return dfrl_fused_covers_iteration(t) && (t->ctx->nranks == 1 || t->ctx->p2p.attached) && !t->ctx->profiling &&
-         c.policy_opt != DFRL_OPT_ADAM && c.value_opt != DFRL_OPT_ADAM;
+  return dfrl_fused_covers_iteration(t) && (t->ctx->nranks == 1 || t->ctx->p2p.attached) && !t->ctx->profiling;
 }
 
 static int learn_graphed(dfrl_trainer *t) {
@@ -691,9 +698,13 @@ static int learn_graphed(dfrl_trainer *t) {
   // the replay changed the parameters of both nets on the device: the host-side bookkeeping that
   // apply_opt / launch_reduce do launch by launch (transposed-weight cache of the layered kernels)
   // has to be repeated here, otherwise dfrl_mlp_eval / dfrl_eval_argmax keep using stale weights
-  t->policy->wt_dirty = true, t->policy->version++;
+  dfrl_mlp_params_changed(t->policy);
   if (t->value)
-    t->value->wt_dirty = true, t->value->version++;
+    dfrl_mlp_params_changed(t->value);
+  if (t->cfg.policy_opt == DFRL_OPT_ADAM)  // host mirrors of the device-side adam step counters
+    t->p_adam_t += (float)t->epochs;
+  if (t->cfg.value_opt == DFRL_OPT_ADAM)
+    t->v_adam_t += 1.f;
   return DFRL_OK;
 }
 

@@ -24,6 +24,7 @@ struct dfrl_trainer {
   float *pgrad_log, *vgrad;
   float *pstate, *vstate;
   float p_adam_t, v_adam_t, kl_beta;
+  float *adam_t_dev;  // [2] device-side adam step counters of the fused path (policy, value)
   // counters: [0] env steps, [1] episodes, [2] reward sum, [3] active envs (episodic rollouts)
   unsigned long long *counters;
   double *acc;  // [4] device accumulators (baseline, KL)
@@ -58,6 +59,9 @@ struct dfrl_opt_spec {
   int kind;
   float *params, *state;
   float lr, wd, beta1, beta2, c1, c2;
+  float *t_dev;  // adam: device-side step counter (float, starts at 1: nn.h:693); the kernel derives the
+                 // bias corrections from it and advances it, so the launch arguments stay constant
+                 // (CUDA-graph replay). null: c1 / c2 above are used.
 };
 
 // fused.cu

@@ -221,6 +221,15 @@ int dfrl_softmax_backward(dfrl_ctx *ctx, const float *x_dev, const float *dy_dev
 /* xylo::model (nn.h:467-542). conv1d layers take `points` from the preceding width. */
 int dfrl_mlp_create(dfrl_ctx *ctx, int n_layers, const int *kinds, const int *ins, const int *outs,
                     int input_cols, dfrl_mlp **out);
+/* Shared-trunk model (BASELINE.json configs[2] "shared-trunk policy/value MLP"; an EXTENSION: the
+ * reference's model is strictly sequential, nn.h:467-542, and ac_training.cc:9-25 builds two nets).
+ * The new model's first n_shared layers ARE the first n_shared layers of `trunk` (same parameters,
+ * same device memory), followed by n_layers own head layers. Every model of such a family addresses
+ * ONE flat parameter vector [trunk model's layers | head 1 | head 2 ...]: param_count / get / set see
+ * the whole vector, a model's flat gradient carries zeros in the other heads' slots, init_params of a
+ * sharer touches its own head only. Create sharers before any trainer; destroy them before `trunk`. */
+int dfrl_mlp_create_shared(dfrl_mlp *trunk, int n_shared, int n_layers, const int *kinds, const int *ins,
+                           const int *outs, dfrl_mlp **out);
 int dfrl_mlp_destroy(dfrl_mlp *mlp);
 int dfrl_mlp_param_count(dfrl_mlp *mlp);
 int dfrl_mlp_output_cols(dfrl_mlp *mlp);

@@ -302,7 +302,19 @@ static int layer_out_cols(const orc_net *net, int l, int in_cols) {
     return in_cols;
   }
 }
+/* Offset of layer l's parameters in the flat vector: explicit (shared-trunk nets) or the running sum
+ * of the reference's sequential layout. */
+static size_t layer_off(const orc_net *net, int l) {
+  if (net->n_params)
+    return (size_t)net->poff[l];
+  size_t off = 0;
+  for (int j = 0; j < l; ++j)
+    off += (size_t)layer_params(net, j);
+  return off;
+}
 int orc_net_param_count(const orc_net *net) {
+  if (net->n_params)
+    return net->n_params;
   int p = 0;
   for (int l = 0; l < net->n; ++l)
     p += layer_params(net, l);
@@ -338,12 +350,10 @@ void orc_net_eval(const orc_net *net, const float *params, const float *x, int r
   int cols = net->input_cols;
   const float *cur = x;
   float *bufs[2] = {NULL, NULL};
-  size_t off = 0;
   for (int l = 0; l < net->n; ++l) {
     int oc = layer_out_cols(net, l, cols);
     float *dst = (l == net->n - 1) ? y : (bufs[l & 1] = (float *)realloc(bufs[l & 1], sizeof(float) * (size_t)rows * oc));
-    layer_forward(net, l, params + off, cur, rows, cols, dst);
-    off += layer_params(net, l);
+    layer_forward(net, l, params + layer_off(net, l), cur, rows, cols, dst);
     cur = dst;
     cols = oc;
   }
@@ -361,13 +371,15 @@ void orc_net_forward_gradient(const orc_net *net, const float *params, const flo
   size_t poff[ORC_MAX_LAYERS + 1];
   acts[0] = (float *)x;
   cols[0] = net->input_cols;
-  poff[0] = 0;
+  poff[0] = layer_off(net, 0);
   for (int l = 0; l < n; ++l) {
     cols[l + 1] = layer_out_cols(net, l, cols[l]);
     acts[l + 1] = (float *)malloc(sizeof(float) * (size_t)rows * cols[l + 1]);
     layer_forward(net, l, params + poff[l], acts[l], rows, cols[l], acts[l + 1]);
-    poff[l + 1] = poff[l] + layer_params(net, l);
+    poff[l + 1] = l + 1 < n ? layer_off(net, l + 1) : 0;
   }
+  if (net->n_params) /* shared-trunk nets: the other net's slots of the flat gradient are zero */
+    memset(grad, 0, sizeof(float) * (size_t)net->n_params);
   if (out)
     memcpy(out, acts[n], sizeof(float) * (size_t)rows * cols[n]);
   float *back = (float *)malloc(sizeof(float) * (size_t)rows * cols[n]);

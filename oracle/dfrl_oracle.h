@@ -37,6 +37,14 @@ typedef struct {
   int in[ORC_MAX_LAYERS];
   int out[ORC_MAX_LAYERS];
   int input_cols;
+  /* Shared-trunk extension (BASELINE configs[2]; the reference's `model` is strictly sequential,
+   * nn.h:467-542, so this is hand-composed from its layer forward / backward / gradient, nn.h:20-33):
+   * n_params != 0 gives every parametric layer an explicit offset poff[l] into ONE flat vector of
+   * n_params floats that another net addresses too -- two nets whose first layers carry the same
+   * offsets share those layers. Gradients are n_params long with zeros in the other net's slots.
+   * n_params == 0: the reference's sequential layout [W out x in][b out] per layer (nn.h:56-59). */
+  int n_params;
+  int poff[ORC_MAX_LAYERS];
 } orc_net;
 
 typedef struct {

@@ -21,7 +21,9 @@ MAX_LAYERS = 16
 
 class NetC(C.Structure):
     _fields_ = [("n", C.c_int), ("kind", C.c_int * MAX_LAYERS), ("in_", C.c_int * MAX_LAYERS),
-                ("out", C.c_int * MAX_LAYERS), ("input_cols", C.c_int)]
+                ("out", C.c_int * MAX_LAYERS), ("input_cols", C.c_int),
+                # shared-trunk extension: explicit parameter offsets into one flat vector (0 = sequential)
+                ("n_params", C.c_int), ("poff", C.c_int * MAX_LAYERS)]
 
 
 class EnvCfgC(C.Structure):
@@ -92,6 +94,15 @@ class Net:
 
     def param_count(self):
         return lib().orc_net_param_count(C.byref(self.c))
+
+    def with_offsets(self, offsets, n_params):
+        """Explicit parameter offset per layer (None for activation layers) into ONE flat vector of
+        n_params floats: two nets that give their first layers the same offsets share a trunk."""
+        net = Net(self.layers, self.input_cols)
+        net.c.n_params = n_params
+        for i, o in enumerate(offsets):
+            net.c.poff[i] = 0 if o is None else o
+        return net
 
     def output_cols(self):
         return lib().orc_net_output_cols(C.byref(self.c))
@@ -315,9 +326,12 @@ class Learner:
     def __init__(self, tcfg, ecfg, pnet, pparams, vnet=None, vparams=None, kl_beta0=1.0, f64=False):
         self.t, self.e, self.pnet, self.vnet = tcfg, ecfg, pnet, vnet
         self.pparams = f32(pparams).copy()
-        self.vparams = None if vparams is None else f32(vparams).copy()
+        # shared-trunk nets (Net.with_offsets): pass vparams=None with a value net -> both nets
+        # address the SAME flat vector, so the critic step moves the trunk the actor step then sees
+        shared = vnet is not None and vparams is None
+        self.vparams = self.pparams if shared else (None if vparams is None else f32(vparams).copy())
         self.pstate = np.zeros(max(1, opt_state_size(tcfg.policy_opt, self.pparams.size)), np.float32)
-        self.vstate = np.zeros(max(1, opt_state_size(tcfg.value_opt, 0 if vparams is None else self.vparams.size)), np.float32)
+        self.vstate = np.zeros(max(1, opt_state_size(tcfg.value_opt, 0 if self.vparams is None else self.vparams.size)), np.float32)
         self.p_t, self.v_t = C.c_float(1.0), C.c_float(1.0)
         self.kl_beta = C.c_float(kl_beta0)
         self.f64 = f64
