@@ -81,24 +81,37 @@ __device__ __forceinline__ void gae_env(const uint8_t *__restrict__ done,
   }
 }
 
-// sgd (nn.h:622-625) / momentum (636-650) / adam (666-690) update of element i.
+// sgd (nn.h:622-625) / momentum (636-650) / adam (666-690: eps 1e-7 outside the sqrt, bias
+// corrections c1 = 1 - beta1^t, c2 = 1 - beta2^t) on values: p = parameter, g = gradient, m / v = the
+// element's optimizer state (momentum: m only).
+__device__ __forceinline__ void opt_update_vals(int kind, float &p, float g, float &m, float &v, float lr, float wd,
+                                                float beta1, float beta2, float c1, float c2) {
+  if (kind == DFRL_OPT_SGD) {
+    p = p * (1.f - wd) - g * lr;
+  } else if (kind == DFRL_OPT_MOMENTUM) {
+    m = m * 0.9f + g;
+    p = p - m * lr;
+  } else {
+    m = m * beta1 + g * (1.f - beta1);
+    v = v * beta2 + g * g * (1.f - beta2);
+    float mu = m / c1, vu = v / c2;
+    p = p - mu * lr / (sqrtf(vu) + 1e-7f);
+  }
+}
+// The same on element i of the flat vectors (state = [m (n)][v (n)]).
 __device__ __forceinline__ void opt_update(int kind, float *__restrict__ params,
                                            const float *__restrict__ grad,
                                            float *__restrict__ state, int n, int i, float lr,
                                            float wd, float beta1, float beta2, float c1, float c2) {
-  float g = grad[i], p = params[i];
-  if (kind == DFRL_OPT_SGD) {
-    params[i] = p * (1.f - wd) - g * lr;
-  } else if (kind == DFRL_OPT_MOMENTUM) {
-    float v = state[i] * 0.9f + g;
-    state[i] = v;
-    params[i] = p - v * lr;
-  } else {
-    float m = state[i] * beta1 + g * (1.f - beta1);
-    float v = state[n + i] * beta2 + g * g * (1.f - beta2);
+  float p = params[i], m = 0.f, v = 0.f;
+  if (kind != DFRL_OPT_SGD)
+    m = state[i];
+  if (kind == DFRL_OPT_ADAM)
+    v = state[n + i];
+  opt_update_vals(kind, p, grad[i], m, v, lr, wd, beta1, beta2, c1, c2);
+  params[i] = p;
+  if (kind != DFRL_OPT_SGD)
     state[i] = m;
+  if (kind == DFRL_OPT_ADAM)
     state[n + i] = v;
-    float mu = m / c1, vu = v / c2;
-    params[i] = p - mu * lr / (sqrtf(vu) + 1e-7f);
-  }
 }

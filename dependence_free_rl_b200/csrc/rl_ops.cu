@@ -125,6 +125,94 @@ __global__ void opt_kernel(int kind, float *__restrict__ params, const float *__
   opt_update(kind, params, grad, state, n, i, lr, wd, beta1, beta2, c1, c2);
 }
 
+// K7 on large parameter vectors: HBM-bound (sgd 12 B / parameter, momentum 20, adam 28). Four
+// parameters per thread as 16-byte accesses, two independent groups in flight per thread,
+// grid-stride over a grid of a few CTAs per SM. n % 4 == 0 and 16-byte aligned pointers.
+__global__ void __launch_bounds__(256) opt_vec4_kernel(int kind, float4 *__restrict__ params, const float4 *__restrict__ grad,
+                                                       float4 *__restrict__ m4, float4 *__restrict__ v4, int n4, float lr,
+                                                       float wd, float beta1, float beta2, float c1, float c2) {
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += 2 * stride) {
+    const int j = i + stride;
+    const bool two = j < n4;
+    float4 p0 = params[i], g0 = __ldg(grad + i), p1, g1;
+    float4 ma = make_float4(0, 0, 0, 0), va = ma, mb = ma, vb = ma;
+    if (two)
+      p1 = params[j], g1 = __ldg(grad + j);
+    if (kind != DFRL_OPT_SGD) {
+      ma = m4[i];
+      if (two)
+        mb = m4[j];
+    }
+    if (kind == DFRL_OPT_ADAM) {
+      va = v4[i];
+      if (two)
+        vb = v4[j];
+    }
+    opt_update_vals(kind, p0.x, g0.x, ma.x, va.x, lr, wd, beta1, beta2, c1, c2);
+    opt_update_vals(kind, p0.y, g0.y, ma.y, va.y, lr, wd, beta1, beta2, c1, c2);
+    opt_update_vals(kind, p0.z, g0.z, ma.z, va.z, lr, wd, beta1, beta2, c1, c2);
+    opt_update_vals(kind, p0.w, g0.w, ma.w, va.w, lr, wd, beta1, beta2, c1, c2);
+    params[i] = p0;
+    if (kind != DFRL_OPT_SGD)
+      m4[i] = ma;
+    if (kind == DFRL_OPT_ADAM)
+      v4[i] = va;
+    if (two) {
+      opt_update_vals(kind, p1.x, g1.x, mb.x, vb.x, lr, wd, beta1, beta2, c1, c2);
+      opt_update_vals(kind, p1.y, g1.y, mb.y, vb.y, lr, wd, beta1, beta2, c1, c2);
+      opt_update_vals(kind, p1.z, g1.z, mb.z, vb.z, lr, wd, beta1, beta2, c1, c2);
+      opt_update_vals(kind, p1.w, g1.w, mb.w, vb.w, lr, wd, beta1, beta2, c1, c2);
+      params[j] = p1;
+      if (kind != DFRL_OPT_SGD)
+        m4[j] = mb;
+      if (kind == DFRL_OPT_ADAM)
+        v4[j] = vb;
+    }
+  }
+}
+
+// K4 on large batches: four environments per thread (16-byte value loads, 4-byte done loads);
+// same recurrence as gae_env. n % 4 == 0.
+__global__ void __launch_bounds__(256) gae_vec4_kernel(const uint8_t *__restrict__ done, const float *__restrict__ v_start,
+                                                       const float *__restrict__ v_end, int n, int T, float gamma, float lambda,
+                                                       float *__restrict__ targets, float *__restrict__ adv) {
+  const int i = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+  if (i >= n)
+    return;
+  float a_next[4] = {0.f, 0.f, 0.f, 0.f};
+  float4 vs_next = make_float4(0, 0, 0, 0);  // v_start of step t + 1 (already loaded)
+  for (int t = T - 1; t >= 0; --t) {
+    const size_t k = (size_t)t * n + i;
+    const uint32_t d4 = *reinterpret_cast<const uint32_t *>(done + k);
+    const float4 vs4 = *reinterpret_cast<const float4 *>(v_start + k);
+    const bool last = t == T - 1;
+    float4 ve4 = make_float4(0, 0, 0, 0);
+    if (last || d4)  // v_end is only defined / needed where a trajectory ends
+      ve4 = *reinterpret_cast<const float4 *>(v_end + k);
+    const float vs[4] = {vs4.x, vs4.y, vs4.z, vs4.w}, ve[4] = {ve4.x, ve4.y, ve4.z, ve4.w};
+    const float vn1[4] = {vs_next.x, vs_next.y, vs_next.z, vs_next.w};
+    float tg[4], ad[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int d = (d4 >> (8 * e)) & 0xff;
+      const bool ends = d || last;
+      const float r = d ? 0.f : 1.f;
+      const float vn = ends ? ve[e] : vn1[e];
+      tg[e] = r + gamma * vn;  // NOT masked at terminals (quirk 6)
+      const float vn_adv = d ? 0.f : vn;
+      const float delta = r + gamma * vn_adv - vs[e];
+      ad[e] = delta + (ends ? 0.f : lambda * gamma * a_next[e]);
+      a_next[e] = ad[e];
+    }
+    if (targets)
+      *reinterpret_cast<float4 *>(targets + k) = make_float4(tg[0], tg[1], tg[2], tg[3]);
+    if (adv)
+      *reinterpret_cast<float4 *>(adv + k) = make_float4(ad[0], ad[1], ad[2], ad[3]);
+    vs_next = vs4;
+  }
+}
+
 }  // namespace
 
 extern "C" int dfrl_sample(dfrl_ctx *ctx, const float *probs_dev, int rows, int cols,
@@ -170,8 +258,14 @@ extern "C" int dfrl_gae(dfrl_ctx *ctx, const uint8_t *done_dev, const float *v_s
                         float *targets_dev, float *adv_dev) {
   DFRL_CHECK(ctx && done_dev && v_start_dev && v_end_dev, "null argument");
   DFRL_CHECK(n_envs > 0 && T > 0, "bad shape");
-  DFRL_LAUNCH(ctx, gae_kernel, ceil_div(n_envs, 128), 128, 0, done_dev, v_start_dev, v_end_dev,
-              n_envs, T, gamma, lambda, targets_dev, adv_dev);
+  auto al16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (n_envs % 4 == 0 && n_envs >= (1 << 14) && al16(v_start_dev) && al16(v_end_dev) && al16(targets_dev) && al16(adv_dev) &&
+      (reinterpret_cast<uintptr_t>(done_dev) & 3) == 0)
+    DFRL_LAUNCH(ctx, gae_vec4_kernel, ceil_div(n_envs / 4, 256), 256, 0, done_dev, v_start_dev, v_end_dev, n_envs, T, gamma,
+                lambda, targets_dev, adv_dev);
+  else
+    DFRL_LAUNCH(ctx, gae_kernel, ceil_div(n_envs, 128), 128, 0, done_dev, v_start_dev, v_end_dev,
+                n_envs, T, gamma, lambda, targets_dev, adv_dev);
   return DFRL_OK;
 }
 
@@ -208,7 +302,18 @@ extern "C" int dfrl_opt_step(dfrl_ctx *ctx, int kind, float *params_dev, const f
     return DFRL_OK;
   // bias corrections as the reference computes them on the host: 1 - powf(beta, t) (nn.h:683-684)
   float c1 = 1.f - powf(beta1, adam_t), c2 = 1.f - powf(beta2, adam_t);
-  DFRL_LAUNCH(ctx, opt_kernel, ceil_div(n, 256), 256, 0, kind, params_dev, grad_dev, state_dev, n,
-              lr, weight_decay, beta1, beta2, c1, c2);
+  auto al16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (n % 4 == 0 && n >= (1 << 16) && al16(params_dev) && al16(grad_dev) && al16(state_dev)) {
+    const int n4 = n / 4;
+    int grid = ceil_div(n4, 2 * 256);
+    if (grid > 8 * ctx->sm_count)
+      grid = 8 * ctx->sm_count;
+    DFRL_LAUNCH(ctx, opt_vec4_kernel, grid, 256, 0, kind, reinterpret_cast<float4 *>(params_dev),
+                reinterpret_cast<const float4 *>(grad_dev), reinterpret_cast<float4 *>(state_dev),
+                reinterpret_cast<float4 *>(state_dev ? state_dev + n : nullptr), n4, lr, weight_decay, beta1, beta2, c1, c2);
+  } else {
+    DFRL_LAUNCH(ctx, opt_kernel, ceil_div(n, 256), 256, 0, kind, params_dev, grad_dev, state_dev, n,
+                lr, weight_decay, beta1, beta2, c1, c2);
+  }
   return DFRL_OK;
 }

@@ -291,7 +291,8 @@ def test_sampling_bit_exact_vs_oracle_and_reference(D, ctx, orc):
 
 # ------------------------------------------------------------------------- K4 returns/GAE ---
 
-@pytest.mark.parametrize("n,T", [(1, 4), (257, 4), (1000, 8), (64, 33)])
+# (the last two sizes take the 4-envs-per-thread kernel: n % 4 == 0, n >= 16384)
+@pytest.mark.parametrize("n,T", [(1, 4), (257, 4), (1000, 8), (64, 33), (16384, 4), (65540, 8)])
 def test_gae_vs_oracle(D, ctx, orc, n, T):
     lib, chk = D._lib.lib, D._lib.check
     rng = np.random.default_rng(n + T)
@@ -355,6 +356,25 @@ def test_optimizers_vs_reference_golden(D, ctx, key, kind, wd):
         chk(lib.dfrl_opt_step(ctx.h, kind, p.p, dg.p, state.p, 50, 1e-2, wd, 0.9, 0.999, t))
         t += 1.0
         close(p.get(), U[key][k], what=f"{key} step {k}")
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_optimizers_large_vector_vs_oracle(D, ctx, orc, kind):
+    # n >= 65536, n % 4 == 0: the 16-byte vectorised kernel (the golden vectors above take the scalar one)
+    lib, chk = D._lib.lib, D._lib.check
+    n = (1 << 17) + 8
+    rng = np.random.default_rng(kind)
+    p0 = rng.standard_normal(n).astype(np.float32)
+    want, wstate = p0.copy(), np.zeros(2 * n, np.float32)
+    p, state = ctx.to_device(p0), ctx.zeros((2 * n,), np.float32)
+    for k in range(3):
+        g = rng.standard_normal(n).astype(np.float32)
+        dg = ctx.to_device(g)
+        chk(lib.dfrl_opt_step(ctx.h, kind, p.p, dg.p, state.p, n, 1e-2, 1e-3 if kind == 0 else 0.0, 0.9, 0.999, 1.0 + k))
+        orc.opt_step(kind, want, g, wstate, 1e-2, wd=1e-3 if kind == 0 else 0.0, t=1.0 + k)
+        close(p.get(), want, what=f"optimizer {kind} step {k}")
+        dg.free()
+    p.free(); state.free()
 
 
 # ------------------------------------------------------------------------- whole learners ---

@@ -22,6 +22,17 @@ def curve(ctx, nets, n=4096, T=4, iters=5000, every=250, seed=1234, lr_scale=1.0
         value = D.Model(ctx, D.fc_layers([32, 64, 64, 1]), 32)
     policy.init_parameters(seed)
     value.init_parameters(seed + 1)
+    if nets != "reference":
+        # He-scaled dense weights: the reference's N(0, 0.01) dense init (nn.h:12-14) leaves a 3-layer FC
+        # net without signal for ~10^5 rounds (its own PPO main uses the He-initialised conv1d net)
+        import numpy as np
+
+        def he_fc(dims, s):
+            r = np.random.default_rng(s)
+            return np.concatenate([np.concatenate([(r.standard_normal(a * b) * np.sqrt(2.0 / a)).astype(np.float32),
+                                                   np.zeros(b, np.float32)]) for a, b in zip(dims[:-1], dims[1:])])
+        policy.set_parameters(he_fc([32, 64, 64, 8], seed))
+        value.set_parameters(he_fc([32, 64, 64, 1], seed + 1))
     env = D.Environment(ctx, n, seed=seed)
     rows = n * T
     tr = D.Trainer(ctx, env, policy, value, algo=D.PPO, work=T, policy_lr=lr_scale * 1e-4 * 32 / rows,
@@ -48,7 +59,7 @@ if __name__ == "__main__":
     ctx = D.Context(0)
     with open(os.path.join(ROOT, "profiles", "r02_convergence_gpu.csv"), "w") as f:
         f.write("nets,iterations,env_steps,mean_reward_argmax_2048ep\n")
-        for nets in ("reference", "c2_fused"):
+        for nets in ("reference", "c2_fused_he_init"):
             for it, steps, mean in curve(ctx, nets, iters=iters, every=every):
                 f.write(f"{nets},{it},{steps},{mean:.4f}\n")
                 f.flush()
