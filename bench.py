@@ -251,13 +251,17 @@ def hbm_kernel_rows(D, ctx, peaks):
     for o in (act, done):
         o.free()
     env.close()
-    # K4 GAE on [T][n] records, T = 4, 16 Mi envs
+    # K4 GAE on [T][n] records, T = 4, 16 Mi envs, 8 % of the steps end an episode (random-policy level)
     T, n = 4, 1 << 24
-    d = ctx.zeros((T, n), np.uint8)
+    dh = (np.random.default_rng(1).random((T, n), dtype=np.float32) < 0.08).astype(np.uint8)
+    ends = int(dh[:T - 1].sum()) + n           # rows whose V(next) comes from v_end: done, or the last step
+    d = ctx.to_device(dh)
     vs, ve = ctx.zeros((T, n), np.float32), ctx.zeros((T, n), np.float32)
     tg, adv = ctx.empty((T, n), np.float32), ctx.empty((T, n), np.float32)
     ms = timed(lambda: chk(lib.dfrl_gae(ctx.h, d.p, vs.p, ve.p, n, T, C.c_float(0.99), C.c_float(0.95), tg.p, adv.p)), 10)
-    row("gae_kernel", ms, T * n * 17, "16 Mi envs x T=4: done + V_t + V_t+1 read, target + advantage written = 17 B/row (K4)")
+    row("gae_kernel", ms, T * n * 13 + 4 * ends,
+        "16 Mi envs x T=4: done + V_t read, target + advantage written = 13 B/row, + 4 B of V(end) for the "
+        f"{100.0 * ends / (T * n):.0f} % of rows that end a trajectory (SURVEY 8d K4 counts 17 B/row: V_t+1 re-read)")
     for o in (d, vs, ve, tg, adv):
         o.free()
     # K7 optimizers, 64 Mi parameters

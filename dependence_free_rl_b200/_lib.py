@@ -68,6 +68,7 @@ PROTOTYPES = {
     "dfrl_debug_policy_clocks": (i32, [vp, vp, i32]),
     "dfrl_debug_critic_clocks": (i32, [vp, vp, i32]),
     "dfrl_debug_set_fused_ctas": (i32, [vp, i32]),
+    "dfrl_debug_set_vend": (i32, [vp, i32]),
     "dfrl_p2p_export": (i32, [vp, vp]),
     "dfrl_p2p_attach": (i32, [vp, vp]),
     "dfrl_p2p_attached": (i32, [vp]),

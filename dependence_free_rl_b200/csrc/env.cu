@@ -75,9 +75,12 @@ __global__ void env_step_scalar_kernel(env_params p, int8_t *__restrict__ state,
 }
 
 // Vector step: B compile-time, 4 envs per thread, every plane read and written as one 32-bit
-// word per thread (128 B per warp per plane, fully coalesced).
-template <int B>
-__global__ void __launch_bounds__(256)
+// word per thread (128 B per warp per plane, fully coalesced). The four environments of a word are
+// stepped together with byte-wise SIMD integer instructions (per bin: select mask = action == b,
+// subtract the masked item, collect the sign bits of the selected bin) and, on the Philox path,
+// share one Philox block for their next items. TERM: also write the overflowed terminal states.
+template <int B, bool TERM>
+__global__ void __launch_bounds__(256, B == 8 ? 3 : 1)
 env_step_vec4_kernel(env_params p, int8_t *__restrict__ state, uint32_t *__restrict__ draws,
                      uint32_t *__restrict__ steps, const uint8_t *__restrict__ actions,
                      uint8_t *__restrict__ done_out, int8_t *__restrict__ terminal) {
@@ -92,13 +95,9 @@ env_step_vec4_kernel(env_params p, int8_t *__restrict__ state, uint32_t *__restr
   for (int q = 0; q < P; ++q)
     w[q] = *reinterpret_cast<const uint32_t *>(state + (size_t)q * S + i0);
   uint32_t act4 = *reinterpret_cast<const uint32_t *>(actions + i0);  // actions padded to stride
-  uint32_t done4 = 0;
-  uint32_t t[P];
-#pragma unroll
-  for (int q = 0; q < P; ++q)
-    t[q] = w[q];
+  act4 = __vminu4(act4, (uint32_t)(B - 1) * 0x01010101u);
+  const bool full = i0 + 3 < p.n;
   uint4 dr = make_uint4(0, 0, 0, 0), st = make_uint4(0, 0, 0, 0);
-  bool full = i0 + 3 < p.n;
   if (full) {
     dr = *reinterpret_cast<const uint4 *>(draws + i0);
     st = *reinterpret_cast<const uint4 *>(steps + i0);
@@ -109,63 +108,62 @@ env_step_vec4_kernel(env_params p, int8_t *__restrict__ state, uint32_t *__restr
       s[e] = steps[i0 + e];
     }
   }
-  uint32_t *drp = &dr.x, *stp = &st.x;
+  // environment::apply (bin_packing.h:53-64): bin[a] -= item; over = the selected bin went negative
+  const uint32_t iw4 = w[2 * B], ih4 = w[2 * B + 1];
+  uint32_t neg = 0;
 #pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    if (i0 + e >= p.n)
-      break;
-    const int sh = 8 * e;
-    int a = (act4 >> sh) & 0xff;
-    a = a < B ? a : B - 1;
-    int iw = (int8_t)(w[2 * B] >> sh), ih = (int8_t)(w[2 * B + 1] >> sh);
-    int bw = 0, bh = 0;
-#pragma unroll
-    for (int b = 0; b < B; ++b) {
-      if (b == a) {
-        bw = (int8_t)(w[2 * b] >> sh);
-        bh = (int8_t)(w[2 * b + 1] >> sh);
-      }
-    }
-    bw -= iw;
-    bh -= ih;
-    bool over = bw < 0 || bh < 0;
-    done4 |= (over ? 1u : 0u) << sh;
-    int s1 = draw_shape1(p, i0 + e, drp[e]);
-    drp[e] += 1;
-    stp[e] += 1;
-    const uint32_t m = 0xffu << sh;
-#pragma unroll
-    for (int b = 0; b < B; ++b) {
-      if (b == a) {
-        t[2 * b] = (t[2 * b] & ~m) | (((uint32_t)bw & 0xff) << sh);
-        t[2 * b + 1] = (t[2 * b + 1] & ~m) | (((uint32_t)bh & 0xff) << sh);
-      }
-      uint32_t nw = over ? (uint32_t)p.cap_w : (b == a ? (uint32_t)bw & 0xff : (w[2 * b] >> sh) & 0xff);
-      uint32_t nh = over ? (uint32_t)p.cap_h : (b == a ? (uint32_t)bh & 0xff : (w[2 * b + 1] >> sh) & 0xff);
-      w[2 * b] = (w[2 * b] & ~m) | (nw << sh);
-      w[2 * b + 1] = (w[2 * b + 1] & ~m) | (nh << sh);
-    }
-    uint32_t niw = (uint32_t)(s1 ? p.iw0 : p.iw1) & 0xff, nih = (uint32_t)(s1 ? p.ih0 : p.ih1) & 0xff;
-    w[2 * B] = (w[2 * B] & ~m) | (niw << sh);
-    w[2 * B + 1] = (w[2 * B + 1] & ~m) | (nih << sh);
+  for (int b = 0; b < B; ++b) {
+    const uint32_t sel = __vcmpeq4(act4, (uint32_t)b * 0x01010101u);  // 0xff in the bytes whose action is b
+    const uint32_t nw = __vsub4(w[2 * b], iw4 & sel), nh = __vsub4(w[2 * b + 1], ih4 & sel);
+    neg |= (nw | nh) & sel;
+    w[2 * b] = nw;
+    w[2 * b + 1] = nh;
   }
+  const uint32_t om = __vcmplts4(neg, 0u);  // 0xff in the bytes of the environments whose episode ended
+  if (TERM) {  // the terminal state keeps its item (bin_packing.h:59-61)
+#pragma unroll
+    for (int q = 0; q < P; ++q)
+      *reinterpret_cast<uint32_t *>(terminal + (size_t)q * S + i0) = w[q];
+  }
+  if (done_out)
+    *reinterpret_cast<uint32_t *>(done_out + i0) = om & 0x01010101u;
+  // reset-on-done (rl.h:341-346, bin_packing.h:67-70)
+  const uint32_t cw4 = ((uint32_t)p.cap_w & 0xffu) * 0x01010101u, ch4 = ((uint32_t)p.cap_h & 0xffu) * 0x01010101u;
+#pragma unroll
+  for (int b = 0; b < B; ++b) {
+    w[2 * b] = (w[2 * b] & ~om) | (cw4 & om);
+    w[2 * b + 1] = (w[2 * b + 1] & ~om) | (ch4 & om);
+  }
+  // next items (drawn after every step, also after a reset: bin_packing.h:62, 69)
+  uint32_t s1m = 0;  // 0xff in the bytes that draw shape 1
+  const uint64_t g0 = (uint64_t)(p.env_offset + i0);
+  uint32_t *drp = &dr.x, *stp = &st.x;
+  if (!p.tape && full && (g0 & 3) == 0 && dr.x == dr.y && dr.x == dr.z && dr.x == dr.w) {
+    const philox4 r = item_block(p, g0 >> 2, dr.x);
+    s1m = (r.x < p.thr ? 0xffu : 0u) | (r.y < p.thr ? 0xff00u : 0u) | (r.z < p.thr ? 0xff0000u : 0u) |
+          (r.w < p.thr ? 0xff000000u : 0u);
+  } else {
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (i0 + e < p.n && draw_shape1(p, i0 + e, drp[e]))
+        s1m |= 0xffu << (8 * e);
+  }
+  const uint32_t iw0 = ((uint32_t)p.iw0 & 0xffu) * 0x01010101u, iw1 = ((uint32_t)p.iw1 & 0xffu) * 0x01010101u;
+  const uint32_t ih0 = ((uint32_t)p.ih0 & 0xffu) * 0x01010101u, ih1 = ((uint32_t)p.ih1 & 0xffu) * 0x01010101u;
+  w[2 * B] = (iw0 & s1m) | (iw1 & ~s1m);
+  w[2 * B + 1] = (ih0 & s1m) | (ih1 & ~s1m);
 #pragma unroll
   for (int q = 0; q < P; ++q)
     *reinterpret_cast<uint32_t *>(state + (size_t)q * S + i0) = w[q];
-  if (terminal) {
-#pragma unroll
-    for (int q = 0; q < P; ++q)
-      *reinterpret_cast<uint32_t *>(terminal + (size_t)q * S + i0) = t[q];
-  }
-  if (done_out)
-    *reinterpret_cast<uint32_t *>(done_out + i0) = done4;
   if (full) {
+    dr.x += 1, dr.y += 1, dr.z += 1, dr.w += 1;
+    st.x += 1, st.y += 1, st.z += 1, st.w += 1;
     *reinterpret_cast<uint4 *>(draws + i0) = dr;
     *reinterpret_cast<uint4 *>(steps + i0) = st;
   } else {
     for (int e = 0; e < 4 && i0 + e < p.n; ++e) {
-      draws[i0 + e] = drp[e];
-      steps[i0 + e] = stp[e];
+      draws[i0 + e] = drp[e] + 1;
+      steps[i0 + e] = stp[e] + 1;
     }
   }
 }
@@ -412,15 +410,22 @@ int dfrl_env_step_internal(dfrl_env *e, const uint8_t *actions_dev, uint8_t *don
   bool vec = actions_padded && (((uintptr_t)actions_dev) % 4 == 0) &&
              (!done_dev || ((uintptr_t)done_dev) % 4 == 0);
   int groups = ceil_div(e->n, 4);
+#define DFRL_ENV_VEC4(BINS)                                                                                     \
+  do {                                                                                                          \
+    if (terminal_dev)                                                                                           \
+      DFRL_LAUNCH(e->ctx, (env_step_vec4_kernel<BINS, true>), ceil_div(groups, 256), 256, 0, p, e->state, e->draws, \
+                  e->steps, actions_dev, done_dev, terminal_dev);                                               \
+    else                                                                                                        \
+      DFRL_LAUNCH(e->ctx, (env_step_vec4_kernel<BINS, false>), ceil_div(groups, 256), 256, 0, p, e->state, e->draws, \
+                  e->steps, actions_dev, done_dev, terminal_dev);                                               \
+  } while (0)
   if (vec && e->B == 8) {
-    DFRL_LAUNCH(e->ctx, env_step_vec4_kernel<8>, ceil_div(groups, 256), 256, 0, p, e->state,
-                e->draws, e->steps, actions_dev, done_dev, terminal_dev);
+    DFRL_ENV_VEC4(8);
   } else if (vec && e->B == 16) {
-    DFRL_LAUNCH(e->ctx, env_step_vec4_kernel<16>, ceil_div(groups, 256), 256, 0, p, e->state,
-                e->draws, e->steps, actions_dev, done_dev, terminal_dev);
+    DFRL_ENV_VEC4(16);
   } else if (vec && e->B == 32) {
-    DFRL_LAUNCH(e->ctx, env_step_vec4_kernel<32>, ceil_div(groups, 256), 256, 0, p, e->state,
-                e->draws, e->steps, actions_dev, done_dev, terminal_dev);
+    DFRL_ENV_VEC4(32);
+#undef DFRL_ENV_VEC4
   } else {
     DFRL_LAUNCH(e->ctx, env_step_scalar_kernel, ceil_div(e->n, 256), 256, 0, p, e->state, e->draws,
                 e->steps, actions_dev, done_dev, terminal_dev);

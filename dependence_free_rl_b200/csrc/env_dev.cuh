@@ -15,11 +15,22 @@ struct env_params {
   int tape_len;
 };
 
+// Item stream (bin_packing.h:73-81: bernoulli(0.4) ? shape1 : shape2): one Philox4x32-10 block per
+// (group of 4 consecutive GLOBAL env ids, draw index), env g takes word g % 4 of the block of group
+// g / 4 -- still a pure function of (seed, global env id, draw index), so results do not depend on how
+// the environments are sharded over ranks, and a thread that steps 4 consecutive environments needs
+// one block instead of four.
+__device__ __forceinline__ philox4 item_block(const env_params &p, uint64_t global_group, uint32_t k) {
+  return philox4x32_10(p.seed, global_group, k, DFRL_STREAM_ITEM);
+}
+__device__ __forceinline__ uint32_t block_word(const philox4 &r, int lane) {
+  return lane == 0 ? r.x : lane == 1 ? r.y : lane == 2 ? r.z : r.w;
+}
 __device__ __forceinline__ int draw_shape1(const env_params &p, int i, uint32_t k) {
   if (p.tape)
     return p.tape[(size_t)i * p.tape_len + (k < (uint32_t)p.tape_len ? k : p.tape_len - 1)] != 0;
-  philox4 r = philox4x32_10(p.seed, (uint64_t)(p.env_offset + i), k, DFRL_STREAM_ITEM);
-  return r.x < p.thr;
+  const uint64_t g = (uint64_t)(p.env_offset + i);
+  return block_word(item_block(p, g >> 2, k), (int)(g & 3)) < p.thr;
 }
 
 

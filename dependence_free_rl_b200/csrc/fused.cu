@@ -247,6 +247,8 @@ struct critic_args {
   float gamma, lambda;
   float *targets_out;  // [T][n] (critic step) -- introspection + parity
   float *adv_out;      // [T][n] (GAE kernel)
+  const float *v_end;  // [T][n] V(end state) where a trajectory ends, from fused_vend_kernel; null: the
+                       // kernel runs its own end pass over all rows of every tile
   float *partials;
   grad_tail tail;      // critic step only
   long long *clk;      // optional: phase clocks of CTA 0, pipeline 0 (debug; critic step only)
@@ -1189,7 +1191,7 @@ __device__ __forceinline__ float epi2_value(uint32_t acc, const tid_t &t, const 
   return s + b3;
 }
 
-template <int D0, int D1, int D2, int MODE>
+template <int D0, int D1, int D2, int MODE, bool EG>
 __global__ void __launch_bounds__((cmap<D1, D2, MODE>::THREADS), 1) fused_critic_kernel(critic_args a) {
   using CM = cmap<D1, D2, MODE>;
   constexpr int NP = CM::NP, NH = CM::NH;
@@ -1252,6 +1254,10 @@ __global__ void __launch_bounds__((cmap<D1, D2, MODE>::THREADS), 1) fused_critic
   uint64_t *bar = bars + wg, *bar_dw2 = bars + NP + wg, *bar_dw1 = bars + 2 * NP + wg, *bar_l1s = bars + 3 * NP + wg,
            *bar_slot = bars + 4 * NP;
   uint32_t rp = 0;
+  // eg: V(end) comes from global memory (fused_vend_kernel ran on the compacted end rows): no end pass.
+  // A tile is then  layer 1 (start rows, staged in H1_LO ahead of the previous tile's dW1 GEMM, as in
+  // fused_policy_step_kernel) -> layer 2 -> values -> ...
+  constexpr bool eg = EG;  // (a.v_end is set)
   // dW3 partial sums. One thread per row: this thread's row-sums of all D2 columns. Two threads per
   // row: ONE register -- after every tile the 32 lanes of a warp transpose-reduce their 32 columns
   // (butterfly, fixed order), lane l keeps column 32 half + l summed over the warp's rows (32
@@ -1277,20 +1283,22 @@ __global__ void __launch_bounds__((cmap<D1, D2, MODE>::THREADS), 1) fused_critic
     };
     bool first = true;
     if (wg < nt) {
-      ready_sync(wg, rp, RT);  // end-row observations of the first tile staged in the H1_LO panel
+      ready_sync(wg, rp, RT);  // observations of the first tile (end rows; eg: start rows) staged in the H1_LO panel
       if (umma::elect_one())
         layer1(wbase + CM::H1_LO, bar);
       __syncwarp();
     }
     for (int j = wg; j < nt; j += NP) {
-      ready_sync(wg, rp, RT);  // H1 (end rows)
-      if (umma::elect_one())
-        layer2();
-      __syncwarp();
-      ready_sync(wg, rp, RT);  // start-row observations in the XS panel
-      if (umma::elect_one())
-        layer1(wbase + CM::XS, bar_l1s);
-      __syncwarp();
+      if (!eg) {
+        ready_sync(wg, rp, RT);  // H1 (end rows)
+        if (umma::elect_one())
+          layer2();
+        __syncwarp();
+        ready_sync(wg, rp, RT);  // start-row observations in the XS panel
+        if (umma::elect_one())
+          layer1(wbase + CM::XS, bar_l1s);
+        __syncwarp();
+      }
       ready_sync(wg, rp, RT);  // H1 (start rows)
       if (umma::elect_one())
         layer2();
@@ -1308,7 +1316,7 @@ __global__ void __launch_bounds__((cmap<D1, D2, MODE>::THREADS), 1) fused_critic
         }
         __syncwarp();
       }
-      ready_sync(wg, rp, RT);  // (dH1 in the shared slot and) the next tile's end-row observations
+      ready_sync(wg, rp, RT);  // (dH1 in the shared slot and) the next tile's observations (end rows; eg: start rows)
       if (umma::elect_one()) {
         if (j + NP < nt)  // ahead of dW1: see fused_policy_step_kernel
           layer1(wbase + CM::H1_LO, bar);
@@ -1330,6 +1338,7 @@ __global__ void __launch_bounds__((cmap<D1, D2, MODE>::THREADS), 1) fused_critic
     // partial values of the tile's rows: ve[half][row], vs[half][row]; V = (sum of the partials) + b3
     float *ve = reinterpret_cast<float *>(smem + CM::SCR) + wg * 2 * NH * TILE, *vs = ve + NH * TILE;
     auto value_of = [&](const float *vp, int r) { return NH == 2 ? (vp[r] + vp[TILE + r]) + b3 : vp[r] + b3; };
+    auto end_value = [&](int r) { return eg ? ve[r] : value_of(ve, r); };
     const int h0 = NH == 2 ? half : 0, h1d1 = NH == 2 ? half + 1 : D1 / (D1 < 32 ? D1 : 32),
               h1d2 = NH == 2 ? half + 1 : D2 / (D2 < 32 ? D2 : 32);
     // two threads per row split the state work: chunk 0's thread prefetches the next START state and
@@ -1363,7 +1372,7 @@ __global__ void __launch_bounds__((cmap<D1, D2, MODE>::THREADS), 1) fused_critic
         done = L.rec_done[(size_t)tt * L.n + i0];
         act = L.rec_action[(size_t)tt * L.n + i0];
       }
-      if (xe_role) {
+      if (xe_role && !eg) {
         row_state<NB> xe;
         load_end_source<NB>(L, tile0, t.row, done, xe);
         fix_end_state<NB>(xe, done, act);
@@ -1372,6 +1381,14 @@ __global__ void __launch_bounds__((cmap<D1, D2, MODE>::THREADS), 1) fused_critic
       if (stager) {
         if (fast)
           load_warp_state<NB>(L.rec_state, false, L, tile0, warp_row0, t.lane, ws);
+        if (eg) {  // the first tile's start-row observations for its layer-1 GEMM
+          row_state<NB> xs;
+          if (fast)
+            gather_row_state<NB>(ws, t.lane, tt < L.T && i0 < L.n, xs);
+          else
+            load_row_state<NB>(L, tile0, t.row, xs);
+          encode_row<NB>(wsm + CM::H1_LO, t.row, xs, L.inv_w, L.inv_h);
+        }
       }
       ready_arrive(wg, rp, RT);
     }
@@ -1386,28 +1403,34 @@ __global__ void __launch_bounds__((cmap<D1, D2, MODE>::THREADS), 1) fused_critic
       if (MODE == CRITIC_GAE && t.row < L.E && i < L.n)
         for (int q = 0; q < L.T && q < 32; ++q)
           dmask |= (uint32_t)(L.rec_done[(size_t)q * L.n + tile * L.E + t.row] != 0) << q;
-      // ---- pass 1: V of the end rows
-      CSTAMP();
-      wait_mma();  // layer 1 (end rows): H1 only as a TMEM A operand
-      CSTAMP();
-      epi2_fwd<D1, true, false>(tm + C2_ACC0, t, b1, nullptr, nullptr, h0, h1d1);
-      ready_arrive(wg, rp, RT);
-      CSTAMP();
-      // start-row observations -> XS (the previous tile's dW1 GEMM ran behind the epilogue above)
-      if (MODE == CRITIC_STEP && !first) {
-        umma::mbar_wait(bar_dw1, phase_dw1);
-        phase_dw1 ^= 1;
+      // V(end) of this row from the compacted pre-pass (eg): needed where the trajectory ends here
+      float vend_g = 0.f;
+      if (eg && valid && (done || last))
+        vend_g = a.v_end[k];
+      if (!eg) {
+        // ---- pass 1: V of the end rows
+        CSTAMP();
+        wait_mma();  // layer 1 (end rows): H1 only as a TMEM A operand
+        CSTAMP();
+        epi2_fwd<D1, true, false>(tm + C2_ACC0, t, b1, nullptr, nullptr, h0, h1d1);
+        ready_arrive(wg, rp, RT);
+        CSTAMP();
+        // start-row observations -> XS (the previous tile's dW1 GEMM ran behind the epilogue above)
+        if (MODE == CRITIC_STEP && !first) {
+          umma::mbar_wait(bar_dw1, phase_dw1);
+          phase_dw1 ^= 1;
+        }
+        if (stager) {
+          row_state<NB> xs;
+          if (fast)
+            gather_row_state<NB>(ws, t.lane, valid, xs);
+          else
+            load_row_state<NB>(L, tile, t.row, xs);  // step counts with E % 4 != 0: loaded where it is used
+          encode_row<NB>(wsm + CM::XS, t.row, xs, L.inv_w, L.inv_h);
+        }
+        ready_arrive(wg, rp, RT);
+        CSTAMP();
       }
-      if (stager) {
-        row_state<NB> xs;
-        if (fast)
-          gather_row_state<NB>(ws, t.lane, valid, xs);
-        else
-          load_row_state<NB>(L, tile, t.row, xs);  // step counts with E % 4 != 0: loaded where it is used
-        encode_row<NB>(wsm + CM::XS, t.row, xs, L.inv_w, L.inv_h);
-      }
-      ready_arrive(wg, rp, RT);
-      CSTAMP();
       // the next tile's state: the start-state loads fly behind the layer-2 GEMM of the end rows and
       // are packed right after it; the end-state loads (source chosen by `done`, known by then) fly
       // behind the start rows' layer 1 / 2
@@ -1419,7 +1442,7 @@ __global__ void __launch_bounds__((cmap<D1, D2, MODE>::THREADS), 1) fused_critic
         if (fast) {
           if (stager)
             load_warp_state<NB>(L.rec_state, false, L, ntile, warp_row0, t.lane, wn);
-          if (xe_role) {
+          if (xe_role && !eg) {
             if (NH == 2)  // (one thread per row: the start words are in wn already)
               load_warp_state<NB>(L.rec_state, false, L, ntile, warp_row0, t.lane, wes);
             load_warp_state<NB>(L.live_state, true, L, ntile, warp_row0, t.lane, wel);
@@ -1430,19 +1453,40 @@ __global__ void __launch_bounds__((cmap<D1, D2, MODE>::THREADS), 1) fused_critic
           nact = L.rec_action[(size_t)tt * L.n + ni];
         }
       }
-      wait_mma();  // layer 2 (end rows)
-      CSTAMP();
-
-      ve[half * TILE + t.row] = epi2_value<D2, false>(tm + C2_ACC1, t, b2, w3, 0.f, nullptr, h0, h1d2);
-      // ---- pass 2: start rows, H1 kept for the dW2 GEMM
-      CSTAMP();
-      umma::mbar_wait(bar_l1s, phase_l1s);  // layer 1 (start rows)
-      phase_l1s ^= 1;
-      umma::fence_after_sync();
+      if (!eg) {
+        wait_mma();  // layer 2 (end rows)
+        CSTAMP();
+        ve[half * TILE + t.row] = epi2_value<D2, false>(tm + C2_ACC1, t, b2, w3, 0.f, nullptr, h0, h1d2);
+        // ---- pass 2: start rows, H1 kept for the dW2 GEMM
+        CSTAMP();
+        umma::mbar_wait(bar_l1s, phase_l1s);  // layer 1 (start rows)
+        phase_l1s ^= 1;
+        umma::fence_after_sync();
+      } else {
+        if (half == 0)
+          ve[t.row] = vend_g;  // the complete value (end_value() below)
+        wait_mma();  // layer 1 (start rows; staged in H1_LO, which the epilogue below overwrites)
+      }
       CSTAMP();
       epi2_fwd<D1, true, MODE == CRITIC_STEP>(tm + C2_ACC0, t, b1, wsm + CM::H1_HI, wsm + CM::H1_LO, h0, h1d1);  // panels: dW2
       ready_arrive(wg, rp, RT);
       CSTAMP();
+      if (eg && MODE == CRITIC_STEP) {
+        // start-row observations -> XS for this tile's dW1 GEMM (the previous tile's dW1 GEMM, which
+        // read XS, ran behind the epilogue above)
+        if (!first) {
+          umma::mbar_wait(bar_dw1, phase_dw1);
+          phase_dw1 ^= 1;
+        }
+        if (stager) {
+          row_state<NB> xs;
+          if (fast)
+            gather_row_state<NB>(ws, t.lane, valid, xs);
+          else
+            load_row_state<NB>(L, tile, t.row, xs);
+          encode_row<NB>(wsm + CM::XS, t.row, xs, L.inv_w, L.inv_h);
+        }
+      }
 
       CSTAMP();
       wait_mma();  // layer 2 (start rows)
@@ -1459,7 +1503,7 @@ __global__ void __launch_bounds__((cmap<D1, D2, MODE>::THREADS), 1) fused_critic
             const int r = q * L.E + t.row;
             const int d = L.T <= 32 ? (int)((dmask >> q) & 1u) : (int)L.rec_done[kq];
             const bool ends = d || q == L.T - 1;
-            const float vn = ends ? value_of(ve, r) : value_of(vs, r + L.E);
+            const float vn = ends ? end_value(r) : value_of(vs, r + L.E);
             const float vn_adv = d ? 0.f : vn;
             const float delta = (d ? 0.f : 1.f) + a.gamma * vn_adv - value_of(vs, r);
             const float adv = delta + (ends ? 0.f : a.lambda * a.gamma * a_next);
@@ -1474,7 +1518,7 @@ __global__ void __launch_bounds__((cmap<D1, D2, MODE>::THREADS), 1) fused_critic
         float dy = 0.f;
         if (valid) {
           const bool ends = done || last;
-          const float vn = ends ? value_of(ve, t.row) : value_of(vs, t.row + L.E);
+          const float vn = ends ? end_value(t.row) : value_of(vs, t.row + L.E);
           const float tgt = (done ? 0.f : 1.f) + a.gamma * vn;  // not masked at terminals (quirk 6)
           dy = value_of(vs, t.row) - tgt;
           if (a.targets_out && stager)
@@ -1540,7 +1584,19 @@ __global__ void __launch_bounds__((cmap<D1, D2, MODE>::THREADS), 1) fused_critic
         umma::mbar_wait(bar_dw2, phase_dw2);  // H1 is free (the dW2 GEMM ran behind the dH1 epilogue)
         phase_dw2 ^= 1;
       }
-      if (has_next) {
+      if (has_next && eg) {
+        if (stager) {  // the next tile's start-row observations for its layer-1 GEMM
+          row_state<NB> xs;
+          const int ni = ntile * L.E + e;
+          if (fast)
+            gather_row_state<NB>(wn, t.lane, tt < L.T && ni < L.n, xs);
+          else
+            load_row_state<NB>(L, ntile, t.row, xs);
+          encode_row<NB>(wsm + CM::H1_LO, t.row, xs, L.inv_w, L.inv_h);
+          ws = wn;
+        }
+        done = ndone;
+      } else if (has_next) {
         if (xe_role) {
           row_state<NB> xe;
           if (fast) {  // end state of the next tile's row: its start state (done) or the live state (last step)
@@ -1677,6 +1733,217 @@ __global__ void __launch_bounds__((cmap<D1, D2, MODE>::THREADS), 1) fused_critic
     umma::tmem_dealloc(tmem, 512);
   if (MODE == CRITIC_STEP)  // cross-CTA reduction (+ exchange) + optimizer update of this CTA's parameter slice
     gradient_tail(a.partials, net, a.tail, reinterpret_cast<float *>(smem + CM::WG0));
+}
+
+// ---------------------------------------------------------------------------------------------
+// V(end states) on COMPACTED rows. The critic target r + gamma V(s') and the advantage pass need the
+// value of a transition's END state only where it is not the next recorded start state: at the
+// rollout's last step (the live environment state) and where an episode ended (the overflowed
+// terminal state, bin_packing.h:54-61) -- about a third of the rows at T = 4. The critic-step and
+// GAE kernels used to push ALL 128 rows of every tile through an end pass; for large batches this
+// forward-only kernel evaluates just the needed rows first and the learner kernels read v_end[T][n].
+//   live units  u < ceil(n / 128): the 128 environments [128 u, 128 u + 128) at step T - 1
+//   scan units: 2048 consecutive (t, i) entries of rec_done with t < T - 1 each; the done entries are
+//               compacted (warp ballots + prefix sums, deterministic) into passes of 128 rows
+// Structure as the rollout kernel: 4 pipelines of 128 epilogue threads + one MMA-issuing warp, hidden
+// activations only in tensor memory.
+struct vend_args {
+  const float *params;
+  net3 net;
+  learner_rows rows;
+  float *v_end;  // [T][n]
+  int n_live_units, n_units;
+};
+template <int D1, int D2>
+struct vmap {
+  static constexpr int NP = 4, CH = 2048;
+  static constexpr uint32_t W1P = 0;
+  static constexpr uint32_t W2_HI = W1P + D1 * 128, W2_LO = W2_HI + D2 * 128;
+  static constexpr uint32_t FLOATS = W2_LO + D2 * 128;  // b1[D1] b2[D2] w3[64] b3[4]
+  static constexpr int F_B1 = 0, F_B2 = D1, F_W3 = D1 + D2, F_B3 = D1 + D2 + 64, N_FLOATS = D1 + D2 + 68;
+  static constexpr uint32_t LISTS = FLOATS + N_FLOATS * 4;  // per pipeline: uint16 lst[CH], int wtot[4], int npass[2]
+  static constexpr uint32_t LIST_BYTES = CH * 2 + 32;
+  static constexpr uint32_t WG0 = (LISTS + NP * LIST_BYTES + 1023) / 1024 * 1024;
+  static constexpr uint32_t BARS = WG0 + NP * PANEL;
+  static constexpr uint32_t TOTAL = BARS + 64;
+  static constexpr int THREADS = 160 * NP;
+};
+
+template <int D0, int D1, int D2>
+__global__ void __launch_bounds__((vmap<D1, D2>::THREADS), 1) fused_vend_kernel(vend_args a) {
+  using VM = vmap<D1, D2>;
+  constexpr int NP = VM::NP, CH = VM::CH, NB = 8, P = 2 * NB + 2;
+  static_assert(D0 == 4 * NB, "observation width");
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
+  float *fl = reinterpret_cast<float *>(smem + VM::FLOATS);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + VM::BARS);  // [wg]: MMA completion
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + VM::BARS + 56);
+  const net3 net = a.net;
+  const learner_rows &L = a.rows;
+  const tid_t t = thread_id();
+  const bool issuer = t.warp >= 4 * NP;
+  const int wg = issuer ? t.warp - 4 * NP : t.warp >> 2;
+  const uint32_t sbase = umma::smem_u32(smem);
+
+  if (t.warp == 0)
+    umma::tmem_alloc(tmem_slot, 512);
+  if (threadIdx.x == 0) {
+    for (int q = 0; q < NP; ++q)
+      umma::mbar_init(bars + q, 1);
+    umma::fence_mbar_init();
+  }
+  {
+    const float *Pm = stage_params_bulk(a.params, net.n_params, smem + VM::WG0, bars + 5);
+    stage_w1_packed<D1>(Pm + net.o_w1, smem + VM::W1P);
+    stage_weight_f16(Pm + net.o_w2, D2, D1, D2, 1.f, smem + VM::W2_HI, smem + VM::W2_LO);
+    for (int i = threadIdx.x; i < D1; i += blockDim.x) fl[VM::F_B1 + i] = Pm[net.o_b1 + i];
+    for (int i = threadIdx.x; i < D2; i += blockDim.x) fl[VM::F_B2 + i] = Pm[net.o_b2 + i];
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) fl[VM::F_W3 + i] = i < D2 ? Pm[net.o_w3 + i] : 0.f;
+    if (threadIdx.x == 0)
+      fl[VM::F_B3] = Pm[net.o_b3];
+  }
+  __syncthreads();  // the scratch (observation panels) is free again
+  zero_bytes(smem + VM::WG0, VM::BARS - VM::WG0);
+  sync_after_smem_writes();
+  const uint32_t tmem = *tmem_slot;
+
+  const int nt = (int)blockIdx.x < a.n_units ? (a.n_units - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  uint8_t *wsm = smem + VM::WG0 + wg * PANEL;
+  const uint32_t wbase = sbase + VM::WG0 + wg * PANEL;
+  const uint32_t tm = tmem + 128u * wg;  // ACC0 (layer 1) at +0, ACC1 (layer 2) at +64
+  uint64_t *bar = bars + wg;
+  uint16_t *lst = reinterpret_cast<uint16_t *>(smem + VM::LISTS + wg * VM::LIST_BYTES);
+  int *wtot = reinterpret_cast<int *>(smem + VM::LISTS + wg * VM::LIST_BYTES + CH * 2);
+  volatile int *npass_slot = wtot + 4;  // [2], alternating per unit
+  uint32_t rp = 0;
+
+  if (issuer) {
+    int u = 0;
+    for (int j = wg; j < nt; j += NP, u ^= 1) {
+      ready_sync(wg, rp);  // the unit's pass count is published (the epilogue threads block on this one too)
+      const int npass = npass_slot[u];
+      for (int ps = 0; ps < npass; ++ps) {
+        ready_sync(wg, rp);  // observations
+        if (umma::elect_one()) {
+          issue_gemm<D0 / 16, false, false, false, true>(tm, wbase, 0, sbase + VM::W1P, sbase + VM::W1P + 64, ID<D1>::FK_FK, false);
+          umma::commit(bar);
+        }
+        __syncwarp();
+        ready_sync(wg, rp);  // H1 (tensor memory)
+        if (umma::elect_one()) {
+          issue_gemm_ta<D1, D1 / 16, false>(tm + 64, tm, sbase + VM::W2_HI, sbase + VM::W2_LO, ID<D2>::FK_FK);
+          umma::commit(bar);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    const float *b1 = fl + VM::F_B1, *b2 = fl + VM::F_B2, *w3 = fl + VM::F_W3;
+    const float b3 = fl[VM::F_B3];
+    uint32_t phase = 0;
+    auto wait_mma = [&]() {
+      umma::mbar_wait(bar, phase);
+      phase ^= 1;
+      umma::fence_after_sync();
+    };
+    const long long scan_rows = (long long)(L.T - 1) * L.n;
+    int u = 0;
+    for (int j = wg; j < nt; j += NP, u ^= 1) {
+      const int unit = blockIdx.x + j * gridDim.x;
+      const bool live = unit < a.n_live_units;
+      long long base = 0;
+      int cnt;
+      if (live) {
+        cnt = min(TILE, L.n - TILE * unit);
+      } else {
+        // ---- compaction of the done entries of this chunk: thread r scans entries 16 r .. 16 r + 15
+        base = (long long)(unit - a.n_live_units) * CH;
+        const long long k0 = base + 16 * t.row;
+        uint32_t bits = 0;
+        if (k0 + 16 <= scan_rows && ((reinterpret_cast<uintptr_t>(L.rec_done) + k0) & 15) == 0) {
+          const uint4 f = *reinterpret_cast<const uint4 *>(L.rec_done + k0);
+          const uint32_t wv[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              bits |= (((wv[q] >> (8 * e)) & 0xffu) ? 1u : 0u) << (4 * q + e);
+        } else {
+          for (int e = 0; e < 16; ++e)
+            if (k0 + e < scan_rows && L.rec_done[k0 + e])
+              bits |= 1u << e;
+        }
+        const int mine = __popc(bits);
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, incl, o);
+          if (t.lane >= o)
+            incl += v;
+        }
+        if (t.lane == 31)
+          wtot[t.w] = incl;
+        asm volatile("bar.sync %0, %1;\n" ::"r"(9 + wg), "r"(128) : "memory");
+        int off = incl - mine;
+        cnt = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (q < t.w)
+            off += wtot[q];
+          cnt += wtot[q];
+        }
+        for (uint32_t b = bits; b; b &= b - 1)
+          lst[off++] = (uint16_t)(16 * t.row + (__ffs(b) - 1));
+        asm volatile("bar.sync %0, %1;\n" ::"r"(9 + wg), "r"(128) : "memory");  // list complete; wtot may be reused
+      }
+      const int npass = (cnt + TILE - 1) / TILE;
+      if (t.row == 0)
+        npass_slot[u] = npass;
+      ready_sync(wg, rp);  // blocking on purpose: an empty unit must not let these threads run ahead of the issuer
+      for (int ps = 0; ps < npass; ++ps) {
+        const int slot = TILE * ps + t.row;
+        const bool has = slot < cnt;
+        long long k = 0;
+        int tt = L.T - 1, i = TILE * unit + t.row;
+        if (has && !live) {
+          k = base + lst[slot];
+          tt = (int)(k / L.n);
+          i = (int)(k - (long long)tt * L.n);
+        } else if (has) {
+          k = (long long)tt * L.n + i;
+        }
+        int done = 0, act = 0;
+        if (has) {
+          done = live ? (int)L.rec_done[k] : 1;
+          act = L.rec_action[k];
+        }
+        // end state: the overflowed terminal state (done) or the live state (last step)
+        row_state<NB> x;
+        const int8_t *src = done ? L.rec_state + (size_t)tt * P * L.stride + i : L.live_state + i;
+#pragma unroll
+        for (int q = 0; q < P; ++q) {
+          x.v[q] = 0;
+          if (has)
+            x.v[q] = src[(size_t)q * L.stride];
+        }
+        fix_end_state<NB>(x, done, act);
+        encode_row<NB>(wsm, t.row, x, L.inv_w, L.inv_h);
+        ready_arrive(wg, rp);
+        wait_mma();  // layer 1
+        epi2_fwd<D1, true, false>(tm, t, b1, nullptr, nullptr);  // H1 only as a TMEM A operand
+        ready_arrive(wg, rp);
+        wait_mma();  // layer 2
+        const float v = epi2_value<D2, false>(tm + 64, t, b2, w3, b3, nullptr);
+        if (has)
+          a.v_end[k] = v;
+      }
+    }
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (t.warp == 0)
+    umma::tmem_dealloc(tmem, 512);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1959,6 +2226,7 @@ struct fused_state {
   int head_bwd;
   float *partials;  // [ctas][max params]
   unsigned *gridbar;  // [2] grid barrier of the gradient tail (arrivals, generation)
+  int vend_mode;      // -1: by batch size, 0 / 1: never / always use the compacted V(end) pre-pass
   int ctas;
   long long *clk;  // [112] phase clocks of the last policy step (allocated on first request)
   long long *clk_critic;  // [112] the same for the critic step
@@ -2034,21 +2302,39 @@ int launch_policy_step(dfrl_ctx *ctx, const policy_step_args &a, int ctas) {
                             ctas, pmap<D1, D2>::THREADS, smem, a);
 }
 
-template <int D0, int D1, int D2>
-int launch_critic_step(dfrl_ctx *ctx, const critic_args &a, int ctas) {
+template <int D0, int D1, int D2, bool EG>
+int launch_critic_step_eg(dfrl_ctx *ctx, const critic_args &a, int ctas) {
   constexpr int smem = cmap<D1, D2, CRITIC_STEP>::TOTAL + 1024;
   static bool attr = false;
-  DFRL_TRY(set_smem_once(fused_critic_kernel<D0, D1, D2, CRITIC_STEP>, smem, &attr));
-  return launch_cooperative(ctx, fused_critic_kernel<D0, D1, D2, CRITIC_STEP>, "(fused_critic_kernel<D0, D1, D2, CRITIC_STEP>)",
+  DFRL_TRY(set_smem_once(fused_critic_kernel<D0, D1, D2, CRITIC_STEP, EG>, smem, &attr));
+  return launch_cooperative(ctx, fused_critic_kernel<D0, D1, D2, CRITIC_STEP, EG>,
+                            "(fused_critic_kernel<D0, D1, D2, CRITIC_STEP, EG>)",
                             ctas, cmap<D1, D2, CRITIC_STEP>::THREADS, smem, a);
+}
+template <int D0, int D1, int D2>
+int launch_critic_step(dfrl_ctx *ctx, const critic_args &a, int ctas) {
+  return a.v_end ? launch_critic_step_eg<D0, D1, D2, true>(ctx, a, ctas) : launch_critic_step_eg<D0, D1, D2, false>(ctx, a, ctas);
+}
+
+template <int D0, int D1, int D2, bool EG>
+int launch_gae_eg(dfrl_ctx *ctx, const critic_args &a, int ctas) {
+  constexpr int smem = cmap<D1, D2, CRITIC_GAE>::TOTAL + 1024;
+  static bool attr = false;
+  DFRL_TRY(set_smem_once(fused_critic_kernel<D0, D1, D2, CRITIC_GAE, EG>, smem, &attr));
+  DFRL_LAUNCH(ctx, (fused_critic_kernel<D0, D1, D2, CRITIC_GAE, EG>), ctas, (cmap<D1, D2, CRITIC_GAE>::THREADS), smem, a);
+  return DFRL_OK;
+}
+template <int D0, int D1, int D2>
+int launch_gae(dfrl_ctx *ctx, const critic_args &a, int ctas) {
+  return a.v_end ? launch_gae_eg<D0, D1, D2, true>(ctx, a, ctas) : launch_gae_eg<D0, D1, D2, false>(ctx, a, ctas);
 }
 
 template <int D0, int D1, int D2>
-int launch_gae(dfrl_ctx *ctx, const critic_args &a, int ctas) {
-  constexpr int smem = cmap<D1, D2, CRITIC_GAE>::TOTAL + 1024;
+int launch_vend(dfrl_ctx *ctx, const vend_args &a, int ctas) {
+  constexpr int smem = vmap<D1, D2>::TOTAL + 1024;
   static bool attr = false;
-  DFRL_TRY(set_smem_once(fused_critic_kernel<D0, D1, D2, CRITIC_GAE>, smem, &attr));
-  DFRL_LAUNCH(ctx, (fused_critic_kernel<D0, D1, D2, CRITIC_GAE>), ctas, (cmap<D1, D2, CRITIC_GAE>::THREADS), smem, a);
+  DFRL_TRY(set_smem_once(fused_vend_kernel<D0, D1, D2>, smem, &attr));
+  DFRL_LAUNCH(ctx, (fused_vend_kernel<D0, D1, D2>), ctas, (vmap<D1, D2>::THREADS), smem, a);
   return DFRL_OK;
 }
 
@@ -2096,6 +2382,7 @@ critic_args make_critic_args(dfrl_trainer *t, fused_state *f) {
   a.adv_out = t->adv;
   a.partials = f->partials;
   memset(&a.tail, 0, sizeof(a.tail));
+  a.v_end = nullptr;
   a.clk = f->clk_critic;
   return a;
 }
@@ -2154,6 +2441,7 @@ int dfrl_fused_try_attach(dfrl_trainer *t) {
     return DFRL_ERR_UNSUPPORTED;
   }
   f->ctas = t->ctx->sm_count;
+  f->vend_mode = -1;
   int maxp = t->policy->n_params;
   if (t->value && t->value->n_params > maxp)
     maxp = t->value->n_params;
@@ -2195,6 +2483,16 @@ extern "C" int dfrl_debug_set_fused_ctas(dfrl_trainer *t, int ctas) {
   fused_state *f = (fused_state *)t->fused_impl;
   DFRL_CHECK(f, "fused path not attached");
   f->ctas = (ctas > 0 && ctas < t->ctx->sm_count) ? ctas : t->ctx->sm_count;
+  return DFRL_OK;
+}
+
+// Test hook: forces (1) / forbids (0) the compacted V(end) pre-pass of the critic-step and GAE kernels,
+// -1 restores the choice by batch size.
+extern "C" int dfrl_debug_set_vend(dfrl_trainer *t, int mode) {
+  DFRL_CHECK(t, "null trainer");
+  fused_state *f = (fused_state *)t->fused_impl;
+  DFRL_CHECK(f, "fused path not attached");
+  f->vend_mode = mode < 0 ? -1 : (mode ? 1 : 0);
   return DFRL_OK;
 }
 
@@ -2254,12 +2552,42 @@ int dfrl_fused_policy_gradient(dfrl_trainer *t, int loss_kind, float *grad_dev, 
   return DFRL_OK;
 }
 
+// V(end) of the rows that end a trajectory (last step, finished episodes) with the CURRENT critic, on
+// compacted rows, into t->v_end. Used by the critic-step and GAE kernels of large batches instead of
+// their own end pass over every row (DFRL_VEND=0 / 1 forces the choice).
+static bool use_vend(const dfrl_trainer *t, const fused_state *f) {
+  static const char *env = getenv("DFRL_VEND");
+  if (f->vend_mode >= 0)
+    return f->vend_mode != 0;
+  if (env)
+    return atoi(env) != 0;
+  return (long long)t->n * t->L >= 65536;
+}
+static int fused_vend(dfrl_trainer *t, fused_state *f) {
+  vend_args a;
+  a.params = t->value->params;
+  a.net = f->vnet;
+  a.rows = make_rows(t);
+  a.v_end = t->v_end;
+  a.n_live_units = ceil_div(t->n, TILE);
+  const long long scan_rows = (long long)(t->L - 1) * t->n;
+  a.n_units = a.n_live_units + ceil_div(scan_rows, vmap<64, 64>::CH);
+  int ctas = a.n_units < f->ctas ? a.n_units : f->ctas;
+  if (f->vnet.d1 == 64)
+    return launch_vend<32, 64, 64>(t->ctx, a, ctas);
+  return launch_vend<32, 16, 16>(t->ctx, a, ctas);
+}
+
 // update_value_model (policy_gradient.h:196-218) up to the gradient: writes t->targets and grad_dev.
 int dfrl_fused_critic_gradient(dfrl_trainer *t, float *grad_dev, const dfrl_opt_spec *opt) {
   fused_state *f = (fused_state *)t->fused_impl;
   if (!f || !f->value_ok)
     return DFRL_ERR_UNSUPPORTED;
   critic_args a = make_critic_args(t, f);
+  if (use_vend(t, f)) {
+    DFRL_TRY(fused_vend(t, f));
+    a.v_end = t->v_end;
+  }
   int ctas = a.n_tiles < f->ctas ? a.n_tiles : f->ctas;
   DFRL_TRY(make_tail(t, f, f->vnet, ctas, grad_dev, opt, &a.tail));
   if (f->vnet.d1 == 64)
@@ -2277,6 +2605,10 @@ int dfrl_fused_gae(dfrl_trainer *t) {
   if (!f || !f->value_ok)
     return DFRL_ERR_UNSUPPORTED;
   critic_args a = make_critic_args(t, f);
+  if (use_vend(t, f)) {
+    DFRL_TRY(fused_vend(t, f));
+    a.v_end = t->v_end;
+  }
   int ctas = a.n_tiles < f->ctas ? a.n_tiles : f->ctas;
   if (f->vnet.d1 == 64)
     DFRL_TRY((launch_gae<32, 64, 64>(t->ctx, a, ctas)));

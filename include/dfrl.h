@@ -401,6 +401,9 @@ int dfrl_debug_critic_clocks(dfrl_trainer *tr, long long *out_host, int n);
  * pipelines). ctas <= 0 restores one CTA per SM. Results do not depend on the grid size beyond the
  * summation order of the per-CTA partial gradients. */
 int dfrl_debug_set_fused_ctas(dfrl_trainer *tr, int ctas);
+/* Test hook: 1 forces / 0 forbids the compacted V(end-state) pre-pass of the fused critic-step and
+ * GAE kernels (policy_gradient.h:196-281 need V(end) only where a trajectory ends); -1: by batch size. */
+int dfrl_debug_set_vend(dfrl_trainer *tr, int mode);
 
 /* deep_agent.cc:28-41 / the periodic eval of the trainer mains (ppo_training.cc:67-81): every
  * env of `env` plays `episodes` episodes with policy_gradient_deterministic_policy (argmax) on

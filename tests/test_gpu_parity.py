@@ -463,10 +463,13 @@ def test_trainer_default_path_vs_reference_trace(D, ctx, name):
     _run_case(D, ctx, name, fused=True)
 
 
+@pytest.mark.parametrize("vend", [0, 1])
 @pytest.mark.parametrize("n,T,ctas", [(512, 4, 0), (200, 4, 0), (96, 8, 0), (70, 5, 0),
                                       (512, 4, 3), (544, 4, 2), (200, 4, 1), (416, 8, 4), (2048, 4, 5),
                                       (300, 1, 2), (150, 16, 2), (60, 32, 1), (40, 128, 0)])
-def test_trainer_vs_oracle_with_uniform_tape(D, ctx, orc, n, T, ctas):
+def test_trainer_vs_oracle_with_uniform_tape(D, ctx, orc, n, T, ctas, vend):
+    # vend = 1: V(end) from the compacted pre-pass kernel (fused_vend_kernel: live units + done-flag scan
+    # units; the learner kernels then run without their end pass) -- the path large batches take
     # ctas > 0: the persistent learner kernels run on that many CTAs only, so that every CTA works
     # through several row tiles per tile pipeline (the steady state of the large configurations):
     # (512, 4, 3) 16 tiles on 3 CTAs; (544, 4, 2) 17 tiles: an odd tile count per CTA, the two
@@ -512,6 +515,7 @@ def test_trainer_vs_oracle_with_uniform_tape(D, ctx, orc, n, T, ctas):
                    action_mode=D.ACT_SAMPLE)
     if ctas:
         D._lib.check(D._lib.lib.dfrl_debug_set_fused_ctas(tr.h, ctas))
+    D._lib.check(D._lib.lib.dfrl_debug_set_vend(tr.h, vend))
     lr = orc.Learner(orc.train_cfg(orc.PPO, T, policy_lr=2e-8, value_lr=2e-8), ecfg, pnet, pp, vnet, vp)
     done_at_last_step = done_mid = 0
     for it in range(5):
@@ -682,6 +686,7 @@ def test_trainer_variants_vs_oracle(D, ctx, orc, algo_name, n, T, B, pdims, vdim
                    action_mode=D.ACT_SAMPLE)
     if cap:
         D._lib.check(D._lib.lib.dfrl_debug_set_fused_ctas(tr.h, int(cap)))
+        D._lib.check(D._lib.lib.dfrl_debug_set_vend(tr.h, 1))  # the capped cases also take the compacted V(end) pre-pass
     lr = orc.Learner(orc.train_cfg(oalgo, T, policy_lr=2e-8, value_lr=2e-8), ecfg, pnet, pp, vnet, vp)
     for it in range(3):
         items = rng.integers(0, 2, (T, n)).astype(np.uint8)
