@@ -122,6 +122,7 @@ PROTOTYPES = {
     "dfrl_trainer_destroy": (i32, [vp]),
     "dfrl_trainer_rollout": (i32, [vp, vp, vp, vp]),
     "dfrl_trainer_learn": (i32, [vp]),
+    "dfrl_trainer_learn_phases": (i32, [vp, i32]),
     "dfrl_trainer_iterate": (i32, [vp, i32]),
     "dfrl_trainer_field_size": (i32, [vp, i32, C.POINTER(sz)]),
     "dfrl_trainer_read": (i32, [vp, i32, vp, sz]),

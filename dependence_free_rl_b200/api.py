@@ -18,7 +18,8 @@ LOSS_SOFTMAX_LOG, LOSS_CLIPPED, LOSS_KL = 0, 1, 2
 ACT_SAMPLE, ACT_ARGMAX, ACT_FORCED = 0, 1, 2
 HEUR_RANDOM, HEUR_FIRSTFIT, HEUR_BESTFIT, HEUR_MINWASTE = 0, 1, 2, 3
 (F_REC_STATE, F_REC_ACTION, F_REC_DONE, F_REC_PROBS, F_REC_LEN, F_ADVANTAGE, F_VALUE_TARGET,
- F_POLICY_GRAD, F_VALUE_GRAD, F_POLICY_GRAD_LOG) = range(10)
+ F_POLICY_GRAD, F_VALUE_GRAD, F_POLICY_GRAD_LOG, F_OBS_START) = range(11)
+PHASE_VALUE, PHASE_ADVANTAGE, PHASE_POLICY, PHASE_ALL = 1, 2, 4, 7
 
 
 def _ptr(a):
@@ -356,8 +357,11 @@ class Trainer:
     def rollout_raw(self, items_ptr, actions_ptr, u_ptr):
         check(lib.dfrl_trainer_rollout(self.h, items_ptr, actions_ptr, u_ptr))
 
-    def learn(self):
-        check(lib.dfrl_trainer_learn(self.h))
+    def learn(self, phases=None):
+        if phases is None:
+            check(lib.dfrl_trainer_learn(self.h))
+        else:
+            check(lib.dfrl_trainer_learn_phases(self.h, phases))
 
     def iterate(self, iters):
         check(lib.dfrl_trainer_iterate(self.h, iters))
@@ -380,6 +384,8 @@ class Trainer:
             return buf.view(np.float32).reshape(-1, n)
         if field == F_POLICY_GRAD_LOG:
             return buf.view(np.float32).reshape(-1, self.policy.n_params)
+        if field == F_OBS_START:
+            return buf.view(np.float32).reshape(-1, n, 4 * B)
         return buf.view(np.float32)
 
     @staticmethod

@@ -335,9 +335,11 @@ __device__ __forceinline__ float exchange_entry(const p2p_view &v, unsigned epoc
 // Whole CTA, after its partial gradient has been written to partials[blockIdx.x][0..n).
 // scratch: (blockDim.x / 64) * 64 floats of shared memory. Contains __syncthreads.
 __device__ __forceinline__ void gradient_tail(const float *__restrict__ partials, const net3 &net, const grad_tail &tl,
-                                              float *scratch) {
+                                              float *scratch, long long *clk = nullptr) {
   const int n = net.n_params;
   const tail_ctx tc = tail_begin(tl);
+  if (clk)
+    clk[0] = clock64();
   __syncthreads();  // every thread's partial-gradient stores precede thread 0's fence (cumulativity)
   if (threadIdx.x == 0) {
     __threadfence();  // ... and are visible device-wide before this CTA arrives
@@ -358,6 +360,8 @@ __device__ __forceinline__ void gradient_tail(const float *__restrict__ partials
     __threadfence();
   }
   __syncthreads();
+  if (clk)
+    clk[1] = clock64();
   const int G = (int)gridDim.x, NS = (int)blockDim.x >> 6, s = (int)threadIdx.x >> 6, p = (int)threadIdx.x & 63;
   const int per = (n + G - 1) / G;
   const int lo = (int)blockIdx.x * per, hi = min(lo + per, n);
@@ -421,7 +425,8 @@ struct pmap {
   static constexpr uint32_t W2_HI = W1P + D1 * 128, W2_LO = W2_HI + D2 * 128;
   static constexpr uint32_t W3A = W2_LO + D2 * 128;  // rows 0..7 = rows 8..15 = hi(W3)
   static constexpr uint32_t W3B = W3A + 16 * 128;    // rows 0..7 = lo(W3), rows 8..15 = 0
-  static constexpr uint32_t FLOATS = W3B + 16 * 128;
+  static constexpr uint32_t W3C = W3B + 16 * 128;    // rows 0..7 = hi(W3), rows 8..15 = lo(W3): forward head
+  static constexpr uint32_t FLOATS = W3C + 16 * 128;
   static constexpr int F_B1 = 0, F_B2 = D1, F_B3 = D1 + D2, N_FLOATS = D1 + D2 + 16;
   static constexpr uint32_t DH1_HI = (FLOATS + N_FLOATS * 4 + 1023) / 1024 * 1024;  // shared slot
   static constexpr uint32_t DH1_LO = DH1_HI + PANEL;
@@ -485,6 +490,7 @@ __device__ void build_policy_image(const float *__restrict__ params, const net3 
     uint32_t off = umma::panel_chunk_off(row, chunk);
     *reinterpret_cast<uint4 *>(smem + PM::W3A + off) = h;
     *reinterpret_cast<uint4 *>(smem + PM::W3B + off) = row < 8 ? l : make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4 *>(smem + PM::W3C + off) = row < 8 ? h : l;
   }
   float *fl = reinterpret_cast<float *>(smem + PM::FLOATS);
   for (int i = threadIdx.x; i < D1; i += blockDim.x) fl[PM::F_B1 + i] = params[net.o_b1 + i];
@@ -749,9 +755,11 @@ __global__ void __launch_bounds__((pmap<D1, D2>::THREADS), 1) fused_policy_step_
         umma::commit(bar);
       }
       __syncwarp();
-      ready_sync(wg, rp, RT);  // H2; head: columns 8..15 of the result repeat 0..7 (stacked B operand), unused
-      if (umma::elect_one()) {  // A = H2 from tensor memory (ACC1)
-        issue_gemm_ta<D2, D2 / 16, false>(tm + P2_ACC0, tm + P2_ACC1, sbase + PM::W3A, sbase + PM::W3B, ID<16>::FK_FK);
+      ready_sync(wg, rp, RT);  // H2
+      if (umma::elect_one()) {
+        // (hi(H2) + lo(H2)) . [hi(W3); lo(W3)], A = H2 from tensor memory (ACC1): two MMAs per K step, the
+        // head adds columns q (hi.hi + lo.hi) and 8 + q (hi.lo + lo.lo)
+        issue_gemm_ta<D2, D2 / 16, false, false>(tm + P2_ACC0, tm + P2_ACC1, sbase + PM::W3C, 0, ID<16>::FK_FK);
         umma::commit(bar);
       }
       __syncwarp();
@@ -866,8 +874,11 @@ __global__ void __launch_bounds__((pmap<D1, D2>::THREADS), 1) fused_policy_step_
       STAMP();
       // ---- head epilogue: softmax, loss gradient, softmax backward -> dY = [hi | lo] in the XD panel
       if (header) {
-        float v[8];
-        tmem_load<8>(tm + P2_ACC0 + t.lane_base, v);
+        float v[16];
+        tmem_load<16>(tm + P2_ACC0 + t.lane_base, v);
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          v[q] += v[8 + q];
         float dl[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q)
@@ -1056,7 +1067,7 @@ __global__ void __launch_bounds__((pmap<D1, D2>::THREADS), 1) fused_policy_step_
   if (t.warp == 0)
     umma::tmem_dealloc(tmem, 512);
   // ---- cross-CTA reduction (+ exchange) + optimizer update of this CTA's parameter slice
-  gradient_tail(a.partials, net, a.tail, reinterpret_cast<float *>(smem + PM::WG0 + PM::H1_HI));
+  gradient_tail(a.partials, net, a.tail, reinterpret_cast<float *>(smem + PM::WG0 + PM::H1_HI), clk ? clk + 108 : nullptr);
   if (clk)
     clk[107] = clock64();
 }
@@ -1743,7 +1754,7 @@ __global__ void __launch_bounds__((cmap<D1, D2, MODE>::THREADS), 1) fused_critic
 // GAE kernels used to push ALL 128 rows of every tile through an end pass; for large batches this
 // forward-only kernel evaluates just the needed rows first and the learner kernels read v_end[T][n].
 //   live units  u < ceil(n / 128): the 128 environments [128 u, 128 u + 128) at step T - 1
-//   scan units: 2048 consecutive (t, i) entries of rec_done with t < T - 1 each; the done entries are
+//   scan units: 1024 consecutive (t, i) entries of rec_done with t < T - 1 each; the done entries are
 //               compacted (warp ballots + prefix sums, deterministic) into passes of 128 rows
 // Structure as the rollout kernel: 4 pipelines of 128 epilogue threads + one MMA-issuing warp, hidden
 // activations only in tensor memory.
@@ -1756,7 +1767,7 @@ struct vend_args {
 };
 template <int D1, int D2>
 struct vmap {
-  static constexpr int NP = 4, CH = 2048;
+  static constexpr int NP = 4, CH = 1024;
   static constexpr uint32_t W1P = 0;
   static constexpr uint32_t W2_HI = W1P + D1 * 128, W2_LO = W2_HI + D2 * 128;
   static constexpr uint32_t FLOATS = W2_LO + D2 * 128;  // b1[D1] b2[D2] w3[64] b3[4]
@@ -1857,20 +1868,28 @@ __global__ void __launch_bounds__((vmap<D1, D2>::THREADS), 1) fused_vend_kernel(
       if (live) {
         cnt = min(TILE, L.n - TILE * unit);
       } else {
-        // ---- compaction of the done entries of this chunk: thread r scans entries 16 r .. 16 r + 15
+        // ---- compaction of the done entries of this chunk: thread r scans entries EPT r .. EPT r + EPT - 1
+        constexpr int EPT = CH / TILE;
+        static_assert(EPT == 8 || EPT == 16, "one 8- or 16-byte load of done flags per thread");
         base = (long long)(unit - a.n_live_units) * CH;
-        const long long k0 = base + 16 * t.row;
+        const long long k0 = base + EPT * t.row;
         uint32_t bits = 0;
-        if (k0 + 16 <= scan_rows && ((reinterpret_cast<uintptr_t>(L.rec_done) + k0) & 15) == 0) {
-          const uint4 f = *reinterpret_cast<const uint4 *>(L.rec_done + k0);
-          const uint32_t wv[4] = {f.x, f.y, f.z, f.w};
+        if (k0 + EPT <= scan_rows && ((reinterpret_cast<uintptr_t>(L.rec_done) + k0) & (EPT - 1)) == 0) {
+          uint32_t wv[4] = {0, 0, 0, 0};
+          if (EPT == 16) {
+            const uint4 f = *reinterpret_cast<const uint4 *>(L.rec_done + k0);
+            wv[0] = f.x, wv[1] = f.y, wv[2] = f.z, wv[3] = f.w;
+          } else {
+            const uint2 f = *reinterpret_cast<const uint2 *>(L.rec_done + k0);
+            wv[0] = f.x, wv[1] = f.y;
+          }
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
+          for (int q = 0; q < EPT / 4; ++q)
 #pragma unroll
             for (int e = 0; e < 4; ++e)
               bits |= (((wv[q] >> (8 * e)) & 0xffu) ? 1u : 0u) << (4 * q + e);
         } else {
-          for (int e = 0; e < 16; ++e)
+          for (int e = 0; e < EPT; ++e)
             if (k0 + e < scan_rows && L.rec_done[k0 + e])
               bits |= 1u << e;
         }
@@ -1894,7 +1913,7 @@ __global__ void __launch_bounds__((vmap<D1, D2>::THREADS), 1) fused_vend_kernel(
           cnt += wtot[q];
         }
         for (uint32_t b = bits; b; b &= b - 1)
-          lst[off++] = (uint16_t)(16 * t.row + (__ffs(b) - 1));
+          lst[off++] = (uint16_t)(EPT * t.row + (__ffs(b) - 1));
         asm volatile("bar.sync %0, %1;\n" ::"r"(9 + wg), "r"(128) : "memory");  // list complete; wtot may be reused
       }
       const int npass = (cnt + TILE - 1) / TILE;

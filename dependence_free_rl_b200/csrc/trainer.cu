@@ -334,6 +334,7 @@ extern "C" int dfrl_trainer_create(dfrl_ctx *ctx, const dfrl_trainer_config *cfg
   t->last_rollout_reward = 0;
   t->fused_impl = nullptr;
   t->obs_valid = false;
+  t->critic_was_fused = false;
   t->graph_exec = nullptr;
   t->graph_launches = 0;
   t->plain_iterations = 0;
@@ -529,7 +530,9 @@ static void after_fused_opt(dfrl_mlp *, int kind, float *adam_t) {
     *adam_t += 1.f;  // nn.h:686 (fused.cu already marked the parameters as changed)
 }
 
-static int learn_layered(dfrl_trainer *t) {
+// phases: DFRL_PHASE_* mask. The whole learn() is VALUE | ADVANTAGE | POLICY; the host mirror runs
+// VALUE | ADVANTAGE, hands the rows to a user's optimize_action override, or runs POLICY for the default.
+static int learn_layered(dfrl_trainer *t, int phases = DFRL_PHASE_ALL) {
   dfrl_ctx *ctx = t->ctx;
   dfrl_env *e = t->env;
   const int n = t->n, L = t->L, B = t->B;
@@ -538,6 +541,7 @@ static int learn_layered(dfrl_trainer *t) {
   const dfrl_trainer_config &c = t->cfg;
 
   if (c.algo == DFRL_ALGO_REINFORCE) {
+    DFRL_CHECK(phases == DFRL_PHASE_ALL, "REINFORCE has a single phase");
     // policy_gradient_learner::learn (policy_gradient.h:95-123)
     float *g = t->targets;
     DFRL_CUDA(cudaMemsetAsync(t->acc, 0, sizeof(double) * 2, ctx->stream));
@@ -561,9 +565,14 @@ static int learn_layered(dfrl_trainer *t) {
   }
 
   // actor_critic_learner::learn (policy_gradient.h:159-185)
+  const int va = phases & (DFRL_PHASE_VALUE | DFRL_PHASE_ADVANTAGE);
+  DFRL_CHECK(va == 0 || va == (DFRL_PHASE_VALUE | DFRL_PHASE_ADVANTAGE), "VALUE and ADVANTAGE run together");
+  int frc = t->critic_was_fused ? DFRL_OK : DFRL_ERR_UNSUPPORTED;
+  if (va) {
   dfrl_opt_spec vspec;
   const bool vfo = fuse_opt(t, t->value, c.value_opt, t->vstate, c.value_lr, c.value_wd, t->v_adam_t, &vspec);
-  int frc = dfrl_fused_critic_gradient(t, t->vgrad, vfo ? &vspec : nullptr);  // tcgen05 fused critic step
+  frc = dfrl_fused_critic_gradient(t, t->vgrad, vfo ? &vspec : nullptr);  // tcgen05 fused critic step
+  t->critic_was_fused = frc == DFRL_OK;
   if (frc == DFRL_OK) {
     if (vfo)
       after_fused_opt(t->value, c.value_opt, &t->v_adam_t);
@@ -590,6 +599,9 @@ static int learn_layered(dfrl_trainer *t) {
     DFRL_TRY(dfrl_mlp_eval(t->value, obs_start, (int)LN, t->v_start));
     DFRL_TRY(dfrl_gae(ctx, t->rec_done, t->v_start, t->v_end, n, L, c.gamma, c.lambda, nullptr, t->adv));
   }
+  }
+  if (!(phases & DFRL_PHASE_POLICY))
+    return DFRL_OK;
   // optimize_action (187-194 / 297-307 / 318-330)
   int kind = c.algo == DFRL_ALGO_ACTOR_CRITIC ? DFRL_LOSS_SOFTMAX_LOG
              : c.algo == DFRL_ALGO_PPO        ? DFRL_LOSS_CLIPPED
@@ -713,6 +725,14 @@ extern "C" int dfrl_trainer_learn(dfrl_trainer *t) {
   return learn_graphed(t);
 }
 
+extern "C" int dfrl_trainer_learn_phases(dfrl_trainer *t, int phases) {
+  DFRL_CHECK(t, "null trainer");
+  DFRL_CHECK(phases > 0 && phases <= DFRL_PHASE_ALL, "bad phase mask %d", phases);
+  if (phases == DFRL_PHASE_ALL)
+    return learn_graphed(t);
+  return learn_layered(t, phases);
+}
+
 extern "C" int dfrl_trainer_iterate(dfrl_trainer *t, int iters) {
   DFRL_CHECK(t, "null trainer");
   DFRL_CHECK(t->cfg.action_mode != DFRL_ACT_FORCED, "iterate() cannot teacher-force");
@@ -741,6 +761,7 @@ extern "C" int dfrl_trainer_field_size(dfrl_trainer *t, int field, size_t *bytes
   case DFRL_F_POLICY_GRAD: *bytes = sizeof(float) * t->policy->n_params; break;
   case DFRL_F_VALUE_GRAD: *bytes = sizeof(float) * (t->value ? t->value->n_params : 0); break;
   case DFRL_F_POLICY_GRAD_LOG: *bytes = sizeof(float) * (size_t)t->epochs * t->policy->n_params; break;
+  case DFRL_F_OBS_START: *bytes = sizeof(float) * LN * t->O; break;
   default:
     dfrl_set_error("unknown field %d", field);
     return DFRL_ERR_INVALID;
@@ -770,6 +791,10 @@ extern "C" int dfrl_trainer_read(dfrl_trainer *t, int field, void *dst_host, siz
   case DFRL_F_POLICY_GRAD: src = t->pgrad_log + (size_t)(t->epochs - 1) * t->policy->n_params; break;
   case DFRL_F_VALUE_GRAD: src = t->vgrad; break;
   case DFRL_F_POLICY_GRAD_LOG: src = t->pgrad_log; break;
+  case DFRL_F_OBS_START:  // observation::to_vector of every recorded start state (encoded on demand)
+    DFRL_TRY(ensure_obs(t));
+    src = t->obs;
+    break;
   }
   if (bytes) {
     DFRL_CUDA(cudaMemcpyAsync(dst_host, src, bytes, cudaMemcpyDeviceToHost, s));

@@ -20,6 +20,7 @@ struct dfrl_trainer {
   // learn workspace
   float *obs;  // [2][L*n][O]: start rows, then end rows (layered kernels only)
   bool obs_valid;  // start rows of `obs` hold the observations of the current records
+  bool critic_was_fused;  // the last VALUE | ADVANTAGE phase ran on the fused kernels (no end-row observations encoded)
   float *v_start, *v_end, *targets, *adv, *dyv, *dprobs;
   float *pgrad_log, *vgrad;
   float *pstate, *vstate;

@@ -7,6 +7,55 @@
 #include <apps/bin_packing/bin_packing.h>
 
 static int fails = 0;
+
+// A user's learner that specialises the reference's hook (policy_gradient.h:187): here it restates the
+// PPO-clip optimize_action (297-307) with host callbacks, as a reference user would write it.
+class my_ppo_learner : public xylo::actor_critic_learner<bp::action, bp::observation> {
+public:
+  using xylo::actor_critic_learner<bp::action, bp::observation>::actor_critic_learner;
+  int calls = 0;
+  std::size_t rows_seen = 0;
+
+protected:
+  void optimize_action(xylo::matrix_view states, const std::vector<bp::action> &actions,
+                       xylo::vector_view advantages) override {
+    ++calls;
+    rows_seen = states.num_rows();
+    for (int k = 0; k < 4; ++k)
+      this->policy_optimizer_.step(states, [&](xylo::matrix_view probs) {
+        xylo::matrix g(probs.shape());
+        for (std::size_t i = 0; i < probs.num_rows(); ++i)
+          actions[i].clipped_gradient(probs[i], g[i], advantages[i]);
+        return g;
+      });
+  }
+};
+
+// An agent whose reward rule differs from the one the environment kernel implements.
+class odd_agent : public xylo::agent<bp::action, bp::observation> {
+public:
+  using xylo::agent<bp::action, bp::observation>::agent;
+
+private:
+  bool game_over(const bp::observation &ob) override { return ob.bins[0].first < 0; }
+  float get_reward(const bp::observation &, const bp::observation &) override { return 2.f; }
+};
+
+static void build_c2_nets(xylo::model &pm, xylo::model &vm) {
+  pm.add_layer(std::make_unique<xylo::full_layer>(32, 64));
+  pm.add_layer(std::make_unique<xylo::relu_activation>());
+  pm.add_layer(std::make_unique<xylo::full_layer>(64, 64));
+  pm.add_layer(std::make_unique<xylo::relu_activation>());
+  pm.add_layer(std::make_unique<xylo::full_layer>(64, 8));
+  pm.add_layer(std::make_unique<xylo::softmax_layer>());
+  vm.add_layer(std::make_unique<xylo::full_layer>(32, 64));
+  vm.add_layer(std::make_unique<xylo::relu_activation>());
+  vm.add_layer(std::make_unique<xylo::full_layer>(64, 64));
+  vm.add_layer(std::make_unique<xylo::relu_activation>());
+  vm.add_layer(std::make_unique<xylo::full_layer>(64, 1));
+  pm.set_init_seed(1234);
+  vm.set_init_seed(1235);
+}
 #define EXPECT(c)                                                  \
   do {                                                             \
     if (!(c)) {                                                    \
@@ -144,6 +193,67 @@ int main() {
     EXPECT(s.env_steps == (long long)(n * T * iters));
     std::printf("ppo env_steps %lld episodes %lld reward_sum %.0f policy_sum %.17g value_sum %.17g\n", s.env_steps,
                 s.episodes, s.reward_sum, ps, vs);
+  }
+  // ---- optimize_action hook: a user override (host callbacks) against the built-in device PPO on the
+  //      same seeds; both see the same rollouts, critic steps and advantages
+  {
+    const std::size_t n = 96;
+    const int T = 4, iters = 2;
+    xylo::vector pa({1}), pb({1}), va({1}), vb({1});
+    int calls = 0;
+    std::size_t rows_seen = 0;
+    for (int user = 0; user < 2; ++user) {
+      xylo::model pm, vm;
+      build_c2_nets(pm, vm);
+      xylo::sgd_optimizer po(pm, 1e-4f), vo(vm, 1e-5f);
+      xylo::replay_buffer<bp::action, bp::observation> rb;
+      bp::environment env(n, 77);
+      xylo::policy_gradient_policy<bp::action, bp::observation> policy(pm);
+      bp::agent agent(policy, env, rb);
+      std::unique_ptr<xylo::learner<bp::action, bp::observation>> learner;
+      my_ppo_learner *mine = nullptr;
+      if (user)
+        learner.reset(mine = new my_ppo_learner(rb, pm, po, vm, vo, 0.99f));
+      else
+        learner.reset(new bp::ppo_learner(rb, pm, po, vm, vo, 0.99f));
+      for (int it = 0; it < iters; ++it) {
+        agent.play_steps(T);
+        learner->step();
+        rb.forget();
+      }
+      (user ? pb : pa) = pm.parameters();
+      (user ? vb : va) = vm.parameters();
+      if (mine)
+        calls = mine->calls, rows_seen = mine->rows_seen;
+    }
+    EXPECT(calls == iters && rows_seen == n * T);
+    double num = 0, den = 0, vdiff = 0;
+    for (std::size_t i = 0; i < pa.size(); ++i)
+      num += (double)(pa[i] - pb[i]) * (pa[i] - pb[i]), den += (double)pa[i] * pa[i];
+    for (std::size_t i = 0; i < va.size(); ++i)
+      vdiff += std::fabs(va[i] - vb[i]);
+    EXPECT(std::sqrt(num / den) < 1e-5);  // same policy steps (layered fp32 kernels vs the fused bf16x3 kernels)
+    EXPECT(vdiff == 0);                   // the critic phase is the same device code in both runs
+    std::printf("hook calls %d rows %zu policy_rel_diff %.3g\n", calls, rows_seen, std::sqrt(num / den));
+  }
+  // ---- an agent whose game_over / get_reward differ from the device rule is rejected, not ignored
+  {
+    xylo::model pm, vm;
+    build_c2_nets(pm, vm);
+    xylo::sgd_optimizer po(pm, 1e-4f), vo(vm, 1e-5f);
+    xylo::replay_buffer<bp::action, bp::observation> rb;
+    bp::environment env(8, 3);
+    xylo::policy_gradient_policy<bp::action, bp::observation> policy(pm);
+    odd_agent agent(policy, env, rb);
+    bp::ppo_learner learner(rb, pm, po, vm, vo, 0.99f);
+    bool threw = false;
+    try {
+      agent.play_steps(2);
+    } catch (const xeno::error &) {
+      threw = true;
+    }
+    EXPECT(threw);
+    std::printf("odd_agent rejected %d\n", (int)threw);
   }
   std::printf(fails ? "FAILED %d\n" : "OK\n", fails);
   return fails ? 1 : 0;

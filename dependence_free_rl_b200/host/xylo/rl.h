@@ -227,6 +227,7 @@ public:
     }
     if (s.algo != DFRL_ALGO_REINFORCE)
       throw xeno::error("play_one_episode needs the REINFORCE learner (episodic records)");
+    verify_rules();
     s.ensure_trainer(1);
     check(dfrl_trainer_rollout(s.trainer, nullptr, nullptr, nullptr));
     s.rolled = true;
@@ -236,6 +237,7 @@ public:
     rollout_store &s = replay_buffer_.store();
     if (s.algo == DFRL_ALGO_REINFORCE)
       throw xeno::error("the REINFORCE learner records whole episodes: use play_one_episode()");
+    verify_rules();
     s.ensure_trainer((int)n);
     check(dfrl_trainer_rollout(s.trainer, nullptr, nullptr, nullptr));
     s.rolled = true;
@@ -244,6 +246,7 @@ public:
   // Parity runs: teacher-forced rollout from host tapes, all [n][size()] step-major (dfrl.h).
   void play_steps(std::size_t n, const uint8_t *items, const uint8_t *actions, const double *uniforms) {
     rollout_store &s = replay_buffer_.store();
+    verify_rules();
     s.ensure_trainer((int)n);
     check(dfrl_trainer_rollout(s.trainer, items, actions, uniforms));
     s.rolled = true;
@@ -252,10 +255,31 @@ public:
   std::size_t id() { return id_; }
 
 protected:
-  // Kept for signature compatibility; the bin-packing rules they express (bin_packing.h:94-106)
-  // run inside the environment kernel.
+  // The rules these two express (bin_packing.h:94-106: done = some bin dimension negative, reward =
+  // done ? 0 : 1) run inside the environment kernel, which never calls back into host code. An
+  // override expressing a DIFFERENT rule must not be ignored silently: before the first rollout it is
+  // evaluated on a live state of slot id_ and on that state with one bin overflowed, and an answer
+  // that differs from the device rule is an error.
   virtual bool game_over(const S &state) = 0;
   virtual float get_reward(const S &state1, const S &state2) = 0;
+
+  void verify_rules() {
+    if (rules_checked_)
+      return;
+    rules_checked_ = true;
+    const S live = env_.view(id_);  // finished slots are reset on the device: live states are never terminal
+    if (game_over(live) || get_reward(live, live) != 1.f)
+      throw xeno::error("agent::game_over / get_reward differ from the rule the environment kernel implements "
+                        "(bin_packing.h:94-106); the device path cannot honour the override");
+    if constexpr (requires(S t) { t.bins[0].first = -1; }) {
+      S over = live;
+      over.bins[0].first = -1;
+      if (!game_over(over) || get_reward(live, over) != 0.f)
+        throw xeno::error("agent::game_over / get_reward differ from the rule the environment kernel implements "
+                          "(bin_packing.h:94-106); the device path cannot honour the override");
+    }
+  }
+  bool rules_checked_ = false;
 
   std::size_t id_;
   const policy<A, S> &policy_;

@@ -355,6 +355,13 @@ int dfrl_trainer_rollout(dfrl_trainer *tr, const uint8_t *items_host, const uint
                          const double *u_host);
 /* learner::step() then replay_buffer::forget() (ppo_training.cc:63-65). */
 int dfrl_trainer_learn(dfrl_trainer *tr);
+/* The phases of actor_critic_learner::learn (policy_gradient.h:159-185) one by one, for the host
+ * mirror's optimize_action hook (policy_gradient.h:187-194, 297-307, 318-330 are virtual overrides of
+ * it): VALUE = update_value_model (196-218), ADVANTAGE = calculate_advantage with the updated critic
+ * (220-281) -- these two run together --, POLICY = the learner's own optimize_action (one step, k
+ * PPO-clip steps, k KL-PPO steps). DFRL_PHASE_ALL is dfrl_trainer_learn. */
+enum { DFRL_PHASE_VALUE = 1, DFRL_PHASE_ADVANTAGE = 2, DFRL_PHASE_POLICY = 4, DFRL_PHASE_ALL = 7 };
+int dfrl_trainer_learn_phases(dfrl_trainer *tr, int phases);
 /* `iters` x (rollout; learn) free-running, no host round trips between iterations. */
 int dfrl_trainer_iterate(dfrl_trainer *tr, int iters);
 
@@ -369,7 +376,8 @@ enum {
   DFRL_F_VALUE_TARGET = 6,/* fp32  [L][N] */
   DFRL_F_POLICY_GRAD = 7, /* fp32  [P] last policy gradient (after all-reduce) */
   DFRL_F_VALUE_GRAD = 8,  /* fp32  [Pv] last value gradient */
-  DFRL_F_POLICY_GRAD_LOG = 9 /* fp32 [epochs][P] every policy gradient of the last learn() */
+  DFRL_F_POLICY_GRAD_LOG = 9, /* fp32 [epochs][P] every policy gradient of the last learn() */
+  DFRL_F_OBS_START = 10   /* fp32  [L][N][4B] observation::to_vector of every recorded start state */
 };
 int dfrl_trainer_field_size(dfrl_trainer *tr, int field, size_t *bytes);
 int dfrl_trainer_read(dfrl_trainer *tr, int field, void *dst_host, size_t bytes);

@@ -34,6 +34,9 @@ def test_host_mirror_builds_and_keeps_reference_signatures():
     for cls in ["policy_gradient_learner", "actor_critic_learner", "ppo_learner", "kl_ppo_learner",
                 "policy_gradient_policy", "policy_gradient_deterministic_policy"]:
         assert f"class {cls}" in pg, cls
+    # the reference's specialisation hook (policy_gradient.h:187) and the rule check of agent::game_over / get_reward
+    assert "virtual void optimize_action(matrix_view" in pg and "const std::vector<A> &" in pg
+    assert "void verify_rules()" in rl
     for sig in ["virtual matrix forward(matrix_view t) = 0;", "virtual matrix backward(matrix_view input, matrix_view loss) = 0;",
                 "virtual vector gradient(matrix_view input, matrix_view backprop) = 0;",
                 "void step(matrix_view input, const loss_grad_func &loss_grad)",
@@ -56,6 +59,10 @@ def test_host_api_matches_python_binding(D, ctx):
     lines = {l.split()[0]: l.split()[1:] for l in out.stdout.splitlines() if l and not l.startswith("OK")}
     assert "FAIL" not in out.stdout
     got = dict(zip(lines["ppo"][0::2], lines["ppo"][1::2]))
+    # a user's optimize_action override was called once per learn() with every start row; an agent
+    # with a different game_over / get_reward rule was rejected
+    assert lines["hook"][:4] == ["calls", "2", "rows", "384"], lines["hook"]
+    assert lines["odd_agent"] == ["rejected", "1"]
     # the same run through the Python binding
     n, T, iters = 4096, 4, 5
     rs = np.float32(32.0) / np.float32(n * T)

@@ -17,5 +17,6 @@ d = np.diff(a, axis=1)
 print("tile totals of one warpgroup (cycles):", (a[1:, 0] - a[:-1, 0]))
 for j, nm in enumerate(names):
     print(f"{nm:18s}", d[1:, j])
-e = np.array(buf[104:108])
-print("entry -> setup done", e[1] - e[0], " setup -> loop end", e[2] - e[1], " drain", e[3] - e[2], " total", e[3] - e[0])
+e = np.array(buf[104:110])
+print("entry -> setup done", e[1] - e[0], " setup -> loop end", e[2] - e[1], " drain (TMEM -> partials)", e[4] - e[2],
+      " grid barrier", e[5] - e[4], " slice reduction + update", e[3] - e[5], " total", e[3] - e[0])
