@@ -576,13 +576,18 @@ def run_ours(args):
         extra["ppo_T32"] = quick_rate(D, ctx, make_trainer(D, ctx, n // 8, 0, (n // 8) * 32, work=32), n // 8, 32, 3, 20)
         # Adam (north_star names it; the reference apps use SGD): device-side step counter, same CUDA graph
         extra["ppo_adam"] = quick_rate(D, ctx, make_trainer(D, ctx, n, 0, n * T_STEPS, opt=D.ADAM, lr_scale=0.1), n, T_STEPS, 5, 50)
-        # the reference's own default nets (ppo_training.cc:10-26: conv1d 4-128-64-1 softmax policy, FC
-        # 32-64-32-1 critic) at 4096 envs: layered path (conv1d products on the tcgen05 GEMMs), beside the
-        # reference's CPU rate for the same nets below
-        extra["reference_nets_4096_envs"] = quick_rate(
-            D, ctx, make_trainer(D, ctx, 4096, 0, 4096 * T_STEPS, player=D.conv_layers([4, 128, 64, 1], D.SOFTMAX),
-                                 vlayer=D.fc_layers([32, 64, 32, 1])), 4096, T_STEPS, 3, 20)
-        extra["reference_nets_4096_envs"]["algorithmic_flop_per_env_step"] = 2296208
+        # the reference's own default nets (ppo_training.cc:10-26: conv1d 4-128-64-1 softmax policy over the
+        # 8 bins, FC 32-64-32-1 critic) on the fused tcgen05 kernels (fused_conv.cuh + the fused critic
+        # kernels, CUDA-graphed learn phase), at 4096 envs (beside the reference's CPU rate for the same
+        # nets below) and at the headline batch size
+        for n_ref, key in ((4096, "reference_nets_4096_envs"), (n, "reference_nets_%d_envs" % n)):
+            row = quick_rate(
+                D, ctx, make_trainer(D, ctx, n_ref, 0, n_ref * T_STEPS, player=D.conv_layers([4, 128, 64, 1], D.SOFTMAX),
+                                     vlayer=D.fc_layers([32, 64, 32, 1])), n_ref, T_STEPS, 3, 20)
+            row["algorithmic_flop_per_env_step"] = 2296208
+            row["algorithmic_tflops_whole_step"] = row["value"] * 2296208 / 1e12
+            row["frac_of_bf16_peak"] = row["algorithmic_tflops_whole_step"] / peaks["bf16_tflops_sustained"]
+            extra[key] = row
         extra["hbm_kernels"] = hbm_kernel_rows(D, ctx, peaks)
     if world == 1 and not args.no_c2:
         # BASELINE configs[1] verbatim: PPO, 4096 parallel envs, 1 GPU (latency-bound size)

@@ -69,6 +69,7 @@ PROTOTYPES = {
     "dfrl_debug_critic_clocks": (i32, [vp, vp, i32]),
     "dfrl_debug_set_fused_ctas": (i32, [vp, i32]),
     "dfrl_debug_set_vend": (i32, [vp, i32]),
+    "dfrl_trainer_fused_coverage": (i32, [vp, C.POINTER(i32)]),
     "dfrl_p2p_export": (i32, [vp, vp]),
     "dfrl_p2p_attach": (i32, [vp, vp]),
     "dfrl_p2p_attached": (i32, [vp]),

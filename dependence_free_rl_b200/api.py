@@ -20,6 +20,7 @@ HEUR_RANDOM, HEUR_FIRSTFIT, HEUR_BESTFIT, HEUR_MINWASTE = 0, 1, 2, 3
 (F_REC_STATE, F_REC_ACTION, F_REC_DONE, F_REC_PROBS, F_REC_LEN, F_ADVANTAGE, F_VALUE_TARGET,
  F_POLICY_GRAD, F_VALUE_GRAD, F_POLICY_GRAD_LOG, F_OBS_START) = range(11)
 PHASE_VALUE, PHASE_ADVANTAGE, PHASE_POLICY, PHASE_ALL = 1, 2, 4, 7
+FUSED_ROLLOUT, FUSED_CRITIC, FUSED_POLICY, FUSED_GRAPH = 1, 2, 4, 8
 
 
 def _ptr(a):
@@ -392,6 +393,15 @@ class Trainer:
     def _stats_dict(s):
         return {"env_steps": s.env_steps, "episodes": s.episodes, "reward_sum": s.reward_sum,
                 "last_mean_reward": s.last_mean_reward, "kl_beta": s.kl_beta}
+
+    def fused_coverage(self):
+        """Mask of FUSED_ROLLOUT | FUSED_CRITIC | FUSED_POLICY | FUSED_GRAPH: phases on the tcgen05 kernels."""
+        m = C.c_int()
+        check(lib.dfrl_trainer_fused_coverage(self.h, C.byref(m)))
+        return m.value
+
+    def fused_covers_iteration(self):
+        return (self.fused_coverage() & 7) == 7
 
     def stats(self):
         s = _lib.TrainerStats()

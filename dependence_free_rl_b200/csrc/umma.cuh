@@ -183,6 +183,14 @@ __device__ __forceinline__ void split8(const float *x, uint4 &hi, uint4 &lo) {
 }
 
 // One lane of a fully converged warp.
+// Programmatic dependent launch (the fused kernels are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization): launch_dependents lets the NEXT kernel of the
+// stream be scheduled as soon as every CTA of this grid has issued it (its CTAs still need this grid's
+// shared memory / tensor memory to be released, but the launch latency is off the critical path);
+// wait blocks until the PREVIOUS grid has completed and its memory is visible. No-ops without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(

@@ -1,10 +1,14 @@
 // ppo_training -- the reference trainer main (apps/bin_packing/ppo_training.cc) on the device.
 // Same phases: rollout (agent.play_steps) -> learner.step() -> replay_buffer.forget() -> periodic
 // argmax evaluation. The 8 worker threads x 8 environments become one batched environment.
-//   ppo_training [num_envs] [iterations] [eval_every]
+//   ppo_training [num_envs] [iterations] [eval_every] [nets]
+// nets = "ref" (default): the reference's own nets, line for line (ppo_training.cc:10-26: conv1d_1
+// 4-128-64-1 softmax policy over the 8 bins, critic 32-64-32-1); "c2": the BASELINE configs[1] nets
+// (policy 32-64-64-8 softmax, critic 32-64-64-1). Both run on the fused tcgen05 kernels.
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <memory>
 
 #include <xylo/nn.h>
@@ -20,21 +24,36 @@ int main(int argc, char **argv) {
   // gradients are SUMS over rows (nn.h:94-98): the reference rates are tuned to 8 x 4 = 32 rows
   const float row_scale = 32.f / float(num_envs * steps_per_worker);
 
-  xylo::model action_model;
-  action_model.add_layer(std::make_unique<xylo::full_layer>(4 * bp::num_bins, 64));
-  action_model.add_layer(std::make_unique<xylo::relu_activation>());
-  action_model.add_layer(std::make_unique<xylo::full_layer>(64, 64));
-  action_model.add_layer(std::make_unique<xylo::relu_activation>());
-  action_model.add_layer(std::make_unique<xylo::full_layer>(64, bp::num_bins));
-  action_model.add_layer(std::make_unique<xylo::softmax_layer>());
-  xylo::sgd_optimizer action_optimizer(action_model, 1e-4 * row_scale);
+  const bool c2 = argc > 4 && std::strcmp(argv[4], "c2") == 0;
 
+  xylo::model action_model;
   xylo::model value_model;
-  value_model.add_layer(std::make_unique<xylo::full_layer>(4 * bp::num_bins, 64));
-  value_model.add_layer(std::make_unique<xylo::relu_activation>());
-  value_model.add_layer(std::make_unique<xylo::full_layer>(64, 64));
-  value_model.add_layer(std::make_unique<xylo::relu_activation>());
-  value_model.add_layer(std::make_unique<xylo::full_layer>(64, 1));
+  if (c2) {
+    action_model.add_layer(std::make_unique<xylo::full_layer>(4 * bp::num_bins, 64));
+    action_model.add_layer(std::make_unique<xylo::relu_activation>());
+    action_model.add_layer(std::make_unique<xylo::full_layer>(64, 64));
+    action_model.add_layer(std::make_unique<xylo::relu_activation>());
+    action_model.add_layer(std::make_unique<xylo::full_layer>(64, bp::num_bins));
+    action_model.add_layer(std::make_unique<xylo::softmax_layer>());
+    value_model.add_layer(std::make_unique<xylo::full_layer>(4 * bp::num_bins, 64));
+    value_model.add_layer(std::make_unique<xylo::relu_activation>());
+    value_model.add_layer(std::make_unique<xylo::full_layer>(64, 64));
+    value_model.add_layer(std::make_unique<xylo::relu_activation>());
+    value_model.add_layer(std::make_unique<xylo::full_layer>(64, 1));
+  } else {
+    action_model.add_layer(std::make_unique<xylo::convolution1d_1_layer>(4, 128));
+    action_model.add_layer(std::make_unique<xylo::relu_activation>());
+    action_model.add_layer(std::make_unique<xylo::convolution1d_1_layer>(128, 64));
+    action_model.add_layer(std::make_unique<xylo::relu_activation>());
+    action_model.add_layer(std::make_unique<xylo::convolution1d_1_layer>(64, 1));
+    action_model.add_layer(std::make_unique<xylo::softmax_layer>());
+    value_model.add_layer(std::make_unique<xylo::full_layer>(4 * bp::num_bins, 64));
+    value_model.add_layer(std::make_unique<xylo::relu_activation>());
+    value_model.add_layer(std::make_unique<xylo::full_layer>(64, 32));
+    value_model.add_layer(std::make_unique<xylo::relu_activation>());
+    value_model.add_layer(std::make_unique<xylo::full_layer>(32, 1));
+  }
+  xylo::sgd_optimizer action_optimizer(action_model, 1e-4 * row_scale);
   xylo::sgd_optimizer value_optimizer(value_model, 1e-5 * row_scale);
   action_model.set_init_seed(1234);
   value_model.set_init_seed(1235);

@@ -412,6 +412,12 @@ int dfrl_debug_set_fused_ctas(dfrl_trainer *tr, int ctas);
 /* Test hook: 1 forces / 0 forbids the compacted V(end-state) pre-pass of the fused critic-step and
  * GAE kernels (policy_gradient.h:196-281 need V(end) only where a trajectory ends); -1: by batch size. */
 int dfrl_debug_set_vend(dfrl_trainer *tr, int mode);
+/* Which phases of this trainer run on the fused tcgen05 kernels (the rest runs on the layered
+ * kernels): a mask of DFRL_FUSED_*. ROLLOUT = agent::play_steps (rl.h:325-360), CRITIC =
+ * update_value_model + calculate_advantage (policy_gradient.h:196-281), POLICY = optimize_action
+ * (187-194, 297-307), GRAPH = learn() replays as one CUDA graph. */
+enum { DFRL_FUSED_ROLLOUT = 1, DFRL_FUSED_CRITIC = 2, DFRL_FUSED_POLICY = 4, DFRL_FUSED_GRAPH = 8 };
+int dfrl_trainer_fused_coverage(dfrl_trainer *tr, int *mask);
 
 /* deep_agent.cc:28-41 / the periodic eval of the trainer mains (ppo_training.cc:67-81): every
  * env of `env` plays `episodes` episodes with policy_gradient_deterministic_policy (argmax) on

@@ -654,6 +654,28 @@ def _safe_params(dims, seed, bias=5.0):
     return np.concatenate(parts)
 
 
+def _conv_safe_params(dims, seed, bias=2.0):
+    """Mask-stable AND well-conditioned parameters for a conv1d_1 net 4-D1-D2-1. The net's 8 outputs
+    per sample go through a softmax, so the output gradients of a sample's 8 rows sum to ~0 and every
+    weight gradient depends only on how the activations VARY across a sample's bins: with the +-5
+    biases of _safe_params that variation is ~1 % of the activations and rounding differences (2^-17
+    relative on the tensor pipe) would be amplified 100 x. Here: hidden biases of +-bias, layer 1
+    |W1 . x| <= 4 * 0.4 (x in [0, 1]) < bias, layer 2 weights with zero sum over the always-on units
+    of layer 1 (no common-mode shift), so pre-activations stay ~bias +- 0.25 * 6 sigma away from zero
+    while the activations vary by ~10-20 % across rows."""
+    r = np.random.default_rng(seed)
+    d0, d1, d2, d3 = dims
+    on1 = np.arange(d1) % 2 == 0
+    w1 = r.uniform(-0.4, 0.4, (d1, d0))
+    b1 = np.where(on1, bias, -bias) + r.uniform(-0.05, 0.05, d1)
+    w2 = r.uniform(-0.1, 0.1, (d2, d1))
+    w2[:, on1] -= w2[:, on1].mean(axis=1, keepdims=True)
+    b2 = np.where(np.arange(d2) % 2 == 0, bias, -bias) + r.uniform(-0.05, 0.05, d2)
+    w3 = r.uniform(-0.3, 0.3, (d3, d2))
+    b3 = r.uniform(-0.05, 0.05, d3)
+    return np.concatenate([w1.ravel(), b1, w2.ravel(), b2, w3.ravel(), b3]).astype(np.float32)
+
+
 @pytest.mark.parametrize("algo_name,n,T,B,pdims,vdims", [
     # 32 bins (O = 128): layered path; 1200 x 4 = 4800 learner rows put the 64-wide products on
     # the tcgen05 GEMMs of gemm_umma.cu, the rest on the FFMA kernels
@@ -666,15 +688,22 @@ def _safe_params(dims, seed, bias=5.0):
     # 16-wide hidden layers (the second instantiation of the fused kernels: one epilogue thread per
     # row in the critic step, K = 16 single-chunk TMEM operands), PPO, 3 CTAs
     ("ppo@3", 700, 4, 8, [32, 16, 16, 8], [32, 16, 16, 1]),
+    # the reference's own critic 32-64-32-1 (ppo_training.cc:19-26) on the fused critic / GAE / V(end) kernels
+    ("ppo@3", 650, 4, 8, [32, 64, 64, 8], [32, 64, 32, 1]),
+    # (the reference's conv1d policies on the fused kernels: tests/test_gpu_scale.py, flip-aware, He init --
+    #  mask-stable "safe" parameters make a conv net's gradient ill-conditioned: see _conv_safe_params)
 ])
 def test_trainer_variants_vs_oracle(D, ctx, orc, algo_name, n, T, B, pdims, vdims):
     algo_name, _, cap = algo_name.partition("@")
     algo, oalgo = (D.PPO, orc.PPO) if algo_name == "ppo" else (D.ACTOR_CRITIC, orc.ACTOR_CRITIC)
     last = D.SOFTMAX if algo_name == "ppo" else D.SOFTMAX_CE
     rng = np.random.default_rng(5)
-    pl, vl = D.fc_layers(pdims, last), D.fc_layers(vdims)
+    conv = isinstance(pdims, tuple)
+    if conv:
+        pdims = pdims[1]
+    pl, vl = (D.conv_layers if conv else D.fc_layers)(pdims, last), D.fc_layers(vdims)
     pnet, vnet = orc.Net(pl, 4 * B), orc.Net(vl, 4 * B)
-    pp, vp = _safe_params(pdims, 11), _safe_params(vdims, 12)
+    pp, vp = (_conv_safe_params(pdims, 11) if conv else _safe_params(pdims, 11)), _safe_params(vdims, 12)
     policy, value = D.Model(ctx, pl, 4 * B), D.Model(ctx, vl, 4 * B)
     policy.set_parameters(pp)
     value.set_parameters(vp)
@@ -684,6 +713,8 @@ def test_trainer_variants_vs_oracle(D, ctx, orc, algo_name, n, T, B, pdims, vdim
     env.set_state(st)
     tr = D.Trainer(ctx, env, policy, value, algo=algo, work=T, policy_lr=2e-8, value_lr=2e-8,
                    action_mode=D.ACT_SAMPLE)
+    if conv:  # the whole iteration runs on the fused kernels (fused_conv.cuh + the fused critic kernels)
+        assert tr.fused_covers_iteration()
     if cap:
         D._lib.check(D._lib.lib.dfrl_debug_set_fused_ctas(tr.h, int(cap)))
         D._lib.check(D._lib.lib.dfrl_debug_set_vend(tr.h, 1))  # the capped cases also take the compacted V(end) pre-pass

@@ -24,11 +24,12 @@ pytestmark = pytest.mark.gpu
 PD, VD = [32, 64, 64, 8], [32, 64, 64, 1]
 
 
-def _setup(D, ctx, orc, n, T, algo, seed):
+def _setup(D, ctx, orc, n, T, algo, seed, conv=None, vd=None):
+    """conv = [4, D1, D2, 1]: the reference's conv1d_1 policy (He init, nn.h:16-18) instead of the dense PD net."""
     B = 8
     shared = algo == "ac_shared"
     last = D.SOFTMAX if algo == "ppo" else D.SOFTMAX_CE
-    pl, vl = D.fc_layers(PD, last), D.fc_layers(VD)
+    pl, vl = (D.conv_layers(conv, last) if conv else D.fc_layers(PD, last)), D.fc_layers(vd or VD)
     policy = D.Model(ctx, pl, 32)
     policy.init_parameters(seed)
     if shared:  # one flat vector [trunk | policy head | value head] (tests/test_shared_trunk.py)
@@ -42,7 +43,10 @@ def _setup(D, ctx, orc, n, T, algo, seed):
         value.init_parameters(seed + 1)
         pnet, vnet = orc.Net(pl, 32), orc.Net(vl, 32)
         pp, vp = policy.parameters(), value.parameters()
-    assert abs(pp[:32 * 64].std() - 0.01) < 1e-3 and np.all(pp[32 * 64:32 * 64 + 64] == 0)  # reference init
+    if conv:
+        assert abs(pp[:4 * conv[1]].std() - np.sqrt(2 / 4)) < 0.1 and np.all(pp[4 * conv[1]:5 * conv[1]] == 0)  # He init
+    else:
+        assert abs(pp[:32 * 64].std() - 0.01) < 1e-3 and np.all(pp[32 * 64:32 * 64 + 64] == 0)  # reference init
     rng = np.random.default_rng(seed + 2)
     ecfg = orc.env_cfg(B)
     st = orc.env_reset_all(ecfg, n, rng.integers(0, 2, n).astype(np.uint8))
@@ -57,7 +61,7 @@ def _setup(D, ctx, orc, n, T, algo, seed):
     return dict(policy=policy, value=value, env=env, tr=tr, lr=lr, st=st, ecfg=ecfg, pnet=pnet, rng=rng, plr=plr)
 
 
-def _iteration(D, orc, S, n, T, algo, it):
+def _iteration(D, orc, S, n, T, algo, it, conv=None):
     tr, lr, st, rng = S["tr"], S["lr"], S["st"], S["rng"]
     items = rng.integers(0, 2, (T, n)).astype(np.uint8)
     st0 = st.copy()
@@ -89,8 +93,10 @@ def _iteration(D, orc, S, n, T, algo, it):
     adv = out["adv"].reshape(-1).astype(np.float64)
     p_old_a = ro["probs"].reshape(-1, 8)[np.arange(T * n), actions].astype(np.float64)
     log = tr.read(D.F_POLICY_GRAD_LOG)
-    NP = 6792  # the policy net's own parameters lead the vector ([trunk | policy head | value head] when shared)
     kind = flipcheck.PPO if algo == "ppo" else flipcheck.AC
+    if conv:
+        return _conv_policy_reports(S, lr, out, log, obs, actions, adv, p_old_a, kind, conv, pp0, it)
+    NP = 6792  # the policy net's own parameters lead the vector ([trunk | policy head | value head] when shared)
     # (shared trunk: the critic step has already moved the trunk when the actor step runs)
     params = pp0.copy() if algo != "ac_shared" else (lr.pparams + out["policy_grads"][0] * np.float32(S["plr"])).astype(np.float32)
     reports = []
@@ -104,6 +110,53 @@ def _iteration(D, orc, S, n, T, algo, it):
     close(S["policy"].parameters(), lr.pparams, what=f"it {it} policy params")
     close(S["value"].parameters(), lr.vparams, what=f"it {it} value params")
     return reports
+
+
+def _conv_policy_reports(S, lr, out, log, obs, actions, adv, p_old_a, kind, dims, pp0, it):
+    """Flip-aware comparison for a conv1d_1 policy: the net is the dense net `dims` = [4, D1, D2, 1]
+    over the (sample, bin) rows (nn.h:127-147), row = 8 * sample + bin; the gradient at a row's scalar
+    output is its sample's logit gradient (float64 forward of the whole batch)."""
+    R = obs.shape[0]
+    xr = np.asarray(obs, np.float64).reshape(R * 8, 4)
+    params = pp0.copy()
+    reports = []
+    for e in range(log.shape[0]):
+        (W1, b1), (W2, b2), (W3, b3) = flipcheck.split_params(params, dims)
+        h2 = np.maximum(np.maximum(xr @ W1.T + b1, 0.0) @ W2.T + b2, 0.0)
+        logits = (h2 @ W3.T + b3).reshape(R, 8)
+        DL = flipcheck.policy_dlogits(logits, actions, adv, p_old_a, kind).reshape(R * 8, 1)
+        Dm, cand = flipcheck.ambiguous_directions(xr.astype(np.float32), params, dims, lambda rows, o: DL[rows])
+        reports.append(flipcheck.flip_close(log[e], out["policy_grads"][e], Dm, what=f"it {it} conv policy gradient {e}"))
+        params = (params - out["policy_grads"][e] * np.float32(S["plr"])).astype(np.float32)
+    close(S["policy"].parameters(), lr.pparams, what=f"it {it} policy params")
+    close(S["value"].parameters(), lr.vparams, what=f"it {it} value params")
+    return reports
+
+
+@pytest.mark.parametrize("algo,n,T,iters,conv,cap", [
+    ("ppo", 4096, 4, 2, [4, 128, 64, 1], 0),   # ppo_training.cc:10-26 nets at the bench's reference_nets_4096_envs size
+    ("ppo", 700, 4, 2, [4, 128, 64, 1], 3),    # 3 CTAs: 59 tiles per CTA (steady state of the tile loop, both observation slots)
+    ("ppo", 37, 4, 1, [4, 128, 64, 1], 0),     # ragged: 148 samples = 9.25 tiles
+    ("ac", 2048, 8, 2, [4, 64, 32, 1], 0),     # ac_training.cc:9-25 nets
+    ("ppo", 500, 4, 1, [4, 64, 32, 1], 2),
+])
+def test_reference_nets_fused_vs_oracle64(D, ctx, orc, algo, n, T, iters, conv, cap):
+    """The reference's OWN default nets (conv1d_1 policy over the 8 bins, He init; critic 32-64-32-1,
+    N(0, 0.01) init) on the fused tcgen05 kernels (fused_conv.cuh + the fused critic kernels) against the
+    double-accumulating oracle: transitions bit-exact, values / advantages / gradients within 1e-4."""
+    S = _setup(D, ctx, orc, n, T, algo, seed=11, conv=conv, vd=[32, 64, 32, 1])
+    assert S["tr"].fused_covers_iteration()
+    if cap:
+        D._lib.check(D._lib.lib.dfrl_debug_set_fused_ctas(S["tr"].h, cap))
+    p0 = S["policy"].parameters().copy()
+    for it in range(iters):
+        for e, r in enumerate(_iteration(D, orc, S, n, T, algo, it, conv=conv)):
+            print(f"[{algo} conv {n}x{T}] iteration {it} policy gradient {e}: raw norm-wise error {r['raw']:.2e}, "
+                  f"{r['ambiguous']} relu-ambiguous units ({r['flipped']} flipped), residual {r['residual']:.2e}")
+            assert r["ambiguous"] < 0.35 * p0.size
+    assert np.any(S["policy"].parameters() != p0)
+    for k in ("tr", "env", "value", "policy"):
+        S[k].close()
 
 
 @pytest.mark.parametrize("algo,n,T,iters", [

@@ -103,7 +103,8 @@ def test_deep_agent_cpp_known_answer(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("binary,args", [("ppo_training", ["4096", "6", "5"]), ("ac_training", ["2048", "4"]),
+@pytest.mark.parametrize("binary,args", [("ppo_training", ["4096", "6", "5"]), ("ppo_training", ["4096", "6", "5", "c2"]),
+                                         ("ac_training", ["2048", "4"]),
                                          ("pg_training", ["256", "3"])])
 def test_trainer_mains_run(binary, args):
     _build()
