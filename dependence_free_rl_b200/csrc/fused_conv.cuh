@@ -22,6 +22,122 @@
 // Weight-gradient sums stay in tensor memory for all tiles of the CTA (fixed order: bitwise
 // reproducible), then gradient_tail (grid barrier, slice reduction, exchange, optimizer).
 
+// Operand precision: FP16 pairs. The 8 logit gradients of a sample sum to zero, so every weight
+// gradient of a conv1d policy depends only on how the activations DIFFER between a sample's bins
+// (often by 10 % or less of their size: most bins of a young episode are identical): the absolute
+// rounding error of an activation is amplified by that ratio, and the bf16 hi/lo pairs of the dense
+// kernels (2^-17 relative) left a 16-sample reference trace 1.1e-4 off (golden `ppo_refnet_conv`).
+// Here every MMA operand is split x = hi + lo with hi, lo in FP16 (11 + 11 significant bits, 2^-22
+// relative) and a product is hi.hi + hi.lo + lo.hi + lo.lo. FP16's narrow exponent range is handled by
+// power-of-two scales (exact): weights are staged as W * S_W with max|W * S_W| in [2^12, 2^13) and the
+// epilogues multiply the accumulators by 1 / S_W; the gradient chain runs on dY * S_g with max|A| * S_g
+// in [8, 16) over the CTA's own rows (the CTA's partial gradient is multiplied by 1 / S_g in the
+// drain). Activations are used unscaled (|h| < 65504 assumed; an overflow would surface as inf / NaN
+// gradients, not silently).
+__device__ __forceinline__ void split2_h(float a, float b, uint32_t &hi, uint32_t &lo) {
+  __half2 h = __floats2half2_rn(a, b);
+  hi = *reinterpret_cast<uint32_t *>(&h);
+  const float2 hf = __half22float2(h);
+  __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  lo = *reinterpret_cast<uint32_t *>(&l);
+}
+__device__ __forceinline__ void split8_h(const float *x, uint4 &hi, uint4 &lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    split2_h(x[2 * i], x[2 * i + 1], h[i], l[i]);
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+__device__ __forceinline__ uint32_t pack2_h(float a, float b) {  // two values that are exact in fp16
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t *>(&h);
+}
+// 0xffff in each half whose fp16 value is > 0
+__device__ __forceinline__ uint32_t pos_mask2_h(uint32_t w) {
+  uint32_t m;
+  asm("set.gt.u32.f16x2 %0, %1, %2;\n" : "=r"(m) : "r"(w), "r"(0u));
+  return m;
+}
+// Power-of-two scale S with max * S in [target / 2, target) (1 when max == 0 or not finite).
+__device__ __forceinline__ float pow2_scale(float mx, int target_log2) {
+  if (!(mx > 0.f) || !(mx < 3.0e38f))
+    return 1.f;
+  int e;
+  frexpf(mx, &e);  // mx = m 2^e, m in [0.5, 1)
+  return ldexpf(1.f, target_log2 - e);
+}
+// idesc with FP16 operands (a_format = b_format = 0), FP32 accumulation
+template <int N> struct IDH {
+  static constexpr uint32_t FK_FK = make_idesc(128, N, 0, 0, 0, 0);  // forward: A K-major, B K-major
+  static constexpr uint32_t BK_FM = make_idesc(128, N, 0, 0, 0, 1);  // dX: A K-major (tensor memory), B MN-major
+  static constexpr uint32_t BM_FM = make_idesc(128, N, 0, 0, 1, 1);  // dW: both MN-major
+};
+// Block-wide maximum of non-negative values (whole CTA; `red` = 32 floats of shared memory).
+__device__ __forceinline__ float block_max(float v, float *red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0)
+    red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float m = 0.f;
+  for (int w = 0; w < (int)(blockDim.x + 31) / 32; ++w)
+    m = fmaxf(m, red[w]);
+  __syncthreads();
+  return m;
+}
+// Hidden-layer epilogues for FP16-pair operands: as epi2_fwd / epi2_bwd with the weight scale undone.
+template <int D, bool SMEM_STORE>
+__device__ __forceinline__ void conv_epi_fwd(uint32_t acc, const tid_t &t, const float *__restrict__ bias, float inv_s, uint8_t *hi,
+                                             uint8_t *lo, int h0, int h1) {
+#pragma unroll
+  for (int h = h0; h < h1; ++h) {
+    float v[32];
+    tmem_load<32>(acc + t.lane_base + h * 32, v);
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      v[j] = fmaxf(fmaf(v[j], inv_s, bias[h * 32 + j]), 0.f);
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      uint4 hh, ll;
+      split8_h(&v[8 * cc], hh, ll);
+      if (SMEM_STORE) {
+        const int c = h * 4 + cc;
+        const uint32_t off = (uint32_t)(c >> 3) * PANEL + umma::panel_chunk_off(t.row, c & 7);
+        *reinterpret_cast<uint4 *>(hi + off) = hh;
+        *reinterpret_cast<uint4 *>(lo + off) = ll;
+      }
+      tmem_put_chunk<32>(acc + t.lane_base + h * 32, cc, hh, ll);
+    }
+  }
+  umma::tmem_st_wait();
+}
+template <int D>
+__device__ __forceinline__ void conv_epi_bwd(uint32_t acc, const tid_t &t, float inv_s, const uint8_t *act_hi, uint8_t *hi, uint8_t *lo,
+                                             int h0, int h1) {
+#pragma unroll
+  for (int h = h0; h < h1; ++h) {
+    float v[32];
+    tmem_load<32>(acc + t.lane_base + h * 32, v);
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      v[j] *= inv_s;
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      const int c = h * 4 + cc;
+      const uint32_t off = (uint32_t)(c >> 3) * PANEL + umma::panel_chunk_off(t.row, c & 7);
+      const uint4 aw = *reinterpret_cast<const uint4 *>(act_hi + off);
+      uint4 hh, ll;
+      split8_h(&v[8 * cc], hh, ll);
+      const uint32_t m0 = pos_mask2_h(aw.x), m1 = pos_mask2_h(aw.y), m2 = pos_mask2_h(aw.z), m3 = pos_mask2_h(aw.w);
+      *reinterpret_cast<uint4 *>(hi + off) = make_uint4(hh.x & m0, hh.y & m1, hh.z & m2, hh.w & m3);
+      *reinterpret_cast<uint4 *>(lo + off) = make_uint4(ll.x & m0, ll.y & m1, ll.z & m2, ll.w & m3);
+    }
+  }
+}
+
 template <int D1, int D2>
 struct cvmap {
   static_assert((D1 == 128 && D2 == 64) || (D1 == 64 && D2 == 32), "conv policy widths: 4-128-64-1 or 4-64-32-1");
@@ -32,7 +148,9 @@ struct cvmap {
   static constexpr uint32_t W2SUB = D2 * 128;  // one 64-column sub-panel of W2: [D2 rows][64 columns]
   static constexpr uint32_t W2_HI = WX + PANEL, W2_LO = W2_HI + NP1 * W2SUB;
   static constexpr uint32_t FLOATS = W2_LO + NP1 * W2SUB;  // b1[D1] b2[D2] w3[D2] b3
-  static constexpr int F_B1 = 0, F_B2 = D1, F_W3 = D1 + D2, F_B3 = D1 + 2 * D2, N_FLOATS = D1 + 2 * D2 + 4;
+  // ... b3, 1 / S_W1, 1 / S_W2, S_g, 1 / S_g; 32 floats of reduction scratch
+  static constexpr int F_B1 = 0, F_B2 = D1, F_W3 = D1 + D2, F_B3 = D1 + 2 * D2, F_IS1 = F_B3 + 1, F_IS2 = F_B3 + 2, F_SG = F_B3 + 3,
+                       F_ISG = F_B3 + 4, F_RED = F_B3 + 8, N_FLOATS = F_RED + 32;
   static constexpr uint32_t SCR = FLOATS + N_FLOATS * 4;  // partial logits [2][128]
   static constexpr uint32_t H1_HI = (SCR + 2 * TILE * 4 + 1023) / 1024 * 1024;
   static constexpr uint32_t H1_LO = H1_HI + NP1 * PANEL;
@@ -61,14 +179,21 @@ struct conv_step_args {
   grad_tail tail;
 };
 
-// W1 [D1][4] and W2 [D2][D1] (fp32, staged copy `P`) -> operand panels; biases / head weights -> floats.
+// W1 [D1][4] and W2 [D2][D1] (fp32, staged copy `P`) -> FP16-pair operand panels of W * S_W (S_W a power
+// of two from max|W|, identical in every CTA); biases / head weights / 1 / S_W -> floats. Whole CTA.
 template <int D1, int D2, typename CM>
 __device__ void stage_conv_weights(const float *__restrict__ P, const net3 &net, uint8_t *smem, float *fl) {
   const float *W1 = P + net.o_w1, *W2 = P + net.o_w2;
+  float m1 = 0.f, m2 = 0.f;
+  for (int i = threadIdx.x; i < D1 * 4; i += blockDim.x)
+    m1 = fmaxf(m1, fabsf(W1[i]));
+  for (int i = threadIdx.x; i < D2 * D1; i += blockDim.x)
+    m2 = fmaxf(m2, fabsf(W2[i]));
+  const float s1 = pow2_scale(block_max(m1, fl + CM::F_RED), 13), s2 = pow2_scale(block_max(m2, fl + CM::F_RED), 13);
   for (int n = threadIdx.x; n < D1; n += blockDim.x) {
-    float x[8] = {W1[n * 4], W1[n * 4 + 1], W1[n * 4 + 2], W1[n * 4 + 3], 0.f, 0.f, 0.f, 0.f};
+    float x[8] = {W1[n * 4] * s1, W1[n * 4 + 1] * s1, W1[n * 4 + 2] * s1, W1[n * 4 + 3] * s1, 0.f, 0.f, 0.f, 0.f};
     uint4 h, l;
-    split8<false>(x, h, l);
+    split8_h(x, h, l);
     *reinterpret_cast<uint4 *>(smem + CM::WX + umma::panel_chunk_off(n, 0)) = h;
     *reinterpret_cast<uint4 *>(smem + CM::WX + umma::panel_chunk_off(n, 2)) = l;
   }
@@ -77,9 +202,9 @@ __device__ void stage_conv_weights(const float *__restrict__ P, const net3 &net,
     float x[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j)
-      x[j] = W2[(size_t)n * D1 + ch * 8 + j];
+      x[j] = W2[(size_t)n * D1 + ch * 8 + j] * s2;
     uint4 h, l;
-    split8<false>(x, h, l);
+    split8_h(x, h, l);
     const uint32_t off = (uint32_t)(ch >> 3) * CM::W2SUB + umma::panel_chunk_off(n, ch & 7);
     *reinterpret_cast<uint4 *>(smem + CM::W2_HI + off) = h;
     *reinterpret_cast<uint4 *>(smem + CM::W2_LO + off) = l;
@@ -87,8 +212,11 @@ __device__ void stage_conv_weights(const float *__restrict__ P, const net3 &net,
   for (int i = threadIdx.x; i < D1; i += blockDim.x) fl[CM::F_B1 + i] = P[net.o_b1 + i];
   for (int i = threadIdx.x; i < D2; i += blockDim.x) fl[CM::F_B2 + i] = P[net.o_b2 + i];
   for (int i = threadIdx.x; i < D2; i += blockDim.x) fl[CM::F_W3 + i] = P[net.o_w3 + i];
-  if (threadIdx.x == 0)
+  if (threadIdx.x == 0) {
     fl[CM::F_B3] = P[net.o_b3];
+    fl[CM::F_IS1] = 1.f / s1;
+    fl[CM::F_IS2] = 1.f / s2;
+  }
 }
 
 // Layer 2: ACC1 = H1 (tensor memory, tmem_put_chunk layout in ACC0) . W2^T, B = W2 sub-panels K-major.
@@ -99,20 +227,20 @@ __device__ __forceinline__ void conv_issue_layer2(uint32_t tm, uint32_t sbase) {
     const uint32_t ah = tm + CM::ACC0 + (k / 2) * 32 + (k % 2) * 8, al = ah + 16;
     const uint32_t boff = (uint32_t)(k / 4) * CM::W2SUB + (uint32_t)(k % 4) * umma::KSTEP_BYTES_KMAJOR;
     const uint64_t bh = desc_lo_hi(desc_lo(sbase + CM::W2_HI + boff, 16)), bl = desc_lo_hi(desc_lo(sbase + CM::W2_LO + boff, 16));
-    umma::mma_bf16_ta(tm + CM::ACC1, ah, bh, ID<D2>::FK_FK, k > 0 ? 1u : 0u);
-    umma::mma_bf16_ta(tm + CM::ACC1, ah, bl, ID<D2>::FK_FK, 1);
-    umma::mma_bf16_ta(tm + CM::ACC1, al, bh, ID<D2>::FK_FK, 1);
-    umma::mma_bf16_ta(tm + CM::ACC1, al, bl, ID<D2>::FK_FK, 1);  // lo.lo too: see the precision note in the header
+    umma::mma_bf16_ta(tm + CM::ACC1, ah, bh, IDH<D2>::FK_FK, k > 0 ? 1u : 0u);
+    umma::mma_bf16_ta(tm + CM::ACC1, ah, bl, IDH<D2>::FK_FK, 1);
+    umma::mma_bf16_ta(tm + CM::ACC1, al, bh, IDH<D2>::FK_FK, 1);
+    umma::mma_bf16_ta(tm + CM::ACC1, al, bl, IDH<D2>::FK_FK, 1);  // lo.lo too: see the precision note in the header
   }
 }
 
 // Observation row [bin.w / cap_w, bin.h / cap_h, item.w / cap_w, item.h / cap_h, 1, 0, 0, 0] of one
-// (sample, bin) row into observation slot `slot` of the WX panel (exact in bf16).
+// (sample, bin) row into observation slot `slot` of the WX panel (exact in fp16).
 template <typename CM>
 __device__ __forceinline__ void conv_encode_row(uint8_t *smem, int row, int slot, int bw, int bh, int iw, int ih, float inv_w,
                                                 float inv_h) {
   *reinterpret_cast<uint4 *>(smem + CM::WX + umma::panel_chunk_off(row, 4 + 2 * slot)) =
-      make_uint4(pack2_fwd((float)bw * inv_w, (float)bh * inv_h), pack2_fwd((float)iw * inv_w, (float)ih * inv_h), 0x00003F80u, 0u);
+      make_uint4(pack2_h((float)bw * inv_w, (float)bh * inv_h), pack2_h((float)iw * inv_w, (float)ih * inv_h), 0x00003C00u, 0u);
 }
 
 template <int D1, int D2>
@@ -155,6 +283,21 @@ __global__ void __launch_bounds__((cvmap<D1, D2>::THREADS), 1) fused_conv_policy
   uint64_t *bar = bars, *bar_dw2 = bars + 1, *bar_dw1 = bars + 2;
   uint32_t rp = 0;
   const long long rows_total = (long long)a.T * a.n;
+  {  // S_g: the gradient chain of this CTA runs on dY * S_g, max|A| * S_g in [8, 16) over the CTA's own samples
+    float mx = 0.f;
+    for (int q = threadIdx.x; q < nt * SPT; q += blockDim.x) {
+      const long long k = (long long)(blockIdx.x + (q / SPT) * gridDim.x) * SPT + q % SPT;
+      if (k < rows_total)
+        mx = fmaxf(mx, fabsf(a.adv[k]));
+    }
+    const float sg = pow2_scale(block_max(mx, fl + CM::F_RED), 4);
+    if (threadIdx.x == 0) {
+      fl[CM::F_SG] = sg;
+      fl[CM::F_ISG] = 1.f / sg;
+    }
+    __syncthreads();
+  }
+  const float inv_s1 = fl[CM::F_IS1], inv_s2 = fl[CM::F_IS2], s_g = fl[CM::F_SG], inv_sg = fl[CM::F_ISG];
 
   // per-thread partial sums (drained after the last tile)
   float dw3[32], db3 = 0.f;
@@ -166,7 +309,7 @@ __global__ void __launch_bounds__((cvmap<D1, D2>::THREADS), 1) fused_conv_policy
     // ================= MMA issuer
     auto layer1 = [&](int slot) {
       issue_gemm<1, false, false, false, true>(tm + CM::ACC0, sbase + CM::WX + 64 + 32 * slot, 0, sbase + CM::WX,
-                                               sbase + CM::WX + 32, ID<D1>::FK_FK, false);
+                                               sbase + CM::WX + 32, IDH<D1>::FK_FK, false);
       umma::commit(bar);
     };
     bool first = true;
@@ -193,18 +336,18 @@ __global__ void __launch_bounds__((cvmap<D1, D2>::THREADS), 1) fused_conv_policy
           const uint32_t ah = tm + CM::ACC1 + (16 * k / CH2) * CH2 + ((16 * k % CH2) / 16) * 8, al = ah + CH2 / 2;
           const uint64_t bh = desc_lo_hi(desc_lo(sbase + CM::W2_HI + k * umma::KSTEP_BYTES_MNMAJOR, CM::W2SUB));
           const uint64_t bl = desc_lo_hi(desc_lo(sbase + CM::W2_LO + k * umma::KSTEP_BYTES_MNMAJOR, CM::W2SUB));
-          umma::mma_bf16_ta(tm + CM::ACC0, ah, bh, ID<D1>::BK_FM, k > 0 ? 1u : 0u);
-          umma::mma_bf16_ta(tm + CM::ACC0, ah, bl, ID<D1>::BK_FM, 1);
-          umma::mma_bf16_ta(tm + CM::ACC0, al, bh, ID<D1>::BK_FM, 1);
-          umma::mma_bf16_ta(tm + CM::ACC0, al, bl, ID<D1>::BK_FM, 1);
+          umma::mma_bf16_ta(tm + CM::ACC0, ah, bh, IDH<D1>::BK_FM, k > 0 ? 1u : 0u);
+          umma::mma_bf16_ta(tm + CM::ACC0, ah, bl, IDH<D1>::BK_FM, 1);
+          umma::mma_bf16_ta(tm + CM::ACC0, al, bh, IDH<D1>::BK_FM, 1);
+          umma::mma_bf16_ta(tm + CM::ACC0, al, bl, IDH<D1>::BK_FM, 1);
         }
         umma::commit(bar);
         // dW2 (+)= [hi(dH2); lo(dH2)]^T . hi(H1) + [hi(dH2); lo(dH2)]^T . lo(H1): runs behind the dH1 epilogue
         issue_gemm<8, true, true, false, true>(tm + CM::DA, sbase + CM::G2_HI, 0, sbase + CM::H1_HI, sbase + CM::H1_LO,
-                                               ID<D1>::BM_FM, !first);
+                                               IDH<D1>::BM_FM, !first);
         // db2 (+)= [hi(dH2); lo(dH2)]^T . [X | 1]: column 4 = the sums over rows (the other columns are not used)
         issue_gemm<8, true, true, false, false>(tm + CM::DB2, sbase + CM::G2_HI, 0, sbase + CM::WX + 64 + 32 * (j & 1), 0,
-                                                ID<16>::BM_FM, !first);
+                                                IDH<16>::BM_FM, !first);
         umma::commit(bar_dw2);
       }
       __syncwarp();
@@ -214,9 +357,9 @@ __global__ void __launch_bounds__((cvmap<D1, D2>::THREADS), 1) fused_conv_policy
           layer1((j + 1) & 1);
         const uint32_t xb = sbase + CM::WX + 64 + 32 * (j & 1);
         if (D1 == 128)  // M = D1 = 128 over the two column panels of dH1, hi and lo passes
-          issue_gemm_mn_lbo<8>(tm + CM::DB, sbase + CM::DH1_HI, sbase + CM::DH1_LO, PANEL, xb, ID<16>::BM_FM, !first);
+          issue_gemm_mn_lbo<8>(tm + CM::DB, sbase + CM::DH1_HI, sbase + CM::DH1_LO, PANEL, xb, IDH<16>::BM_FM, !first);
         else  // D1 = 64: [hi(dH1); lo(dH1)] stacked (the lo panel follows the hi panel), one MMA per K step
-          issue_gemm<8, true, true, false, false>(tm + CM::DB, sbase + CM::DH1_HI, 0, xb, 0, ID<16>::BM_FM, !first);
+          issue_gemm<8, true, true, false, false>(tm + CM::DB, sbase + CM::DH1_HI, 0, xb, 0, IDH<16>::BM_FM, !first);
         umma::commit(bar_dw1);
       }
       __syncwarp();
@@ -276,7 +419,7 @@ __global__ void __launch_bounds__((cvmap<D1, D2>::THREADS), 1) fused_conv_policy
         umma::mbar_wait(bar_dw2, phase_dw2);
         phase_dw2 ^= 1;
       }
-      epi2_fwd<D1, true>(tm + CM::ACC0, t, b1, smem + CM::H1_HI, smem + CM::H1_LO, c1_0, c1_1);
+      conv_epi_fwd<D1, true>(tm + CM::ACC0, t, b1, inv_s1, smem + CM::H1_HI, smem + CM::H1_LO, c1_0, c1_1);
       ready_arrive(0, rp, RT);
       wait_mma();  // layer 2
       // ---- head: H2 = relu(acc + b2) (registers), logit = H2 . w3 + b3 (the row's two threads exchange
@@ -287,7 +430,7 @@ __global__ void __launch_bounds__((cvmap<D1, D2>::THREADS), 1) fused_conv_policy
         tmem_load<32>(tm + CM::ACC1 + t.lane_base + half * 32, v);
 #pragma unroll
         for (int q = 0; q < 32; ++q) {
-          y[q] = fmaxf(v[q] + b2[half * 32 + q], 0.f);
+          y[q] = fmaxf(fmaf(v[q], inv_s2, b2[half * 32 + q]), 0.f);
           s = fmaf(y[q], w3[half * 32 + q], s);
         }
       } else {
@@ -346,15 +489,16 @@ __global__ void __launch_bounds__((cvmap<D1, D2>::THREADS), 1) fused_conv_policy
         // dH2 = dY w3 . relu' (rank 1), dW3 += dY H2; dH2 -> its panels (A of the dW2 / db2 GEMMs) and, in
         // place over the accumulator columns just read, tensor memory (A of the dH1 GEMM)
         float v[32];
+        const float dYs = dY * s_g;
 #pragma unroll
         for (int q = 0; q < 32; ++q) {
-          v[q] = y[q] > 0.f ? dY * w3[half * 32 + q] : 0.f;
+          v[q] = y[q] > 0.f ? dYs * w3[half * 32 + q] : 0.f;
           dw3[q] = fmaf(dY, y[q], dw3[q]);
         }
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
           uint4 hh, ll;
-          split8<false>(&v[8 * cc], hh, ll);
+          split8_h(&v[8 * cc], hh, ll);
           const uint32_t off = umma::panel_chunk_off(t.row, half * 4 + cc);
           *reinterpret_cast<uint4 *>(smem + CM::G2_HI + off) = hh;
           *reinterpret_cast<uint4 *>(smem + CM::G2_LO + off) = ll;
@@ -368,7 +512,7 @@ __global__ void __launch_bounds__((cvmap<D1, D2>::THREADS), 1) fused_conv_policy
         umma::mbar_wait(bar_dw1, phase_dw1);
         phase_dw1 ^= 1;
       }
-      epi2_bwd<D1>(tm + CM::ACC0, t, smem + CM::H1_HI, smem + CM::DH1_HI, smem + CM::DH1_LO, c1_0, c1_1);
+      conv_epi_bwd<D1>(tm + CM::ACC0, t, inv_s2, smem + CM::H1_HI, smem + CM::DH1_HI, smem + CM::DH1_LO, c1_0, c1_1);
       if (has_next && half == 0)
         conv_encode_row<CM>(smem, t.row, (j + 1) & 1, nbw, nbh, niw, nih, a.inv_w, a.inv_h);
       ready_arrive(0, rp, RT);
@@ -410,7 +554,7 @@ __global__ void __launch_bounds__((cvmap<D1, D2>::THREADS), 1) fused_conv_policy
         tmem_load<32>(tm + CM::DA + t.lane_base + half * HC + c0, v);
 #pragma unroll
         for (int q = 0; q < 32; ++q)
-          part[net.o_w2 + t.row * D1 + half * HC + c0 + q] = v[q] + sc[t.row * (D1 + 1) + half * HC + c0 + q];
+          part[net.o_w2 + t.row * D1 + half * HC + c0 + q] = (v[q] + sc[t.row * (D1 + 1) + half * HC + c0 + q]) * inv_sg;
       }
     }
     // [dW1 | db1]: DB lane n, columns 0..3 and 4 (D1 = 64: the lo part in lanes 64..127)
@@ -420,8 +564,8 @@ __global__ void __launch_bounds__((cvmap<D1, D2>::THREADS), 1) fused_conv_policy
       if (D1 == 128) {
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          part[net.o_w1 + t.row * 4 + q] = w[q];
-        part[net.o_b1 + t.row] = w[4];
+          part[net.o_w1 + t.row * 4 + q] = w[q] * inv_sg;
+        part[net.o_b1 + t.row] = w[4] * inv_sg;
       } else {
         float *s2 = sc + 64 * (D1 + 1);
         if (t.row >= 64)
@@ -432,8 +576,8 @@ __global__ void __launch_bounds__((cvmap<D1, D2>::THREADS), 1) fused_conv_policy
         if (t.row < 64) {
 #pragma unroll
           for (int q = 0; q < 4; ++q)
-            part[net.o_w1 + t.row * 4 + q] = w[q] + s2[t.row * 8 + q];
-          part[net.o_b1 + t.row] = w[4] + s2[t.row * 8 + 4];
+            part[net.o_w1 + t.row * 4 + q] = (w[q] + s2[t.row * 8 + q]) * inv_sg;
+          part[net.o_b1 + t.row] = (w[4] + s2[t.row * 8 + 4]) * inv_sg;
         }
       }
     }
@@ -459,7 +603,7 @@ __global__ void __launch_bounds__((cvmap<D1, D2>::THREADS), 1) fused_conv_policy
       for (int r = 0; r < TILE; ++r)
         s3 += r3[r * (D2 + 1) + threadIdx.x];
       part[net.o_w3 + threadIdx.x] = s3;
-      part[net.o_b2 + threadIdx.x] = r2[threadIdx.x] + r2[64 + threadIdx.x];
+      part[net.o_b2 + threadIdx.x] = (r2[threadIdx.x] + r2[64 + threadIdx.x]) * inv_sg;
     } else if (threadIdx.x == D2) {
       float s1 = 0.f;
       for (int r = 0; r < TILE; ++r)
@@ -488,7 +632,8 @@ struct cvrmap {
   static constexpr uint32_t W2SUB = D2 * 128;
   static constexpr uint32_t W2_HI = WX + PANEL, W2_LO = W2_HI + NP1 * W2SUB;
   static constexpr uint32_t FLOATS = W2_LO + NP1 * W2SUB;
-  static constexpr int F_B1 = 0, F_B2 = D1, F_W3 = D1 + D2, F_B3 = D1 + 2 * D2, N_FLOATS = D1 + 2 * D2 + 4;
+  static constexpr int F_B1 = 0, F_B2 = D1, F_W3 = D1 + D2, F_B3 = D1 + 2 * D2, F_IS1 = F_B3 + 1, F_IS2 = F_B3 + 2, F_RED = F_B3 + 8,
+                       N_FLOATS = F_RED + 32;
   static constexpr uint32_t SCRATCH = (FLOATS + N_FLOATS * 4 + 1023) / 1024 * 1024;  // parameter staging (<= 36 KB)
   static constexpr uint32_t BARS = SCRATCH + 36 * 1024;
   static constexpr uint32_t TOTAL = BARS + 128;
@@ -537,7 +682,7 @@ __global__ void __launch_bounds__(160 * NP, 1) fused_conv_rollout_kernel(rollout
         ready_sync(wg, rp);  // observations staged in this pipeline's slot
         if (umma::elect_one()) {
           issue_gemm<1, false, false, false, true>(tm + RM::ACC0, sbase + RM::WX + 64 + 32 * wg, 0, sbase + RM::WX,
-                                                   sbase + RM::WX + 32, ID<D1>::FK_FK, false);
+                                                   sbase + RM::WX + 32, IDH<D1>::FK_FK, false);
           umma::commit(bar);
         }
         __syncwarp();
@@ -550,7 +695,7 @@ __global__ void __launch_bounds__(160 * NP, 1) fused_conv_rollout_kernel(rollout
       }
   } else {
     const float *b1 = fl + RM::F_B1, *b2 = fl + RM::F_B2, *w3 = fl + RM::F_W3;
-    const float b3 = fl[RM::F_B3];
+    const float b3 = fl[RM::F_B3], inv_s1 = fl[RM::F_IS1], inv_s2 = fl[RM::F_IS2];
     uint32_t phase = 0;
     auto wait_mma = [&]() {
       umma::mbar_wait(bar, phase);
@@ -599,10 +744,19 @@ __global__ void __launch_bounds__(160 * NP, 1) fused_conv_rollout_kernel(rollout
             tape_item = a.item_tape[k];
         }
         wait_mma();  // layer 1
-        epi2_fwd<D1, true, false>(tm + RM::ACC0, t, b1, nullptr, nullptr);  // H1 only as a TMEM A operand
+        conv_epi_fwd<D1, false>(tm + RM::ACC0, t, b1, inv_s1, nullptr, nullptr, 0, D1 / 32);  // H1 only as a TMEM A operand
         ready_arrive(wg, rp);
         wait_mma();  // layer 2
-        const float logit = epi2_value<D2, false>(tm + RM::ACC1, t, b2, w3, b3, nullptr);
+        float logit = 0.f;
+#pragma unroll
+        for (int h = 0; h < D2 / 32; ++h) {
+          float v[32];
+          tmem_load<32>(tm + RM::ACC1 + t.lane_base + h * 32, v);
+#pragma unroll
+          for (int q = 0; q < 32; ++q)
+            logit = fmaf(fmaxf(fmaf(v[q], inv_s2, b2[h * 32 + q]), 0.f), w3[h * 32 + q], logit);
+        }
+        logit += b3;
         // ---- head: softmax over the environment's 8 rows (no max subtraction, nn.h:382-392), action, apply
         const float e = expf(logit);
         float p[B], s = 0.f;
