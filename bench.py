@@ -515,7 +515,18 @@ def run_ours(args):
         obj = [D.Context.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(obj, src=0)
         nccl_id = obj[0]
-    ctx = D.Context(local_rank, world, rank, nccl_id)
+    # (NCCL prints its version banner to fd 1 during ncclCommInitRank whatever NCCL_DEBUG_FILE says:
+    #  fd 1 points at stderr while the communicator is created)
+    sys.stdout.flush()
+    saved_fd1 = os.dup(1) if world > 1 else -1
+    if world > 1:
+        os.dup2(2, 1)
+    try:
+        ctx = D.Context(local_rank, world, rank, nccl_id)
+    finally:
+        if world > 1:
+            os.dup2(saved_fd1, 1)
+            os.close(saved_fd1)
     exchange = "none (single rank)"
     if world > 1:
         exchange = "ncclAllReduce + optimizer kernel"

@@ -2695,6 +2695,7 @@ int dfrl_fused_policy_gradient(dfrl_trainer *t, int loss_kind, float *grad_dev, 
     c.loss_kind = loss_kind;
     c.head_bwd = f->head_bwd;
     c.partials = f->partials;
+    c.clk = f->clk;
     int ctas = c.n_tiles < f->ctas ? c.n_tiles : f->ctas;
     DFRL_TRY(make_tail(t, f, f->pnet, ctas, grad_dev, opt, &c.tail));
     if (f->pnet.d1 == 128)

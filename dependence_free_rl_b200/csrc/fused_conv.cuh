@@ -177,6 +177,7 @@ struct conv_step_args {
   int loss_kind, head_bwd;
   float *partials;
   grad_tail tail;
+  long long *clk;  // optional: phase clocks of CTA 0 (debug): 7 stamps per tile, first 14 tiles
 };
 
 // W1 [D1][4] and W2 [D2][D1] (fp32, staged copy `P`) -> FP16-pair operand panels of W * S_W (S_W a power
@@ -390,6 +391,9 @@ __global__ void __launch_bounds__((cvmap<D1, D2>::THREADS), 1) fused_conv_policy
         ih = src[(size_t)(2 * NB + 1) * a.stride];
       }
     };
+    long long *clk = (a.clk && blockIdx.x == 0 && threadIdx.x == 96) ? a.clk : nullptr;
+    int clk_n = 0;
+#define STAMP() do { if (clk && clk_n < 98) clk[clk_n++] = clock64(); } while (0)
     int nbw = 0, nbh = 0, niw = 0, nih = 0;
     if (nt > 0) {
       if (half == 0) {
@@ -414,14 +418,18 @@ __global__ void __launch_bounds__((cvmap<D1, D2>::THREADS), 1) fused_conv_policy
       const bool has_next = j + 1 < nt;
       if (has_next && half == 0)
         load_state(tile + gridDim.x, nbw, nbh, niw, nih);
+      STAMP();
       wait_mma();  // layer 1
       if (j > 0) {  // the previous tile's dW2 GEMM (reads the H1 and dH2 panels) ran behind its dH1 epilogue
         umma::mbar_wait(bar_dw2, phase_dw2);
         phase_dw2 ^= 1;
       }
+      STAMP();
       conv_epi_fwd<D1, true>(tm + CM::ACC0, t, b1, inv_s1, smem + CM::H1_HI, smem + CM::H1_LO, c1_0, c1_1);
       ready_arrive(0, rp, RT);
+      STAMP();
       wait_mma();  // layer 2
+      STAMP();
       // ---- head: H2 = relu(acc + b2) (registers), logit = H2 . w3 + b3 (the row's two threads exchange
       //      their partial sums), softmax over the sample's 8 rows, loss gradient, Jacobian -> dY
       float y[32], s = 0.f;
@@ -507,16 +515,20 @@ __global__ void __launch_bounds__((cvmap<D1, D2>::THREADS), 1) fused_conv_policy
         umma::tmem_st_wait();
       }
       ready_arrive(0, rp, RT);
+      STAMP();
       wait_mma();  // dH1
       if (j > 0) {  // the previous tile's dW1 GEMM (reads the dH1 panels and its observation slot)
         umma::mbar_wait(bar_dw1, phase_dw1);
         phase_dw1 ^= 1;
       }
+      STAMP();
       conv_epi_bwd<D1>(tm + CM::ACC0, t, inv_s2, smem + CM::H1_HI, smem + CM::DH1_HI, smem + CM::DH1_LO, c1_0, c1_1);
       if (has_next && half == 0)
         conv_encode_row<CM>(smem, t.row, (j + 1) & 1, nbw, nbh, niw, nih, a.inv_w, a.inv_h);
       ready_arrive(0, rp, RT);
+      STAMP();
     }
+#undef STAMP
     if (nt > 0) {  // the last tile's weight-gradient GEMMs
       umma::mbar_wait(bar_dw2, phase_dw2);
       umma::mbar_wait(bar_dw1, phase_dw1);
