@@ -13,16 +13,38 @@
 
 namespace bp {
 
-constexpr std::size_t num_bins = 8;
+// The problem definition. The reference fixes it at compile time (bin_packing.h:12 `constexpr
+// std::size_t num_bins = 8`, :24 capacity (8, 8), :73-78 items (4, 2) with probability 0.4 else
+// (1, 2)); here it is a set of LAUNCH parameters of the device environment (dfrl_env_config): set
+// them before constructing models / environments (the trainer mains do it from command-line flags,
+// xeno/configuration.h) and sweep the number of bins without recompiling.
+struct problem {
+  std::size_t num_bins = 8;
+  std::pair<int, int> capacity{8, 8};
+  std::pair<int, int> shape1{4, 2}, shape2{1, 2};
+  float p_shape1 = 0.4f;
+};
+inline problem &config() {
+  static problem p;
+  return p;
+}
+inline void configure(const problem &p) {
+  if (p.num_bins < 1 || p.num_bins > 64)
+    throw xeno::error("num_bins must lie in [1, 64]");
+  config() = p;
+  xylo::dynamic_cardinality() = p.num_bins;
+}
+// `bp::num_bins` reads like the reference's constant (`4 * bp::num_bins`, `bins.size() == bp::num_bins`).
+inline constexpr struct num_bins_t {
+  operator std::size_t() const { return config().num_bins; }
+} num_bins;
 
-using action = xylo::discrete_action<num_bins>;
+using action = xylo::discrete_action<0>;  // 0: run-time cardinality (= num_bins, set by configure())
 
 struct observation {
-  static std::size_t length() { return 4 * num_bins; }
+  static std::size_t length() { return 4 * config().num_bins; }
 
-  static constexpr std::pair<int, int> capacity{8, 8};
-
-  observation(const std::pair<int, int> &bin_shape) : bins(num_bins, bin_shape), item{0, 0} {}
+  observation(const std::pair<int, int> &bin_shape) : bins(config().num_bins, bin_shape), item{0, 0} {}
 
   std::string to_string() const {
     std::ostringstream oss;
@@ -32,8 +54,9 @@ struct observation {
     return oss.str();
   }
 
-  // [bin.w / 8, bin.h / 8, item.w / 8, item.h / 8] per bin (bin_packing.h:31-40)
+  // [bin.w / cap.w, bin.h / cap.h, item.w / cap.w, item.h / cap.h] per bin (bin_packing.h:31-40)
   void to_vector(xylo::vector_view o) const {
+    const std::pair<int, int> capacity = config().capacity;
     for (std::size_t i = 0; i < bins.size(); ++i) {
       o[4 * i + 0] = float(bins[i].first) / capacity.first;
       o[4 * i + 1] = float(bins[i].second) / capacity.second;
@@ -50,19 +73,22 @@ struct observation {
 // environment (bin_packing.h:50-52).
 class environment : public xylo::environment<action, observation> {
 public:
-  static constexpr std::pair<int, int> capacity{8, 8};
-
-  explicit environment(std::size_t n_envs = 1, uint64_t seed = 1234, int64_t env_offset = 0) : n_(n_envs) {
+  explicit environment(std::size_t n_envs = 1, uint64_t seed = 1234, int64_t env_offset = 0) : n_(n_envs), cfg_(config()) {
     dfrl_env_config c;
     dfrl_env_config_default(&c);  // 8 bins of (8, 8); items (4, 2) w.p. 0.4 else (1, 2)
     c.n_envs = (int)n_envs;
-    c.n_bins = (int)num_bins;
+    c.n_bins = (int)cfg_.num_bins;
+    c.cap_w = cfg_.capacity.first;
+    c.cap_h = cfg_.capacity.second;
+    c.item_w[0] = cfg_.shape1.first, c.item_h[0] = cfg_.shape1.second;
+    c.item_w[1] = cfg_.shape2.first, c.item_h[1] = cfg_.shape2.second;
+    c.p_shape1 = cfg_.p_shape1;
     c.seed = seed;
     c.env_offset = env_offset;
     xylo::check(dfrl_env_create(xylo::device::get(), &c, &env_));
   }
   environment(const environment &) = delete;
-  environment(environment &&o) noexcept : n_(o.n_), env_(o.env_) { o.env_ = nullptr; }
+  environment(environment &&o) noexcept : n_(o.n_), cfg_(o.cfg_), env_(o.env_) { o.env_ = nullptr; }
   ~environment() override {
     if (env_)
       dfrl_env_destroy(env_);
@@ -72,12 +98,13 @@ public:
     xylo::check(dfrl_env_apply_one(env_, (int)id, (int)action.choice));
   }
   observation view(std::size_t id) const override {
-    int8_t s[2 * num_bins + 2];
-    xylo::check(dfrl_env_view_one(env_, (int)id, s));
-    observation o(capacity);
-    for (std::size_t b = 0; b < num_bins; ++b)
+    const std::size_t B = cfg_.num_bins;
+    std::vector<int8_t> s(2 * B + 2);
+    xylo::check(dfrl_env_view_one(env_, (int)id, s.data()));
+    observation o(cfg_.capacity);
+    for (std::size_t b = 0; b < B; ++b)
       o.bins[b] = {s[2 * b], s[2 * b + 1]};
-    o.item = {s[2 * num_bins], s[2 * num_bins + 1]};
+    o.item = {s[2 * B], s[2 * B + 1]};
     return o;
   }
   void reset(std::size_t id) override { xylo::check(dfrl_env_reset_one(env_, (int)id)); }
@@ -87,6 +114,7 @@ public:
 
 private:
   std::size_t n_;
+  problem cfg_;  // the problem definition this environment was created with
   dfrl_env *env_ = nullptr;
 };
 

@@ -1,30 +1,45 @@
 // ppo_training -- the reference trainer main (apps/bin_packing/ppo_training.cc) on the device.
 // Same phases: rollout (agent.play_steps) -> learner.step() -> replay_buffer.forget() -> periodic
 // argmax evaluation. The 8 worker threads x 8 environments become one batched environment.
-//   ppo_training [num_envs] [iterations] [eval_every] [nets]
+//   ppo_training [--num_bins=B] [--capacity=C] [--p_shape1=P] [num_envs] [iterations] [eval_every] [nets]
 // nets = "ref" (default): the reference's own nets, line for line (ppo_training.cc:10-26: conv1d_1
-// 4-128-64-1 softmax policy over the 8 bins, critic 32-64-32-1); "c2": the BASELINE configs[1] nets
-// (policy 32-64-64-8 softmax, critic 32-64-64-1). Both run on the fused tcgen05 kernels.
+// 4-128-64-1 softmax policy over the bins, critic 4B-64-32-1); "c2": the BASELINE configs[1] nets
+// (policy 4B-64-64-B softmax, critic 4B-64-64-1). With the reference's 8 bins both run on the fused
+// tcgen05 kernels. The flags (xeno::flagstore, reference xeno/configuration.h) turn the reference's
+// compile-time problem definition (bin_packing.h:12, 24, 73-78) into launch parameters: e.g.
+// `ppo_training --num_bins=32 4096 100 0 c2` is the "more bins" sweep without recompiling.
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
 
+#include <xeno/configuration.h>
 #include <xylo/nn.h>
 #include <xylo/rl.h>
 
 #include <apps/bin_packing/bin_packing.h>
 
 int main(int argc, char **argv) {
-  const std::size_t num_envs = argc > 1 ? std::strtoul(argv[1], nullptr, 10) : 4096;
-  const int iterations = argc > 2 ? std::atoi(argv[2]) : 1000;
-  const int eval_every = argc > 3 ? std::atoi(argv[3]) : 100;
+  xeno::flagstore flags;
+  flags.define_flag<int>("num_bins", 'b', 8);          // bin_packing.h:12
+  flags.define_flag<int>("capacity", 'c', 8);          // bin_packing.h:24 (square bins)
+  flags.define_flag<double>("p_shape1", 'p', 0.4);     // bin_packing.h:50
+  const std::vector<std::string_view> pos = flags.parse_from_args(argc, argv);
+  bp::problem problem;
+  problem.num_bins = (std::size_t)flags.get_flag<int>("num_bins");
+  problem.capacity = {flags.get_flag<int>("capacity"), flags.get_flag<int>("capacity")};
+  problem.p_shape1 = (float)flags.get_flag<double>("p_shape1");
+  bp::configure(problem);
+  auto arg = [&](std::size_t i) { return std::string(pos[i]); };
+  const std::size_t num_envs = pos.size() > 0 ? std::stoul(arg(0)) : 4096;
+  const int iterations = pos.size() > 1 ? std::stoi(arg(1)) : 1000;
+  const int eval_every = pos.size() > 2 ? std::stoi(arg(2)) : 100;
   constexpr int steps_per_worker = 4;  // ppo_training.cc:31
   // gradients are SUMS over rows (nn.h:94-98): the reference rates are tuned to 8 x 4 = 32 rows
   const float row_scale = 32.f / float(num_envs * steps_per_worker);
 
-  const bool c2 = argc > 4 && std::strcmp(argv[4], "c2") == 0;
+  const bool c2 = pos.size() > 3 && pos[3] == "c2";
 
   xylo::model action_model;
   xylo::model value_model;

@@ -34,20 +34,27 @@ template <typename T> vector to_vector(const T &t) {
   return result;
 }
 
+// discrete_action<0>: the cardinality is a run-time value (apps/bin_packing: the number of bins as a launch parameter).
+inline std::size_t &dynamic_cardinality() {
+  static std::size_t n = 8;
+  return n;
+}
+
 template <std::size_t range> struct discrete_action {
-  static std::size_t cardinality() { return range; }
+  static std::size_t cardinality() { return range ? range : dynamic_cardinality(); }
   std::size_t choice = 0;
   std::optional<vector> distrib;
 
   // std::discrete_distribution semantics (tensor.cc:467-470), evaluated by dfrl_sample.
   void from_vector(vector_view a) {
-    if (a.size() != range)
+    const std::size_t range_ = cardinality();
+    if (a.size() != range_)
       throw xeno::error("action vector has the wrong size");
     double u = std::generate_canonical<double, 53>(default_generator());
-    device_buffer p(range), ud(2), act(1);
-    p.upload(a.data(), range);
+    device_buffer p(range_), ud(2), act(1);
+    p.upload(a.data(), range_);
     check(dfrl_memcpy_h2d(device::get(), ud.get(), &u, sizeof(double)));
-    check(dfrl_sample(device::get(), p.get(), 1, (int)range, reinterpret_cast<const double *>(ud.get()),
+    check(dfrl_sample(device::get(), p.get(), 1, (int)range_, reinterpret_cast<const double *>(ud.get()),
                       reinterpret_cast<uint8_t *>(act.get()), nullptr));
     uint8_t c = 0;
     check(dfrl_memcpy_d2h(device::get(), &c, act.get(), 1));
@@ -66,18 +73,19 @@ template <std::size_t range> struct discrete_action {
 
 private:
   void row_rule(int kind, vector_view input, vector_view output, float advantage) const {
-    if (input.size() != range || output.size() != range)
+    const std::size_t range_ = cardinality();
+    if (input.size() != range_ || output.size() != range_)
       throw xeno::error("action vector has the wrong size");
-    device_buffer p(range), o(range), adv(1), act(1), po(1);
-    p.upload(input.data(), range);
+    device_buffer p(range_), o(range_), adv(1), act(1), po(1);
+    p.upload(input.data(), range_);
     adv.upload(&advantage, 1);
     uint8_t c = (uint8_t)choice;
     check(dfrl_memcpy_h2d(device::get(), act.get(), &c, 1));
     float pold = distrib ? (*distrib)[choice] : 1.f;
     po.upload(&pold, 1);
     check(dfrl_loss_grad(device::get(), kind, p.get(), reinterpret_cast<const uint8_t *>(act.get()), adv.get(),
-                         po.get(), 0.f, 1, (int)range, o.get()));
-    o.download(output.data(), range);
+                         po.get(), 0.f, 1, (int)range_, o.get()));
+    o.download(output.data(), range_);
   }
 };
 

@@ -11,7 +11,7 @@ import refcases
 
 ROOT = refcases.ROOT
 HOST = os.path.join(ROOT, "dependence_free_rl_b200", "host")
-BINS = ["ppo_training", "ac_training", "pg_training", "deep_agent", "host_api_test"]
+BINS = ["ppo_training", "ac_training", "pg_training", "deep_agent", "host_api_test", "flagstore_test"]
 
 
 def _build():
@@ -49,6 +49,14 @@ def test_host_mirror_builds_and_keeps_reference_signatures():
             if f.endswith((".h", ".cc")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "cuda_runtime" not in txt and "<<<" not in txt, f
+
+
+def test_flagstore_and_runtime_problem_definition():
+    """xeno::flagstore (reference xeno/configuration.h:17-118) and bp::configure: the reference's constexpr
+    num_bins / capacity / item shapes as launch parameters. No device needed."""
+    _build()
+    out = subprocess.run([os.path.join(HOST, ".out", "flagstore_test")], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and out.stdout.strip().endswith("OK"), out.stdout + out.stderr
 
 
 @pytest.mark.gpu
@@ -104,6 +112,8 @@ def test_deep_agent_cpp_known_answer(tmp_path):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("binary,args", [("ppo_training", ["4096", "6", "5"]), ("ppo_training", ["4096", "6", "5", "c2"]),
+                                         ("ppo_training", ["--num_bins=16", "1024", "3", "2", "c2"]),   # run-time bins: layered path
+                                         ("ppo_training", ["-b", "5", "--capacity", "16", "512", "3", "0"]),
                                          ("ac_training", ["2048", "4"]),
                                          ("pg_training", ["256", "3"])])
 def test_trainer_mains_run(binary, args):
