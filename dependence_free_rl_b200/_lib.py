@@ -121,6 +121,7 @@ PROTOTYPES = {
     "dfrl_trainer_config_default": (None, [C.POINTER(TrainerConfig)]),
     "dfrl_trainer_create": (i32, [vp, C.POINTER(TrainerConfig), vp, vp, vp, C.POINTER(vp)]),
     "dfrl_trainer_destroy": (i32, [vp]),
+    "dfrl_trainer_set_rates": (i32, [vp, f32, f32, f32, f32]),
     "dfrl_trainer_rollout": (i32, [vp, vp, vp, vp]),
     "dfrl_trainer_learn": (i32, [vp]),
     "dfrl_trainer_learn_phases": (i32, [vp, i32]),

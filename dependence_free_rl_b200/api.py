@@ -367,6 +367,10 @@ class Trainer:
     def iterate(self, iters):
         check(lib.dfrl_trainer_iterate(self.h, iters))
 
+    def set_rates(self, policy_lr, value_lr=0.0, policy_wd=0.0, value_wd=0.0):
+        """optimizer::set_rate (nn.h:592) on the live learner; optimizer state is kept."""
+        check(lib.dfrl_trainer_set_rates(self.h, policy_lr, policy_wd, value_lr, value_wd))
+
     def read(self, field):
         nb = C.c_size_t()
         check(lib.dfrl_trainer_field_size(self.h, field, C.byref(nb)))

@@ -85,6 +85,45 @@ extern "C" int dfrl_nccl_unique_id(void *id128_host) {
 }
 
 // ------------------------------------------------------------------ context ------------------
+// Everything a context owns; also the error path of dfrl_init (members that were never created are null).
+static void release_ctx(dfrl_ctx *ctx) {
+  cudaSetDevice(ctx->device);
+  if (ctx->stream)
+    cudaStreamSynchronize(ctx->stream);
+  if (ctx->nccl_comm && g_nccl.destroy)
+    g_nccl.destroy(ctx->nccl_comm);
+  if (ctx->scratch)
+    cudaFree(ctx->scratch);
+  if (ctx->umma_ws)
+    cudaFree(ctx->umma_ws);
+  for (int r = 0; r < ctx->nranks && ctx->p2p.attached; ++r)
+    if (r != ctx->rank && ctx->p2p.peer[r])
+      cudaIpcCloseMemHandle(ctx->p2p.peer[r]);
+  if (ctx->p2p.local)
+    cudaFree(ctx->p2p.local);
+  if (ctx->ev0)
+    cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1)
+    cudaEventDestroy(ctx->ev1);
+  if (ctx->stream)
+    cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+static int init_resources(dfrl_ctx *ctx, const void *nccl_id) {
+  DFRL_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  DFRL_CUDA(cudaEventCreate(&ctx->ev0));
+  DFRL_CUDA(cudaEventCreate(&ctx->ev1));
+  if (ctx->nranks > 1) {
+    DFRL_CHECK(nccl_id, "nccl_id required for nranks > 1");
+    DFRL_TRY(load_nccl());
+    nccl_uid id;
+    memcpy(&id, nccl_id, 128);
+    DFRL_TRY(nccl_check(g_nccl.init_rank(&ctx->nccl_comm, ctx->nranks, id, ctx->rank), "ncclCommInitRank"));
+  }
+  return DFRL_OK;
+}
+
 extern "C" int dfrl_init(int device, int nranks, int rank, const void *nccl_id, dfrl_ctx **out) {
   DFRL_CHECK(out, "null out");
   DFRL_CHECK(nranks >= 1 && rank >= 0 && rank < nranks, "bad rank %d / %d", rank, nranks);
@@ -112,15 +151,10 @@ extern "C" int dfrl_init(int device, int nranks, int rank, const void *nccl_id, 
   ctx->cc_major = prop.major;
   ctx->cc_minor = prop.minor;
   ctx->hbm_bytes = prop.totalGlobalMem;
-  DFRL_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-  DFRL_CUDA(cudaEventCreate(&ctx->ev0));
-  DFRL_CUDA(cudaEventCreate(&ctx->ev1));
-  if (nranks > 1) {
-    DFRL_CHECK(nccl_id, "nccl_id required for nranks > 1");
-    DFRL_TRY(load_nccl());
-    nccl_uid id;
-    memcpy(&id, nccl_id, 128);
-    DFRL_TRY(nccl_check(g_nccl.init_rank(&ctx->nccl_comm, nranks, id, rank), "ncclCommInitRank"));
+  int rc = init_resources(ctx, nccl_id);
+  if (rc != DFRL_OK) {  // release whatever was created (dfrl_last_error keeps the reason)
+    release_ctx(ctx);
+    return rc;
   }
   *out = ctx;
   return DFRL_OK;
@@ -129,23 +163,7 @@ extern "C" int dfrl_init(int device, int nranks, int rank, const void *nccl_id, 
 extern "C" int dfrl_destroy(dfrl_ctx *ctx) {
   if (!ctx)
     return DFRL_OK;
-  cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
-  if (ctx->nccl_comm && g_nccl.destroy)
-    g_nccl.destroy(ctx->nccl_comm);
-  if (ctx->scratch)
-    cudaFree(ctx->scratch);
-  if (ctx->umma_ws)
-    cudaFree(ctx->umma_ws);
-  for (int r = 0; r < ctx->nranks && ctx->p2p.attached; ++r)
-    if (r != ctx->rank && ctx->p2p.peer[r])
-      cudaIpcCloseMemHandle(ctx->p2p.peer[r]);
-  if (ctx->p2p.local)
-    cudaFree(ctx->p2p.local);
-  cudaEventDestroy(ctx->ev0);
-  cudaEventDestroy(ctx->ev1);
-  cudaStreamDestroy(ctx->stream);
-  delete ctx;
+  release_ctx(ctx);
   return DFRL_OK;
 }
 

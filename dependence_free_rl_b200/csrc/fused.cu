@@ -2352,11 +2352,14 @@ bool conv_widths_ok(const net3 &n) { return (n.d1 == 128 && n.d2 == 64) || (n.d1
 
 bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
 
+// cudaFuncSetAttribute is a per-device setting: one bit per device ordinal (a process may own contexts
+// on several GPUs).
 template <typename K>
-int set_smem_once(K kernel, int smem, bool *done) {
-  if (!*done) {
+int set_smem_once(const dfrl_ctx *ctx, K kernel, int smem, unsigned long long *done) {
+  const unsigned long long bit = 1ull << (ctx->device & 63);
+  if (!(*done & bit)) {
     DFRL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    *done = true;
+    *done |= bit;
   }
   return DFRL_OK;
 }
@@ -2399,8 +2402,8 @@ int launch_fused(dfrl_ctx *ctx, K kernel, const char *name, int grid, int block,
 template <int D0, int D1, int D2, int NOUT>
 int launch_policy_step(dfrl_ctx *ctx, const policy_step_args &a, int ctas) {
   constexpr int smem = pmap<D1, D2>::TOTAL + 1024;
-  static bool attr = false;
-  DFRL_TRY(set_smem_once(fused_policy_step_kernel<D0, D1, D2, NOUT>, smem, &attr));
+  static unsigned long long attr = 0;
+  DFRL_TRY(set_smem_once(ctx, fused_policy_step_kernel<D0, D1, D2, NOUT>, smem, &attr));
   return launch_fused(ctx, fused_policy_step_kernel<D0, D1, D2, NOUT>, "(fused_policy_step_kernel<D0, D1, D2, NOUT>)",
                             ctas, pmap<D1, D2>::THREADS, smem, a);
 }
@@ -2408,8 +2411,8 @@ int launch_policy_step(dfrl_ctx *ctx, const policy_step_args &a, int ctas) {
 template <int D0, int D1, int D2, bool EG>
 int launch_critic_step_eg(dfrl_ctx *ctx, const critic_args &a, int ctas) {
   constexpr int smem = cmap<D1, D2, CRITIC_STEP>::TOTAL + 1024;
-  static bool attr = false;
-  DFRL_TRY(set_smem_once(fused_critic_kernel<D0, D1, D2, CRITIC_STEP, EG>, smem, &attr));
+  static unsigned long long attr = 0;
+  DFRL_TRY(set_smem_once(ctx, fused_critic_kernel<D0, D1, D2, CRITIC_STEP, EG>, smem, &attr));
   return launch_fused(ctx, fused_critic_kernel<D0, D1, D2, CRITIC_STEP, EG>,
                             "(fused_critic_kernel<D0, D1, D2, CRITIC_STEP, EG>)",
                             ctas, cmap<D1, D2, CRITIC_STEP>::THREADS, smem, a);
@@ -2422,8 +2425,8 @@ int launch_critic_step(dfrl_ctx *ctx, const critic_args &a, int ctas) {
 template <int D0, int D1, int D2, bool EG>
 int launch_gae_eg(dfrl_ctx *ctx, const critic_args &a, int ctas) {
   constexpr int smem = cmap<D1, D2, CRITIC_GAE>::TOTAL + 1024;
-  static bool attr = false;
-  DFRL_TRY(set_smem_once(fused_critic_kernel<D0, D1, D2, CRITIC_GAE, EG>, smem, &attr));
+  static unsigned long long attr = 0;
+  DFRL_TRY(set_smem_once(ctx, fused_critic_kernel<D0, D1, D2, CRITIC_GAE, EG>, smem, &attr));
   return launch_fused(ctx, fused_critic_kernel<D0, D1, D2, CRITIC_GAE, EG>, "(fused_critic_kernel<D0, D1, D2, CRITIC_GAE, EG>)", ctas,
                       cmap<D1, D2, CRITIC_GAE>::THREADS, smem, a);
 }
@@ -2435,8 +2438,8 @@ int launch_gae(dfrl_ctx *ctx, const critic_args &a, int ctas) {
 template <int D0, int D1, int D2>
 int launch_vend(dfrl_ctx *ctx, const vend_args &a, int ctas) {
   constexpr int smem = vmap<D1, D2>::TOTAL + 1024;
-  static bool attr = false;
-  DFRL_TRY(set_smem_once(fused_vend_kernel<D0, D1, D2>, smem, &attr));
+  static unsigned long long attr = 0;
+  DFRL_TRY(set_smem_once(ctx, fused_vend_kernel<D0, D1, D2>, smem, &attr));
   return launch_fused(ctx, fused_vend_kernel<D0, D1, D2>, "(fused_vend_kernel<D0, D1, D2>)", ctas, vmap<D1, D2>::THREADS, smem, a);
 }
 
@@ -2446,8 +2449,8 @@ template <int D0, int D1, int D2, int NOUT>
 int launch_rollout(dfrl_ctx *ctx, const rollout_args &a, int ctas) {
   constexpr int NP = 4;
   constexpr int smem = rmap<D1, D2, NP>::TOTAL + 1024;
-  static bool attr = false;
-  DFRL_TRY(set_smem_once(fused_rollout_kernel<D0, D1, D2, NOUT, NP>, smem, &attr));
+  static unsigned long long attr = 0;
+  DFRL_TRY(set_smem_once(ctx, fused_rollout_kernel<D0, D1, D2, NOUT, NP>, smem, &attr));
   return launch_fused(ctx, fused_rollout_kernel<D0, D1, D2, NOUT, NP>, "(fused_rollout_kernel<D0, D1, D2, NOUT, NP>)", ctas,
                       160 * NP, smem, a);
 }
@@ -2455,8 +2458,8 @@ int launch_rollout(dfrl_ctx *ctx, const rollout_args &a, int ctas) {
 template <int D1, int D2>
 int launch_conv_policy_step(dfrl_ctx *ctx, const conv_step_args &a, int ctas) {
   constexpr int smem = cvmap<D1, D2>::TOTAL + 1024;
-  static bool attr = false;
-  DFRL_TRY(set_smem_once(fused_conv_policy_step_kernel<D1, D2>, smem, &attr));
+  static unsigned long long attr = 0;
+  DFRL_TRY(set_smem_once(ctx, fused_conv_policy_step_kernel<D1, D2>, smem, &attr));
   return launch_fused(ctx, fused_conv_policy_step_kernel<D1, D2>, "(fused_conv_policy_step_kernel<D1, D2>)", ctas,
                       cvmap<D1, D2>::THREADS, smem, a);
 }
@@ -2464,8 +2467,8 @@ template <int D1, int D2>
 int launch_conv_rollout(dfrl_ctx *ctx, const rollout_args &a, int ctas) {
   constexpr int NP = 2;
   constexpr int smem = cvrmap<D1, D2, NP>::TOTAL + 1024;
-  static bool attr = false;
-  DFRL_TRY(set_smem_once(fused_conv_rollout_kernel<D1, D2, NP>, smem, &attr));
+  static unsigned long long attr = 0;
+  DFRL_TRY(set_smem_once(ctx, fused_conv_rollout_kernel<D1, D2, NP>, smem, &attr));
   return launch_fused(ctx, fused_conv_rollout_kernel<D1, D2, NP>, "(fused_conv_rollout_kernel<D1, D2, NP>)", ctas, 160 * NP,
                       smem, a);
 }

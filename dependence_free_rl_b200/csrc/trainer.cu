@@ -230,6 +230,9 @@ static size_t opt_state_floats(int kind, int n) {
   return kind == DFRL_OPT_SGD ? 0 : kind == DFRL_OPT_MOMENTUM ? (size_t)n : (size_t)2 * n;
 }
 
+static int trainer_setup(dfrl_trainer *t, dfrl_ctx *ctx, const dfrl_trainer_config *cfg, dfrl_env *env,
+                         dfrl_mlp *policy, dfrl_mlp *value);
+
 extern "C" int dfrl_trainer_create(dfrl_ctx *ctx, const dfrl_trainer_config *cfg, dfrl_env *env,
                                    dfrl_mlp *policy, dfrl_mlp *value, dfrl_trainer **out) {
   DFRL_CHECK(ctx && cfg && env && policy && out, "null argument");
@@ -243,8 +246,21 @@ extern "C" int dfrl_trainer_create(dfrl_ctx *ctx, const dfrl_trainer_config *cfg
     DFRL_CHECK(value->input_cols == 4 * env->B, "value input width mismatch");
     DFRL_CHECK(value->output_cols == 1, "value model must output one column");
   }
-  dfrl_trainer *t = new dfrl_trainer();
+  dfrl_trainer *t = new dfrl_trainer();  // value-initialised: every member null / zero
   t->ctx = ctx;
+  int rc = trainer_setup(t, ctx, cfg, env, policy, value);
+  if (rc != DFRL_OK) {  // a failed allocation: release what exists (dfrl_last_error keeps the reason)
+    dfrl_trainer_destroy(t);
+    return rc;
+  }
+  *out = t;
+  if (cfg->fused)
+    dfrl_fused_try_attach(t);  // silently stays layered when the nets do not qualify
+  return DFRL_OK;
+}
+
+static int trainer_setup(dfrl_trainer *t, dfrl_ctx *ctx, const dfrl_trainer_config *cfg, dfrl_env *env,
+                         dfrl_mlp *policy, dfrl_mlp *value) {
   t->cfg = *cfg;
   t->env = env;
   t->policy = policy;
@@ -338,9 +354,6 @@ extern "C" int dfrl_trainer_create(dfrl_ctx *ctx, const dfrl_trainer_config *cfg
   t->graph_exec = nullptr;
   t->graph_launches = 0;
   t->plain_iterations = 0;
-  *out = t;
-  if (cfg->fused)
-    dfrl_fused_try_attach(t);  // silently stays layered when the nets do not qualify
   return DFRL_OK;
 }
 
@@ -723,6 +736,22 @@ static int learn_graphed(dfrl_trainer *t) {
 extern "C" int dfrl_trainer_learn(dfrl_trainer *t) {
   DFRL_CHECK(t, "null trainer");
   return learn_graphed(t);
+}
+
+// optimizer::set_rate (nn.h:592) on a live learner. The rates are arguments of the captured kernels.
+extern "C" int dfrl_trainer_set_rates(dfrl_trainer *t, float policy_lr, float policy_wd, float value_lr, float value_wd) {
+  DFRL_CHECK(t, "null trainer");
+  dfrl_trainer_config &c = t->cfg;
+  if (c.policy_lr == policy_lr && c.policy_wd == policy_wd && c.value_lr == value_lr && c.value_wd == value_wd)
+    return DFRL_OK;
+  c.policy_lr = policy_lr, c.policy_wd = policy_wd, c.value_lr = value_lr, c.value_wd = value_wd;
+  if (t->graph_exec) {
+    DFRL_CUDA(cudaStreamSynchronize(t->ctx->stream));
+    cudaGraphExecDestroy((cudaGraphExec_t)t->graph_exec);
+    t->graph_exec = nullptr;
+    t->graph_launches = 0;
+  }
+  return DFRL_OK;
 }
 
 extern "C" int dfrl_trainer_learn_phases(dfrl_trainer *t, int phases) {

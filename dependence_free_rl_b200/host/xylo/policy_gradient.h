@@ -64,6 +64,8 @@ public:
     if (!s.trainer || !s.rolled)
       throw xeno::error("learn() before any rollout");
     // update_value_model (196-218) + calculate_advantage (220-281) with the updated critic
+    s.sync_rates();
+    s.learned = true;
     check(dfrl_trainer_learn_phases(s.trainer, DFRL_PHASE_VALUE | DFRL_PHASE_ADVANTAGE));
     std::size_t bytes = 0;
     check(dfrl_trainer_field_size(s.trainer, DFRL_F_ADVANTAGE, &bytes));

@@ -129,6 +129,7 @@ struct rollout_store {
   dfrl_trainer *trainer = nullptr;
   int work = 0;
   bool rolled = false;
+  bool learned = false;  // a learn() ran on this trainer: optimizer state lives on the device
   // evaluation-only bookkeeping (agent::play_one_episode with a deterministic policy)
   double eval_reward = 0;
   long long eval_episodes = 0;
@@ -139,6 +140,15 @@ struct rollout_store {
       dfrl_trainer_destroy(trainer);
     trainer = nullptr;
   }
+  // optimizer::set_rate (nn.h:592) after the first rollout: the device learner reads the optimizers'
+  // current rates before every learn() (momentum / Adam state, the Adam step counter and the KL beta
+  // are kept; only a captured CUDA graph is re-captured).
+  void sync_rates() {
+    if (!trainer || !policy_opt)
+      return;
+    check(dfrl_trainer_set_rates(trainer, policy_opt->rate(), policy_opt->weight_decay(),
+                                 value_opt ? value_opt->rate() : 0.f, value_opt ? value_opt->weight_decay() : 0.f));
+  }
   void ensure_trainer(int w) {
     if (trainer && w == work)
       return;
@@ -146,6 +156,12 @@ struct rollout_store {
       throw xeno::error("no learner is attached to this replay buffer");
     if (!env || !policy_model)
       throw xeno::error("no agent is attached to this replay buffer");
+    // The record buffers are sized by the rollout length. Re-creating the device learner would silently
+    // drop momentum / Adam state, the Adam step counter, the KL beta and the statistics: refuse once
+    // anything has been learned (a different length BEFORE the first learn() is harmless).
+    if (trainer && learned)
+      throw xeno::error("the rollout length changed after learn(): play_steps(n) must keep its n "
+                        "(the device records and the optimizer state belong to one rollout length)");
     drop();
     dfrl_trainer_config c;
     dfrl_trainer_config_default(&c);
@@ -310,7 +326,9 @@ protected:
     rollout_store &s = replay_buffer_.store();
     if (!s.trainer || !s.rolled)
       throw xeno::error("learn() before any rollout");
+    s.sync_rates();
     check(dfrl_trainer_learn(s.trainer));
+    s.learned = true;
   }
   replay_buffer<A, S> &replay_buffer_;
   model &policy_model_;

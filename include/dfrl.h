@@ -344,6 +344,11 @@ void dfrl_trainer_config_default(dfrl_trainer_config *cfg);
 int dfrl_trainer_create(dfrl_ctx *ctx, const dfrl_trainer_config *cfg, dfrl_env *env,
                         dfrl_mlp *policy, dfrl_mlp *value, dfrl_trainer **out);
 int dfrl_trainer_destroy(dfrl_trainer *tr);
+/* optimizer::set_rate (nn.h:592) after the learner exists: the learning rates (and weight decays) of the
+ * next learn(). Optimizer state (momentum / Adam moments, Adam step counter), the KL beta and the
+ * statistics are kept; a captured CUDA graph of the learn phase is dropped (rates are kernel arguments)
+ * and re-captured by the next graph-eligible learn(). */
+int dfrl_trainer_set_rates(dfrl_trainer *tr, float policy_lr, float policy_wd, float value_lr, float value_wd);
 
 /* Rollout phase of the trainer mains (ppo_training.cc:55-61): every env plays `work` steps
  * (or episodes). Optional host tapes, all [work][N] step-major (AC/PPO only):

@@ -244,6 +244,40 @@ def test_eval_after_graph_replay_uses_current_weights(D, ctx):
     tr.close(); env.close(); policy.close(); value.close()
 
 
+def test_set_rates_on_a_graph_replaying_learner(D, ctx):
+    """optimizer::set_rate (nn.h:592) after the learn phase has been captured as a CUDA graph: the new
+    rates take effect at the next learn() (rates are kernel arguments: the graph is re-captured), the
+    momentum state survives. Checked against a second trainer that is driven launch by launch
+    (learn_phases never replays a graph) through the same schedule."""
+    n, T = 1024, 4
+    def run(graphed):
+        policy = D.Model(ctx, D.fc_layers(PD, D.SOFTMAX), 32)
+        value = D.Model(ctx, D.fc_layers(VD), 32)
+        policy.init_parameters(5)
+        value.init_parameters(6)
+        env = D.Environment(ctx, n, seed=3)
+        lr = 1e-2 / (n * T)
+        tr = D.Trainer(ctx, env, policy, value, algo=D.PPO, work=T, policy_lr=lr, value_lr=lr,
+                       policy_opt=D.MOMENTUM, value_opt=D.MOMENTUM)
+        out = []
+        for it in range(8):
+            if it == 5:
+                tr.set_rates(3 * lr, 0.5 * lr)
+            tr.rollout()
+            if graphed:
+                tr.learn()
+            else:
+                tr.learn(D.PHASE_VALUE | D.PHASE_ADVANTAGE)
+                tr.learn(D.PHASE_POLICY)
+            out.append((policy.parameters().copy(), value.parameters().copy()))
+        tr.close(); env.close(); policy.close(); value.close()
+        return out
+    g, l = run(True), run(False)
+    assert not np.array_equal(g[4][0], g[5][0])
+    for it in range(8):
+        assert np.array_equal(g[it][0], l[it][0]) and np.array_equal(g[it][1], l[it][1]), f"iteration {it}"
+
+
 @pytest.mark.parametrize("nets,iters", [("reference", 1000), ("c2_fused_he_init", 3000)])
 def test_ppo_learns_bin_packing(D, ctx, nets, iters):
     """The reference's only own test is the reward of the argmax policy climbing towards 26.55

@@ -59,6 +59,37 @@ def test_flagstore_and_runtime_problem_definition():
     assert out.returncode == 0 and out.stdout.strip().endswith("OK"), out.stdout + out.stderr
 
 
+def test_own_xmake_builds_the_host_targets(tmp_path):
+    """The repo's own build tool (tools/xmake/xmake.cc, C++ like the reference's build/xmake.cc; target
+    schema of build/xmake.cc:92-103 + the `cuda` rule): stage-0 bootstrap, a dry-run plan that compiles the
+    .cu sources with nvcc for sm_100a and links the host main against the device library only, and an
+    mtime-based no-op on the second run."""
+    xm = subprocess.run([os.path.join(ROOT, "tools", "xmake", "bootstrap.sh")], capture_output=True, text=True, timeout=300)
+    assert xm.returncode == 0, xm.stdout + xm.stderr
+    exe = xm.stdout.strip().splitlines()[-1]
+    pkg = os.path.join(HOST, "apps", "bin_packing")
+    plan = subprocess.run([exe, "-n", "-B", "ppo_training"], cwd=pkg, capture_output=True, text=True, timeout=60)
+    assert plan.returncode == 0, plan.stdout + plan.stderr
+    lines = plan.stdout.strip().splitlines()
+    cu = [l for l in lines if l.startswith("nvcc") and " -c " in l]
+    assert len(cu) == 8 and all("arch=compute_100a,code=sm_100a" in l and "-lineinfo" in l for l in cu), plan.stdout
+    assert any("-shared" in l and "libdfrl_b200.so" in l for l in lines)
+    assert "-std=c++20" in lines[-2] and "ppo_training.cc" in lines[-2]
+    assert "-ldfrl_b200" in lines[-1] and "cudart" not in lines[-1] and lines[-1].rstrip().endswith("ppo_training")
+    # a real build of a host-only test target (the device library is linked, not rebuilt, when it is current)
+    tests_pkg = os.path.join(HOST, "tests")
+    lib = os.path.join(ROOT, "dependence_free_rl_b200", "csrc", ".out", "libdfrl_b200.so")
+    if os.path.exists(lib):
+        out = subprocess.run([exe, "flagstore_test"], cwd=tests_pkg, capture_output=True, text=True, timeout=900)
+        assert out.returncode == 0, out.stdout + out.stderr
+        again = subprocess.run([exe, "flagstore_test"], cwd=tests_pkg, capture_output=True, text=True, timeout=60)
+        assert again.returncode == 0 and again.stdout.strip() == "", again.stdout
+        run = subprocess.run([os.path.join(tests_pkg, ".out", "flagstore_test")], capture_output=True, text=True, timeout=60)
+        assert run.returncode == 0 and run.stdout.strip().endswith("OK")
+    bad = subprocess.run([exe, "no_such_target"], cwd=pkg, capture_output=True, text=True, timeout=60)
+    assert bad.returncode != 0 and "no target" in bad.stderr
+
+
 @pytest.mark.gpu
 def test_host_api_matches_python_binding(D, ctx):
     _build()
