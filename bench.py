@@ -599,6 +599,29 @@ def run_ours(args):
             row["algorithmic_tflops_whole_step"] = row["value"] * 2296208 / 1e12
             row["frac_of_bf16_peak"] = row["algorithmic_tflops_whole_step"] / peaks["bf16_tflops_sustained"]
             extra[key] = row
+        # The two learners that stay on the layered kernels: KL-PPO (kl_ppo_learner,
+        # policy_gradient.h:310-335: end rows join the policy pass, beta adapts from the mean KL of all
+        # rows between epochs -- one host read per epoch) and REINFORCE with the reference's FC policy
+        # 32-256-128-8 + softmax-CE (pg_training.cc:12-18; whole episodes per iteration: env-steps
+        # counted by the device statistics). 4096 envs each; wall clock around synchronous iterations.
+        def layered_rate(objs, n_envs, warm, iters):
+            tr = objs[0]
+            tr.iterate(warm)
+            s0 = tr.stats()["env_steps"]
+            l0 = ctx.launches()
+            t0 = time.perf_counter()
+            tr.iterate(iters)
+            s1 = tr.stats()["env_steps"]          # (synchronises)
+            dt = time.perf_counter() - t0
+            launches = (ctx.launches() - l0) / iters
+            for o in (objs[0], objs[1], objs[3], objs[2]):
+                if o is not None:
+                    o.close()
+            return {"value": (s1 - s0) / dt, "unit": "env-steps/s", "ms_per_step": 1e3 * dt / iters, "envs": n_envs,
+                    "env_steps_per_iter": (s1 - s0) / iters, "launches_per_step": launches, "path": "layered kernels"}
+        extra["kl_ppo_4096_envs"] = layered_rate(make_trainer(D, ctx, 4096, 0, 4096 * T_STEPS, algo=D.KL_PPO), 4096, 3, 20)
+        pg = make_trainer(D, ctx, 4096, 0, 4096 * 13, algo=D.REINFORCE, work=1, pdims=[32, 256, 128, 8], last=D.SOFTMAX_CE)
+        extra["reinforce_refnet_4096_envs"] = layered_rate(pg, 4096, 2, 10)
         extra["hbm_kernels"] = hbm_kernel_rows(D, ctx, peaks)
     if world == 1 and not args.no_c2:
         # BASELINE configs[1] verbatim: PPO, 4096 parallel envs, 1 GPU (latency-bound size)

@@ -2592,6 +2592,12 @@ int dfrl_fused_try_attach(dfrl_trainer *t) {
     delete f;
     return DFRL_ERR_CUDA;
   }
+  if (f->policy_conv)
+    if (const char *e = getenv("DFRL_CONV_LOLO")) {
+      const int v = atoi(e) != 0;
+      cudaMemcpyToSymbolAsync(c_conv_lolo, &v, sizeof(int), 0, cudaMemcpyHostToDevice, t->ctx->stream);
+      cudaStreamSynchronize(t->ctx->stream);
+    }
   t->fused_impl = f;
   return DFRL_OK;
 }

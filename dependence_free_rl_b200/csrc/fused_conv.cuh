@@ -28,12 +28,20 @@
 // rounding error of an activation is amplified by that ratio, and the bf16 hi/lo pairs of the dense
 // kernels (2^-17 relative) left a 16-sample reference trace 1.1e-4 off (golden `ppo_refnet_conv`).
 // Here every MMA operand is split x = hi + lo with hi, lo in FP16 (11 + 11 significant bits, 2^-22
-// relative) and a product is hi.hi + hi.lo + lo.hi + lo.lo. FP16's narrow exponent range is handled by
+// relative) and a product is hi.hi + hi.lo + lo.hi (+ lo.lo where it is free: the stacked weight-gradient
+// GEMMs; see c_conv_lolo). FP16's narrow exponent range is handled by
 // power-of-two scales (exact): weights are staged as W * S_W with max|W * S_W| in [2^12, 2^13) and the
 // epilogues multiply the accumulators by 1 / S_W; the gradient chain runs on dY * S_g with max|A| * S_g
 // in [8, 16) over the CTA's own rows (the CTA's partial gradient is multiplied by 1 / S_g in the
 // drain). Activations are used unscaled (|h| < 65504 assumed; an overflow would surface as inf / NaN
 // gradients, not silently).
+// Whether the A-from-TMEM GEMMs (layer 2, dH1) also issue the lo.lo product (2^-22 of a term; the stacked
+// weight-gradient GEMMs carry it for free). OFF: measured on B200 (profiles/r02c_conv_lolo_ab.log) the
+// fourth product costs 4.8 % of the policy step (982 -> 935 us at 131 072 envs) and 4 % of the rollout and
+// changes no parity figure (conv policy gradients 0.5e-6 .. 1.4e-5 from the fp64 oracle either way: the
+// error floor is the fp32 accumulation order, not the operand split). DFRL_CONV_LOLO=1 turns it on.
+__constant__ int c_conv_lolo = 0;
+
 __device__ __forceinline__ void split2_h(float a, float b, uint32_t &hi, uint32_t &lo) {
   __half2 h = __floats2half2_rn(a, b);
   hi = *reinterpret_cast<uint32_t *>(&h);
@@ -231,7 +239,8 @@ __device__ __forceinline__ void conv_issue_layer2(uint32_t tm, uint32_t sbase) {
     umma::mma_bf16_ta(tm + CM::ACC1, ah, bh, IDH<D2>::FK_FK, k > 0 ? 1u : 0u);
     umma::mma_bf16_ta(tm + CM::ACC1, ah, bl, IDH<D2>::FK_FK, 1);
     umma::mma_bf16_ta(tm + CM::ACC1, al, bh, IDH<D2>::FK_FK, 1);
-    umma::mma_bf16_ta(tm + CM::ACC1, al, bl, IDH<D2>::FK_FK, 1);  // lo.lo too: see the precision note in the header
+    if (c_conv_lolo)
+      umma::mma_bf16_ta(tm + CM::ACC1, al, bl, IDH<D2>::FK_FK, 1);  // lo.lo too: see the precision note in the header
   }
 }
 
@@ -340,7 +349,8 @@ __global__ void __launch_bounds__((cvmap<D1, D2>::THREADS), 1) fused_conv_policy
           umma::mma_bf16_ta(tm + CM::ACC0, ah, bh, IDH<D1>::BK_FM, k > 0 ? 1u : 0u);
           umma::mma_bf16_ta(tm + CM::ACC0, ah, bl, IDH<D1>::BK_FM, 1);
           umma::mma_bf16_ta(tm + CM::ACC0, al, bh, IDH<D1>::BK_FM, 1);
-          umma::mma_bf16_ta(tm + CM::ACC0, al, bl, IDH<D1>::BK_FM, 1);
+          if (c_conv_lolo)
+            umma::mma_bf16_ta(tm + CM::ACC0, al, bl, IDH<D1>::BK_FM, 1);
         }
         umma::commit(bar);
         // dW2 (+)= [hi(dH2); lo(dH2)]^T . hi(H1) + [hi(dH2); lo(dH2)]^T . lo(H1): runs behind the dH1 epilogue
