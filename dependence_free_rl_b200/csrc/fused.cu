@@ -72,6 +72,18 @@ __device__ __forceinline__ tid_t thread_id() {
   return t;
 }
 
+// Load-balance probe (debug): %globaltimer in ns and the SM a CTA runs on.
+__device__ __forceinline__ long long global_ns() {
+  long long v;
+  asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(v));
+  return v;
+}
+__device__ __forceinline__ unsigned sm_id() {
+  unsigned v;
+  asm volatile("mov.u32 %0, %%smid;\n" : "=r"(v));
+  return v;
+}
+
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float *v) {
   uint32_t r[8];
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
@@ -269,7 +281,8 @@ struct policy_step_args {
   int loss_kind, head_bwd;
   float *partials;     // [gridDim.x][n_params]
   grad_tail tail;
-  long long *clk;      // optional: phase clocks of CTA 0 (debug)
+  long long *clk;      // optional: phase clocks of CTA clk_cta (debug)
+  int clk_cta;
 };
 
 // ---- gradient tail (see grad_tail) ------------------------------------------------------------
@@ -335,14 +348,24 @@ __device__ __forceinline__ float exchange_entry(const p2p_view &v, unsigned epoc
     g += __uint_as_float((unsigned)x[q]);
   return g;
 }
-// Whole CTA, after its partial gradient has been written to partials[blockIdx.x][0..n).
-// scratch: (blockDim.x / 64) * 64 floats of shared memory. Contains __syncthreads.
+// Row stride (floats) of the per-CTA partial gradients: rows are 16-byte aligned for the tail's loads.
+__host__ __device__ __forceinline__ int partial_stride(int n_params) { return (n_params + 3) & ~3; }
+
+// Whole CTA, after its partial gradient has been written to partials[blockIdx.x * partial_stride(n)][0..n).
+// scratch: (blockDim.x / 16) * 64 floats of shared memory. Contains __syncthreads.
+//
+// The tail runs once per launch, i.e. on a cold instruction cache: round 2 measured 8 800 .. 17 000 cycles
+// for "30 loads per thread + sum" when that was 3 KB of unrolled straight-line code (the whole kernel is
+// 105 KB of SASS). Hence few, wide instructions: the CTA's slice is a multiple of 4 parameters, a thread
+// loads 16-byte words (4 parameters of one CTA's partial) for <= 10 source CTAs -- all in flight at once
+// -- and the source-CTA groups are combined through shared memory in a fixed order.
 __device__ __forceinline__ void gradient_tail(const float *__restrict__ partials, const net3 &net, const grad_tail &tl,
                                               float *scratch, long long *clk = nullptr) {
-  const int n = net.n_params;
+  const int n = net.n_params, ps = partial_stride(n);
   const tail_ctx tc = tail_begin(tl);
-  const int G = (int)gridDim.x, NS = (int)blockDim.x >> 6, s = (int)threadIdx.x >> 6, p = (int)threadIdx.x & 63;
-  const int per = (n + G - 1) / G;
+  const int G = (int)gridDim.x, p = (int)threadIdx.x & 63;
+  const int R = (int)blockDim.x >> 4, rg = (int)threadIdx.x >> 4, q4 = (int)threadIdx.x & 15;  // source-CTA group, 16-byte column
+  const int per = (((n + G - 1) / G) + 3) & ~3;
   const int lo = (int)blockIdx.x * per, hi = min(lo + per, n);
   const dfrl_opt_spec &opt = tl.opt;
   const bool exchange = opt.params && tl.v.nranks > 1;
@@ -350,8 +373,9 @@ __device__ __forceinline__ void gradient_tail(const float *__restrict__ partials
   // 64 are loaded BEFORE the grid barrier, so that the update behind the reduction costs no further
   // L2 round trip (the tail is a chain of round trips: barrier, partials, update).
   const bool updates = opt.params != nullptr;
+  const bool owner = threadIdx.x < 64;
   float p0 = 0.f, m0 = 0.f, v0 = 0.f;
-  if (updates && s == 0 && lo + p < hi) {
+  if (updates && owner && lo + p < hi) {
     p0 = __ldcg(opt.params + lo + p);
     if (opt.kind != DFRL_OPT_SGD)
       m0 = __ldcg(opt.state + lo + p);
@@ -382,28 +406,31 @@ __device__ __forceinline__ void gradient_tail(const float *__restrict__ partials
   __syncthreads();
   if (clk)
     clk[1] = clock64();
-  constexpr int MAXL = 32;  // loads in flight per thread: one L2 round trip for <= 32 NS partials (160 CTAs at NS = 5)
+  constexpr int MAXR = 10;  // 16-byte loads in flight per thread: one L2 round trip for <= 10 R source CTAs (R >= 18)
   for (int base = lo; base < hi; base += 64) {
     const int i = base + p;
-    float acc = 0.f;
-    if (i < hi && s < NS)
-      for (int c0 = s; c0 < G; c0 += MAXL * NS) {  // fixed order
-        float x[MAXL];
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (base + 4 * q4 < hi) {
+      const float4 *src = reinterpret_cast<const float4 *>(partials + base + 4 * q4);
+      for (int c0 = rg; c0 < G; c0 += MAXR * R) {  // fixed order
+        float4 x[MAXR];
 #pragma unroll
-        for (int q = 0; q < MAXL; ++q) {
-          const int c = c0 + q * NS;
-          x[q] = c < G ? __ldcg(partials + (size_t)c * n + i) : 0.f;
+        for (int q = 0; q < MAXR; ++q) {
+          const int c = c0 + q * R;
+          x[q] = c < G ? __ldcg(src + (size_t)c * (ps >> 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
-        for (int q = 0; q < MAXL; ++q)
-          acc += x[q];
+        for (int q = 0; q < MAXR; ++q)
+          acc.x += x[q].x, acc.y += x[q].y, acc.z += x[q].z, acc.w += x[q].w;
       }
-    if (s < NS)
-      scratch[s * 64 + p] = acc;
+    }
+    reinterpret_cast<float4 *>(scratch)[rg * 16 + q4] = acc;
     __syncthreads();
-    if (s == 0 && i < hi) {
+    if (clk && base == lo)
+      clk[2] = clock64();
+    if (owner && i < hi) {
       float g = 0.f;
-      for (int q = 0; q < NS; ++q)
+      for (int q = 0; q < R; ++q)  // source-CTA groups in order
         g += scratch[q * 64 + p];
       if (exchange)
         g = exchange_entry(tl.v, tc.epoch, i, g);
@@ -581,7 +608,7 @@ template <int D, bool TMEM_COPY = false, bool SMEM_STORE = true>
 __device__ __forceinline__ void epi2_fwd(uint32_t acc, const tid_t &t, const float *__restrict__ bias, uint8_t *hi,
                                          uint8_t *lo, int h0 = 0, int h1 = D / (D < 32 ? D : 32)) {
   constexpr int CH = D < 32 ? D : 32;
-#pragma unroll
+#pragma unroll  // (rolling this loop was measured slower: the chunks' TMEM loads / stores no longer overlap)
   for (int h = h0; h < h1; ++h) {
     float v[CH];
     tmem_load<CH>(acc + t.lane_base + h * CH, v);
@@ -756,7 +783,11 @@ __global__ void __launch_bounds__((pmap<D1, D2>::THREADS), 1) fused_policy_step_
   uint64_t *bar = bars + wg, *bar_dw2 = bars + 3 + wg, *bar_dw1 = bars + 5 + wg;
   uint32_t rp = 0;  // parity of the operands-ready barrier
 
-  long long *clk = (a.clk && blockIdx.x == 0 && threadIdx.x == 96) ? a.clk : nullptr;  // pipeline 0, chunk 0
+  long long *clk = (a.clk && (int)blockIdx.x == a.clk_cta && threadIdx.x == 96) ? a.clk : nullptr;  // pipeline 0, chunk 0
+  // every CTA: %globaltimer (ns) at entry / end of the tile loop / end of the kernel, and its SM (load balance)
+  long long *gclk = (a.clk && threadIdx.x == 96 && blockIdx.x < 160) ? a.clk + 112 + 4 * blockIdx.x : nullptr;
+  if (gclk)
+    gclk[0] = global_ns(), gclk[3] = sm_id();
   int clk_n = 0;
 #define STAMP() do { if (clk && clk_n < 104) clk[clk_n++] = clock64(); } while (0)
   if (clk)
@@ -886,22 +917,29 @@ __global__ void __launch_bounds__((pmap<D1, D2>::THREADS), 1) fused_policy_step_
       const bool has_next = j + 2 < nt;
       if (has_next && stager)
         load_row_state<NOUT>(L, tile + 2 * gridDim.x, t.row, xn);
-      wait_mma();  // layer 1
-      STAMP();
-      epi2_fwd<D1, true>(tm + P2_ACC0, t, fl + PM::F_B1, wsm + PM::H1_HI, wsm + PM::H1_LO, h0, h1d1);
-      ready_arrive(wg, rp, RT);
-      if (!first) {  // the previous tile's dW1 GEMM (XD, dH2 in the H2 slot) ran behind this epilogue
-        umma::mbar_wait(bar_dw1, phase_dw1);
-        phase_dw1 ^= 1;
+      // The two forward epilogues (and, below, the two backward ones) are ONE copy of code run twice with
+      // affine arguments: the epilogue threads' loop body was 36 KB of straight-line SASS, which the SM's
+      // instruction cache does not hold -- epilogue phases ran 20 - 30 % longer on the SMs far from the L2
+      // (the only SM-position-dependent cost of this kernel: 2 650 .. 3 000 ns per tile across the chip).
+      static_assert(D1 == D2 && P2_ACC1 == P2_ACC0 + 64 && PM::H2_HI == PM::H1_HI + 2 * PANEL && PM::H2_LO == PM::H1_LO + 2 * PANEL &&
+                    PM::F_B2 == PM::F_B1 + D1, "the forward / backward epilogue loops assume equal widths and affine operand slots");
+#pragma unroll 1
+      for (int ph = 0; ph < 2; ++ph) {
+        wait_mma();  // layer 1, layer 2
+        STAMP();
+        epi2_fwd<D1, true>(tm + P2_ACC0 + 64 * ph, t, fl + PM::F_B1 + D1 * ph, wsm + PM::H1_HI + 2 * PANEL * ph,
+                           wsm + PM::H1_LO + 2 * PANEL * ph, h0, h1d1);
+        ready_arrive(wg, rp, RT);
+        if (ph == 0) {
+          if (!first) {  // the previous tile's dW1 GEMM (XD, dH2 in the H2 slot) ran behind this epilogue
+            umma::mbar_wait(bar_dw1, phase_dw1);
+            phase_dw1 ^= 1;
+          }
+          if (stager)
+            encode_row<NOUT>(wsm + PM::XD, t.row, xr, L.inv_w, L.inv_h);
+        }
+        STAMP();
       }
-      if (stager)
-        encode_row<NOUT>(wsm + PM::XD, t.row, xr, L.inv_w, L.inv_h);
-      STAMP();
-      wait_mma();  // layer 2
-      STAMP();
-      epi2_fwd<D2, true>(tm + P2_ACC1, t, fl + PM::F_B2, wsm + PM::H2_HI, wsm + PM::H2_LO, h0, h1d2);
-      ready_arrive(wg, rp, RT);
-      STAMP();
       wait_mma();  // layer 3
       STAMP();
       // ---- head epilogue: softmax, loss gradient, softmax backward -> dY = [hi | lo] in the XD panel
@@ -969,19 +1007,22 @@ __global__ void __launch_bounds__((pmap<D1, D2>::THREADS), 1) fused_policy_step_
       }
       ready_arrive(wg, rp, RT);
       STAMP();
-      wait_mma();  // dW3, dH2
-      STAMP();
-      epi2_bwd<D2, true>(tm + P2_ACC0, t, wsm + PM::H2_HI, wsm + PM::H2_HI, wsm + PM::H2_LO, h0, h1d2);
-      ready_arrive(wg, rp, RT);
-      STAMP();
-      wait_mma();  // dH1
-      // the shared dH1 slot: free once the previous tile of this CTA (the other pipeline's) has
-      // finished its dW1 GEMM (completion j - 1 of bars[2])
-      if (j > 0)
-        umma::mbar_wait(bars + 2, (uint32_t)(j - 1) & 1u);
-      STAMP();
-      epi2_bwd<D1>(tm + P2_ACC1, t, wsm + PM::H1_HI, smem + PM::DH1_HI, smem + PM::DH1_LO, h0, h1d1);
-      STAMP();
+#pragma unroll 1
+      for (int ph = 0; ph < 2; ++ph) {
+        wait_mma();  // dW3 + dH2; dH1
+        // the shared dH1 slot: free once the previous tile of this CTA (the other pipeline's) has
+        // finished its dW1 GEMM (completion j - 1 of bars[2])
+        if (ph == 1 && j > 0)
+          umma::mbar_wait(bars + 2, (uint32_t)(j - 1) & 1u);
+        STAMP();
+        // dH2 (mask from H2's hi panel) overwrites H2; dH1 (mask from H1) goes to the shared slot. Both leave
+        // their packed copy in tensor memory (the A operand of the dH1 GEMM; dH1's copy is never read)
+        uint8_t *dst = ph ? smem + PM::DH1_HI : wsm + PM::H2_HI;
+        epi2_bwd<D1, true>(tm + P2_ACC0 + 64 * ph, t, wsm + PM::H2_HI - 2 * PANEL * ph, dst, dst + PANEL, h0, h1d1);
+        if (ph == 0)
+          ready_arrive(wg, rp, RT);
+        STAMP();
+      }
       umma::mbar_wait(bar_dw2, phase_dw2);  // H1 is free (the dW2 GEMM ran behind the dH1 epilogue)
       phase_dw2 ^= 1;
       STAMP();
@@ -1001,21 +1042,31 @@ __global__ void __launch_bounds__((pmap<D1, D2>::THREADS), 1) fused_policy_step_
 #undef STAMP
   if (clk)
     clk[106] = clock64();
+  if (gclk)
+    gclk[1] = global_ns();
 
-  // ---- drain: partial gradient of this CTA (warpgroup 0's sums + warpgroup 1's) -> global
+  // ---- drain: partial gradient of this CTA (warpgroup 0's sums + warpgroup 1's) -> global.
+  // The TMEM accumulators are read row-wise (lane = a weight row), so direct stores would scatter 4-byte
+  // words over 16 .. 32 cache lines per instruction (measured: 9 300 cycles for 27 KB). The values are
+  // staged in shared memory instead (pipeline 1's dead panels, logical parameter order, one pad word per
+  // 32: conflict-free for row strides 32 and 64) and leave as fully coalesced stores.
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
-  float *part = a.partials + (size_t)blockIdx.x * net.n_params;
+  float *part = a.partials + (size_t)blockIdx.x * partial_stride(net.n_params);
+  float *sg = reinterpret_cast<float *>(smem + PM::WG0 + PM::WG_BYTES);
+  static_assert(PM::WG_BYTES >= 8448 * 4, "staging area of the partial gradient");
+  auto put = [&](int i, float v) { sg[i + (i >> 5)] = v; };
   const bool two = nt > 1;  // warpgroup 1 had at least one tile
   if (nt == 0) {
     for (int q = threadIdx.x; q < net.n_params; q += blockDim.x)
       part[q] = 0.f;
   } else {
-    if (net.shared)  // the other heads' slots of the flat gradient
+    if (net.shared) {  // the other heads' slots of the flat gradient
       for (int q = threadIdx.x; q < net.n_params; q += blockDim.x)
         if (!net_owns(net, q))
-          part[q] = 0.f;
+          put(q, 0.f);
+    }
     // dW2[n][k]: DA (M = 64) row n = TMEM lane 32 (n / 16) + n % 16, col k
     const bool drainer = threadIdx.x < 256;  // 256 threads read the TMEM accumulators (t.wg = 0, 1)
     if (drainer) {
@@ -1032,7 +1083,7 @@ __global__ void __launch_bounds__((pmap<D1, D2>::THREADS), 1) fused_policy_step_
       if (nrow >= 0 && nrow < D2)
 #pragma unroll
         for (int q = 0; q < DC; ++q)
-          part[net.o_w2 + nrow * D1 + t.wg * DC + q] = v[q];
+          put(net.o_w2 + nrow * D1 + t.wg * DC + q, v[q]);
     }
     // dW1[n][k] + db1[n]: DB row n, cols 0..D0-1 and D0; db2[n]: DB row 64 + n, col D0
     if (drainer) {
@@ -1050,11 +1101,11 @@ __global__ void __launch_bounds__((pmap<D1, D2>::THREADS), 1) fused_policy_step_
         int col = t.wg * DC + q;
         if (t.row < D1) {
           if (col < D0)
-            part[net.o_w1 + t.row * D0 + col] = v[q];
+            put(net.o_w1 + t.row * D0 + col, v[q]);
           else if (col == D0)
-            part[net.o_b1 + t.row] = v[q];
+            put(net.o_b1 + t.row, v[q]);
         } else if (t.row >= 64 && t.row - 64 < D2 && col == D0) {
-          part[net.o_b2 + t.row - 64] = v[q];
+          put(net.o_b2 + t.row - 64, v[q]);
         }
       }
     }
@@ -1072,7 +1123,7 @@ __global__ void __launch_bounds__((pmap<D1, D2>::THREADS), 1) fused_policy_step_
       if (krow >= 0 && krow < D2)
 #pragma unroll
         for (int q = 0; q < NOUT; ++q)
-          part[net.o_w3 + q * D2 + krow] = v[q] + v[8 + q];
+          put(net.o_w3 + q * D2 + krow, v[q] + v[8 + q]);
     }
     // db3: fixed-order tree inside each warp, then the epilogue warps in order (scratch = pipeline 0's H1)
     float *red = reinterpret_cast<float *>(smem + PM::WG0 + PM::H1_HI);
@@ -1091,8 +1142,11 @@ __global__ void __launch_bounds__((pmap<D1, D2>::THREADS), 1) fused_policy_step_
 #pragma unroll
       for (int w = 0; w < 8 * NH; ++w)
         s += red[w * 8 + threadIdx.x];
-      part[net.o_b3 + threadIdx.x] = s;
+      put(net.o_b3 + threadIdx.x, s);
     }
+    __syncthreads();
+    for (int q = threadIdx.x; q < net.n_params; q += blockDim.x)
+      part[q] = sg[q + (q >> 5)];
   }
   umma::fence_before_sync();
   __syncthreads();
@@ -1102,6 +1156,8 @@ __global__ void __launch_bounds__((pmap<D1, D2>::THREADS), 1) fused_policy_step_
   gradient_tail(a.partials, net, a.tail, reinterpret_cast<float *>(smem + PM::WG0 + PM::H1_HI), clk ? clk + 108 : nullptr);
   if (clk)
     clk[107] = clock64();
+  if (gclk)
+    gclk[2] = global_ns();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1257,6 +1313,10 @@ __global__ void __launch_bounds__((cmap<D1, D2, MODE>::THREADS), 1) fused_critic
   const int wg = issuer ? t.warp - 4 * NH * NP : t.warp / (4 * NH);  // pipeline index
   const int half = NH == 2 ? (t.warp >> 2) & 1 : 0;                   // which 32-column chunk (NH = 2)
   const uint32_t sbase = umma::smem_u32(smem);
+  // every CTA: wall clock at entry / end of the tile loop / end of the kernel, and its SM (load balance)
+  long long *gclk = (MODE == CRITIC_STEP && a.clk && threadIdx.x == 96 && blockIdx.x < 160) ? a.clk + 112 + 4 * blockIdx.x : nullptr;
+  if (gclk)
+    gclk[0] = global_ns(), gclk[3] = sm_id();
 
   umma::pdl_launch_dependents();
   if (t.warp == 0)
@@ -1674,12 +1734,19 @@ __global__ void __launch_bounds__((cmap<D1, D2, MODE>::THREADS), 1) fused_critic
     }
   }
 
+  if (gclk)
+    gclk[1] = global_ns();
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
   if (MODE == CRITIC_STEP) {
-    // ---- drain: partial gradient of this CTA (pipeline 0's sums + pipeline 1's) -> global
-    float *part = a.partials + (size_t)blockIdx.x * net.n_params;
+    // ---- drain: partial gradient of this CTA (pipeline 0's sums + pipeline 1's) -> global, staged in
+    //      shared memory (pipeline 1's dead panels) so that it leaves as coalesced stores (see the policy step)
+    float *part = a.partials + (size_t)blockIdx.x * partial_stride(net.n_params);
+    float *sg = reinterpret_cast<float *>(smem + CM::WG0 + CM::WG_BYTES);
+    static_assert(MODE != CRITIC_STEP || CM::WG_BYTES >= 8448 * 4, "staging area of the partial gradient");
+    static_assert(MODE != CRITIC_STEP || 257 * (D2 + 1) * 4 + 4 * (D2 + 1) * 4 <= CM::WG_BYTES, "dW3 scratch vs staging area");
+    auto put = [&](int i, float v) { sg[i + (i >> 5)] = v; };
     const bool two = nt > 1;
     if (nt == 0) {
       for (int q = threadIdx.x; q < net.n_params; q += blockDim.x)
@@ -1688,7 +1755,7 @@ __global__ void __launch_bounds__((cmap<D1, D2, MODE>::THREADS), 1) fused_critic
       if (net.shared)  // the other heads' slots of the flat gradient
         for (int q = threadIdx.x; q < net.n_params; q += blockDim.x)
           if (!net_owns(net, q))
-            part[q] = 0.f;
+            put(q, 0.f);
       const bool drainer = threadIdx.x < 256;  // 256 threads read the TMEM accumulators (t.wg = 0, 1)
       if (drainer) {  // dW2[n][k]: DA (M = 64) row n = TMEM lane 32 (n / 16) + n % 16, col k
         constexpr int DC = D1 / 2;
@@ -1704,7 +1771,7 @@ __global__ void __launch_bounds__((cmap<D1, D2, MODE>::THREADS), 1) fused_critic
         if (nrow >= 0 && nrow < D2)
 #pragma unroll
           for (int q = 0; q < DC; ++q)
-            part[net.o_w2 + nrow * D1 + t.wg * DC + q] = v[q];
+            put(net.o_w2 + nrow * D1 + t.wg * DC + q, v[q]);
       }
       if (drainer) {  // dW1[n][k] + db1[n]: DB row n, cols 0..D0-1 and D0; db2[n]: DB row 64 + n, col D0
         constexpr int DC = (D0 + 16) / 2;
@@ -1721,11 +1788,11 @@ __global__ void __launch_bounds__((cmap<D1, D2, MODE>::THREADS), 1) fused_critic
           int col = t.wg * DC + q;
           if (t.row < D1) {
             if (col < D0)
-              part[net.o_w1 + t.row * D0 + col] = v[q];
+              put(net.o_w1 + t.row * D0 + col, v[q]);
             else if (col == D0)
-              part[net.o_b1 + t.row] = v[q];
+              put(net.o_b1 + t.row, v[q]);
           } else if (t.row >= 64 && t.row - 64 < D2 && col == D0) {
-            part[net.o_b2 + t.row - 64] = v[q];
+            put(net.o_b2 + t.row - 64, v[q]);
           }
         }
       }
@@ -1765,10 +1832,13 @@ __global__ void __launch_bounds__((cmap<D1, D2, MODE>::THREADS), 1) fused_critic
       if (threadIdx.x < W) {
         const float s = (quart[threadIdx.x] + quart[W + threadIdx.x]) + (quart[2 * W + threadIdx.x] + quart[3 * W + threadIdx.x]);
         if (threadIdx.x < D2)
-          part[net.o_w3 + threadIdx.x] = s;
+          put(net.o_w3 + threadIdx.x, s);
         else
-          part[net.o_b3] = s;
+          put(net.o_b3, s);
       }
+      __syncthreads();
+      for (int q = threadIdx.x; q < net.n_params; q += blockDim.x)
+        part[q] = sg[q + (q >> 5)];
     }
   }
   umma::fence_before_sync();
@@ -1777,6 +1847,8 @@ __global__ void __launch_bounds__((cmap<D1, D2, MODE>::THREADS), 1) fused_critic
     umma::tmem_dealloc(tmem, 512);
   if (MODE == CRITIC_STEP)  // cross-CTA reduction (+ exchange) + optimizer update of this CTA's parameter slice
     gradient_tail(a.partials, net, a.tail, reinterpret_cast<float *>(smem + CM::WG0));
+  if (gclk)
+    gclk[2] = global_ns();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -2177,12 +2249,21 @@ __global__ void __launch_bounds__(160 * NP, 1) fused_rollout_kernel(rollout_args
           if (a.item_tape)
             tape_item = a.item_tape[k];
         }
-        wait_mma();  // layer 1
-        epi2_fwd<D1, true, false>(tm, t, b1, nullptr, nullptr);  // H1 only as a TMEM A operand
-        ready_arrive(wg, rp);
-        wait_mma();  // layer 2
-        epi2_fwd<D2, true, false>(tm + 64, t, b2, nullptr, nullptr);
-        ready_arrive(wg, rp);
+        if (D1 == D2) {  // one copy of the epilogue code, run twice (instruction-cache footprint, see the policy step)
+#pragma unroll 1
+          for (int ph = 0; ph < 2; ++ph) {
+            wait_mma();  // layer 1, layer 2
+            epi2_fwd<D1, true, false>(tm + 64 * ph, t, ph ? b2 : b1, nullptr, nullptr);  // activations only as TMEM A operands
+            ready_arrive(wg, rp);
+          }
+        } else {
+          wait_mma();  // layer 1
+          epi2_fwd<D1, true, false>(tm, t, b1, nullptr, nullptr);  // H1 only as a TMEM A operand
+          ready_arrive(wg, rp);
+          wait_mma();  // layer 2
+          epi2_fwd<D2, true, false>(tm + 64, t, b2, nullptr, nullptr);
+          ready_arrive(wg, rp);
+        }
         wait_mma();  // layer 3
         // ---- head: softmax (no max subtraction, nn.h:382-392), action, environment::apply
         float v[16];
@@ -2577,12 +2658,17 @@ int dfrl_fused_try_attach(dfrl_trainer *t) {
     delete f;
     return DFRL_ERR_UNSUPPORTED;
   }
+  // (the learner kernels stage a CTA's partial gradient in 33 KB of shared memory)
+  if ((f->policy_ok && !f->policy_conv && t->policy->n_params > 8192) || (f->value_ok && t->value->n_params > 8192)) {
+    delete f;
+    return DFRL_ERR_UNSUPPORTED;
+  }
   f->ctas = t->ctx->sm_count;
   f->vend_mode = -1;
   int maxp = t->policy->n_params;
   if (t->value && t->value->n_params > maxp)
     maxp = t->value->n_params;
-  bool ok = cudaMalloc(&f->partials, sizeof(float) * (size_t)f->ctas * maxp) == cudaSuccess;
+  bool ok = cudaMalloc(&f->partials, sizeof(float) * (size_t)f->ctas * partial_stride(maxp)) == cudaSuccess;
   if (ok)
     ok = cudaMalloc(&f->gridbar, 2 * sizeof(unsigned)) == cudaSuccess &&
          cudaMemsetAsync(f->gridbar, 0, 2 * sizeof(unsigned), t->ctx->stream) == cudaSuccess;
@@ -2656,12 +2742,12 @@ extern "C" int dfrl_trainer_fused_coverage(dfrl_trainer *t, int *mask) {
 // Phase clocks (SM cycles) of CTA 0 of the fused policy step: 12 stamps per tile, first 8 tiles.
 // The first call arms the instrumentation (returns zeros); later calls return the last launch.
 extern "C" int dfrl_debug_policy_clocks(dfrl_trainer *t, long long *out_host, int n) {
-  DFRL_CHECK(t && out_host && n > 0 && n <= 112, "bad argument");
+  DFRL_CHECK(t && out_host && n > 0 && n <= 752, "bad argument");  // 112 phase stamps of CTA 0 + 4 per CTA (160 CTAs)
   fused_state *f = (fused_state *)t->fused_impl;
   DFRL_CHECK(f, "fused path not attached");
   if (!f->clk) {
-    DFRL_CUDA(cudaMalloc(&f->clk, sizeof(long long) * 112));
-    DFRL_CUDA(cudaMemsetAsync(f->clk, 0, sizeof(long long) * 112, t->ctx->stream));
+    DFRL_CUDA(cudaMalloc(&f->clk, sizeof(long long) * 752));
+    DFRL_CUDA(cudaMemsetAsync(f->clk, 0, sizeof(long long) * 752, t->ctx->stream));
   }
   DFRL_CUDA(cudaMemcpyAsync(out_host, f->clk, sizeof(long long) * n, cudaMemcpyDeviceToHost, t->ctx->stream));
   DFRL_CUDA(cudaStreamSynchronize(t->ctx->stream));
@@ -2670,12 +2756,12 @@ extern "C" int dfrl_debug_policy_clocks(dfrl_trainer *t, long long *out_host, in
 
 // The same for the critic step (pipeline 0 of CTA 0): 15 stamps per tile, first 7 tiles.
 extern "C" int dfrl_debug_critic_clocks(dfrl_trainer *t, long long *out_host, int n) {
-  DFRL_CHECK(t && out_host && n > 0 && n <= 112, "bad argument");
+  DFRL_CHECK(t && out_host && n > 0 && n <= 752, "bad argument");
   fused_state *f = (fused_state *)t->fused_impl;
   DFRL_CHECK(f, "fused path not attached");
   if (!f->clk_critic) {
-    DFRL_CUDA(cudaMalloc(&f->clk_critic, sizeof(long long) * 112));
-    DFRL_CUDA(cudaMemsetAsync(f->clk_critic, 0, sizeof(long long) * 112, t->ctx->stream));
+    DFRL_CUDA(cudaMalloc(&f->clk_critic, sizeof(long long) * 752));
+    DFRL_CUDA(cudaMemsetAsync(f->clk_critic, 0, sizeof(long long) * 752, t->ctx->stream));
   }
   DFRL_CUDA(cudaMemcpyAsync(out_host, f->clk_critic, sizeof(long long) * n, cudaMemcpyDeviceToHost, t->ctx->stream));
   DFRL_CUDA(cudaStreamSynchronize(t->ctx->stream));
@@ -2726,6 +2812,7 @@ int dfrl_fused_policy_gradient(dfrl_trainer *t, int loss_kind, float *grad_dev, 
   a.head_bwd = f->head_bwd;
   a.partials = f->partials;
   a.clk = f->clk;
+  a.clk_cta = getenv("DFRL_CLK_CTA") ? atoi(getenv("DFRL_CLK_CTA")) : 0;  // (debug: tools/policy_phase_clocks.py)
   int ctas = a.n_tiles < f->ctas ? a.n_tiles : f->ctas;
   DFRL_TRY(make_tail(t, f, f->pnet, ctas, grad_dev, opt, &a.tail));
   if (f->pnet.d1 == 64)

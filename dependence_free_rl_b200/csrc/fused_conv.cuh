@@ -38,7 +38,7 @@
 // Whether the A-from-TMEM GEMMs (layer 2, dH1) also issue the lo.lo product (2^-22 of a term; the stacked
 // weight-gradient GEMMs carry it for free). OFF: measured on B200 (profiles/r02c_conv_lolo_ab.log) the
 // fourth product costs 4.8 % of the policy step (982 -> 935 us at 131 072 envs) and 4 % of the rollout and
-// changes no parity figure (conv policy gradients 0.5e-6 .. 1.4e-5 from the fp64 oracle either way: the
+// changes no parity figure (conv policy gradients 0.5e-6 .. 1.4e-5 from the fp64 yardstick of the tests either way: the
 // error floor is the fp32 accumulation order, not the operand split). DFRL_CONV_LOLO=1 turns it on.
 __constant__ int c_conv_lolo = 0;
 
@@ -550,8 +550,13 @@ __global__ void __launch_bounds__((cvmap<D1, D2>::THREADS), 1) fused_conv_policy
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
-  float *part = a.partials + (size_t)blockIdx.x * net.n_params;
+  float *part = a.partials + (size_t)blockIdx.x * partial_stride(net.n_params);
   float *sc = reinterpret_cast<float *>(smem + CM::H1_HI);
+  // the partial gradient is staged in shared memory (the dead dH1 panels behind the tail's 8 KB of scratch; one pad
+  // word per 32) and leaves as coalesced stores: the accumulators are read row-wise, direct stores scatter
+  float *sg = reinterpret_cast<float *>(smem + CM::DH1_HI + 8192);
+  static_assert(2 * CM::NP1 * PANEL - 8192 >= (D1 == 128 ? 9280u : 2560u) * 4, "staging area of the partial gradient");
+  auto put = [&](int i, float v) { sg[i + (i >> 5)] = v; };
   if (nt == 0) {
     for (int q = threadIdx.x; q < net.n_params; q += blockDim.x)
       part[q] = 0.f;
@@ -576,7 +581,7 @@ __global__ void __launch_bounds__((cvmap<D1, D2>::THREADS), 1) fused_conv_policy
         tmem_load<32>(tm + CM::DA + t.lane_base + half * HC + c0, v);
 #pragma unroll
         for (int q = 0; q < 32; ++q)
-          part[net.o_w2 + t.row * D1 + half * HC + c0 + q] = (v[q] + sc[t.row * (D1 + 1) + half * HC + c0 + q]) * inv_sg;
+          put(net.o_w2 + t.row * D1 + half * HC + c0 + q, (v[q] + sc[t.row * (D1 + 1) + half * HC + c0 + q]) * inv_sg);
       }
     }
     // [dW1 | db1]: DB lane n, columns 0..3 and 4 (D1 = 64: the lo part in lanes 64..127)
@@ -586,8 +591,8 @@ __global__ void __launch_bounds__((cvmap<D1, D2>::THREADS), 1) fused_conv_policy
       if (D1 == 128) {
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          part[net.o_w1 + t.row * 4 + q] = w[q] * inv_sg;
-        part[net.o_b1 + t.row] = w[4] * inv_sg;
+          put(net.o_w1 + t.row * 4 + q, w[q] * inv_sg);
+        put(net.o_b1 + t.row, w[4] * inv_sg);
       } else {
         float *s2 = sc + 64 * (D1 + 1);
         if (t.row >= 64)
@@ -598,8 +603,8 @@ __global__ void __launch_bounds__((cvmap<D1, D2>::THREADS), 1) fused_conv_policy
         if (t.row < 64) {
 #pragma unroll
           for (int q = 0; q < 4; ++q)
-            part[net.o_w1 + t.row * 4 + q] = (w[q] + s2[t.row * 8 + q]) * inv_sg;
-          part[net.o_b1 + t.row] = (w[4] + s2[t.row * 8 + 4]) * inv_sg;
+            put(net.o_w1 + t.row * 4 + q, (w[q] + s2[t.row * 8 + q]) * inv_sg);
+          put(net.o_b1 + t.row, (w[4] + s2[t.row * 8 + 4]) * inv_sg);
         }
       }
     }
@@ -624,14 +629,17 @@ __global__ void __launch_bounds__((cvmap<D1, D2>::THREADS), 1) fused_conv_policy
       float s3 = 0.f;
       for (int r = 0; r < TILE; ++r)
         s3 += r3[r * (D2 + 1) + threadIdx.x];
-      part[net.o_w3 + threadIdx.x] = s3;
-      part[net.o_b2 + threadIdx.x] = (r2[threadIdx.x] + r2[64 + threadIdx.x]) * inv_sg;
+      put(net.o_w3 + threadIdx.x, s3);
+      put(net.o_b2 + threadIdx.x, (r2[threadIdx.x] + r2[64 + threadIdx.x]) * inv_sg);
     } else if (threadIdx.x == D2) {
       float s1 = 0.f;
       for (int r = 0; r < TILE; ++r)
         s1 += r1[r];
-      part[net.o_b3] = s1;
+      put(net.o_b3, s1);
     }
+    __syncthreads();
+    for (int q = threadIdx.x; q < net.n_params; q += blockDim.x)
+      part[q] = sg[q + (q >> 5)];
   }
   umma::fence_before_sync();
   __syncthreads();
