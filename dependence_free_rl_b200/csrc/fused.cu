@@ -141,7 +141,7 @@ __device__ __forceinline__ void issue_gemm(uint32_t tmem_d, uint32_t a_hi, uint3
   constexpr uint32_t a_lbo = A_MN ? PANEL : 16, b_lbo = B_MN ? PANEL : 16;
   const uint32_t ah0 = desc_lo(a_hi, a_lbo), al0 = desc_lo(a_lo, a_lbo);
   const uint32_t bh0 = desc_lo(b_hi, b_lbo), bl0 = desc_lo(b_lo, b_lbo);
-#pragma unroll
+#pragma unroll  // (rolling the 8-step weight-gradient GEMMs: measured 0.6 % slower -- the issue rate matters more than the code size)
   for (int k = 0; k < KSTEPS; ++k) {
     uint64_t ah = desc_lo_hi(ah0 + k * a_step), bh = desc_lo_hi(bh0 + k * b_step);
     umma::mma_bf16(tmem_d, ah, bh, idesc, (k > 0 || accumulate) ? 1u : 0u);
@@ -726,7 +726,9 @@ __device__ __forceinline__ void ready_sync(int wg, uint32_t &parity, int threads
 // warps 8 / 9 = their MMA issuers. tcgen05.mma issue blocks the issuing thread for about the pipe
 // time of the instruction (measured: tools/mma_microbench.py), so a GEMM that is meant to run behind
 // an epilogue must not be issued by a thread that takes part in that epilogue.
-template <int D0, int D1, int D2, int NOUT>
+// PROBE: the phase-clock / load-balance stamps of tools/policy_phase_clocks.py. A separate instantiation:
+// the stamp code costs 1.3 % of the iteration when it is merely compiled in (measured, in-run A/B).
+template <int D0, int D1, int D2, int NOUT, bool PROBE = false>
 __global__ void __launch_bounds__((pmap<D1, D2>::THREADS), 1) fused_policy_step_kernel(policy_step_args a) {
   using PM = pmap<D1, D2>;
   constexpr int NH = PM::NH;          // epilogue threads per row
@@ -783,13 +785,13 @@ __global__ void __launch_bounds__((pmap<D1, D2>::THREADS), 1) fused_policy_step_
   uint64_t *bar = bars + wg, *bar_dw2 = bars + 3 + wg, *bar_dw1 = bars + 5 + wg;
   uint32_t rp = 0;  // parity of the operands-ready barrier
 
-  long long *clk = (a.clk && (int)blockIdx.x == a.clk_cta && threadIdx.x == 96) ? a.clk : nullptr;  // pipeline 0, chunk 0
+  long long *clk = (PROBE && a.clk && (int)blockIdx.x == a.clk_cta && threadIdx.x == 96) ? a.clk : nullptr;  // pipeline 0, chunk 0
   // every CTA: %globaltimer (ns) at entry / end of the tile loop / end of the kernel, and its SM (load balance)
-  long long *gclk = (a.clk && threadIdx.x == 96 && blockIdx.x < 160) ? a.clk + 112 + 4 * blockIdx.x : nullptr;
+  long long *gclk = (PROBE && a.clk && threadIdx.x == 96 && blockIdx.x < 160) ? a.clk + 112 + 4 * blockIdx.x : nullptr;
   if (gclk)
     gclk[0] = global_ns(), gclk[3] = sm_id();
   int clk_n = 0;
-#define STAMP() do { if (clk && clk_n < 104) clk[clk_n++] = clock64(); } while (0)
+#define STAMP() do { if (PROBE && clk && clk_n < 104) clk[clk_n++] = clock64(); } while (0)
   if (clk)
     clk[104] = clk_entry, clk[105] = clock64();
 
@@ -1290,7 +1292,7 @@ __device__ __forceinline__ float epi2_value(uint32_t acc, const tid_t &t, const 
   return s + b3;
 }
 
-template <int D0, int D1, int D2, int MODE, bool EG>
+template <int D0, int D1, int D2, int MODE, bool EG, bool PROBE = false>
 __global__ void __launch_bounds__((cmap<D1, D2, MODE>::THREADS), 1) fused_critic_kernel(critic_args a) {
   using CM = cmap<D1, D2, MODE>;
   constexpr int NP = CM::NP, NH = CM::NH;
@@ -1314,7 +1316,7 @@ __global__ void __launch_bounds__((cmap<D1, D2, MODE>::THREADS), 1) fused_critic
   const int half = NH == 2 ? (t.warp >> 2) & 1 : 0;                   // which 32-column chunk (NH = 2)
   const uint32_t sbase = umma::smem_u32(smem);
   // every CTA: wall clock at entry / end of the tile loop / end of the kernel, and its SM (load balance)
-  long long *gclk = (MODE == CRITIC_STEP && a.clk && threadIdx.x == 96 && blockIdx.x < 160) ? a.clk + 112 + 4 * blockIdx.x : nullptr;
+  long long *gclk = (PROBE && MODE == CRITIC_STEP && a.clk && threadIdx.x == 96 && blockIdx.x < 160) ? a.clk + 112 + 4 * blockIdx.x : nullptr;
   if (gclk)
     gclk[0] = global_ns(), gclk[3] = sm_id();
 
@@ -1460,9 +1462,9 @@ __global__ void __launch_bounds__((cmap<D1, D2, MODE>::THREADS), 1) fused_critic
     const int tt = t.row / L.E, e = t.row % L.E;
     const bool last = tt == L.T - 1;
     bool first = true;
-    long long *clk = (MODE == CRITIC_STEP && a.clk && blockIdx.x == 0 && threadIdx.x == 96) ? a.clk : nullptr;
+    long long *clk = (PROBE && MODE == CRITIC_STEP && a.clk && blockIdx.x == 0 && threadIdx.x == 96) ? a.clk : nullptr;
     int clk_n = 0;
-#define CSTAMP() do { if (clk && clk_n < 112) clk[clk_n++] = clock64(); } while (0)
+#define CSTAMP() do { if (PROBE && clk && clk_n < 112) clk[clk_n++] = clock64(); } while (0)
     // prefetched state of the rows of this warp (warp_state: 5 words per thread); `fast` = the
     // word-wise path applies (E % 4 == 0), otherwise byte loads at the point of use
     const bool fast = L.E % 4 == 0;
@@ -2249,21 +2251,14 @@ __global__ void __launch_bounds__(160 * NP, 1) fused_rollout_kernel(rollout_args
           if (a.item_tape)
             tape_item = a.item_tape[k];
         }
-        if (D1 == D2) {  // one copy of the epilogue code, run twice (instruction-cache footprint, see the policy step)
-#pragma unroll 1
-          for (int ph = 0; ph < 2; ++ph) {
-            wait_mma();  // layer 1, layer 2
-            epi2_fwd<D1, true, false>(tm + 64 * ph, t, ph ? b2 : b1, nullptr, nullptr);  // activations only as TMEM A operands
-            ready_arrive(wg, rp);
-          }
-        } else {
-          wait_mma();  // layer 1
-          epi2_fwd<D1, true, false>(tm, t, b1, nullptr, nullptr);  // H1 only as a TMEM A operand
-          ready_arrive(wg, rp);
-          wait_mma();  // layer 2
-          epi2_fwd<D2, true, false>(tm + 64, t, b2, nullptr, nullptr);
-          ready_arrive(wg, rp);
-        }
+        // (running these two epilogues as one copy of code in a 2-trip loop, as the policy step does, was measured
+        //  0.3 % slower at 131 072 envs: this kernel's loop is 25 KB either way)
+        wait_mma();  // layer 1
+        epi2_fwd<D1, true, false>(tm, t, b1, nullptr, nullptr);  // H1 only as a TMEM A operand
+        ready_arrive(wg, rp);
+        wait_mma();  // layer 2
+        epi2_fwd<D2, true, false>(tm + 64, t, b2, nullptr, nullptr);
+        ready_arrive(wg, rp);
         wait_mma();  // layer 3
         // ---- head: softmax (no max subtraction, nn.h:382-392), action, environment::apply
         float v[16];
@@ -2480,27 +2475,35 @@ int launch_fused(dfrl_ctx *ctx, K kernel, const char *name, int grid, int block,
   return DFRL_OK;
 }
 
-template <int D0, int D1, int D2, int NOUT>
-int launch_policy_step(dfrl_ctx *ctx, const policy_step_args &a, int ctas) {
+template <int D0, int D1, int D2, int NOUT, bool PROBE>
+int launch_policy_step_p(dfrl_ctx *ctx, const policy_step_args &a, int ctas) {
   constexpr int smem = pmap<D1, D2>::TOTAL + 1024;
   static unsigned long long attr = 0;
-  DFRL_TRY(set_smem_once(ctx, fused_policy_step_kernel<D0, D1, D2, NOUT>, smem, &attr));
-  return launch_fused(ctx, fused_policy_step_kernel<D0, D1, D2, NOUT>, "(fused_policy_step_kernel<D0, D1, D2, NOUT>)",
+  DFRL_TRY(set_smem_once(ctx, fused_policy_step_kernel<D0, D1, D2, NOUT, PROBE>, smem, &attr));
+  return launch_fused(ctx, fused_policy_step_kernel<D0, D1, D2, NOUT, PROBE>, "(fused_policy_step_kernel<D0, D1, D2, NOUT>)",
                             ctas, pmap<D1, D2>::THREADS, smem, a);
 }
+template <int D0, int D1, int D2, int NOUT>
+int launch_policy_step(dfrl_ctx *ctx, const policy_step_args &a, int ctas) {
+  if (a.clk && D1 == 64)  // the phase-clock tools asked for stamps (64-wide nets only)
+    return launch_policy_step_p<D0, D1, D2, NOUT, D1 == 64>(ctx, a, ctas);
+  return launch_policy_step_p<D0, D1, D2, NOUT, false>(ctx, a, ctas);
+}
 
-template <int D0, int D1, int D2, bool EG>
+template <int D0, int D1, int D2, bool EG, bool PROBE>
 int launch_critic_step_eg(dfrl_ctx *ctx, const critic_args &a, int ctas) {
   constexpr int smem = cmap<D1, D2, CRITIC_STEP>::TOTAL + 1024;
   static unsigned long long attr = 0;
-  DFRL_TRY(set_smem_once(ctx, fused_critic_kernel<D0, D1, D2, CRITIC_STEP, EG>, smem, &attr));
-  return launch_fused(ctx, fused_critic_kernel<D0, D1, D2, CRITIC_STEP, EG>,
+  DFRL_TRY(set_smem_once(ctx, fused_critic_kernel<D0, D1, D2, CRITIC_STEP, EG, PROBE>, smem, &attr));
+  return launch_fused(ctx, fused_critic_kernel<D0, D1, D2, CRITIC_STEP, EG, PROBE>,
                             "(fused_critic_kernel<D0, D1, D2, CRITIC_STEP, EG>)",
                             ctas, cmap<D1, D2, CRITIC_STEP>::THREADS, smem, a);
 }
 template <int D0, int D1, int D2>
 int launch_critic_step(dfrl_ctx *ctx, const critic_args &a, int ctas) {
-  return a.v_end ? launch_critic_step_eg<D0, D1, D2, true>(ctx, a, ctas) : launch_critic_step_eg<D0, D1, D2, false>(ctx, a, ctas);
+  if (a.clk && a.v_end && D1 == 64 && D2 == 64)  // tools/critic_phase_clocks.py (64-wide nets, compacted end rows)
+    return launch_critic_step_eg<D0, D1, D2, true, D1 == 64 && D2 == 64>(ctx, a, ctas);
+  return a.v_end ? launch_critic_step_eg<D0, D1, D2, true, false>(ctx, a, ctas) : launch_critic_step_eg<D0, D1, D2, false, false>(ctx, a, ctas);
 }
 
 template <int D0, int D1, int D2, bool EG>
