@@ -2539,13 +2539,19 @@ int launch_rollout(dfrl_ctx *ctx, const rollout_args &a, int ctas) {
                       160 * NP, smem, a);
 }
 
-template <int D1, int D2>
-int launch_conv_policy_step(dfrl_ctx *ctx, const conv_step_args &a, int ctas) {
+template <int D1, int D2, bool PROBE>
+int launch_conv_policy_step_p(dfrl_ctx *ctx, const conv_step_args &a, int ctas) {
   constexpr int smem = cvmap<D1, D2>::TOTAL + 1024;
   static unsigned long long attr = 0;
-  DFRL_TRY(set_smem_once(ctx, fused_conv_policy_step_kernel<D1, D2>, smem, &attr));
-  return launch_fused(ctx, fused_conv_policy_step_kernel<D1, D2>, "(fused_conv_policy_step_kernel<D1, D2>)", ctas,
+  DFRL_TRY(set_smem_once(ctx, fused_conv_policy_step_kernel<D1, D2, PROBE>, smem, &attr));
+  return launch_fused(ctx, fused_conv_policy_step_kernel<D1, D2, PROBE>, "(fused_conv_policy_step_kernel<D1, D2>)", ctas,
                       cvmap<D1, D2>::THREADS, smem, a);
+}
+template <int D1, int D2>
+int launch_conv_policy_step(dfrl_ctx *ctx, const conv_step_args &a, int ctas) {
+  if (a.clk && D1 == 128)  // tools/conv_phase_clocks.py asked for stamps (reference PPO net only)
+    return launch_conv_policy_step_p<D1, D2, D1 == 128>(ctx, a, ctas);
+  return launch_conv_policy_step_p<D1, D2, false>(ctx, a, ctas);
 }
 template <int D1, int D2>
 int launch_conv_rollout(dfrl_ctx *ctx, const rollout_args &a, int ctas) {

@@ -253,7 +253,7 @@ __device__ __forceinline__ void conv_encode_row(uint8_t *smem, int row, int slot
       make_uint4(pack2_h((float)bw * inv_w, (float)bh * inv_h), pack2_h((float)iw * inv_w, (float)ih * inv_h), 0x00003C00u, 0u);
 }
 
-template <int D1, int D2>
+template <int D1, int D2, bool PROBE = false>  // PROBE: phase stamps of tools/conv_phase_clocks.py (a separate instantiation)
 __global__ void __launch_bounds__((cvmap<D1, D2>::THREADS), 1) fused_conv_policy_step_kernel(conv_step_args a) {
   using CM = cvmap<D1, D2>;
   constexpr int NB = 8, P = 2 * NB + 2, SPT = TILE / NB;  // bins, state planes, samples per tile
@@ -401,9 +401,9 @@ __global__ void __launch_bounds__((cvmap<D1, D2>::THREADS), 1) fused_conv_policy
         ih = src[(size_t)(2 * NB + 1) * a.stride];
       }
     };
-    long long *clk = (a.clk && blockIdx.x == 0 && threadIdx.x == 96) ? a.clk : nullptr;
+    long long *clk = (PROBE && a.clk && blockIdx.x == 0 && threadIdx.x == 96) ? a.clk : nullptr;
     int clk_n = 0;
-#define STAMP() do { if (clk && clk_n < 98) clk[clk_n++] = clock64(); } while (0)
+#define STAMP() do { if (PROBE && clk && clk_n < 98) clk[clk_n++] = clock64(); } while (0)
     int nbw = 0, nbh = 0, niw = 0, nih = 0;
     if (nt > 0) {
       if (half == 0) {
