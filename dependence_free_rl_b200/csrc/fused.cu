@@ -165,8 +165,10 @@ __device__ __forceinline__ void sync_after_smem_writes() {
 // scratch pointer; contains __syncthreads. It is the FIRST access to global memory of every fused
 // kernel: the programmatic-dependent-launch wait sits here (what precedes it -- tensor-memory
 // allocation, mbarrier set-up -- may run while the previous kernel of the stream drains).
-__device__ __forceinline__ const float *stage_params_bulk(const float *__restrict__ params, int n, uint8_t *scratch,
-                                                          uint64_t *pbar) {
+// In two halves, so that a kernel can put work that does not need the parameters (zero fills, the first
+// tile's state loads) between the issue and the wait: stage_params_issue, __syncthreads, stage_params_wait.
+__device__ __forceinline__ const float *stage_params_issue(const float *__restrict__ params, int n, uint8_t *scratch,
+                                                           uint64_t *pbar) {
   umma::pdl_wait();
   float *dst = reinterpret_cast<float *>(scratch);
   const bool aligned = (reinterpret_cast<uintptr_t>(params) & 15) == 0;
@@ -182,9 +184,19 @@ __device__ __forceinline__ const float *stage_params_bulk(const float *__restric
   }
   for (int i = (int)(bytes / 4) + threadIdx.x; i < n; i += blockDim.x)  // tail (or everything if misaligned)
     dst[i] = params[i];
-  __syncthreads();  // the mbarrier is initialised (and the tail is visible) for every thread
-  if (bytes)
+  return dst;
+}
+// After a __syncthreads that follows stage_params_issue (the mbarrier is initialised, the tail is visible).
+__device__ __forceinline__ void stage_params_wait(const float *__restrict__ params, int n, uint64_t *pbar) {
+  const bool aligned = (reinterpret_cast<uintptr_t>(params) & 15) == 0;
+  if (aligned && (((uint32_t)n * 4u) & ~15u))
     umma::mbar_wait(pbar, 0);
+}
+__device__ __forceinline__ const float *stage_params_bulk(const float *__restrict__ params, int n, uint8_t *scratch,
+                                                          uint64_t *pbar) {
+  const float *dst = stage_params_issue(params, n, scratch, pbar);
+  __syncthreads();  // the mbarrier is initialised (and the tail is visible) for every thread
+  stage_params_wait(params, n, pbar);
   return dst;
 }
 
@@ -757,27 +769,35 @@ __global__ void __launch_bounds__((pmap<D1, D2>::THREADS), 1) fused_policy_step_
       umma::mbar_init(bars + q, 1);
     umma::fence_mbar_init();
   }
-  build_policy_image<D0, D1, D2, NOUT>(
-      stage_params_bulk(a.params, net.n_params, smem + PM::WG0 + PM::H1_HI, bars + 8), net, smem);
-  __syncthreads();  // the scratch (pipeline 0's H1 panels) is free again
+  // The parameter copy is issued first; what does not need it flies behind it: the first tile's state loads
+  // (an exposed L2 round trip otherwise) and the zero fill.
+  const float *Pm = stage_params_issue(a.params, net.n_params, smem + PM::WG0 + PM::H1_HI, bars + 8);
+  // this CTA's tiles: blockIdx.x + j * gridDim.x, j < nt; pipeline wg takes j = wg, wg + 2, ...
+  const int nt = (int)blockIdx.x < a.n_tiles ? (a.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  row_state<NOUT> xr;  // raw state of the pipeline's current tile (epilogue threads)
+  if (!issuer && half == NH - 1 && wg < nt)
+    load_row_state<NOUT>(L, blockIdx.x + wg * gridDim.x, t.row, xr);
   // 64-wide layers: every panel byte an MMA reads is written first (epilogues cover all 128 rows x
   // 64 columns), except columns 32..47 of the XD panels ([1 | 0] for the bias gradients): zeroing
-  // 32 KB instead of 192 KB takes ~0.8 us off every launch
+  // 32 KB instead of 192 KB takes ~0.8 us off every launch (the XD panels are not part of the scratch)
   if (D1 == 64 && D2 == 64) {
     zero_bytes(smem + PM::WG0 + PM::XD, PANEL);
     zero_bytes(smem + PM::WG0 + PM::WG_BYTES + PM::XD, PANEL);
-  } else {
-    zero_bytes(smem + PM::DH1_HI, PM::BARS - PM::DH1_HI);
   }
-  __syncthreads();
+  __syncthreads();  // the copy's mbarrier is initialised, the tail of the vector and the zeros are visible
+  stage_params_wait(a.params, net.n_params, bars + 8);
+  build_policy_image<D0, D1, D2, NOUT>(Pm, net, smem);
+  __syncthreads();  // the scratch (pipeline 0's H1 panels) is free again
+  if (!(D1 == 64 && D2 == 64)) {
+    zero_bytes(smem + PM::DH1_HI, PM::BARS - PM::DH1_HI);
+    __syncthreads();
+  }
   // ones column (col D0) of both XD panels: [dH1|dH2]^T . 1 = bias gradients for free
   if (!issuer && half == 0)
     *reinterpret_cast<uint16_t *>(smem + PM::WG0 + wg * PM::WG_BYTES + PM::XD + umma::panel_off(t.row, D0)) = 0x3F80;
   sync_after_smem_writes();
   const uint32_t tmem = *tmem_slot;
 
-  // this CTA's tiles: blockIdx.x + j * gridDim.x, j < nt; pipeline wg takes j = wg, wg + 2, ...
-  const int nt = (int)blockIdx.x < a.n_tiles ? (a.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   uint8_t *wsm = smem + PM::WG0 + wg * PM::WG_BYTES;
   const uint32_t wbase = sbase + PM::WG0 + wg * PM::WG_BYTES;
   const uint32_t tm = tmem + 256u * wg;
@@ -883,15 +903,13 @@ __global__ void __launch_bounds__((pmap<D1, D2>::THREADS), 1) fused_policy_step_
               h1d2 = NH == 2 ? half + 1 : D2 / (D2 < 32 ? D2 : 32);
     const bool header = half == 0, stager = half == NH - 1;
     bool first = true;
-    row_state<NOUT> xr, xn;  // raw state of this tile / of the next tile
+    row_state<NOUT> xn;  // raw state of the next tile (xr: this tile's, loaded behind the parameter copy)
     // The observations of a tile are encoded twice: into the (dead) H1_LO panel for the layer-1
     // GEMM, so that the tile can start while the previous tile's dW1 GEMM still reads its XD panel,
     // and, behind the layer-2 GEMM, into the XD panel for this tile's own dW1 GEMM.
     if (wg < nt) {
-      if (stager) {
-        load_row_state<NOUT>(L, blockIdx.x + wg * gridDim.x, t.row, xr);
+      if (stager)
         encode_row<NOUT>(wsm + PM::H1_LO, t.row, xr, L.inv_w, L.inv_h);
-      }
       ready_arrive(wg, rp, RT);
     }
     for (int j = wg; j < nt; j += 2) {
@@ -1328,9 +1346,15 @@ __global__ void __launch_bounds__((cmap<D1, D2, MODE>::THREADS), 1) fused_critic
       umma::mbar_init(bars + q, 1);
     umma::fence_mbar_init();
   }
+  constexpr bool small_zero = MODE == CRITIC_STEP && D1 == 64 && D2 == 64;  // see fused_policy_step_kernel
   {
-    const float *P = stage_params_bulk(a.params, net.n_params, smem + CM::WG0 + (MODE == CRITIC_STEP ? PANEL : 0),
-                                       bars + 29);
+    const float *P = stage_params_issue(a.params, net.n_params, smem + CM::WG0 + (MODE == CRITIC_STEP ? PANEL : 0), bars + 29);
+    if (small_zero) {  // (the XS panels are not part of the scratch: zeroed behind the parameter copy)
+      zero_bytes(smem + CM::WG0 + CM::XS, PANEL);
+      zero_bytes(smem + CM::WG0 + CM::WG_BYTES + CM::XS, PANEL);
+    }
+    __syncthreads();
+    stage_params_wait(a.params, net.n_params, bars + 29);
     stage_w1_packed<D1>(P + net.o_w1, smem + CM::W1P);
     stage_weight_f16(P + net.o_w2, D2, D1, D2, 1.f, smem + CM::W2_HI, smem + CM::W2_LO);
     for (int i = threadIdx.x; i < D1; i += blockDim.x) fl[CM::F_B1 + i] = P[net.o_b1 + i];
@@ -1340,13 +1364,10 @@ __global__ void __launch_bounds__((cmap<D1, D2, MODE>::THREADS), 1) fused_critic
       fl[CM::F_B3] = P[net.o_b3];
     __syncthreads();  // the scratch (activation panels) is free again
   }
-  if (MODE == CRITIC_STEP && D1 == 64 && D2 == 64) {  // see fused_policy_step_kernel
-    zero_bytes(smem + CM::WG0 + CM::XS, PANEL);
-    zero_bytes(smem + CM::WG0 + CM::WG_BYTES + CM::XS, PANEL);
-  } else {
+  if (!small_zero) {
     zero_bytes(smem + CM::DH1_HI, CM::BARS - CM::DH1_HI);
+    __syncthreads();
   }
-  __syncthreads();
   if (!issuer && MODE == CRITIC_STEP)  // ones column (col D0) of both XS panels: bias gradients for free
     *reinterpret_cast<uint16_t *>(smem + CM::WG0 + wg * CM::WG_BYTES + CM::XS + umma::panel_off(t.row, D0)) = 0x3F80;
   sync_after_smem_writes();
