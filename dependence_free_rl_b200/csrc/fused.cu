@@ -276,6 +276,8 @@ struct critic_args {
   float *adv_out;      // [T][n] (GAE kernel)
   const float *v_end;  // [T][n] V(end state) where a trajectory ends, from fused_vend_kernel; null: the
                        // kernel runs its own end pass over all rows of every tile
+  float *v_end_out;    // GAE kernel, non-null (== v_end): every pipeline first evaluates the end rows of ITS
+                       // OWN tiles, compacted into passes of 128 rows, and writes them here -- no pre-pass launch
   float *partials;
   grad_tail tail;      // critic step only
   long long *clk;      // optional: phase clocks of CTA 0, pipeline 0 (debug; critic step only)
@@ -1409,6 +1411,24 @@ __global__ void __launch_bounds__((cmap<D1, D2, MODE>::THREADS), 1) fused_critic
       umma::commit(bar);
     };
     bool first = true;
+    if (MODE == CRITIC_GAE && eg && a.v_end_out) {  // compacted end-row passes of this pipeline's tiles (see the epilogue side)
+      volatile int *npass_slot = reinterpret_cast<int *>(smem + CM::SCR) + wg * 2 * NH * TILE + 136;
+      int u = 0;
+      for (int j = wg; j < nt; j += NP, u ^= 1) {
+        ready_sync(wg, rp, RT);  // the pass count after this tile's end rows joined the list
+        const int npass = npass_slot[u];
+        for (int ps = 0; ps < npass; ++ps) {
+          ready_sync(wg, rp, RT);  // observations
+          if (umma::elect_one())
+            layer1(wbase + CM::H1_LO, bar);
+          __syncwarp();
+          ready_sync(wg, rp, RT);  // H1 (tensor memory)
+          if (umma::elect_one())
+            layer2();
+          __syncwarp();
+        }
+      }
+    }
     if (wg < nt) {
       ready_sync(wg, rp, RT);  // observations of the first tile (end rows; eg: start rows) staged in the H1_LO panel
       if (umma::elect_one())
@@ -1490,6 +1510,87 @@ __global__ void __launch_bounds__((cmap<D1, D2, MODE>::THREADS), 1) fused_critic
     // word-wise path applies (E % 4 == 0), otherwise byte loads at the point of use
     const bool fast = L.E % 4 == 0;
     const int warp_row0 = t.row - t.lane;
+    if (MODE == CRITIC_GAE && eg && a.v_end_out) {
+      // ---- V(end state) of the rows of this pipeline's tiles that END a trajectory (done, or the rollout's last
+      //      step: about a third of the rows at T = 4), compacted into passes of 128 rows: the rows of tile after
+      //      tile join a list (ballot + prefix sums, deterministic order), a pass runs whenever 128 are waiting
+      //      and once more after the last tile. Replaces the second fused_vend_kernel launch of an iteration:
+      //      its fixed cost (set-up, launch, tail imbalance) was larger than its work.
+      //      list: uint16 (done << 15 | tile ordinal << 7 | row) x 256, then 4 warp totals + 2 pass-count slots, in the
+      //      pipeline's ve / vs scratch (unused until the tile loop)
+      uint16_t *lst = reinterpret_cast<uint16_t *>(ve);
+      int *wtot = reinterpret_cast<int *>(ve) + 128;
+      volatile int *npass_slot = wtot + 8;
+      int cnt = 0, u = 0;
+      for (int j = wg; j < nt; j += NP, u ^= 1) {
+        const int tile = blockIdx.x + j * gridDim.x, i = tile * L.E + e;
+        const bool valid = tt < L.T && i < L.n;
+        const int dn = valid ? (int)(L.rec_done[(size_t)tt * L.n + i] != 0) : 0;
+        const bool ends = valid && (last || dn);
+        const unsigned bal = __ballot_sync(0xffffffffu, ends);
+        if (t.lane == 0)
+          wtot[t.w] = __popc(bal);
+        asm volatile("bar.sync %0, %1;\n" ::"r"(9 + wg), "r"(128) : "memory");
+        int off = cnt + __popc(bal & ((1u << t.lane) - 1u)), total = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (q < t.w)
+            off += wtot[q];
+          total += wtot[q];
+        }
+        if (ends)  // done flag | tile ordinal | row: the pass below needs no dependent load
+          lst[off] = (uint16_t)((dn << 15) | (((j - wg) / NP) << 7) | t.row);
+        cnt += total;
+        asm volatile("bar.sync %0, %1;\n" ::"r"(9 + wg), "r"(128) : "memory");  // list complete; wtot may be reused
+        const bool last_tile = j + NP >= nt;
+        const int npass = cnt / TILE + ((last_tile && cnt % TILE) ? 1 : 0);
+        if (t.row == 0)
+          npass_slot[u] = npass;
+        ready_sync(wg, rp, RT);  // blocking on purpose: the issuer reads the count, these threads must not run ahead of it
+        for (int ps = 0; ps < npass; ++ps) {
+          const int m = cnt < TILE ? cnt : TILE;
+          const bool has = t.row < m;
+          const int entry = has ? (int)lst[t.row] : 0;
+          const int tile2 = blockIdx.x + (wg + ((entry >> 7) & 255) * NP) * gridDim.x, r2 = entry & 127;
+          const int tt2 = r2 / L.E, i2 = tile2 * L.E + r2 % L.E;
+          const size_t k2 = (size_t)tt2 * L.n + i2;
+          const int done2 = entry >> 15;
+          int act2 = 0;
+          if (done2)
+            act2 = L.rec_action[k2];
+          row_state<NB> x;
+          {
+            constexpr int P = 2 * NB + 2;
+            const int8_t *src = done2 ? L.rec_state + (size_t)tt2 * P * L.stride + i2 : L.live_state + i2;
+#pragma unroll
+            for (int q = 0; q < P; ++q) {
+              x.v[q] = 0;
+              if (has)
+                x.v[q] = src[(size_t)q * L.stride];
+            }
+          }
+          fix_end_state<NB>(x, done2, act2);
+          // the rest of the list moves down (every thread has read its entry of this pass)
+          const int rest = cnt - m;
+          const int moved = t.row < rest ? (int)lst[TILE + t.row] : 0;
+          asm volatile("bar.sync %0, %1;\n" ::"r"(9 + wg), "r"(128) : "memory");
+          if (t.row < rest)
+            lst[t.row] = (uint16_t)moved;
+          cnt = rest;
+          encode_row<NB>(wsm + CM::H1_LO, t.row, x, L.inv_w, L.inv_h);
+          ready_arrive(wg, rp, RT);
+          wait_mma();  // layer 1
+          epi2_fwd<D1, true, false>(tm + C2_ACC0, t, b1, nullptr, nullptr, h0, h1d1);  // H1 only as a TMEM A operand
+          ready_arrive(wg, rp, RT);
+          wait_mma();  // layer 2
+          const float v = epi2_value<D2, false>(tm + C2_ACC1, t, b2, w3, b3, nullptr, h0, h1d2);
+          if (has)
+            a.v_end_out[k2] = v;
+        }
+      }
+      __threadfence_block();
+      asm volatile("bar.sync %0, %1;\n" ::"r"(9 + wg), "r"(128) : "memory");  // the pipeline's V(end) are visible to its threads
+    }
     warp_state<NB> ws;  // start state of this tile (chunk 0's threads)
     int done = 0;
     if (wg < nt) {
@@ -2629,6 +2730,7 @@ critic_args make_critic_args(dfrl_trainer *t, fused_state *f) {
   a.partials = f->partials;
   memset(&a.tail, 0, sizeof(a.tail));
   a.v_end = nullptr;
+  a.v_end_out = nullptr;
   a.clk = f->clk_critic;
   return a;
 }
@@ -2907,8 +3009,13 @@ int dfrl_fused_gae(dfrl_trainer *t) {
     return DFRL_ERR_UNSUPPORTED;
   critic_args a = make_critic_args(t, f);
   if (use_vend(t, f)) {
-    DFRL_TRY(fused_vend(t, f));
+    static const bool local = !getenv("DFRL_GAE_LOCAL_END") || atoi(getenv("DFRL_GAE_LOCAL_END")) != 0;
     a.v_end = t->v_end;
+    const int ctas0 = a.n_tiles < f->ctas ? a.n_tiles : f->ctas;
+    if (local && ceil_div(a.n_tiles, ctas0) <= 1000)  // (16-bit list entries: < 256 tiles per pipeline)
+      a.v_end_out = t->v_end;  // the GAE kernel's pipelines evaluate the end rows of their own tiles first
+    else
+      DFRL_TRY(fused_vend(t, f));
   }
   int ctas = a.n_tiles < f->ctas ? a.n_tiles : f->ctas;
 #define CALL(A, B, C) DFRL_TRY((launch_gae<A, B, C>(t->ctx, a, ctas)))
@@ -2957,8 +3064,4 @@ int dfrl_fused_rollout(dfrl_trainer *t, const uint8_t *items_dev, const uint8_t 
     DFRL_TRY((launch_rollout<32, 16, 16, 8>(t->ctx, a, ctas)));
   t->obs_valid = false;
   return DFRL_OK;
-}
-
-int dfrl_fused_eval_argmax(dfrl_ctx *, dfrl_env *, dfrl_mlp *, int, double *, long long *) {
-  return DFRL_ERR_UNSUPPORTED;
 }

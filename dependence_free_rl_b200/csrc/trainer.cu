@@ -886,9 +886,6 @@ extern "C" int dfrl_eval_argmax(dfrl_ctx *ctx, dfrl_env *env, dfrl_mlp *policy, 
   DFRL_CHECK(episodes > 0, "episodes must be positive");
   DFRL_CHECK(policy->input_cols == 4 * env->B && policy->output_cols == env->B,
              "policy shape does not match the env");
-  int fused_rc = dfrl_fused_eval_argmax(ctx, env, policy, episodes, mean_reward, env_steps);
-  if (fused_rc != DFRL_ERR_UNSUPPORTED)
-    return fused_rc;
   const int n = env->n, B = env->B;
   int max_ep = env_max_episode_len(env->cfg);
   DFRL_CHECK(max_ep > 0, "episodes never end with zero-sized items");

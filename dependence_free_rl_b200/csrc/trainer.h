@@ -77,5 +77,3 @@ int dfrl_fused_gae(dfrl_trainer *t);
 // Returns DFRL_ERR_UNSUPPORTED when the fused policy kernel does not cover this trainer.
 // opt != null: the optimizer update runs inside the reduction kernel (caller bumps adam_t).
 int dfrl_fused_policy_gradient(dfrl_trainer *t, int loss_kind, float *grad_dev, const dfrl_opt_spec *opt);
-int dfrl_fused_eval_argmax(dfrl_ctx *ctx, dfrl_env *env, dfrl_mlp *policy, int episodes,
-                           double *mean_reward, long long *env_steps);
