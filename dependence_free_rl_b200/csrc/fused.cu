@@ -2847,13 +2847,14 @@ extern "C" int dfrl_debug_set_fused_ctas(dfrl_trainer *t, int ctas) {
   return DFRL_OK;
 }
 
-// Test hook: forces (1) / forbids (0) the compacted V(end) pre-pass of the critic-step and GAE kernels,
-// -1 restores the choice by batch size.
+// Test hook: forces (1, 2) / forbids (0) the compacted V(end) evaluation of the critic-step and GAE kernels,
+// -1 restores the choice by batch size. 1: the GAE kernel's pipelines evaluate the end rows of their own
+// tiles (the default when compaction is on), 2: fused_vend_kernel runs before the GAE kernel too.
 extern "C" int dfrl_debug_set_vend(dfrl_trainer *t, int mode) {
   DFRL_CHECK(t, "null trainer");
   fused_state *f = (fused_state *)t->fused_impl;
   DFRL_CHECK(f, "fused path not attached");
-  f->vend_mode = mode < 0 ? -1 : (mode ? 1 : 0);
+  f->vend_mode = mode < 0 ? -1 : (mode > 2 ? 1 : mode);
   return DFRL_OK;
 }
 
@@ -3012,7 +3013,7 @@ int dfrl_fused_gae(dfrl_trainer *t) {
     static const bool local = !getenv("DFRL_GAE_LOCAL_END") || atoi(getenv("DFRL_GAE_LOCAL_END")) != 0;
     a.v_end = t->v_end;
     const int ctas0 = a.n_tiles < f->ctas ? a.n_tiles : f->ctas;
-    if (local && ceil_div(a.n_tiles, ctas0) <= 1000)  // (16-bit list entries: < 256 tiles per pipeline)
+    if (local && f->vend_mode != 2 && ceil_div(a.n_tiles, ctas0) <= 1000)  // (16-bit list entries: < 256 tiles per pipeline)
       a.v_end_out = t->v_end;  // the GAE kernel's pipelines evaluate the end rows of their own tiles first
     else
       DFRL_TRY(fused_vend(t, f));

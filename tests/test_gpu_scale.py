@@ -244,6 +244,38 @@ def test_eval_after_graph_replay_uses_current_weights(D, ctx):
     tr.close(); env.close(); policy.close(); value.close()
 
 
+@pytest.mark.parametrize("n,T,cap", [(65536, 4, 0), (3000, 4, 5), (2048, 8, 3), (777, 1, 2)])
+def test_gae_local_end_rows_equal_the_prepass_launch(D, ctx, n, T, cap):
+    """V(end) of the rows that end a trajectory: the GAE kernel's pipelines evaluate the end rows of their OWN
+    tiles in compacted passes (list carried from tile to tile; default for large batches) -- same values, bit for
+    bit, as the separate fused_vend_kernel launch (every row goes through the same row-wise GEMM chain), hence
+    bit-identical advantages. cap: CTA cap = several tiles per pipeline at small sizes."""
+    def run(mode):
+        policy = D.Model(ctx, D.fc_layers(PD, D.SOFTMAX), 32)
+        value = D.Model(ctx, D.fc_layers(VD), 32)
+        policy.init_parameters(5)
+        value.set_parameters((np.random.default_rng(6).standard_normal(value.n_params) * 0.1).astype(np.float32))
+        env = D.Environment(ctx, n, seed=3)
+        tr = D.Trainer(ctx, env, policy, value, algo=D.PPO, work=T, policy_lr=1e-3 / (n * T), value_lr=1e-3 / (n * T))
+        if cap:
+            D._lib.check(D._lib.lib.dfrl_debug_set_fused_ctas(tr.h, cap))
+        D._lib.check(D._lib.lib.dfrl_debug_set_vend(tr.h, mode))
+        out = []
+        for _ in range(2):
+            tr.rollout()
+            tr.learn(D.PHASE_VALUE | D.PHASE_ADVANTAGE)
+            out.append((tr.read(D.F_ADVANTAGE).copy(), tr.read(D.F_REC_DONE).copy()))
+            tr.learn(D.PHASE_POLICY)
+        tr.close(); env.close(); policy.close(); value.close()
+        return out
+    local, launch = run(1), run(2)
+    for it in range(2):
+        assert np.array_equal(local[it][1], launch[it][1])
+        assert local[it][1].any() or T == 1
+        assert np.array_equal(local[it][0], launch[it][0]), f"iteration {it}: advantages differ"
+        assert np.all(np.isfinite(local[it][0])) and np.abs(local[it][0]).max() > 0
+
+
 def test_set_rates_on_a_graph_replaying_learner(D, ctx):
     """optimizer::set_rate (nn.h:592) after the learn phase has been captured as a CUDA graph: the new
     rates take effect at the next learn() (rates are kernel arguments: the graph is re-captured), the
