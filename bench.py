@@ -599,9 +599,9 @@ def run_ours(args):
             row["algorithmic_tflops_whole_step"] = row["value"] * 2296208 / 1e12
             row["frac_of_bf16_peak"] = row["algorithmic_tflops_whole_step"] / peaks["bf16_tflops_sustained"]
             extra[key] = row
-        # The two learners that stay on the layered kernels: KL-PPO (kl_ppo_learner,
-        # policy_gradient.h:310-335: end rows join the policy pass, beta adapts from the mean KL of all
-        # rows between epochs -- one host read per epoch) and REINFORCE with the reference's FC policy
+        # The two learners whose policy steps stay on the layered kernels: KL-PPO (kl_ppo_learner,
+        # policy_gradient.h:310-335: end rows join the policy pass; critic step / GAE fused, beta adapted on the
+        # device between the steps, learn phase replayed as a CUDA graph) and REINFORCE with the reference's FC policy
         # 32-256-128-8 + softmax-CE (pg_training.cc:12-18; whole episodes per iteration: env-steps
         # counted by the device statistics). 4096 envs each; wall clock around synchronous iterations.
         def layered_rate(objs, n_envs, warm, iters):

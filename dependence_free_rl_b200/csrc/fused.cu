@@ -2825,6 +2825,11 @@ bool dfrl_fused_covers_iteration(const dfrl_trainer *t) {
   return f && f->policy_ok && f->value_ok && f->rollout_ok && t->cfg.algo != DFRL_ALGO_KL_PPO;
 }
 
+bool dfrl_fused_covers_critic(const dfrl_trainer *t) {
+  const fused_state *f = (const fused_state *)t->fused_impl;
+  return f && f->value_ok && f->rollout_ok;
+}
+
 void dfrl_fused_detach(dfrl_trainer *t) {
   fused_state *f = (fused_state *)t->fused_impl;
   if (f) {

@@ -135,12 +135,13 @@ __global__ void policy_loss_kernel(int kind, const float *__restrict__ probs,
                                    const uint8_t *__restrict__ rec_action,
                                    const uint8_t *__restrict__ rec_done,
                                    const int *__restrict__ rec_len, const float *__restrict__ adv,
-                                   const float *__restrict__ p_old, float beta, int n, int L, int B,
+                                   const float *__restrict__ p_old, const float *__restrict__ beta_dev, int n, int L, int B,
                                    int with_end_rows, float *__restrict__ out,
                                    double *__restrict__ kl_acc) {
   long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long LN = (long long)L * n;
   long long total = with_end_rows ? 2 * LN : LN;
+  const float beta = beta_dev ? *beta_dev : 0.f;  // kl_ppo_learner::beta_ lives on the device (no host round trip per step)
   double kl = 0.0, cnt = 0.0;
   if (r < total) {
     bool is_end = r >= LN;
@@ -185,6 +186,18 @@ __global__ void policy_loss_kernel(int kind, const float *__restrict__ probs,
   }
 }
 
+// Adaptive beta of kl_regulated_loss (policy_gradient.h:68-83): acc = {sum of D_KL over the rows, row count} of ALL
+// ranks; halved / doubled around d_targ, clamped to [1e-25, 0.1]. One thread.
+__global__ void kl_beta_update_kernel(const double *__restrict__ acc, float *__restrict__ beta, float kl_target) {
+  const float d_average = (float)(acc[0] / acc[1]);
+  float b = *beta;
+  if (fabsf(d_average) < kl_target / 1.5f)
+    b /= 2;
+  else if (fabsf(d_average) > kl_target * 1.5f)
+    b *= 2;
+  *beta = fminf(fmaxf(b, 1e-25f), 0.1f);
+}
+
 // square_loss_grad (nn.h:548-550) for the critic on start rows; rows past rec_len get 0.
 __global__ void value_loss_kernel(const float *__restrict__ v, const float *__restrict__ tgt,
                                   long long rows, float *__restrict__ out) {
@@ -225,6 +238,9 @@ extern "C" void dfrl_trainer_config_default(dfrl_trainer_config *c) {
   c->action_mode = DFRL_ACT_SAMPLE;
   c->fused = 1;
 }
+
+// kl_ppo_learner::beta_ (policy_gradient.h:333) on the device: the float behind the four statistics counters.
+static float *kl_beta_dev(dfrl_trainer *t) { return reinterpret_cast<float *>(t->counters + 4); }
 
 static size_t opt_state_floats(int kind, int n) {
   return kind == DFRL_OPT_SGD ? 0 : kind == DFRL_OPT_MOMENTUM ? (size_t)n : (size_t)2 * n;
@@ -311,6 +327,7 @@ static int trainer_setup(dfrl_trainer *t, dfrl_ctx *ctx, const dfrl_trainer_conf
   DFRL_CUDA(cudaMemsetAsync(t->vstate, 0, sizeof(float) * (vs ? vs : 1), ctx->stream));
   DFRL_CUDA(cudaMalloc(&t->counters, sizeof(unsigned long long) * 8));
   DFRL_CUDA(cudaMemsetAsync(t->counters, 0, sizeof(unsigned long long) * 8, ctx->stream));
+  DFRL_CUDA(cudaMemcpyAsync(kl_beta_dev(t), &cfg->kl_beta0, sizeof(float), cudaMemcpyHostToDevice, ctx->stream));  // (synchronised below)
   DFRL_CUDA(cudaMalloc(&t->acc, sizeof(double) * 4));
   {
     const float ones[2] = {1.f, 1.f};  // nn.h:693
@@ -336,7 +353,7 @@ static int trainer_setup(dfrl_trainer *t, dfrl_ctx *ctx, const dfrl_trainer_conf
   DFRL_CUDA(cudaMalloc(&t->tape_actions, LN));
   DFRL_CUDA(cudaMalloc(&t->tape_u, sizeof(double) * LN));
   DFRL_CUDA(cudaMallocHost(&t->pin, 64));
-  DFRL_CUDA(cudaMallocHost(&t->stats_pin, 4 * 32));
+  DFRL_CUDA(cudaMallocHost(&t->stats_pin, 4 * 48));
   for (int i = 0; i < 4; ++i) {
     cudaEvent_t e;
     DFRL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -354,6 +371,7 @@ static int trainer_setup(dfrl_trainer *t, dfrl_ctx *ctx, const dfrl_trainer_conf
   t->graph_exec = nullptr;
   t->graph_launches = 0;
   t->plain_iterations = 0;
+  t->graph_failed = 0;
   return DFRL_OK;
 }
 
@@ -417,10 +435,11 @@ static int rollout_step(dfrl_trainer *t, int slot, int mode, const uint8_t *forc
   return DFRL_OK;
 }
 
-static int read_counters(dfrl_trainer *t, unsigned long long *h4) {
-  DFRL_CUDA(cudaMemcpyAsync(t->pin, t->counters, 32, cudaMemcpyDeviceToHost, t->ctx->stream));
+// The four counters, and (h5 only) the device-side KL beta in the low half of h[4].
+static int read_counters(dfrl_trainer *t, unsigned long long *h, int words = 4) {
+  DFRL_CUDA(cudaMemcpyAsync(t->pin, t->counters, 8 * words, cudaMemcpyDeviceToHost, t->ctx->stream));
   DFRL_CUDA(cudaStreamSynchronize(t->ctx->stream));
-  memcpy(h4, t->pin, 32);
+  memcpy(h, t->pin, 8 * words);
   return DFRL_OK;
 }
 
@@ -570,7 +589,7 @@ static int learn_layered(dfrl_trainer *t, int phases = DFRL_PHASE_ALL) {
     DFRL_TRY(ensure_obs(t));
     DFRL_TRY(dfrl_mlp_forward_keep(t->policy, obs_start, (int)LN, &probs));
     DFRL_LAUNCH(ctx, policy_loss_kernel, ceil_div(LN, 128), 128, 0, DFRL_LOSS_SOFTMAX_LOG, probs,
-                t->rec_action, t->rec_done, t->rec_len, t->adv, t->rec_probs, 0.f, n, L, B, 0,
+                t->rec_action, t->rec_done, t->rec_len, t->adv, t->rec_probs, (const float *)nullptr, n, L, B, 0,
                 t->dprobs, (double *)nullptr);
     DFRL_TRY(dfrl_mlp_backward(t->policy, t->dprobs, t->pgrad_log));
     DFRL_TRY(apply_opt(t, t->policy, c.policy_opt, t->pgrad_log, t->pstate, c.policy_lr, c.policy_wd, &t->p_adam_t));
@@ -648,24 +667,16 @@ static int learn_layered(dfrl_trainer *t, int phases = DFRL_PHASE_ALL) {
     if (with_end)
       DFRL_CUDA(cudaMemsetAsync(t->acc, 0, sizeof(double) * 2, ctx->stream));
     DFRL_LAUNCH(ctx, policy_loss_kernel, ceil_div(rows, 128), 128, 0, kind, probs, t->rec_action,
-                t->rec_done, (const int *)nullptr, t->adv, t->rec_probs, t->kl_beta, n, L, B, with_end,
+                t->rec_done, (const int *)nullptr, t->adv, t->rec_probs,
+                with_end ? (const float *)kl_beta_dev(t) : (const float *)nullptr, n, L, B, with_end,
                 t->dprobs, with_end ? t->acc : (double *)nullptr);
     float *grad = t->pgrad_log + (size_t)ep * t->policy->n_params;
     DFRL_TRY(dfrl_mlp_backward(t->policy, t->dprobs, grad));
     if (with_end) {
-      // adaptive beta (policy_gradient.h:68-83): mean KL over ALL rows of all ranks
+      // adaptive beta (policy_gradient.h:68-83): mean KL over ALL rows of all ranks, updated on the device (the
+      // next step's loss kernel reads it there: no host round trip inside the learn phase)
       DFRL_TRY(dfrl_allreduce_sum_f64(ctx, t->acc, 2));
-      double h[2];
-      DFRL_CUDA(cudaMemcpyAsync(t->pin, t->acc, 16, cudaMemcpyDeviceToHost, ctx->stream));
-      DFRL_CUDA(cudaStreamSynchronize(ctx->stream));
-      memcpy(h, t->pin, 16);
-      float d_average = (float)(h[0] / h[1]);
-      if (fabsf(d_average) < c.kl_target / 1.5f)
-        t->kl_beta /= 2;
-      else if (fabsf(d_average) > c.kl_target * 1.5f)
-        t->kl_beta *= 2;
-      t->kl_beta = fmaxf(t->kl_beta, 1e-25f);
-      t->kl_beta = fminf(t->kl_beta, 0.1f);
+      DFRL_LAUNCH(ctx, kl_beta_update_kernel, 1, 1, 0, (const double *)t->acc, kl_beta_dev(t), c.kl_target);
     }
     DFRL_TRY(apply_opt(t, t->policy, c.policy_opt, grad, t->pstate, c.policy_lr, c.policy_wd, &t->p_adam_t));
   }
@@ -681,8 +692,17 @@ static int learn_layered(dfrl_trainer *t, int phases = DFRL_PHASE_ALL) {
 // its step counter t lives on the device and the kernels derive the bias corrections 1 - beta^t from
 // it. Not eligible: NCCL exchanges, per-kernel profiling, learners with host decisions inside the
 // phase (REINFORCE, KL-PPO).
+// KL-PPO: critic step / GAE on the fused kernels, the k policy steps on the layered kernels with beta adapted on
+// the device -- no host decision inside the phase either, so it replays as a graph too (one rank: its
+// exchanges are NCCL calls; SGD / momentum: the layered optimizer kernel takes Adam's step count by value).
+static bool kl_graph_eligible(const dfrl_trainer *t) {
+  return t->cfg.algo == DFRL_ALGO_KL_PPO && dfrl_fused_covers_critic(t) && t->ctx->nranks == 1 &&
+         t->cfg.policy_opt != DFRL_OPT_ADAM && t->cfg.value_opt != DFRL_OPT_ADAM && !t->graph_failed;
+}
 static bool graph_eligible(const dfrl_trainer *t) {
-  return dfrl_fused_covers_iteration(t) && (t->ctx->nranks == 1 || t->ctx->p2p.attached) && !t->ctx->profiling;
+  if (t->ctx->profiling)
+    return false;
+  return (dfrl_fused_covers_iteration(t) && (t->ctx->nranks == 1 || t->ctx->p2p.attached)) || kl_graph_eligible(t);
 }
 
 static int learn_graphed(dfrl_trainer *t) {
@@ -705,6 +725,10 @@ static int learn_graphed(dfrl_trainer *t) {
       if (graph)
         cudaGraphDestroy(graph);
       cudaGetLastError();
+      if (kl_graph_eligible(t)) {  // a layered kernel's workspace grew during the capture: launch by launch from now on
+        t->graph_failed = 1;         // (nothing ran; the SGD / momentum layered path keeps no host-side state)
+        return learn_layered(t);
+      }
       if (rc == DFRL_OK)
         dfrl_set_error("graph capture of the learn phase failed: %s", cudaGetErrorString(e));
       return rc != DFRL_OK ? rc : DFRL_ERR_CUDA;
@@ -842,7 +866,7 @@ extern "C" int dfrl_trainer_stats_begin(dfrl_trainer *t) {
   DFRL_CHECK(t, "null trainer");
   DFRL_CHECK(t->stats_head - t->stats_tail < 4, "4 statistics reads already in flight");
   const unsigned slot = t->stats_head & 3u;
-  DFRL_CUDA(cudaMemcpyAsync((char *)t->stats_pin + 32 * slot, t->counters, 32, cudaMemcpyDeviceToHost, t->ctx->stream));
+  DFRL_CUDA(cudaMemcpyAsync((char *)t->stats_pin + 48 * slot, t->counters, 40, cudaMemcpyDeviceToHost, t->ctx->stream));
   DFRL_CUDA(cudaEventRecord((cudaEvent_t)t->stats_event[slot], t->ctx->stream));
   t->stats_head++;
   return DFRL_OK;
@@ -852,8 +876,8 @@ extern "C" int dfrl_trainer_stats_end(dfrl_trainer *t, dfrl_trainer_stats *out) 
   DFRL_CHECK(t->stats_head != t->stats_tail, "no statistics read in flight");
   const unsigned slot = t->stats_tail & 3u;
   DFRL_CUDA(cudaEventSynchronize((cudaEvent_t)t->stats_event[slot]));
-  unsigned long long h[4];
-  memcpy(h, (char *)t->stats_pin + 32 * slot, 32);
+  unsigned long long h[5];
+  memcpy(h, (char *)t->stats_pin + 48 * slot, 40);
   t->stats_tail++;
   fill_stats(t, h, out);
   return DFRL_OK;
@@ -861,8 +885,8 @@ extern "C" int dfrl_trainer_stats_end(dfrl_trainer *t, dfrl_trainer_stats *out) 
 
 extern "C" int dfrl_trainer_get_stats(dfrl_trainer *t, dfrl_trainer_stats *out) {
   DFRL_CHECK(t && out, "null argument");
-  unsigned long long h[4];
-  DFRL_TRY(read_counters(t, h));
+  unsigned long long h[5];
+  DFRL_TRY(read_counters(t, h, 5));
   fill_stats(t, h, out);
   return DFRL_OK;
 }
@@ -876,6 +900,7 @@ static void fill_stats(dfrl_trainer *t, const unsigned long long *h, dfrl_traine
   out->last_mean_reward = ds > 0 ? (double)dr / (double)ds : 0.0;
   t->last_rollout_steps = (long long)h[0];
   t->last_rollout_reward = (long long)h[2];
+  memcpy(&t->kl_beta, &h[4], sizeof(float));  // host mirror of the device-side beta, as of this read
   out->kl_beta = t->kl_beta;
 }
 

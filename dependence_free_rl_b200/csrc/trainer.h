@@ -50,6 +50,7 @@ struct dfrl_trainer {
   void *graph_exec;        // cudaGraphExec_t
   long long graph_launches;  // kernels per captured iteration
   int plain_iterations;    // iterations run launch by launch so far
+  int graph_failed;        // a capture attempt failed (KL-PPO's layered policy steps): no further attempts
 };
 
 // fused.cu: true when rollout, critic step, GAE and policy steps all run on the fused kernels
@@ -71,6 +72,7 @@ void dfrl_fused_detach(dfrl_trainer *t);
 int dfrl_fused_rollout(dfrl_trainer *t, const uint8_t *items_dev, const uint8_t *actions_dev,
                        const double *u_dev);
 // update_value_model up to the flat gradient (writes t->targets) / calculate_advantage (t->adv).
+bool dfrl_fused_covers_critic(const dfrl_trainer *t);  // rollout, critic step and GAE run on the fused kernels
 int dfrl_fused_critic_gradient(dfrl_trainer *t, float *grad_dev, const dfrl_opt_spec *opt);
 int dfrl_fused_gae(dfrl_trainer *t);
 // One policy gradient over all recorded rows (forward + loss gradient + backward), SUM over rows.

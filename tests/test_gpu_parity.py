@@ -444,6 +444,11 @@ def _run_case(D, ctx, name, fused):
                 flipcheck.flip_close(log[e], c["policy_grads"][pg_i], Dm, what=f"{name} it{it} policy grad {e}")
             pg_i += 1
         close(policy.parameters(), c["policy_params_log"][pg_i - 1], what=f"{name} it{it} policy params")
+        if algo == D.KL_PPO:
+            # kl_ppo_learner::beta_ lives on the device (adapted by a one-thread kernel between the steps, read back
+            # with the statistics): 1 -> doubled -> clamped to 0.1 after the first step (d_targ = 1e-9,
+            # policy_gradient.h:68-83, 333-334); the per-step gradients above already depend on it
+            assert tr.stats()["kl_beta"] == pytest.approx(0.1, rel=1e-6)
     close(policy.parameters(), c["pparams_final"], what="final policy params")
     if value is not None:
         close(value.parameters(), c["vparams_final"], what="final value params")

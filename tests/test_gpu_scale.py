@@ -276,6 +276,46 @@ def test_gae_local_end_rows_equal_the_prepass_launch(D, ctx, n, T, cap):
         assert np.all(np.isfinite(local[it][0])) and np.abs(local[it][0]).max() > 0
 
 
+def test_kl_ppo_learn_phase_replays_as_a_graph(D, ctx):
+    """KL-PPO (kl_ppo_learner, policy_gradient.h:310-335): critic step / GAE on the fused kernels, the k policy
+    steps on the layered kernels, beta adapted on the device between the steps -- no host round trip, so the
+    learn phase is captured as a CUDA graph from the third learn() on. Same parameters and beta, bit for bit,
+    as the launch-by-launch path (learn_phases never replays a graph)."""
+    n, T = 1024, 4
+    def run(graphed):
+        policy = D.Model(ctx, D.fc_layers(PD, D.SOFTMAX), 32)
+        value = D.Model(ctx, D.fc_layers(VD), 32)
+        policy.init_parameters(5)
+        value.init_parameters(6)
+        env = D.Environment(ctx, n, seed=3)
+        lr = 1e-2 / (n * T)
+        tr = D.Trainer(ctx, env, policy, value, algo=D.KL_PPO, work=T, policy_lr=lr, value_lr=lr, policy_wd=1e-5,
+                       kl_target=1e-3, kl_beta0=0.05)
+        out = []
+        launches = []
+        for it in range(7):
+            tr.rollout()
+            l0 = ctx.launches()
+            if graphed:
+                tr.learn()
+            else:
+                tr.learn(D.PHASE_VALUE | D.PHASE_ADVANTAGE)
+                tr.learn(D.PHASE_POLICY)
+            launches.append(ctx.launches() - l0)
+            out.append((policy.parameters().copy(), value.parameters().copy(), tr.stats()["kl_beta"]))
+        cov = tr.fused_coverage()
+        tr.close(); env.close(); policy.close(); value.close()
+        return out, launches, cov
+    (g, gl, cov), (l, ll, _) = run(True), run(False)
+    assert cov & D.FUSED_CRITIC
+    betas = [x[2] for x in g]
+    assert len(set(betas)) > 1, betas          # beta really adapts at this target
+    for it in range(7):
+        assert np.array_equal(g[it][0], l[it][0]) and np.array_equal(g[it][1], l[it][1]), f"iteration {it}"
+        assert g[it][2] == l[it][2], (it, g[it][2], l[it][2])
+    assert gl[-1] == ll[-1]                    # the replayed graph stands for the same kernels
+
+
 def test_set_rates_on_a_graph_replaying_learner(D, ctx):
     """optimizer::set_rate (nn.h:592) after the learn phase has been captured as a CUDA graph: the new
     rates take effect at the next learn() (rates are kernel arguments: the graph is re-captured), the
