@@ -726,7 +726,11 @@ static int learn_graphed(dfrl_trainer *t) {
         cudaGraphDestroy(graph);
       cudaGetLastError();
       if (kl_graph_eligible(t)) {  // a layered kernel's workspace grew during the capture: launch by launch from now on
-        t->graph_failed = 1;         // (nothing ran; the SGD / momentum layered path keeps no host-side state)
+        t->graph_failed = 1;         // (nothing ran; the SGD / momentum layered path keeps no host-side counters:
+        t->obs_valid = false;        //  only the caches that the aborted pass marked as refreshed are reset)
+        dfrl_mlp_params_changed(t->policy);
+        if (t->value)
+          dfrl_mlp_params_changed(t->value);
         return learn_layered(t);
       }
       if (rc == DFRL_OK)
