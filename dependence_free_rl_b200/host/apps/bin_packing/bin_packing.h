@@ -169,4 +169,27 @@ public:
 
 } // namespace bp
 
+// How replay_buffer::sample_td() (xylo/rl.h) rebuilds observations from the device's rollout record: one column
+// of 2B + 2 int8 planes [bin0.w, bin0.h, ..., item.w, item.h]; a finished episode ends in the overflowed state
+// (the chosen bin minus the item, item kept: reference bin_packing.h:54-61), which the device derives instead
+// of storing.
+namespace xylo {
+template <> struct record_codec<bp::observation> {
+  static bp::observation decode(const int8_t *s) {
+    const std::size_t B = bp::config().num_bins;
+    bp::observation o(bp::config().capacity);
+    for (std::size_t b = 0; b < B; ++b)
+      o.bins[b] = {s[2 * b], s[2 * b + 1]};
+    o.item = {s[2 * B], s[2 * B + 1]};
+    return o;
+  }
+  static bp::observation terminal(const bp::observation &start, std::size_t choice) {
+    bp::observation o = start;
+    o.bins[choice].first -= o.item.first;
+    o.bins[choice].second -= o.item.second;
+    return o;
+  }
+};
+} // namespace xylo
+
 #endif

@@ -178,8 +178,49 @@ int main() {
     xylo::policy_gradient_policy<bp::action, bp::observation> policy(pm);
     bp::agent agent(policy, env, rb);
     bp::ppo_learner learner(rb, pm, po, vm, vo, 0.99f);
+    long long episodes_before_last = 0;
     for (int it = 0; it < iters; ++it) {
       agent.play_steps(T);
+      if (it == iters - 1) {
+        // replay_buffer::sample_td (rl.h:222-234): the last rollout read back as trajectories / transitions
+        const dfrl_trainer_stats before = rb.stats();
+        auto experience = rb.sample_td();
+        std::size_t transitions = 0, frozen = 0;
+        double rewards = 0;
+        for (const auto &traj : experience) {
+          EXPECT(traj.size() > 0);
+          frozen += traj.frozen();
+          const bp::observation *prev = nullptr;
+          for (const auto &x : traj) {
+            ++transitions;
+            rewards += x.reward;
+            EXPECT(x.start_state != nullptr);
+            EXPECT(prev == nullptr || x.start_state == prev);  // chained through the previous end state
+            prev = &x.end_state;
+            EXPECT(x.action.distrib.has_value() && x.action.choice < bp::num_bins);
+            float psum = 0;
+            for (std::size_t q = 0; q < bp::num_bins; ++q)
+              psum += (*x.action.distrib)[q];
+            EXPECT(std::fabs(psum - 1.f) < 1e-4f);
+            // the transition itself: the chosen bin shrinks by the item; game over <=> a dimension went negative
+            const bp::observation &a = *x.start_state, &b = x.end_state;
+            const std::size_t c = x.action.choice;
+            const bool over = a.bins[c].first - a.item.first < 0 || a.bins[c].second - a.item.second < 0;
+            EXPECT((x.reward == 0.f) == over);
+            if (over || &x != &traj.back() || true)
+              EXPECT(b.bins[c].first == a.bins[c].first - a.item.first && b.bins[c].second == a.bins[c].second - a.item.second);
+          }
+          EXPECT(traj.frozen() == (traj.back().reward == 0.f));
+        }
+        EXPECT(transitions == n * (std::size_t)T);
+        // rewards of this rollout = the device counters' increment over the rollout
+        EXPECT(std::fabs(xylo::total_rewards<bp::action, bp::observation>(experience) - (float)rewards) < 0.5f);
+        EXPECT((long long)frozen == before.episodes - episodes_before_last);
+        std::printf("sample_td: %zu trajectories (%zu frozen), %zu transitions, reward %.0f\n", experience.size(), frozen,
+                    transitions, rewards);
+      } else {
+        episodes_before_last = rb.stats().episodes;
+      }
       learner.step();
       rb.forget();
     }

@@ -6,12 +6,14 @@
 // `id` (already a parameter of environment::apply / view / reset, rl.h:163-170) selects a slot;
 // ONE agent drives every slot, so agent::step() is one transition of every environment and
 // play_steps(n) is the whole rollout phase of a trainer iteration in one launch. The replay buffer
-// is the struct-of-arrays rollout record on the device (dfrl_trainer); sample_td() has no host-side
-// meaning any more, forget() is implicit (the next rollout overwrites the records and open
+// is the struct-of-arrays rollout record on the device (dfrl_trainer); sample_td() (rl.h:222-234) reads the
+// last rollout's records back into the reference's transition / trajectory / td types (an inspection path:
+// the learners never touch it), forget() is implicit (the next rollout overwrites the records and open
 // trajectories continue from the live state, rl.h:274-291).
 #ifndef XYLO_RL_
 #define XYLO_RL_
 
+#include <list>
 #include <optional>
 #include <random>
 #include <vector>
@@ -189,11 +191,78 @@ struct rollout_store {
   }
 };
 
+// transition / trajectory / td (reference rl.h:111-208) with the reference's members. On the device a
+// transition is one column of the rollout record; these host objects exist only in what sample_td() returns.
+template <typename A, typename S> struct transition {
+  transition(A &&a, float r, S &&next) : action(std::move(a)), reward(r), end_state(std::move(next)) {}
+  const S *start_state = nullptr;  // the trajectory's opening state or the previous transition's end state
+  A action;                        // choice + the policy output it was drawn from (action.distrib)
+  float reward = 0.f;
+  S end_state;
+};
+template <typename A, typename S> struct trajectory {
+  explicit trajectory(S &&o) : opening(std::move(o)) {}
+  const S &last_state() const { return transitions.empty() ? opening : transitions.back().end_state; }
+  std::size_t size() const { return transitions.size(); }
+  void add_transition(A &&a, float r, S &&next) {
+    transitions.emplace_back(std::move(a), r, std::move(next));
+  }
+  void fill_reference() {  // start_state pointers along the chain (std::list nodes do not move)
+    const S *prev = &opening;
+    for (auto &x : transitions)
+      x.start_state = prev, prev = &x.end_state;
+  }
+  void freeze() { frozen = true, fill_reference(); }
+  S opening;
+  std::list<transition<A, S>> transitions;
+  bool frozen = false;  // the episode ended inside the record (game_over)
+};
+// Temporal differences: a read-only window on one trajectory.
+template <typename A, typename S> class td {
+public:
+  using container = std::list<transition<A, S>>;
+  explicit td(const trajectory<A, S> &traj) : traj_(&traj) {}
+  typename container::const_iterator begin() const { return traj_->transitions.begin(); }
+  typename container::const_iterator end() const { return traj_->transitions.end(); }
+  std::size_t size() const { return traj_->transitions.size(); }
+  bool frozen() const { return traj_->frozen; }
+  const transition<A, S> &front() const { return traj_->transitions.front(); }
+  const transition<A, S> &back() const { return traj_->transitions.back(); }
+
+private:
+  const trajectory<A, S> *traj_;
+};
+template <typename A, typename S> float total_rewards(const std::vector<td<A, S>> &experience) {
+  float sum = 0;
+  for (const auto &t : experience)
+    for (const auto &x : t)
+      sum += x.reward;
+  return sum;
+}
+
+// How an application's state type S is rebuilt from one column of the device record (2B + 2 int8 planes) and
+// what state a finished episode ends in (the device derives it from the start state and the action instead of
+// storing it). Applications specialise it next to S (apps/bin_packing/bin_packing.h).
+template <typename S> struct record_codec;  // static S decode(const int8_t *planes); static S terminal(const S &start, std::size_t choice);
+
 template <typename A, typename S> class replay_buffer {
 public:
   // learner::step() then forget() (ppo_training.cc:63-65): the device records are overwritten by
   // the next rollout; open trajectories continue from the live environment state.
-  void forget() {}
+  void forget() { host_.clear(); }
+
+  // replay_buffer::sample_td (rl.h:222-234): every trajectory of the LAST rollout, read back from the device
+  // records: per environment slot the recorded steps split where an episode ended (frozen trajectories);
+  // an open trajectory ends in the slot's live state. O(transitions) host work and one device read per field:
+  // an inspection / custom-learner path, not part of the training loop.
+  std::vector<td<A, S>> sample_td() {
+    materialise();
+    std::vector<td<A, S>> out;
+    out.reserve(host_.size());
+    for (const auto &t : host_)
+      out.emplace_back(t);
+    return out;
+  }
 
   dfrl_trainer_stats stats() {
     dfrl_trainer_stats s{};
@@ -204,7 +273,63 @@ public:
   rollout_store &store() { return store_; }
 
 private:
+  template <typename T> std::vector<T> field(int f) {
+    std::size_t bytes = 0;
+    check(dfrl_trainer_field_size(store_.trainer, f, &bytes));
+    std::vector<T> v(bytes / sizeof(T));
+    check(dfrl_trainer_read(store_.trainer, f, v.data(), bytes));
+    return v;
+  }
+  void materialise() {
+    host_.clear();
+    if (!store_.trainer || !store_.rolled)
+      throw xeno::error("sample_td() before any rollout (evaluation runs keep totals only: total_rewards(rb))");
+    const std::size_t B = A::cardinality(), P = 2 * B + 2;
+    const std::vector<uint8_t> act = field<uint8_t>(DFRL_F_REC_ACTION), done = field<uint8_t>(DFRL_F_REC_DONE);
+    const std::vector<int8_t> state = field<int8_t>(DFRL_F_REC_STATE);
+    const std::vector<float> probs = field<float>(DFRL_F_REC_PROBS);
+    const std::vector<int32_t> len = field<int32_t>(DFRL_F_REC_LEN);
+    const std::size_t n = len.size(), L = act.size() / n, stride = state.size() / (L * P);
+    const bool episodic = store_.algo == DFRL_ALGO_REINFORCE;  // REINFORCE records whole episodes: len[i] steps
+    std::vector<int8_t> col(P);
+    auto start_of = [&](std::size_t t, std::size_t i) {
+      for (std::size_t q = 0; q < P; ++q)
+        col[q] = state[(t * P + q) * stride + i];
+      return record_codec<S>::decode(col.data());
+    };
+    for (std::size_t i = 0; i < n; ++i) {
+      const std::size_t steps = episodic ? (std::size_t)len[i] : L;
+      trajectory<A, S> *open = nullptr;
+      for (std::size_t t = 0; t < steps; ++t) {
+        const std::size_t k = t * n + i;
+        S start = start_of(t, i);
+        if (!open) {
+          host_.emplace_back(S(start));
+          open = &host_.back();
+        }
+        A a;
+        a.choice = act[k];
+        vector d({B});
+        for (std::size_t q = 0; q < B; ++q)
+          d[q] = probs[k * B + q];
+        a.distrib = std::move(d);
+        if (done[k]) {  // the overflowed state of a finished episode: reward 0, trajectory frozen (rl.h:333-346)
+          open->add_transition(std::move(a), 0.f, record_codec<S>::terminal(start, act[k]));
+          open->freeze();
+          open = nullptr;
+        } else if (t + 1 < steps) {
+          open->add_transition(std::move(a), 1.f, start_of(t + 1, i));
+        } else {  // the record ends here: the slot's live state
+          check(dfrl_env_view_one(store_.env, (int)i, col.data()));
+          open->add_transition(std::move(a), 1.f, record_codec<S>::decode(col.data()));
+        }
+      }
+      if (open)
+        open->fill_reference();
+    }
+  }
   rollout_store store_;
+  std::list<trajectory<A, S>> host_;  // what the last sample_td() returned windows on
 };
 
 // total_rewards(rb.sample_td()) of the evaluation loop (ppo_training.cc:75-79).

@@ -37,6 +37,11 @@ def test_host_mirror_builds_and_keeps_reference_signatures():
     # the reference's specialisation hook (policy_gradient.h:187) and the rule check of agent::game_over / get_reward
     assert "virtual void optimize_action(matrix_view" in pg and "const std::vector<A> &" in pg
     assert "void verify_rules()" in rl
+    # trajectory types and replay_buffer::sample_td (reference rl.h:111-234): a read-back of the device records
+    for sig in ["template <typename A, typename S> struct transition {", "template <typename A, typename S> struct trajectory {",
+                "template <typename A, typename S> class td {", "std::vector<td<A, S>> sample_td()",
+                "float total_rewards(const std::vector<td<A, S>> &experience)"]:
+        assert sig in rl, sig
     for sig in ["virtual matrix forward(matrix_view t) = 0;", "virtual matrix backward(matrix_view input, matrix_view loss) = 0;",
                 "virtual vector gradient(matrix_view input, matrix_view backprop) = 0;",
                 "void step(matrix_view input, const loss_grad_func &loss_grad)",
