@@ -133,6 +133,58 @@ private:
   float get_reward(const observation &, const observation &ob) override { return game_over(ob) ? 0 : 1; }
 };
 
+// The reference's rule-based agents (firstfit_agent.cc:10-28, bestfit_agent.cc:10-30, minwaste_agent.cc:10-39,
+// random_agent.cc + rl.h:305-315): there each main defines a policy class with a host react(); here the four
+// rules are built into the environment kernel (dfrl_heuristic_react / dfrl_heuristic_play) and these classes
+// name them. react() is the per-state slow path: the state goes through the SAME device rule on a private
+// one-slot environment.
+class rule_policy : public xylo::policy<action, observation> {
+public:
+  explicit rule_policy(int kind) : kind_(kind) {}
+  rule_policy(const rule_policy &) = delete;
+  ~rule_policy() override {
+    if (one_)
+      dfrl_env_destroy(one_);
+  }
+  int device_rule() const override { return kind_; }
+  action react(const observation &state) const override {
+    const std::size_t B = config().num_bins;
+    if (state.bins.size() != B)
+      throw xeno::error("observation with the wrong number of bins");
+    if (!one_) {
+      dfrl_env_config c;
+      dfrl_env_config_default(&c);
+      c.n_envs = 1;
+      c.n_bins = (int)B;
+      c.cap_w = config().capacity.first, c.cap_h = config().capacity.second;
+      xylo::check(dfrl_env_create(xylo::device::get(), &c, &one_));
+    }
+    std::vector<int8_t> planes(2 * B + 2);  // host layout of dfrl_env_set_state: [2B + 2][N], N = 1
+    for (std::size_t b = 0; b < B; ++b) {
+      planes[2 * b] = (int8_t)state.bins[b].first;
+      planes[2 * b + 1] = (int8_t)state.bins[b].second;
+    }
+    planes[2 * B] = (int8_t)state.item.first;
+    planes[2 * B + 1] = (int8_t)state.item.second;
+    xylo::check(dfrl_env_set_state(one_, planes.data()));
+    xylo::device_buffer act(1);
+    xylo::check(dfrl_heuristic_react(one_, kind_, reinterpret_cast<uint8_t *>(act.get())));
+    uint8_t c = 0;
+    xylo::check(dfrl_memcpy_d2h(xylo::device::get(), &c, act.get(), 1));
+    action a;
+    a.choice = c;
+    return a;
+  }
+
+private:
+  int kind_;
+  mutable dfrl_env *one_ = nullptr;
+};
+struct firstfit_policy : rule_policy { firstfit_policy() : rule_policy(DFRL_HEUR_FIRSTFIT) {} };
+struct bestfit_policy : rule_policy { bestfit_policy() : rule_policy(DFRL_HEUR_BESTFIT) {} };
+struct minwaste_policy : rule_policy { minwaste_policy() : rule_policy(DFRL_HEUR_MINWASTE) {} };
+struct random_policy : rule_policy { random_policy() : rule_policy(DFRL_HEUR_RANDOM) {} };
+
 class pg_learner : public xylo::policy_gradient_learner<action, observation> {
 public:
   pg_learner(xylo::replay_buffer<action, observation> &rb, xylo::model &action_model,

@@ -113,6 +113,9 @@ public:
   // NN-backed policies run inside the rollout kernel: the net, and sample vs argmax.
   virtual model *backing_model() const { return nullptr; }
   virtual bool deterministic() const { return false; }
+  // Rule-based policies (the reference's first-fit / best-fit / min-waste / random agents: user classes with a
+  // host react()) run inside the environment kernel as one of its built-in rules: DFRL_HEUR_*, -1 = none.
+  virtual int device_rule() const { return -1; }
 };
 
 // What the agent (rollout side) and the learner (update side) share through the replay buffer:
@@ -120,6 +123,7 @@ public:
 struct rollout_store {
   dfrl_env *env = nullptr;
   model *policy_model = nullptr;
+  int device_rule = -1;  // DFRL_HEUR_*: a rule-based policy instead of a net
   bool deterministic = false;
   std::size_t obs_cols = 0;
   int algo = -1;  // DFRL_ALGO_*, -1: no learner attached (evaluation only)
@@ -347,10 +351,11 @@ public:
     rollout_store &s = rb.store();
     s.env = env.device_env();
     s.policy_model = p.backing_model();
+    s.device_rule = p.device_rule();
     s.deterministic = p.deterministic();
     s.obs_cols = S::length();
-    if (!s.env || !s.policy_model)
-      throw xeno::error("the agent needs a device environment and a model-backed policy (no CPU path)");
+    if (!s.env || (!s.policy_model && s.device_rule < 0))
+      throw xeno::error("the agent needs a device environment and a model-backed or rule-based policy (no CPU path)");
   }
   virtual ~agent() = default;
 
@@ -366,6 +371,14 @@ public:
   // evaluation loop of the trainer mains / deep_agent.cc.
   void play_one_episode() {
     rollout_store &s = replay_buffer_.store();
+    if (s.algo < 0 && s.device_rule >= 0) {  // firstfit_agent.cc / bestfit_agent.cc / minwaste_agent.cc / random_agent.cc
+      double total = 0;
+      long long steps = 0;
+      check(dfrl_heuristic_play(s.env, s.device_rule, 1, &total, &steps));
+      s.eval_reward += total;
+      s.eval_episodes += (long long)env_.size();
+      return;
+    }
     if (s.algo < 0) {
       double mean = 0;
       long long steps = 0;

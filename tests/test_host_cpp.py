@@ -11,7 +11,7 @@ import refcases
 
 ROOT = refcases.ROOT
 HOST = os.path.join(ROOT, "dependence_free_rl_b200", "host")
-BINS = ["ppo_training", "ac_training", "pg_training", "deep_agent", "host_api_test", "flagstore_test"]
+BINS = ["ppo_training", "ac_training", "pg_training", "deep_agent", "heuristic_agent", "host_api_test", "flagstore_test"]
 
 
 def _build():
@@ -144,6 +144,23 @@ def test_deep_agent_cpp_known_answer(tmp_path):
     assert out.returncode == 0, out.stdout + out.stderr
     mean = float(out.stdout.split()[1])
     assert 26.45 < mean < 26.65, out.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rule,lo,hi", [("minwaste", 26.45, 26.65), ("firstfit", 25.7, 25.95), ("bestfit", 25.7, 25.95),
+                                        ("random", 11.3, 11.9)])
+def test_heuristic_agents_reach_the_reference_levels(rule, lo, hi):
+    """firstfit_agent.cc / bestfit_agent.cc / minwaste_agent.cc / random_agent.cc through the host mirror: rule-based
+    policies behind xylo::policy (device_rule), whole episodes on the device; mean reward per episode at the
+    reference's logged levels (minwaste.log: 26.553 +- 0.009)."""
+    _build()
+    out = subprocess.run([os.path.join(HOST, ".out", "heuristic_agent"), rule, "16384", "4", "2"], capture_output=True, text=True,
+                         timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    rounds = [float(l.split()[3]) for l in out.stdout.splitlines() if l.startswith("round")]
+    assert len(rounds) == 2 and all(lo < r < hi for r in rounds), out.stdout
+    react = [l for l in out.stdout.splitlines() if l.startswith("react(")]
+    assert react and (rule == "random" or react[0].endswith("bin 0")), out.stdout   # an empty board: the first bin
 
 
 @pytest.mark.gpu
