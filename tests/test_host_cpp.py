@@ -11,7 +11,7 @@ import refcases
 
 ROOT = refcases.ROOT
 HOST = os.path.join(ROOT, "dependence_free_rl_b200", "host")
-BINS = ["ppo_training", "ac_training", "pg_training", "deep_agent", "heuristic_agent", "host_api_test", "flagstore_test"]
+BINS = ["ppo_training", "ppo2_training", "ac_training", "pg_training", "deep_agent", "heuristic_agent", "host_api_test", "flagstore_test"]
 
 
 def _build():
@@ -167,6 +167,7 @@ def test_heuristic_agents_reach_the_reference_levels(rule, lo, hi):
 @pytest.mark.parametrize("binary,args", [("ppo_training", ["4096", "6", "5"]), ("ppo_training", ["4096", "6", "5", "c2"]),
                                          ("ppo_training", ["--num_bins=16", "1024", "3", "2", "c2"]),   # run-time bins: layered path
                                          ("ppo_training", ["-b", "5", "--capacity", "16", "512", "3", "0"]),
+                                         ("ppo2_training", ["1024", "5", "4"]),   # KL-PPO: beta on the device
                                          ("ac_training", ["2048", "4"]),
                                          ("pg_training", ["256", "3"])])
 def test_trainer_mains_run(binary, args):
