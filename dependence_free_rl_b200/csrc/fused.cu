@@ -2472,12 +2472,18 @@ __global__ void __launch_bounds__(160 * NP, 1) fused_rollout_kernel(rollout_args
 }
 
 #include "fused_conv.cuh"
+#include "conv_table.cuh"
 
 // ---------------------------------------------------------------------------------------------
 struct fused_state {
   net3 pnet, vnet;
   bool policy_ok, value_ok, rollout_ok;
   bool policy_conv;  // the policy is a conv1d_1 net 4-D1-D2-1 over the 8 bins (fused_conv.cuh)
+  // conv1d_1 policy on its finite input domain (conv_table.cuh): logit table, fixed-point histogram of dY, max |A|
+  bool policy_table;
+  int tbl_Dw, tbl_Dh;
+  float *tbl_logits;
+  unsigned long long *tbl_hist;  // [D] + one word: the bit pattern of max |A| in its low half
   int head_bwd;
   float *partials;  // [ctas][max params]
   unsigned *gridbar;  // [2] grid barrier of the gradient tail (arrivals, generation)
@@ -2685,6 +2691,37 @@ int launch_conv_rollout(dfrl_ctx *ctx, const rollout_args &a, int ctas) {
                       smem, a);
 }
 
+// conv1d_1 policy on its input domain (conv_table.cuh)
+template <int D1, int D2>
+int launch_conv_table_forward(dfrl_ctx *ctx, const float *params, const net3 &net, float inv_w, float inv_h, int Dw, int Dh,
+                              float *logits) {
+  const int D = Dw * Dh * Dw * Dh, grid = ceil_div(D, 8) < 4 * ctx->sm_count ? (int)ceil_div(D, 8) : 4 * ctx->sm_count;
+  DFRL_LAUNCH(ctx, (conv_table_forward_kernel<D1, D2>), grid, 256, 0, params, net, inv_w, inv_h, Dw, Dh, logits);
+  return DFRL_OK;
+}
+template <int D1, int D2>
+int launch_conv_table_step(dfrl_ctx *ctx, const conv_table_args &ta, int ctas) {
+  const conv_step_args &a = ta.s;
+  const int D = ta.Dw * ta.Dh * ta.Dw * ta.Dh;
+  const long long rows = (long long)a.T * a.n;
+  DFRL_CUDA(cudaMemsetAsync(ta.hist, 0, sizeof(unsigned long long) * (D + 1), ctx->stream));
+  DFRL_LAUNCH(ctx, conv_table_absmax_kernel, ctx->sm_count, 256, 0, a.adv, rows, const_cast<unsigned *>(ta.maxbits));
+  DFRL_TRY((launch_conv_table_forward<D1, D2>(ctx, a.params, a.net, a.inv_w, a.inv_h, ta.Dw, ta.Dh, const_cast<float *>(ta.logits))));
+  const int smem = 12 * D;
+  static unsigned long long attr = 0;
+  DFRL_TRY(set_smem_once(ctx, conv_table_head_kernel, smem, &attr));
+  DFRL_LAUNCH(ctx, conv_table_head_kernel, 2 * ctx->sm_count, 256, smem, ta);
+  DFRL_LAUNCH(ctx, (conv_table_backward_kernel<D1, D2>), ctas, 256, 0, ta);
+  return DFRL_OK;
+}
+int launch_conv_table_rollout(dfrl_ctx *ctx, const rollout_args &a, const float *logits, int Dw, int Dh) {
+  const int smem = 4 * Dw * Dh * Dw * Dh;
+  static unsigned long long attr = 0;
+  DFRL_TRY(set_smem_once(ctx, conv_table_rollout_kernel, smem, &attr));
+  DFRL_LAUNCH(ctx, conv_table_rollout_kernel, (int)ceil_div(a.ep.n, 128), 128, smem, a, logits, Dw, Dh);
+  return DFRL_OK;
+}
+
 bool widths_ok(const net3 &n) {
   return n.d0 == 32 && ((n.d1 == 64 && n.d2 == 64) || (n.d1 == 16 && n.d2 == 16));
 }
@@ -2810,6 +2847,20 @@ int dfrl_fused_try_attach(dfrl_trainer *t) {
     delete f;
     return DFRL_ERR_CUDA;
   }
+  if (f->policy_conv) {
+    const char *e = getenv("DFRL_CONV_TABLE");
+    const long long Dw = t->env->cfg.cap_w + 1, Dh = t->env->cfg.cap_h + 1, D = Dw * Dh * Dw * Dh;
+    // (from 8 192 environments x 4 steps on: below that the table's fixed cost per optimizer step -- 6 561 entries
+    //  forward, histogram flush, a backward pass of few CTAs -- exceeds the tensor-core kernels' whole step;
+    //  DFRL_CONV_TABLE=1 / 0 forces / forbids it)
+    const bool big = (long long)t->n * t->L >= 32768;
+    if ((e ? atoi(e) != 0 : big) && D <= 16384) {
+      f->tbl_Dw = (int)Dw, f->tbl_Dh = (int)Dh;
+      if (cudaMalloc(&f->tbl_logits, sizeof(float) * D) == cudaSuccess &&
+          cudaMalloc(&f->tbl_hist, sizeof(unsigned long long) * (D + 1)) == cudaSuccess)
+        f->policy_table = true;
+    }
+  }
   if (f->policy_conv)
     if (const char *e = getenv("DFRL_CONV_LOLO")) {
       const int v = atoi(e) != 0;
@@ -2834,6 +2885,8 @@ void dfrl_fused_detach(dfrl_trainer *t) {
   fused_state *f = (fused_state *)t->fused_impl;
   if (f) {
     cudaFree(f->partials);
+    cudaFree(f->tbl_logits);
+    cudaFree(f->tbl_hist);
     cudaFree(f->clk);
     cudaFree(f->clk_critic);
     cudaFree(f->gridbar);
@@ -2931,7 +2984,18 @@ int dfrl_fused_policy_gradient(dfrl_trainer *t, int loss_kind, float *grad_dev, 
     c.clk = f->clk;
     int ctas = c.n_tiles < f->ctas ? c.n_tiles : f->ctas;
     DFRL_TRY(make_tail(t, f, f->pnet, ctas, grad_dev, opt, &c.tail));
-    if (f->pnet.d1 == 128)
+    if (f->policy_table) {  // the net on its finite input domain: table, histogram of dY, one backward pass
+      conv_table_args ta;
+      ta.s = c;
+      ta.logits = f->tbl_logits;
+      ta.hist = f->tbl_hist;
+      ta.Dw = f->tbl_Dw, ta.Dh = f->tbl_Dh;
+      ta.maxbits = reinterpret_cast<const unsigned *>(f->tbl_hist + (size_t)ta.Dw * ta.Dh * ta.Dw * ta.Dh);
+      if (f->pnet.d1 == 128)
+        DFRL_TRY((launch_conv_table_step<128, 64>(t->ctx, ta, ctas)));
+      else
+        DFRL_TRY((launch_conv_table_step<64, 32>(t->ctx, ta, ctas)));
+    } else if (f->pnet.d1 == 128)
       DFRL_TRY((launch_conv_policy_step<128, 64>(t->ctx, c, ctas)));
     else
       DFRL_TRY((launch_conv_policy_step<64, 32>(t->ctx, c, ctas)));
@@ -3060,7 +3124,13 @@ int dfrl_fused_rollout(dfrl_trainer *t, const uint8_t *items_dev, const uint8_t 
   if (f->policy_conv)
     a.n_tiles = ceil_div(t->n, TILE / 8);
   int ctas = a.n_tiles < f->ctas ? a.n_tiles : f->ctas;
-  if (f->policy_conv && f->pnet.d1 == 128)
+  if (f->policy_conv && f->policy_table) {
+    if (f->pnet.d1 == 128)
+      DFRL_TRY((launch_conv_table_forward<128, 64>(t->ctx, a.params, a.net, a.inv_w, a.inv_h, f->tbl_Dw, f->tbl_Dh, f->tbl_logits)));
+    else
+      DFRL_TRY((launch_conv_table_forward<64, 32>(t->ctx, a.params, a.net, a.inv_w, a.inv_h, f->tbl_Dw, f->tbl_Dh, f->tbl_logits)));
+    DFRL_TRY(launch_conv_table_rollout(t->ctx, a, f->tbl_logits, f->tbl_Dw, f->tbl_Dh));
+  } else if (f->policy_conv && f->pnet.d1 == 128)
     DFRL_TRY((launch_conv_rollout<128, 64>(t->ctx, a, ctas)));
   else if (f->policy_conv)
     DFRL_TRY((launch_conv_rollout<64, 32>(t->ctx, a, ctas)));
