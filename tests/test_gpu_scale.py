@@ -140,10 +140,14 @@ def _conv_policy_reports(S, lr, out, log, obs, actions, adv, p_old_a, kind, dims
     ("ac", 2048, 8, 2, [4, 64, 32, 1], 0),     # ac_training.cc:9-25 nets
     ("ppo", 500, 4, 1, [4, 64, 32, 1], 2),
 ])
-def test_reference_nets_fused_vs_oracle64(D, ctx, orc, algo, n, T, iters, conv, cap):
+@pytest.mark.parametrize("table", [0, 1])
+def test_reference_nets_fused_vs_oracle64(D, ctx, orc, monkeypatch, algo, n, T, iters, conv, cap, table):
     """The reference's OWN default nets (conv1d_1 policy over the 8 bins, He init; critic 32-64-32-1,
-    N(0, 0.01) init) on the fused tcgen05 kernels (fused_conv.cuh + the fused critic kernels) against the
-    double-accumulating oracle: transitions bit-exact, values / advantages / gradients within 1e-4."""
+    N(0, 0.01) init) against the double-accumulating oracle: transitions bit-exact, values / advantages /
+    gradients within 1e-4. table = 0: the fused tcgen05 kernels (fused_conv.cuh + the fused critic kernels);
+    table = 1: the policy on its finite input domain (conv_table.cuh: logit table, fixed-point histogram of dY,
+    one backward pass), the default from 8 192 envs x 4 steps on."""
+    monkeypatch.setenv("DFRL_CONV_TABLE", str(table))
     S = _setup(D, ctx, orc, n, T, algo, seed=11, conv=conv, vd=[32, 64, 32, 1])
     assert S["tr"].fused_covers_iteration()
     if cap:
@@ -314,6 +318,44 @@ def test_kl_ppo_learn_phase_replays_as_a_graph(D, ctx):
         assert np.array_equal(g[it][0], l[it][0]) and np.array_equal(g[it][1], l[it][1]), f"iteration {it}"
         assert g[it][2] == l[it][2], (it, g[it][2], l[it][2])
     assert gl[-1] == ll[-1]                    # the replayed graph stands for the same kernels
+
+
+def test_conv_table_path_is_deterministic_and_agrees_with_the_tensor_core_path(D, ctx, monkeypatch):
+    """conv1d policy, 16 384 envs x 4 (the table path's default range): two runs bit-identical (the histogram of dY
+    accumulates in fixed point: integer atomics commute), free-running rollouts identical to the tensor-core
+    kernels' until probabilities differ in the last bits, gradients of the first policy step within 1e-4 of theirs,
+    and the learn phase replays as a CUDA graph."""
+    n, T = 16384, 4
+    def run(table, iters):
+        monkeypatch.setenv("DFRL_CONV_TABLE", str(table))
+        policy = D.Model(ctx, D.conv_layers([4, 128, 64, 1], D.SOFTMAX), 32)
+        value = D.Model(ctx, D.fc_layers([32, 64, 32, 1]), 32)
+        policy.init_parameters(21)
+        value.init_parameters(22)
+        env = D.Environment(ctx, n, seed=5)
+        tr = D.Trainer(ctx, env, policy, value, algo=D.PPO, work=T, policy_lr=1e-4 * 32 / (n * T), value_lr=1e-5 * 32 / (n * T))
+        assert tr.fused_covers_iteration()
+        out = []
+        for it in range(iters):
+            tr.rollout()
+            acts, probs = tr.read(D.F_REC_ACTION).copy(), tr.read(D.F_REC_PROBS).copy()
+            tr.learn()
+            out.append(dict(acts=acts, probs=probs, g=tr.read(D.F_POLICY_GRAD_LOG).copy(), p=policy.parameters().copy(),
+                            adv=tr.read(D.F_ADVANTAGE).copy()))
+        tr.close(); env.close(); policy.close(); value.close()
+        return out
+    a, b, c = run(1, 5), run(1, 5), run(0, 1)
+    for it in range(5):   # iterations 3.. replay the captured graph
+        for key in ("acts", "probs", "g", "p", "adv"):
+            assert np.array_equal(a[it][key], b[it][key]), (it, key)
+    assert np.all(np.isfinite(a[-1]["p"])) and np.any(a[-1]["p"] != a[0]["p"])
+    # against the tensor-core kernels: same first rollout up to rounding of the probabilities, same gradients to 1e-4
+    assert np.abs(a[0]["probs"] - c[0]["probs"]).max() < 1e-5
+    same = np.mean(a[0]["acts"] == c[0]["acts"])
+    assert same > 0.9999, same
+    if same == 1.0:
+        for e in range(4):
+            close(a[0]["g"][e].astype(np.float64), c[0]["g"][e].astype(np.float64), rtol=1e-4, what=f"policy gradient {e}: table vs tensor cores")
 
 
 def test_set_rates_on_a_graph_replaying_learner(D, ctx):
