@@ -591,13 +591,26 @@ def run_ours(args):
         # 8 bins, FC 32-64-32-1 critic) on the fused tcgen05 kernels (fused_conv.cuh + the fused critic
         # kernels, CUDA-graphed learn phase), at 4096 envs (beside the reference's CPU rate for the same
         # nets below) and at the headline batch size
-        for n_ref, key in ((4096, "reference_nets_4096_envs"), (n, "reference_nets_%d_envs" % n)):
+        # Two implementations of the conv1d policy: the tcgen05 kernels (every (sample, bin) row through the MLP) and,
+        # from 8 192 envs x 4 steps on, the net evaluated on its FINITE input domain (conv_table.cuh: a conv1d_1 net
+        # sees only (bin, item) pairs -- 6 561 distinct rows for 8 x 8 bins -- so the forward pass is a table lookup and
+        # the backward pass one pass over the entries that occur, weighted by a fixed-point histogram of dY: the same
+        # function and gradient, regrouped). Both are reported at the headline size; DFRL_CONV_TABLE picks one.
+        for n_ref, key, table in ((4096, "reference_nets_4096_envs", None), (n, "reference_nets_%d_envs" % n, None),
+                                  (n, "reference_nets_%d_envs_tensor_core_kernels" % n, "0")):
+            if table is not None:
+                os.environ["DFRL_CONV_TABLE"] = table
             row = quick_rate(
                 D, ctx, make_trainer(D, ctx, n_ref, 0, n_ref * T_STEPS, player=D.conv_layers([4, 128, 64, 1], D.SOFTMAX),
                                      vlayer=D.fc_layers([32, 64, 32, 1])), n_ref, T_STEPS, 3, 20)
-            row["algorithmic_flop_per_env_step"] = 2296208
-            row["algorithmic_tflops_whole_step"] = row["value"] * 2296208 / 1e12
-            row["frac_of_bf16_peak"] = row["algorithmic_tflops_whole_step"] / peaks["bf16_tflops_sustained"]
+            os.environ.pop("DFRL_CONV_TABLE", None)
+            on_table = table != "0" and n_ref * T_STEPS >= 32768
+            row["policy_path"] = ("finite-domain table + fixed-point dY histogram (conv_table.cuh), HBM / L2-bound"
+                                  if on_table else "tcgen05 kernels (fused_conv.cuh), FP16 hi / lo pairs")
+            row["algorithmic_flop_per_env_step"] = 2296208   # SURVEY 8d, if every row went through the MLP
+            if not on_table:
+                row["algorithmic_tflops_whole_step"] = row["value"] * 2296208 / 1e12
+                row["frac_of_bf16_peak"] = row["algorithmic_tflops_whole_step"] / peaks["bf16_tflops_sustained"]
             extra[key] = row
         # The two learners whose policy steps stay on the layered kernels: KL-PPO (kl_ppo_learner,
         # policy_gradient.h:310-335: end rows join the policy pass; critic step / GAE fused, beta adapted on the

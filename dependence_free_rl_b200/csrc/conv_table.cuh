@@ -28,7 +28,8 @@ __device__ __forceinline__ int tbl_clamp(int v, int hi) { return v < 0 ? 0 : (v 
 //      entries; a row of W2 is read once (coalesced: consecutive lanes, consecutive columns) for the two.
 template <int D1, int D2>
 __global__ void __launch_bounds__(256) conv_table_forward_kernel(const float *__restrict__ params, net3 net, float inv_w,
-                                                                 float inv_h, int Dw, int Dh, float *__restrict__ logits) {
+                                                                 float inv_h, int Dw, int Dh, float *__restrict__ logits,
+                                                                 const uint8_t *__restrict__ present) {
   constexpr int C = D1 / 32;  // hidden-1 units per lane
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int D = Dw * Dh * Dw * Dh;
@@ -36,6 +37,10 @@ __global__ void __launch_bounds__(256) conv_table_forward_kernel(const float *__
               *w3 = params + net.o_w3;
   const float b3 = params[net.o_b3];
   for (int d0 = 2 * (blockIdx.x * 8 + warp); d0 < D; d0 += 2 * gridDim.x * 8) {
+    // present != null: only the entries that occur in the batch (a policy step knows its rows: <= 90 of the
+    // 6 561 entries are reachable with two item shapes); null: every entry (a rollout's future states)
+    if (present && !present[d0] && !(d0 + 1 < D && present[d0 + 1]))
+      continue;
     float h[2][C];
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
@@ -50,33 +55,45 @@ __global__ void __launch_bounds__(256) conv_table_forward_kernel(const float *__
       }
     }
     float l0 = 0.f, l1 = 0.f;
-    for (int j = 0; j < D2; ++j) {
-      const float *wr = W2 + (size_t)j * D1;
-      float a0 = 0.f, a1 = 0.f;
+    constexpr int JB = 8;  // rows of W2 in flight (a rolled loop paid one L2 round trip per row: 26 us per table)
+    for (int j0 = 0; j0 < D2; j0 += JB) {
+      float w[JB][C], bj[JB], wj[JB];
 #pragma unroll
-      for (int c = 0; c < C; ++c) {
-        const float w = wr[lane + 32 * c];
-        a0 = fmaf(h[0][c], w, a0);
-        a1 = fmaf(h[1][c], w, a1);
+      for (int q = 0; q < JB; ++q) {
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+          w[q][c] = W2[(size_t)(j0 + q) * D1 + lane + 32 * c];
+        bj[q] = b2[j0 + q], wj[q] = w3[j0 + q];
       }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+      for (int q = 0; q < JB; ++q) {
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          a0 = fmaf(h[0][c], w[q][c], a0);
+          a1 = fmaf(h[1][c], w[q][c], a1);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+          a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+        }
+        l0 = fmaf(fmaxf(a0 + bj[q], 0.f), wj[q], l0);
+        l1 = fmaf(fmaxf(a1 + bj[q], 0.f), wj[q], l1);
       }
-      const float bj = b2[j], wj = w3[j];
-      l0 = fmaf(fmaxf(a0 + bj, 0.f), wj, l0);
-      l1 = fmaf(fmaxf(a1 + bj, 0.f), wj, l1);
     }
-    if (lane == 0) {
-      logits[d0] = l0 + b3;
-      if (d0 + 1 < D)
-        logits[d0 + 1] = l1 + b3;
+    if (lane == 0) {  // the table holds exp(logit): what the softmax of every row needs (no max subtraction, nn.h:382-392)
+      if (!present || present[d0])
+        logits[d0] = expf(l0 + b3);
+      if (d0 + 1 < D && (!present || present[d0 + 1]))
+        logits[d0 + 1] = expf(l1 + b3);
     }
   }
 }
 
-// ---- max |A| over the rows (order-independent: unsigned max on the bit patterns of non-negative floats)
+// ---- max |A| over the rows (order-independent: unsigned max on the bit patterns of non-negative floats).
+//      (Marking the domain entries that occur in the batch here, to restrict the table to them, was measured
+//      slower than computing the whole table: 58 us of contended byte flags against 6 us.)
 __global__ void conv_table_absmax_kernel(const float *__restrict__ adv, long long rows, unsigned *__restrict__ maxbits) {
   unsigned m = 0;
   for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < rows; k += (long long)gridDim.x * blockDim.x) {
@@ -185,7 +202,7 @@ __global__ void __launch_bounds__(256) conv_table_head_kernel(conv_table_args ta
 #pragma unroll
       for (int q = 0; q < NB; ++q) {
         d[q] = tbl_index(tbl_clamp(v[2 * q], Dw - 1), tbl_clamp(v[2 * q + 1], Dh - 1), iw, ih, Dw, Dh);
-        p[q] = expf(ls[d[q]]);  // no max subtraction (nn.h:382-392)
+        p[q] = ls[d[q]];  // exp(logit) from the table
         ssum += p[q];
       }
       const float inv_s = 1.f / ssum;
@@ -362,7 +379,7 @@ __global__ void __launch_bounds__(128) conv_table_rollout_kernel(rollout_args a,
       float p[B], s = 0.f;
 #pragma unroll
       for (int q = 0; q < B; ++q) {
-        p[q] = expf(ls[tbl_index(tbl_clamp(st[2 * q], Dw - 1), tbl_clamp(st[2 * q + 1], Dh - 1), ciw, cih, Dw, Dh)]);
+        p[q] = ls[tbl_index(tbl_clamp(st[2 * q], Dw - 1), tbl_clamp(st[2 * q + 1], Dh - 1), ciw, cih, Dw, Dh)];  // exp(logit)
         s += p[q];  // sequential sum in bin order, no max subtraction (nn.h:382-392)
       }
 #pragma unroll

@@ -2694,9 +2694,9 @@ int launch_conv_rollout(dfrl_ctx *ctx, const rollout_args &a, int ctas) {
 // conv1d_1 policy on its input domain (conv_table.cuh)
 template <int D1, int D2>
 int launch_conv_table_forward(dfrl_ctx *ctx, const float *params, const net3 &net, float inv_w, float inv_h, int Dw, int Dh,
-                              float *logits) {
-  const int D = Dw * Dh * Dw * Dh, grid = ceil_div(D, 8) < 4 * ctx->sm_count ? (int)ceil_div(D, 8) : 4 * ctx->sm_count;
-  DFRL_LAUNCH(ctx, (conv_table_forward_kernel<D1, D2>), grid, 256, 0, params, net, inv_w, inv_h, Dw, Dh, logits);
+                              float *logits, const uint8_t *present) {
+  const int D = Dw * Dh * Dw * Dh, grid = ceil_div(D, 16) < 4 * ctx->sm_count ? (int)ceil_div(D, 16) : 4 * ctx->sm_count;
+  DFRL_LAUNCH(ctx, (conv_table_forward_kernel<D1, D2>), grid, 256, 0, params, net, inv_w, inv_h, Dw, Dh, logits, present);
   return DFRL_OK;
 }
 template <int D1, int D2>
@@ -2706,7 +2706,8 @@ int launch_conv_table_step(dfrl_ctx *ctx, const conv_table_args &ta, int ctas) {
   const long long rows = (long long)a.T * a.n;
   DFRL_CUDA(cudaMemsetAsync(ta.hist, 0, sizeof(unsigned long long) * (D + 1), ctx->stream));
   DFRL_LAUNCH(ctx, conv_table_absmax_kernel, ctx->sm_count, 256, 0, a.adv, rows, const_cast<unsigned *>(ta.maxbits));
-  DFRL_TRY((launch_conv_table_forward<D1, D2>(ctx, a.params, a.net, a.inv_w, a.inv_h, ta.Dw, ta.Dh, const_cast<float *>(ta.logits))));
+  DFRL_TRY((launch_conv_table_forward<D1, D2>(ctx, a.params, a.net, a.inv_w, a.inv_h, ta.Dw, ta.Dh, const_cast<float *>(ta.logits),
+                                              nullptr)));
   const int smem = 12 * D;
   static unsigned long long attr = 0;
   DFRL_TRY(set_smem_once(ctx, conv_table_head_kernel, smem, &attr));
@@ -2857,7 +2858,7 @@ int dfrl_fused_try_attach(dfrl_trainer *t) {
     if ((e ? atoi(e) != 0 : big) && D <= 16384) {
       f->tbl_Dw = (int)Dw, f->tbl_Dh = (int)Dh;
       if (cudaMalloc(&f->tbl_logits, sizeof(float) * D) == cudaSuccess &&
-          cudaMalloc(&f->tbl_hist, sizeof(unsigned long long) * (D + 1)) == cudaSuccess)
+          cudaMalloc(&f->tbl_hist, sizeof(unsigned long long) * (D + 1) + (size_t)D) == cudaSuccess)
         f->policy_table = true;
     }
   }
@@ -3126,9 +3127,9 @@ int dfrl_fused_rollout(dfrl_trainer *t, const uint8_t *items_dev, const uint8_t 
   int ctas = a.n_tiles < f->ctas ? a.n_tiles : f->ctas;
   if (f->policy_conv && f->policy_table) {
     if (f->pnet.d1 == 128)
-      DFRL_TRY((launch_conv_table_forward<128, 64>(t->ctx, a.params, a.net, a.inv_w, a.inv_h, f->tbl_Dw, f->tbl_Dh, f->tbl_logits)));
+      DFRL_TRY((launch_conv_table_forward<128, 64>(t->ctx, a.params, a.net, a.inv_w, a.inv_h, f->tbl_Dw, f->tbl_Dh, f->tbl_logits, nullptr)));
     else
-      DFRL_TRY((launch_conv_table_forward<64, 32>(t->ctx, a.params, a.net, a.inv_w, a.inv_h, f->tbl_Dw, f->tbl_Dh, f->tbl_logits)));
+      DFRL_TRY((launch_conv_table_forward<64, 32>(t->ctx, a.params, a.net, a.inv_w, a.inv_h, f->tbl_Dw, f->tbl_Dh, f->tbl_logits, nullptr)));
     DFRL_TRY(launch_conv_table_rollout(t->ctx, a, f->tbl_logits, f->tbl_Dw, f->tbl_Dh));
   } else if (f->policy_conv && f->pnet.d1 == 128)
     DFRL_TRY((launch_conv_rollout<128, 64>(t->ctx, a, ctas)));
