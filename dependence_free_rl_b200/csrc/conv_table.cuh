@@ -24,26 +24,31 @@ __host__ __device__ __forceinline__ int tbl_index(int bw, int bh, int iw, int ih
 }
 __device__ __forceinline__ int tbl_clamp(int v, int hi) { return v < 0 ? 0 : (v > hi ? hi : v); }
 
-// ---- L[d] for every domain entry: one warp per PAIR of entries. Lane l holds H1[l], H1[l + 32], ... of both
-//      entries; a row of W2 is read once (coalesced: consecutive lanes, consecutive columns) for the two.
+// ---- L[d] = exp(logit) for every domain entry: one warp per group of E entries. Lane l holds H1[l], H1[l + 32],
+//      ... of the E entries; a row of W2 is read once (coalesced: consecutive lanes, consecutive columns) for all
+//      of them, JB rows in flight.
 template <int D1, int D2>
 __global__ void __launch_bounds__(256) conv_table_forward_kernel(const float *__restrict__ params, net3 net, float inv_w,
                                                                  float inv_h, int Dw, int Dh, float *__restrict__ logits,
                                                                  const uint8_t *__restrict__ present) {
   constexpr int C = D1 / 32;  // hidden-1 units per lane
+  constexpr int E = 4, JB = 4;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int D = Dw * Dh * Dw * Dh;
   const float *W1 = params + net.o_w1, *b1 = params + net.o_b1, *W2 = params + net.o_w2, *b2 = params + net.o_b2,
               *w3 = params + net.o_w3;
   const float b3 = params[net.o_b3];
-  for (int d0 = 2 * (blockIdx.x * 8 + warp); d0 < D; d0 += 2 * gridDim.x * 8) {
-    // present != null: only the entries that occur in the batch (a policy step knows its rows: <= 90 of the
-    // 6 561 entries are reachable with two item shapes); null: every entry (a rollout's future states)
-    if (present && !present[d0] && !(d0 + 1 < D && present[d0 + 1]))
-      continue;
-    float h[2][C];
+  for (int d0 = E * (blockIdx.x * 8 + warp); d0 < D; d0 += E * gridDim.x * 8) {
+    if (present) {  // only the entries that occur in a batch (unused: marking them costs more than the whole table)
+      bool any = false;
+      for (int e = 0; e < E; ++e)
+        any = any || (d0 + e < D && present[d0 + e]);
+      if (!any)
+        continue;
+    }
+    float h[E][C];
 #pragma unroll
-    for (int e = 0; e < 2; ++e) {
+    for (int e = 0; e < E; ++e) {
       const int d = min(d0 + e, D - 1);
       const int bh = d % Dh, bw = (d / Dh) % Dw, ih = (d / (Dh * Dw)) % Dh, iw = d / (Dh * Dw * Dh);
       const float x0 = (float)bw * inv_w, x1 = (float)bh * inv_h, x2 = (float)iw * inv_w, x3 = (float)ih * inv_h;
@@ -54,8 +59,10 @@ __global__ void __launch_bounds__(256) conv_table_forward_kernel(const float *__
         h[e][c] = fmaxf(fmaf(x3, w.w, fmaf(x2, w.z, fmaf(x1, w.y, fmaf(x0, w.x, b1[j])))), 0.f);
       }
     }
-    float l0 = 0.f, l1 = 0.f;
-    constexpr int JB = 8;  // rows of W2 in flight (a rolled loop paid one L2 round trip per row: 26 us per table)
+    float l[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+      l[e] = 0.f;
     for (int j0 = 0; j0 < D2; j0 += JB) {
       float w[JB][C], bj[JB], wj[JB];
 #pragma unroll
@@ -67,26 +74,29 @@ __global__ void __launch_bounds__(256) conv_table_forward_kernel(const float *__
       }
 #pragma unroll
       for (int q = 0; q < JB; ++q) {
-        float a0 = 0.f, a1 = 0.f;
+        float acc[E];
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-          a0 = fmaf(h[0][c], w[q][c], a0);
-          a1 = fmaf(h[1][c], w[q][c], a1);
+        for (int e = 0; e < E; ++e) {
+          acc[e] = 0.f;
+#pragma unroll
+          for (int c = 0; c < C; ++c)
+            acc[e] = fmaf(h[e][c], w[q][c], acc[e]);
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-          a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-        }
-        l0 = fmaf(fmaxf(a0 + bj[q], 0.f), wj[q], l0);
-        l1 = fmaf(fmaxf(a1 + bj[q], 0.f), wj[q], l1);
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+          for (int e = 0; e < E; ++e)
+            acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], o);
+#pragma unroll
+        for (int e = 0; e < E; ++e)
+          l[e] = fmaf(fmaxf(acc[e] + bj[q], 0.f), wj[q], l[e]);
       }
     }
     if (lane == 0) {  // the table holds exp(logit): what the softmax of every row needs (no max subtraction, nn.h:382-392)
-      if (!present || present[d0])
-        logits[d0] = expf(l0 + b3);
-      if (d0 + 1 < D && (!present || present[d0 + 1]))
-        logits[d0 + 1] = expf(l1 + b3);
+#pragma unroll
+      for (int e = 0; e < E; ++e)
+        if (d0 + e < D && (!present || present[d0 + e]))
+          logits[d0 + e] = expf(l[e] + b3);
     }
   }
 }
