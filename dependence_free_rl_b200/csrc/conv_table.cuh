@@ -35,8 +35,19 @@ __global__ void __launch_bounds__(256) conv_table_forward_kernel(const float *__
   constexpr int E = 4, JB = 4;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int D = Dw * Dh * Dw * Dh;
-  const float *W1 = params + net.o_w1, *b1 = params + net.o_b1, *W2 = params + net.o_w2, *b2 = params + net.o_b2,
-              *w3 = params + net.o_w3;
+  // W2, b2, w3 once per CTA into shared memory (one L2 round trip with every load in flight; read from global
+  // memory row by row inside the loop, the kernel was a chain of L2 latencies: 23 us per table)
+  __shared__ __align__(16) float W2[D2 * D1];
+  __shared__ float b2[D2], w3[D2];
+  {
+    const float4 *src = reinterpret_cast<const float4 *>(params + net.o_w2);
+    for (int q = threadIdx.x; q < D2 * D1 / 4; q += blockDim.x)
+      reinterpret_cast<float4 *>(W2)[q] = src[q];
+    for (int q = threadIdx.x; q < D2; q += blockDim.x)
+      b2[q] = params[net.o_b2 + q], w3[q] = params[net.o_w3 + q];
+  }
+  __syncthreads();
+  const float *W1 = params + net.o_w1, *b1 = params + net.o_b1;
   const float b3 = params[net.o_b3];
   for (int d0 = E * (blockIdx.x * 8 + warp); d0 < D; d0 += E * gridDim.x * 8) {
     if (present) {  // only the entries that occur in a batch (unused: marking them costs more than the whole table)
@@ -289,8 +300,21 @@ __global__ void __launch_bounds__(256, 1) conv_table_backward_kernel(conv_table_
 #pragma unroll
   for (int q = 0; q < JPT; ++q)
     dw2[q] = 0.f;
-  for (int d = blockIdx.x; d < D; d += gridDim.x) {
-    const long long fx = (long long)ta.hist[d];
+  // this CTA's histogram entries, all loads in flight (read one by one in the loop below they were a chain of
+  // ~ 44 L2 round trips: half of the kernel's 33 us)
+  __shared__ long long myh[256];
+  for (int d0 = blockIdx.x; d0 < D; d0 += 256 * gridDim.x) {
+  {
+    const int dd = d0 + tid * (int)gridDim.x;
+    __syncthreads();
+    myh[tid] = dd < D ? (long long)ta.hist[dd] : 0;
+    __syncthreads();
+  }
+  for (int slot = 0; slot < 256; ++slot) {
+    const int d = d0 + slot * (int)gridDim.x;
+    if (d >= D)
+      break;
+    const long long fx = myh[slot];
     if (fx == 0)
       continue;  // (uniform: every thread reads the same entry)
     const float g = (float)((double)fx * (double)inv_S);
@@ -337,6 +361,7 @@ __global__ void __launch_bounds__(256, 1) conv_table_backward_kernel(conv_table_
         dw2[q] = fmaf(G2[jg * JPT + q], h1, dw2[q]);
     }
     __syncthreads();
+  }
   }
   // ---- this CTA's partial gradient (flat parameter order), then the tail
   float *part = a.partials + (size_t)blockIdx.x * partial_stride(net.n_params);
