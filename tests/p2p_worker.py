@@ -12,10 +12,17 @@ sys.path.insert(0, ROOT)
 import dependence_free_rl_b200 as D  # noqa: E402
 
 
+CONV = os.environ.get("P2P_NETS", "dense") == "conv"   # the reference's conv1d policy on the table path (conv_table.cuh)
+
+
 def run(ctx, rank, world, n, iters):
     T = 4
-    policy = D.Model(ctx, D.fc_layers([32, 64, 64, 8], D.SOFTMAX), 32)
-    value = D.Model(ctx, D.fc_layers([32, 64, 64, 1]), 32)
+    if CONV:
+        policy = D.Model(ctx, D.conv_layers([4, 128, 64, 1], D.SOFTMAX), 32)
+        value = D.Model(ctx, D.fc_layers([32, 64, 32, 1]), 32)
+    else:
+        policy = D.Model(ctx, D.fc_layers([32, 64, 64, 8], D.SOFTMAX), 32)
+        value = D.Model(ctx, D.fc_layers([32, 64, 64, 1]), 32)
     policy.init_parameters(1234)
     value.init_parameters(1235)
     env = D.Environment(ctx, n, seed=1234, env_offset=rank * n)
@@ -34,7 +41,7 @@ def main():
     obj = [D.Context.nccl_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(obj, src=0)
     ctx = D.Context(int(os.environ.get("LOCAL_RANK", rank)), world, rank, obj[0])
-    n, iters = 4096, 6
+    n, iters = (16384, 4) if CONV else (4096, 6)
     p_nccl, v_nccl, _ = run(ctx, rank, world, n, iters)       # NCCL all-reduce + optimizer kernel
     handles = [None] * world
     dist.all_gather_object(handles, ctx.p2p_export())
@@ -57,7 +64,7 @@ def main():
 
 
 def D_init(ctx):
-    m = D.Model(ctx, D.fc_layers([32, 64, 64, 8], D.SOFTMAX), 32)
+    m = D.Model(ctx, D.conv_layers([4, 128, 64, 1], D.SOFTMAX) if CONV else D.fc_layers([32, 64, 64, 8], D.SOFTMAX), 32)
     m.init_parameters(1234)
     p = m.parameters().copy()
     m.close()

@@ -180,17 +180,20 @@ def test_trainer_mains_run(binary, args):
 
 
 @pytest.mark.gpu
-def test_p2p_gradient_exchange_two_ranks():
+@pytest.mark.parametrize("nets", ["dense", "conv"])
+def test_p2p_gradient_exchange_two_ranks(nets):
     """Fused peer-memory exchange (dfrl_p2p_*) on 2 GPUs: bit-identical parameters on both ranks and
-    the NCCL path's result. Needs 2 visible GPUs (`gpurun --gpus 2`); skipped on a 1-GPU box."""
+    the NCCL path's result -- for the dense nets (tcgen05 learner kernels) and for the reference's conv1d policy
+    on the table path (conv_table.cuh: the same gradient tail). Needs 2 visible GPUs (`gpurun --gpus 2`); skipped
+    on a 1-GPU box."""
     import json
     import sys
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
-           "127.0.0.1", "--master-port", "29571", os.path.join(ROOT, "tests", "p2p_worker.py")]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+           "127.0.0.1", "--master-port", "29571" if nets == "dense" else "29572", os.path.join(ROOT, "tests", "p2p_worker.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, P2P_NETS=nets))
     assert out.returncode == 0, out.stderr[-3000:]
     line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
     d = json.loads(line)
