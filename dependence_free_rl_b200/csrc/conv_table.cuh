@@ -253,21 +253,23 @@ __global__ void __launch_bounds__(256) conv_table_head_kernel(conv_table_args ta
         for (int q = 0; q < NB; ++q)
           dot = fmaf(p[q], g[q], dot);
       }
+      // bins of the sample that share an entry (all the untouched bins of a young episode) are merged first, in
+      // fp32 and in bin order (a fixed order inside the thread: still reproducible), then converted to fixed point
+      float dY[NB];
 #pragma unroll
-      for (int q = 0; q < NB; ++q) {
-        const float dY = a.head_bwd == HEAD_JACOBIAN ? p[q] * (g[q] - dot) : g[q];
-        fx[q] = __float2ll_rn(dY * S);
-      }
-      // bins of the sample that share an entry (all the untouched bins of a young episode) are merged first
+      for (int q = 0; q < NB; ++q)
+        dY[q] = a.head_bwd == HEAD_JACOBIAN ? p[q] * (g[q] - dot) : g[q];
 #pragma unroll
       for (int q = 1; q < NB; ++q)
 #pragma unroll
         for (int r = 0; r < q; ++r)
           if (d[q] >= 0 && d[q] == d[r]) {
-            fx[r] += fx[q];
-            fx[q] = 0;
+            dY[r] += dY[q];
             d[q] = -1;
           }
+#pragma unroll
+      for (int q = 0; q < NB; ++q)
+        fx[q] = d[q] >= 0 ? __float2ll_rn(dY[q] * S) : 0;
     }
 #pragma unroll
     for (int q = 0; q < NB; ++q)

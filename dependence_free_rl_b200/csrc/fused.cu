@@ -2484,6 +2484,7 @@ struct fused_state {
   int tbl_Dw, tbl_Dh;
   float *tbl_logits;
   unsigned long long *tbl_hist;  // [D] + one word: the bit pattern of max |A| in its low half
+  bool tbl_scale_valid;          // max |A| of the current advantages is known (reset by every rollout / GAE pass)
   int head_bwd;
   float *partials;  // [ctas][max params]
   unsigned *gridbar;  // [2] grid barrier of the gradient tail (arrivals, generation)
@@ -2700,12 +2701,15 @@ int launch_conv_table_forward(dfrl_ctx *ctx, const float *params, const net3 &ne
   return DFRL_OK;
 }
 template <int D1, int D2>
-int launch_conv_table_step(dfrl_ctx *ctx, const conv_table_args &ta, int ctas) {
+int launch_conv_table_step(dfrl_ctx *ctx, const conv_table_args &ta, int ctas, bool scan_adv) {
   const conv_step_args &a = ta.s;
   const int D = ta.Dw * ta.Dh * ta.Dw * ta.Dh;
   const long long rows = (long long)a.T * a.n;
-  DFRL_CUDA(cudaMemsetAsync(ta.hist, 0, sizeof(unsigned long long) * (D + 1), ctx->stream));
-  DFRL_LAUNCH(ctx, conv_table_absmax_kernel, ctx->sm_count, 256, 0, a.adv, rows, const_cast<unsigned *>(ta.maxbits));
+  // the histogram is cleared for every step; max |A| (the fixed-point scale) only when the advantages are new: the
+  // k steps of a PPO iteration share them
+  DFRL_CUDA(cudaMemsetAsync(ta.hist, 0, sizeof(unsigned long long) * (D + (scan_adv ? 1 : 0)), ctx->stream));
+  if (scan_adv)
+    DFRL_LAUNCH(ctx, conv_table_absmax_kernel, ctx->sm_count, 256, 0, a.adv, rows, const_cast<unsigned *>(ta.maxbits));
   DFRL_TRY((launch_conv_table_forward<D1, D2>(ctx, a.params, a.net, a.inv_w, a.inv_h, ta.Dw, ta.Dh, const_cast<float *>(ta.logits),
                                               nullptr)));
   const int smem = 12 * D;
@@ -2992,10 +2996,12 @@ int dfrl_fused_policy_gradient(dfrl_trainer *t, int loss_kind, float *grad_dev, 
       ta.hist = f->tbl_hist;
       ta.Dw = f->tbl_Dw, ta.Dh = f->tbl_Dh;
       ta.maxbits = reinterpret_cast<const unsigned *>(f->tbl_hist + (size_t)ta.Dw * ta.Dh * ta.Dw * ta.Dh);
+      const bool scan = !f->tbl_scale_valid;
       if (f->pnet.d1 == 128)
-        DFRL_TRY((launch_conv_table_step<128, 64>(t->ctx, ta, ctas)));
+        DFRL_TRY((launch_conv_table_step<128, 64>(t->ctx, ta, ctas, scan)));
       else
-        DFRL_TRY((launch_conv_table_step<64, 32>(t->ctx, ta, ctas)));
+        DFRL_TRY((launch_conv_table_step<64, 32>(t->ctx, ta, ctas, scan)));
+      f->tbl_scale_valid = true;
     } else if (f->pnet.d1 == 128)
       DFRL_TRY((launch_conv_policy_step<128, 64>(t->ctx, c, ctas)));
     else
@@ -3056,6 +3062,8 @@ static int fused_vend(dfrl_trainer *t, fused_state *f) {
 // update_value_model (policy_gradient.h:196-218) up to the gradient: writes t->targets and grad_dev.
 int dfrl_fused_critic_gradient(dfrl_trainer *t, float *grad_dev, const dfrl_opt_spec *opt) {
   fused_state *f = (fused_state *)t->fused_impl;
+  if (f)
+    f->tbl_scale_valid = false;  // every VALUE phase ends in new advantages (also on the layered critic path)
   if (!f || !f->value_ok)
     return DFRL_ERR_UNSUPPORTED;
   critic_args a = make_critic_args(t, f);
@@ -3076,6 +3084,8 @@ int dfrl_fused_critic_gradient(dfrl_trainer *t, float *grad_dev, const dfrl_opt_
 // calculate_advantage (policy_gradient.h:220-281) with the current (updated) critic: writes t->adv.
 int dfrl_fused_gae(dfrl_trainer *t) {
   fused_state *f = (fused_state *)t->fused_impl;
+  if (f)
+    f->tbl_scale_valid = false;  // new advantages
   if (!f || !f->value_ok)
     return DFRL_ERR_UNSUPPORTED;
   critic_args a = make_critic_args(t, f);
@@ -3099,6 +3109,8 @@ int dfrl_fused_gae(dfrl_trainer *t) {
 int dfrl_fused_rollout(dfrl_trainer *t, const uint8_t *items_dev, const uint8_t *actions_dev,
                        const double *u_dev) {
   fused_state *f = (fused_state *)t->fused_impl;
+  if (f)
+    f->tbl_scale_valid = false;  // (the layered GAE path does not pass through dfrl_fused_gae)
   if (!f || !f->rollout_ok)
     return DFRL_ERR_UNSUPPORTED;
   dfrl_env *e = t->env;
