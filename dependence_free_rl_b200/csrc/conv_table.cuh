@@ -24,25 +24,25 @@ __host__ __device__ __forceinline__ int tbl_index(int bw, int bh, int iw, int ih
 }
 __device__ __forceinline__ int tbl_clamp(int v, int hi) { return v < 0 ? 0 : (v > hi ? hi : v); }
 
-// ---- L[d] = exp(logit) for every domain entry: one warp per group of E entries. Lane l holds H1[l], H1[l + 32],
-//      ... of the E entries; a row of W2 is read once (coalesced: consecutive lanes, consecutive columns) for all
-//      of them, JB rows in flight.
+// ---- L[d] = exp(logit) for every domain entry: one warp per pair of entries. W2 sits TRANSPOSED in shared memory
+//      (row i = the weights of hidden-1 unit i, padded: conflict-free both ways), a lane owns D2 / 32 hidden-2 units of
+//      both entries and walks the D1 inputs (H1 of the pair broadcast from shared memory): 8 instructions per input
+//      and ONE warp reduction per pair. (A lane per input with a warp reduction per hidden-2 unit took 40
+//      instructions per unit: 24 us per table instead of 7.)
 template <int D1, int D2>
 __global__ void __launch_bounds__(256) conv_table_forward_kernel(const float *__restrict__ params, net3 net, float inv_w,
                                                                  float inv_h, int Dw, int Dh, float *__restrict__ logits,
                                                                  const uint8_t *__restrict__ present) {
-  constexpr int C = D1 / 32;  // hidden-1 units per lane
-  constexpr int E = 4, JB = 4;
+  constexpr int C = D1 / 32, C2 = D2 / 32, E = 2, LD = D2 + 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int D = Dw * Dh * Dw * Dh;
-  // W2, b2, w3 once per CTA into shared memory (one L2 round trip with every load in flight; read from global
-  // memory row by row inside the loop, the kernel was a chain of L2 latencies: 23 us per table)
-  __shared__ __align__(16) float W2[D2 * D1];
+  __shared__ float W2T[D1 * LD];
+  __shared__ float H1s[8][E][D1];
   __shared__ float b2[D2], w3[D2];
   {
-    const float4 *src = reinterpret_cast<const float4 *>(params + net.o_w2);
-    for (int q = threadIdx.x; q < D2 * D1 / 4; q += blockDim.x)
-      reinterpret_cast<float4 *>(W2)[q] = src[q];
+    const float *W2g = params + net.o_w2;  // [D2][D1]: read along i (coalesced), stored transposed
+    for (int q = threadIdx.x; q < D2 * D1; q += blockDim.x)
+      W2T[(q % D1) * LD + q / D1] = W2g[q];
     for (int q = threadIdx.x; q < D2; q += blockDim.x)
       b2[q] = params[net.o_b2 + q], w3[q] = params[net.o_w3 + q];
   }
@@ -57,7 +57,6 @@ __global__ void __launch_bounds__(256) conv_table_forward_kernel(const float *__
       if (!any)
         continue;
     }
-    float h[E][C];
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       const int d = min(d0 + e, D - 1);
@@ -67,41 +66,40 @@ __global__ void __launch_bounds__(256) conv_table_forward_kernel(const float *__
       for (int c = 0; c < C; ++c) {
         const int j = lane + 32 * c;
         const float4 w = *reinterpret_cast<const float4 *>(W1 + 4 * j);
-        h[e][c] = fmaxf(fmaf(x3, w.w, fmaf(x2, w.z, fmaf(x1, w.y, fmaf(x0, w.x, b1[j])))), 0.f);
+        H1s[warp][e][j] = fmaxf(fmaf(x3, w.w, fmaf(x2, w.z, fmaf(x1, w.y, fmaf(x0, w.x, b1[j])))), 0.f);
+      }
+    }
+    __syncwarp();
+    float acc[E][C2];
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+#pragma unroll
+      for (int c = 0; c < C2; ++c)
+        acc[e][c] = b2[lane + 32 * c];
+#pragma unroll 8
+    for (int i = 0; i < D1; ++i) {
+      float w[C2];
+#pragma unroll
+      for (int c = 0; c < C2; ++c)
+        w[c] = W2T[i * LD + lane + 32 * c];
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const float h = H1s[warp][e][i];
+#pragma unroll
+        for (int c = 0; c < C2; ++c)
+          acc[e][c] = fmaf(h, w[c], acc[e][c]);
       }
     }
     float l[E];
 #pragma unroll
-    for (int e = 0; e < E; ++e)
+    for (int e = 0; e < E; ++e) {
       l[e] = 0.f;
-    for (int j0 = 0; j0 < D2; j0 += JB) {
-      float w[JB][C], bj[JB], wj[JB];
 #pragma unroll
-      for (int q = 0; q < JB; ++q) {
+      for (int c = 0; c < C2; ++c)
+        l[e] = fmaf(fmaxf(acc[e][c], 0.f), w3[lane + 32 * c], l[e]);
 #pragma unroll
-        for (int c = 0; c < C; ++c)
-          w[q][c] = W2[(size_t)(j0 + q) * D1 + lane + 32 * c];
-        bj[q] = b2[j0 + q], wj[q] = w3[j0 + q];
-      }
-#pragma unroll
-      for (int q = 0; q < JB; ++q) {
-        float acc[E];
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-          acc[e] = 0.f;
-#pragma unroll
-          for (int c = 0; c < C; ++c)
-            acc[e] = fmaf(h[e][c], w[q][c], acc[e]);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-          for (int e = 0; e < E; ++e)
-            acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], o);
-#pragma unroll
-        for (int e = 0; e < E; ++e)
-          l[e] = fmaf(fmaxf(acc[e] + bj[q], 0.f), wj[q], l[e]);
-      }
+      for (int o = 16; o > 0; o >>= 1)
+        l[e] += __shfl_xor_sync(0xffffffffu, l[e], o);
     }
     if (lane == 0) {  // the table holds exp(logit): what the softmax of every row needs (no max subtraction, nn.h:382-392)
 #pragma unroll
@@ -109,6 +107,7 @@ __global__ void __launch_bounds__(256) conv_table_forward_kernel(const float *__
         if (d0 + e < D && (!present || present[d0 + e]))
           logits[d0 + e] = expf(l[e] + b3);
     }
+    __syncwarp();
   }
 }
 

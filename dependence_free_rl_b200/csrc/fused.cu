@@ -2696,7 +2696,7 @@ int launch_conv_rollout(dfrl_ctx *ctx, const rollout_args &a, int ctas) {
 template <int D1, int D2>
 int launch_conv_table_forward(dfrl_ctx *ctx, const float *params, const net3 &net, float inv_w, float inv_h, int Dw, int Dh,
                               float *logits, const uint8_t *present) {
-  const int D = Dw * Dh * Dw * Dh, grid = ceil_div(D, 32) < 4 * ctx->sm_count ? (int)ceil_div(D, 32) : 4 * ctx->sm_count;  // 8 warps x 4 entries
+  const int D = Dw * Dh * Dw * Dh, grid = ceil_div(D, 16) < 4 * ctx->sm_count ? (int)ceil_div(D, 16) : 4 * ctx->sm_count;  // 8 warps x 2 entries
   DFRL_LAUNCH(ctx, (conv_table_forward_kernel<D1, D2>), grid, 256, 0, params, net, inv_w, inv_h, Dw, Dh, logits, present);
   return DFRL_OK;
 }
