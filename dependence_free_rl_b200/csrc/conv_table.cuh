@@ -327,12 +327,24 @@ __global__ void __launch_bounds__(256, 1) conv_table_backward_kernel(conv_table_
     if (tid < D1)
       H1[tid] = fmaxf(fmaf(X[3], W1[4 * tid + 3], fmaf(X[2], W1[4 * tid + 2], fmaf(X[1], W1[4 * tid + 1], fmaf(X[0], W1[4 * tid], b1[tid])))), 0.f);
     __syncthreads();
+    {  // hidden 2: the dot products in 256 / D2 parts per unit (a thread per unit walked a row of W2 alone:
+       // D1 dependent, uncoalesced loads on the kernel's critical path)
+      constexpr int PARTS = 256 / D2, LEN = D1 / PARTS;
+      const int j = tid % D2, part = tid / D2;
+      const float *wr = W2 + (size_t)j * D1 + part * LEN;
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < LEN; ++i)
+        acc = fmaf(H1[part * LEN + i], wr[i], acc);
+      scratch[part * D2 + j] = acc;
+    }
+    __syncthreads();
     if (tid < D2) {
+      constexpr int PARTS = 256 / D2;
       float acc = b2[tid];
-      const float *wr = W2 + (size_t)tid * D1;
-#pragma unroll 8
-      for (int i = 0; i < D1; ++i)
-        acc = fmaf(H1[i], wr[i], acc);
+#pragma unroll
+      for (int q = 0; q < PARTS; ++q)
+        acc += scratch[q * D2 + tid];
       const float h2 = fmaxf(acc, 0.f);
       H2[tid] = h2;
       const float g2 = h2 > 0.f ? g * w3[tid] : 0.f;  // dH2 = dY w3 . relu'
