@@ -2480,7 +2480,8 @@ struct fused_state {
   bool policy_ok, value_ok, rollout_ok;
   bool policy_conv;  // the policy is a conv1d_1 net 4-D1-D2-1 over the 8 bins (fused_conv.cuh)
   // conv1d_1 policy on its finite input domain (conv_table.cuh): logit table, fixed-point histogram of dY, max |A|
-  bool policy_table;
+  bool policy_table;   // the optimizer steps run on the table (large batches)
+  bool rollout_table;  // the rollout runs on the table (same range)
   int tbl_Dw, tbl_Dh;
   float *tbl_logits;
   unsigned long long *tbl_hist;  // [D] + one word: the bit pattern of max |A| in its low half
@@ -2859,11 +2860,14 @@ int dfrl_fused_try_attach(dfrl_trainer *t) {
     //  forward, histogram flush, a backward pass of few CTAs -- exceeds the tensor-core kernels' whole step;
     //  DFRL_CONV_TABLE=1 / 0 forces / forbids it)
     const bool big = (long long)t->n * t->L >= 32768;
-    if ((e ? atoi(e) != 0 : big) && D <= 16384) {
+    if ((!e || atoi(e) != 0) && D <= 16384) {
       f->tbl_Dw = (int)Dw, f->tbl_Dh = (int)Dh;
       if (cudaMalloc(&f->tbl_logits, sizeof(float) * D) == cudaSuccess &&
-          cudaMalloc(&f->tbl_hist, sizeof(unsigned long long) * (D + 1) + (size_t)D) == cudaSuccess)
-        f->policy_table = true;
+          cudaMalloc(&f->tbl_hist, sizeof(unsigned long long) * (D + 1) + (size_t)D) == cudaSuccess) {
+        // (the table rollout alone was measured slower than the tensor-core rollout at 1 024 / 4 096 envs:
+        //  two launches and 6 561 table entries against one launch)
+        f->policy_table = f->rollout_table = e ? true : big;
+      }
     }
   }
   if (f->policy_conv)
@@ -3137,7 +3141,7 @@ int dfrl_fused_rollout(dfrl_trainer *t, const uint8_t *items_dev, const uint8_t 
   if (f->policy_conv)
     a.n_tiles = ceil_div(t->n, TILE / 8);
   int ctas = a.n_tiles < f->ctas ? a.n_tiles : f->ctas;
-  if (f->policy_conv && f->policy_table) {
+  if (f->policy_conv && f->rollout_table) {
     if (f->pnet.d1 == 128)
       DFRL_TRY((launch_conv_table_forward<128, 64>(t->ctx, a.params, a.net, a.inv_w, a.inv_h, f->tbl_Dw, f->tbl_Dh, f->tbl_logits, nullptr)));
     else
