@@ -278,6 +278,8 @@ struct critic_args {
                        // kernel runs its own end pass over all rows of every tile
   float *v_end_out;    // GAE kernel, non-null (== v_end): every pipeline first evaluates the end rows of ITS
                        // OWN tiles, compacted into passes of 128 rows, and writes them here -- no pre-pass launch
+  unsigned *adv_maxbits;  // GAE kernel, optional: atomicMax of the bits of max |advantage| (the fixed-point scale of
+                          // the table path, conv_table.cuh; zeroed by the caller)
   float *partials;
   grad_tail tail;      // critic step only
   long long *clk;      // optional: phase clocks of CTA 0, pipeline 0 (debug; critic step only)
@@ -1737,6 +1739,9 @@ __global__ void __launch_bounds__((cmap<D1, D2, MODE>::THREADS), 1) fused_critic
             const float adv = delta + (ends ? 0.f : a.lambda * a.gamma * a_next);
             a.adv_out[kq] = adv;
             a_next = adv;
+            const float aa = fabsf(adv);
+            if (aa < 3.0e38f)           // (false for NaN too: same filter as conv_table_absmax_kernel)
+              db3 = fmaxf(db3, aa);     // db3 is free in this mode: running max |A| of this thread
           }
         }
         asm volatile("bar.sync %0, %1;\n" ::"r"(9 + wg), "r"(XT) : "memory");  // ve / vs may be overwritten
@@ -1860,6 +1865,11 @@ __global__ void __launch_bounds__((cmap<D1, D2, MODE>::THREADS), 1) fused_critic
 
   if (gclk)
     gclk[1] = global_ns();
+  if (MODE == CRITIC_GAE && a.adv_maxbits && !issuer) {  // one atomic per epilogue warp
+    const unsigned m = __reduce_max_sync(0xffffffffu, __float_as_uint(db3));
+    if ((threadIdx.x & 31) == 0 && m)
+      atomicMax(a.adv_maxbits, m);
+  }
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
@@ -2774,6 +2784,7 @@ critic_args make_critic_args(dfrl_trainer *t, fused_state *f) {
   memset(&a.tail, 0, sizeof(a.tail));
   a.v_end = nullptr;
   a.v_end_out = nullptr;
+  a.adv_maxbits = nullptr;
   a.clk = f->clk_critic;
   return a;
 }
@@ -3102,10 +3113,17 @@ int dfrl_fused_gae(dfrl_trainer *t) {
     else
       DFRL_TRY(fused_vend(t, f));
   }
+  if (f->policy_table) {  // the table path's fixed-point scale (max |A|) comes out of this kernel: no scan pass
+    unsigned long long *mb = f->tbl_hist + (size_t)f->tbl_Dw * f->tbl_Dh * f->tbl_Dw * f->tbl_Dh;
+    DFRL_CUDA(cudaMemsetAsync(mb, 0, sizeof(*mb), t->ctx->stream));
+    a.adv_maxbits = reinterpret_cast<unsigned *>(mb);
+  }
   int ctas = a.n_tiles < f->ctas ? a.n_tiles : f->ctas;
 #define CALL(A, B, C) DFRL_TRY((launch_gae<A, B, C>(t->ctx, a, ctas)))
   DFRL_VNET_DISPATCH(f->vnet, CALL);
 #undef CALL
+  if (a.adv_maxbits)
+    f->tbl_scale_valid = true;
   return DFRL_OK;
 }
 
