@@ -2495,6 +2495,9 @@ struct fused_state {
   int tbl_Dw, tbl_Dh;
   float *tbl_logits;
   unsigned long long *tbl_hist;  // [D] + one word: the bit pattern of max |A| in its low half
+  bool tbl_reuse;                // a policy step may use a table that an earlier launch computed from the same parameters
+  bool tbl_have;                 // tbl_logits holds the table of the policy parameters at version tbl_version
+  uint64_t tbl_version;
   bool tbl_scale_valid;          // max |A| of the current advantages is known (reset by every rollout / GAE pass)
   int head_bwd;
   float *partials;  // [ctas][max params]
@@ -2712,7 +2715,7 @@ int launch_conv_table_forward(dfrl_ctx *ctx, const float *params, const net3 &ne
   return DFRL_OK;
 }
 template <int D1, int D2>
-int launch_conv_table_step(dfrl_ctx *ctx, const conv_table_args &ta, int ctas, bool scan_adv) {
+int launch_conv_table_step(dfrl_ctx *ctx, const conv_table_args &ta, int ctas, bool scan_adv, bool forward) {
   const conv_step_args &a = ta.s;
   const int D = ta.Dw * ta.Dh * ta.Dw * ta.Dh;
   const long long rows = (long long)a.T * a.n;
@@ -2721,8 +2724,9 @@ int launch_conv_table_step(dfrl_ctx *ctx, const conv_table_args &ta, int ctas, b
   DFRL_CUDA(cudaMemsetAsync(ta.hist, 0, sizeof(unsigned long long) * (D + (scan_adv ? 1 : 0)), ctx->stream));
   if (scan_adv)
     DFRL_LAUNCH(ctx, conv_table_absmax_kernel, ctx->sm_count, 256, 0, a.adv, rows, const_cast<unsigned *>(ta.maxbits));
-  DFRL_TRY((launch_conv_table_forward<D1, D2>(ctx, a.params, a.net, a.inv_w, a.inv_h, ta.Dw, ta.Dh, const_cast<float *>(ta.logits),
-                                              nullptr)));
+  if (forward)  // (not after a rollout on the same parameters: PPO's first step sees the rollout's table)
+    DFRL_TRY((launch_conv_table_forward<D1, D2>(ctx, a.params, a.net, a.inv_w, a.inv_h, ta.Dw, ta.Dh, const_cast<float *>(ta.logits),
+                                                nullptr)));
   const int smem = 12 * D;
   static unsigned long long attr = 0;
   DFRL_TRY(set_smem_once(ctx, conv_table_head_kernel, smem, &attr));
@@ -2878,6 +2882,8 @@ int dfrl_fused_try_attach(dfrl_trainer *t) {
         // (the table rollout alone was measured slower than the tensor-core rollout at 1 024 / 4 096 envs:
         //  two launches and 6 561 table entries against one launch)
         f->policy_table = f->rollout_table = e ? true : big;
+        const char *r = getenv("DFRL_TABLE_REUSE");  // 0: every policy step computes its own table (tests)
+        f->tbl_reuse = !r || atoi(r) != 0;
       }
     }
   }
@@ -3012,11 +3018,13 @@ int dfrl_fused_policy_gradient(dfrl_trainer *t, int loss_kind, float *grad_dev, 
       ta.Dw = f->tbl_Dw, ta.Dh = f->tbl_Dh;
       ta.maxbits = reinterpret_cast<const unsigned *>(f->tbl_hist + (size_t)ta.Dw * ta.Dh * ta.Dw * ta.Dh);
       const bool scan = !f->tbl_scale_valid;
+      const bool fwd = !(f->tbl_reuse && f->tbl_have && f->tbl_version == t->policy->version);
       if (f->pnet.d1 == 128)
-        DFRL_TRY((launch_conv_table_step<128, 64>(t->ctx, ta, ctas, scan)));
+        DFRL_TRY((launch_conv_table_step<128, 64>(t->ctx, ta, ctas, scan, fwd)));
       else
-        DFRL_TRY((launch_conv_table_step<64, 32>(t->ctx, ta, ctas, scan)));
+        DFRL_TRY((launch_conv_table_step<64, 32>(t->ctx, ta, ctas, scan, fwd)));
       f->tbl_scale_valid = true;
+      f->tbl_have = true, f->tbl_version = t->policy->version;
     } else if (f->pnet.d1 == 128)
       DFRL_TRY((launch_conv_policy_step<128, 64>(t->ctx, c, ctas)));
     else
@@ -3096,6 +3104,11 @@ int dfrl_fused_critic_gradient(dfrl_trainer *t, float *grad_dev, const dfrl_opt_
   return DFRL_OK;
 }
 
+int dfrl_fused_learn_key(const dfrl_trainer *t) {
+  const fused_state *f = (const fused_state *)t->fused_impl;
+  return f && f->policy_table && f->tbl_reuse && f->tbl_have && f->tbl_version == t->policy->version ? 1 : 0;
+}
+
 // calculate_advantage (policy_gradient.h:220-281) with the current (updated) critic: writes t->adv.
 int dfrl_fused_gae(dfrl_trainer *t) {
   fused_state *f = (fused_state *)t->fused_impl;
@@ -3164,6 +3177,7 @@ int dfrl_fused_rollout(dfrl_trainer *t, const uint8_t *items_dev, const uint8_t 
       DFRL_TRY((launch_conv_table_forward<128, 64>(t->ctx, a.params, a.net, a.inv_w, a.inv_h, f->tbl_Dw, f->tbl_Dh, f->tbl_logits, nullptr)));
     else
       DFRL_TRY((launch_conv_table_forward<64, 32>(t->ctx, a.params, a.net, a.inv_w, a.inv_h, f->tbl_Dw, f->tbl_Dh, f->tbl_logits, nullptr)));
+    f->tbl_have = true, f->tbl_version = t->policy->version;
     DFRL_TRY(launch_conv_table_rollout(t->ctx, a, f->tbl_logits, f->tbl_Dw, f->tbl_Dh));
   } else if (f->policy_conv && f->pnet.d1 == 128)
     DFRL_TRY((launch_conv_rollout<128, 64>(t->ctx, a, ctas)));

@@ -372,6 +372,7 @@ static int trainer_setup(dfrl_trainer *t, dfrl_ctx *ctx, const dfrl_trainer_conf
   t->graph_launches = 0;
   t->plain_iterations = 0;
   t->graph_failed = 0;
+  t->graph_key = 0;
   return DFRL_OK;
 }
 
@@ -713,6 +714,13 @@ static int learn_graphed(dfrl_trainer *t) {
     ++t->plain_iterations;
     return learn_layered(t);
   }
+  const int key = t->fused_impl ? dfrl_fused_learn_key(t) : 0;
+  if (t->graph_exec && key != t->graph_key) {  // captured under other host-side decisions: capture again
+    DFRL_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaGraphExecDestroy((cudaGraphExec_t)t->graph_exec);
+    t->graph_exec = nullptr;
+    t->graph_launches = 0;
+  }
   if (!t->graph_exec) {
     cudaGraph_t graph = nullptr;
     const long long before = ctx->launches;
@@ -745,6 +753,7 @@ static int learn_graphed(dfrl_trainer *t) {
       return DFRL_ERR_CUDA;
     }
     t->graph_exec = exec;
+    t->graph_key = key;
   }
   DFRL_CUDA(cudaGraphLaunch((cudaGraphExec_t)t->graph_exec, ctx->stream));
   ctx->launches += t->graph_launches;

@@ -50,6 +50,7 @@ struct dfrl_trainer {
   void *graph_exec;        // cudaGraphExec_t
   long long graph_launches;  // kernels per captured iteration
   int plain_iterations;    // iterations run launch by launch so far
+  int graph_key;           // dfrl_fused_learn_key() at capture time: host decisions frozen into the graph
   int graph_failed;        // a capture attempt failed (KL-PPO's layered policy steps): no further attempts
 };
 
@@ -75,6 +76,10 @@ int dfrl_fused_rollout(dfrl_trainer *t, const uint8_t *items_dev, const uint8_t 
 bool dfrl_fused_covers_critic(const dfrl_trainer *t);  // rollout, critic step and GAE run on the fused kernels
 int dfrl_fused_critic_gradient(dfrl_trainer *t, float *grad_dev, const dfrl_opt_spec *opt);
 int dfrl_fused_gae(dfrl_trainer *t);
+// The host-side decisions of the learn phase that depend on state from BEFORE the phase (bit 0: the logit table of
+// the conv1d policy's table path is current, i.e. the rollout computed it with the parameters the first policy step
+// sees, and that step skips its table pass). A captured learn phase is replayed only under the key it was captured with.
+int dfrl_fused_learn_key(const dfrl_trainer *t);
 // One policy gradient over all recorded rows (forward + loss gradient + backward), SUM over rows.
 // Returns DFRL_ERR_UNSUPPORTED when the fused policy kernel does not cover this trainer.
 // opt != null: the optimizer update runs inside the reduction kernel (caller bumps adam_t).

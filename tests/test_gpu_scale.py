@@ -358,6 +358,40 @@ def test_conv_table_path_is_deterministic_and_agrees_with_the_tensor_core_path(D
             close(a[0]["g"][e].astype(np.float64), c[0]["g"][e].astype(np.float64), rtol=1e-4, what=f"policy gradient {e}: table vs tensor cores")
 
 
+def test_conv_table_reuse_follows_the_parameters(D, ctx, monkeypatch):
+    """PPO's first policy step sees the parameters of the rollout, so it takes the rollout's logit table instead of
+    computing its own (fused.cu: tbl_version == the policy's parameter version). The reuse must stop the moment the
+    parameters are not the rollout's: parameters replaced between rollout and learn, a second learn() without a
+    rollout -- also across the CUDA-graph replay of the learn phase, which is captured under the key
+    dfrl_fused_learn_key() and captured again when the key changes. Bit-identical to a trainer whose every step
+    computes its table (DFRL_TABLE_REUSE=0) through the same schedule."""
+    n, T = 16384, 4
+    def run(reuse):
+        monkeypatch.setenv("DFRL_CONV_TABLE", "1")
+        monkeypatch.setenv("DFRL_TABLE_REUSE", str(reuse))
+        policy = D.Model(ctx, D.conv_layers([4, 128, 64, 1], D.SOFTMAX), 32)
+        value = D.Model(ctx, D.fc_layers([32, 64, 32, 1]), 32)
+        policy.init_parameters(31)
+        value.init_parameters(32)
+        env = D.Environment(ctx, n, seed=7)
+        tr = D.Trainer(ctx, env, policy, value, algo=D.PPO, work=T, policy_lr=1e-4 * 32 / (n * T), value_lr=1e-5 * 32 / (n * T))
+        out = []
+        for it in range(9):
+            if it != 6:                       # iteration 6: learn() again on the same records, new parameters
+                tr.rollout()
+            if it == 4:                       # parameters replaced between rollout and learn
+                policy.set_parameters((policy.parameters() * np.float32(1.02)).astype(np.float32))
+            tr.learn()
+            out.append(dict(g=tr.read(D.F_POLICY_GRAD_LOG).copy(), p=policy.parameters().copy()))
+        tr.close(); env.close(); policy.close(); value.close()
+        return out
+    a, b = run(1), run(0)
+    for it in range(9):
+        for key in ("g", "p"):
+            assert np.array_equal(a[it][key], b[it][key]), (it, key)
+    assert np.any(a[4]["g"][0] != a[3]["g"][0])
+
+
 def test_set_rates_on_a_graph_replaying_learner(D, ctx):
     """optimizer::set_rate (nn.h:592) after the learn phase has been captured as a CUDA graph: the new
     rates take effect at the next learn() (rates are kernel arguments: the graph is re-captured), the
